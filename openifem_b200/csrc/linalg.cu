@@ -1,0 +1,396 @@
+#include "linalg.h"
+
+#include <algorithm>
+
+#include "comm.h"
+
+namespace ifem
+{
+  // ---------------------------------------------------------------------------
+  // Context
+  // ---------------------------------------------------------------------------
+  static constexpr int kMaxPartials = 4096;
+
+  Context::Context()
+  {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      throw std::runtime_error("openifem_b200: no CUDA device available - this library has no CPU fallback");
+    IFEM_CUDA(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    IFEM_CUDA(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    IFEM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    partials.alloc(kMaxPartials);
+    results.alloc(64);
+    IFEM_CUDA(cudaMallocHost(&h_results, 64 * sizeof(double)));
+  }
+
+  Context::~Context()
+  {
+    if (h_results) cudaFreeHost(h_results);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  Context &default_context()
+  {
+    static Context ctx;
+    return ctx;
+  }
+
+  // ---------------------------------------------------------------------------
+  // Bcsr
+  // ---------------------------------------------------------------------------
+  void Bcsr::init(const Pattern &P, int R_, int C_, cudaStream_t s)
+  {
+    R = R_;
+    C = C_;
+    n_brows = P.n_rows;
+    n_bcols = P.n_cols;
+    n_blocks = (int64_t)P.col.size();
+    rowptr.alloc(P.rowptr.size());
+    rowptr.upload(P.rowptr.data(), P.rowptr.size(), s);
+    col.alloc(P.col.size());
+    col.upload(P.col.data(), P.col.size(), s);
+    val.alloc((size_t)n_blocks * R * C);
+    val.zero(s);
+    IFEM_CUDA(cudaStreamSynchronize(s));
+    const double avg = n_brows ? double(n_blocks) / n_brows : 0.0;
+    tpr = avg >= 40 ? 32 : avg >= 20 ? 16 : avg >= 10 ? 8 : 4;
+  }
+
+  void Bcsr::to_host_csr(cudaStream_t s, std::vector<int64_t> &rp, std::vector<int> &ci, std::vector<double> &v) const
+  {
+    const std::vector<int64_t> brp = rowptr.to_host(s);
+    const std::vector<int> bci = col.to_host(s);
+    const std::vector<double> bv = val.to_host(s);
+    rp.assign((size_t)n_brows * R + 1, 0);
+    ci.resize((size_t)n_blocks * R * C);
+    v.resize((size_t)n_blocks * R * C);
+    int64_t pos = 0;
+    for (int i = 0; i < n_brows; ++i)
+      {
+        const int64_t base = brp[i], nb = brp[i + 1] - base;
+        for (int r = 0; r < R; ++r)
+          {
+            rp[(size_t)i * R + r] = pos;
+            for (int64_t j = 0; j < nb; ++j)
+              for (int c = 0; c < C; ++c)
+                {
+                  ci[pos] = bci[base + j] * C + c;
+                  v[pos] = bv[base * R * C + (int64_t)(r * C + c) * nb + j];
+                  ++pos;
+                }
+          }
+      }
+    rp[(size_t)n_brows * R] = pos;
+  }
+
+  // ---------------------------------------------------------------------------
+  // SpMV: TPR lanes cooperate on one block row; every plane of the row is read
+  // with unit stride across the lanes (coalesced, read-once -> streaming loads),
+  // x is gathered through L1/L2, the R partial sums are shuffled down.
+  // ---------------------------------------------------------------------------
+  template <int R, int C, int TPR>
+  __global__ void __launch_bounds__(256)
+  bcsr_spmv_kernel(int n_brows, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
+                   const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, int accumulate)
+  {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = gt / TPR;
+    const int lane = (int)(gt % TPR);
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    if (row < n_brows)
+      {
+        const int64_t base = rowptr[row];
+        const int nb = (int)(rowptr[row + 1] - base);
+        const double *v = val + base * (R * C);
+        const int *ci = col + base;
+#pragma unroll 2
+        for (int j = lane; j < nb; j += TPR)
+          {
+            const int c0 = ld_stream(ci + j);
+            double xv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) xv[c] = __ldg(x + (int64_t)c0 * C + c);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+              for (int c = 0; c < C; ++c) acc[r] = fma(ld_stream(v + (int64_t)(r * C + c) * nb + j), xv[c], acc[r]);
+          }
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    if (row < n_brows && lane == 0)
+      {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          {
+            double *yp = y + row * R + r;
+            *yp = accumulate ? (*yp + acc[r]) : acc[r];
+          }
+      }
+  }
+
+  template <int R, int C>
+  static void spmv_launch(Context &ctx, const Bcsr &A, const double *x, double *y, bool accumulate)
+  {
+    if (A.n_brows == 0) return;
+    const int threads = 256;
+    auto launch = [&](auto tpr_tag) {
+      constexpr int TPR = decltype(tpr_tag)::value;
+      const int64_t total = (int64_t)A.n_brows * TPR;
+      const int64_t blocks = (total + threads - 1) / threads;
+      bcsr_spmv_kernel<R, C, TPR><<<(unsigned)blocks, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, A.val.p, x, y,
+                                                                                accumulate ? 1 : 0);
+    };
+    switch (A.tpr)
+      {
+      case 32: launch(std::integral_constant<int, 32>()); break;
+      case 16: launch(std::integral_constant<int, 16>()); break;
+      case 8: launch(std::integral_constant<int, 8>()); break;
+      default: launch(std::integral_constant<int, 4>()); break;
+      }
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+  }
+
+  void spmv(Context &ctx, const Bcsr &A, const double *x, double *y, bool accumulate)
+  {
+    const int key = A.R * 10 + A.C;
+    switch (key)
+      {
+      case 11: spmv_launch<1, 1>(ctx, A, x, y, accumulate); break;
+      case 22: spmv_launch<2, 2>(ctx, A, x, y, accumulate); break;
+      case 21: spmv_launch<2, 1>(ctx, A, x, y, accumulate); break;
+      case 12: spmv_launch<1, 2>(ctx, A, x, y, accumulate); break;
+      case 33: spmv_launch<3, 3>(ctx, A, x, y, accumulate); break;
+      case 31: spmv_launch<3, 1>(ctx, A, x, y, accumulate); break;
+      case 13: spmv_launch<1, 3>(ctx, A, x, y, accumulate); break;
+      default: throw std::runtime_error("spmv: unsupported block shape");
+      }
+  }
+
+  // ---------------------------------------------------------------------------
+  // BLAS-1
+  // ---------------------------------------------------------------------------
+  namespace
+  {
+    constexpr int kThreads = 256;
+
+    inline int grid_for(const Context &ctx, int64_t n)
+    {
+      const int64_t want = (n + kThreads * 4 - 1) / (kThreads * 4);
+      return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min(kMaxPartials, ctx.sm_count * 8)));
+    }
+
+    __device__ __forceinline__ double block_sum(double v)
+    {
+      __shared__ double sh[kThreads / 32];
+      v = warp_sum(v);
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      __syncthreads();
+      if (l == 0) sh[w] = v;
+      __syncthreads();
+      double r = 0.0;
+      if (w == 0)
+        {
+          r = l < kThreads / 32 ? sh[l] : 0.0;
+          r = warp_sum(r);
+        }
+      return r;
+    }
+
+    __global__ void __launch_bounds__(kThreads) dot_partial_kernel(int64_t n, const double *__restrict__ x,
+                                                                   const double *__restrict__ y, double *__restrict__ partial)
+    {
+      double s = 0.0;
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s = fma(x[i], y[i], s);
+      s = block_sum(s);
+      if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+
+    __global__ void __launch_bounds__(kThreads)
+    add_and_dot_partial_kernel(int64_t n, double *__restrict__ aux, double a, const double *__restrict__ V,
+                               const double *__restrict__ W, double *__restrict__ partial)
+    {
+      double s = 0.0;
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        {
+          const double t = fma(a, V[i], aux[i]);
+          aux[i] = t;
+          // W may alias aux (norm of the updated vector)
+          const double w = (W == aux) ? t : W[i];
+          s = fma(t, w, s);
+        }
+      s = block_sum(s);
+      if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+
+    __global__ void __launch_bounds__(kThreads) reduce_final_kernel(int n, const double *__restrict__ partial, double *__restrict__ out)
+    {
+      double s = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+      s = block_sum(s);
+      if (threadIdx.x == 0) out[0] = s;
+    }
+
+    double finish_reduction(Context &ctx, int g)
+    {
+      reduce_final_kernel<<<1, kThreads, 0, ctx.stream>>>(g, ctx.partials.p, ctx.results.p);
+      IFEM_KERNEL_CHECK();
+      ctx.kernel_launches++;
+      if (ctx.comm) comm_allreduce_sum(*ctx.comm, ctx.results.p, 1, ctx.stream);
+      IFEM_CUDA(cudaMemcpyAsync(ctx.h_results, ctx.results.p, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+      IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+      return ctx.h_results[0];
+    }
+
+    template <typename F>
+    __global__ void __launch_bounds__(kThreads) map_kernel(int64_t n, F f)
+    {
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+    }
+
+    template <typename F>
+    void map(Context &ctx, int64_t n, F f)
+    {
+      if (n <= 0) return;
+      const int64_t want = (n + kThreads - 1) / kThreads;
+      const int g = (int)std::min<int64_t>(want, (int64_t)ctx.sm_count * 16);
+      map_kernel<<<g, kThreads, 0, ctx.stream>>>(n, f);
+      IFEM_KERNEL_CHECK();
+      ctx.kernel_launches++;
+    }
+  } // namespace
+
+  double dot(Context &ctx, int64_t n, const double *x, const double *y)
+  {
+    const int g = grid_for(ctx, n);
+    dot_partial_kernel<<<g, kThreads, 0, ctx.stream>>>(n, x, y, ctx.partials.p);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+    return finish_reduction(ctx, g);
+  }
+
+  double nrm2(Context &ctx, int64_t n, const double *x) { return std::sqrt(dot(ctx, n, x, x)); }
+
+  double add_and_dot(Context &ctx, int64_t n, double *aux, double a, const double *V, const double *W)
+  {
+    const int g = grid_for(ctx, n);
+    add_and_dot_partial_kernel<<<g, kThreads, 0, ctx.stream>>>(n, aux, a, V, W, ctx.partials.p);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+    return finish_reduction(ctx, g);
+  }
+
+  void axpy(Context &ctx, int64_t n, double a, const double *x, double *y)
+  {
+    map(ctx, n, [=] __device__(int64_t i) { y[i] = fma(a, x[i], y[i]); });
+  }
+  void axpby(Context &ctx, int64_t n, double a, const double *x, double b, double *y)
+  {
+    map(ctx, n, [=] __device__(int64_t i) { y[i] = a * x[i] + b * y[i]; });
+  }
+  void scale(Context &ctx, int64_t n, double a, double *x)
+  {
+    map(ctx, n, [=] __device__(int64_t i) { x[i] *= a; });
+  }
+  void equ(Context &ctx, int64_t n, double a, const double *x, double *y)
+  {
+    map(ctx, n, [=] __device__(int64_t i) { y[i] = a * x[i]; });
+  }
+  void copy(Context &ctx, int64_t n, const double *x, double *y)
+  {
+    if (n > 0) IFEM_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+  }
+  void fill(Context &ctx, int64_t n, double v, double *x)
+  {
+    if (v == 0.0)
+      {
+        if (n > 0) IFEM_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), ctx.stream));
+        return;
+      }
+    map(ctx, n, [=] __device__(int64_t i) { x[i] = v; });
+  }
+  void lin3(Context &ctx, int64_t n, double *z, const double *x, double a, const double *y, double b, const double *w)
+  {
+    map(ctx, n, [=] __device__(int64_t i) { z[i] = x[i] + a * y[i] + b * w[i]; });
+  }
+  void set_indexed(Context &ctx, int n_idx, const int *idx, const double *vals, double *x)
+  {
+    map(ctx, n_idx, [=] __device__(int64_t k) { x[idx[k]] = vals ? vals[k] : 0.0; });
+  }
+  void reciprocal(Context &ctx, int64_t n, const double *x, double *y)
+  {
+    map(ctx, n, [=] __device__(int64_t i) { y[i] = 1.0 / x[i]; });
+  }
+
+  void block_diag_apply(Context &ctx, int n_nodes, int bs, const double *binv, const double *x, double *y)
+  {
+    if (bs == 2)
+      map(ctx, n_nodes, [=] __device__(int64_t i) {
+        const double *b = binv + i * 4;
+        const double x0 = x[2 * i], x1 = x[2 * i + 1];
+        y[2 * i] = b[0] * x0 + b[1] * x1;
+        y[2 * i + 1] = b[2] * x0 + b[3] * x1;
+      });
+    else if (bs == 3)
+      map(ctx, n_nodes, [=] __device__(int64_t i) {
+        const double *b = binv + i * 9;
+        const double x0 = x[3 * i], x1 = x[3 * i + 1], x2 = x[3 * i + 2];
+        y[3 * i] = b[0] * x0 + b[1] * x1 + b[2] * x2;
+        y[3 * i + 1] = b[3] * x0 + b[4] * x1 + b[5] * x2;
+        y[3 * i + 2] = b[6] * x0 + b[7] * x1 + b[8] * x2;
+      });
+    else if (bs == 1)
+      map(ctx, n_nodes, [=] __device__(int64_t i) { y[i] = binv[i] * x[i]; });
+    else
+      throw std::runtime_error("block_diag_apply: unsupported block size");
+  }
+
+  void block_diag_inverse(Context &ctx, const Bcsr &A, double *binv)
+  {
+    if (A.R != A.C) throw std::runtime_error("block_diag_inverse: square blocks required");
+    const int bs = A.R;
+    const int64_t *rowptr = A.rowptr.p;
+    const int *col = A.col.p;
+    const double *val = A.val.p;
+    map(ctx, A.n_brows, [=] __device__(int64_t i) {
+      const int64_t base = rowptr[i];
+      const int nb = (int)(rowptr[i + 1] - base);
+      int lo = 0, hi = nb - 1, j = -1;
+      while (lo <= hi)
+        {
+          const int mid = (lo + hi) >> 1;
+          const int c = col[base + mid];
+          if (c == (int)i) { j = mid; break; }
+          if (c < (int)i) lo = mid + 1; else hi = mid - 1;
+        }
+      double m[9];
+      for (int k = 0; k < bs * bs; ++k) m[k] = j >= 0 ? val[base * bs * bs + (int64_t)k * nb + j] : 0.0;
+      double *o = binv + i * bs * bs;
+      if (bs == 1)
+        o[0] = 1.0 / m[0];
+      else if (bs == 2)
+        {
+          const double d = 1.0 / (m[0] * m[3] - m[1] * m[2]);
+          o[0] = m[3] * d; o[1] = -m[1] * d; o[2] = -m[2] * d; o[3] = m[0] * d;
+        }
+      else
+        {
+          const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+          const double d = 1.0 / (m[0] * c00 + m[1] * c01 + m[2] * c02);
+          o[0] = c00 * d; o[1] = (m[2] * m[7] - m[1] * m[8]) * d; o[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+          o[3] = c01 * d; o[4] = (m[0] * m[8] - m[2] * m[6]) * d; o[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+          o[6] = c02 * d; o[7] = (m[1] * m[6] - m[0] * m[7]) * d; o[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+        }
+    });
+  }
+} // namespace ifem

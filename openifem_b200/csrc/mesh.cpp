@@ -1,0 +1,450 @@
+#include "mesh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <stdexcept>
+
+#include "fe_tables.h"
+
+namespace ifem
+{
+  // ---------------------------------------------------------------------------
+  // GridGenerator
+  // ---------------------------------------------------------------------------
+  void GridGenerator::subdivided_hyper_rectangle(Triangulation &tria, const std::vector<unsigned int> &reps,
+                                                 const double *p1, const double *p2, bool colorize)
+  {
+    const int dim = (int)reps.size();
+    if (dim != 2 && dim != 3) throw std::runtime_error("subdivided_hyper_rectangle: dim must be 2 or 3");
+    tria = Triangulation();
+    tria.dim = dim;
+    int n[3] = {1, 1, 1}, nv[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d)
+      {
+        n[d] = (int)reps[d];
+        nv[d] = n[d] + 1;
+      }
+    const size_t n_vert = (size_t)nv[0] * nv[1] * nv[2];
+    tria.vertices.resize(n_vert * dim);
+    for (int k = 0; k < nv[2]; ++k)
+      for (int j = 0; j < nv[1]; ++j)
+        for (int i = 0; i < nv[0]; ++i)
+          {
+            const size_t v = (size_t)i + (size_t)nv[0] * (j + (size_t)nv[1] * k);
+            const int ijk[3] = {i, j, k};
+            for (int d = 0; d < dim; ++d)
+              tria.vertices[v * dim + d] = p1[d] + ijk[d] * ((p2[d] - p1[d]) / n[d]);
+          }
+    const int vpc = 1 << dim;
+    const size_t nc = (size_t)n[0] * n[1] * n[2];
+    tria.cells.resize(nc * vpc);
+    tria.material_id.assign(nc, 1);
+    for (int k = 0; k < n[2]; ++k)
+      for (int j = 0; j < n[1]; ++j)
+        for (int i = 0; i < n[0]; ++i)
+          {
+            const size_t c = (size_t)i + (size_t)n[0] * (j + (size_t)n[1] * k);
+            for (int v = 0; v < vpc; ++v)
+              {
+                const int oi = v & 1, oj = (v >> 1) & 1, ok = (v >> 2) & 1;
+                tria.cells[c * vpc + v] = (int)((i + oi) + (size_t)nv[0] * ((j + oj) + (size_t)nv[1] * (k + ok)));
+              }
+            const int ijk[3] = {i, j, k};
+            for (int axis = 0; axis < dim; ++axis)
+              for (int side = 0; side < 2; ++side)
+                if (ijk[axis] == (side ? n[axis] - 1 : 0))
+                  {
+                    tria.boundary_faces.push_back((int)c);
+                    tria.boundary_faces.push_back(2 * axis + side);
+                    tria.boundary_faces.push_back(colorize ? 2 * axis + side : 0);
+                  }
+          }
+  }
+
+  void GridGenerator::hyper_cube(Triangulation &tria, int dim, double left, double right, bool colorize)
+  {
+    const double a[3] = {left, left, left}, b[3] = {right, right, right};
+    subdivided_hyper_rectangle(tria, std::vector<unsigned int>(dim, 1u), a, b, colorize);
+  }
+
+  // ---------------------------------------------------------------------------
+  // Node numbering
+  // ---------------------------------------------------------------------------
+  namespace
+  {
+    struct Key
+    {
+      int v[4];
+      bool operator==(const Key &o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2] && v[3] == o.v[3]; }
+    };
+    inline uint64_t hash_key(const Key &k)
+    {
+      uint64_t h = 0x9E3779B97F4A7C15ull;
+      for (int i = 0; i < 4; ++i)
+        {
+          h ^= (uint64_t)(uint32_t)k.v[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+          h *= 0xff51afd7ed558ccdull;
+          h ^= h >> 33;
+        }
+      return h;
+    }
+    struct FlatMap
+    {
+      std::vector<int> slot; // index into keys, -1 empty
+      std::vector<Key> keys;
+      uint64_t mask;
+      explicit FlatMap(size_t expected)
+      {
+        size_t cap = 16;
+        while (cap < 2 * expected) cap <<= 1;
+        slot.assign(cap, -1);
+        mask = cap - 1;
+        keys.reserve(expected);
+      }
+      int find_or_insert(const Key &k)
+      {
+        uint64_t h = hash_key(k) & mask;
+        while (true)
+          {
+            const int s = slot[h];
+            if (s < 0)
+              {
+                slot[h] = (int)keys.size();
+                keys.push_back(k);
+                return (int)keys.size() - 1;
+              }
+            if (keys[s] == k) return s;
+            h = (h + 1) & mask;
+          }
+      }
+    };
+
+    // renumber nodes in lexicographic (z,y,x) order of quantised coordinates
+    void spatial_renumber(NodeTable &nt)
+    {
+      const int dim = nt.dim, n = nt.n_nodes;
+      double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+      for (int d = 0; d < dim; ++d) lo[d] = hi[d] = nt.coords[d];
+      for (int i = 0; i < n; ++i)
+        for (int d = 0; d < dim; ++d)
+          {
+            lo[d] = std::min(lo[d], nt.coords[(size_t)i * dim + d]);
+            hi[d] = std::max(hi[d], nt.coords[(size_t)i * dim + d]);
+          }
+      std::vector<std::pair<uint64_t, int>> keyed(n);
+      const double Q = double((1u << 21) - 1);
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n; ++i)
+        {
+          uint64_t key = 0;
+          for (int d = dim - 1; d >= 0; --d)
+            {
+              const double ext = hi[d] - lo[d];
+              const double t = ext > 0 ? (nt.coords[(size_t)i * dim + d] - lo[d]) / ext : 0.0;
+              const uint64_t q = (uint64_t)std::llround(t * Q);
+              key = (key << 21) | q;
+            }
+          keyed[i] = {key, i};
+        }
+      std::sort(keyed.begin(), keyed.end());
+      std::vector<int> new_id(n);
+      std::vector<double> c2((size_t)n * dim);
+      for (int r = 0; r < n; ++r)
+        {
+          const int old = keyed[r].second;
+          new_id[old] = r;
+          for (int d = 0; d < dim; ++d) c2[(size_t)r * dim + d] = nt.coords[(size_t)old * dim + d];
+        }
+      nt.coords.swap(c2);
+#pragma omp parallel for schedule(static)
+      for (size_t k = 0; k < nt.cell_nodes.size(); ++k) nt.cell_nodes[k] = new_id[nt.cell_nodes[k]];
+    }
+  } // namespace
+
+  NodeTable build_node_table(const Triangulation &tria, int p)
+  {
+    if (p != 1 && p != 2) throw std::runtime_error("build_node_table: only FE_Q(1) and FE_Q(2) are supported");
+    const int dim = tria.dim, vpc = tria.verts_per_cell(), nc = tria.n_cells();
+    NodeTable nt;
+    nt.p = p;
+    nt.dim = dim;
+    FEQ fe(dim, p);
+    nt.nodes_per_cell = fe.n;
+    nt.cell_nodes.resize((size_t)nc * fe.n);
+    if (p == 1)
+      {
+        nt.n_nodes = tria.n_vertices();
+        nt.coords = tria.vertices;
+        for (size_t k = 0; k < tria.cells.size(); ++k) nt.cell_nodes[k] = tria.cells[k];
+        spatial_renumber(nt);
+        return nt;
+      }
+    // p == 2: a node is identified by the set of cell corners it averages
+    const int nv = tria.n_vertices();
+    FlatMap map((size_t)nc * (dim == 3 ? 8 : 4) + 16);
+    // vertices keep ids 0..nv-1, shared entities follow, cell-interior nodes last
+    std::vector<int> corner_sets((size_t)fe.n * 8, -1), corner_cnt(fe.n, 0);
+    for (int a = 0; a < fe.n; ++a)
+      {
+        int cnt = 0;
+        for (int v = 0; v < vpc; ++v)
+          {
+            bool ok = true;
+            for (int d = 0; d < dim; ++d)
+              {
+                const int l = fe.lattice[a][d], bit = (v >> d) & 1;
+                if (l == 0 && bit != 0) ok = false;
+                if (l == 2 && bit != 1) ok = false;
+              }
+            if (ok) corner_sets[(size_t)a * 8 + cnt++] = v;
+          }
+        corner_cnt[a] = cnt;
+      }
+    int n_shared = 0;
+    std::vector<int> tmp_ids((size_t)nc * fe.n);
+    for (int c = 0; c < nc; ++c)
+      {
+        const int *cv = &tria.cells[(size_t)c * vpc];
+        for (int a = 0; a < fe.n; ++a)
+          {
+            const int cnt = corner_cnt[a];
+            int id;
+            if (cnt == 1)
+              id = cv[corner_sets[(size_t)a * 8]];
+            else if (cnt == vpc)
+              id = -1 - c; // cell-interior node, resolved below
+            else
+              {
+                Key k{{-1, -1, -1, -1}};
+                for (int i = 0; i < cnt; ++i) k.v[i] = cv[corner_sets[(size_t)a * 8 + i]];
+                std::sort(k.v, k.v + cnt);
+                id = nv + map.find_or_insert(k);
+              }
+            tmp_ids[(size_t)c * fe.n + a] = id;
+          }
+      }
+    n_shared = (int)map.keys.size();
+    nt.n_nodes = nv + n_shared + nc;
+    nt.coords.assign((size_t)nt.n_nodes * dim, 0.0);
+    for (int c = 0; c < nc; ++c)
+      {
+        const int *cv = &tria.cells[(size_t)c * vpc];
+        for (int a = 0; a < fe.n; ++a)
+          {
+            int id = tmp_ids[(size_t)c * fe.n + a];
+            if (id < 0) id = nv + n_shared + c;
+            nt.cell_nodes[(size_t)c * fe.n + a] = id;
+            const int cnt = corner_cnt[a];
+            double x[3] = {0, 0, 0};
+            for (int i = 0; i < cnt; ++i)
+              for (int d = 0; d < dim; ++d) x[d] += tria.vertices[(size_t)cv[corner_sets[(size_t)a * 8 + i]] * dim + d];
+            for (int d = 0; d < dim; ++d) nt.coords[(size_t)id * dim + d] = x[d] / cnt;
+          }
+      }
+    spatial_renumber(nt);
+    return nt;
+  }
+
+  std::vector<int> face_local_nodes(int dim, int p, int face_no)
+  {
+    FEQ fe(dim, p);
+    const int axis = face_no / 2, side = face_no % 2;
+    std::vector<int> out;
+    for (int a = 0; a < fe.n; ++a)
+      if (fe.lattice[a][axis] == (side ? p : 0)) out.push_back(a);
+    return out;
+  }
+
+  void Triangulation::refine_global(int times)
+  {
+    for (int t = 0; t < times; ++t)
+      {
+        const NodeTable nt = build_node_table(*this, 2);
+        const int vpc = verts_per_cell(), nc = n_cells();
+        FEQ fe(dim, 2);
+        std::vector<int> new_cells((size_t)nc * vpc * vpc);
+        std::vector<int> new_mat((size_t)nc * vpc);
+        for (int c = 0; c < nc; ++c)
+          for (int child = 0; child < vpc; ++child)
+            {
+              new_mat[(size_t)c * vpc + child] = material_id[c];
+              for (int v = 0; v < vpc; ++v)
+                {
+                  int a = 0, stride = 1;
+                  for (int d = 0; d < dim; ++d)
+                    {
+                      a += (((child >> d) & 1) + ((v >> d) & 1)) * stride;
+                      stride *= 3;
+                    }
+                  new_cells[((size_t)c * vpc + child) * vpc + v] = nt.cell_nodes[(size_t)c * fe.n + a];
+                }
+            }
+        std::vector<int> new_bf;
+        for (int f = 0; f < n_boundary_faces(); ++f)
+          {
+            const int c = boundary_faces[3 * f], face = boundary_faces[3 * f + 1], id = boundary_faces[3 * f + 2];
+            const int axis = face / 2, side = face % 2;
+            for (int child = 0; child < vpc; ++child)
+              if (((child >> axis) & 1) == side)
+                {
+                  new_bf.push_back(c * vpc + child);
+                  new_bf.push_back(face);
+                  new_bf.push_back(id);
+                }
+          }
+        vertices = nt.coords;
+        cells.swap(new_cells);
+        material_id.swap(new_mat);
+        boundary_faces.swap(new_bf);
+      }
+  }
+
+  // ---------------------------------------------------------------------------
+  // Patterns
+  // ---------------------------------------------------------------------------
+  namespace
+  {
+    // node -> cells adjacency (CSR)
+    void node_to_cells(int n_cells, const int *table, int per_cell, int n_nodes, std::vector<int64_t> &ptr,
+                       std::vector<int> &adj)
+    {
+      ptr.assign((size_t)n_nodes + 1, 0);
+      for (size_t k = 0; k < (size_t)n_cells * per_cell; ++k) ptr[table[k] + 1]++;
+      for (int i = 0; i < n_nodes; ++i) ptr[i + 1] += ptr[i];
+      adj.resize(ptr[n_nodes]);
+      std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
+      for (int c = 0; c < n_cells; ++c)
+        for (int a = 0; a < per_cell; ++a) adj[pos[table[(size_t)c * per_cell + a]]++] = c;
+    }
+  } // namespace
+
+  Pattern build_pattern(int n_cells, const int *row_table, int nr, int n_rows, const int *col_table, int ncl, int n_cols)
+  {
+    Pattern P;
+    P.n_rows = n_rows;
+    P.n_cols = n_cols;
+    std::vector<int64_t> ptr;
+    std::vector<int> adj;
+    node_to_cells(n_cells, row_table, nr, n_rows, ptr, adj);
+    P.rowptr.assign((size_t)n_rows + 1, 0);
+    for (int pass = 0; pass < 2; ++pass)
+      {
+#pragma omp parallel
+        {
+          std::vector<int> buf;
+#pragma omp for schedule(dynamic, 4096)
+          for (int r = 0; r < n_rows; ++r)
+            {
+              buf.clear();
+              for (int64_t k = ptr[r]; k < ptr[r + 1]; ++k)
+                {
+                  const int *cn = col_table + (size_t)adj[k] * ncl;
+                  buf.insert(buf.end(), cn, cn + ncl);
+                }
+              std::sort(buf.begin(), buf.end());
+              const int cnt = (int)(std::unique(buf.begin(), buf.end()) - buf.begin());
+              if (pass == 0)
+                P.rowptr[r + 1] = cnt;
+              else
+                std::copy(buf.begin(), buf.begin() + cnt, P.col.begin() + P.rowptr[r]);
+            }
+        }
+        if (pass == 0)
+          {
+            for (int r = 0; r < n_rows; ++r) P.rowptr[r + 1] += P.rowptr[r];
+            P.col.resize(P.rowptr[n_rows]);
+          }
+      }
+    return P;
+  }
+
+  Pattern build_schur_pattern(const Triangulation &tria, const NodeTable &pn)
+  {
+    const int nc = tria.n_cells(), vpc = tria.verts_per_cell();
+    // cells around each vertex, then cells around each p-node
+    std::vector<int64_t> vptr, pptr;
+    std::vector<int> vadj, padj;
+    node_to_cells(nc, tria.cells.data(), vpc, tria.n_vertices(), vptr, vadj);
+    node_to_cells(nc, pn.cell_nodes.data(), pn.nodes_per_cell, pn.n_nodes, pptr, padj);
+    Pattern P;
+    P.n_rows = P.n_cols = pn.n_nodes;
+    P.rowptr.assign((size_t)pn.n_nodes + 1, 0);
+    for (int pass = 0; pass < 2; ++pass)
+      {
+#pragma omp parallel
+        {
+          std::vector<int> cbuf, buf;
+#pragma omp for schedule(dynamic, 1024)
+          for (int r = 0; r < pn.n_nodes; ++r)
+            {
+              cbuf.clear();
+              for (int64_t k = pptr[r]; k < pptr[r + 1]; ++k)
+                {
+                  const int *cv = &tria.cells[(size_t)padj[k] * vpc];
+                  for (int v = 0; v < vpc; ++v)
+                    for (int64_t m = vptr[cv[v]]; m < vptr[cv[v] + 1]; ++m) cbuf.push_back(vadj[m]);
+                }
+              std::sort(cbuf.begin(), cbuf.end());
+              cbuf.erase(std::unique(cbuf.begin(), cbuf.end()), cbuf.end());
+              buf.clear();
+              for (int c : cbuf)
+                {
+                  const int *cn = &pn.cell_nodes[(size_t)c * pn.nodes_per_cell];
+                  buf.insert(buf.end(), cn, cn + pn.nodes_per_cell);
+                }
+              std::sort(buf.begin(), buf.end());
+              const int cnt = (int)(std::unique(buf.begin(), buf.end()) - buf.begin());
+              if (pass == 0)
+                P.rowptr[r + 1] = cnt;
+              else
+                std::copy(buf.begin(), buf.begin() + cnt, P.col.begin() + P.rowptr[r]);
+            }
+        }
+        if (pass == 0)
+          {
+            for (int r = 0; r < pn.n_nodes; ++r) P.rowptr[r + 1] += P.rowptr[r];
+            P.col.resize(P.rowptr[pn.n_nodes]);
+          }
+      }
+    return P;
+  }
+
+  void colour_cells(int n_cells, const int *table, int per_cell, int n_nodes, std::vector<int> &order,
+                    std::vector<int> &offsets)
+  {
+    std::vector<int64_t> ptr;
+    std::vector<int> adj;
+    node_to_cells(n_cells, table, per_cell, n_nodes, ptr, adj);
+    std::vector<int> colour(n_cells, -1);
+    int n_colours = 0;
+    std::vector<int> stamp(64, -1);
+    for (int c = 0; c < n_cells; ++c)
+      {
+        for (int a = 0; a < per_cell; ++a)
+          {
+            const int node = table[(size_t)c * per_cell + a];
+            for (int64_t k = ptr[node]; k < ptr[node + 1]; ++k)
+              {
+                const int col = colour[adj[k]];
+                if (col >= 0)
+                  {
+                    if (col >= (int)stamp.size()) stamp.resize(col + 1, -1);
+                    stamp[col] = c;
+                  }
+              }
+          }
+        int pick = 0;
+        while (pick < (int)stamp.size() && stamp[pick] == c) ++pick;
+        if (pick >= (int)stamp.size()) stamp.resize(pick + 1, -1);
+        colour[c] = pick;
+        n_colours = std::max(n_colours, pick + 1);
+      }
+    offsets.assign(n_colours + 1, 0);
+    for (int c = 0; c < n_cells; ++c) offsets[colour[c] + 1]++;
+    for (int k = 0; k < n_colours; ++k) offsets[k + 1] += offsets[k];
+    order.resize(n_cells);
+    std::vector<int> pos(offsets.begin(), offsets.end() - 1);
+    for (int c = 0; c < n_cells; ++c) order[pos[colour[c]]++] = c;
+  }
+} // namespace ifem

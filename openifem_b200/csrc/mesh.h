@@ -1,0 +1,79 @@
+// Minimal stand-ins for the deal.II mesh / DoF objects the OpenIFEM hot path is
+// written against (deal.II is not available in this image): a hexahedral /
+// quadrilateral Triangulation with boundary ids, GridGenerator box meshes with
+// colorize = true (boundary id = 2*axis + side), uniform refinement, FE_Q(p)
+// node numbering (p = 1, 2) and node-level sparsity patterns.
+//
+// Reference: triangulations are created in the test drivers
+// (tests/fluid_cavity/fluid_cavity.cpp:28-34, tests/fluid_pipe_mpi/fluid_pipe_mpi.cpp:37-45)
+// and consumed by Fluid::MPI::FluidSolver::setup_dofs / initialize_system
+// (source/mpi_fluid_solver.cpp:116-162, 305-365).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <string>
+#include <vector>
+
+namespace ifem
+{
+  struct Triangulation
+  {
+    int dim = 0;
+    std::vector<double> vertices;    // [n_vertices][dim]
+    std::vector<int> cells;          // [n_cells][2^dim], lexicographic (x fastest) vertex order
+    std::vector<int> boundary_faces; // [n_bfaces][3] = (cell, face_no = 2*axis+side, boundary id)
+    std::vector<int> material_id;    // [n_cells]
+
+    int n_vertices() const { return dim ? (int)(vertices.size() / dim) : 0; }
+    int verts_per_cell() const { return 1 << dim; }
+    int n_cells() const { return dim ? (int)(cells.size() / verts_per_cell()) : 0; }
+    int n_boundary_faces() const { return (int)(boundary_faces.size() / 3); }
+    int n_active_cells() const { return n_cells(); }
+
+    void refine_global(int times);
+  };
+
+  namespace GridGenerator
+  {
+    void subdivided_hyper_rectangle(Triangulation &tria, const std::vector<unsigned int> &repetitions, const double *p1,
+                                    const double *p2, bool colorize);
+    void hyper_cube(Triangulation &tria, int dim, double left, double right, bool colorize);
+  } // namespace GridGenerator
+
+  // FE_Q(p) node numbering on a triangulation: nodes are unique geometric entities
+  // (vertices, edge / face / cell midpoints for p = 2), numbered in lexicographic
+  // (z, y, x) order of their position so that rows of the operators stay local in
+  // memory and a slab partition owns contiguous ranges.
+  struct NodeTable
+  {
+    int p = 0, nodes_per_cell = 0, n_nodes = 0, dim = 0;
+    std::vector<int> cell_nodes; // [n_cells][nodes_per_cell], local order lexicographic
+    std::vector<double> coords;  // [n_nodes][dim]
+  };
+  NodeTable build_node_table(const Triangulation &tria, int p);
+
+  // local node indices of FE_Q(p) on face 2*axis+side
+  std::vector<int> face_local_nodes(int dim, int p, int face_no);
+
+  // Node-level CSR pattern: row node r couples with every column node that shares a
+  // cell with it (DoFTools::make_sparsity_pattern without coupling table,
+  // source/mpi_fluid_solver.cpp:311-312). Columns sorted.
+  struct Pattern
+  {
+    int n_rows = 0, n_cols = 0;
+    std::vector<int64_t> rowptr;
+    std::vector<int> col;
+  };
+  Pattern build_pattern(int n_cells, const int *row_table, int nr, int n_rows, const int *col_table, int ncl, int n_cols);
+
+  // Pattern of B * B^T on pressure nodes (compute_mmult_pattern,
+  // source/mpi_fluid_solver.cpp:326-329): p-nodes of all cells that share a vertex
+  // with a cell containing the row node.
+  Pattern build_schur_pattern(const Triangulation &tria, const NodeTable &pn);
+
+  // Greedy colouring: cells of one colour share no node of `table`.
+  // Returns cell ids grouped by colour and the group offsets.
+  void colour_cells(int n_cells, const int *table, int per_cell, int n_nodes, std::vector<int> &order,
+                    std::vector<int> &offsets);
+} // namespace ifem

@@ -1,0 +1,44 @@
+"""The CPU oracle (oracle/) against the reference's own golden values for the
+INS hot path. These are the only reference-pinned numbers for
+this path; everything else is checked GPU-vs-oracle.
+
+  fluid_pipe_mpi        (Fluid::MPI::InsIM, 50x5 cells r=1, 20 steps dt 0.1): max v = 1.5 +-1e-2
+                        reference tests/fluid_pipe_mpi/fluid_pipe_mpi.cpp:50-55
+  fluid_gravity         (serial InsIM, 100x10 r=1): p_max - p_min = 20 +-1e-3
+                        reference tests/fluid_gravity/fluid_gravity.cpp:37-41
+  fluid_pressure_driven (serial InsIM, 100x10 r=1, Neumann face term): max v = 2.5e-2 +-1e-3
+                        reference tests/fluid_pressure_driven/fluid_pressure_driven.cpp:42-44
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fem, ins, prm
+
+
+def _run(golden_dir, name, reps, lo, hi, mode, max_steps=None):
+    p = prm.Params(os.path.join(golden_dir, name))
+    mesh = fem.BoxMesh(reps, lo, hi).refine_global(p.global_refinements[0])
+    s = ins.InsIM(mesh, p, mode=mode)
+    s.run(max_steps=max_steps)
+    return s
+
+
+def test_fluid_pipe_mpi_golden(golden_dir):
+    s = _run(golden_dir, "ins_pipe_2d.prm", (50, 5), (0, 0), (2.0, 0.2), "mpi")
+    vmax = s.velocity().max()
+    assert abs(vmax - 1.5) / 1.5 < 1e-2
+
+
+def test_fluid_gravity_golden(golden_dir):
+    s = _run(golden_dir, "ins_gravity_2d.prm", (100, 10), (0, 0), (2.0, 0.2), "serial")
+    p = s.pressure()
+    assert abs((p.max() - p.min()) - 20) / 20 < 1e-3
+
+
+@pytest.mark.slow
+def test_fluid_pressure_driven_golden(golden_dir):
+    s = _run(golden_dir, "ins_pressure_driven_2d.prm", (100, 10), (0, 0), (2.0, 0.2), "serial")
+    vmax = s.velocity().max()
+    assert abs(vmax - 2.5e-2) / 2.5e-2 < 1e-3

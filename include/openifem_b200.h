@@ -1,0 +1,119 @@
+/* openifem_b200 C ABI - the drop-in boundary of the B200-native hot path.
+ *
+ * OpenIFEM has no FFI of its own: its boundary is the C++ class surface consumed by
+ * the test drivers (reference include/mpi_fluid_solver.h:99-183, include/mpi_insim.h:42-87,
+ * include/parameters.h:191). This header is the extern "C" layer underneath our
+ * same-named C++ classes (include/openifem/*.h); every entry point cites the
+ * reference member it stands for. Plain pointers and sizes only; handles are
+ * opaque; all functions return 0 on success and a non-zero code on failure with the
+ * message available from ifem_last_error() (the reference throws dealii exceptions;
+ * the C++ facade converts the code back into a throw).
+ *
+ * There is no CPU fallback: every compute entry point fails with IFEM_ERR_NO_DEVICE
+ * when no CUDA device is present.
+ */
+#ifndef OPENIFEM_B200_H
+#define OPENIFEM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFEM_OK 0
+#define IFEM_ERR 1
+#define IFEM_ERR_NO_DEVICE 2
+
+typedef struct ifem_tria ifem_tria;     /* dealii::Triangulation<dim> stand-in */
+typedef struct ifem_params ifem_params; /* Parameters::AllParameters */
+typedef struct ifem_insim ifem_insim;   /* Fluid::MPI::InsIM<dim> */
+
+const char *ifem_last_error(void);
+int ifem_version(void);
+/* bind this process (= one rank) to a CUDA device; called once before any solver is created */
+int ifem_init(int device);
+/* number of kernels launched by the library so far in this process */
+int ifem_kernel_launches(int64_t *count);
+
+/* ---- Triangulation: GridGenerator calls of the reference test drivers
+ *      (tests/fluid_cavity/fluid_cavity.cpp:28-34, tests/fluid_pipe_mpi/fluid_pipe_mpi.cpp:37-45) ---- */
+int ifem_tria_create(int dim, ifem_tria **out);
+int ifem_tria_destroy(ifem_tria *t);
+int ifem_tria_subdivided_hyper_rectangle(ifem_tria *t, const unsigned int *repetitions, const double *p1, const double *p2,
+                                         int colorize);
+int ifem_tria_hyper_cube(ifem_tria *t, double left, double right, int colorize);
+int ifem_tria_refine_global(ifem_tria *t, int times);
+int ifem_tria_counts(const ifem_tria *t, int64_t *n_vertices, int64_t *n_cells, int64_t *n_boundary_faces);
+
+/* ---- Parameters::AllParameters(prm_file) (include/parameters.h:191, source/parameters.cpp:618-658) ---- */
+int ifem_params_from_file(const char *prm_file, ifem_params **out);
+int ifem_params_from_text(const char *prm_text, ifem_params **out);
+int ifem_params_destroy(ifem_params *p);
+
+/* ---- Fluid::MPI::InsIM<dim> (include/mpi_insim.h:42-87, source/mpi_insim.cpp) ---- */
+typedef struct
+{
+  double fgmres_rel, fgmres_floor; /* SolverControl tol = max(floor, rel*|rhs|), mpi_insim.cpp:379-380 */
+  double cg_mp_rel, cg_sm_rel, cg_floor; /* mpi_insim.cpp:73-109 */
+  double a_inv_rel;   /* inner Krylov stand-in for the MUMPS LU of A~ (mpi_insim.cpp:124-127) */
+  int a_inv_max_it;
+  int basis_size;     /* SolverFGMRES max_basis_size (deal.II default 30) */
+} ifem_ins_control;
+
+typedef struct
+{
+  unsigned int timestep, iteration;
+  double abs_res, rel_res; /* the ITR / ABS_RES / REL_RES line, mpi_insim.cpp:456-460 */
+  int gmres_its;
+  double gmres_res;
+  int cg_mp_its, cg_sm_its, a_inv_its, precond_applies;
+} ifem_newton_record;
+
+/* InsIM(tria, parameters): the solver keeps a reference to the caller-owned triangulation
+ * (mpi_fluid_solver.h:187) and a copy of the parameters (:222) */
+int ifem_insim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out);
+int ifem_insim_destroy(ifem_insim *s);
+int ifem_insim_default_control(int serial_twin, ifem_ins_control *out);
+int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c);
+int ifem_insim_set_verbose(ifem_insim *s, int verbose);
+/* setup_dofs(); make_constraints(); initialize_system();  (mpi_insim.cpp:504-506) - no refinement */
+int ifem_insim_setup(ifem_insim *s);
+/* run(): refine_global(Global refinements[0]) + setup + time loop (mpi_insim.cpp:492-519) */
+int ifem_insim_run(ifem_insim *s);
+/* run_one_step(apply_nonzero_constraints) (mpi_insim.cpp:397-490) */
+int ifem_insim_run_one_step(ifem_insim *s, int apply_nonzero_constraints);
+/* assemble(use_nonzero_constraints) (mpi_insim.cpp:152-362) at the current evaluation_point */
+int ifem_insim_assemble(ifem_insim *s, int use_nonzero_constraints);
+/* solve(use_nonzero_constraints) (mpi_insim.cpp:364-395): newton_update from the assembled system */
+int ifem_insim_solve(ifem_insim *s, int use_nonzero_constraints, unsigned int *its, double *res);
+int ifem_insim_sizes(const ifem_insim *s, int64_t *n_u, int64_t *n_p, int64_t *nnz_system, int64_t *nnz_mp, int64_t *nnz_schur);
+/* support point of every dof, [n_dofs][dim] */
+int ifem_insim_support_points(const ifem_insim *s, double *pts);
+/* get_current_solution() (mpi_fluid_solver.h:113): block vector [u | p] to a host buffer */
+int ifem_insim_get_current_solution(ifem_insim *s, double *host);
+/* which: 0 present_solution, 1 evaluation_point, 2 fsi_acceleration, 3 newton_update, 4 system_rhs, 5 diag(M_u) (n_u) */
+int ifem_insim_set_vector(ifem_insim *s, int which, const double *host);
+int ifem_insim_get_vector(ifem_insim *s, int which, double *host);
+int ifem_insim_set_indicator(ifem_insim *s, const int *host_indicator);
+/* assembled operators as scalar CSR on the host (parity tests): which = 0 system_matrix, 1 M_p, 2 mass_schur */
+int ifem_insim_get_matrix(ifem_insim *s, int which, int64_t *rowptr, int *col, double *val);
+/* y = system_matrix * x with host buffers (BlockSparseMatrix::vmult) */
+int ifem_insim_vmult(ifem_insim *s, const double *x_host, double *y_host);
+int ifem_insim_history(const ifem_insim *s, int max_records, ifem_newton_record *out, int *n_records);
+/* accumulated device milliseconds of a TimerOutput section ("Assemble system", "Solve linear system",
+ * "CG for Mp", "CG for Sm", "A_inv") */
+int ifem_insim_timer_ms(const ifem_insim *s, const char *section, double *ms);
+int ifem_insim_time(const ifem_insim *s, unsigned int *timestep, double *current);
+
+/* ---- measurement hooks (bench.py): device-resident, CUDA-event timed on the library's stream ---- */
+/* reps applications of the block SpMV on resident vectors; returns mean ms per application and the
+ * algorithmic bytes of one application */
+int ifem_insim_bench_vmult(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
+/* same for the velocity-velocity block alone (the dominant kernel) */
+int ifem_insim_bench_spmv_uu(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
+int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms_per_assembly);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

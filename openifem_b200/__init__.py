@@ -1,0 +1,226 @@
+"""openifem_b200: B200-native hot path of OpenIFEM behind the reference's class surface.
+
+Python mirror (over the C ABI, via ctypes) of the classes the reference's test
+drivers use: `Triangulation` + `GridGenerator` (deal.II stand-ins),
+`Parameters.AllParameters` (include/parameters.h:191) and `Fluid.MPI.InsIM`
+(include/mpi_insim.h:42-87). All arithmetic runs in the CUDA library
+openifem_b200/lib/libopenifem_b200.so; there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import IfemError, InsControl, NewtonRecord, check, dptr, iptr, lptr, lib
+
+__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "IfemError", "init", "kernel_launches"]
+
+
+def init(device: int = 0):
+    check(lib().ifem_init(C.c_int(device)))
+
+
+def kernel_launches() -> int:
+    n = C.c_int64(0)
+    check(lib().ifem_kernel_launches(C.byref(n)))
+    return n.value
+
+
+class Triangulation:
+    def __init__(self, dim: int):
+        self.dim = dim
+        self._h = C.c_void_p()
+        check(lib().ifem_tria_create(C.c_int(dim), C.byref(self._h)))
+
+    def refine_global(self, times: int):
+        check(lib().ifem_tria_refine_global(self._h, C.c_int(times)))
+
+    def _counts(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().ifem_tria_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def n_vertices(self):
+        return self._counts()[0]
+
+    def n_active_cells(self):
+        return self._counts()[1]
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib._lib is not None:
+            _lib._lib.ifem_tria_destroy(self._h)
+            self._h = None
+
+
+class GridGenerator:
+    @staticmethod
+    def subdivided_hyper_rectangle(tria: Triangulation, repetitions, p1, p2, colorize=False):
+        reps = (C.c_uint * tria.dim)(*[int(r) for r in repetitions])
+        a = (C.c_double * tria.dim)(*[float(x) for x in p1])
+        b = (C.c_double * tria.dim)(*[float(x) for x in p2])
+        check(lib().ifem_tria_subdivided_hyper_rectangle(tria._h, reps, a, b, C.c_int(1 if colorize else 0)))
+
+    @staticmethod
+    def hyper_cube(tria: Triangulation, left=0.0, right=1.0, colorize=False):
+        check(lib().ifem_tria_hyper_cube(tria._h, C.c_double(left), C.c_double(right), C.c_int(1 if colorize else 0)))
+
+
+class Parameters:
+    class AllParameters:
+        def __init__(self, prm_file: str = None, text: str = None):
+            self._h = C.c_void_p()
+            if text is not None:
+                check(lib().ifem_params_from_text(text.encode(), C.byref(self._h)))
+            else:
+                check(lib().ifem_params_from_file(prm_file.encode(), C.byref(self._h)))
+
+        def __del__(self):
+            if getattr(self, "_h", None) and _lib._lib is not None:
+                _lib._lib.ifem_params_destroy(self._h)
+                self._h = None
+
+
+class _InsIM:
+    """Fluid::MPI::InsIM<dim>(triangulation, parameters)."""
+
+    PRESENT, EVALUATION_POINT, FSI_ACCELERATION, NEWTON_UPDATE, SYSTEM_RHS, DIAG_MU = range(6)
+
+    def __init__(self, tria: Triangulation, params: "Parameters.AllParameters"):
+        self.tria, self.params = tria, params  # the solver keeps a reference to the caller's triangulation
+        self._h = C.c_void_p()
+        check(lib().ifem_insim_create(tria._h, params._h, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib._lib is not None:
+            _lib._lib.ifem_insim_destroy(self._h)
+            self._h = None
+
+    # -- reference surface --------------------------------------------------
+    def run(self):
+        check(lib().ifem_insim_run(self._h))
+
+    def run_one_step(self, apply_nonzero_constraints: bool, assemble_system: bool = True):
+        check(lib().ifem_insim_run_one_step(self._h, C.c_int(1 if apply_nonzero_constraints else 0)))
+
+    def get_current_solution(self) -> np.ndarray:
+        out = np.empty(self.n_dofs)
+        check(lib().ifem_insim_get_current_solution(self._h, dptr(out)))
+        return out
+
+    def setup(self):
+        """setup_dofs(); make_constraints(); initialize_system()"""
+        check(lib().ifem_insim_setup(self._h))
+
+    def assemble(self, use_nonzero_constraints: bool):
+        check(lib().ifem_insim_assemble(self._h, C.c_int(1 if use_nonzero_constraints else 0)))
+
+    def solve(self, use_nonzero_constraints: bool):
+        its, res = C.c_uint(), C.c_double()
+        check(lib().ifem_insim_solve(self._h, C.c_int(1 if use_nonzero_constraints else 0), C.byref(its), C.byref(res)))
+        return its.value, res.value
+
+    # -- inspection -----------------------------------------------------------
+    def sizes(self):
+        v = [C.c_int64() for _ in range(5)]
+        check(lib().ifem_insim_sizes(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    @property
+    def n_u(self):
+        return self.sizes()[0]
+
+    @property
+    def n_p(self):
+        return self.sizes()[1]
+
+    @property
+    def n_dofs(self):
+        s = self.sizes()
+        return s[0] + s[1]
+
+    def support_points(self):
+        pts = np.empty((self.n_dofs, self.tria.dim))
+        check(lib().ifem_insim_support_points(self._h, dptr(pts)))
+        return pts
+
+    def set_control(self, serial_twin=False, **kw):
+        c = InsControl()
+        check(lib().ifem_insim_default_control(C.c_int(1 if serial_twin else 0), C.byref(c)))
+        for k, v in kw.items():
+            if not hasattr(c, k):
+                raise KeyError(k)
+            setattr(c, k, v)
+        check(lib().ifem_insim_set_control(self._h, C.byref(c)))
+
+    def set_verbose(self, v=True):
+        check(lib().ifem_insim_set_verbose(self._h, C.c_int(1 if v else 0)))
+
+    def set_vector(self, which: int, host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        check(lib().ifem_insim_set_vector(self._h, C.c_int(which), dptr(host)))
+
+    def get_vector(self, which: int) -> np.ndarray:
+        n = self.n_u if which == self.DIAG_MU else self.n_dofs
+        out = np.empty(n)
+        check(lib().ifem_insim_get_vector(self._h, C.c_int(which), dptr(out)))
+        return out
+
+    def set_indicator(self, ind: np.ndarray):
+        ind = np.ascontiguousarray(ind, dtype=np.int32)
+        check(lib().ifem_insim_set_indicator(self._h, iptr(ind)))
+
+    def get_matrix(self, which=0):
+        """0 system_matrix, 1 M_p, 2 mass_schur -> scipy.sparse.csr_matrix"""
+        import scipy.sparse as sp
+
+        n_u, n_p, nnz, nnz_mp, nnz_s = self.sizes()
+        n, z = {0: (n_u + n_p, nnz), 1: (n_p, nnz_mp), 2: (n_p, nnz_s)}[which]
+        rp, ci, v = np.empty(n + 1, dtype=np.int64), np.empty(z, dtype=np.int32), np.empty(z)
+        check(lib().ifem_insim_get_matrix(self._h, C.c_int(which), lptr(rp), iptr(ci), dptr(v)))
+        return sp.csr_matrix((v, ci, rp), shape=(n, n))
+
+    def vmult(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        check(lib().ifem_insim_vmult(self._h, dptr(x), dptr(y)))
+        return y
+
+    def history(self, max_records=4096):
+        buf = (NewtonRecord * max_records)()
+        n = C.c_int()
+        check(lib().ifem_insim_history(self._h, C.c_int(max_records), buf, C.byref(n)))
+        k = min(n.value, max_records)
+        return [{f: getattr(buf[i], f) for f, _ in NewtonRecord._fields_} for i in range(k)]
+
+    def timer_ms(self, section: str) -> float:
+        ms = C.c_double()
+        check(lib().ifem_insim_timer_ms(self._h, section.encode(), C.byref(ms)))
+        return ms.value
+
+    def time(self):
+        ts, cur = C.c_uint(), C.c_double()
+        check(lib().ifem_insim_time(self._h, C.byref(ts), C.byref(cur)))
+        return ts.value, cur.value
+
+    # -- measurement hooks ---------------------------------------------------
+    def bench_vmult(self, reps):
+        ms, b = C.c_double(), C.c_double()
+        check(lib().ifem_insim_bench_vmult(self._h, C.c_int(reps), C.byref(ms), C.byref(b)))
+        return ms.value, b.value
+
+    def bench_spmv_uu(self, reps):
+        ms, b = C.c_double(), C.c_double()
+        check(lib().ifem_insim_bench_spmv_uu(self._h, C.c_int(reps), C.byref(ms), C.byref(b)))
+        return ms.value, b.value
+
+    def bench_assemble(self, reps):
+        ms = C.c_double()
+        check(lib().ifem_insim_bench_assemble(self._h, C.c_int(reps), C.byref(ms)))
+        return ms.value
+
+
+class Fluid:
+    class MPI:
+        InsIM = _InsIM

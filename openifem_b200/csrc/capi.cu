@@ -1,0 +1,424 @@
+// extern "C" layer: see include/openifem_b200.h for the contract.
+#include "../../include/openifem_b200.h"
+
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "insim.h"
+
+using namespace ifem;
+
+struct ifem_tria
+{
+  Triangulation t;
+};
+struct ifem_params
+{
+  std::unique_ptr<Parameters::AllParameters> p;
+};
+struct ifem_insim
+{
+  std::unique_ptr<InsIM> s;
+};
+
+namespace
+{
+  thread_local std::string g_error;
+  bool g_initialised = false;
+
+  template <typename F>
+  int guard(F &&f)
+  {
+    try
+      {
+        f();
+        return IFEM_OK;
+      }
+    catch (const std::exception &e)
+      {
+        g_error = e.what();
+        return g_error.find("no CUDA device") != std::string::npos ? IFEM_ERR_NO_DEVICE : IFEM_ERR;
+      }
+    catch (...)
+      {
+        g_error = "unknown error";
+        return IFEM_ERR;
+      }
+  }
+
+  void require_device()
+  {
+    if (g_initialised) return;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      throw std::runtime_error("openifem_b200: no CUDA device available - this library has no CPU fallback");
+    g_initialised = true;
+  }
+
+  // scalar CSR of a BCSR matrix appended at a row/column offset
+  struct HostCsr
+  {
+    std::vector<int64_t> rp;
+    std::vector<int> ci;
+    std::vector<double> v;
+  };
+} // namespace
+
+template <typename F>
+static double time_reps(Context &ctx, int reps, F &&f)
+{
+  cudaEvent_t e0, e1;
+  IFEM_CUDA(cudaEventCreate(&e0));
+  IFEM_CUDA(cudaEventCreate(&e1));
+  IFEM_CUDA(cudaEventRecord(e0, ctx.stream));
+  for (int i = 0; i < reps; ++i) f();
+  IFEM_CUDA(cudaEventRecord(e1, ctx.stream));
+  IFEM_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  IFEM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return (double)ms / reps;
+}
+
+static DevBuf<double> *pick_vector(InsIM &m, int which, int64_t &n)
+{
+  n = m.fs.n_dofs;
+  switch (which)
+    {
+    case 0: return &m.present_solution;
+    case 1: return &m.evaluation_point;
+    case 2: return &m.fsi_acceleration;
+    case 3: return &m.newton_update;
+    case 4: return &m.fs.rhs;
+    case 5: n = m.fs.n_u; return &m.fs.diag_Mu;
+    default: throw std::runtime_error("unknown vector id");
+    }
+}
+extern "C" {
+
+const char *ifem_last_error(void) { return g_error.c_str(); }
+int ifem_version(void) { return 100; }
+
+int ifem_init(int device)
+{
+  return guard([&] {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      throw std::runtime_error("openifem_b200: no CUDA device available - this library has no CPU fallback");
+    IFEM_CUDA(cudaSetDevice(device));
+    g_initialised = true;
+    (void)default_context();
+  });
+}
+
+int ifem_kernel_launches(int64_t *count)
+{
+  return guard([&] {
+    require_device();
+    *count = default_context().kernel_launches;
+  });
+}
+
+int ifem_tria_create(int dim, ifem_tria **out)
+{
+  return guard([&] {
+    if (dim != 2 && dim != 3) throw std::runtime_error("Triangulation: dim must be 2 or 3");
+    *out = new ifem_tria;
+    (*out)->t.dim = dim;
+  });
+}
+int ifem_tria_destroy(ifem_tria *t)
+{
+  delete t;
+  return IFEM_OK;
+}
+int ifem_tria_subdivided_hyper_rectangle(ifem_tria *t, const unsigned int *reps, const double *p1, const double *p2, int colorize)
+{
+  return guard([&] {
+    const int dim = t->t.dim;
+    GridGenerator::subdivided_hyper_rectangle(t->t, std::vector<unsigned int>(reps, reps + dim), p1, p2, colorize != 0);
+  });
+}
+int ifem_tria_hyper_cube(ifem_tria *t, double left, double right, int colorize)
+{
+  return guard([&] { GridGenerator::hyper_cube(t->t, t->t.dim, left, right, colorize != 0); });
+}
+int ifem_tria_refine_global(ifem_tria *t, int times)
+{
+  return guard([&] { t->t.refine_global(times); });
+}
+int ifem_tria_counts(const ifem_tria *t, int64_t *nv, int64_t *nc, int64_t *nbf)
+{
+  return guard([&] {
+    if (nv) *nv = t->t.n_vertices();
+    if (nc) *nc = t->t.n_cells();
+    if (nbf) *nbf = t->t.n_boundary_faces();
+  });
+}
+
+int ifem_params_from_file(const char *prm_file, ifem_params **out)
+{
+  return guard([&] {
+    auto *p = new ifem_params;
+    p->p.reset(new Parameters::AllParameters(std::string(prm_file)));
+    *out = p;
+  });
+}
+int ifem_params_from_text(const char *text, ifem_params **out)
+{
+  return guard([&] {
+    auto *p = new ifem_params;
+    p->p.reset(new Parameters::AllParameters(Parameters::AllParameters::from_text(std::string(text))));
+    *out = p;
+  });
+}
+int ifem_params_destroy(ifem_params *p)
+{
+  delete p;
+  return IFEM_OK;
+}
+
+int ifem_insim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out)
+{
+  return guard([&] {
+    require_device();
+    auto *h = new ifem_insim;
+    h->s.reset(new InsIM(default_context(), tria->t, *params->p));
+    *out = h;
+  });
+}
+int ifem_insim_destroy(ifem_insim *s)
+{
+  delete s;
+  return IFEM_OK;
+}
+int ifem_insim_default_control(int serial_twin, ifem_ins_control *out)
+{
+  return guard([&] {
+    const InsSolverControl c = serial_twin ? InsSolverControl::serial() : InsSolverControl();
+    out->fgmres_rel = c.fgmres_rel;
+    out->fgmres_floor = c.fgmres_floor;
+    out->cg_mp_rel = c.cg_mp_rel;
+    out->cg_sm_rel = c.cg_sm_rel;
+    out->cg_floor = c.cg_floor;
+    out->a_inv_rel = c.a_inv_rel;
+    out->a_inv_max_it = c.a_inv_max_it;
+    out->basis_size = c.basis_size;
+  });
+}
+int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
+{
+  return guard([&] {
+    InsSolverControl &k = s->s->control;
+    k.fgmres_rel = c->fgmres_rel;
+    k.fgmres_floor = c->fgmres_floor;
+    k.cg_mp_rel = c->cg_mp_rel;
+    k.cg_sm_rel = c->cg_sm_rel;
+    k.cg_floor = c->cg_floor;
+    k.a_inv_rel = c->a_inv_rel;
+    k.a_inv_max_it = c->a_inv_max_it;
+    k.basis_size = c->basis_size;
+  });
+}
+int ifem_insim_set_verbose(ifem_insim *s, int verbose)
+{
+  s->s->verbose = verbose != 0;
+  return IFEM_OK;
+}
+int ifem_insim_setup(ifem_insim *s)
+{
+  return guard([&] {
+    s->s->setup_dofs();
+    s->s->make_constraints();
+    s->s->initialize_system();
+  });
+}
+int ifem_insim_run(ifem_insim *s)
+{
+  return guard([&] { s->s->run(); });
+}
+int ifem_insim_run_one_step(ifem_insim *s, int nz)
+{
+  return guard([&] { s->s->run_one_step(nz != 0); });
+}
+int ifem_insim_assemble(ifem_insim *s, int nz)
+{
+  return guard([&] {
+    s->s->assemble(nz != 0);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+int ifem_insim_solve(ifem_insim *s, int nz, unsigned int *its, double *res)
+{
+  return guard([&] {
+    fill(s->s->ctx, s->s->fs.n_dofs, 0.0, s->s->newton_update.p);
+    const auto r = s->s->solve(nz != 0);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+    if (its) *its = r.first;
+    if (res) *res = r.second;
+  });
+}
+int ifem_insim_sizes(const ifem_insim *s, int64_t *n_u, int64_t *n_p, int64_t *nnz, int64_t *nnz_mp, int64_t *nnz_schur)
+{
+  return guard([&] {
+    const FluidSpace &fs = s->s->fs;
+    if (n_u) *n_u = fs.n_u;
+    if (n_p) *n_p = fs.n_p;
+    if (nnz) *nnz = fs.A_uu.nnz() + fs.A_up.nnz() + fs.A_pu.nnz() + fs.A_pp.nnz();
+    if (nnz_mp) *nnz_mp = fs.M_p.nnz();
+    if (nnz_schur) *nnz_schur = fs.S_m.nnz();
+  });
+}
+int ifem_insim_support_points(const ifem_insim *s, double *pts)
+{
+  return guard([&] {
+    const FluidSpace &fs = s->s->fs;
+    const int dim = fs.dim;
+    for (int n = 0; n < fs.un.n_nodes; ++n)
+      for (int c = 0; c < dim; ++c)
+        for (int d = 0; d < dim; ++d) pts[((size_t)dim * n + c) * dim + d] = fs.un.coords[(size_t)n * dim + d];
+    for (int n = 0; n < fs.pn.n_nodes; ++n)
+      for (int d = 0; d < dim; ++d) pts[((size_t)fs.n_u + n) * dim + d] = fs.pn.coords[(size_t)n * dim + d];
+  });
+}
+int ifem_insim_get_current_solution(ifem_insim *s, double *host)
+{
+  return guard([&] { s->s->present_solution.download(host, s->s->fs.n_dofs, s->s->ctx.stream); });
+}
+
+int ifem_insim_set_vector(ifem_insim *s, int which, const double *host)
+{
+  return guard([&] {
+    int64_t n;
+    DevBuf<double> *v = pick_vector(*s->s, which, n);
+    v->upload(host, n, s->s->ctx.stream);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+int ifem_insim_get_vector(ifem_insim *s, int which, double *host)
+{
+  return guard([&] {
+    int64_t n;
+    DevBuf<double> *v = pick_vector(*s->s, which, n);
+    v->download(host, n, s->s->ctx.stream);
+  });
+}
+int ifem_insim_set_indicator(ifem_insim *s, const int *ind)
+{
+  return guard([&] {
+    s->s->fs.d_indicator.upload(ind, s->s->fs.n_cells, s->s->ctx.stream);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+
+int ifem_insim_get_matrix(ifem_insim *s, int which, int64_t *rowptr, int *col, double *val)
+{
+  return guard([&] {
+    FluidSpace &fs = s->s->fs;
+    cudaStream_t st = s->s->ctx.stream;
+    std::vector<int64_t> rp;
+    std::vector<int> ci;
+    std::vector<double> v;
+    if (which == 1 || which == 2)
+      {
+        (which == 1 ? fs.M_p : fs.S_m).to_host_csr(st, rp, ci, v);
+        std::copy(rp.begin(), rp.end(), rowptr);
+        std::copy(ci.begin(), ci.end(), col);
+        std::copy(v.begin(), v.end(), val);
+        return;
+      }
+    if (which != 0) throw std::runtime_error("unknown matrix id");
+    HostCsr uu, up, pu, ppm;
+    fs.A_uu.to_host_csr(st, uu.rp, uu.ci, uu.v);
+    fs.A_up.to_host_csr(st, up.rp, up.ci, up.v);
+    fs.A_pu.to_host_csr(st, pu.rp, pu.ci, pu.v);
+    const bool has_pp = fs.A_pp.n_brows > 0;
+    if (has_pp) fs.A_pp.to_host_csr(st, ppm.rp, ppm.ci, ppm.v);
+    int64_t pos = 0;
+    for (int64_t r = 0; r < fs.n_u; ++r)
+      {
+        rowptr[r] = pos;
+        for (int64_t k = uu.rp[r]; k < uu.rp[r + 1]; ++k, ++pos) { col[pos] = uu.ci[k]; val[pos] = uu.v[k]; }
+        for (int64_t k = up.rp[r]; k < up.rp[r + 1]; ++k, ++pos) { col[pos] = (int)(fs.n_u + up.ci[k]); val[pos] = up.v[k]; }
+      }
+    for (int64_t r = 0; r < fs.n_p; ++r)
+      {
+        rowptr[fs.n_u + r] = pos;
+        for (int64_t k = pu.rp[r]; k < pu.rp[r + 1]; ++k, ++pos) { col[pos] = pu.ci[k]; val[pos] = pu.v[k]; }
+        if (has_pp)
+          for (int64_t k = ppm.rp[r]; k < ppm.rp[r + 1]; ++k, ++pos) { col[pos] = (int)(fs.n_u + ppm.ci[k]); val[pos] = ppm.v[k]; }
+      }
+    rowptr[fs.n_dofs] = pos;
+  });
+}
+
+int ifem_insim_vmult(ifem_insim *s, const double *x_host, double *y_host)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    DevBuf<double> x(m.fs.n_dofs), y(m.fs.n_dofs);
+    x.upload(x_host, m.fs.n_dofs, m.ctx.stream);
+    block_vmult(m.ctx, m.fs, x.p, y.p);
+    y.download(y_host, m.fs.n_dofs, m.ctx.stream);
+  });
+}
+
+int ifem_insim_history(const ifem_insim *s, int max_records, ifem_newton_record *out, int *n_records)
+{
+  return guard([&] {
+    const auto &h = s->s->history;
+    *n_records = (int)h.size();
+    const int first = std::max(0, (int)h.size() - max_records);
+    for (int i = first; i < (int)h.size(); ++i)
+      {
+        ifem_newton_record &r = out[i - first];
+        r.timestep = h[i].timestep; r.iteration = h[i].iteration; r.abs_res = h[i].abs_res; r.rel_res = h[i].rel_res;
+        r.gmres_its = h[i].gmres_its; r.gmres_res = h[i].gmres_res; r.cg_mp_its = h[i].cg_mp_its; r.cg_sm_its = h[i].cg_sm_its;
+        r.a_inv_its = h[i].a_inv_its; r.precond_applies = h[i].precond_applies;
+      }
+  });
+}
+
+int ifem_insim_timer_ms(const ifem_insim *s, const char *section, double *ms)
+{
+  return guard([&] {
+    auto it = s->s->timer_ms.find(section);
+    *ms = it == s->s->timer_ms.end() ? 0.0 : it->second;
+  });
+}
+int ifem_insim_time(const ifem_insim *s, unsigned int *timestep, double *current)
+{
+  return guard([&] {
+    if (timestep) *timestep = s->s->time.get_timestep();
+    if (current) *current = s->s->time.current();
+  });
+}
+
+int ifem_insim_bench_vmult(ifem_insim *s, int reps, double *ms, double *bytes)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    DevBuf<double> y(m.fs.n_dofs);
+    *ms = time_reps(m.ctx, reps, [&] { block_vmult(m.ctx, m.fs, m.fs.rhs.p, y.p); });
+    *bytes = m.fs.A_uu.spmv_bytes() + m.fs.A_up.spmv_bytes() + m.fs.A_pu.spmv_bytes() + (m.fs.A_pp.n_brows ? m.fs.A_pp.spmv_bytes() : 0.0);
+  });
+}
+int ifem_insim_bench_spmv_uu(ifem_insim *s, int reps, double *ms, double *bytes)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    DevBuf<double> y(m.fs.n_u);
+    *ms = time_reps(m.ctx, reps, [&] { spmv(m.ctx, m.fs.A_uu, m.fs.rhs.p, y.p); });
+    *bytes = m.fs.A_uu.spmv_bytes();
+  });
+}
+int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    *ms = time_reps(m.ctx, reps, [&] { m.assemble(false); });
+  });
+}
+} // extern "C"

@@ -1,0 +1,861 @@
+#include "fluid.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace ifem
+{
+  // ===========================================================================
+  // Setup: setup_dofs + initialize_system (mpi_fluid_solver.cpp:116-162, 305-365)
+  // ===========================================================================
+  namespace
+  {
+    // slot of column node B in the sorted column list of block row A
+    __global__ void build_slots_kernel(int n_cells, int nr, int nc, const int *__restrict__ row_tab, const int *__restrict__ col_tab,
+                                       const int64_t *__restrict__ rowptr, const int *__restrict__ col,
+                                       unsigned char *__restrict__ slots, int stride, int offset, int *__restrict__ err)
+    {
+      const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      const int64_t total = (int64_t)n_cells * nr * nc;
+      if (t >= total) return;
+      const int cell = (int)(t / (nr * nc));
+      const int rem = (int)(t % (nr * nc));
+      const int a = rem / nc, b = rem % nc;
+      const int A = row_tab[(int64_t)cell * nr + a], B = col_tab[(int64_t)cell * nc + b];
+      const int64_t base = rowptr[A];
+      int lo = 0, hi = (int)(rowptr[A + 1] - base) - 1, j = -1;
+      while (lo <= hi)
+        {
+          const int mid = (lo + hi) >> 1;
+          const int c = col[base + mid];
+          if (c == B) { j = mid; break; }
+          if (c < B) lo = mid + 1; else hi = mid - 1;
+        }
+      if (j < 0 || j > 255) { atomicExch(err, 1); j = 0; }
+      slots[(int64_t)cell * stride + offset + rem] = (unsigned char)j;
+    }
+  } // namespace
+
+  void FluidSpace::setup(Context &ctx, const Triangulation &tria, int pu_, int pp_, bool with_App)
+  {
+    dim = tria.dim;
+    pu = pu_;
+    pp = pp_;
+    n_cells = tria.n_cells();
+    nv = 1 << dim;
+    fe_u = FEQ(dim, pu);
+    fe_p = FEQ(dim, pp);
+    fe_geo = FEQ(dim, 1);
+    nu = fe_u.n;
+    np = fe_p.n;
+    quad = Quadrature(dim, pu + 1);
+    nq = quad.nq;
+    tab_u = ShapeTable(fe_u, quad.points, nq);
+    tab_p = ShapeTable(fe_p, quad.points, nq);
+    tab_geo = ShapeTable(fe_geo, quad.points, nq);
+    un = build_node_table(tria, pu);
+    pn = build_node_table(tria, pp);
+    n_u = (int64_t)dim * un.n_nodes;
+    n_p = pn.n_nodes;
+    n_dofs = n_u + n_p;
+
+    P_uu = build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, un.cell_nodes.data(), nu, un.n_nodes);
+    P_up = build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes);
+    P_pu = build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, un.cell_nodes.data(), nu, un.n_nodes);
+    P_pp = build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes);
+    colour_cells(n_cells, un.cell_nodes.data(), nu, un.n_nodes, colour_order, colour_offsets);
+
+    cudaStream_t s = ctx.stream;
+    d_cell_un.upload(un.cell_nodes, s);
+    d_cell_pn.upload(pn.cell_nodes, s);
+    d_colour_order.upload(colour_order, s);
+    {
+      std::vector<double> cx((size_t)n_cells * nv * dim);
+      for (int c = 0; c < n_cells; ++c)
+        for (int v = 0; v < nv; ++v)
+          for (int d = 0; d < dim; ++d)
+            cx[((size_t)c * nv + v) * dim + d] = tria.vertices[(size_t)tria.cells[(size_t)c * nv + v] * dim + d];
+      d_cell_x.upload(cx, s);
+      IFEM_CUDA(cudaStreamSynchronize(s));
+    }
+    {
+      std::vector<double> t;
+      t.insert(t.end(), tab_u.N.begin(), tab_u.N.end());
+      t.insert(t.end(), tab_u.dN.begin(), tab_u.dN.end());
+      t.insert(t.end(), tab_p.N.begin(), tab_p.N.end());
+      t.insert(t.end(), tab_geo.dN.begin(), tab_geo.dN.end());
+      t.insert(t.end(), quad.weights.begin(), quad.weights.end());
+      d_tables.upload(t, s);
+      IFEM_CUDA(cudaStreamSynchronize(s));
+    }
+    A_uu.init(P_uu, dim, dim, s);
+    A_up.init(P_up, dim, 1, s);
+    A_pu.init(P_pu, 1, dim, s);
+    if (with_App) A_pp.init(P_pp, 1, 1, s);
+    M_p.init(P_pp, 1, 1, s);
+    diag_Mu.alloc(n_u);
+    rhs.alloc(n_dofs);
+    d_indicator.alloc(n_cells);
+    d_indicator.zero(s);
+
+    // per-cell slot tables
+    const int spc = slots_per_cell();
+    d_slots.alloc((size_t)n_cells * spc);
+    DevBuf<int> err(1);
+    err.zero(s);
+    auto launch = [&](int nr, int nc, const DevBuf<int> &rt, const DevBuf<int> &ct, const Bcsr &M, int offset) {
+      const int64_t total = (int64_t)n_cells * nr * nc;
+      const int threads = 256;
+      build_slots_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(n_cells, nr, nc, rt.p, ct.p, M.rowptr.p,
+                                                                                         M.col.p, d_slots.p, spc, offset, err.p);
+      IFEM_KERNEL_CHECK();
+    };
+    launch(nu, nu, d_cell_un, d_cell_un, A_uu, 0);
+    launch(nu, np, d_cell_un, d_cell_pn, A_up, nu * nu);
+    launch(np, nu, d_cell_pn, d_cell_un, A_pu, nu * nu + nu * np);
+    launch(np, np, d_cell_pn, d_cell_pn, M_p, nu * nu + 2 * nu * np);
+    if (err.to_host(s)[0]) throw std::runtime_error("FluidSpace::setup: a matrix row has more than 256 block columns");
+
+    P_schur = build_schur_pattern(tria, pn);
+    S_m.init(P_schur, 1, 1, s);
+
+    con.assign(n_dofs, 0);
+    nonzero_val.assign(n_dofs, 0.0);
+    d_con.upload(con, s);
+    d_nonzero_val.upload(nonzero_val, s);
+    IFEM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  void FluidSpace::make_constraints(Context &ctx, const Triangulation &tria,
+                                    const std::map<unsigned int, std::pair<unsigned int, std::vector<double>>> &dirichlet,
+                                    const std::function<bool(int, const double *, int, double &)> &hard_coded)
+  {
+    std::fill(con.begin(), con.end(), 0);
+    std::fill(nonzero_val.begin(), nonzero_val.end(), 0.0);
+    std::vector<std::vector<int>> face_nodes(2 * dim);
+    for (int f = 0; f < 2 * dim; ++f) face_nodes[f] = face_local_nodes(dim, pu, f);
+    // std::map iterates boundary ids in ascending order; a dof already constrained
+    // keeps its first value (VectorTools::interpolate_boundary_values semantics)
+    for (const auto &bc : dirichlet)
+      {
+        const int id = (int)bc.first;
+        const unsigned flag = bc.second.first;
+        double aug[3] = {0, 0, 0};
+        int k = 0;
+        for (int c = 0; c < dim; ++c)
+          if (flag & (1u << c)) aug[c] = bc.second.second.at(k++);
+        for (int f = 0; f < tria.n_boundary_faces(); ++f)
+          {
+            if (tria.boundary_faces[3 * f + 2] != id) continue;
+            const int cell = tria.boundary_faces[3 * f], face = tria.boundary_faces[3 * f + 1];
+            for (int a : face_nodes[face])
+              {
+                const int node = un.cell_nodes[(size_t)cell * nu + a];
+                for (int c = 0; c < dim; ++c)
+                  {
+                    if (!(flag & (1u << c))) continue;
+                    const int64_t g = (int64_t)dim * node + c;
+                    if (con[g]) continue;
+                    con[g] = 1;
+                    double v = aug[c];
+                    if (hard_coded) hard_coded(id, &un.coords[(size_t)node * dim], c, v);
+                    nonzero_val[g] = v;
+                  }
+              }
+          }
+      }
+    std::vector<int> idx;
+    for (int64_t g = 0; g < n_dofs; ++g)
+      if (con[g]) idx.push_back((int)g);
+    n_con = (int)idx.size();
+    cudaStream_t s = ctx.stream;
+    d_con.upload(con, s);
+    d_nonzero_val.upload(nonzero_val, s);
+    if (n_con) d_con_idx.upload(idx, s);
+    IFEM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  void FluidSpace::set_neumann_faces(Context &ctx, const Triangulation &tria, const std::map<unsigned int, double> &neumann)
+  {
+    std::vector<int> fc;
+    std::vector<double> fv;
+    for (int f = 0; f < tria.n_boundary_faces(); ++f)
+      {
+        auto it = neumann.find((unsigned)tria.boundary_faces[3 * f + 2]);
+        if (it == neumann.end()) continue;
+        fc.push_back(tria.boundary_faces[3 * f]);
+        fc.push_back(tria.boundary_faces[3 * f + 1]);
+        fv.push_back(it->second);
+      }
+    n_nfaces = (int)fv.size();
+    if (!n_nfaces) return;
+    // face quadrature QGauss<dim-1>(pu+1) placed on each of the 2*dim reference faces
+    Quadrature fq(dim - 1, pu + 1);
+    nqf = fq.nq;
+    std::vector<double> t;
+    std::vector<double> Nf((size_t)2 * dim * nqf * nu), Gf((size_t)2 * dim * nqf * nv * dim);
+    std::vector<double> N(nu), dN((size_t)nu * dim), g(nv), dg((size_t)nv * dim);
+    for (int face = 0; face < 2 * dim; ++face)
+      for (int q = 0; q < nqf; ++q)
+        {
+          double xi[3];
+          int k = 0;
+          for (int d = 0; d < dim; ++d) xi[d] = (d == face / 2) ? double(face % 2) : fq.points[(size_t)q * (dim - 1) + k++];
+          fe_u.eval(xi, N.data(), dN.data());
+          fe_geo.eval(xi, g.data(), dg.data());
+          std::copy(N.begin(), N.end(), Nf.begin() + ((size_t)face * nqf + q) * nu);
+          std::copy(dg.begin(), dg.end(), Gf.begin() + ((size_t)face * nqf + q) * nv * dim);
+        }
+    t.insert(t.end(), Nf.begin(), Nf.end());
+    t.insert(t.end(), Gf.begin(), Gf.end());
+    t.insert(t.end(), fq.weights.begin(), fq.weights.end());
+    cudaStream_t s = ctx.stream;
+    d_face_tables.upload(t, s);
+    d_nface_cell.upload(fc, s);
+    d_nface_val.upload(fv, s);
+    IFEM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  // ===========================================================================
+  // INS cell assembly kernel: one cell per warp, cells of one colour per launch
+  // (no two cells of a colour share a velocity node, so the scatter is a plain
+  // read-modify-write and the result is bitwise reproducible).
+  // ===========================================================================
+  namespace
+  {
+    template <int DIM>
+    struct InsT
+    {
+      static constexpr int NU = DIM == 2 ? 9 : 27;
+      static constexpr int NP = DIM == 2 ? 4 : 8;
+      static constexpr int NQ = NU;
+      static constexpr int NV = 1 << DIM;
+      static constexpr int DPC = NU * DIM + NP;
+      static constexpr int WARPS = DIM == 2 ? 8 : 5;
+      static constexpr int TAB = NQ * NU + NQ * NU * DIM + NQ * NP + NQ * NV * DIM + NQ; // doubles
+    };
+
+    template <int DIM>
+    struct WarpScratch
+    {
+      using T = InsT<DIM>;
+      double g[T::NQ][T::NU][DIM]; // physical gradients of the velocity shape functions
+      double ug[T::NQ][T::NU];     // u(q) . grad N_b(q)
+      double Jinv[T::NQ][DIM * DIM];
+      double JxW[T::NQ];
+      double u[T::NQ][DIM], G[T::NQ][DIM * DIM], p[T::NQ], du[T::NQ][DIM], acc[T::NQ][DIM], divu[T::NQ];
+      double Ue[T::NU][DIM], Up[T::NU][DIM], Ua[T::NU][DIM], Pe[T::NP];
+      double lrhs[T::DPC], ldiag[T::DPC], inh[T::DPC];
+      int con[T::DPC];
+      int un[T::NU], pn[T::NP];
+    };
+
+    struct BcsrView
+    {
+      const int64_t *rowptr;
+      double *val;
+    };
+
+    struct InsArgs
+    {
+      int n_list;
+      const int *cell_list;
+      const int *cell_un, *cell_pn;
+      const double *cell_x;
+      const double *tables;
+      const unsigned char *slots;
+      const double *eval_pt, *present, *fsi_acc;
+      const int *indicator;
+      int64_t n_u;
+      double mu, gamma, rho, inv_dt, grav[3];
+      const unsigned char *con;
+      const double *inhom; // null: homogeneous (zero_constraints)
+      BcsrView uu, up, pu, mp;
+      double *diag_Mu, *rhs;
+      int assemble_mass;
+    };
+
+    template <int DIM>
+    __device__ __forceinline__ void invert(const double *J, double *Ji, double &det)
+    {
+      if (DIM == 2)
+        {
+          det = J[0] * J[3] - J[1] * J[2];
+          const double d = 1.0 / det;
+          Ji[0] = J[3] * d; Ji[1] = -J[1] * d; Ji[2] = -J[2] * d; Ji[3] = J[0] * d;
+        }
+      else
+        {
+          const double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
+          det = J[0] * c00 + J[1] * c01 + J[2] * c02;
+          const double d = 1.0 / det;
+          Ji[0] = c00 * d; Ji[1] = (J[2] * J[7] - J[1] * J[8]) * d; Ji[2] = (J[1] * J[5] - J[2] * J[4]) * d;
+          Ji[3] = c01 * d; Ji[4] = (J[0] * J[8] - J[2] * J[6]) * d; Ji[5] = (J[2] * J[3] - J[0] * J[5]) * d;
+          Ji[6] = c02 * d; Ji[7] = (J[1] * J[6] - J[0] * J[7]) * d; Ji[8] = (J[0] * J[4] - J[1] * J[3]) * d;
+        }
+    }
+
+    template <int DIM>
+    __global__ void __launch_bounds__(InsT<DIM>::WARPS * 32) ins_assemble_kernel(const InsArgs a)
+    {
+      using T = InsT<DIM>;
+      constexpr int NU = T::NU, NP = T::NP, NQ = T::NQ, NV = T::NV;
+      extern __shared__ double smem[];
+      double *tN = smem;                    // [NQ][NU]
+      double *tdN = tN + NQ * NU;           // [NQ][NU][DIM]
+      double *tNp = tdN + NQ * NU * DIM;    // [NQ][NP]
+      double *tdG = tNp + NQ * NP;          // [NQ][NV][DIM]
+      double *tqw = tdG + NQ * NV * DIM;    // [NQ]
+      for (int i = threadIdx.x; i < T::TAB; i += blockDim.x) smem[i] = a.tables[i];
+      __syncthreads();
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      WarpScratch<DIM> &S = *reinterpret_cast<WarpScratch<DIM> *>(smem + ((T::TAB + 1) & ~1) + (size_t)warp * (sizeof(WarpScratch<DIM>) / 8));
+      const double mu = a.mu, rho = a.rho, gam_rho = a.gamma * a.rho, rho_dt = a.rho * a.inv_dt;
+      constexpr int SPC = NU * NU + 2 * NU * NP + NP * NP;
+
+      for (int li = blockIdx.x * T::WARPS + warp; li < a.n_list; li += gridDim.x * T::WARPS)
+        {
+          const int cell = a.cell_list[li];
+          const int ind = a.indicator ? a.indicator[cell] : 0;
+          // ---- phase 0: cell tables and local dof values ----
+          if (lane < NU) S.un[lane] = a.cell_un[(int64_t)cell * NU + lane];
+          if (lane < NP) S.pn[lane] = a.cell_pn[(int64_t)cell * NP + lane];
+          __syncwarp();
+          for (int i = lane; i < NU * DIM; i += 32)
+            {
+              const int b = i / DIM, c = i % DIM;
+              const int64_t g = (int64_t)DIM * S.un[b] + c;
+              S.Ue[b][c] = a.eval_pt[g];
+              S.Up[b][c] = a.present[g];
+              S.Ua[b][c] = (ind && a.fsi_acc) ? a.fsi_acc[g] : 0.0;
+              const int cf = a.con[g];
+              S.con[i] = cf;
+              S.inh[i] = (cf && a.inhom) ? a.inhom[g] : 0.0;
+              S.lrhs[i] = 0.0;
+              S.ldiag[i] = 0.0;
+            }
+          if (lane < NP)
+            {
+              const int64_t g = a.n_u + S.pn[lane];
+              S.Pe[lane] = a.eval_pt[g];
+              const int cf = a.con[g];
+              S.con[NU * DIM + lane] = cf;
+              S.inh[NU * DIM + lane] = (cf && a.inhom) ? a.inhom[g] : 0.0;
+              S.lrhs[NU * DIM + lane] = 0.0;
+              S.ldiag[NU * DIM + lane] = 0.0;
+            }
+          // ---- phase 1: geometry at the quadrature points (lane = q) ----
+          if (lane < NQ)
+            {
+              const int q = lane;
+              const double *X = a.cell_x + (int64_t)cell * NV * DIM;
+              double J[DIM * DIM];
+#pragma unroll
+              for (int i = 0; i < DIM * DIM; ++i) J[i] = 0.0;
+              for (int v = 0; v < NV; ++v)
+#pragma unroll
+                for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                  for (int j = 0; j < DIM; ++j) J[i * DIM + j] = fma(X[v * DIM + i], tdG[(q * NV + v) * DIM + j], J[i * DIM + j]);
+              double Ji[DIM * DIM], det;
+              invert<DIM>(J, Ji, det);
+#pragma unroll
+              for (int i = 0; i < DIM * DIM; ++i) S.Jinv[q][i] = Ji[i];
+              S.JxW[q] = det * tqw[q];
+            }
+          __syncwarp();
+          // ---- phase 2: physical gradients g[q][b][k] = sum_j dN[q][b][j] Jinv[j][k] (lane = b) ----
+          if (lane < NU)
+            for (int q = 0; q < NQ; ++q)
+              {
+                double r[DIM];
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) r[j] = tdN[(q * NU + lane) * DIM + j];
+#pragma unroll
+                for (int k = 0; k < DIM; ++k)
+                  {
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) s = fma(r[j], S.Jinv[q][j * DIM + k], s);
+                    S.g[q][lane][k] = s;
+                  }
+              }
+          __syncwarp();
+          // ---- phase 3: field values at q (lane = q): get_function_values / gradients (:219-232) ----
+          if (lane < NQ)
+            {
+              const int q = lane;
+              double u[DIM], up[DIM], ac[DIM], G[DIM * DIM], p = 0.0;
+#pragma unroll
+              for (int c = 0; c < DIM; ++c) u[c] = up[c] = ac[c] = 0.0;
+#pragma unroll
+              for (int i = 0; i < DIM * DIM; ++i) G[i] = 0.0;
+              for (int b = 0; b < NU; ++b)
+                {
+                  const double N = tN[q * NU + b];
+#pragma unroll
+                  for (int c = 0; c < DIM; ++c)
+                    {
+                      const double ue = S.Ue[b][c];
+                      u[c] = fma(N, ue, u[c]);
+                      up[c] = fma(N, S.Up[b][c], up[c]);
+                      ac[c] = fma(N, S.Ua[b][c], ac[c]);
+#pragma unroll
+                      for (int k = 0; k < DIM; ++k) G[c * DIM + k] = fma(ue, S.g[q][b][k], G[c * DIM + k]);
+                    }
+                }
+              for (int j = 0; j < NP; ++j) p = fma(tNp[q * NP + j], S.Pe[j], p);
+              double div = 0.0;
+#pragma unroll
+              for (int c = 0; c < DIM; ++c)
+                {
+                  S.u[q][c] = u[c];
+                  S.du[q][c] = u[c] - up[c];
+                  S.acc[q][c] = ac[c];
+                  div += G[c * DIM + c];
+                }
+#pragma unroll
+              for (int i = 0; i < DIM * DIM; ++i) S.G[q][i] = G[i];
+              S.p[q] = p;
+              S.divu[q] = div;
+            }
+          __syncwarp();
+          if (lane < NU)
+            for (int q = 0; q < NQ; ++q)
+              {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) s = fma(S.u[q][k], S.g[q][lane][k], s);
+                S.ug[q][lane] = s;
+              }
+          __syncwarp();
+          // ---- phase 4: local rhs (:281-304) and diag(M_u) (lane = a), pressure rows (lane = j) ----
+          if (lane < NU)
+            {
+              const int aN = lane;
+              double r[DIM], m = 0.0;
+#pragma unroll
+              for (int c = 0; c < DIM; ++c) r[c] = 0.0;
+              for (int q = 0; q < NQ; ++q)
+                {
+                  const double w = S.JxW[q], N = tN[q * NU + aN];
+                  m = fma(w * N, N, m);
+                  double ga[DIM];
+#pragma unroll
+                  for (int k = 0; k < DIM; ++k) ga[k] = S.g[q][aN][k];
+                  const double pd = S.p[q] - gam_rho * S.divu[q];
+#pragma unroll
+                  for (int c = 0; c < DIM; ++c)
+                    {
+                      double t = 0.0, conv = 0.0;
+#pragma unroll
+                      for (int k = 0; k < DIM; ++k)
+                        {
+                          t = fma(S.G[q][c * DIM + k], ga[k], t);         // grad u : grad phi_i
+                          conv = fma(S.G[q][c * DIM + k], S.u[q][k], conv); // (grad u) u
+                        }
+                      double v = -mu * t + pd * ga[c] + N * (-rho * conv - rho_dt * S.du[q][c] + rho * a.grav[c]);
+                      if (ind == 1) v += rho * S.acc[q][c] * N;
+                      r[c] = fma(w, v, r[c]);
+                    }
+                }
+#pragma unroll
+              for (int c = 0; c < DIM; ++c) S.lrhs[aN * DIM + c] = r[c];
+              if (a.assemble_mass)
+                {
+#pragma unroll
+                  for (int c = 0; c < DIM; ++c) a.diag_Mu[(int64_t)DIM * S.un[aN] + c] += m;
+                }
+            }
+          if (lane < NP)
+            {
+              double r = 0.0;
+              for (int q = 0; q < NQ; ++q) r = fma(S.JxW[q] * S.divu[q], tNp[q * NP + lane], r);
+              S.lrhs[NU * DIM + lane] = r;
+            }
+          __syncwarp();
+          const unsigned char *slots = a.slots + (int64_t)cell * SPC;
+          // ---- phase 5: velocity-velocity blocks (:263-273), lane = column node b, 3 row nodes per pass ----
+          {
+            const int b = lane < NU ? lane : NU - 1;
+            int cb[DIM];
+            double ib[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+              {
+                cb[d] = S.con[b * DIM + d];
+                ib[d] = S.inh[b * DIM + d];
+              }
+            constexpr int TA = 3;
+            for (int a0 = 0; a0 < NU; a0 += TA)
+              {
+                double K[TA][DIM * DIM];
+#pragma unroll
+                for (int t = 0; t < TA; ++t)
+#pragma unroll
+                  for (int i = 0; i < DIM * DIM; ++i) K[t][i] = 0.0;
+                for (int q = 0; q < NQ; ++q)
+                  {
+                    const double w = S.JxW[q];
+                    const double Nb = tN[q * NU + b], ugb = S.ug[q][b];
+                    double gb[DIM], wG[DIM * DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) gb[k] = S.g[q][b][k];
+#pragma unroll
+                    for (int i = 0; i < DIM * DIM; ++i) wG[i] = w * rho * S.G[q][i];
+                    const double c1 = w * rho * ugb, c2 = w * rho_dt * Nb;
+#pragma unroll
+                    for (int t = 0; t < TA; ++t)
+                      {
+                        const int aN = a0 + t;
+                        const double Na = tN[q * NU + aN];
+                        double ga[DIM];
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) ga[k] = S.g[q][aN][k];
+                        double gg = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) gg = fma(ga[k], gb[k], gg);
+                        const double s = fma(w * mu, gg, Na * (c1 + c2));
+                        const double NaNb = Na * Nb;
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c)
+                          {
+                            const double wga = w * gam_rho * ga[c];
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d)
+                              {
+                                double v = fma(NaNb, wG[c * DIM + d], wga * gb[d]);
+                                if (c == d) v += s;
+                                K[t][c * DIM + d] += v;
+                              }
+                          }
+                      }
+                  }
+                // scatter the TA x (DIM x DIM) blocks of this lane
+#pragma unroll
+                for (int t = 0; t < TA; ++t)
+                  {
+                    const int aN = a0 + t;
+                    const int A = S.un[aN];
+                    const int64_t rp = a.uu.rowptr[A];
+                    const int nb = (int)(a.uu.rowptr[A + 1] - rp);
+                    double *base = a.uu.val + rp * (DIM * DIM);
+                    const int slot = slots[aN * NU + b];
+                    double corr[DIM];
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) corr[c] = 0.0;
+                    if (lane < NU)
+                      {
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c)
+                          {
+                            const int rc = S.con[aN * DIM + c];
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d)
+                              {
+                                const double v = K[t][c * DIM + d];
+                                if (rc)
+                                  {
+                                    if (b == aN && c == d)
+                                      {
+                                        base[(int64_t)(c * DIM + d) * nb + slot] += fabs(v);
+                                        S.ldiag[aN * DIM + c] = fabs(v);
+                                      }
+                                  }
+                                else if (cb[d])
+                                  corr[c] = fma(v, ib[d], corr[c]);
+                                else
+                                  base[(int64_t)(c * DIM + d) * nb + slot] += v;
+                              }
+                          }
+                      }
+                    if (a.inhom)
+                      {
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c)
+                          {
+                            const double sc = warp_sum(corr[c]);
+                            if (lane == 0) S.lrhs[aN * DIM + c] -= sc;
+                          }
+                      }
+                  }
+              }
+          }
+          __syncwarp();
+          // ---- phase 6: velocity-pressure coupling  -div(phi_i) psi_j  and its transpose (lane = a) ----
+          if (lane < NU)
+            {
+              const int aN = lane;
+              double B[NP][DIM];
+#pragma unroll
+              for (int j = 0; j < NP; ++j)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) B[j][c] = 0.0;
+              for (int q = 0; q < NQ; ++q)
+                {
+                  const double w = -S.JxW[q];
+                  double ga[DIM];
+#pragma unroll
+                  for (int k = 0; k < DIM; ++k) ga[k] = w * S.g[q][aN][k];
+#pragma unroll
+                  for (int j = 0; j < NP; ++j)
+                    {
+                      const double psi = tNp[q * NP + j];
+#pragma unroll
+                      for (int c = 0; c < DIM; ++c) B[j][c] = fma(ga[c], psi, B[j][c]);
+                    }
+                }
+              const int A = S.un[aN];
+              const int64_t rp = a.up.rowptr[A];
+              const int nb = (int)(a.up.rowptr[A + 1] - rp);
+              double *base = a.up.val + rp * DIM;
+              const unsigned char *s_up = slots + NU * NU;
+              const unsigned char *s_pu = slots + NU * NU + NU * NP;
+#pragma unroll
+              for (int j = 0; j < NP; ++j)
+                {
+                  const int slot = s_up[aN * NP + j];
+                  const int pc = S.con[NU * DIM + j];
+                  // row = pressure node j, column = velocity node a
+                  const int Pn = S.pn[j];
+                  const int64_t rq = a.pu.rowptr[Pn];
+                  const int nbq = (int)(a.pu.rowptr[Pn + 1] - rq);
+                  double *baseq = a.pu.val + rq * DIM;
+                  const int slotq = s_pu[j * NU + aN];
+#pragma unroll
+                  for (int c = 0; c < DIM; ++c)
+                    {
+                      const int uc = S.con[aN * DIM + c];
+                      const double v = B[j][c];
+                      if (!uc && !pc)
+                        {
+                          base[(int64_t)c * nb + slot] += v;    // A_up block row a, plane c
+                          baseq[(int64_t)c * nbq + slotq] += v; // A_pu row j, plane c
+                        }
+                      else if (uc && !pc && a.inhom)
+                        atomicAdd(&S.lrhs[NU * DIM + j], -v * S.inh[aN * DIM + c]); // column (a,c) constrained
+                    }
+                }
+            }
+          __syncwarp();
+          // ---- phase 7: pressure mass matrix (:274-276) ----
+          if (a.assemble_mass)
+            for (int e = lane; e < NP * NP; e += 32)
+              {
+                const int i = e / NP, j = e % NP;
+                double m = 0.0;
+                for (int q = 0; q < NQ; ++q) m = fma(S.JxW[q] * tNp[q * NP + i], tNp[q * NP + j], m);
+                const int Pn = S.pn[i];
+                const int64_t rp = a.mp.rowptr[Pn];
+                a.mp.val[rp + slots[NU * NU + 2 * NU * NP + e]] += m;
+              }
+          __syncwarp();
+          // ---- scatter local rhs through the constraints (distribute_local_to_global) ----
+          for (int i = lane; i < T::DPC; i += 32)
+            {
+              const int64_t g = i < NU * DIM ? (int64_t)DIM * S.un[i / DIM] + i % DIM : a.n_u + S.pn[i - NU * DIM];
+              if (!S.con[i])
+                a.rhs[g] += S.lrhs[i];
+              else if (a.inhom)
+                a.rhs[g] += S.ldiag[i] * S.inh[i];
+            }
+          __syncwarp();
+        }
+    }
+
+    // Pressure Neumann faces (:313-341): rhs_i -= phi_i . n  p  JxW_face on unconstrained rows.
+    template <int DIM>
+    __global__ void ins_neumann_kernel(int n_faces, int nqf, const int *__restrict__ face_cell, const double *__restrict__ face_val,
+                                       const double *__restrict__ ftab, const int *__restrict__ cell_un,
+                                       const double *__restrict__ cell_x, const unsigned char *__restrict__ con,
+                                       double *__restrict__ rhs)
+    {
+      using T = InsT<DIM>;
+      constexpr int NU = T::NU, NV = T::NV;
+      const int f = blockIdx.x;
+      if (f >= n_faces) return;
+      const int cell = face_cell[2 * f], face = face_cell[2 * f + 1];
+      const int axis = face / 2, side = face % 2;
+      const double pbar = face_val[f];
+      const double *Nf = ftab;
+      const double *Gf = ftab + (size_t)2 * DIM * nqf * NU;
+      const double *qwf = Gf + (size_t)2 * DIM * nqf * NV * DIM;
+      const double *X = cell_x + (int64_t)cell * NV * DIM;
+      for (int i = threadIdx.x; i < NU * DIM; i += blockDim.x)
+        {
+          const int node = i / DIM, c = i % DIM;
+          double r = 0.0;
+          for (int q = 0; q < nqf; ++q)
+            {
+              const size_t fq = (size_t)face * nqf + q;
+              double J[DIM * DIM], Ji[DIM * DIM], det;
+              for (int k = 0; k < DIM * DIM; ++k) J[k] = 0.0;
+              for (int v = 0; v < NV; ++v)
+                for (int ii = 0; ii < DIM; ++ii)
+                  for (int jj = 0; jj < DIM; ++jj) J[ii * DIM + jj] = fma(X[v * DIM + ii], Gf[(fq * NV + v) * DIM + jj], J[ii * DIM + jj]);
+              invert<DIM>(J, Ji, det);
+              // n dS = det(J) J^{-T} n_ref
+              const double nds = det * Ji[axis * DIM + c] * (side ? 1.0 : -1.0) * qwf[q];
+              r -= Nf[fq * NU + node] * nds * pbar;
+            }
+          const int64_t g = (int64_t)DIM * cell_un[(int64_t)cell * NU + node] + c;
+          if (!con[g] && r != 0.0) atomicAdd(&rhs[g], r);
+        }
+    }
+  } // namespace
+
+  template <int DIM>
+  static void ins_assemble_dim(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt,
+                               const double *present, const double *fsi_acc, bool use_nonzero, bool assemble_mass)
+  {
+    using T = InsT<DIM>;
+    if (fs.nu != T::NU || fs.np != T::NP) throw std::runtime_error("ins_assemble: only Q2/Q1 elements are supported");
+    cudaStream_t s = ctx.stream;
+    fs.A_uu.zero(s);
+    fs.A_up.zero(s);
+    fs.A_pu.zero(s);
+    fs.rhs.zero(s);
+    if (assemble_mass)
+      {
+        fs.M_p.zero(s);
+        fs.diag_Mu.zero(s);
+      }
+    InsArgs a;
+    a.cell_un = fs.d_cell_un.p;
+    a.cell_pn = fs.d_cell_pn.p;
+    a.cell_x = fs.d_cell_x.p;
+    a.tables = fs.d_tables.p;
+    a.slots = fs.d_slots.p;
+    a.eval_pt = eval_pt;
+    a.present = present;
+    a.fsi_acc = fsi_acc;
+    a.indicator = fs.d_indicator.p;
+    a.n_u = fs.n_u;
+    a.mu = prm.viscosity;
+    a.gamma = prm.gamma;
+    a.rho = prm.rho;
+    a.inv_dt = 1.0 / prm.dt;
+    for (int d = 0; d < 3; ++d) a.grav[d] = prm.gravity[d];
+    a.con = fs.d_con.p;
+    a.inhom = use_nonzero ? fs.d_nonzero_val.p : nullptr;
+    a.uu = {fs.A_uu.rowptr.p, fs.A_uu.val.p};
+    a.up = {fs.A_up.rowptr.p, fs.A_up.val.p};
+    a.pu = {fs.A_pu.rowptr.p, fs.A_pu.val.p};
+    a.mp = {fs.M_p.rowptr.p, fs.M_p.val.p};
+    a.diag_Mu = fs.diag_Mu.p;
+    a.rhs = fs.rhs.p;
+    a.assemble_mass = assemble_mass ? 1 : 0;
+    const size_t smem = (size_t)((T::TAB + 1) & ~1) * 8 + (size_t)T::WARPS * sizeof(WarpScratch<DIM>);
+    static bool attr_set[4] = {false, false, false, false};
+    if (!attr_set[DIM])
+      {
+        IFEM_CUDA(cudaFuncSetAttribute(ins_assemble_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[DIM] = true;
+      }
+    const int n_colours = (int)fs.colour_offsets.size() - 1;
+    for (int k = 0; k < n_colours; ++k)
+      {
+        a.n_list = fs.colour_offsets[k + 1] - fs.colour_offsets[k];
+        a.cell_list = fs.d_colour_order.p + fs.colour_offsets[k];
+        if (a.n_list == 0) continue;
+        const int blocks = std::min((a.n_list + T::WARPS - 1) / T::WARPS, ctx.sm_count * (DIM == 2 ? 4 : 1));
+        ins_assemble_kernel<DIM><<<blocks, T::WARPS * 32, smem, s>>>(a);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+    if (fs.n_nfaces)
+      {
+        ins_neumann_kernel<DIM><<<fs.n_nfaces, 64, 0, s>>>(fs.n_nfaces, fs.nqf, fs.d_nface_cell.p, fs.d_nface_val.p,
+                                                           fs.d_face_tables.p, fs.d_cell_un.p, fs.d_cell_x.p, fs.d_con.p, fs.rhs.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+  }
+
+  void ins_assemble(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt, const double *present,
+                    const double *fsi_acc, bool use_nonzero_constraints, bool assemble_mass)
+  {
+    if (fs.dim == 2)
+      ins_assemble_dim<2>(ctx, fs, prm, eval_pt, present, fsi_acc, use_nonzero_constraints, assemble_mass);
+    else
+      ins_assemble_dim<3>(ctx, fs, prm, eval_pt, present, fsi_acc, use_nonzero_constraints, assemble_mass);
+  }
+
+  void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y)
+  {
+    spmv(ctx, fs.A_uu, x, y, false);
+    spmv(ctx, fs.A_up, x + fs.n_u, y, true);
+    spmv(ctx, fs.A_pu, x, y + fs.n_u, false);
+    if (fs.A_pp.n_brows) spmv(ctx, fs.A_pp, x + fs.n_u, y + fs.n_u, true);
+  }
+
+  // ===========================================================================
+  // S_m = B diag(M_u)^-1 B^T, B = A_pu, B^T = A_up (mpi_insim.cpp:44-49), numeric
+  // phase on the fixed pattern: one warp per pressure row, accumulation in shared
+  // memory, slots located by binary search in the (sorted) Schur row.
+  // ===========================================================================
+  namespace
+  {
+    template <int DIM>
+    __global__ void __launch_bounds__(128) mass_schur_kernel(int n_p, const int64_t *__restrict__ pu_rp, const int *__restrict__ pu_col,
+                                                             const double *__restrict__ pu_val, const int64_t *__restrict__ up_rp,
+                                                             const int *__restrict__ up_col, const double *__restrict__ up_val,
+                                                             const double *__restrict__ diag_Mu, const int64_t *__restrict__ s_rp,
+                                                             const int *__restrict__ s_col, double *__restrict__ s_val)
+    {
+      __shared__ double acc[4][256];
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int row = blockIdx.x * 4 + warp;
+      if (row >= n_p) return;
+      const int64_t sb = s_rp[row];
+      const int sn = (int)(s_rp[row + 1] - sb);
+      for (int i = lane; i < sn; i += 32) acc[warp][i] = 0.0;
+      __syncwarp();
+      const int64_t rb = pu_rp[row];
+      const int rn = (int)(pu_rp[row + 1] - rb);
+      // lanes walk the velocity nodes k of B's row; each visits the B^T rows of (k, d)
+      for (int jk = lane; jk < rn; jk += 32)
+        {
+          const int k = pu_col[rb + jk];
+          const int64_t ub = up_rp[k];
+          const int un = (int)(up_rp[k + 1] - ub);
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+            {
+              const double bkd = pu_val[rb * DIM + (int64_t)d * rn + jk] / diag_Mu[(int64_t)DIM * k + d];
+              if (bkd == 0.0) continue;
+              for (int m = 0; m < un; ++m)
+                {
+                  const int pj = up_col[ub + m];
+                  const double v = bkd * up_val[ub * DIM + (int64_t)d * un + m];
+                  int lo = 0, hi = sn - 1;
+                  while (lo < hi)
+                    {
+                      const int mid = (lo + hi) >> 1;
+                      if (s_col[sb + mid] < pj) lo = mid + 1; else hi = mid;
+                    }
+                  atomicAdd(&acc[warp][lo], v);
+                }
+            }
+        }
+      __syncwarp();
+      for (int i = lane; i < sn; i += 32) s_val[sb + i] = acc[warp][i];
+    }
+  } // namespace
+
+  void compute_mass_schur(Context &ctx, FluidSpace &fs)
+  {
+    const int n_p = (int)fs.n_p;
+    const int blocks = (n_p + 3) / 4;
+    auto go = [&](auto tag) {
+      constexpr int DIM = decltype(tag)::value;
+      mass_schur_kernel<DIM><<<blocks, 128, 0, ctx.stream>>>(n_p, fs.A_pu.rowptr.p, fs.A_pu.col.p, fs.A_pu.val.p, fs.A_up.rowptr.p,
+                                                             fs.A_up.col.p, fs.A_up.val.p, fs.diag_Mu.p, fs.S_m.rowptr.p,
+                                                             fs.S_m.col.p, fs.S_m.val.p);
+    };
+    if (fs.dim == 2) go(std::integral_constant<int, 2>()); else go(std::integral_constant<int, 3>());
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+  }
+} // namespace ifem

@@ -1,0 +1,93 @@
+// Device-resident state of Fluid::MPI::FluidSolver<dim> (reference
+// include/mpi_fluid_solver.h:185-287, source/mpi_fluid_solver.cpp:116-365): FE
+// space, DoF numbering, Dirichlet constraints, sparsity patterns and the block
+// matrices / vectors the assembly kernels write and the Krylov loop reads.
+//
+// DoF layout (one rank): velocity block node-major, u dof = dim*node + c; pressure
+// block behind it, p dof = n_u + pnode (block structure [u | p] as produced by
+// DoFRenumbering::component_wise with block_component = {0,..,0,1},
+// mpi_fluid_solver.cpp:125-138). The 2x2 block system is stored as four BCSR
+// matrices on NODE patterns: A_uu (dim x dim blocks), A_up (dim x 1), A_pu (1 x dim),
+// A_pp (1 x 1, only allocated for the slightly compressible solver). Of the
+// reference's full-pattern mass_matrix only what is ever read is stored:
+// diag(M_u) and M_p (mpi_insim.cpp:44, 80-82).
+#pragma once
+#include <memory>
+
+#include "fe_tables.h"
+#include "linalg.h"
+#include "mesh.h"
+#include "parameters.h"
+
+namespace ifem
+{
+  struct FluidSpace
+  {
+    int dim = 0, pu = 0, pp = 0;
+    int nu = 0, np = 0, nq = 0, nv = 0; // per cell: velocity nodes, pressure nodes, quadrature points, vertices
+    int n_cells = 0;
+    NodeTable un, pn;
+    int64_t n_u = 0, n_p = 0, n_dofs = 0;
+
+    // host FE tables (kept for face terms and point evaluation)
+    FEQ fe_u, fe_p, fe_geo;
+    Quadrature quad;
+    ShapeTable tab_u, tab_p, tab_geo;
+
+    // host patterns
+    Pattern P_uu, P_up, P_pu, P_pp, P_schur;
+    std::vector<int> colour_order, colour_offsets;
+
+    // constraints (host mirror): flag per dof, nonzero value per dof
+    std::vector<unsigned char> con;
+    std::vector<double> nonzero_val;
+
+    // ---- device ----
+    DevBuf<int> d_cell_un, d_cell_pn, d_colour_order;
+    DevBuf<double> d_cell_x;  // [n_cells][nv][dim]
+    DevBuf<double> d_tables;  // N[nq][nu] | dN[nq][nu][dim] | Np[nq][np] | dNgeo[nq][nv][dim] | qw[nq]
+    DevBuf<unsigned char> d_slots; // per cell: uu[nu][nu] | up[nu][np] | pu[np][nu] | pp[np][np]
+    DevBuf<unsigned char> d_con;
+    DevBuf<double> d_nonzero_val;
+    DevBuf<int> d_con_idx; // list of constrained dofs
+    int n_con = 0;
+    DevBuf<int> d_indicator; // CellProperty::indicator
+    // boundary faces carrying a pressure Neumann condition: (cell, face_no) + value
+    DevBuf<int> d_nface_cell;
+    DevBuf<double> d_nface_val;
+    DevBuf<double> d_face_tables; // per face: Nu_face[2*dim][nqf][nu] | dNgeo_face[2*dim][nqf][nv][dim] | qwf[nqf]
+    int n_nfaces = 0, nqf = 0;
+
+    Bcsr A_uu, A_up, A_pu, A_pp, M_p, S_m;
+    DevBuf<double> diag_Mu; // [n_u]
+    DevBuf<double> rhs;     // [n_dofs]
+
+    int slots_per_cell() const { return nu * nu + 2 * nu * np + np * np; }
+
+    void setup(Context &ctx, const Triangulation &tria, int pu, int pp, bool with_App);
+    // Dirichlet constraints from the .prm maps, "first boundary id wins"
+    // (mpi_fluid_solver.cpp:165-280). hard_coded(id, point, component) may be null.
+    void make_constraints(Context &ctx, const Triangulation &tria,
+                          const std::map<unsigned int, std::pair<unsigned int, std::vector<double>>> &dirichlet,
+                          const std::function<bool(int, const double *, int, double &)> &hard_coded);
+    void set_neumann_faces(Context &ctx, const Triangulation &tria, const std::map<unsigned int, double> &neumann);
+  };
+
+  struct InsAssembleParams
+  {
+    double viscosity, gamma, rho, dt;
+    double gravity[3];
+  };
+
+  // Fluid::MPI::InsIM<dim>::assemble (reference source/mpi_insim.cpp:152-362).
+  // eval_pt / present / fsi_acc are block vectors of n_dofs doubles on the device;
+  // fills A_uu, A_up, A_pu, M_p, diag_Mu, rhs of the space.
+  void ins_assemble(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt, const double *present,
+                    const double *fsi_acc, bool use_nonzero_constraints, bool assemble_mass);
+
+  // y = A x on the 2x2 block system (BlockSparseMatrix::vmult)
+  void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y);
+
+  // S_m = B diag(M_u)^-1 B^T on the fixed Schur pattern (mpi_insim.cpp:44-49)
+  void compute_mass_schur(Context &ctx, FluidSpace &fs);
+} // namespace ifem

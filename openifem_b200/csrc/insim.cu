@@ -1,0 +1,205 @@
+#include "insim.h"
+
+#include <chrono>
+#include <cstdio>
+
+namespace ifem
+{
+  namespace
+  {
+    struct ScopedTimer
+    {
+      Context &ctx;
+      double &acc;
+      std::chrono::steady_clock::time_point t0;
+      ScopedTimer(Context &c, double &a) : ctx(c), acc(a)
+      {
+        cudaStreamSynchronize(ctx.stream);
+        t0 = std::chrono::steady_clock::now();
+      }
+      ~ScopedTimer()
+      {
+        cudaStreamSynchronize(ctx.stream);
+        acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      }
+    };
+  } // namespace
+
+  InsIM::InsIM(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params)
+    : ctx(ctx_), triangulation(tria), parameters(params),
+      time(params.end_time, params.time_step, params.output_interval, params.refinement_interval, params.save_interval)
+  {
+    // mpi_insim.cpp:135-139
+    if (parameters.fluid_velocity_degree - parameters.fluid_pressure_degree != 1)
+      throw std::runtime_error("Velocity finite element should be one order higher than pressure!");
+    if (parameters.fluid_velocity_degree != 2) throw std::runtime_error("InsIM: only Q2/Q1 is implemented on the device");
+  }
+
+  void InsIM::add_hard_coded_boundary_condition(int id, std::function<double(const double *, unsigned int, double)> f)
+  {
+    hard_coded[id] = std::move(f);
+  }
+
+  void InsIM::setup_dofs()
+  {
+    fs.setup(ctx, triangulation, (int)parameters.fluid_velocity_degree, (int)parameters.fluid_pressure_degree, false);
+    dofs_ready = true;
+  }
+
+  void InsIM::make_constraints()
+  {
+    std::function<bool(int, const double *, int, double &)> hc;
+    if (!hard_coded.empty())
+      hc = [this](int id, const double *pt, int c, double &v) {
+        auto it = hard_coded.find(id);
+        if (it == hard_coded.end()) return false;
+        v = it->second(pt, (unsigned)c, time.current());
+        return true;
+      };
+    fs.make_constraints(ctx, triangulation, parameters.fluid_dirichlet_bcs, hc);
+    fs.set_neumann_faces(ctx, triangulation, parameters.fluid_neumann_bcs);
+    std::vector<double> vals(fs.n_con);
+    int k = 0;
+    for (int64_t g = 0; g < fs.n_dofs; ++g)
+      if (fs.con[g]) vals[k++] = fs.nonzero_val[g];
+    if (fs.n_con) d_con_vals.upload(vals, ctx.stream);
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void InsIM::initialize_system()
+  {
+    const int64_t n = fs.n_dofs;
+    for (DevBuf<double> *v : {&present_solution, &evaluation_point, &solution_increment, &newton_update, &fsi_acceleration})
+      {
+        v->alloc(n);
+        v->zero(ctx.stream);
+      }
+    d_binv.alloc((size_t)fs.un.n_nodes * fs.dim * fs.dim);
+    d_tmp_p.alloc(fs.n_p);
+    d_utmp.alloc(fs.n_u);
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void InsIM::assemble(bool use_nonzero_constraints)
+  {
+    ScopedTimer t(ctx, timer_ms["Assemble system"]);
+    InsAssembleParams p;
+    p.viscosity = parameters.viscosity;
+    p.gamma = parameters.grad_div;
+    p.rho = parameters.fluid_rho;
+    p.dt = time.get_delta_t();
+    for (int d = 0; d < 3; ++d) p.gravity[d] = d < (int)parameters.gravity.size() ? parameters.gravity[d] : 0.0;
+    ins_assemble(ctx, fs, p, evaluation_point.p, present_solution.p, fsi_acceleration.p, use_nonzero_constraints, true);
+  }
+
+  // BlockSchurPreconditioner::vmult (mpi_insim.cpp:56-128)
+  void InsIM::precondition(const double *src, double *dst)
+  {
+    const int64_t n_u = fs.n_u, n_p = fs.n_p;
+    const double *src_u = src, *src_p = src + n_u;
+    double *dst_u = dst, *dst_p = dst + n_u;
+    double *tmp = d_tmp_p.p, *utmp = d_utmp.p;
+    const double nrm = nrm2(ctx, n_p, src_p);
+    {
+      ScopedTimer t(ctx, timer_ms["CG for Mp"]);
+      fill(ctx, n_p, 0.0, tmp);
+      LinOp Mp = [&](const double *x, double *y) { spmv(ctx, fs.M_p, x, y); };
+      const SolveResult r = cg(ctx, n_p, Mp, src_p, tmp, true, std::max(control.cg_floor, control.cg_mp_rel * nrm), (int)n_p, pool_cg);
+      cur.cg_mp_its += r.iterations;
+      scale(ctx, n_p, -(parameters.viscosity + parameters.grad_div * parameters.fluid_rho), tmp);
+    }
+    {
+      ScopedTimer t(ctx, timer_ms["CG for Sm"]);
+      fill(ctx, n_p, 0.0, dst_p);
+      LinOp Sm = [&](const double *x, double *y) { spmv(ctx, fs.S_m, x, y); };
+      const SolveResult r = cg(ctx, n_p, Sm, src_p, dst_p, true, std::max(control.cg_floor, control.cg_sm_rel * nrm), (int)n_p, pool_cg);
+      cur.cg_sm_its += r.iterations;
+      // dst_p = -rho/dt * dst_p + tmp
+      axpby(ctx, n_p, 1.0, tmp, -parameters.fluid_rho / time.get_delta_t(), dst_p);
+    }
+    // utmp = src_u - B^T dst_p
+    spmv(ctx, fs.A_up, dst_p, utmp);
+    axpby(ctx, n_u, 1.0, src_u, -1.0, utmp);
+    {
+      ScopedTimer t(ctx, timer_ms["A_inv"]);
+      LinOp Auu = [&](const double *x, double *y) { spmv(ctx, fs.A_uu, x, y); };
+      LinOp jac = [&](const double *x, double *y) { block_diag_apply(ctx, fs.un.n_nodes, fs.dim, d_binv.p, x, y); };
+      const double unrm = nrm2(ctx, n_u, utmp);
+      const SolveResult r = bicgstab(ctx, n_u, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);
+      cur.a_inv_its += r.iterations;
+    }
+    cur.precond_applies++;
+  }
+
+  std::pair<unsigned int, double> InsIM::solve(bool use_nonzero_constraints)
+  {
+    ScopedTimer t(ctx, timer_ms["Solve linear system"]);
+    // BlockSchurPreconditioner ctor (mpi_insim.cpp:13-50)
+    compute_mass_schur(ctx, fs);
+    block_diag_inverse(ctx, fs.A_uu, d_binv.p);
+    const int64_t n = fs.n_dofs;
+    const double nrm = nrm2(ctx, n, fs.rhs.p);
+    const double tol = control.fgmres_floor_is_max ? std::max(control.fgmres_floor, control.fgmres_rel * nrm)
+                                                   : std::max(control.fgmres_floor, control.fgmres_rel * nrm);
+    LinOp A = [&](const double *x, double *y) { block_vmult(ctx, fs, x, y); };
+    LinOp P = [&](const double *x, double *y) { precondition(x, y); };
+    const SolveResult r = fgmres(ctx, n, A, P, fs.rhs.p, newton_update.p, tol, n, control.basis_size, pool_fgmres);
+    // constraints_used.distribute(newton_update)
+    if (fs.n_con) set_indexed(ctx, fs.n_con, fs.d_con_idx.p, use_nonzero_constraints ? d_con_vals.p : nullptr, newton_update.p);
+    return {(unsigned)r.iterations, r.residual};
+  }
+
+  void InsIM::run_one_step(bool apply_nonzero_constraints, bool /*assemble_system*/)
+  {
+    time.increment();
+    if (verbose)
+      std::printf("%s\nTime step = %u, at t = %e\n", std::string(96, '*').c_str(), time.get_timestep(), time.current());
+    double current_residual = 1.0, initial_residual = 1.0, relative_residual = 1.0;
+    unsigned int outer_iteration = 0;
+    const int64_t n = fs.n_dofs;
+    copy(ctx, n, present_solution.p, evaluation_point.p);
+    while (relative_residual > parameters.fluid_tolerance && current_residual > 1e-11)
+      {
+        if (outer_iteration >= parameters.fluid_max_iterations) throw std::runtime_error("Too many Newton iterations!");
+        fill(ctx, n, 0.0, newton_update.p);
+        cur = NewtonRecord{};
+        const bool nz = apply_nonzero_constraints && outer_iteration == 0;
+        assemble(nz);
+        const auto state = solve(nz);
+        current_residual = nrm2(ctx, n, fs.rhs.p);
+        axpy(ctx, n, 1.0, newton_update.p, evaluation_point.p);
+        if (outer_iteration == 0) initial_residual = current_residual;
+        relative_residual = current_residual / initial_residual;
+        cur.timestep = time.get_timestep();
+        cur.iteration = outer_iteration;
+        cur.abs_res = current_residual;
+        cur.rel_res = relative_residual;
+        cur.gmres_its = (int)state.first;
+        cur.gmres_res = state.second;
+        history.push_back(cur);
+        if (verbose)
+          std::printf(" ITR = %-2u ABS_RES = %e REL_RES = %e GMRES_ITR = %-3u GMRES_RES = %e  [cg_mp %d cg_sm %d a_inv %d / %d]\n",
+                      outer_iteration, current_residual, relative_residual, state.first, state.second, cur.cg_mp_its,
+                      cur.cg_sm_its, cur.a_inv_its, cur.precond_applies);
+        outer_iteration++;
+      }
+    // solution_increment = present - evaluation_point ; present = evaluation_point
+    lin3(ctx, n, solution_increment.p, present_solution.p, -1.0, evaluation_point.p, 0.0, evaluation_point.p);
+    copy(ctx, n, evaluation_point.p, present_solution.p);
+  }
+
+  void InsIM::run()
+  {
+    if (!dofs_ready)
+      {
+        triangulation.refine_global(parameters.global_refinements.empty() ? 0 : parameters.global_refinements[0]);
+        setup_dofs();
+        make_constraints();
+        initialize_system();
+      }
+    run_one_step(true);
+    while (time.end() - time.current() > 1e-12) run_one_step(false);
+  }
+
+  std::vector<double> InsIM::get_current_solution() { return present_solution.to_host(ctx.stream); }
+} // namespace ifem

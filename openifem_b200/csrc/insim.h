@@ -1,0 +1,116 @@
+// Fluid::MPI::InsIM<dim> on the device (reference include/mpi_insim.h:42-194,
+// source/mpi_insim.cpp): implicit incompressible Navier-Stokes, Newton iteration
+// with grad-div stabilisation, FGMRES + block Schur preconditioner. The class keeps
+// the reference's method names; dimension is a run-time property of the
+// triangulation (the templated facade in include/openifem/ instantiates <2>/<3>).
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "fluid.h"
+#include "krylov.h"
+
+namespace ifem
+{
+  // Utils::Time (reference include/utilities.h:27-63, source/utilities.cpp:6-36)
+  class Time
+  {
+  public:
+    Time(double time_end, double delta_t, double output_interval, double refinement_interval, double save_interval)
+      : timestep(0), time_current(0.0), delta_t(delta_t), time_end(time_end), output_interval(output_interval),
+        refinement_interval(refinement_interval), save_interval(save_interval)
+    {
+    }
+    double current() const { return time_current; }
+    double end() const { return time_end; }
+    double get_delta_t() const { return delta_t; }
+    unsigned int get_timestep() const { return timestep; }
+    bool time_to_output() const { return due(output_interval); }
+    bool time_to_refine() const { return due(refinement_interval); }
+    bool time_to_save() const { return due(save_interval); }
+    void increment() { time_current += delta_t; ++timestep; }
+    void decrement() { time_current -= delta_t; --timestep; }
+    void set_delta_t(double d) { delta_t = d; }
+
+  private:
+    bool due(double interval) const
+    {
+      const auto delta = static_cast<unsigned int>(interval / delta_t);
+      return delta != 0 && timestep >= delta && timestep % delta == 0;
+    }
+    unsigned int timestep;
+    double time_current, delta_t;
+    const double time_end, output_interval, refinement_interval, save_interval;
+  };
+
+  struct NewtonRecord
+  {
+    unsigned int timestep, iteration;
+    double abs_res, rel_res;
+    int gmres_its;
+    double gmres_res;
+    int cg_mp_its, cg_sm_its, a_inv_its, precond_applies;
+  };
+
+  // Tolerances of the linear solvers; defaults = Fluid::MPI::InsIM
+  // (mpi_insim.cpp:73-109, 379-380). serial() = Fluid::InsIM (insim.cpp:353-358).
+  struct InsSolverControl
+  {
+    double fgmres_rel = 1e-4, fgmres_floor = 1e-12;
+    bool fgmres_floor_is_max = true; // max(floor, rel*|rhs|)
+    double cg_mp_rel = 1e-6, cg_sm_rel = 1e-3, cg_floor = 1e-10;
+    // A~^-1: the reference factorises with MUMPS; here an inner BiCGStab on A_uu with
+    // the node-block Jacobi preconditioner, run to a_inv_rel * |src| (hard part 2)
+    double a_inv_rel = 1e-3;
+    int a_inv_max_it = 2000;
+    int basis_size = 30;
+    static InsSolverControl serial()
+    {
+      InsSolverControl c;
+      c.fgmres_rel = 1e-8;
+      c.fgmres_floor = 1e-10;
+      c.cg_sm_rel = 1e-6;
+      return c;
+    }
+  };
+
+  class InsIM
+  {
+  public:
+    InsIM(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params);
+
+    void run();
+    void run_one_step(bool apply_nonzero_constraints, bool assemble_system = true);
+    // BlockVector of n_u + n_p doubles, copied to the host
+    std::vector<double> get_current_solution();
+    void add_hard_coded_boundary_condition(int id, std::function<double(const double *, unsigned int, double)> f);
+
+    void setup_dofs();
+    void make_constraints();
+    void initialize_system();
+    void assemble(bool use_nonzero_constraints);
+    std::pair<unsigned int, double> solve(bool use_nonzero_constraints);
+
+    Context &ctx;
+    Triangulation &triangulation;
+    Parameters::AllParameters parameters;
+    FluidSpace fs;
+    Time time;
+    InsSolverControl control;
+    bool verbose = false;
+    DevBuf<double> present_solution, evaluation_point, solution_increment, newton_update, fsi_acceleration;
+    std::vector<NewtonRecord> history;
+    std::map<int, std::function<double(const double *, unsigned int, double)>> hard_coded;
+    // per-section device time, keyed by the reference's TimerOutput section names
+    std::map<std::string, double> timer_ms;
+    bool dofs_ready = false;
+
+  private:
+    void precondition(const double *src, double *dst);
+    DevBuf<double> d_binv, d_con_vals, d_tmp_p, d_utmp;
+    VecPool pool_fgmres, pool_cg, pool_ainv;
+    NewtonRecord cur{};
+  };
+} // namespace ifem

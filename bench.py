@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""bench.py - BASELINE.json's metric on BASELINE.json's config.
+
+Metric : wall seconds per time step of the 3-D INS lid-driven cavity "256^3" (= 128^3 hex cells, 257^3
+         velocity nodes, Q2/Q1, 53 070 468 DoF, 1.13e10 matrix entries; SURVEY.md 8 "config 3") through the
+         whole hot path - Newton iterations of { cell-loop assembly -> FGMRES + block-Schur preconditioner },
+         plus the achieved HBM GB/s of the dominant kernel (the velocity-block SpMV) against the measured
+         copy peak.
+A step : one call of Fluid::MPI::InsIM::run_one_step (one time step = ~3 Newton iterations).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--cells C] [--impl ours|reference]
+
+N = 1 : config 3 on one B200.  N > 1 : the same mesh (strong scaling) split into z-slabs, one rank per GPU,
+launched by torch.distributed.run; NCCL carries only ghost-DoF halos and Krylov dot products.
+`--impl reference` times the reference's CPU path: /root/reference cannot be built (deal.II / PETSc /
+p4est absent), so this arm runs oracle/ - the CPU restatement of the same algorithm - on all host cores on
+a bounded sample (a 16^3-cell cavity step), scaled linearly in the number of cells.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "time_step_wall_s (3D INS cavity 128^3 cells Q2/Q1, 53.07M DoF)"
+UNIT = "s/step"
+SAMPLE_CELLS = 16  # CPU baseline sample: 16^3 cells
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
+
+
+def cpu_reference_step(cells, steps=1, warmup=0):
+    """The oracle (CPU restatement of mpi_insim.cpp) on all host cores: seconds per time step on a cells^3 cavity."""
+    from util import cavity_prm, make_oracle
+
+    o = make_oracle(cavity_prm(3), (cells,) * 3, (0, 0, 0), (1, 1, 1), a_inv=("bicgstab", 1e-1, 2000))
+    k = 0
+    for _ in range(warmup):
+        o.run_one_step(k == 0)
+        k += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.run_one_step(k == 0)
+        k += 1
+    return (time.perf_counter() - t0) / steps, o
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # bounded sample: every "step" is one time step on SAMPLE_CELLS^3 cells, scaled linearly in cells
+    sec, o = cpu_reference_step(SAMPLE_CELLS, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    scale = (args.cells / SAMPLE_CELLS) ** 3
+    value = sec * scale
+    sample = (f"{max(1, args.steps)} time step(s) of the {SAMPLE_CELLS}^3-cell cavity (same prm, oracle/ CPU restatement, "
+              f"OpenMP on {cores} cores: {sec:.2f} s/step), scaled x{scale:.0f} linearly in cells to {args.cells}^3 "
+              f"(optimistic for the CPU: Krylov iteration counts grow with refinement)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D INS lid-driven cavity {args.cells}^3 hex cells Q2/Q1 (config 3), one time step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from util import cavity_prm
+
+    import openifem_b200 as ifem
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU path not wired in this build")
+    torch.cuda.set_device(local_rank)
+    ifem.init(local_rank)
+    n = args.cells
+    t_setup = time.perf_counter()
+    tria = ifem.Triangulation(3)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, (n, n, n), (0, 0, 0), (1, 1, 1), True)
+    params = ifem.Parameters.AllParameters(text=cavity_prm(3))
+    flow = ifem.Fluid.MPI.InsIM(tria, params)
+    flow.setup()
+    flow.set_control(a_inv_rel=1e-1, a_inv_fp32=1)
+    t_setup = time.perf_counter() - t_setup
+    n_u, n_p, nnz, _, _ = flow.sizes()
+    n_dofs = n_u + n_p
+    host = torch.zeros(n_dofs, dtype=torch.float64).pin_memory()
+    host_np = host.numpy()
+
+    step_no = 0
+    for _ in range(args.warmup):
+        flow.run_one_step(step_no == 0)
+        step_no += 1
+    host_np[:] = flow.get_current_solution()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ifem.kernel_launches()
+    torch.cuda.synchronize()
+    t_e2e = t_dev_ms = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        flow.set_vector(flow.PRESENT, host_np)                      # H2D of the step's input (pinned)
+        t_dev_ms += flow.bench_steps(1, step_no == 0)               # CUDA events on the library stream
+        host_np[:] = flow.get_current_solution()                    # D2H of the step's result
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+        step_no += 1
+    launches = ifem.kernel_launches() - launches0
+    clocks = sampler.stop()
+    sec_dev = t_dev_ms * 1e-3 / args.steps
+    sec_e2e = t_e2e / args.steps
+
+    # dominant kernel: BCSR SpMV of the velocity block (A_uu is 86 % of the matrix bytes); timed live, matrix >> L2
+    ms_uu, bytes_uu = flow.bench_spmv_uu(20)
+    ms_blk, bytes_blk = flow.bench_vmult(10)
+    peak, peak_src = _peaks()
+    achieved = bytes_uu / (ms_uu * 1e-3) / 1e9
+    hist = flow.history()
+    last = [h for h in hist if h["timestep"] == hist[-1]["timestep"]]
+    sections = {k: flow.timer_ms(k) for k in ["Assemble system", "Solve linear system", "CG for Mp", "CG for Sm", "A_inv"]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        sec, _ = cpu_reference_step(SAMPLE_CELLS)
+        scale = (n / SAMPLE_CELLS) ** 3
+        cpu = {"value": sec * scale, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 time step of the {SAMPLE_CELLS}^3-cell cavity with the oracle (same algorithm, OpenMP {cores} cores): "
+                         f"{sec:.2f} s, scaled x{scale:.0f} linearly in cells"}
+
+    line = {
+        "metric": METRIC, "value": sec_dev, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec_dev * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"3D INS lid-driven cavity {n}^3 hex cells Q2/Q1 (config 3): {n_dofs} DoF, {nnz} matrix entries, "
+                               f"Re 100, dt 1e-2, from rest; step = run_one_step (Newton x (assembly + FGMRES/Schur))",
+                   "l2": "inputs larger than L2 (A_uu alone is %.1f GB)" % (bytes_uu / 1e9),
+                   "a_inv": "BiCGStab(block-Jacobi) to 1e-1, fp32-streamed A_uu inside the preconditioner only",
+                   "setup_s": round(t_setup, 1), "newton_its_last_step": len(last),
+                   "fgmres_its_last_step": [h["gmres_its"] for h in last], "section_ms_total": sections},
+        "e2e": {"value": sec_e2e, "unit": UNIT, "h2d_bytes_per_step": n_dofs * 8, "d2h_bytes_per_step": n_dofs * 8},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "bcsr_spmv_kernel<3,3,32,double> (A_uu, FGMRES + inner solves)",
+                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "algorithmic_bytes": bytes_uu, "ms": ms_uu,
+                     "block_vmult": {"ms": ms_blk, "bytes": bytes_blk, "GB/s": bytes_blk / (ms_blk * 1e-3) / 1e9,
+                                     "csr_equivalent_bytes": 12.0 * nnz + 20.0 * n_dofs}},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cells", type=int, default=128, help="cells per direction (config 3 = 128)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

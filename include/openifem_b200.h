@@ -58,6 +58,7 @@ typedef struct
   double a_inv_rel;   /* inner Krylov stand-in for the MUMPS LU of A~ (mpi_insim.cpp:124-127) */
   int a_inv_max_it;
   int basis_size;     /* SolverFGMRES max_basis_size (deal.II default 30) */
+  int a_inv_fp32;     /* 1: the inner solve streams A_uu as fp32 (preconditioner only; the operator stays fp64) */
 } ifem_ins_control;
 
 typedef struct
@@ -112,6 +113,8 @@ int ifem_insim_bench_vmult(ifem_insim *s, int reps, double *ms_per_apply, double
 /* same for the velocity-velocity block alone (the dominant kernel) */
 int ifem_insim_bench_spmv_uu(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
 int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms_per_assembly);
+/* n_steps calls of run_one_step bracketed by CUDA events on the library's stream; total device ms */
+int ifem_insim_bench_steps(ifem_insim *s, int n_steps, int first_applies_nonzero_constraints, double *ms_total);
 
 #ifdef __cplusplus
 }

@@ -215,6 +215,11 @@ class _InsIM:
         check(lib().ifem_insim_bench_spmv_uu(self._h, C.c_int(reps), C.byref(ms), C.byref(b)))
         return ms.value, b.value
 
+    def bench_steps(self, n_steps, first_applies_nonzero_constraints=False):
+        ms = C.c_double()
+        check(lib().ifem_insim_bench_steps(self._h, C.c_int(n_steps), C.c_int(1 if first_applies_nonzero_constraints else 0), C.byref(ms)))
+        return ms.value
+
     def bench_assemble(self, reps):
         ms = C.c_double()
         check(lib().ifem_insim_bench_assemble(self._h, C.c_int(reps), C.byref(ms)))

@@ -206,6 +206,7 @@ int ifem_insim_default_control(int serial_twin, ifem_ins_control *out)
     out->a_inv_rel = c.a_inv_rel;
     out->a_inv_max_it = c.a_inv_max_it;
     out->basis_size = c.basis_size;
+    out->a_inv_fp32 = c.a_inv_fp32 ? 1 : 0;
   });
 }
 int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
@@ -220,6 +221,7 @@ int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
     k.a_inv_rel = c->a_inv_rel;
     k.a_inv_max_it = c->a_inv_max_it;
     k.basis_size = c->basis_size;
+    k.a_inv_fp32 = c->a_inv_fp32 != 0;
   });
 }
 int ifem_insim_set_verbose(ifem_insim *s, int verbose)
@@ -412,6 +414,14 @@ int ifem_insim_bench_spmv_uu(ifem_insim *s, int reps, double *ms, double *bytes)
     DevBuf<double> y(m.fs.n_u);
     *ms = time_reps(m.ctx, reps, [&] { spmv(m.ctx, m.fs.A_uu, m.fs.rhs.p, y.p); });
     *bytes = m.fs.A_uu.spmv_bytes();
+  });
+}
+int ifem_insim_bench_steps(ifem_insim *s, int n_steps, int first_nz, double *ms_total)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    int k = 0;
+    *ms_total = n_steps * time_reps(m.ctx, n_steps, [&] { m.run_one_step(first_nz != 0 && k++ == 0); });
   });
 }
 int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms)

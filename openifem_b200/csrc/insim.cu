@@ -122,7 +122,9 @@ namespace ifem
     axpby(ctx, n_u, 1.0, src_u, -1.0, utmp);
     {
       ScopedTimer t(ctx, timer_ms["A_inv"]);
-      LinOp Auu = [&](const double *x, double *y) { spmv(ctx, fs.A_uu, x, y); };
+      LinOp Auu = [&](const double *x, double *y) {
+        if (control.a_inv_fp32) spmv_fp32(ctx, fs.A_uu, x, y); else spmv(ctx, fs.A_uu, x, y);
+      };
       LinOp jac = [&](const double *x, double *y) { block_diag_apply(ctx, fs.un.n_nodes, fs.dim, d_binv.p, x, y); };
       const double unrm = nrm2(ctx, n_u, utmp);
       const SolveResult r = bicgstab(ctx, n_u, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);
@@ -137,6 +139,7 @@ namespace ifem
     // BlockSchurPreconditioner ctor (mpi_insim.cpp:13-50)
     compute_mass_schur(ctx, fs);
     block_diag_inverse(ctx, fs.A_uu, d_binv.p);
+    if (control.a_inv_fp32) make_fp32_copy(ctx, fs.A_uu);
     const int64_t n = fs.n_dofs;
     const double nrm = nrm2(ctx, n, fs.rhs.p);
     const double tol = control.fgmres_floor_is_max ? std::max(control.fgmres_floor, control.fgmres_rel * nrm)

@@ -65,6 +65,7 @@ namespace ifem
     // the node-block Jacobi preconditioner, run to a_inv_rel * |src| (hard part 2)
     double a_inv_rel = 1e-3;
     int a_inv_max_it = 2000;
+    bool a_inv_fp32 = false; // stream A_uu as fp32 inside the inner solve (legal: FGMRES is flexible)
     int basis_size = 30;
     static InsSolverControl serial()
     {

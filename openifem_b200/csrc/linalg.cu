@@ -92,10 +92,12 @@ namespace ifem
   // with unit stride across the lanes (coalesced, read-once -> streaming loads),
   // x is gathered through L1/L2, the R partial sums are shuffled down.
   // ---------------------------------------------------------------------------
-  template <int R, int C, int TPR>
+  __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+
+  template <int R, int C, int TPR, typename VT>
   __global__ void __launch_bounds__(256)
   bcsr_spmv_kernel(int n_brows, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
-                   const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, int accumulate)
+                   const VT *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, int accumulate)
   {
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = gt / TPR;
@@ -107,7 +109,7 @@ namespace ifem
       {
         const int64_t base = rowptr[row];
         const int nb = (int)(rowptr[row + 1] - base);
-        const double *v = val + base * (R * C);
+        const VT *v = val + base * (R * C);
         const int *ci = col + base;
 #pragma unroll 2
         for (int j = lane; j < nb; j += TPR)
@@ -119,7 +121,7 @@ namespace ifem
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
-              for (int c = 0; c < C; ++c) acc[r] = fma(ld_stream(v + (int64_t)(r * C + c) * nb + j), xv[c], acc[r]);
+              for (int c = 0; c < C; ++c) acc[r] = fma((double)ld_stream(v + (int64_t)(r * C + c) * nb + j), xv[c], acc[r]);
           }
       }
 #pragma unroll
@@ -137,8 +139,8 @@ namespace ifem
       }
   }
 
-  template <int R, int C>
-  static void spmv_launch(Context &ctx, const Bcsr &A, const double *x, double *y, bool accumulate)
+  template <int R, int C, typename VT>
+  static void spmv_launch(Context &ctx, const Bcsr &A, const VT *val, const double *x, double *y, bool accumulate)
   {
     if (A.n_brows == 0) return;
     const int threads = 256;
@@ -146,7 +148,7 @@ namespace ifem
       constexpr int TPR = decltype(tpr_tag)::value;
       const int64_t total = (int64_t)A.n_brows * TPR;
       const int64_t blocks = (total + threads - 1) / threads;
-      bcsr_spmv_kernel<R, C, TPR><<<(unsigned)blocks, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, A.val.p, x, y,
+      bcsr_spmv_kernel<R, C, TPR, VT><<<(unsigned)blocks, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, val, x, y,
                                                                                 accumulate ? 1 : 0);
     };
     switch (A.tpr)
@@ -165,15 +167,46 @@ namespace ifem
     const int key = A.R * 10 + A.C;
     switch (key)
       {
-      case 11: spmv_launch<1, 1>(ctx, A, x, y, accumulate); break;
-      case 22: spmv_launch<2, 2>(ctx, A, x, y, accumulate); break;
-      case 21: spmv_launch<2, 1>(ctx, A, x, y, accumulate); break;
-      case 12: spmv_launch<1, 2>(ctx, A, x, y, accumulate); break;
-      case 33: spmv_launch<3, 3>(ctx, A, x, y, accumulate); break;
-      case 31: spmv_launch<3, 1>(ctx, A, x, y, accumulate); break;
-      case 13: spmv_launch<1, 3>(ctx, A, x, y, accumulate); break;
+      case 11: spmv_launch<1, 1>(ctx, A, A.val.p, x, y, accumulate); break;
+      case 22: spmv_launch<2, 2>(ctx, A, A.val.p, x, y, accumulate); break;
+      case 21: spmv_launch<2, 1>(ctx, A, A.val.p, x, y, accumulate); break;
+      case 12: spmv_launch<1, 2>(ctx, A, A.val.p, x, y, accumulate); break;
+      case 33: spmv_launch<3, 3>(ctx, A, A.val.p, x, y, accumulate); break;
+      case 31: spmv_launch<3, 1>(ctx, A, A.val.p, x, y, accumulate); break;
+      case 13: spmv_launch<1, 3>(ctx, A, A.val.p, x, y, accumulate); break;
       default: throw std::runtime_error("spmv: unsupported block shape");
       }
+  }
+
+  void spmv_fp32(Context &ctx, const Bcsr &A, const double *x, double *y)
+  {
+    if (!A.val32.p) throw std::runtime_error("spmv_fp32: no fp32 copy (call make_fp32_copy)");
+    const int key = A.R * 10 + A.C;
+    switch (key)
+      {
+      case 11: spmv_launch<1, 1>(ctx, A, A.val32.p, x, y, false); break;
+      case 22: spmv_launch<2, 2>(ctx, A, A.val32.p, x, y, false); break;
+      case 33: spmv_launch<3, 3>(ctx, A, A.val32.p, x, y, false); break;
+      default: throw std::runtime_error("spmv_fp32: unsupported block shape");
+      }
+  }
+
+  namespace
+  {
+    __global__ void to_fp32_kernel(int64_t n, const double *__restrict__ a, float *__restrict__ b)
+    {
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        b[i] = (float)a[i];
+    }
+  } // namespace
+
+  void make_fp32_copy(Context &ctx, Bcsr &A)
+  {
+    if (A.val32.n != A.val.n) A.val32.alloc(A.val.n);
+    if (!A.val.n) return;
+    to_fp32_kernel<<<ctx.sm_count * 16, 256, 0, ctx.stream>>>((int64_t)A.val.n, A.val.p, A.val32.p);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
   }
 
   // ---------------------------------------------------------------------------

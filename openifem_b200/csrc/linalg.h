@@ -26,6 +26,7 @@ namespace ifem
     DevBuf<int64_t> rowptr;
     DevBuf<int> col;
     DevBuf<double> val;
+    DevBuf<float> val32; // optional fp32 copy of val in the same layout (inexact inner solves only)
     int tpr = 32; // threads per block row chosen from the average row length
 
     void init(const Pattern &P, int R_, int C_, cudaStream_t s);
@@ -42,6 +43,11 @@ namespace ifem
 
   // y = A x  (accumulate = false)   or   y += A x  (accumulate = true)
   void spmv(Context &ctx, const Bcsr &A, const double *x, double *y, bool accumulate = false);
+  // refresh A.val32 from A.val (allocates on first use)
+  void make_fp32_copy(Context &ctx, Bcsr &A);
+  // y = A32 x: matrix entries read as fp32 (half the HBM traffic), x / y / accumulation in fp64.
+  // Only legal inside a flexible preconditioner (the A~^-1 stand-in), never for the operator itself.
+  void spmv_fp32(Context &ctx, const Bcsr &A, const double *x, double *y);
 
   // ---- BLAS-1 on device vectors (deterministic two-stage reductions) -----------
   double dot(Context &ctx, int64_t n, const double *x, const double *y);

@@ -206,6 +206,8 @@ class InsIM:
     def __init__(self, mesh: fem.BoxMesh, params, mode="mpi", a_inv="lu", hard_coded=None, verbose=False):
         self.mesh, self.prm, self.mode, self.a_inv = mesh, params, mode, a_inv
         self.verbose = verbose
+        # FGMRES relative tolerance: mpi_insim.cpp:380 (1e-4) / insim.cpp:354 (1e-8); tests may tighten it
+        self.fgmres_rel = 1e-4 if mode == "mpi" else 1e-8
         dim = mesh.dim
         self.dim = dim
         pu, pp = params.fluid_velocity_degree, params.fluid_pressure_degree
@@ -338,7 +340,7 @@ class InsIM:
         prec = self._make_preconditioner()
         A_op = CsrOp(self.system_matrix)
         nrm = np.linalg.norm(self.system_rhs)
-        tol = max(1e-12, 1e-4 * nrm) if self.mode == "mpi" else max(1e-8 * nrm, 1e-10)
+        tol = max(1e-12, self.fgmres_rel * nrm) if self.mode == "mpi" else max(self.fgmres_rel * nrm, 1e-10)
         x, its, res = fgmres(A_op, prec, self.system_rhs, tol, self.n)
         # constraints.distribute(newton_update)
         x[self.con != 0] = self.nonzero_val[self.con != 0] if use_nonzero_constraints else 0.0

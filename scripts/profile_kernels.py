@@ -1,0 +1,23 @@
+"""Target for ncu: set up the 3-D cavity at <cells>^3, assemble once, then launch the kernels to be
+profiled a few times (development / profiling aid; numbers printed under ncu are not bench values)."""
+import sys
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+from util import cavity_prm
+
+import openifem_b200 as ifem
+
+n = int(sys.argv[1])
+what = sys.argv[2] if len(sys.argv) > 2 else "spmv"
+ifem.init(0)
+tria = ifem.Triangulation(3)
+ifem.GridGenerator.subdivided_hyper_rectangle(tria, (n, n, n), (0, 0, 0), (1, 1, 1), True)
+flow = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(text=cavity_prm(3)))
+flow.setup()
+flow.assemble(True)
+if what == "spmv":
+    print("uu", flow.bench_spmv_uu(3))
+    print("block", flow.bench_vmult(2))
+else:
+    print("assemble", flow.bench_assemble(2))

@@ -76,9 +76,17 @@ def test_assembly_3d_neumann_fsi():
 
 def test_mass_schur_and_preconditioned_solve_2d():
     prm = cavity_prm(2)
-    o, g = _compare_assembly(prm, (8, 8), (0, 0), (1, 1), True, seed=5)
-    # solve the assembled Newton system on both sides with tight inner tolerances
-    o.a_inv = "lu"
+    o, g = make_oracle(prm, (8, 8), (0, 0), (1, 1)), make_gpu(prm, (8, 8), (0, 0), (1, 1))
+    rng = np.random.default_rng(5)
+    pts = o.dofs.support_points()
+    ev = 0.2 * np.sin(3 * pts[:, 0]) * np.cos(2 * pts[:, 1]) + 0.01 * rng.uniform(-1, 1, o.n)
+    ev[o.con != 0] = 0.0  # no net boundary flux: keeps the closed-cavity system compatible (pressure null space)
+    o.evaluation_point[:], o.present[:] = ev, 0.5 * ev
+    g.set_vector(g.EVALUATION_POINT, ev)
+    g.set_vector(g.PRESENT, 0.5 * ev)
+    o.assemble(True)
+    g.assemble(True)
+    # solve the assembled Newton system on both sides; GPU inner A~ solve run (almost) to exactness
     its_o, res_o = o.solve(True)
     g.set_control(a_inv_rel=1e-12, a_inv_max_it=5000)
     its_g, res_g = g.solve(True)
@@ -86,7 +94,8 @@ def test_mass_schur_and_preconditioned_solve_2d():
     du_g = g.get_vector(g.NEWTON_UPDATE)
     # FGMRES with an (almost) exact A~^-1 follows the oracle iteration for iteration
     assert its_g == its_o
-    assert rel(du_g, o.newton_update) < 1e-3  # both stop at 1e-4 |rhs|: agreement to solver tolerance
+    assert abs(res_g - res_o) <= 1e-6 * res_o
+    assert rel(du_g, o.newton_update) < 1e-6
     A = o.system_matrix
     assert np.linalg.norm(A @ du_g_unconstrained(du_g, o) - rhs_unconstrained(o)) <= 1.01 * max(1e-12, 1e-4 * np.linalg.norm(o.system_rhs))
 
@@ -103,10 +112,16 @@ def rhs_unconstrained(o):
     return r
 
 
-def _run_both(prm_text, reps, lo, hi, steps, mode="mpi"):
+def _run_both(prm_text, reps, lo, hi, steps, mode="mpi", fgmres_rel=None):
     o = make_oracle(prm_text, reps, lo, hi, mode=mode)
     g = make_gpu(prm_text, reps, lo, hi)
-    g.set_control(serial_twin=(mode == "serial"), a_inv_rel=1e-10, a_inv_max_it=5000)
+    kw = {}
+    if fgmres_rel is not None:
+        # linear solves tightened on both sides so that the Newton residual HISTORY (not only the
+        # converged state) is comparable to 1e-6
+        o.fgmres_rel = fgmres_rel
+        kw["fgmres_rel"] = fgmres_rel
+    g.set_control(serial_twin=(mode == "serial"), a_inv_rel=1e-10, a_inv_max_it=5000, **kw)
     for k in range(steps):
         o.run_one_step(k == 0)
         g.run_one_step(k == 0)
@@ -131,13 +146,13 @@ def _compare_fields(o, g, closed=True):
 def test_cavity_2d_time_steps_match_oracle():
     # config 1 (tests/fluid_cavity) at reduced size, Newton tolerance tightened so both converge to the same state
     prm = cavity_prm(2, newton_tol=1e-9)
-    o, g = _run_both(prm, (8, 8), (0, 0), (1, 1), steps=3)
+    o, g = _run_both(prm, (8, 8), (0, 0), (1, 1), steps=3, fgmres_rel=1e-9)
     _compare_fields(o, g)
 
 
 def test_cavity_3d_time_steps_match_oracle():
     prm = cavity_prm(3, newton_tol=1e-9)
-    o, g = _run_both(prm, (4, 4, 4), (0, 0, 0), (1, 1, 1), steps=2)
+    o, g = _run_both(prm, (4, 4, 4), (0, 0, 0), (1, 1, 1), steps=2, fgmres_rel=1e-9)
     _compare_fields(o, g)
 
 

@@ -140,13 +140,30 @@ def run_ours(args):
 
     import openifem_b200 as ifem
 
-    rank = int(os.environ.get("RANK", "0"))
+    import torch.distributed as dist
+
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU path not wired in this build")
-    torch.cuda.set_device(local_rank)
-    ifem.init(local_rank)
+    rank, world = ifem.init_distributed(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.item()
+
     n = args.cells
     t_setup = time.perf_counter()
     tria = ifem.Triangulation(3)
@@ -155,10 +172,14 @@ def run_ours(args):
     flow = ifem.Fluid.MPI.InsIM(tria, params)
     flow.setup()
     flow.set_control(a_inv_rel=1e-1, a_inv_fp32=1)
+    barrier()
     t_setup = time.perf_counter() - t_setup
-    n_u, n_p, nnz, _, _ = flow.sizes()
-    n_dofs = n_u + n_p
-    host = torch.zeros(n_dofs, dtype=torch.float64).pin_memory()
+    n_u, n_p, nnz_local, _, _ = flow.sizes()
+    n_local = n_u + n_p  # local block vector (owned + ghost entries) exchanged with the host
+    ou, op = flow.partition(0)[0], flow.partition(1)[0]
+    n_dofs = int(sum_over_ranks(3 * ou + op))
+    nnz = int(sum_over_ranks(nnz_local))
+    host = torch.zeros(n_local, dtype=torch.float64).pin_memory()
     host_np = host.numpy()
 
     step_no = 0
@@ -170,7 +191,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ifem.kernel_launches()
-    torch.cuda.synchronize()
+    barrier()
     t_e2e = t_dev_ms = 0.0
     for _ in range(args.steps):
         t0 = time.perf_counter()
@@ -180,10 +201,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         t_e2e += time.perf_counter() - t0
         step_no += 1
+    barrier()
     launches = ifem.kernel_launches() - launches0
     clocks = sampler.stop()
-    sec_dev = t_dev_ms * 1e-3 / args.steps
-    sec_e2e = t_e2e / args.steps
+    sec_dev = max_over_ranks(t_dev_ms * 1e-3 / args.steps)
+    sec_e2e = max_over_ranks(t_e2e / args.steps)
+    h2d = int(sum_over_ranks(n_local * 8))
 
     # dominant kernel: BCSR SpMV of the velocity block (A_uu is 86 % of the matrix bytes); timed live, matrix >> L2
     ms_uu, bytes_uu = flow.bench_spmv_uu(20)
@@ -194,8 +217,15 @@ def run_ours(args):
     last = [h for h in hist if h["timestep"] == hist[-1]["timestep"]]
     sections = {k: flow.timer_ms(k) for k in ["Assemble system", "Solve linear system", "CG for Mp", "CG for Sm", "A_inv"]}
 
+    if world > 1:
+        ms_uu, ms_blk = max_over_ranks(ms_uu), max_over_ranks(ms_blk)
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count()
         sec, _ = cpu_reference_step(SAMPLE_CELLS)
         scale = (n / SAMPLE_CELLS) ** 3
@@ -204,25 +234,28 @@ def run_ours(args):
                          f"{sec:.2f} s, scaled x{scale:.0f} linearly in cells"}
 
     line = {
-        "metric": METRIC, "value": sec_dev, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": sec_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec_dev * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"3D INS lid-driven cavity {n}^3 hex cells Q2/Q1 (config 3): {n_dofs} DoF, {nnz} matrix entries, "
                                f"Re 100, dt 1e-2, from rest; step = run_one_step (Newton x (assembly + FGMRES/Schur))",
                    "l2": "inputs larger than L2 (A_uu alone is %.1f GB)" % (bytes_uu / 1e9),
                    "a_inv": "BiCGStab(block-Jacobi) to 1e-1, fp32-streamed A_uu inside the preconditioner only",
+                   "parallelism": f"{world} z-slab(s), one rank per GPU; NCCL: ghost halos + dot-product all-reduces only",
                    "setup_s": round(t_setup, 1), "newton_its_last_step": len(last),
                    "fgmres_its_last_step": [h["gmres_its"] for h in last], "section_ms_total": sections},
-        "e2e": {"value": sec_e2e, "unit": UNIT, "h2d_bytes_per_step": n_dofs * 8, "d2h_bytes_per_step": n_dofs * 8},
+        "e2e": {"value": sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d},
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "bcsr_spmv_kernel<3,3,32,double> (A_uu, FGMRES + inner solves)",
+        "roofline": {"bound": "hbm", "kernel": "bcsr_spmv_kernel<3,3,32,double> (A_uu, FGMRES + inner solves), per GPU (rank 0's rows)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "algorithmic_bytes": bytes_uu, "ms": ms_uu,
                      "block_vmult": {"ms": ms_blk, "bytes": bytes_blk, "GB/s": bytes_blk / (ms_blk * 1e-3) / 1e9,
-                                     "csr_equivalent_bytes": 12.0 * nnz + 20.0 * n_dofs}},
+                                     "csr_equivalent_bytes_per_gpu": 12.0 * nnz_local + 20.0 * (3 * ou + op)}},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

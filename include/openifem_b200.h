@@ -35,6 +35,24 @@ int ifem_init(int device);
 /* number of kernels launched by the library so far in this process */
 int ifem_kernel_launches(int64_t *count);
 
+/* ---- ranks: one process per GPU. Rank 0 creates the NCCL unique id, the launcher broadcasts the 128 bytes
+ *      (torch.distributed / MPI / files) and every rank calls ifem_comm_init before creating solvers.
+ *      Replaces MPI_COMM_WORLD of the reference (source/mpi_fluid_solver.cpp:37). ---- */
+int ifem_comm_unique_id(unsigned char id[128]);
+int ifem_comm_init(int rank, int size, const unsigned char id[128]);
+int ifem_comm_finalize(void);
+
+/* ---- host-side domain decomposition (what p4est + DoFHandler::distribute_dofs decide in the reference,
+ *      include/mpi_fluid_solver.h:187, source/mpi_fluid_solver.cpp:140-152); no device needed ---- */
+typedef struct ifem_partition ifem_partition;
+int ifem_partition_create(const ifem_tria *t, int velocity_degree, int pressure_degree, int rank, int size, ifem_partition **out);
+int ifem_partition_destroy(ifem_partition *p);
+/* which: 0 velocity nodes, 1 pressure nodes */
+int ifem_partition_counts(const ifem_partition *p, int which, int *n_owned, int *n_local, int *n_neighbours, int *n_local_cells);
+int ifem_partition_local_to_global(const ifem_partition *p, int which, int *global_ids);
+int ifem_partition_neighbour(const ifem_partition *p, int which, int k, int *rank, int *n_send, int *recv_offset, int *recv_count);
+int ifem_partition_send_list(const ifem_partition *p, int which, int k, int *local_ids);
+
 /* ---- Triangulation: GridGenerator calls of the reference test drivers
  *      (tests/fluid_cavity/fluid_cavity.cpp:28-34, tests/fluid_pipe_mpi/fluid_pipe_mpi.cpp:37-45) ---- */
 int ifem_tria_create(int dim, ifem_tria **out);
@@ -105,6 +123,10 @@ int ifem_insim_history(const ifem_insim *s, int max_records, ifem_newton_record 
  * "CG for Mp", "CG for Sm", "A_inv") */
 int ifem_insim_timer_ms(const ifem_insim *s, const char *section, double *ms);
 int ifem_insim_time(const ifem_insim *s, unsigned int *timestep, double *current);
+/* this rank's share of the dofs: vectors exchanged with the host are LOCAL block vectors
+ * [u of local nodes (owned first, then ghosts) | p of local nodes]; which: 0 velocity nodes, 1 pressure nodes */
+int ifem_insim_partition(const ifem_insim *s, int which, int *n_owned_nodes, int *n_local_nodes);
+int ifem_insim_local_to_global(const ifem_insim *s, int which, int *global_node_ids);
 
 /* ---- measurement hooks (bench.py): device-resident, CUDA-event timed on the library's stream ---- */
 /* reps applications of the block SpMV on resident vectors; returns mean ms per application and the

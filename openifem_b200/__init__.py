@@ -15,11 +15,84 @@ import numpy as np
 from . import _lib
 from ._lib import IfemError, InsControl, NewtonRecord, check, dptr, iptr, lptr, lib
 
-__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "IfemError", "init", "kernel_launches"]
+__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Partition", "IfemError", "init", "init_distributed",
+           "comm_unique_id", "comm_init", "comm_finalize", "kernel_launches"]
 
 
 def init(device: int = 0):
     check(lib().ifem_init(C.c_int(device)))
+
+
+def comm_unique_id() -> bytes:
+    """Rank 0: create the 128-byte NCCL unique id to broadcast to the other ranks."""
+    buf = (C.c_ubyte * 128)()
+    check(lib().ifem_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(rank: int, size: int, unique_id: bytes):
+    """One process per GPU: join the NCCL communicator (replaces MPI_COMM_WORLD of the reference)."""
+    buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+    check(lib().ifem_comm_init(C.c_int(rank), C.c_int(size), buf))
+
+
+def comm_finalize():
+    check(lib().ifem_comm_finalize())
+
+
+def init_distributed(local_rank: int = None):
+    """Convenience for torchrun launches: bind the device, then build the library's communicator from
+    torch.distributed's rendezvous (the id travels through the process group, nothing else does)."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0")) if local_rank is None else local_rank
+    torch.cuda.set_device(local_rank)
+    init(local_rank)
+    if world > 1:
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm_init(rank, world, box[0])
+    return rank, world
+
+
+class Partition:
+    """Host-side domain decomposition of a triangulation for FE_Q(pu)^dim x FE_Q(pp) (no device needed)."""
+
+    def __init__(self, tria, velocity_degree, pressure_degree, rank, size):
+        self._h = C.c_void_p()
+        check(lib().ifem_partition_create(tria._h, C.c_int(velocity_degree), C.c_int(pressure_degree), C.c_int(rank),
+                                          C.c_int(size), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib._lib is not None:
+            _lib._lib.ifem_partition_destroy(self._h)
+            self._h = None
+
+    def counts(self, which):
+        v = [C.c_int() for _ in range(4)]
+        check(lib().ifem_partition_counts(self._h, C.c_int(which), *[C.byref(x) for x in v]))
+        return dict(n_owned=v[0].value, n_local=v[1].value, n_neighbours=v[2].value, n_local_cells=v[3].value)
+
+    def local_to_global(self, which):
+        out = np.empty(self.counts(which)["n_local"], dtype=np.int32)
+        check(lib().ifem_partition_local_to_global(self._h, C.c_int(which), iptr(out)))
+        return out
+
+    def neighbours(self, which):
+        res = []
+        for k in range(self.counts(which)["n_neighbours"]):
+            v = [C.c_int() for _ in range(4)]
+            check(lib().ifem_partition_neighbour(self._h, C.c_int(which), C.c_int(k), *[C.byref(x) for x in v]))
+            send = np.empty(v[1].value, dtype=np.int32)
+            check(lib().ifem_partition_send_list(self._h, C.c_int(which), C.c_int(k), iptr(send)))
+            res.append(dict(rank=v[0].value, send_local=send, recv_offset=v[2].value, recv_count=v[3].value))
+        return res
 
 
 def kernel_launches() -> int:
@@ -193,6 +266,29 @@ class _InsIM:
         check(lib().ifem_insim_history(self._h, C.c_int(max_records), buf, C.byref(n)))
         k = min(n.value, max_records)
         return [{f: getattr(buf[i], f) for f, _ in NewtonRecord._fields_} for i in range(k)]
+
+    def partition(self, which):
+        """(n_owned_nodes, n_local_nodes) of velocity (0) / pressure (1) nodes on this rank"""
+        a, b = C.c_int(), C.c_int()
+        check(lib().ifem_insim_partition(self._h, C.c_int(which), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def local_to_global(self, which):
+        out = np.empty(self.partition(which)[1], dtype=np.int32)
+        check(lib().ifem_insim_local_to_global(self._h, C.c_int(which), iptr(out)))
+        return out
+
+    def owned_global_dofs(self, n_unodes_global):
+        """(local dof indices, global dof indices) of the dofs this rank owns, global numbering [u | p]."""
+        dim = self.tria.dim
+        ou, lu = self.partition(0)
+        op, _ = self.partition(1)
+        gu, gp = self.local_to_global(0), self.local_to_global(1)
+        loc_u = (np.arange(ou)[:, None] * dim + np.arange(dim)[None, :]).ravel()
+        glo_u = (gu[:ou, None].astype(np.int64) * dim + np.arange(dim)[None, :]).ravel()
+        loc_p = dim * lu + np.arange(op)
+        glo_p = dim * n_unodes_global + gp[:op].astype(np.int64)
+        return np.concatenate([loc_u, loc_p]), np.concatenate([glo_u, glo_p])
 
     def timer_ms(self, section: str) -> float:
         ms = C.c_double()

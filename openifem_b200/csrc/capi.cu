@@ -5,7 +5,9 @@
 #include <memory>
 #include <string>
 
+#include "comm.h"
 #include "insim.h"
+#include "partition.h"
 
 using namespace ifem;
 
@@ -20,6 +22,10 @@ struct ifem_params
 struct ifem_insim
 {
   std::unique_ptr<InsIM> s;
+};
+struct ifem_partition
+{
+  Partition p;
 };
 
 namespace
@@ -96,6 +102,8 @@ static DevBuf<double> *pick_vector(InsIM &m, int which, int64_t &n)
     default: throw std::runtime_error("unknown vector id");
     }
 }
+static const NodePartition &pick_np(const Partition &p, int which) { return which == 0 ? p.u : p.p; }
+
 extern "C" {
 
 const char *ifem_last_error(void) { return g_error.c_str(); }
@@ -118,6 +126,78 @@ int ifem_kernel_launches(int64_t *count)
   return guard([&] {
     require_device();
     *count = default_context().kernel_launches;
+  });
+}
+
+int ifem_comm_unique_id(unsigned char id[128])
+{
+  return guard([&] { comm_get_unique_id(id); });
+}
+int ifem_comm_init(int rank, int size, const unsigned char id[128])
+{
+  return guard([&] {
+    require_device();
+    Context &ctx = default_context();
+    if (ctx.comm) comm_destroy(ctx.comm);
+    ctx.comm = comm_create(rank, size, id);
+  });
+}
+int ifem_comm_finalize(void)
+{
+  return guard([&] {
+    if (!g_initialised) return;
+    Context &ctx = default_context();
+    if (ctx.comm) comm_destroy(ctx.comm);
+    ctx.comm = nullptr;
+  });
+}
+
+int ifem_partition_create(const ifem_tria *t, int pu, int pp, int rank, int size, ifem_partition **out)
+{
+  return guard([&] {
+    const NodeTable un = build_node_table(t->t, pu), pn = build_node_table(t->t, pp);
+    auto *h = new ifem_partition;
+    h->p = build_partition(t->t, un, pn, rank, size);
+    *out = h;
+  });
+}
+int ifem_partition_destroy(ifem_partition *p)
+{
+  delete p;
+  return IFEM_OK;
+}
+int ifem_partition_counts(const ifem_partition *p, int which, int *n_owned, int *n_local, int *n_nb, int *n_cells)
+{
+  return guard([&] {
+    const NodePartition &np = pick_np(p->p, which);
+    if (n_owned) *n_owned = np.n_owned;
+    if (n_local) *n_local = np.n_local;
+    if (n_nb) *n_nb = (int)np.neighbours.size();
+    if (n_cells) *n_cells = (int)p->p.local_cells.size();
+  });
+}
+int ifem_partition_local_to_global(const ifem_partition *p, int which, int *ids)
+{
+  return guard([&] {
+    const NodePartition &np = pick_np(p->p, which);
+    std::copy(np.local_to_global.begin(), np.local_to_global.end(), ids);
+  });
+}
+int ifem_partition_neighbour(const ifem_partition *p, int which, int k, int *rank, int *n_send, int *recv_offset, int *recv_count)
+{
+  return guard([&] {
+    const NodePartition &np = pick_np(p->p, which);
+    *rank = np.neighbours.at(k);
+    *n_send = (int)np.send_local.at(k).size();
+    *recv_offset = np.recv_offset.at(k);
+    *recv_count = np.recv_count.at(k);
+  });
+}
+int ifem_partition_send_list(const ifem_partition *p, int which, int k, int *ids)
+{
+  return guard([&] {
+    const auto &l = pick_np(p->p, which).send_local.at(k);
+    std::copy(l.begin(), l.end(), ids);
   });
 }
 
@@ -414,6 +494,28 @@ int ifem_insim_bench_spmv_uu(ifem_insim *s, int reps, double *ms, double *bytes)
     DevBuf<double> y(m.fs.n_u);
     *ms = time_reps(m.ctx, reps, [&] { spmv(m.ctx, m.fs.A_uu, m.fs.rhs.p, y.p); });
     *bytes = m.fs.A_uu.spmv_bytes();
+  });
+}
+int ifem_insim_partition(const ifem_insim *s, int which, int *n_owned, int *n_local)
+{
+  return guard([&] {
+    const FluidSpace &fs = s->s->fs;
+    *n_owned = which == 0 ? fs.n_owned_unodes : fs.n_owned_pnodes;
+    *n_local = which == 0 ? fs.un.n_nodes : fs.pn.n_nodes;
+  });
+}
+int ifem_insim_local_to_global(const ifem_insim *s, int which, int *ids)
+{
+  return guard([&] {
+    const FluidSpace &fs = s->s->fs;
+    const int n = which == 0 ? fs.un.n_nodes : fs.pn.n_nodes;
+    if (fs.n_ranks == 1)
+      for (int i = 0; i < n; ++i) ids[i] = i;
+    else
+      {
+        const auto &l = (which == 0 ? fs.part.u : fs.part.p).local_to_global;
+        std::copy(l.begin(), l.end(), ids);
+      }
   });
 }
 int ifem_insim_bench_steps(ifem_insim *s, int n_steps, int first_nz, double *ms_total)

@@ -1,5 +1,7 @@
 #include "fluid.h"
 
+#include "comm.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -13,7 +15,7 @@ namespace ifem
   {
     // slot of column node B in the sorted column list of block row A
     __global__ void build_slots_kernel(int n_cells, int nr, int nc, const int *__restrict__ row_tab, const int *__restrict__ col_tab,
-                                       const int64_t *__restrict__ rowptr, const int *__restrict__ col,
+                                       const int64_t *__restrict__ rowptr, const int *__restrict__ col, int n_rows_owned,
                                        unsigned char *__restrict__ slots, int stride, int offset, int *__restrict__ err)
     {
       const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -23,6 +25,11 @@ namespace ifem
       const int rem = (int)(t % (nr * nc));
       const int a = rem / nc, b = rem % nc;
       const int A = row_tab[(int64_t)cell * nr + a], B = col_tab[(int64_t)cell * nc + b];
+      if (A >= n_rows_owned) // ghost row: assembled by its owner
+        {
+          slots[(int64_t)cell * stride + offset + rem] = 0;
+          return;
+        }
       const int64_t base = rowptr[A];
       int lo = 0, hi = (int)(rowptr[A + 1] - base) - 1, j = -1;
       while (lo <= hi)
@@ -54,16 +61,52 @@ namespace ifem
     tab_u = ShapeTable(fe_u, quad.points, nq);
     tab_p = ShapeTable(fe_p, quad.points, nq);
     tab_geo = ShapeTable(fe_geo, quad.points, nq);
-    un = build_node_table(tria, pu);
-    pn = build_node_table(tria, pp);
+    rank = ctx.comm ? ctx.comm->rank : 0;
+    n_ranks = ctx.comm ? ctx.comm->size : 1;
+    if (n_ranks > 1)
+      {
+        un_global = build_node_table(tria, pu);
+        pn_global = build_node_table(tria, pp);
+        part = build_partition(tria, un_global, pn_global, rank, n_ranks);
+        local_cells = part.local_cells;
+        un = localise(un_global, local_cells, part.u);
+        pn = localise(pn_global, local_cells, part.p);
+        n_owned_unodes = part.u.n_owned;
+        n_owned_pnodes = part.p.n_owned;
+      }
+    else
+      {
+        un = build_node_table(tria, pu);
+        pn = build_node_table(tria, pp);
+        local_cells.resize(n_cells);
+        for (int c = 0; c < n_cells; ++c) local_cells[c] = c;
+        n_owned_unodes = un.n_nodes;
+        n_owned_pnodes = pn.n_nodes;
+        part = Partition();
+        part.u.n_owned = part.u.n_local = un.n_nodes;
+        part.p.n_owned = part.p.n_local = pn.n_nodes;
+      }
+    n_cells = (int)local_cells.size();
     n_u = (int64_t)dim * un.n_nodes;
     n_p = pn.n_nodes;
     n_dofs = n_u + n_p;
+    vs_all = VecSpace((int64_t)dim * n_owned_unodes, n_u, n_owned_pnodes, n_dofs);
+    vs_u = VecSpace((int64_t)dim * n_owned_unodes, 0, 0, n_u);
+    vs_p = VecSpace(n_owned_pnodes, 0, 0, n_p);
+    halo_u.init(ctx, part.u, dim);
+    halo_p.init(ctx, part.p, 1);
 
-    P_uu = build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, un.cell_nodes.data(), nu, un.n_nodes);
-    P_up = build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes);
-    P_pu = build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, un.cell_nodes.data(), nu, un.n_nodes);
-    P_pp = build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes);
+    // patterns: rows = owned nodes (they come first in the local numbering), columns = local nodes
+    auto owned_rows = [](Pattern P, int n_owned) {
+      P.n_rows = n_owned;
+      P.rowptr.resize((size_t)n_owned + 1);
+      P.col.resize(P.rowptr[n_owned]);
+      return P;
+    };
+    P_uu = owned_rows(build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, un.cell_nodes.data(), nu, un.n_nodes), n_owned_unodes);
+    P_up = owned_rows(build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes), n_owned_unodes);
+    P_pu = owned_rows(build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, un.cell_nodes.data(), nu, un.n_nodes), n_owned_pnodes);
+    P_pp = owned_rows(build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes), n_owned_pnodes);
     colour_cells(n_cells, un.cell_nodes.data(), nu, un.n_nodes, colour_order, colour_offsets);
 
     cudaStream_t s = ctx.stream;
@@ -75,7 +118,7 @@ namespace ifem
       for (int c = 0; c < n_cells; ++c)
         for (int v = 0; v < nv; ++v)
           for (int d = 0; d < dim; ++d)
-            cx[((size_t)c * nv + v) * dim + d] = tria.vertices[(size_t)tria.cells[(size_t)c * nv + v] * dim + d];
+            cx[((size_t)c * nv + v) * dim + d] = tria.vertices[(size_t)tria.cells[(size_t)local_cells[c] * nv + v] * dim + d];
       d_cell_x.upload(cx, s);
       IFEM_CUDA(cudaStreamSynchronize(s));
     }
@@ -108,7 +151,7 @@ namespace ifem
       const int64_t total = (int64_t)n_cells * nr * nc;
       const int threads = 256;
       build_slots_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(n_cells, nr, nc, rt.p, ct.p, M.rowptr.p,
-                                                                                         M.col.p, d_slots.p, spc, offset, err.p);
+                                                                                         M.col.p, M.n_brows, d_slots.p, spc, offset, err.p);
       IFEM_KERNEL_CHECK();
     };
     launch(nu, nu, d_cell_un, d_cell_un, A_uu, 0);
@@ -117,8 +160,11 @@ namespace ifem
     launch(np, np, d_cell_pn, d_cell_pn, M_p, nu * nu + 2 * nu * np);
     if (err.to_host(s)[0]) throw std::runtime_error("FluidSpace::setup: a matrix row has more than 256 block columns");
 
-    P_schur = build_schur_pattern(tria, pn);
-    S_m.init(P_schur, 1, 1, s);
+    if (n_ranks == 1)
+      {
+        P_schur = build_schur_pattern(tria, pn);
+        S_m.init(P_schur, 1, 1, s);
+      }
 
     con.assign(n_dofs, 0);
     nonzero_val.assign(n_dofs, 0.0);
@@ -131,8 +177,12 @@ namespace ifem
                                     const std::map<unsigned int, std::pair<unsigned int, std::vector<double>>> &dirichlet,
                                     const std::function<bool(int, const double *, int, double &)> &hard_coded)
   {
-    std::fill(con.begin(), con.end(), 0);
-    std::fill(nonzero_val.begin(), nonzero_val.end(), 0.0);
+    // The pass runs over the GLOBAL boundary faces and node table (every rank holds the whole
+    // triangulation), so "first boundary id wins" cannot depend on the partition; the flags are then
+    // restricted to the local dofs.
+    const NodeTable &g = n_ranks > 1 ? un_global : un;
+    std::vector<unsigned char> gcon((size_t)dim * g.n_nodes, 0);
+    std::vector<double> gval((size_t)dim * g.n_nodes, 0.0);
     std::vector<std::vector<int>> face_nodes(2 * dim);
     for (int f = 0; f < 2 * dim; ++f) face_nodes[f] = face_local_nodes(dim, pu, f);
     // std::map iterates boundary ids in ascending order; a dof already constrained
@@ -151,23 +201,34 @@ namespace ifem
             const int cell = tria.boundary_faces[3 * f], face = tria.boundary_faces[3 * f + 1];
             for (int a : face_nodes[face])
               {
-                const int node = un.cell_nodes[(size_t)cell * nu + a];
+                const int node = g.cell_nodes[(size_t)cell * nu + a];
                 for (int c = 0; c < dim; ++c)
                   {
                     if (!(flag & (1u << c))) continue;
-                    const int64_t g = (int64_t)dim * node + c;
-                    if (con[g]) continue;
-                    con[g] = 1;
+                    const int64_t gd = (int64_t)dim * node + c;
+                    if (gcon[gd]) continue;
+                    gcon[gd] = 1;
                     double v = aug[c];
-                    if (hard_coded) hard_coded(id, &un.coords[(size_t)node * dim], c, v);
-                    nonzero_val[g] = v;
+                    if (hard_coded) hard_coded(id, &g.coords[(size_t)node * dim], c, v);
+                    gval[gd] = v;
                   }
               }
           }
       }
+    std::fill(con.begin(), con.end(), 0);
+    std::fill(nonzero_val.begin(), nonzero_val.end(), 0.0);
+    for (int l = 0; l < un.n_nodes; ++l)
+      {
+        const int gn = n_ranks > 1 ? part.u.local_to_global[l] : l;
+        for (int c = 0; c < dim; ++c)
+          {
+            con[(size_t)dim * l + c] = gcon[(size_t)dim * gn + c];
+            nonzero_val[(size_t)dim * l + c] = gval[(size_t)dim * gn + c];
+          }
+      }
     std::vector<int> idx;
-    for (int64_t g = 0; g < n_dofs; ++g)
-      if (con[g]) idx.push_back((int)g);
+    for (int64_t gd = 0; gd < n_dofs; ++gd)
+      if (con[gd]) idx.push_back((int)gd);
     n_con = (int)idx.size();
     cudaStream_t s = ctx.stream;
     d_con.upload(con, s);
@@ -180,11 +241,20 @@ namespace ifem
   {
     std::vector<int> fc;
     std::vector<double> fv;
+    if (neumann.empty())
+      {
+        n_nfaces = 0;
+        return;
+      }
+    std::vector<int> g2l(tria.n_cells(), -1);
+    for (int l = 0; l < n_cells; ++l) g2l[local_cells[l]] = l;
     for (int f = 0; f < tria.n_boundary_faces(); ++f)
       {
         auto it = neumann.find((unsigned)tria.boundary_faces[3 * f + 2]);
         if (it == neumann.end()) continue;
-        fc.push_back(tria.boundary_faces[3 * f]);
+        const int lc = g2l[tria.boundary_faces[3 * f]];
+        if (lc < 0) continue; // not a local cell of this rank
+        fc.push_back(lc);
         fc.push_back(tria.boundary_faces[3 * f + 1]);
         fv.push_back(it->second);
       }
@@ -268,6 +338,7 @@ namespace ifem
       const double *eval_pt, *present, *fsi_acc;
       const int *indicator;
       int64_t n_u;
+      int n_owned_u, n_owned_p; // rows of nodes >= these are ghosts: assembled by their owner
       double mu, gamma, rho, inv_dt, grav[3];
       const unsigned char *con;
       const double *inhom; // null: homogeneous (zero_constraints)
@@ -462,7 +533,7 @@ namespace ifem
                 }
 #pragma unroll
               for (int c = 0; c < DIM; ++c) S.lrhs[aN * DIM + c] = r[c];
-              if (a.assemble_mass)
+              if (a.assemble_mass && S.un[aN] < a.n_owned_u)
                 {
 #pragma unroll
                   for (int c = 0; c < DIM; ++c) a.diag_Mu[(int64_t)DIM * S.un[aN] + c] += m;
@@ -538,6 +609,7 @@ namespace ifem
                   {
                     const int aN = a0 + t;
                     const int A = S.un[aN];
+                    if (A >= a.n_owned_u) continue; // warp-uniform
                     const int64_t rp = a.uu.rowptr[A];
                     const int nb = (int)(a.uu.rowptr[A + 1] - rp);
                     double *base = a.uu.val + rp * (DIM * DIM);
@@ -607,8 +679,9 @@ namespace ifem
                     }
                 }
               const int A = S.un[aN];
-              const int64_t rp = a.up.rowptr[A];
-              const int nb = (int)(a.up.rowptr[A + 1] - rp);
+              const bool own_row = A < a.n_owned_u;
+              const int64_t rp = own_row ? a.up.rowptr[A] : 0;
+              const int nb = own_row ? (int)(a.up.rowptr[A + 1] - rp) : 0;
               double *base = a.up.val + rp * DIM;
               const unsigned char *s_up = slots + NU * NU;
               const unsigned char *s_pu = slots + NU * NU + NU * NP;
@@ -619,8 +692,9 @@ namespace ifem
                   const int pc = S.con[NU * DIM + j];
                   // row = pressure node j, column = velocity node a
                   const int Pn = S.pn[j];
-                  const int64_t rq = a.pu.rowptr[Pn];
-                  const int nbq = (int)(a.pu.rowptr[Pn + 1] - rq);
+                  const bool own_p = Pn < a.n_owned_p;
+                  const int64_t rq = own_p ? a.pu.rowptr[Pn] : 0;
+                  const int nbq = own_p ? (int)(a.pu.rowptr[Pn + 1] - rq) : 0;
                   double *baseq = a.pu.val + rq * DIM;
                   const int slotq = s_pu[j * NU + aN];
 #pragma unroll
@@ -630,8 +704,8 @@ namespace ifem
                       const double v = B[j][c];
                       if (!uc && !pc)
                         {
-                          base[(int64_t)c * nb + slot] += v;    // A_up block row a, plane c
-                          baseq[(int64_t)c * nbq + slotq] += v; // A_pu row j, plane c
+                          if (own_row) base[(int64_t)c * nb + slot] += v;   // A_up block row a, plane c
+                          if (own_p) baseq[(int64_t)c * nbq + slotq] += v;  // A_pu row j, plane c
                         }
                       else if (uc && !pc && a.inhom)
                         atomicAdd(&S.lrhs[NU * DIM + j], -v * S.inh[aN * DIM + c]); // column (a,c) constrained
@@ -647,6 +721,7 @@ namespace ifem
                 double m = 0.0;
                 for (int q = 0; q < NQ; ++q) m = fma(S.JxW[q] * tNp[q * NP + i], tNp[q * NP + j], m);
                 const int Pn = S.pn[i];
+                if (Pn >= a.n_owned_p) continue;
                 const int64_t rp = a.mp.rowptr[Pn];
                 a.mp.val[rp + slots[NU * NU + 2 * NU * NP + e]] += m;
               }
@@ -654,6 +729,8 @@ namespace ifem
           // ---- scatter local rhs through the constraints (distribute_local_to_global) ----
           for (int i = lane; i < T::DPC; i += 32)
             {
+              const bool own = i < NU * DIM ? S.un[i / DIM] < a.n_owned_u : S.pn[i - NU * DIM] < a.n_owned_p;
+              if (!own) continue;
               const int64_t g = i < NU * DIM ? (int64_t)DIM * S.un[i / DIM] + i % DIM : a.n_u + S.pn[i - NU * DIM];
               if (!S.con[i])
                 a.rhs[g] += S.lrhs[i];
@@ -668,7 +745,7 @@ namespace ifem
     template <int DIM>
     __global__ void ins_neumann_kernel(int n_faces, int nqf, const int *__restrict__ face_cell, const double *__restrict__ face_val,
                                        const double *__restrict__ ftab, const int *__restrict__ cell_un,
-                                       const double *__restrict__ cell_x, const unsigned char *__restrict__ con,
+                                       const double *__restrict__ cell_x, const unsigned char *__restrict__ con, int n_owned_u,
                                        double *__restrict__ rhs)
     {
       using T = InsT<DIM>;
@@ -699,8 +776,9 @@ namespace ifem
               const double nds = det * Ji[axis * DIM + c] * (side ? 1.0 : -1.0) * qwf[q];
               r -= Nf[fq * NU + node] * nds * pbar;
             }
-          const int64_t g = (int64_t)DIM * cell_un[(int64_t)cell * NU + node] + c;
-          if (!con[g] && r != 0.0) atomicAdd(&rhs[g], r);
+          const int gn = cell_un[(int64_t)cell * NU + node];
+          const int64_t g = (int64_t)DIM * gn + c;
+          if (gn < n_owned_u && !con[g] && r != 0.0) atomicAdd(&rhs[g], r);
         }
     }
   } // namespace
@@ -732,6 +810,8 @@ namespace ifem
     a.fsi_acc = fsi_acc;
     a.indicator = fs.d_indicator.p;
     a.n_u = fs.n_u;
+    a.n_owned_u = fs.n_owned_unodes;
+    a.n_owned_p = fs.n_owned_pnodes;
     a.mu = prm.viscosity;
     a.gamma = prm.gamma;
     a.rho = prm.rho;
@@ -767,7 +847,7 @@ namespace ifem
     if (fs.n_nfaces)
       {
         ins_neumann_kernel<DIM><<<fs.n_nfaces, 64, 0, s>>>(fs.n_nfaces, fs.nqf, fs.d_nface_cell.p, fs.d_nface_val.p,
-                                                           fs.d_face_tables.p, fs.d_cell_un.p, fs.d_cell_x.p, fs.d_con.p, fs.rhs.p);
+                                                           fs.d_face_tables.p, fs.d_cell_un.p, fs.d_cell_x.p, fs.d_con.p, fs.n_owned_unodes, fs.rhs.p);
         IFEM_KERNEL_CHECK();
         ctx.kernel_launches++;
       }
@@ -784,6 +864,8 @@ namespace ifem
 
   void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y)
   {
+    // ghost entries of x are scratch by design: refresh them from their owners first
+    const_cast<FluidSpace &>(fs).halo_update(ctx, const_cast<double *>(x));
     spmv(ctx, fs.A_uu, x, y, false);
     spmv(ctx, fs.A_up, x + fs.n_u, y, true);
     spmv(ctx, fs.A_pu, x, y + fs.n_u, false);
@@ -844,8 +926,18 @@ namespace ifem
     }
   } // namespace
 
+  void apply_mass_schur_matrix_free(Context &ctx, FluidSpace &fs, const double *x_p, double *y_p, double *tmp_u)
+  {
+    fs.halo_p.update(ctx, const_cast<double *>(x_p));
+    spmv(ctx, fs.A_up, x_p, tmp_u);
+    divide(ctx, fs.vs_u, fs.diag_Mu.p, tmp_u);
+    fs.halo_u.update(ctx, tmp_u);
+    spmv(ctx, fs.A_pu, tmp_u, y_p);
+  }
+
   void compute_mass_schur(Context &ctx, FluidSpace &fs)
   {
+    if (fs.n_ranks > 1) throw std::runtime_error("compute_mass_schur: explicit S_m is single-rank only");
     const int n_p = (int)fs.n_p;
     const int blocks = (n_p + 3) / 4;
     auto go = [&](auto tag) {

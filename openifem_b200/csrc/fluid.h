@@ -15,6 +15,7 @@
 #include <memory>
 
 #include "fe_tables.h"
+#include "halo.h"
 #include "linalg.h"
 #include "mesh.h"
 #include "parameters.h"
@@ -26,8 +27,18 @@ namespace ifem
     int dim = 0, pu = 0, pp = 0;
     int nu = 0, np = 0, nq = 0, nv = 0; // per cell: velocity nodes, pressure nodes, quadrature points, vertices
     int n_cells = 0;
-    NodeTable un, pn;
-    int64_t n_u = 0, n_p = 0, n_dofs = 0;
+    NodeTable un, pn;                     // LOCAL node tables of this rank (owned nodes first, then ghosts)
+    int64_t n_u = 0, n_p = 0, n_dofs = 0; // local vector sizes: dim * un.n_nodes, pn.n_nodes, sum
+    // domain decomposition (single rank: everything owned, no halos)
+    int rank = 0, n_ranks = 1;
+    Partition part;
+    NodeTable un_global, pn_global;       // kept on multi-rank runs for the global constraint pass
+    std::vector<int> local_cells;         // global cell id of each local cell
+    int n_owned_unodes = 0, n_owned_pnodes = 0;
+    Halo halo_u, halo_p;
+    VecSpace vs_all, vs_u, vs_p;          // owned entries of a block / velocity / pressure vector
+    // refresh ghost entries of a block vector [u | p]
+    void halo_update(Context &ctx, double *x) { halo_u.update(ctx, x); halo_p.update(ctx, x + n_u); }
 
     // host FE tables (kept for face terms and point evaluation)
     FEQ fe_u, fe_p, fe_geo;
@@ -88,6 +99,8 @@ namespace ifem
   // y = A x on the 2x2 block system (BlockSparseMatrix::vmult)
   void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y);
 
-  // S_m = B diag(M_u)^-1 B^T on the fixed Schur pattern (mpi_insim.cpp:44-49)
+  // S_m = B diag(M_u)^-1 B^T on the fixed Schur pattern (mpi_insim.cpp:44-49); single rank only
   void compute_mass_schur(Context &ctx, FluidSpace &fs);
+  // y_p = B diag(M_u)^-1 B^T x_p applied matrix-free (two SpMVs + halos): the multi-rank form of S_m
+  void apply_mass_schur_matrix_free(Context &ctx, FluidSpace &fs, const double *x_p, double *y_p, double *tmp_u);
 } // namespace ifem

@@ -1,5 +1,7 @@
 #include "insim.h"
 
+#include "comm.h"
+
 #include <chrono>
 #include <cstdio>
 
@@ -74,15 +76,36 @@ namespace ifem
         v->alloc(n);
         v->zero(ctx.stream);
       }
-    d_binv.alloc((size_t)fs.un.n_nodes * fs.dim * fs.dim);
+    d_binv.alloc((size_t)fs.n_owned_unodes * fs.dim * fs.dim);
     d_tmp_p.alloc(fs.n_p);
     d_utmp.alloc(fs.n_u);
+    if (fs.n_ranks > 1) d_utmp2.alloc(fs.n_u);
+    // global sizes (iteration caps of the reference are the global matrix dimensions)
+    n_dofs_global = fs.vs_all.n_owned();
+    n_p_global = fs.vs_p.n_owned();
+    if (fs.n_ranks > 1)
+      {
+        DevBuf<double> cnt(2);
+        const double h[2] = {(double)n_dofs_global, (double)n_p_global};
+        cnt.upload(h, 2, ctx.stream);
+        comm_allreduce_sum(*ctx.comm, cnt.p, 2, ctx.stream);
+        const std::vector<double> g = cnt.to_host(ctx.stream);
+        n_dofs_global = (int64_t)g[0];
+        n_p_global = (int64_t)g[1];
+      }
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
 
   void InsIM::assemble(bool use_nonzero_constraints)
   {
     ScopedTimer t(ctx, timer_ms["Assemble system"]);
+    if (fs.n_ranks > 1)
+      {
+        // the gather in the cell loop reads ghosted vectors (get_function_values on ghosted PETSc vectors)
+        fs.halo_update(ctx, evaluation_point.p);
+        fs.halo_update(ctx, present_solution.p);
+        fs.halo_update(ctx, fsi_acceleration.p);
+      }
     InsAssembleParams p;
     p.viscosity = parameters.viscosity;
     p.gamma = parameters.grad_div;
@@ -95,39 +118,51 @@ namespace ifem
   // BlockSchurPreconditioner::vmult (mpi_insim.cpp:56-128)
   void InsIM::precondition(const double *src, double *dst)
   {
-    const int64_t n_u = fs.n_u, n_p = fs.n_p;
+    const int64_t n_u = fs.n_u;
+    const VecSpace &vu = fs.vs_u, &vp = fs.vs_p;
     const double *src_u = src, *src_p = src + n_u;
     double *dst_u = dst, *dst_p = dst + n_u;
     double *tmp = d_tmp_p.p, *utmp = d_utmp.p;
-    const double nrm = nrm2(ctx, n_p, src_p);
+    const double nrm = nrm2(ctx, vp, src_p);
+    const int max_p_its = (int)std::min<int64_t>(n_p_global, 1 << 30);
     {
       ScopedTimer t(ctx, timer_ms["CG for Mp"]);
-      fill(ctx, n_p, 0.0, tmp);
-      LinOp Mp = [&](const double *x, double *y) { spmv(ctx, fs.M_p, x, y); };
-      const SolveResult r = cg(ctx, n_p, Mp, src_p, tmp, true, std::max(control.cg_floor, control.cg_mp_rel * nrm), (int)n_p, pool_cg);
+      fill(ctx, vp, 0.0, tmp);
+      LinOp Mp = [&](const double *x, double *y) {
+        fs.halo_p.update(ctx, const_cast<double *>(x));
+        spmv(ctx, fs.M_p, x, y);
+      };
+      const SolveResult r = cg(ctx, vp, Mp, src_p, tmp, true, std::max(control.cg_floor, control.cg_mp_rel * nrm), max_p_its, pool_cg);
       cur.cg_mp_its += r.iterations;
-      scale(ctx, n_p, -(parameters.viscosity + parameters.grad_div * parameters.fluid_rho), tmp);
+      scale(ctx, vp, -(parameters.viscosity + parameters.grad_div * parameters.fluid_rho), tmp);
     }
     {
       ScopedTimer t(ctx, timer_ms["CG for Sm"]);
-      fill(ctx, n_p, 0.0, dst_p);
-      LinOp Sm = [&](const double *x, double *y) { spmv(ctx, fs.S_m, x, y); };
-      const SolveResult r = cg(ctx, n_p, Sm, src_p, dst_p, true, std::max(control.cg_floor, control.cg_sm_rel * nrm), (int)n_p, pool_cg);
+      fill(ctx, vp, 0.0, dst_p);
+      LinOp Sm = [&](const double *x, double *y) {
+        if (fs.n_ranks > 1)
+          apply_mass_schur_matrix_free(ctx, fs, x, y, d_utmp2.p);
+        else
+          spmv(ctx, fs.S_m, x, y);
+      };
+      const SolveResult r = cg(ctx, vp, Sm, src_p, dst_p, true, std::max(control.cg_floor, control.cg_sm_rel * nrm), max_p_its, pool_cg);
       cur.cg_sm_its += r.iterations;
       // dst_p = -rho/dt * dst_p + tmp
-      axpby(ctx, n_p, 1.0, tmp, -parameters.fluid_rho / time.get_delta_t(), dst_p);
+      axpby(ctx, vp, 1.0, tmp, -parameters.fluid_rho / time.get_delta_t(), dst_p);
     }
     // utmp = src_u - B^T dst_p
+    fs.halo_p.update(ctx, dst_p);
     spmv(ctx, fs.A_up, dst_p, utmp);
-    axpby(ctx, n_u, 1.0, src_u, -1.0, utmp);
+    axpby(ctx, vu, 1.0, src_u, -1.0, utmp);
     {
       ScopedTimer t(ctx, timer_ms["A_inv"]);
       LinOp Auu = [&](const double *x, double *y) {
+        fs.halo_u.update(ctx, const_cast<double *>(x));
         if (control.a_inv_fp32) spmv_fp32(ctx, fs.A_uu, x, y); else spmv(ctx, fs.A_uu, x, y);
       };
-      LinOp jac = [&](const double *x, double *y) { block_diag_apply(ctx, fs.un.n_nodes, fs.dim, d_binv.p, x, y); };
-      const double unrm = nrm2(ctx, n_u, utmp);
-      const SolveResult r = bicgstab(ctx, n_u, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);
+      LinOp jac = [&](const double *x, double *y) { block_diag_apply(ctx, fs.n_owned_unodes, fs.dim, d_binv.p, x, y); };
+      const double unrm = nrm2(ctx, vu, utmp);
+      const SolveResult r = bicgstab(ctx, vu, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);
       cur.a_inv_its += r.iterations;
     }
     cur.precond_applies++;
@@ -137,16 +172,15 @@ namespace ifem
   {
     ScopedTimer t(ctx, timer_ms["Solve linear system"]);
     // BlockSchurPreconditioner ctor (mpi_insim.cpp:13-50)
-    compute_mass_schur(ctx, fs);
+    if (fs.n_ranks == 1) compute_mass_schur(ctx, fs);
     block_diag_inverse(ctx, fs.A_uu, d_binv.p);
     if (control.a_inv_fp32) make_fp32_copy(ctx, fs.A_uu);
-    const int64_t n = fs.n_dofs;
-    const double nrm = nrm2(ctx, n, fs.rhs.p);
-    const double tol = control.fgmres_floor_is_max ? std::max(control.fgmres_floor, control.fgmres_rel * nrm)
-                                                   : std::max(control.fgmres_floor, control.fgmres_rel * nrm);
+    const VecSpace &va = fs.vs_all;
+    const double nrm = nrm2(ctx, va, fs.rhs.p);
+    const double tol = std::max(control.fgmres_floor, control.fgmres_rel * nrm);
     LinOp A = [&](const double *x, double *y) { block_vmult(ctx, fs, x, y); };
     LinOp P = [&](const double *x, double *y) { precondition(x, y); };
-    const SolveResult r = fgmres(ctx, n, A, P, fs.rhs.p, newton_update.p, tol, n, control.basis_size, pool_fgmres);
+    const SolveResult r = fgmres(ctx, va, A, P, fs.rhs.p, newton_update.p, tol, n_dofs_global, control.basis_size, pool_fgmres);
     // constraints_used.distribute(newton_update)
     if (fs.n_con) set_indexed(ctx, fs.n_con, fs.d_con_idx.p, use_nonzero_constraints ? d_con_vals.p : nullptr, newton_update.p);
     return {(unsigned)r.iterations, r.residual};
@@ -155,11 +189,11 @@ namespace ifem
   void InsIM::run_one_step(bool apply_nonzero_constraints, bool /*assemble_system*/)
   {
     time.increment();
-    if (verbose)
+    if (verbose && fs.rank == 0)
       std::printf("%s\nTime step = %u, at t = %e\n", std::string(96, '*').c_str(), time.get_timestep(), time.current());
     double current_residual = 1.0, initial_residual = 1.0, relative_residual = 1.0;
     unsigned int outer_iteration = 0;
-    const int64_t n = fs.n_dofs;
+    const VecSpace &n = fs.vs_all;
     copy(ctx, n, present_solution.p, evaluation_point.p);
     while (relative_residual > parameters.fluid_tolerance && current_residual > 1e-11)
       {
@@ -171,6 +205,7 @@ namespace ifem
         const auto state = solve(nz);
         current_residual = nrm2(ctx, n, fs.rhs.p);
         axpy(ctx, n, 1.0, newton_update.p, evaluation_point.p);
+        fs.halo_update(ctx, evaluation_point.p); // evaluation_point = tmp (ghosted), mpi_insim.cpp:444-448
         if (outer_iteration == 0) initial_residual = current_residual;
         relative_residual = current_residual / initial_residual;
         cur.timestep = time.get_timestep();
@@ -180,7 +215,7 @@ namespace ifem
         cur.gmres_its = (int)state.first;
         cur.gmres_res = state.second;
         history.push_back(cur);
-        if (verbose)
+        if (verbose && fs.rank == 0)
           std::printf(" ITR = %-2u ABS_RES = %e REL_RES = %e GMRES_ITR = %-3u GMRES_RES = %e  [cg_mp %d cg_sm %d a_inv %d / %d]\n",
                       outer_iteration, current_residual, relative_residual, state.first, state.second, cur.cg_mp_its,
                       cur.cg_sm_its, cur.a_inv_its, cur.precond_applies);

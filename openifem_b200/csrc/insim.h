@@ -110,7 +110,8 @@ namespace ifem
 
   private:
     void precondition(const double *src, double *dst);
-    DevBuf<double> d_binv, d_con_vals, d_tmp_p, d_utmp;
+    DevBuf<double> d_binv, d_con_vals, d_tmp_p, d_utmp, d_utmp2;
+    int64_t n_dofs_global = 0, n_p_global = 0;
     VecPool pool_fgmres, pool_cg, pool_ainv;
     NewtonRecord cur{};
   };

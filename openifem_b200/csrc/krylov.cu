@@ -2,10 +2,10 @@
 
 namespace ifem
 {
-  SolveResult cg(Context &ctx, int64_t n, const LinOp &A, const double *b, double *x, bool x_is_zero, double tol_abs, int max_it,
+  SolveResult cg(Context &ctx, const VecSpace &n, const LinOp &A, const double *b, double *x, bool x_is_zero, double tol_abs, int max_it,
                  VecPool &pool)
   {
-    double *r = pool.get(0, n), *p = pool.get(1, n), *Ap = pool.get(2, n);
+    double *r = pool.get(0, n.n_alloc), *p = pool.get(1, n.n_alloc), *Ap = pool.get(2, n.n_alloc);
     SolveResult out;
     if (x_is_zero)
       copy(ctx, n, b, r);
@@ -42,11 +42,11 @@ namespace ifem
     return out;
   }
 
-  SolveResult bicgstab(Context &ctx, int64_t n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
+  SolveResult bicgstab(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
                        int max_it, VecPool &pool)
   {
-    double *r = pool.get(0, n), *r0 = pool.get(1, n), *p = pool.get(2, n), *v = pool.get(3, n), *ph = pool.get(4, n),
-           *s = pool.get(5, n), *sh = pool.get(6, n), *t = pool.get(7, n);
+    double *r = pool.get(0, n.n_alloc), *r0 = pool.get(1, n.n_alloc), *p = pool.get(2, n.n_alloc), *v = pool.get(3, n.n_alloc), *ph = pool.get(4, n.n_alloc),
+           *s = pool.get(5, n.n_alloc), *sh = pool.get(6, n.n_alloc), *t = pool.get(7, n.n_alloc);
     SolveResult out;
     fill(ctx, n, 0.0, x);
     copy(ctx, n, b, r);
@@ -94,13 +94,13 @@ namespace ifem
     return out;
   }
 
-  SolveResult fgmres(Context &ctx, int64_t n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
+  SolveResult fgmres(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
                      int64_t max_it, int m, VecPool &pool)
   {
     // pool slots: 0 aux, 1..m V, m+1..2m Z
-    double *aux = pool.get(0, n);
-    auto V = [&](int j) { return pool.get(1 + j, n); };
-    auto Z = [&](int j) { return pool.get(1 + m + j, n); };
+    double *aux = pool.get(0, n.n_alloc);
+    auto V = [&](int j) { return pool.get(1 + j, n.n_alloc); };
+    auto Z = [&](int j) { return pool.get(1 + m + j, n.n_alloc); };
     SolveResult out;
     fill(ctx, n, 0.0, x);
     int64_t accumulated = 0;

@@ -42,13 +42,13 @@ namespace ifem
     }
   };
 
-  SolveResult cg(Context &ctx, int64_t n, const LinOp &A, const double *b, double *x, bool x_is_zero, double tol_abs, int max_it,
+  SolveResult cg(Context &ctx, const VecSpace &n, const LinOp &A, const double *b, double *x, bool x_is_zero, double tol_abs, int max_it,
                  VecPool &pool);
 
-  SolveResult bicgstab(Context &ctx, int64_t n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
+  SolveResult bicgstab(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
                        int max_it, VecPool &pool);
 
   // x0 = 0 is assumed (x is overwritten). Throws on failure like deal.II's NoConvergence.
-  SolveResult fgmres(Context &ctx, int64_t n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
+  SolveResult fgmres(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
                      int64_t max_it, int basis_size, VecPool &pool);
 } // namespace ifem

@@ -216,6 +216,13 @@ namespace ifem
   {
     constexpr int kThreads = 256;
 
+    struct Seg
+    {
+      int64_t len0, shift, total; // i >= len0 -> i + shift
+      __host__ __device__ int64_t operator()(int64_t i) const { return i < len0 ? i : i + shift; }
+    };
+    inline Seg seg_of(const VecSpace &v) { return Seg{v.len0, v.off1 - v.len0, v.len0 + v.len1}; }
+
     inline int grid_for(const Context &ctx, int64_t n)
     {
       const int64_t want = (n + kThreads * 4 - 1) / (kThreads * 4);
@@ -239,23 +246,27 @@ namespace ifem
       return r;
     }
 
-    __global__ void __launch_bounds__(kThreads) dot_partial_kernel(int64_t n, const double *__restrict__ x,
+    __global__ void __launch_bounds__(kThreads) dot_partial_kernel(Seg sg, const double *__restrict__ x,
                                                                    const double *__restrict__ y, double *__restrict__ partial)
     {
       double s = 0.0;
-      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        s = fma(x[i], y[i], s);
+      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < sg.total; k += (int64_t)gridDim.x * blockDim.x)
+        {
+          const int64_t i = sg(k);
+          s = fma(x[i], y[i], s);
+        }
       s = block_sum(s);
       if (threadIdx.x == 0) partial[blockIdx.x] = s;
     }
 
     __global__ void __launch_bounds__(kThreads)
-    add_and_dot_partial_kernel(int64_t n, double *__restrict__ aux, double a, const double *__restrict__ V,
+    add_and_dot_partial_kernel(Seg sg, double *__restrict__ aux, double a, const double *__restrict__ V,
                                const double *__restrict__ W, double *__restrict__ partial)
     {
       double s = 0.0;
-      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < sg.total; k += (int64_t)gridDim.x * blockDim.x)
         {
+          const int64_t i = sg(k);
           const double t = fma(a, V[i], aux[i]);
           aux[i] = t;
           // W may alias aux (norm of the updated vector)
@@ -279,80 +290,82 @@ namespace ifem
       reduce_final_kernel<<<1, kThreads, 0, ctx.stream>>>(g, ctx.partials.p, ctx.results.p);
       IFEM_KERNEL_CHECK();
       ctx.kernel_launches++;
-      if (ctx.comm) comm_allreduce_sum(*ctx.comm, ctx.results.p, 1, ctx.stream);
+      if (ctx.comm && ctx.comm->size > 1) comm_allreduce_sum(*ctx.comm, ctx.results.p, 1, ctx.stream);
       IFEM_CUDA(cudaMemcpyAsync(ctx.h_results, ctx.results.p, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
       IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
       return ctx.h_results[0];
     }
 
     template <typename F>
-    __global__ void __launch_bounds__(kThreads) map_kernel(int64_t n, F f)
+    __global__ void __launch_bounds__(kThreads) map_kernel(Seg sg, F f)
     {
-      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < sg.total; k += (int64_t)gridDim.x * blockDim.x) f(sg(k));
     }
 
     template <typename F>
-    void map(Context &ctx, int64_t n, F f)
+    void map(Context &ctx, const VecSpace &vs, F f)
     {
+      const int64_t n = vs.n_owned();
       if (n <= 0) return;
       const int64_t want = (n + kThreads - 1) / kThreads;
       const int g = (int)std::min<int64_t>(want, (int64_t)ctx.sm_count * 16);
-      map_kernel<<<g, kThreads, 0, ctx.stream>>>(n, f);
+      map_kernel<<<g, kThreads, 0, ctx.stream>>>(seg_of(vs), f);
       IFEM_KERNEL_CHECK();
       ctx.kernel_launches++;
     }
   } // namespace
 
-  double dot(Context &ctx, int64_t n, const double *x, const double *y)
+  double dot(Context &ctx, const VecSpace &n, const double *x, const double *y)
   {
-    const int g = grid_for(ctx, n);
-    dot_partial_kernel<<<g, kThreads, 0, ctx.stream>>>(n, x, y, ctx.partials.p);
+    const int g = grid_for(ctx, n.n_owned());
+    dot_partial_kernel<<<g, kThreads, 0, ctx.stream>>>(seg_of(n), x, y, ctx.partials.p);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
     return finish_reduction(ctx, g);
   }
 
-  double nrm2(Context &ctx, int64_t n, const double *x) { return std::sqrt(dot(ctx, n, x, x)); }
+  double nrm2(Context &ctx, const VecSpace &n, const double *x) { return std::sqrt(dot(ctx, n, x, x)); }
 
-  double add_and_dot(Context &ctx, int64_t n, double *aux, double a, const double *V, const double *W)
+  double add_and_dot(Context &ctx, const VecSpace &n, double *aux, double a, const double *V, const double *W)
   {
-    const int g = grid_for(ctx, n);
-    add_and_dot_partial_kernel<<<g, kThreads, 0, ctx.stream>>>(n, aux, a, V, W, ctx.partials.p);
+    const int g = grid_for(ctx, n.n_owned());
+    add_and_dot_partial_kernel<<<g, kThreads, 0, ctx.stream>>>(seg_of(n), aux, a, V, W, ctx.partials.p);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
     return finish_reduction(ctx, g);
   }
 
-  void axpy(Context &ctx, int64_t n, double a, const double *x, double *y)
+  void axpy(Context &ctx, const VecSpace &n, double a, const double *x, double *y)
   {
     map(ctx, n, [=] __device__(int64_t i) { y[i] = fma(a, x[i], y[i]); });
   }
-  void axpby(Context &ctx, int64_t n, double a, const double *x, double b, double *y)
+  void axpby(Context &ctx, const VecSpace &n, double a, const double *x, double b, double *y)
   {
     map(ctx, n, [=] __device__(int64_t i) { y[i] = a * x[i] + b * y[i]; });
   }
-  void scale(Context &ctx, int64_t n, double a, double *x)
+  void scale(Context &ctx, const VecSpace &n, double a, double *x)
   {
     map(ctx, n, [=] __device__(int64_t i) { x[i] *= a; });
   }
-  void equ(Context &ctx, int64_t n, double a, const double *x, double *y)
+  void equ(Context &ctx, const VecSpace &n, double a, const double *x, double *y)
   {
     map(ctx, n, [=] __device__(int64_t i) { y[i] = a * x[i]; });
   }
-  void copy(Context &ctx, int64_t n, const double *x, double *y)
+  void copy(Context &ctx, const VecSpace &n, const double *x, double *y)
   {
-    if (n > 0) IFEM_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+    // whole allocation, ghosts included (they are scratch between halo updates)
+    if (n.n_alloc > 0) IFEM_CUDA(cudaMemcpyAsync(y, x, n.n_alloc * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
   }
-  void fill(Context &ctx, int64_t n, double v, double *x)
+  void fill(Context &ctx, const VecSpace &n, double v, double *x)
   {
     if (v == 0.0)
       {
-        if (n > 0) IFEM_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), ctx.stream));
+        if (n.n_alloc > 0) IFEM_CUDA(cudaMemsetAsync(x, 0, n.n_alloc * sizeof(double), ctx.stream));
         return;
       }
     map(ctx, n, [=] __device__(int64_t i) { x[i] = v; });
   }
-  void lin3(Context &ctx, int64_t n, double *z, const double *x, double a, const double *y, double b, const double *w)
+  void lin3(Context &ctx, const VecSpace &n, double *z, const double *x, double a, const double *y, double b, const double *w)
   {
     map(ctx, n, [=] __device__(int64_t i) { z[i] = x[i] + a * y[i] + b * w[i]; });
   }
@@ -360,7 +373,11 @@ namespace ifem
   {
     map(ctx, n_idx, [=] __device__(int64_t k) { x[idx[k]] = vals ? vals[k] : 0.0; });
   }
-  void reciprocal(Context &ctx, int64_t n, const double *x, double *y)
+  void divide(Context &ctx, const VecSpace &n, const double *d, double *y)
+  {
+    map(ctx, n, [=] __device__(int64_t i) { y[i] /= d[i]; });
+  }
+  void reciprocal(Context &ctx, const VecSpace &n, const double *x, double *y)
   {
     map(ctx, n, [=] __device__(int64_t i) { y[i] = 1.0 / x[i]; });
   }

@@ -49,23 +49,38 @@ namespace ifem
   // Only legal inside a flexible preconditioner (the A~^-1 stand-in), never for the operator itself.
   void spmv_fp32(Context &ctx, const Bcsr &A, const double *x, double *y);
 
-  // ---- BLAS-1 on device vectors (deterministic two-stage reductions) -----------
-  double dot(Context &ctx, int64_t n, const double *x, const double *y);
-  double nrm2(Context &ctx, int64_t n, const double *x);
-  void axpy(Context &ctx, int64_t n, double a, const double *x, double *y);             // y += a x
-  void axpby(Context &ctx, int64_t n, double a, const double *x, double b, double *y);  // y = a x + b y
-  void scale(Context &ctx, int64_t n, double a, double *x);                              // x *= a
-  void equ(Context &ctx, int64_t n, double a, const double *x, double *y);               // y = a x
-  void copy(Context &ctx, int64_t n, const double *x, double *y);
-  void fill(Context &ctx, int64_t n, double v, double *x);
+  // Index space of a distributed vector on this rank: the entries a Krylov method owns are up to two
+  // contiguous segments [0, len0) and [off1, off1 + len1) of an allocation of n_alloc doubles (the rest
+  // are ghost copies refreshed by halo exchange). A plain length converts to a single segment.
+  struct VecSpace
+  {
+    int64_t len0 = 0, off1 = 0, len1 = 0, n_alloc = 0;
+    VecSpace() = default;
+    VecSpace(int64_t n) : len0(n), off1(0), len1(0), n_alloc(n) {}
+    VecSpace(int64_t l0, int64_t o1, int64_t l1, int64_t alloc) : len0(l0), off1(o1), len1(l1), n_alloc(alloc) {}
+    int64_t n_owned() const { return len0 + len1; }
+  };
+
+  // ---- BLAS-1 on device vectors (deterministic two-stage reductions; dot products are summed over
+  //      the ranks of ctx.comm) -----------
+  double dot(Context &ctx, const VecSpace &n, const double *x, const double *y);
+  double nrm2(Context &ctx, const VecSpace &n, const double *x);
+  void axpy(Context &ctx, const VecSpace &n, double a, const double *x, double *y);             // y += a x
+  void axpby(Context &ctx, const VecSpace &n, double a, const double *x, double b, double *y);  // y = a x + b y
+  void scale(Context &ctx, const VecSpace &n, double a, double *x);                              // x *= a
+  void equ(Context &ctx, const VecSpace &n, double a, const double *x, double *y);               // y = a x
+  void copy(Context &ctx, const VecSpace &n, const double *x, double *y);
+  void fill(Context &ctx, const VecSpace &n, double v, double *x);
   // aux += a V ; return aux . W   (deal.II Vector::add_and_dot, used by FGMRES' MGS)
-  double add_and_dot(Context &ctx, int64_t n, double *aux, double a, const double *V, const double *W);
+  double add_and_dot(Context &ctx, const VecSpace &n, double *aux, double a, const double *V, const double *W);
   // z = x + a y + b w
-  void lin3(Context &ctx, int64_t n, double *z, const double *x, double a, const double *y, double b, const double *w);
+  void lin3(Context &ctx, const VecSpace &n, double *z, const double *x, double a, const double *y, double b, const double *w);
   // x[idx[k]] = vals ? vals[k] : 0   (AffineConstraints::distribute for Dirichlet lines)
   void set_indexed(Context &ctx, int n_idx, const int *idx, const double *vals, double *x);
+  // y[i] /= d[i]
+  void divide(Context &ctx, const VecSpace &n, const double *d, double *y);
   // y[i] = 1 / x[i]
-  void reciprocal(Context &ctx, int64_t n, const double *x, double *y);
+  void reciprocal(Context &ctx, const VecSpace &n, const double *x, double *y);
   // block-diagonal apply: y_node = Binv_node * x_node (dim x dim blocks, row-major)
   void block_diag_apply(Context &ctx, int n_nodes, int bs, const double *binv, const double *x, double *y);
   // extract and invert the bs x bs diagonal blocks of a square Bcsr with R = C = bs

@@ -1,0 +1,36 @@
+"""The C++ facade (include/openifem/openifem.h) compiles against the C ABI with plain g++ (CPU check) and
+the reference's fluid_pipe_mpi driver passes its golden assertion through it on the GPU."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "_build", "fluid_pipe_mpi")
+
+
+def _build():
+    from openifem_b200 import build
+
+    lib = build.build()
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "fluid_pipe_mpi.cpp"),
+           "-o", EXE, "-L", os.path.dirname(lib), "-lopenifem_b200", f"-Wl,-rpath,{os.path.dirname(lib)}"]
+    subprocess.check_call(cmd)
+
+
+def test_cpp_driver_compiles_and_fails_loudly_without_gpu(golden_dir):
+    _build()
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([EXE, os.path.join(golden_dir, "ins_pipe_2d.prm")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_driver_reference_golden(golden_dir):
+    _build()
+    r = subprocess.run([EXE, os.path.join(golden_dir, "ins_pipe_2d.prm")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout

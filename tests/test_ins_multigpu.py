@@ -1,0 +1,140 @@
+"""Multi-GPU parity: the slab-partitioned path (owner-computes assembly, NCCL halo exchange,
+all-reduced Krylov dot products, matrix-free S_m) must reproduce the single-GPU path, which the other GPU
+tests tie to the oracle. Needs >= 2 GPUs (run with `gpurun --gpus 2`); skipped otherwise.
+
+Tolerances: block SpMV 1e-13 relative; Newton residual history and final fields 1e-6 relative with the
+linear solves tightened on both sides (same rule as tests/test_ins_gpu.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def _worker(rank, size, idfile, dim, reps, steps, q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import time
+
+        import torch
+
+        torch.cuda.set_device(rank)
+        from util import cavity_prm
+
+        import openifem_b200 as ifem
+
+        ifem.init(rank)
+        if size > 1:
+            if rank == 0:
+                uid = ifem.comm_unique_id()
+                with open(idfile + ".tmp", "wb") as f:
+                    f.write(uid)
+                os.replace(idfile + ".tmp", idfile)
+            else:
+                while not os.path.exists(idfile):
+                    time.sleep(0.05)
+                uid = open(idfile, "rb").read()
+            ifem.comm_init(rank, size, uid)
+        tria = ifem.Triangulation(dim)
+        ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
+        flow = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(text=cavity_prm(dim, newton_tol=1e-9)))
+        flow.setup()
+        flow.set_control(a_inv_rel=1e-10, a_inv_max_it=5000, fgmres_rel=1e-9)
+        n_un_glob = int(np.prod([2 * k + 1 for k in reps]))
+        n_pn_glob = int(np.prod([k + 1 for k in reps]))
+        n_glob = dim * n_un_glob + n_pn_glob
+        loc, glo = flow.owned_global_dofs(n_un_glob)
+        # block SpMV of a global vector known to every rank
+        gu, gp = flow.local_to_global(0).astype(np.int64), flow.local_to_global(1).astype(np.int64)
+        xg = np.sin(0.11 * np.arange(n_glob)) + 0.3
+        ev = 0.1 * np.cos(0.05 * np.arange(n_glob))
+
+        def localise(vg):
+            vu = vg[(gu[:, None] * dim + np.arange(dim)[None, :]).ravel()]
+            return np.concatenate([vu, vg[dim * n_un_glob + gp]])
+
+        flow.set_vector(flow.EVALUATION_POINT, localise(ev))
+        flow.set_vector(flow.PRESENT, localise(0.5 * ev))
+        flow.assemble(True)
+        y = flow.vmult(localise(xg))
+        rhs = flow.get_vector(flow.SYSTEM_RHS)
+        # time steps from rest
+        zero = np.zeros(flow.n_dofs)
+        flow.set_vector(flow.EVALUATION_POINT, zero)
+        flow.set_vector(flow.PRESENT, zero)
+        for k in range(steps):
+            flow.run_one_step(k == 0)
+        sol = flow.get_current_solution()
+        hist = [(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in flow.history()]
+        q.put((rank, "ok", glo, y[loc], rhs[loc], sol[loc], hist))
+        if size > 1:
+            ifem.comm_finalize()
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, "fail", traceback.format_exc(), None, None, None, None))
+
+
+def _run(size, dim, reps, steps, tmp_path):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    idfile = str(tmp_path / f"nccl_id_{size}")
+    procs = [ctx.Process(target=_worker, args=(r, size, idfile, dim, reps, steps, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert r[1] == "ok", f"rank {r[0]} failed:\n{r[2]}"
+    n = sum(len(r[2]) for r in res)
+    y, rhs, sol = np.zeros(n), np.zeros(n), np.zeros(n)
+    seen = np.zeros(n, dtype=int)
+    for r in res:
+        y[r[2]], rhs[r[2]], sol[r[2]] = r[3], r[4], r[5]
+        seen[r[2]] += 1
+    assert np.all(seen == 1)  # owned dofs of the ranks tile the global vector exactly once
+    hist = [r for r in res if r[0] == 0][0][6]
+    return y, rhs, sol, hist
+
+
+@pytest.mark.parametrize("dim,reps,size", [(3, (4, 4, 6), 2), (2, (6, 8), 2)])
+def test_two_ranks_match_one_rank(dim, reps, size, tmp_path):
+    if _n_gpus() < size:
+        pytest.skip(f"needs {size} GPUs")
+    y1, rhs1, sol1, h1 = _run(1, dim, reps, 2, tmp_path)
+    y2, rhs2, sol2, h2 = _run(size, dim, reps, 2, tmp_path)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(y2, y1) < 1e-13
+    assert rel(rhs2, rhs1) < 1e-13
+    assert len(h1) == len(h2)
+    for a, b in zip(h2, h1):
+        assert a[:2] == b[:2]
+        assert abs(a[2] - b[2]) <= 1e-6 * max(b[2], 1e-9)
+    nu = dim * int(np.prod([2 * k + 1 for k in reps]))
+    assert rel(sol2[:nu], sol1[:nu]) < 1e-6
+    p2, p1 = sol2[nu:] - sol2[nu:].mean(), sol1[nu:] - sol1[nu:].mean()
+    assert rel(p2, p1) < 1e-6
+
+
+def test_four_ranks_match_one_rank(tmp_path):
+    if _n_gpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    y1, rhs1, sol1, h1 = _run(1, 3, (4, 4, 12), 1, tmp_path)
+    y4, rhs4, sol4, h4 = _run(4, 3, (4, 4, 12), 1, tmp_path)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(y4, y1) < 1e-13 and rel(rhs4, rhs1) < 1e-13
+    nu = 3 * 9 * 9 * 25
+    assert rel(sol4[:nu], sol1[:nu]) < 1e-6

@@ -42,3 +42,19 @@ def test_fluid_pressure_driven_golden(golden_dir):
     s = _run(golden_dir, "ins_pressure_driven_2d.prm", (100, 10), (0, 0), (2.0, 0.2), "serial")
     vmax = s.velocity().max()
     assert abs(vmax - 2.5e-2) / 2.5e-2 < 1e-3
+
+
+# ---- Solid::MPI::HyperElasticity + NeoHookean (oracle/solid.py) ------------------------------------
+# reference tests/solid_beam_bending_mpi_NeoHookean/solid_beam_bending_mpi_NeoHookean.cpp:59-68:
+#   2-D (40 x 4):     u_min = -0.0616287, u_max = 0.00867069, rel 1e-3
+#   3-D (40 x 4 x 4): u_min = -0.0617214, u_max = 0.00867507, rel 1e-3
+@pytest.mark.parametrize("dim,reps,hi,umin,umax", [(2, (40, 4), (10.0, 1.0), -0.0616287, 0.00867069),
+                                                   (3, (40, 4, 4), (10.0, 1.0, 1.0), -0.0617214, 0.00867507)])
+def test_solid_beam_bending_neohookean_golden(golden_dir, dim, reps, hi, umin, umax):
+    from oracle import solid
+
+    p = prm.Params(os.path.join(golden_dir, f"solid_beam_neohookean_{dim}d.prm"))
+    s = solid.HyperElasticity(fem.BoxMesh(reps, (0,) * dim, hi), p)
+    s.run()
+    assert abs((s.cur_u.min() - umin) / umin) < 1e-3
+    assert abs((s.cur_u.max() - umax) / umax) < 1e-3

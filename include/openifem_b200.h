@@ -128,12 +128,49 @@ int ifem_insim_time(const ifem_insim *s, unsigned int *timestep, double *current
 int ifem_insim_partition(const ifem_insim *s, int which, int *n_owned_nodes, int *n_local_nodes);
 int ifem_insim_local_to_global(const ifem_insim *s, int which, int *global_node_ids);
 
+/* ---- Solid::MPI::HyperElasticity<dim> (include/mpi_hyper_elasticity.h:96-176, source/mpi_hyper_elasticity.cpp;
+ *      base class include/mpi_solid_solver.h:75-79, source/mpi_solid_solver.cpp) ---- */
+typedef struct ifem_hyper ifem_hyper;
+typedef struct
+{
+  unsigned int timestep, iteration;
+  double res_F, res_U; /* the "res_F = / res_U =" line, mpi_hyper_elasticity.cpp:174-179 */
+  int cg_its;
+} ifem_solid_record;
+int ifem_hyper_create(ifem_tria *tria, const ifem_params *params, ifem_hyper **out);
+int ifem_hyper_destroy(ifem_hyper *s);
+int ifem_hyper_set_verbose(ifem_hyper *s, int verbose);
+/* setup_dofs(); initialize_system() (incl. setup_qph) - no refinement */
+int ifem_hyper_setup(ifem_hyper *s);
+/* run(): refine_global(Global refinements[1]) + setup + time loop (mpi_solid_solver.cpp:316-328) */
+int ifem_hyper_run(ifem_hyper *s);
+/* run_one_step(first_step) (mpi_hyper_elasticity.cpp:83-207) */
+int ifem_hyper_run_one_step(ifem_hyper *s, int first_step);
+/* update_qph(current_displacement) (:241-275) */
+int ifem_hyper_update_qph(ifem_hyper *s);
+/* assemble_system(initial_step) (:317-535): initial -> mass_matrix, else system_matrix; system_rhs in both */
+int ifem_hyper_assemble_system(ifem_hyper *s, int initial_step);
+int ifem_hyper_sizes(const ifem_hyper *s, int64_t *n_dofs, int64_t *nnz, int64_t *n_quadrature_points, int *nsym);
+/* get_current_solution(): current_displacement (mpi_solid_solver.cpp:331-334) */
+int ifem_hyper_get_current_solution(ifem_hyper *s, double *host);
+/* which: 0 current_displacement 1 current_velocity 2 current_acceleration 3 previous_displacement
+ *        4 previous_velocity 5 previous_acceleration 6 system_rhs */
+int ifem_hyper_set_vector(ifem_hyper *s, int which, const double *host);
+int ifem_hyper_get_vector(ifem_hyper *s, int which, double *host);
+/* which: 0 system_matrix, 1 mass_matrix; scalar CSR on the host */
+int ifem_hyper_get_matrix(ifem_hyper *s, int which, int64_t *rowptr, int *col, double *val);
+/* PointHistory arrays [cell][q]: F_inv [dim*dim], tau [dim*dim], Jc [nsym*nsym] (Voigt pairs (0,0),(1,1)[,(2,2)],(0,1)[,(0,2),(1,2)]), det F */
+int ifem_hyper_get_qph(ifem_hyper *s, double *F_inv, double *tau, double *Jc, double *det_F);
+int ifem_hyper_history(const ifem_hyper *s, int max_records, ifem_solid_record *out, int *n_records);
+
 /* ---- measurement hooks (bench.py): device-resident, CUDA-event timed on the library's stream ---- */
 /* reps applications of the block SpMV on resident vectors; returns mean ms per application and the
  * algorithmic bytes of one application */
 int ifem_insim_bench_vmult(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
 /* same for the velocity-velocity block alone (the dominant kernel) */
 int ifem_insim_bench_spmv_uu(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
+/* fp32-streamed copy of A_uu (inner solve only) */
+int ifem_insim_bench_spmv_uu_fp32(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
 int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms_per_assembly);
 /* n_steps calls of run_one_step bracketed by CUDA events on the library's stream; total device ms */
 int ifem_insim_bench_steps(ifem_insim *s, int n_steps, int first_applies_nonzero_constraints, double *ms_total);

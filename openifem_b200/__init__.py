@@ -13,9 +13,9 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import IfemError, InsControl, NewtonRecord, check, dptr, iptr, lptr, lib
+from ._lib import IfemError, InsControl, NewtonRecord, SolidRecord, check, dptr, iptr, lptr, lib
 
-__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Partition", "IfemError", "init", "init_distributed",
+__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Solid", "Partition", "IfemError", "init", "init_distributed",
            "comm_unique_id", "comm_init", "comm_finalize", "kernel_launches"]
 
 
@@ -311,6 +311,11 @@ class _InsIM:
         check(lib().ifem_insim_bench_spmv_uu(self._h, C.c_int(reps), C.byref(ms), C.byref(b)))
         return ms.value, b.value
 
+    def bench_spmv_uu_fp32(self, reps):
+        ms, b = C.c_double(), C.c_double()
+        check(lib().ifem_insim_bench_spmv_uu_fp32(self._h, C.c_int(reps), C.byref(ms), C.byref(b)))
+        return ms.value, b.value
+
     def bench_steps(self, n_steps, first_applies_nonzero_constraints=False):
         ms = C.c_double()
         check(lib().ifem_insim_bench_steps(self._h, C.c_int(n_steps), C.c_int(1 if first_applies_nonzero_constraints else 0), C.byref(ms)))
@@ -322,6 +327,90 @@ class _InsIM:
         return ms.value
 
 
+class _HyperElasticity:
+    """Solid::MPI::HyperElasticity<dim>(triangulation, parameters) - NeoHookean, Newmark-beta."""
+
+    CUR_U, CUR_V, CUR_A, PREV_U, PREV_V, PREV_A, SYSTEM_RHS = range(7)
+
+    def __init__(self, tria: Triangulation, params: "Parameters.AllParameters"):
+        self.tria, self.params = tria, params
+        self._h = C.c_void_p()
+        check(lib().ifem_hyper_create(tria._h, params._h, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib._lib is not None:
+            _lib._lib.ifem_hyper_destroy(self._h)
+            self._h = None
+
+    def run(self):
+        check(lib().ifem_hyper_run(self._h))
+
+    def run_one_step(self, first_step: bool):
+        check(lib().ifem_hyper_run_one_step(self._h, C.c_int(1 if first_step else 0)))
+
+    def setup(self):
+        check(lib().ifem_hyper_setup(self._h))
+
+    def set_verbose(self, v=True):
+        check(lib().ifem_hyper_set_verbose(self._h, C.c_int(1 if v else 0)))
+
+    def sizes(self):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        check(lib().ifem_hyper_sizes(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    @property
+    def n_dofs(self):
+        return self.sizes()[0]
+
+    def get_current_solution(self):
+        out = np.empty(self.n_dofs)
+        check(lib().ifem_hyper_get_current_solution(self._h, dptr(out)))
+        return out
+
+    def set_vector(self, which, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        check(lib().ifem_hyper_set_vector(self._h, C.c_int(which), dptr(host)))
+
+    def get_vector(self, which):
+        out = np.empty(self.n_dofs)
+        check(lib().ifem_hyper_get_vector(self._h, C.c_int(which), dptr(out)))
+        return out
+
+    def update_qph(self):
+        check(lib().ifem_hyper_update_qph(self._h))
+
+    def assemble_system(self, initial_step: bool):
+        check(lib().ifem_hyper_assemble_system(self._h, C.c_int(1 if initial_step else 0)))
+
+    def get_matrix(self, which=0):
+        import scipy.sparse as sp
+
+        n, nnz, _, _ = self.sizes()
+        rp, ci, v = np.empty(n + 1, dtype=np.int64), np.empty(nnz, dtype=np.int32), np.empty(nnz)
+        check(lib().ifem_hyper_get_matrix(self._h, C.c_int(which), lptr(rp), iptr(ci), dptr(v)))
+        return sp.csr_matrix((v, ci, rp), shape=(n, n))
+
+    def get_qph(self):
+        _, _, nqp, nsym = self.sizes()
+        dim = self.tria.dim
+        Finv, tau = np.empty((nqp, dim, dim)), np.empty((nqp, dim, dim))
+        Jc, det = np.empty((nqp, nsym, nsym)), np.empty(nqp)
+        check(lib().ifem_hyper_get_qph(self._h, dptr(Finv), dptr(tau), dptr(Jc), dptr(det)))
+        return Finv, tau, Jc, det
+
+    def history(self, max_records=4096):
+        buf = (SolidRecord * max_records)()
+        n = C.c_int()
+        check(lib().ifem_hyper_history(self._h, C.c_int(max_records), buf, C.byref(n)))
+        return [{f: getattr(buf[i], f) for f, _ in SolidRecord._fields_} for i in range(min(n.value, max_records))]
+
+
 class Fluid:
     class MPI:
         InsIM = _InsIM
+
+
+class Solid:
+    class MPI:
+        HyperElasticity = _HyperElasticity

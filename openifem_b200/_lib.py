@@ -23,6 +23,10 @@ class NewtonRecord(C.Structure):
                 ("a_inv_its", C.c_int), ("precond_applies", C.c_int)]
 
 
+class SolidRecord(C.Structure):
+    _fields_ = [("timestep", C.c_uint), ("iteration", C.c_uint), ("res_F", C.c_double), ("res_U", C.c_double), ("cg_its", C.c_int)]
+
+
 _lib = None
 
 

@@ -8,6 +8,7 @@
 #include "comm.h"
 #include "insim.h"
 #include "partition.h"
+#include "solid.h"
 
 using namespace ifem;
 
@@ -22,6 +23,10 @@ struct ifem_params
 struct ifem_insim
 {
   std::unique_ptr<InsIM> s;
+};
+struct ifem_hyper
+{
+  std::unique_ptr<HyperElasticity> s;
 };
 struct ifem_partition
 {
@@ -102,6 +107,21 @@ static DevBuf<double> *pick_vector(InsIM &m, int which, int64_t &n)
     default: throw std::runtime_error("unknown vector id");
     }
 }
+static DevBuf<double> *pick_solid_vector(HyperElasticity &m, int which)
+{
+  switch (which)
+    {
+    case 0: return &m.current_displacement;
+    case 1: return &m.current_velocity;
+    case 2: return &m.current_acceleration;
+    case 3: return &m.previous_displacement;
+    case 4: return &m.previous_velocity;
+    case 5: return &m.previous_acceleration;
+    case 6: return &m.ss.rhs;
+    default: throw std::runtime_error("unknown vector id");
+    }
+}
+
 static const NodePartition &pick_np(const Partition &p, int which) { return which == 0 ? p.u : p.p; }
 
 extern "C" {
@@ -526,11 +546,131 @@ int ifem_insim_bench_steps(ifem_insim *s, int n_steps, int first_nz, double *ms_
     *ms_total = n_steps * time_reps(m.ctx, n_steps, [&] { m.run_one_step(first_nz != 0 && k++ == 0); });
   });
 }
+int ifem_insim_bench_spmv_uu_fp32(ifem_insim *s, int reps, double *ms, double *bytes)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    DevBuf<double> y(m.fs.n_u);
+    make_fp32_copy(m.ctx, m.fs.A_uu);
+    *ms = time_reps(m.ctx, reps, [&] { spmv_fp32(m.ctx, m.fs.A_uu, m.fs.rhs.p, y.p); });
+    *bytes = m.fs.A_uu.spmv_bytes() - 4.0 * m.fs.A_uu.nnz();
+  });
+}
 int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms)
 {
   return guard([&] {
     InsIM &m = *s->s;
     *ms = time_reps(m.ctx, reps, [&] { m.assemble(false); });
+  });
+}
+
+int ifem_hyper_create(ifem_tria *tria, const ifem_params *params, ifem_hyper **out)
+{
+  return guard([&] {
+    require_device();
+    auto *h = new ifem_hyper;
+    h->s.reset(new HyperElasticity(default_context(), tria->t, *params->p));
+    *out = h;
+  });
+}
+int ifem_hyper_destroy(ifem_hyper *s)
+{
+  delete s;
+  return IFEM_OK;
+}
+int ifem_hyper_set_verbose(ifem_hyper *s, int v)
+{
+  s->s->verbose = v != 0;
+  return IFEM_OK;
+}
+int ifem_hyper_setup(ifem_hyper *s)
+{
+  return guard([&] {
+    s->s->setup_dofs();
+    s->s->initialize_system();
+  });
+}
+int ifem_hyper_run(ifem_hyper *s)
+{
+  return guard([&] { s->s->run(); });
+}
+int ifem_hyper_run_one_step(ifem_hyper *s, int first)
+{
+  return guard([&] { s->s->run_one_step(first != 0); });
+}
+int ifem_hyper_update_qph(ifem_hyper *s)
+{
+  return guard([&] {
+    s->s->update_qph(s->s->current_displacement.p);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+int ifem_hyper_assemble_system(ifem_hyper *s, int initial)
+{
+  return guard([&] {
+    s->s->assemble_system(initial != 0);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+int ifem_hyper_sizes(const ifem_hyper *s, int64_t *n_dofs, int64_t *nnz, int64_t *nqp, int *nsym)
+{
+  return guard([&] {
+    const SolidSpace &ss = s->s->ss;
+    if (n_dofs) *n_dofs = ss.n_dofs;
+    if (nnz) *nnz = ss.K.nnz();
+    if (nqp) *nqp = (int64_t)ss.n_cells * ss.nq;
+    if (nsym) *nsym = ss.nsym;
+  });
+}
+int ifem_hyper_get_current_solution(ifem_hyper *s, double *host)
+{
+  return guard([&] { s->s->current_displacement.download(host, s->s->ss.n_dofs, s->s->ctx.stream); });
+}
+int ifem_hyper_set_vector(ifem_hyper *s, int which, const double *host)
+{
+  return guard([&] {
+    pick_solid_vector(*s->s, which)->upload(host, s->s->ss.n_dofs, s->s->ctx.stream);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+int ifem_hyper_get_vector(ifem_hyper *s, int which, double *host)
+{
+  return guard([&] { pick_solid_vector(*s->s, which)->download(host, s->s->ss.n_dofs, s->s->ctx.stream); });
+}
+int ifem_hyper_get_matrix(ifem_hyper *s, int which, int64_t *rowptr, int *col, double *val)
+{
+  return guard([&] {
+    std::vector<int64_t> rp;
+    std::vector<int> ci;
+    std::vector<double> v;
+    (which == 0 ? s->s->ss.K : s->s->ss.M).to_host_csr(s->s->ctx.stream, rp, ci, v);
+    std::copy(rp.begin(), rp.end(), rowptr);
+    std::copy(ci.begin(), ci.end(), col);
+    std::copy(v.begin(), v.end(), val);
+  });
+}
+int ifem_hyper_get_qph(ifem_hyper *s, double *F_inv, double *tau, double *Jc, double *det_F)
+{
+  return guard([&] {
+    const SolidSpace &ss = s->s->ss;
+    cudaStream_t st = s->s->ctx.stream;
+    if (F_inv) ss.d_Finv.download(F_inv, ss.d_Finv.n, st);
+    if (tau) ss.d_tau.download(tau, ss.d_tau.n, st);
+    if (Jc) ss.d_Jc.download(Jc, ss.d_Jc.n, st);
+    if (det_F) ss.d_detF.download(det_F, ss.d_detF.n, st);
+  });
+}
+int ifem_hyper_history(const ifem_hyper *s, int max_records, ifem_solid_record *out, int *n_records)
+{
+  return guard([&] {
+    const auto &h = s->s->history;
+    *n_records = (int)h.size();
+    const int first = std::max(0, (int)h.size() - max_records);
+    for (int i = first; i < (int)h.size(); ++i)
+      {
+        ifem_solid_record &r = out[i - first];
+        r.timestep = h[i].timestep; r.iteration = h[i].iteration; r.res_F = h[i].res_F; r.res_U = h[i].res_U; r.cg_its = h[i].cg_its;
+      }
   });
 }
 } // extern "C"

@@ -98,6 +98,7 @@ namespace ifem
     DevBuf<double> results;  // small device scalars
     double *h_results = nullptr; // pinned
     Comm *comm = nullptr;
+    int spmv_variant = 0; // 0 = default kernel; see linalg.cu
     long long kernel_launches = 0; // counted by every launcher (bench "gpu_launches")
     Context();
     ~Context();

@@ -42,6 +42,43 @@ namespace ifem
     return out;
   }
 
+  SolveResult pcg(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
+                  int max_it, VecPool &pool)
+  {
+    double *r = pool.get(0, n.n_alloc), *p = pool.get(1, n.n_alloc), *Ap = pool.get(2, n.n_alloc), *z = pool.get(3, n.n_alloc);
+    SolveResult out;
+    fill(ctx, n, 0.0, x);
+    copy(ctx, n, b, r);
+    out.residual = nrm2(ctx, n, r);
+    if (out.residual <= tol_abs)
+      {
+        out.converged = true;
+        return out;
+      }
+    prec(r, z);
+    copy(ctx, n, z, p);
+    double rz = dot(ctx, n, r, z);
+    while (out.iterations < max_it)
+      {
+        A(p, Ap);
+        const double alpha = rz / dot(ctx, n, p, Ap);
+        axpy(ctx, n, alpha, p, x);
+        const double rr = add_and_dot(ctx, n, r, -alpha, Ap, r);
+        out.iterations++;
+        out.residual = std::sqrt(rr);
+        if (out.residual <= tol_abs)
+          {
+            out.converged = true;
+            break;
+          }
+        prec(r, z);
+        const double rz_new = dot(ctx, n, r, z);
+        axpby(ctx, n, 1.0, z, rz_new / rz, p);
+        rz = rz_new;
+      }
+    return out;
+  }
+
   SolveResult bicgstab(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
                        int max_it, VecPool &pool)
   {

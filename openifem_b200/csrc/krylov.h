@@ -45,6 +45,10 @@ namespace ifem
   SolveResult cg(Context &ctx, const VecSpace &n, const LinOp &A, const double *b, double *x, bool x_is_zero, double tol_abs, int max_it,
                  VecPool &pool);
 
+  // preconditioned CG, x0 = 0 (PETSc KSPCG + PC; solid solver, mpi_solid_solver.cpp:143-161)
+  SolveResult pcg(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
+                  int max_it, VecPool &pool);
+
   SolveResult bicgstab(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
                        int max_it, VecPool &pool);
 

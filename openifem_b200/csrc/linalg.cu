@@ -1,6 +1,7 @@
 #include "linalg.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "comm.h"
 
@@ -25,6 +26,7 @@ namespace ifem
     partials.alloc(kMaxPartials);
     results.alloc(64);
     IFEM_CUDA(cudaMallocHost(&h_results, 64 * sizeof(double)));
+    if (const char *v = std::getenv("IFEM_SPMV_VARIANT")) spmv_variant = std::atoi(v);
   }
 
   Context::~Context()
@@ -94,8 +96,8 @@ namespace ifem
   // ---------------------------------------------------------------------------
   __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
 
-  template <int R, int C, int TPR, typename VT>
-  __global__ void __launch_bounds__(256)
+  template <int R, int C, int TPR, typename VT, int UNROLL = 2, int MINB = 1>
+  __global__ void __launch_bounds__(256, MINB)
   bcsr_spmv_kernel(int n_brows, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
                    const VT *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, int accumulate)
   {
@@ -111,7 +113,7 @@ namespace ifem
         const int nb = (int)(rowptr[row + 1] - base);
         const VT *v = val + base * (R * C);
         const int *ci = col + base;
-#pragma unroll 2
+#pragma unroll UNROLL
         for (int j = lane; j < nb; j += TPR)
           {
             const int c0 = ld_stream(ci + j);
@@ -148,6 +150,22 @@ namespace ifem
       constexpr int TPR = decltype(tpr_tag)::value;
       const int64_t total = (int64_t)A.n_brows * TPR;
       const int64_t blocks = (total + threads - 1) / threads;
+      if (R == 3 && C == 3 && TPR == 32 && ctx.spmv_variant)
+        {
+          // tuning variants (IFEM_SPMV_VARIANT = 10 * unroll + min blocks per SM), velocity block only
+#define IFEM_SPMV_V(U, M)                                                                                                         \
+  case U * 10 + M:                                                                                                                \
+    bcsr_spmv_kernel<R, C, TPR, VT, U, M><<<(unsigned)blocks, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, val, x, y, \
+                                                                                          accumulate ? 1 : 0);                    \
+    return;
+          switch (ctx.spmv_variant)
+            {
+              IFEM_SPMV_V(1, 4) IFEM_SPMV_V(1, 6) IFEM_SPMV_V(1, 8) IFEM_SPMV_V(2, 2) IFEM_SPMV_V(2, 3) IFEM_SPMV_V(2, 4) IFEM_SPMV_V(2, 6)
+              IFEM_SPMV_V(4, 1) IFEM_SPMV_V(4, 2) IFEM_SPMV_V(4, 3) IFEM_SPMV_V(4, 4)
+            default: break;
+            }
+#undef IFEM_SPMV_V
+        }
       bcsr_spmv_kernel<R, C, TPR, VT><<<(unsigned)blocks, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, val, x, y,
                                                                                 accumulate ? 1 : 0);
     };

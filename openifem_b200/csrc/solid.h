@@ -1,0 +1,86 @@
+// Solid::MPI::HyperElasticity<dim> on the device (reference include/mpi_hyper_elasticity.h,
+// source/mpi_hyper_elasticity.cpp; base class source/mpi_solid_solver.cpp): total-Lagrangian
+// NeoHookean solid, Newmark-beta time integration, Newton iteration, CG linear solves.
+//
+// Per-quadrature-point history (Internal::PointHistory: F_inv, tau, Jc, det F) lives in flat device
+// arrays indexed [cell][q] instead of the reference's shared_ptr<PointHistory> per point
+// (mpi_hyper_elasticity.h:59-66); `update_qph` is one kernel, one thread per quadrature point.
+// The solid mesh is small and (as in MPI::FSI's SharedSolidSolver) replicated on every rank.
+#pragma once
+#include <map>
+
+#include "insim.h" // Time
+#include "krylov.h"
+#include "mesh.h"
+#include "parameters.h"
+
+namespace ifem
+{
+  struct SolidSpace
+  {
+    int dim = 0, degree = 1, npc = 0, nq = 0, nv = 0, nsym = 0;
+    int n_cells = 0;
+    NodeTable nt;
+    int64_t n_dofs = 0;
+    Pattern P;
+    std::vector<int> colour_order, colour_offsets;
+    std::vector<unsigned char> con;
+    DevBuf<int> d_cell_nodes, d_colour_order, d_con_idx;
+    DevBuf<unsigned char> d_slots, d_con;
+    int n_con = 0;
+    DevBuf<double> d_N;    // [nq][npc]
+    DevBuf<double> d_G;    // [n_cells][nq][npc][dim] physical gradients on the reference configuration
+    DevBuf<double> d_JxW;  // [n_cells][nq]
+    DevBuf<double> d_node_x; // [n_nodes][dim]
+    // PointHistory
+    DevBuf<double> d_Finv; // [n_cells][nq][dim*dim]
+    DevBuf<double> d_tau;  // [n_cells][nq][dim*dim]
+    DevBuf<double> d_Jc;   // [n_cells][nq][nsym*nsym]  (Voigt pairs: diagonal first, then (0,1),(0,2),(1,2))
+    DevBuf<double> d_detF; // [n_cells][nq]
+    // Neumann faces
+    DevBuf<int> d_nface;       // (cell, face)
+    DevBuf<double> d_nface_val; // dim values per face (traction) or 1 (pressure)
+    DevBuf<double> d_face_tables;
+    int n_nfaces = 0, nqf = 0, neumann_is_pressure = 0;
+    Bcsr K, M;
+    DevBuf<double> rhs;
+
+    void setup(Context &ctx, const Triangulation &tria, const Parameters::AllParameters &prm);
+  };
+
+  class HyperElasticity
+  {
+  public:
+    HyperElasticity(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params);
+    void run();
+    void run_one_step(bool first_step);
+    std::vector<double> get_current_solution();
+    void setup_dofs();
+    void initialize_system();
+    void update_qph(const double *u_dev);
+    void assemble_system(bool initial_step);
+    std::pair<unsigned int, double> solve(Bcsr &A, double *x, const double *b);
+
+    Context &ctx;
+    Triangulation &triangulation;
+    Parameters::AllParameters parameters;
+    SolidSpace ss;
+    Time time;
+    bool verbose = false, dofs_ready = false;
+    DevBuf<double> current_displacement, current_velocity, current_acceleration, previous_displacement, previous_velocity,
+      previous_acceleration;
+    struct Record
+    {
+      unsigned int timestep, iteration;
+      double res_F, res_U;
+      int cg_its;
+    };
+    std::vector<Record> history;
+    std::map<std::string, double> timer_ms;
+
+  private:
+    double get_error(const double *v);
+    DevBuf<double> d_binv, d_tmp, d_pred, d_update;
+    VecPool pool;
+  };
+} // namespace ifem

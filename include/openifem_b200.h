@@ -163,6 +163,30 @@ int ifem_hyper_get_matrix(ifem_hyper *s, int which, int64_t *rowptr, int *col, d
 int ifem_hyper_get_qph(ifem_hyper *s, double *F_inv, double *tau, double *Jc, double *det_F);
 int ifem_hyper_history(const ifem_hyper *s, int max_records, ifem_solid_record *out, int *n_records);
 
+/* ---- MPI::FSI<dim> immersed coupling kernels (include/mpi_fsi.h:39-47, source/mpi_fsi.cpp:95-119, 143-224,
+ *      292-319, 324-663). The solid is the replicated solver the reference's MPI::FSI takes
+ *      (SharedSolidSolver, mpi_fsi.h:39-40). ---- */
+typedef struct ifem_fsi ifem_fsi;
+/* FSI(fluid, solid, parameters, use_dirichlet_bc): holds references to both solvers (mpi_fsi.h:135-136) */
+int ifem_fsi_create(ifem_insim *fluid, ifem_hyper *solid, const ifem_params *params, int use_dirichlet_bc, ifem_fsi **out);
+int ifem_fsi_destroy(ifem_fsi *f);
+/* update_solid_box(): box[2*dim] = min0, max0, min1, max1, ... of the solid moved by its current displacement */
+int ifem_fsi_update_solid_box(ifem_fsi *f, double *box);
+/* update_indicator(): CellProperty::indicator of every local fluid cell */
+int ifem_fsi_update_indicator(ifem_fsi *f);
+int ifem_fsi_get_indicator(ifem_fsi *f, int *indicator_host);
+/* find_fluid_bc(): fills the fluid's fsi_acceleration (read it with ifem_insim_get_vector(s, 2, ..)); with
+ * use_dirichlet_bc the inner constraints are merged into the fluid's (left object wins) */
+int ifem_fsi_find_fluid_bc(ifem_fsi *f);
+/* inner constraints of the last find_fluid_bc before the merge: flag and inhomogeneity per local fluid dof */
+int ifem_fsi_get_inner_constraints(ifem_fsi *f, unsigned char *flags, double *inhomogeneity);
+/* point_in_solid for a batch of points [n][dim] on the current deformed solid */
+int ifem_fsi_point_in_solid(ifem_fsi *f, int n, const double *points, int *inside);
+/* GridInterpolator::point_value of a solid field (0 velocity, 1 acceleration, 2 displacement): values [n][dim],
+ * found[n] = index of the solid cell used or -1 (value 0, as utilities.cpp:228-233) */
+int ifem_fsi_interpolate(ifem_fsi *f, int which, int n, const double *points, double *values, int *found);
+int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms);
+
 /* ---- measurement hooks (bench.py): device-resident, CUDA-event timed on the library's stream ---- */
 /* reps applications of the block SpMV on resident vectors; returns mean ms per application and the
  * algorithmic bytes of one application */

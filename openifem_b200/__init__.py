@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import IfemError, InsControl, NewtonRecord, SolidRecord, check, dptr, iptr, lptr, lib
 
-__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Solid", "Partition", "IfemError", "init", "init_distributed",
+__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Solid", "MPI", "Partition", "IfemError", "init", "init_distributed",
            "comm_unique_id", "comm_init", "comm_finalize", "kernel_launches"]
 
 
@@ -404,6 +404,66 @@ class _HyperElasticity:
         n = C.c_int()
         check(lib().ifem_hyper_history(self._h, C.c_int(max_records), buf, C.byref(n)))
         return [{f: getattr(buf[i], f) for f, _ in SolidRecord._fields_} for i in range(min(n.value, max_records))]
+
+
+class _FSI:
+    """MPI::FSI<dim>(fluid_solver, solid_solver, parameters, use_dirichlet_bc) - coupling kernels."""
+
+    def __init__(self, fluid, solid, params, use_dirichlet_bc=False):
+        self.fluid, self.solid, self.params = fluid, solid, params
+        self._h = C.c_void_p()
+        check(lib().ifem_fsi_create(fluid._h, solid._h, params._h, C.c_int(1 if use_dirichlet_bc else 0), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib._lib is not None:
+            _lib._lib.ifem_fsi_destroy(self._h)
+            self._h = None
+
+    def update_solid_box(self):
+        box = np.empty(2 * self.fluid.tria.dim)
+        check(lib().ifem_fsi_update_solid_box(self._h, dptr(box)))
+        return box
+
+    def update_indicator(self):
+        check(lib().ifem_fsi_update_indicator(self._h))
+        ind = np.empty(self.fluid.tria.n_active_cells() if self.fluid.partition(0)[0] == self.fluid.partition(0)[1] else self._n_local_cells(), dtype=np.int32)
+        check(lib().ifem_fsi_get_indicator(self._h, iptr(ind)))
+        return ind
+
+    def _n_local_cells(self):
+        raise NotImplementedError("indicator download on multi-rank runs: use the C ABI with the local cell count")
+
+    def find_fluid_bc(self):
+        check(lib().ifem_fsi_find_fluid_bc(self._h))
+        return self.fluid.get_vector(self.fluid.FSI_ACCELERATION)
+
+    def inner_constraints(self):
+        n = self.fluid.n_dofs
+        flags, inhom = np.empty(n, dtype=np.uint8), np.empty(n)
+        check(lib().ifem_fsi_get_inner_constraints(self._h, flags.ctypes.data_as(C.POINTER(C.c_ubyte)), dptr(inhom)))
+        return flags, inhom
+
+    def point_in_solid(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        out = np.empty(pts.shape[0], dtype=np.int32)
+        check(lib().ifem_fsi_point_in_solid(self._h, C.c_int(pts.shape[0]), dptr(pts), iptr(out)))
+        return out.astype(bool)
+
+    def interpolate(self, which, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        vals = np.empty_like(pts)
+        found = np.empty(pts.shape[0], dtype=np.int32)
+        check(lib().ifem_fsi_interpolate(self._h, C.c_int(which), C.c_int(pts.shape[0]), dptr(pts), dptr(vals), iptr(found)))
+        return vals, found
+
+    def timer_ms(self, section):
+        ms = C.c_double()
+        check(lib().ifem_fsi_timer_ms(self._h, section.encode(), C.byref(ms)))
+        return ms.value
+
+
+class MPI:
+    FSI = _FSI
 
 
 class Fluid:

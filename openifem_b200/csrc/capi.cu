@@ -6,6 +6,7 @@
 #include <string>
 
 #include "comm.h"
+#include "fsi.h"
 #include "insim.h"
 #include "partition.h"
 #include "solid.h"
@@ -27,6 +28,10 @@ struct ifem_insim
 struct ifem_hyper
 {
   std::unique_ptr<HyperElasticity> s;
+};
+struct ifem_fsi
+{
+  std::unique_ptr<FsiCoupling> f;
 };
 struct ifem_partition
 {
@@ -671,6 +676,68 @@ int ifem_hyper_history(const ifem_hyper *s, int max_records, ifem_solid_record *
         ifem_solid_record &r = out[i - first];
         r.timestep = h[i].timestep; r.iteration = h[i].iteration; r.res_F = h[i].res_F; r.res_U = h[i].res_U; r.cg_its = h[i].cg_its;
       }
+  });
+}
+
+int ifem_fsi_create(ifem_insim *fluid, ifem_hyper *solid, const ifem_params *params, int use_dirichlet_bc, ifem_fsi **out)
+{
+  return guard([&] {
+    require_device();
+    auto *h = new ifem_fsi;
+    h->f.reset(new FsiCoupling(default_context(), *fluid->s, *solid->s, *params->p, use_dirichlet_bc != 0));
+    *out = h;
+  });
+}
+int ifem_fsi_destroy(ifem_fsi *f)
+{
+  delete f;
+  return IFEM_OK;
+}
+int ifem_fsi_update_solid_box(ifem_fsi *f, double *box)
+{
+  return guard([&] {
+    const std::vector<double> b = f->f->update_solid_box();
+    if (box) std::copy(b.begin(), b.end(), box);
+  });
+}
+int ifem_fsi_update_indicator(ifem_fsi *f)
+{
+  return guard([&] {
+    f->f->update_indicator();
+    IFEM_CUDA(cudaStreamSynchronize(f->f->ctx.stream));
+  });
+}
+int ifem_fsi_get_indicator(ifem_fsi *f, int *host)
+{
+  return guard([&] { f->f->fluid.fs.d_indicator.download(host, f->f->fluid.fs.n_cells, f->f->ctx.stream); });
+}
+int ifem_fsi_find_fluid_bc(ifem_fsi *f)
+{
+  return guard([&] {
+    f->f->find_fluid_bc();
+    IFEM_CUDA(cudaStreamSynchronize(f->f->ctx.stream));
+  });
+}
+int ifem_fsi_get_inner_constraints(ifem_fsi *f, unsigned char *flags, double *inhom)
+{
+  return guard([&] {
+    f->f->d_inner_con.download(flags, f->f->fluid.fs.n_dofs, f->f->ctx.stream);
+    f->f->d_inner_inhom.download(inhom, f->f->fluid.fs.n_dofs, f->f->ctx.stream);
+  });
+}
+int ifem_fsi_point_in_solid(ifem_fsi *f, int n, const double *points, int *inside)
+{
+  return guard([&] { f->f->point_in_solid(n, points, inside); });
+}
+int ifem_fsi_interpolate(ifem_fsi *f, int which, int n, const double *points, double *values, int *found)
+{
+  return guard([&] { f->f->interpolate(which, n, points, values, found); });
+}
+int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms)
+{
+  return guard([&] {
+    auto it = f->f->timer_ms.find(section);
+    *ms = it == f->f->timer_ms.end() ? 0.0 : it->second;
   });
 }
 } // extern "C"

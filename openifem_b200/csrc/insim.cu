@@ -60,6 +60,18 @@ namespace ifem
       };
     fs.make_constraints(ctx, triangulation, parameters.fluid_dirichlet_bcs, hc);
     fs.set_neumann_faces(ctx, triangulation, parameters.fluid_neumann_bcs);
+    upload_constraints();
+  }
+
+  void InsIM::upload_constraints()
+  {
+    std::vector<int> idx;
+    for (int64_t g = 0; g < fs.n_dofs; ++g)
+      if (fs.con[g]) idx.push_back((int)g);
+    fs.n_con = (int)idx.size();
+    fs.d_con.upload(fs.con, ctx.stream);
+    fs.d_nonzero_val.upload(fs.nonzero_val, ctx.stream);
+    if (fs.n_con) fs.d_con_idx.upload(idx, ctx.stream);
     std::vector<double> vals(fs.n_con);
     int k = 0;
     for (int64_t g = 0; g < fs.n_dofs; ++g)

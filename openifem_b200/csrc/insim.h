@@ -90,6 +90,8 @@ namespace ifem
 
     void setup_dofs();
     void make_constraints();
+    // push the host constraint flags / values (fs.con, fs.nonzero_val) to the device after a merge
+    void upload_constraints();
     void initialize_system();
     void assemble(bool use_nonzero_constraints);
     std::pair<unsigned int, double> solve(bool use_nonzero_constraints);

@@ -150,18 +150,25 @@ namespace ifem
       constexpr int TPR = decltype(tpr_tag)::value;
       const int64_t total = (int64_t)A.n_brows * TPR;
       const int64_t blocks = (total + threads - 1) / threads;
-      if (R == 3 && C == 3 && TPR == 32 && ctx.spmv_variant)
+      if (R == 3 && C == 3 && TPR == 32)
         {
-          // tuning variants (IFEM_SPMV_VARIANT = 10 * unroll + min blocks per SM), velocity block only
-#define IFEM_SPMV_V(U, M)                                                                                                         \
-  case U * 10 + M:                                                                                                                \
-    bcsr_spmv_kernel<R, C, TPR, VT, U, M><<<(unsigned)blocks, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, val, x, y, \
-                                                                                          accumulate ? 1 : 0);                    \
-    return;
-          switch (ctx.spmv_variant)
+          // velocity block: tuned variants, key = 100 * lanes per row + 10 * unroll + min CTAs per SM
+          // (IFEM_SPMV_VARIANT overrides; default chosen from the round-1 sweep, profiles/r01_spmv_sweep.txt)
+          const int key = ctx.spmv_variant ? ctx.spmv_variant : (sizeof(VT) == 8 ? 3214 : 1614);
+#define IFEM_SPMV_V(T, U, M)                                                                                                    \
+  case T * 100 + U * 10 + M:                                                                                                    \
+    {                                                                                                                           \
+      const int64_t nblk = ((int64_t)A.n_brows * T + threads - 1) / threads;                                                    \
+      bcsr_spmv_kernel<R, C, T, VT, U, M><<<(unsigned)nblk, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, val, x, y, \
+                                                                                      accumulate ? 1 : 0);                      \
+      return;                                                                                                                   \
+    }
+          switch (key)
             {
-              IFEM_SPMV_V(1, 4) IFEM_SPMV_V(1, 6) IFEM_SPMV_V(1, 8) IFEM_SPMV_V(2, 2) IFEM_SPMV_V(2, 3) IFEM_SPMV_V(2, 4) IFEM_SPMV_V(2, 6)
-              IFEM_SPMV_V(4, 1) IFEM_SPMV_V(4, 2) IFEM_SPMV_V(4, 3) IFEM_SPMV_V(4, 4)
+              IFEM_SPMV_V(32, 1, 4) IFEM_SPMV_V(32, 1, 6) IFEM_SPMV_V(32, 1, 8) IFEM_SPMV_V(32, 2, 4) IFEM_SPMV_V(32, 2, 6)
+              IFEM_SPMV_V(16, 1, 4) IFEM_SPMV_V(16, 1, 6) IFEM_SPMV_V(16, 1, 8) IFEM_SPMV_V(16, 2, 4) IFEM_SPMV_V(16, 2, 6)
+              IFEM_SPMV_V(8, 1, 4) IFEM_SPMV_V(8, 1, 6) IFEM_SPMV_V(8, 1, 8) IFEM_SPMV_V(8, 2, 4) IFEM_SPMV_V(8, 2, 6) IFEM_SPMV_V(8, 4, 4)
+              IFEM_SPMV_V(4, 1, 4) IFEM_SPMV_V(4, 1, 6) IFEM_SPMV_V(4, 2, 4) IFEM_SPMV_V(4, 4, 4)
             default: break;
             }
 #undef IFEM_SPMV_V

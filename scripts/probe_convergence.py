@@ -14,6 +14,7 @@ n = int(sys.argv[1])
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 a_inv_rel = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-3
 fp32 = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+max_it = int(sys.argv[5]) if len(sys.argv) > 5 else 2000
 ifem.init(0)
 t0 = time.time()
 tria = ifem.Triangulation(3)
@@ -22,7 +23,7 @@ params = ifem.Parameters.AllParameters(text=cavity_prm(3))
 s = ifem.Fluid.MPI.InsIM(tria, params)
 s.setup()
 print(f"n={n} setup {time.time()-t0:.1f}s sizes={s.sizes()}", flush=True)
-s.set_control(a_inv_rel=a_inv_rel, a_inv_fp32=fp32)
+s.set_control(a_inv_rel=a_inv_rel, a_inv_fp32=fp32, a_inv_max_it=max_it)
 s.set_verbose(True)
 for k in range(steps):
     t0 = time.time()

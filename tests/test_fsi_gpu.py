@@ -1,0 +1,129 @@
+"""GPU parity of the immersed coupling kernels: update_solid_box, point_in_solid,
+update_indicator, find_fluid_bc and the point location / interpolation underneath, against oracle/fsi.py
+(restating source/mpi_fsi.cpp:95-119, 143-224, 292-319, 324-663 and source/utilities.cpp:193-341).
+
+Bars: indicator field and point_in_solid EXACT; interpolated values and fsi_acceleration 1e-10 relative.
+Fluid lattices use binary-representable coordinates where points are meant to lie exactly on solid faces
+(the reference's box / crossing tests are exact floating-point comparisons)."""
+import os
+
+import numpy as np
+import pytest
+
+from util import cavity_prm
+
+pytestmark = pytest.mark.gpu
+
+
+def _solid_prm(golden_dir, dim):
+    return os.path.join(golden_dir, f"solid_beam_neohookean_{dim}d.prm")
+
+
+def _setup(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, disp_fn, use_dirichlet=False, seed=0):
+    import openifem_b200 as ifem
+    from oracle import fem, fsi, ins, prm
+
+    lo, hi = (0.0,) * dim, (1.0,) * dim
+    ftext = cavity_prm(dim)
+    # oracle side
+    o_fluid = ins.InsIM(fem.BoxMesh(f_reps, lo, hi), prm.Params(ftext, is_text=True))
+    s_mesh = fem.BoxMesh(s_reps, s_lo, s_hi)
+    rng = np.random.default_rng(seed)
+    disp = disp_fn(s_mesh.vertices).ravel()
+    vel = rng.uniform(-1, 1, disp.size)
+    acc = rng.uniform(-1, 1, disp.size)
+    present = rng.uniform(-1, 1, o_fluid.n)
+    o_fluid.present[:] = present
+    geo = fsi.SolidGeometry(s_mesh, disp)
+    # device side
+    ftria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(ftria, f_reps, lo, hi, True)
+    fluid = ifem.Fluid.MPI.InsIM(ftria, ifem.Parameters.AllParameters(text=ftext))
+    fluid.setup()
+    fluid.set_vector(fluid.PRESENT, present)
+    stria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(stria, s_reps, s_lo, s_hi, True)
+    sprm = ifem.Parameters.AllParameters(_solid_prm(golden_dir, dim))
+    solid = ifem.Solid.MPI.HyperElasticity(stria, sprm)
+    solid.setup()
+    solid.set_vector(solid.CUR_U, disp)
+    solid.set_vector(solid.CUR_V, vel)
+    solid.set_vector(solid.CUR_A, acc)
+    coupling = ifem.MPI.FSI(fluid, solid, ifem.Parameters.AllParameters(text=ftext), use_dirichlet)
+    return o_fluid, geo, (disp, vel, acc), fluid, solid, coupling
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
+
+
+SHEAR2 = lambda X: np.stack([0.12 * X[:, 1] ** 2, 0.04 * X[:, 0]], axis=1)
+BEND3 = lambda X: np.stack([0.08 * X[:, 2] ** 2, 0.03 * X[:, 0] * X[:, 2], -0.02 * X[:, 1]], axis=1)
+ZERO = lambda X: np.zeros_like(X)
+
+
+@pytest.mark.parametrize("dim,f_reps,s_reps,s_lo,s_hi,disp", [
+    (2, (16, 16), (5, 7), (0.3, 0.2), (0.6, 0.9), SHEAR2),
+    (2, (16, 16), (4, 4), (0.25, 0.25), (0.75, 0.75), ZERO),      # fluid vertices exactly on the solid boundary
+    (3, (8, 8, 8), (3, 4, 5), (0.2, 0.25, 0.1), (0.7, 0.8, 0.85), BEND3),
+    (3, (8, 8, 8), (2, 2, 3), (0.25, 0.25, 0.25), (0.75, 0.75, 0.625), ZERO),
+])
+def test_box_point_in_solid_indicator(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, disp):
+    from oracle import fsi
+
+    o_fluid, geo, fields, fluid, solid, coupling = _setup(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, disp)
+    box = coupling.update_solid_box()
+    assert np.array_equal(box, geo.box)  # min / max of identical doubles: exact
+    rng = np.random.default_rng(1)
+    pts = np.concatenate([rng.uniform(0, 1, size=(300, dim)), geo.x[::3], o_fluid.mesh.vertices[::5]])
+    inside = coupling.point_in_solid(pts)
+    ref = np.array([geo.point_in_solid(p) for p in pts])
+    assert np.array_equal(inside, ref)
+    ind = coupling.update_indicator()
+    assert np.array_equal(ind, fsi.update_indicator(o_fluid.mesh, geo))
+    assert ind.sum() > 0
+    # interpolation of the solid velocity at points inside (GridInterpolator::point_value)
+    vals, found = coupling.interpolate(0, pts)
+    for p, v, f in zip(pts, vals, found):
+        c, _ = geo.locate(p)
+        assert (c is None) == (f < 0)
+        if c is not None:
+            assert f == c
+            assert np.allclose(v, geo.interpolate(fields[1], p), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("dim,f_reps,s_reps,s_lo,s_hi,disp", [
+    (2, (12, 12), (5, 7), (0.3, 0.2), (0.6, 0.9), SHEAR2),
+    (3, (6, 6, 6), (3, 4, 5), (0.2, 0.25, 0.1), (0.7, 0.8, 0.85), BEND3),
+])
+def test_find_fluid_bc_acceleration(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, disp):
+    from oracle import fsi
+
+    o_fluid, geo, (d, vel, acc), fluid, solid, coupling = _setup(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, disp)
+    coupling.update_solid_box()
+    ind = coupling.update_indicator()
+    ref_acc, _, _ = fsi.find_fluid_bc(o_fluid, geo, ind, vel, acc, o_fluid.dt, use_dirichlet_bc=False)
+    got = coupling.find_fluid_bc()
+    assert np.count_nonzero(ref_acc) > 0
+    assert np.array_equal(got != 0, ref_acc != 0)
+    assert _rel(got, ref_acc) < 1e-10
+
+
+@pytest.mark.parametrize("dim,f_reps,s_reps,s_lo,s_hi,disp", [
+    (2, (12, 12), (5, 7), (0.3, 0.2), (0.6, 0.9), SHEAR2),
+    (3, (6, 6, 6), (3, 4, 5), (0.2, 0.25, 0.1), (0.7, 0.8, 0.85), BEND3),
+])
+def test_find_fluid_bc_dirichlet(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, disp):
+    from oracle import fsi
+
+    o_fluid, geo, (d, vel, acc), fluid, solid, coupling = _setup(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, disp,
+                                                                 use_dirichlet=True)
+    coupling.update_solid_box()
+    ind = coupling.update_indicator()
+    _, ref_con, ref_inhom = fsi.find_fluid_bc(o_fluid, geo, ind, vel, acc, o_fluid.dt, use_dirichlet_bc=True)
+    got_acc = coupling.find_fluid_bc()
+    assert not got_acc.any()  # no fsi_acceleration in the Dirichlet variant (:489)
+    flags, inhom = coupling.inner_constraints()
+    assert ref_con.sum() > 0
+    assert np.array_equal(flags, ref_con)
+    assert _rel(inhom, ref_inhom) < 1e-10

@@ -742,14 +742,13 @@ namespace ifem
     }
 
     // Pressure Neumann faces (:313-341): rhs_i -= phi_i . n  p  JxW_face on unconstrained rows.
-    template <int DIM>
+    template <int DIM, int NU>
     __global__ void ins_neumann_kernel(int n_faces, int nqf, const int *__restrict__ face_cell, const double *__restrict__ face_val,
                                        const double *__restrict__ ftab, const int *__restrict__ cell_un,
                                        const double *__restrict__ cell_x, const unsigned char *__restrict__ con, int n_owned_u,
                                        double *__restrict__ rhs)
     {
-      using T = InsT<DIM>;
-      constexpr int NU = T::NU, NV = T::NV;
+      constexpr int NV = 1 << DIM;
       const int f = blockIdx.x;
       if (f >= n_faces) return;
       const int cell = face_cell[2 * f], face = face_cell[2 * f + 1];
@@ -782,6 +781,26 @@ namespace ifem
         }
     }
   } // namespace
+
+  void neumann_faces(Context &ctx, FluidSpace &fs)
+  {
+    if (!fs.n_nfaces) return;
+    auto go = [&](auto dim_tag, auto nu_tag) {
+      constexpr int DIM = decltype(dim_tag)::value, NU = decltype(nu_tag)::value;
+      ins_neumann_kernel<DIM, NU><<<fs.n_nfaces, 64, 0, ctx.stream>>>(fs.n_nfaces, fs.nqf, fs.d_nface_cell.p, fs.d_nface_val.p,
+                                                                      fs.d_face_tables.p, fs.d_cell_un.p, fs.d_cell_x.p, fs.d_con.p,
+                                                                      fs.n_owned_unodes, fs.rhs.p);
+    };
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    if (fs.dim == 2 && fs.nu == 9) go(I2(), std::integral_constant<int, 9>());
+    else if (fs.dim == 2 && fs.nu == 4) go(I2(), std::integral_constant<int, 4>());
+    else if (fs.dim == 3 && fs.nu == 27) go(I3(), std::integral_constant<int, 27>());
+    else if (fs.dim == 3 && fs.nu == 8) go(I3(), std::integral_constant<int, 8>());
+    else throw std::runtime_error("neumann_faces: unsupported element");
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+  }
 
   template <int DIM>
   static void ins_assemble_dim(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt,
@@ -844,13 +863,7 @@ namespace ifem
         IFEM_KERNEL_CHECK();
         ctx.kernel_launches++;
       }
-    if (fs.n_nfaces)
-      {
-        ins_neumann_kernel<DIM><<<fs.n_nfaces, 64, 0, s>>>(fs.n_nfaces, fs.nqf, fs.d_nface_cell.p, fs.d_nface_val.p,
-                                                           fs.d_face_tables.p, fs.d_cell_un.p, fs.d_cell_x.p, fs.d_con.p, fs.n_owned_unodes, fs.rhs.p);
-        IFEM_KERNEL_CHECK();
-        ctx.kernel_launches++;
-      }
+    neumann_faces(ctx, fs);
   }
 
   void ins_assemble(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt, const double *present,

@@ -96,6 +96,10 @@ namespace ifem
   void ins_assemble(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt, const double *present,
                     const double *fsi_acc, bool use_nonzero_constraints, bool assemble_mass);
 
+  // pressure Neumann faces: rhs_i -= phi_i . n  p  JxW_face on unconstrained owned rows (mpi_insim.cpp:313-341,
+  // mpi_scnsim.cpp:516-546)
+  void neumann_faces(Context &ctx, FluidSpace &fs);
+
   // y = A x on the 2x2 block system (BlockSparseMatrix::vmult)
   void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y);
 

@@ -27,10 +27,11 @@ namespace ifem
     };
   } // namespace
 
-  InsIM::InsIM(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params)
+  InsIM::InsIM(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params, bool taylor_hood_only)
     : ctx(ctx_), triangulation(tria), parameters(params),
       time(params.end_time, params.time_step, params.output_interval, params.refinement_interval, params.save_interval)
   {
+    if (!taylor_hood_only) return;
     // mpi_insim.cpp:135-139
     if (parameters.fluid_velocity_degree - parameters.fluid_pressure_degree != 1)
       throw std::runtime_error("Velocity finite element should be one order higher than pressure!");

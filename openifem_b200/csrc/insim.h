@@ -80,21 +80,22 @@ namespace ifem
   class InsIM
   {
   public:
-    InsIM(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params);
+    InsIM(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params, bool taylor_hood_only = true);
+    virtual ~InsIM() = default;
 
     void run();
-    void run_one_step(bool apply_nonzero_constraints, bool assemble_system = true);
+    virtual void run_one_step(bool apply_nonzero_constraints, bool assemble_system = true);
     // BlockVector of n_u + n_p doubles, copied to the host
     std::vector<double> get_current_solution();
     void add_hard_coded_boundary_condition(int id, std::function<double(const double *, unsigned int, double)> f);
 
-    void setup_dofs();
+    virtual void setup_dofs();
     void make_constraints();
     // push the host constraint flags / values (fs.con, fs.nonzero_val) to the device after a merge
     void upload_constraints();
-    void initialize_system();
-    void assemble(bool use_nonzero_constraints);
-    std::pair<unsigned int, double> solve(bool use_nonzero_constraints);
+    virtual void initialize_system();
+    virtual void assemble(bool use_nonzero_constraints);
+    virtual std::pair<unsigned int, double> solve(bool use_nonzero_constraints);
 
     Context &ctx;
     Triangulation &triangulation;
@@ -110,7 +111,7 @@ namespace ifem
     std::map<std::string, double> timer_ms;
     bool dofs_ready = false;
 
-  private:
+  protected:
     void precondition(const double *src, double *dst);
     DevBuf<double> d_binv, d_con_vals, d_tmp_p, d_utmp, d_utmp2;
     int64_t n_dofs_global = 0, n_p_global = 0;

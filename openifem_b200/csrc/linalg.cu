@@ -398,6 +398,10 @@ namespace ifem
   {
     map(ctx, n_idx, [=] __device__(int64_t k) { x[idx[k]] = vals ? vals[k] : 0.0; });
   }
+  void hadamard(Context &ctx, const VecSpace &n, const double *d, const double *x, double *y)
+  {
+    map(ctx, n, [=] __device__(int64_t i) { y[i] = d[i] * x[i]; });
+  }
   void divide(Context &ctx, const VecSpace &n, const double *d, double *y)
   {
     map(ctx, n, [=] __device__(int64_t i) { y[i] /= d[i]; });

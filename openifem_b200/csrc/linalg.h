@@ -77,6 +77,8 @@ namespace ifem
   void lin3(Context &ctx, const VecSpace &n, double *z, const double *x, double a, const double *y, double b, const double *w);
   // x[idx[k]] = vals ? vals[k] : 0   (AffineConstraints::distribute for Dirichlet lines)
   void set_indexed(Context &ctx, int n_idx, const int *idx, const double *vals, double *x);
+  // y[i] = d[i] * x[i]
+  void hadamard(Context &ctx, const VecSpace &n, const double *d, const double *x, double *y);
   // y[i] /= d[i]
   void divide(Context &ctx, const VecSpace &n, const double *d, double *y);
   // y[i] = 1 / x[i]

@@ -1,0 +1,42 @@
+// Fluid::MPI::SCnsIM<dim> on the device (reference include/mpi_scnsim.h, source/mpi_scnsim.cpp:15-568) on top
+// of Fluid::MPI::SUPGFluidSolver (include/mpi_supg_solver.h, source/mpi_supg_solver.cpp): slightly
+// compressible Navier-Stokes, SUPG / PSPG / LSIC stabilisation, PML attenuation, artificial-fluid terms for
+// the immersed solid. Equal-order Q1/Q1 elements (what every reference SCnsIM test and BASELINE configs 4, 5
+// use). Shares the FluidSpace / Newton / FGMRES machinery of InsIM; differs in the cell integrand, in
+// update_stress() after every step and in the block preconditioner (BlockIncompSchurPreconditioner).
+#pragma once
+#include "insim.h"
+
+namespace ifem
+{
+  class SCnsIM : public InsIM
+  {
+  public:
+    SCnsIM(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params);
+
+    // set_body_force / set_sigma_pml_field / set_initial_condition (include/mpi_fluid_solver.h:120-143):
+    // f(point, component) evaluated on the host at setup, stored per quadrature point / per dof
+    void set_body_force(std::function<double(const double *, unsigned int)> f) { body_force = std::move(f); }
+    void set_sigma_pml_field(std::function<double(const double *, unsigned int)> f) { sigma_pml_field = std::move(f); }
+    void set_initial_condition(std::function<double(const double *, unsigned int)> f) { initial_condition = std::move(f); }
+
+    void setup_dofs() override;
+    void initialize_system() override;
+    void assemble(bool use_nonzero_constraints) override;
+    std::pair<unsigned int, double> solve(bool use_nonzero_constraints) override;
+    void run_one_step(bool apply_nonzero_constraints, bool assemble_system = true) override;
+    // FluidSolver::update_stress (source/mpi_fluid_solver.cpp:716-811)
+    void update_stress();
+
+    DevBuf<double> stress;     // [dim*dim][n_unodes] nodal viscous stress
+    DevBuf<double> fsi_stress; // [dim(dim+1)/2][n_unodes]
+    int tpp_its = 0;
+
+  private:
+    void precondition_supg(const double *src, double *dst);
+    std::function<double(const double *, unsigned int)> body_force, sigma_pml_field, initial_condition;
+    DevBuf<double> d_sigma_pml, d_body_force; // [n_cells][nq], [n_cells][nq][dim] (empty when unset)
+    DevBuf<double> d_qpt_to_dof, d_count, d_rowsum_inv, d_b2pp_diag_inv, d_pt1, d_pt2, d_ut1, d_ut2;
+    VecPool pool_tpp;
+  };
+} // namespace ifem

@@ -48,7 +48,8 @@ typedef struct ifem_partition ifem_partition;
 int ifem_partition_create(const ifem_tria *t, int velocity_degree, int pressure_degree, int rank, int size, ifem_partition **out);
 int ifem_partition_destroy(ifem_partition *p);
 /* which: 0 velocity nodes, 1 pressure nodes */
-int ifem_partition_counts(const ifem_partition *p, int which, int *n_owned, int *n_local, int *n_neighbours, int *n_local_cells);
+/* n_layer1 = owned + layer-1 ghosts; n_messages = halo messages (one per ghost layer and neighbour) */
+int ifem_partition_counts(const ifem_partition *p, int which, int *n_owned, int *n_layer1, int *n_local, int *n_messages, int *n_local_cells);
 int ifem_partition_local_to_global(const ifem_partition *p, int which, int *global_ids);
 int ifem_partition_neighbour(const ifem_partition *p, int which, int k, int *rank, int *n_send, int *recv_offset, int *recv_count);
 int ifem_partition_send_list(const ifem_partition *p, int which, int k, int *local_ids);
@@ -127,6 +128,21 @@ int ifem_insim_time(const ifem_insim *s, unsigned int *timestep, double *current
  * [u of local nodes (owned first, then ghosts) | p of local nodes]; which: 0 velocity nodes, 1 pressure nodes */
 int ifem_insim_partition(const ifem_insim *s, int which, int *n_owned_nodes, int *n_local_nodes);
 int ifem_insim_local_to_global(const ifem_insim *s, int which, int *global_node_ids);
+
+/* ---- Fluid::MPI::SCnsIM<dim> (include/mpi_scnsim.h, source/mpi_scnsim.cpp:15-568) on SUPGFluidSolver
+ *      (source/mpi_supg_solver.cpp). The handle is an ifem_insim: every ifem_insim_* entry point (setup, run,
+ *      run_one_step, assemble, solve, vectors, matrices, history) applies. Q1/Q1 elements. ---- */
+typedef double (*ifem_field_fn)(const double *point, unsigned int component, void *user);
+int ifem_scnsim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out);
+/* set_body_force / set_sigma_pml_field / set_initial_condition (include/mpi_fluid_solver.h:120-143); call before setup */
+int ifem_scnsim_set_body_force(ifem_insim *s, ifem_field_fn f, void *user);
+int ifem_scnsim_set_sigma_pml_field(ifem_insim *s, ifem_field_fn f, void *user);
+int ifem_scnsim_set_initial_condition(ifem_insim *s, ifem_field_fn f, void *user);
+/* update_stress() (source/mpi_fluid_solver.cpp:716-811): nodal viscous stress from present_solution */
+int ifem_scnsim_update_stress(ifem_insim *s);
+/* which: 0 stress [dim*dim][n_velocity_nodes], 1 fsi_stress [dim(dim+1)/2][n_velocity_nodes] */
+int ifem_scnsim_get_field(ifem_insim *s, int which, double *host);
+int ifem_scnsim_set_field(ifem_insim *s, int which, const double *host);
 
 /* ---- Solid::MPI::HyperElasticity<dim> (include/mpi_hyper_elasticity.h:96-176, source/mpi_hyper_elasticity.cpp;
  *      base class include/mpi_solid_solver.h:75-79, source/mpi_solid_solver.cpp) ---- */

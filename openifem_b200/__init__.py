@@ -75,9 +75,9 @@ class Partition:
             self._h = None
 
     def counts(self, which):
-        v = [C.c_int() for _ in range(4)]
+        v = [C.c_int() for _ in range(5)]
         check(lib().ifem_partition_counts(self._h, C.c_int(which), *[C.byref(x) for x in v]))
-        return dict(n_owned=v[0].value, n_local=v[1].value, n_neighbours=v[2].value, n_local_cells=v[3].value)
+        return dict(n_owned=v[0].value, n_layer1=v[1].value, n_local=v[2].value, n_neighbours=v[3].value, n_local_cells=v[4].value)
 
     def local_to_global(self, which):
         out = np.empty(self.counts(which)["n_local"], dtype=np.int32)
@@ -327,6 +327,50 @@ class _InsIM:
         return ms.value
 
 
+FIELD_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_uint, C.c_void_p)
+
+
+class _SCnsIM(_InsIM):
+    """Fluid::MPI::SCnsIM<dim>(triangulation, parameters); shares the InsIM handle API."""
+
+    def __init__(self, tria, params):
+        self.tria, self.params = tria, params
+        self._h = C.c_void_p()
+        self._keep = []
+        check(lib().ifem_scnsim_create(tria._h, params._h, C.byref(self._h)))
+
+    def _wrap(self, f):
+        dim = self.tria.dim
+        cb = FIELD_FN(lambda p, c, _u: float(f([p[i] for i in range(dim)], int(c))))
+        self._keep.append(cb)
+        return cb
+
+    def set_body_force(self, f):
+        check(lib().ifem_scnsim_set_body_force(self._h, self._wrap(f), None))
+
+    def set_sigma_pml_field(self, f):
+        check(lib().ifem_scnsim_set_sigma_pml_field(self._h, self._wrap(f), None))
+
+    def set_initial_condition(self, f):
+        check(lib().ifem_scnsim_set_initial_condition(self._h, self._wrap(f), None))
+
+    def update_stress(self):
+        check(lib().ifem_scnsim_update_stress(self._h))
+
+    def _field_shape(self, which):
+        dim = self.tria.dim
+        return (dim * dim if which == 0 else dim * (dim + 1) // 2, self.partition(0)[1])
+
+    def get_field(self, which):
+        out = np.empty(self._field_shape(which))
+        check(lib().ifem_scnsim_get_field(self._h, C.c_int(which), dptr(out)))
+        return out
+
+    def set_field(self, which, host):
+        host = np.ascontiguousarray(host, dtype=np.float64).reshape(self._field_shape(which))
+        check(lib().ifem_scnsim_set_field(self._h, C.c_int(which), dptr(host)))
+
+
 class _HyperElasticity:
     """Solid::MPI::HyperElasticity<dim>(triangulation, parameters) - NeoHookean, Newmark-beta."""
 
@@ -469,6 +513,7 @@ class MPI:
 class Fluid:
     class MPI:
         InsIM = _InsIM
+        SCnsIM = _SCnsIM
 
 
 class Solid:

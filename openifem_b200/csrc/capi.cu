@@ -9,6 +9,7 @@
 #include "fsi.h"
 #include "insim.h"
 #include "partition.h"
+#include "scnsim.h"
 #include "solid.h"
 
 using namespace ifem;
@@ -127,6 +128,13 @@ static DevBuf<double> *pick_solid_vector(HyperElasticity &m, int which)
     }
 }
 
+static SCnsIM &as_scns(ifem_insim *s)
+{
+  auto *p = dynamic_cast<SCnsIM *>(s->s.get());
+  if (!p) throw std::runtime_error("handle is not a SCnsIM solver");
+  return *p;
+}
+
 static const NodePartition &pick_np(const Partition &p, int which) { return which == 0 ? p.u : p.p; }
 
 extern "C" {
@@ -191,11 +199,12 @@ int ifem_partition_destroy(ifem_partition *p)
   delete p;
   return IFEM_OK;
 }
-int ifem_partition_counts(const ifem_partition *p, int which, int *n_owned, int *n_local, int *n_nb, int *n_cells)
+int ifem_partition_counts(const ifem_partition *p, int which, int *n_owned, int *n_layer1, int *n_local, int *n_nb, int *n_cells)
 {
   return guard([&] {
     const NodePartition &np = pick_np(p->p, which);
     if (n_owned) *n_owned = np.n_owned;
+    if (n_layer1) *n_layer1 = np.n_layer1;
     if (n_local) *n_local = np.n_local;
     if (n_nb) *n_nb = (int)np.neighbours.size();
     if (n_cells) *n_cells = (int)p->p.local_cells.size();
@@ -738,6 +747,52 @@ int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms)
   return guard([&] {
     auto it = f->f->timer_ms.find(section);
     *ms = it == f->f->timer_ms.end() ? 0.0 : it->second;
+  });
+}
+
+int ifem_scnsim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out)
+{
+  return guard([&] {
+    require_device();
+    auto *h = new ifem_insim;
+    h->s.reset(new SCnsIM(default_context(), tria->t, *params->p));
+    *out = h;
+  });
+}
+int ifem_scnsim_set_body_force(ifem_insim *s, ifem_field_fn f, void *user)
+{
+  return guard([&] { as_scns(s).set_body_force([f, user](const double *p, unsigned c) { return f(p, c, user); }); });
+}
+int ifem_scnsim_set_sigma_pml_field(ifem_insim *s, ifem_field_fn f, void *user)
+{
+  return guard([&] { as_scns(s).set_sigma_pml_field([f, user](const double *p, unsigned c) { return f(p, c, user); }); });
+}
+int ifem_scnsim_set_initial_condition(ifem_insim *s, ifem_field_fn f, void *user)
+{
+  return guard([&] { as_scns(s).set_initial_condition([f, user](const double *p, unsigned c) { return f(p, c, user); }); });
+}
+int ifem_scnsim_update_stress(ifem_insim *s)
+{
+  return guard([&] {
+    as_scns(s).update_stress();
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+int ifem_scnsim_get_field(ifem_insim *s, int which, double *host)
+{
+  return guard([&] {
+    SCnsIM &m = as_scns(s);
+    DevBuf<double> &v = which == 0 ? m.stress : m.fsi_stress;
+    v.download(host, v.n, m.ctx.stream);
+  });
+}
+int ifem_scnsim_set_field(ifem_insim *s, int which, const double *host)
+{
+  return guard([&] {
+    SCnsIM &m = as_scns(s);
+    DevBuf<double> &v = which == 0 ? m.stress : m.fsi_stress;
+    v.upload(host, v.n, m.ctx.stream);
+    IFEM_CUDA(cudaStreamSynchronize(m.ctx.stream));
   });
 }
 } // extern "C"

@@ -73,6 +73,8 @@ namespace ifem
         pn = localise(pn_global, local_cells, part.p);
         n_owned_unodes = part.u.n_owned;
         n_owned_pnodes = part.p.n_owned;
+        n_layer1_unodes = part.u.n_layer1;
+        n_layer1_pnodes = part.p.n_layer1;
       }
     else
       {
@@ -82,9 +84,12 @@ namespace ifem
         for (int c = 0; c < n_cells; ++c) local_cells[c] = c;
         n_owned_unodes = un.n_nodes;
         n_owned_pnodes = pn.n_nodes;
+        n_layer1_unodes = un.n_nodes;
+        n_layer1_pnodes = pn.n_nodes;
         part = Partition();
-        part.u.n_owned = part.u.n_local = un.n_nodes;
-        part.p.n_owned = part.p.n_local = pn.n_nodes;
+        part.u.n_owned = part.u.n_layer1 = part.u.n_local = un.n_nodes;
+        part.p.n_owned = part.p.n_layer1 = part.p.n_local = pn.n_nodes;
+        part.cell_layer.assign(n_cells, 1);
       }
     n_cells = (int)local_cells.size();
     n_u = (int64_t)dim * un.n_nodes;
@@ -104,10 +109,20 @@ namespace ifem
       return P;
     };
     P_uu = owned_rows(build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, un.cell_nodes.data(), nu, un.n_nodes), n_owned_unodes);
-    P_up = owned_rows(build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes), n_owned_unodes);
+    // A_up keeps the rows of the layer-1 ghost velocity nodes as well: B^T rows the explicit Schur complement of
+    // the owned pressure rows needs (complete, because every cell around a layer-1 node is local)
+    P_up = owned_rows(build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes), n_layer1_unodes);
     P_pu = owned_rows(build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, un.cell_nodes.data(), nu, un.n_nodes), n_owned_pnodes);
     P_pp = owned_rows(build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes), n_owned_pnodes);
     colour_cells(n_cells, un.cell_nodes.data(), nu, un.n_nodes, colour_order, colour_offsets);
+    // inside every colour: cells that touch an owned node first (the ones every assembly visits)
+    colour_n1.assign(colour_offsets.size() - 1, 0);
+    for (size_t k = 0; k + 1 < colour_offsets.size(); ++k)
+      {
+        auto b = colour_order.begin() + colour_offsets[k], e = colour_order.begin() + colour_offsets[k + 1];
+        auto mid = std::stable_partition(b, e, [&](int c) { return part.cell_layer[c] == 1; });
+        colour_n1[k] = (int)(mid - b);
+      }
 
     cudaStream_t s = ctx.stream;
     d_cell_un.upload(un.cell_nodes, s);
@@ -134,6 +149,7 @@ namespace ifem
     }
     A_uu.init(P_uu, dim, dim, s);
     A_up.init(P_up, dim, 1, s);
+    A_up.n_brows_spmv = n_owned_unodes;
     A_pu.init(P_pu, 1, dim, s);
     if (with_App) A_pp.init(P_pp, 1, 1, s);
     M_p.init(P_pp, 1, 1, s);
@@ -160,11 +176,10 @@ namespace ifem
     launch(np, np, d_cell_pn, d_cell_pn, M_p, nu * nu + 2 * nu * np);
     if (err.to_host(s)[0]) throw std::runtime_error("FluidSpace::setup: a matrix row has more than 256 block columns");
 
-    if (n_ranks == 1)
-      {
-        P_schur = build_schur_pattern(tria, pn);
-        S_m.init(P_schur, 1, 1, s);
-      }
+    // pattern of B B^T on the owned pressure rows (compute_mmult_pattern, mpi_fluid_solver.cpp:326-329)
+    P_schur = product_pattern(P_pu, P_up, pn.n_nodes);
+    S_m.init(P_schur, 1, 1, s);
+    schur_valid = false;
 
     con.assign(n_dofs, 0);
     nonzero_val.assign(n_dofs, 0.0);
@@ -339,6 +354,8 @@ namespace ifem
       const int *indicator;
       int64_t n_u;
       int n_owned_u, n_owned_p; // rows of nodes >= these are ghosts: assembled by their owner
+      int lim_up, lim_diag;      // row limits of A_up / diag(M_u): owned, or owned + layer-1 ghosts in the Schur pass
+      int do_uu, do_rhs;         // Schur pass: only the (solution independent) coupling blocks and diag(M_u)
       double mu, gamma, rho, inv_dt, grav[3];
       const unsigned char *con;
       const double *inhom; // null: homogeneous (zero_constraints)
@@ -533,7 +550,7 @@ namespace ifem
                 }
 #pragma unroll
               for (int c = 0; c < DIM; ++c) S.lrhs[aN * DIM + c] = r[c];
-              if (a.assemble_mass && S.un[aN] < a.n_owned_u)
+              if (a.assemble_mass && S.un[aN] < a.lim_diag)
                 {
 #pragma unroll
                   for (int c = 0; c < DIM; ++c) a.diag_Mu[(int64_t)DIM * S.un[aN] + c] += m;
@@ -548,6 +565,7 @@ namespace ifem
           __syncwarp();
           const unsigned char *slots = a.slots + (int64_t)cell * SPC;
           // ---- phase 5: velocity-velocity blocks (:263-273), lane = column node b, 3 row nodes per pass ----
+          if (a.do_uu)
           {
             const int b = lane < NU ? lane : NU - 1;
             int cb[DIM];
@@ -679,7 +697,7 @@ namespace ifem
                     }
                 }
               const int A = S.un[aN];
-              const bool own_row = A < a.n_owned_u;
+              const bool own_row = A < a.lim_up;
               const int64_t rp = own_row ? a.up.rowptr[A] : 0;
               const int nb = own_row ? (int)(a.up.rowptr[A + 1] - rp) : 0;
               double *base = a.up.val + rp * DIM;
@@ -714,7 +732,7 @@ namespace ifem
             }
           __syncwarp();
           // ---- phase 7: pressure mass matrix (:274-276) ----
-          if (a.assemble_mass)
+          if (a.assemble_mass && a.do_rhs)
             for (int e = lane; e < NP * NP; e += 32)
               {
                 const int i = e / NP, j = e % NP;
@@ -727,6 +745,7 @@ namespace ifem
               }
           __syncwarp();
           // ---- scatter local rhs through the constraints (distribute_local_to_global) ----
+          if (a.do_rhs)
           for (int i = lane; i < T::DPC; i += 32)
             {
               const bool own = i < NU * DIM ? S.un[i / DIM] < a.n_owned_u : S.pn[i - NU * DIM] < a.n_owned_p;
@@ -804,19 +823,30 @@ namespace ifem
 
   template <int DIM>
   static void ins_assemble_dim(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt,
-                               const double *present, const double *fsi_acc, bool use_nonzero, bool assemble_mass)
+                               const double *present, const double *fsi_acc, bool use_nonzero, bool assemble_mass, bool schur_pass)
   {
     using T = InsT<DIM>;
     if (fs.nu != T::NU || fs.np != T::NP) throw std::runtime_error("ins_assemble: only Q2/Q1 elements are supported");
     cudaStream_t s = ctx.stream;
-    fs.A_uu.zero(s);
-    fs.A_up.zero(s);
-    fs.A_pu.zero(s);
-    fs.rhs.zero(s);
-    if (assemble_mass)
+    if (schur_pass)
       {
-        fs.M_p.zero(s);
+        // only the solution-independent coupling blocks and diag(M_u), on the rows of owned + layer-1 nodes
+        fs.A_up.zero(s);
+        fs.A_pu.zero(s);
         fs.diag_Mu.zero(s);
+        assemble_mass = true;
+      }
+    else
+      {
+        fs.A_uu.zero(s);
+        fs.A_up.zero(s);
+        fs.A_pu.zero(s);
+        fs.rhs.zero(s);
+        if (assemble_mass)
+          {
+            fs.M_p.zero(s);
+            fs.diag_Mu.zero(s);
+          }
       }
     InsArgs a;
     a.cell_un = fs.d_cell_un.p;
@@ -831,6 +861,10 @@ namespace ifem
     a.n_u = fs.n_u;
     a.n_owned_u = fs.n_owned_unodes;
     a.n_owned_p = fs.n_owned_pnodes;
+    a.lim_up = schur_pass ? fs.n_layer1_unodes : fs.n_owned_unodes;
+    a.lim_diag = a.lim_up;
+    a.do_uu = schur_pass ? 0 : 1;
+    a.do_rhs = schur_pass ? 0 : 1;
     a.mu = prm.viscosity;
     a.gamma = prm.gamma;
     a.rho = prm.rho;
@@ -855,7 +889,8 @@ namespace ifem
     const int n_colours = (int)fs.colour_offsets.size() - 1;
     for (int k = 0; k < n_colours; ++k)
       {
-        a.n_list = fs.colour_offsets[k + 1] - fs.colour_offsets[k];
+        // layer-1 cells come first inside every colour; the Schur pass also visits the layer-2 cells
+        a.n_list = schur_pass ? fs.colour_offsets[k + 1] - fs.colour_offsets[k] : fs.colour_n1[k];
         a.cell_list = fs.d_colour_order.p + fs.colour_offsets[k];
         if (a.n_list == 0) continue;
         const int blocks = std::min((a.n_list + T::WARPS - 1) / T::WARPS, ctx.sm_count * (DIM == 2 ? 4 : 1));
@@ -863,16 +898,16 @@ namespace ifem
         IFEM_KERNEL_CHECK();
         ctx.kernel_launches++;
       }
-    neumann_faces(ctx, fs);
+    if (!schur_pass) neumann_faces(ctx, fs);
   }
 
   void ins_assemble(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt, const double *present,
-                    const double *fsi_acc, bool use_nonzero_constraints, bool assemble_mass)
+                    const double *fsi_acc, bool use_nonzero_constraints, bool assemble_mass, bool schur_pass)
   {
     if (fs.dim == 2)
-      ins_assemble_dim<2>(ctx, fs, prm, eval_pt, present, fsi_acc, use_nonzero_constraints, assemble_mass);
+      ins_assemble_dim<2>(ctx, fs, prm, eval_pt, present, fsi_acc, use_nonzero_constraints, assemble_mass, schur_pass);
     else
-      ins_assemble_dim<3>(ctx, fs, prm, eval_pt, present, fsi_acc, use_nonzero_constraints, assemble_mass);
+      ins_assemble_dim<3>(ctx, fs, prm, eval_pt, present, fsi_acc, use_nonzero_constraints, assemble_mass, schur_pass);
   }
 
   void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y)
@@ -950,8 +985,7 @@ namespace ifem
 
   void compute_mass_schur(Context &ctx, FluidSpace &fs)
   {
-    if (fs.n_ranks > 1) throw std::runtime_error("compute_mass_schur: explicit S_m is single-rank only");
-    const int n_p = (int)fs.n_p;
+    const int n_p = fs.n_owned_pnodes;
     const int blocks = (n_p + 3) / 4;
     auto go = [&](auto tag) {
       constexpr int DIM = decltype(tag)::value;

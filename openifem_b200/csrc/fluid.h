@@ -35,6 +35,9 @@ namespace ifem
     NodeTable un_global, pn_global;       // kept on multi-rank runs for the global constraint pass
     std::vector<int> local_cells;         // global cell id of each local cell
     int n_owned_unodes = 0, n_owned_pnodes = 0;
+    int n_layer1_unodes = 0, n_layer1_pnodes = 0; // owned + layer-1 ghosts
+    std::vector<int> colour_n1;                   // per colour: number of layer-1 cells (they come first)
+    bool schur_valid = false;                     // S_m matches the current constraints (B and diag(M_u) do not depend on the solution)
     Halo halo_u, halo_p;
     VecSpace vs_all, vs_u, vs_p;          // owned entries of a block / velocity / pressure vector
     // refresh ghost entries of a block vector [u | p]
@@ -93,8 +96,9 @@ namespace ifem
   // Fluid::MPI::InsIM<dim>::assemble (reference source/mpi_insim.cpp:152-362).
   // eval_pt / present / fsi_acc are block vectors of n_dofs doubles on the device;
   // fills A_uu, A_up, A_pu, M_p, diag_Mu, rhs of the space.
+  // schur_pass: recompute only A_up / A_pu / diag(M_u), including the rows of layer-1 ghost velocity nodes
   void ins_assemble(Context &ctx, FluidSpace &fs, const InsAssembleParams &prm, const double *eval_pt, const double *present,
-                    const double *fsi_acc, bool use_nonzero_constraints, bool assemble_mass);
+                    const double *fsi_acc, bool use_nonzero_constraints, bool assemble_mass, bool schur_pass = false);
 
   // pressure Neumann faces: rhs_i -= phi_i . n  p  JxW_face on unconstrained owned rows (mpi_insim.cpp:313-341,
   // mpi_scnsim.cpp:516-546)
@@ -103,7 +107,7 @@ namespace ifem
   // y = A x on the 2x2 block system (BlockSparseMatrix::vmult)
   void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y);
 
-  // S_m = B diag(M_u)^-1 B^T on the fixed Schur pattern (mpi_insim.cpp:44-49); single rank only
+  // S_m = B diag(M_u)^-1 B^T on the fixed Schur pattern (mpi_insim.cpp:44-49), owned pressure rows
   void compute_mass_schur(Context &ctx, FluidSpace &fs);
   // y_p = B diag(M_u)^-1 B^T x_p applied matrix-free (two SpMVs + halos): the multi-rank form of S_m
   void apply_mass_schur_matrix_free(Context &ctx, FluidSpace &fs, const double *x_p, double *y_p, double *tmp_u);

@@ -73,6 +73,7 @@ namespace ifem
     fs.d_con.upload(fs.con, ctx.stream);
     fs.d_nonzero_val.upload(fs.nonzero_val, ctx.stream);
     if (fs.n_con) fs.d_con_idx.upload(idx, ctx.stream);
+    fs.schur_valid = false;
     std::vector<double> vals(fs.n_con);
     int k = 0;
     for (int64_t g = 0; g < fs.n_dofs; ++g)
@@ -153,10 +154,8 @@ namespace ifem
       ScopedTimer t(ctx, timer_ms["CG for Sm"]);
       fill(ctx, vp, 0.0, dst_p);
       LinOp Sm = [&](const double *x, double *y) {
-        if (fs.n_ranks > 1)
-          apply_mass_schur_matrix_free(ctx, fs, x, y, d_utmp2.p);
-        else
-          spmv(ctx, fs.S_m, x, y);
+        fs.halo_p.update(ctx, const_cast<double *>(x)); // both ghost layers: S_m reaches two cells deep
+        spmv(ctx, fs.S_m, x, y);
       };
       const SolveResult r = cg(ctx, vp, Sm, src_p, dst_p, true, std::max(control.cg_floor, control.cg_sm_rel * nrm), max_p_its, pool_cg);
       cur.cg_sm_its += r.iterations;
@@ -185,7 +184,22 @@ namespace ifem
   {
     ScopedTimer t(ctx, timer_ms["Solve linear system"]);
     // BlockSchurPreconditioner ctor (mpi_insim.cpp:13-50)
-    if (fs.n_ranks == 1) compute_mass_schur(ctx, fs);
+    if (!fs.schur_valid)
+      {
+        // B = A_pu, B^T = A_up and diag(M_u) depend on the mesh and on WHICH dofs are constrained only, so the
+        // reference's per-solve mmult (mpi_insim.cpp:48-49) is hoisted: recomputed when the constraints change
+        if (fs.n_ranks > 1)
+          {
+            InsAssembleParams p{};
+            p.viscosity = parameters.viscosity;
+            p.gamma = parameters.grad_div;
+            p.rho = parameters.fluid_rho;
+            p.dt = time.get_delta_t();
+            ins_assemble(ctx, fs, p, evaluation_point.p, present_solution.p, fsi_acceleration.p, use_nonzero_constraints, true, true);
+          }
+        compute_mass_schur(ctx, fs);
+        fs.schur_valid = true;
+      }
     block_diag_inverse(ctx, fs.A_uu, d_binv.p);
     if (control.a_inv_fp32) make_fp32_copy(ctx, fs.A_uu);
     const VecSpace &va = fs.vs_all;

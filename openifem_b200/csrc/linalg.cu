@@ -144,11 +144,12 @@ namespace ifem
   template <int R, int C, typename VT>
   static void spmv_launch(Context &ctx, const Bcsr &A, const VT *val, const double *x, double *y, bool accumulate)
   {
-    if (A.n_brows == 0) return;
+    const int n_rows = A.n_brows_spmv >= 0 ? A.n_brows_spmv : A.n_brows;
+    if (n_rows == 0) return;
     const int threads = 256;
     auto launch = [&](auto tpr_tag) {
       constexpr int TPR = decltype(tpr_tag)::value;
-      const int64_t total = (int64_t)A.n_brows * TPR;
+      const int64_t total = (int64_t)n_rows * TPR;
       const int64_t blocks = (total + threads - 1) / threads;
       if (R == 3 && C == 3 && TPR == 32)
         {
@@ -158,8 +159,8 @@ namespace ifem
 #define IFEM_SPMV_V(T, U, M)                                                                                                    \
   case T * 100 + U * 10 + M:                                                                                                    \
     {                                                                                                                           \
-      const int64_t nblk = ((int64_t)A.n_brows * T + threads - 1) / threads;                                                    \
-      bcsr_spmv_kernel<R, C, T, VT, U, M><<<(unsigned)nblk, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, val, x, y, \
+      const int64_t nblk = ((int64_t)n_rows * T + threads - 1) / threads;                                                    \
+      bcsr_spmv_kernel<R, C, T, VT, U, M><<<(unsigned)nblk, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, y, \
                                                                                       accumulate ? 1 : 0);                      \
       return;                                                                                                                   \
     }
@@ -173,7 +174,7 @@ namespace ifem
             }
 #undef IFEM_SPMV_V
         }
-      bcsr_spmv_kernel<R, C, TPR, VT><<<(unsigned)blocks, threads, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.col.p, val, x, y,
+      bcsr_spmv_kernel<R, C, TPR, VT><<<(unsigned)blocks, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, y,
                                                                                 accumulate ? 1 : 0);
     };
     switch (A.tpr)

@@ -22,6 +22,7 @@ namespace ifem
   {
     int R = 1, C = 1;
     int n_brows = 0, n_bcols = 0;
+    int n_brows_spmv = -1; // rows a mat-vec covers (owned rows); -1: all stored rows
     int64_t n_blocks = 0;
     DevBuf<int64_t> rowptr;
     DevBuf<int> col;

@@ -410,6 +410,44 @@ namespace ifem
     return P;
   }
 
+  Pattern product_pattern(const Pattern &A, const Pattern &B, int n_cols)
+  {
+    Pattern P;
+    P.n_rows = A.n_rows;
+    P.n_cols = n_cols;
+    P.rowptr.assign((size_t)A.n_rows + 1, 0);
+    for (int pass = 0; pass < 2; ++pass)
+      {
+#pragma omp parallel
+        {
+          std::vector<int> buf;
+#pragma omp for schedule(dynamic, 1024)
+          for (int r = 0; r < A.n_rows; ++r)
+            {
+              buf.clear();
+              for (int64_t k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k)
+                {
+                  const int m = A.col[k];
+                  if (m >= B.n_rows) continue;
+                  buf.insert(buf.end(), B.col.begin() + B.rowptr[m], B.col.begin() + B.rowptr[m + 1]);
+                }
+              std::sort(buf.begin(), buf.end());
+              const int cnt = (int)(std::unique(buf.begin(), buf.end()) - buf.begin());
+              if (pass == 0)
+                P.rowptr[r + 1] = cnt;
+              else
+                std::copy(buf.begin(), buf.begin() + cnt, P.col.begin() + P.rowptr[r]);
+            }
+        }
+        if (pass == 0)
+          {
+            for (int r = 0; r < A.n_rows; ++r) P.rowptr[r + 1] += P.rowptr[r];
+            P.col.resize(P.rowptr[A.n_rows]);
+          }
+      }
+    return P;
+  }
+
   void colour_cells(int n_cells, const int *table, int per_cell, int n_nodes, std::vector<int> &order,
                     std::vector<int> &offsets)
   {

@@ -72,6 +72,9 @@ namespace ifem
   // with a cell containing the row node.
   Pattern build_schur_pattern(const Triangulation &tria, const NodeTable &pn);
 
+  // Pattern of A * B for CSR patterns A (rows x mid) and B (mid x cols): union of B's rows over A's columns.
+  Pattern product_pattern(const Pattern &A, const Pattern &B, int n_cols);
+
   // Greedy colouring: cells of one colour share no node of `table`.
   // Returns cell ids grouped by colour and the group offsets.
   void colour_cells(int n_cells, const int *table, int per_cell, int n_nodes, std::vector<int> &order,

@@ -53,57 +53,107 @@ namespace ifem
       return owner;
     }
 
-    NodePartition partition_nodes(const NodeTable &nt, int n_cells, const std::vector<int> &owner,
-                                  const std::vector<char> &cell_local_on_me, const std::vector<std::vector<int>> &cell_ranks_touching,
-                                  int rank, int size)
+    // ghost sets of rank r for one node table: layer-1 and layer-2 ghost nodes, each sorted by (owner, global id)
+    struct GhostSets
     {
-      NodePartition np;
+      std::vector<int> owned, g1, g2;
+    };
+
+    GhostSets ghost_sets(const NodeTable &nt, int n_cells, const std::vector<int> &owner, const std::vector<char> &layer_of_cell, int rank)
+    {
+      GhostSets G;
       const int npc = nt.nodes_per_cell;
-      // local nodes
-      std::vector<char> is_local(nt.n_nodes, 0);
-      for (int c = 0; c < n_cells; ++c)
-        if (cell_local_on_me[c])
-          for (int a = 0; a < npc; ++a) is_local[nt.cell_nodes[(size_t)c * npc + a]] = 1;
-      std::vector<int> owned, ghosts;
-      for (int n = 0; n < nt.n_nodes; ++n)
-        if (is_local[n]) (owner[n] == rank ? owned : ghosts).push_back(n);
-      std::stable_sort(ghosts.begin(), ghosts.end(), [&](int a, int b) { return owner[a] < owner[b]; });
-      np.n_owned = (int)owned.size();
-      np.local_to_global = owned;
-      np.local_to_global.insert(np.local_to_global.end(), ghosts.begin(), ghosts.end());
-      np.n_local = (int)np.local_to_global.size();
-      // receive ranges
-      std::vector<std::vector<int>> recv_from(size), send_to(size);
-      for (size_t k = 0; k < ghosts.size(); ++k) recv_from[owner[ghosts[k]]].push_back(np.n_owned + (int)k);
-      // send lists: my owned nodes inside cells that are local on another rank
-      std::vector<int> g2l(nt.n_nodes, -1);
-      for (int l = 0; l < np.n_local; ++l) g2l[np.local_to_global[l]] = l;
+      std::vector<char> cls(nt.n_nodes, 0); // 1 = in a layer-1 cell, 2 = only in layer-2 cells
       for (int c = 0; c < n_cells; ++c)
         {
-          const auto &rs = cell_ranks_touching[c];
-          if (rs.size() < 2) continue;
-          for (int s : rs)
+          if (!layer_of_cell[c]) continue;
+          for (int a = 0; a < npc; ++a)
             {
-              if (s == rank) continue;
-              for (int a = 0; a < npc; ++a)
-                {
-                  const int n = nt.cell_nodes[(size_t)c * npc + a];
-                  if (owner[n] == rank) send_to[s].push_back(n);
-                }
+              char &k = cls[nt.cell_nodes[(size_t)c * npc + a]];
+              if (k == 0 || layer_of_cell[c] < k) k = layer_of_cell[c];
             }
         }
-      for (int s = 0; s < size; ++s)
+      for (int n = 0; n < nt.n_nodes; ++n)
         {
-          auto &v = send_to[s];
-          std::sort(v.begin(), v.end());
-          v.erase(std::unique(v.begin(), v.end()), v.end());
-          if (v.empty() && recv_from[s].empty()) continue;
-          np.neighbours.push_back(s);
-          std::vector<int> loc(v.size());
-          for (size_t k = 0; k < v.size(); ++k) loc[k] = g2l[v[k]];
-          np.send_local.push_back(loc);
-          np.recv_offset.push_back(recv_from[s].empty() ? np.n_local : recv_from[s].front());
-          np.recv_count.push_back((int)recv_from[s].size());
+          if (!cls[n]) continue;
+          if (owner[n] == rank) G.owned.push_back(n);
+          else (cls[n] == 1 ? G.g1 : G.g2).push_back(n);
+        }
+      auto by_owner = [&](int a, int b) { return owner[a] < owner[b]; };
+      std::stable_sort(G.g1.begin(), G.g1.end(), by_owner);
+      std::stable_sort(G.g2.begin(), G.g2.end(), by_owner);
+      return G;
+    }
+
+    // layer of every cell as seen from rank r: 1 = touches a velocity node owned by r, 2 = touches a node of a
+    // layer-1 cell, 0 = not local
+    std::vector<char> cell_layers(const NodeTable &un, int n_cells, const std::vector<int> &owner_u, int r)
+    {
+      const int npc = un.nodes_per_cell;
+      std::vector<char> layer(n_cells, 0), node1(un.n_nodes, 0);
+      for (int c = 0; c < n_cells; ++c)
+        for (int a = 0; a < npc; ++a)
+          if (owner_u[un.cell_nodes[(size_t)c * npc + a]] == r)
+            {
+              layer[c] = 1;
+              break;
+            }
+      for (int c = 0; c < n_cells; ++c)
+        if (layer[c] == 1)
+          for (int a = 0; a < npc; ++a) node1[un.cell_nodes[(size_t)c * npc + a]] = 1;
+      for (int c = 0; c < n_cells; ++c)
+        if (!layer[c])
+          for (int a = 0; a < npc; ++a)
+            if (node1[un.cell_nodes[(size_t)c * npc + a]])
+              {
+                layer[c] = 2;
+                break;
+              }
+      return layer;
+    }
+
+    NodePartition partition_nodes(const NodeTable &nt, int n_cells, const std::vector<int> &owner,
+                                  const std::vector<std::vector<char>> &layers_of_rank, int rank, int size)
+    {
+      NodePartition np;
+      const GhostSets mine = ghost_sets(nt, n_cells, owner, layers_of_rank[rank], rank);
+      np.n_owned = (int)mine.owned.size();
+      np.n_layer1 = np.n_owned + (int)mine.g1.size();
+      np.local_to_global = mine.owned;
+      np.local_to_global.insert(np.local_to_global.end(), mine.g1.begin(), mine.g1.end());
+      np.local_to_global.insert(np.local_to_global.end(), mine.g2.begin(), mine.g2.end());
+      np.n_local = (int)np.local_to_global.size();
+      std::vector<int> g2l(nt.n_nodes, -1);
+      for (int l = 0; l < np.n_local; ++l) g2l[np.local_to_global[l]] = l;
+      // what every other rank expects from me, per layer (its ghost sets, computed from the same global data)
+      std::vector<GhostSets> theirs(size);
+      for (int s = 0; s < size; ++s)
+        if (s != rank) theirs[s] = ghost_sets(nt, n_cells, owner, layers_of_rank[s], s);
+      for (int layer = 1; layer <= 2; ++layer)
+        {
+          const std::vector<int> &my_ghosts = layer == 1 ? mine.g1 : mine.g2;
+          const int base = layer == 1 ? np.n_owned : np.n_layer1;
+          for (int s = 0; s < size; ++s)
+            {
+              if (s == rank) continue;
+              // receive: my layer-`layer` ghosts owned by s (contiguous, ascending global id)
+              int first = -1, count = 0;
+              for (size_t k = 0; k < my_ghosts.size(); ++k)
+                if (owner[my_ghosts[k]] == s)
+                  {
+                    if (first < 0) first = (int)k;
+                    ++count;
+                  }
+              // send: s's layer-`layer` ghosts owned by me, in s's order
+              std::vector<int> send;
+              for (int n : (layer == 1 ? theirs[s].g1 : theirs[s].g2))
+                if (owner[n] == rank) send.push_back(g2l[n]);
+              if (!count && send.empty()) continue;
+              np.neighbours.push_back(s);
+              np.send_local.push_back(send);
+              np.recv_offset.push_back(count ? base + first : np.n_local);
+              np.recv_count.push_back(count);
+            }
         }
       return np;
     }
@@ -118,30 +168,18 @@ namespace ifem
     const std::vector<int> cell_rank = slab_cell_ranks(tria, size);
     const std::vector<int> owner_u = node_owners(un, nc, cell_rank, size);
     const std::vector<int> owner_p = node_owners(pn, nc, cell_rank, size);
-    // a cell is local on every rank that owns one of its velocity nodes (pressure nodes coincide with
-    // velocity vertex nodes and get the same owner, so this covers the pressure rows as well)
-    std::vector<std::vector<int>> touching(nc);
-    std::vector<char> local_on_me(nc, 0);
+    // pressure nodes coincide with velocity vertex nodes and get the same owner, so the cell layers defined
+    // through the velocity nodes cover the pressure rows as well
+    std::vector<std::vector<char>> layers(size);
+    for (int s = 0; s < size; ++s) layers[s] = cell_layers(un, nc, owner_u, s);
     for (int c = 0; c < nc; ++c)
-      {
-        auto &rs = touching[c];
-        for (int a = 0; a < un.nodes_per_cell; ++a)
-          {
-            const int o = owner_u[un.cell_nodes[(size_t)c * un.nodes_per_cell + a]];
-            if (std::find(rs.begin(), rs.end(), o) == rs.end()) rs.push_back(o);
-          }
-        std::sort(rs.begin(), rs.end());
-        if (std::binary_search(rs.begin(), rs.end(), rank)) local_on_me[c] = 1;
-      }
-    // local cells in slab order
-    {
-      std::vector<int> order(nc);
-      std::iota(order.begin(), order.end(), 0);
-      for (int c : order)
-        if (local_on_me[c]) P.local_cells.push_back(c);
-    }
-    P.u = partition_nodes(un, nc, owner_u, local_on_me, touching, rank, size);
-    P.p = partition_nodes(pn, nc, owner_p, local_on_me, touching, rank, size);
+      if (layers[rank][c])
+        {
+          P.local_cells.push_back(c);
+          P.cell_layer.push_back(layers[rank][c]);
+        }
+    P.u = partition_nodes(un, nc, owner_u, layers, rank, size);
+    P.p = partition_nodes(pn, nc, owner_p, layers, rank, size);
     return P;
   }
 

@@ -20,19 +20,25 @@
 
 namespace ifem
 {
+  // Nodes of a rank come in three classes: owned | ghost layer 1 (nodes of cells that touch an owned node) |
+  // ghost layer 2 (nodes of cells that touch a layer-1 node). Operator rows are owned; layer 1 is what a
+  // mat-vec reads; layer 2 exists so that the rows of B^T for layer-1 velocity nodes - and with them the
+  // explicit Schur complement B diag(M_u)^-1 B^T of the owned pressure rows - can be formed without
+  // communication. Messages: one per (layer, neighbour), in that order on both sides.
   struct NodePartition
   {
-    int n_owned = 0, n_local = 0;
+    int n_owned = 0, n_layer1 = 0, n_local = 0; // n_layer1 = owned + layer-1 ghosts
     std::vector<int> local_to_global;          // [n_local]
-    std::vector<int> neighbours;               // ranks exchanged with (ascending)
-    std::vector<std::vector<int>> send_local;  // per neighbour: owned local ids it holds as ghosts
-    std::vector<int> recv_offset, recv_count;  // per neighbour: ghost range (local id = recv_offset, count)
+    std::vector<int> neighbours;               // rank of every message (a rank appears once per layer)
+    std::vector<std::vector<int>> send_local;  // per message: owned local ids the neighbour holds as ghosts
+    std::vector<int> recv_offset, recv_count;  // per message: ghost range (local id = recv_offset, count)
   };
 
   struct Partition
   {
     int rank = 0, size = 1;
-    std::vector<int> local_cells; // global cell ids (ascending slab order)
+    std::vector<int> local_cells; // global cell ids, ascending: every cell within two layers of the owned nodes
+    std::vector<char> cell_layer; // 1: touches an owned node (assembled every time), 2: only needed for the Schur pass
     NodePartition u, p;
   };
 

@@ -38,19 +38,29 @@ def test_partition_is_a_partition_and_plans_match(dim, reps, size):
             owned.append(o)
         allo = np.concatenate(owned)
         assert len(allo) == n_nodes[which] and len(np.unique(allo)) == n_nodes[which]  # disjoint cover
-        # what r sends to s is exactly what s expects from r, in the same order
+        # the k-th message r sends to s is exactly what s expects as its k-th message from r (one message per
+        # ghost layer), in the same order
         for r, p in enumerate(parts):
             l2g_r = p.local_to_global(which)
-            for nb in p.neighbours(which):
-                s = nb["rank"]
-                q = parts[s]
+            for s, q in enumerate(parts):
+                if s == r:
+                    continue
+                out = [x for x in p.neighbours(which) if x["rank"] == s]
                 back = [x for x in q.neighbours(which) if x["rank"] == r]
-                assert len(back) == 1
+                assert len(out) == len(back) <= 2
                 l2g_s = q.local_to_global(which)
-                sent = l2g_r[nb["send_local"]]
-                expect = l2g_s[back[0]["recv_offset"]: back[0]["recv_offset"] + back[0]["recv_count"]]
-                assert np.array_equal(sent, expect)
-                assert np.all(nb["send_local"] < p.counts(which)["n_owned"])
+                for a, b in zip(out, back):
+                    sent = l2g_r[a["send_local"]]
+                    expect = l2g_s[b["recv_offset"]: b["recv_offset"] + b["recv_count"]]
+                    assert np.array_equal(sent, expect)
+                    assert np.all(a["send_local"] < p.counts(which)["n_owned"])
+            c = p.counts(which)
+            assert c["n_owned"] <= c["n_layer1"] <= c["n_local"]
+            # every ghost is received exactly once
+            got = np.zeros(c["n_local"], dtype=int)
+            for nb in p.neighbours(which):
+                got[nb["recv_offset"]: nb["recv_offset"] + nb["recv_count"]] += 1
+            assert np.all(got[c["n_owned"]:] == 1) and np.all(got[: c["n_owned"]] == 0)
     # every cell is local somewhere; the ghost layer is one cell deep for slabs
     assert sum(p.counts(0)["n_local_cells"] for p in parts) >= int(np.prod(reps))
 

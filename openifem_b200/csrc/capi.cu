@@ -567,6 +567,7 @@ int ifem_insim_bench_spmv_uu_fp32(ifem_insim *s, int reps, double *ms, double *b
     DevBuf<double> y(m.fs.n_u);
     make_fp32_copy(m.ctx, m.fs.A_uu);
     *ms = time_reps(m.ctx, reps, [&] { spmv_fp32(m.ctx, m.fs.A_uu, m.fs.rhs.p, y.p); });
+    // algorithmic bytes of the fp32 stream (unpadded): 4 B per value instead of 8
     *bytes = m.fs.A_uu.spmv_bytes() - 4.0 * m.fs.A_uu.nnz();
   });
 }

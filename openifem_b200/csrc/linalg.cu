@@ -204,33 +204,144 @@ namespace ifem
       }
   }
 
+  // ---------------------------------------------------------------------------
+  // fp32-streamed SpMV (preconditioner-only): TPR lanes per block row, each lane owns 4 consecutive blocks
+  // per step and reads every plane with one LDG.128; x, products and sums stay fp64.
+  // ---------------------------------------------------------------------------
+  template <int R, int C, int TPR, int MINB>
+  __global__ void __launch_bounds__(256, MINB)
+  bcsr_spmv_f32x4_kernel(int n_brows, const int64_t *__restrict__ rowptr32, const int *__restrict__ col32,
+                         const float *__restrict__ val32, const double *__restrict__ x, double *__restrict__ y)
+  {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = gt / TPR;
+    const int lane = (int)(gt % TPR);
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    if (row < n_brows)
+      {
+        const int64_t base = rowptr32[row];
+        const int nbp = (int)(rowptr32[row + 1] - base); // multiple of 4
+        const float *v = val32 + base * (R * C);
+        const int *ci = col32 + base;
+        for (int j = 4 * lane; j < nbp; j += 4 * TPR)
+          {
+            const int4 c4 = __ldcs(reinterpret_cast<const int4 *>(ci + j));
+            const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            double xv[4][C];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int c = 0; c < C; ++c) xv[k][c] = __ldg(x + (int64_t)cc[k] * C + c);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+              for (int c = 0; c < C; ++c)
+                {
+                  const float4 a4 = __ldcs(reinterpret_cast<const float4 *>(v + (int64_t)(r * C + c) * nbp + j));
+                  acc[r] = fma((double)a4.x, xv[0][c], acc[r]);
+                  acc[r] = fma((double)a4.y, xv[1][c], acc[r]);
+                  acc[r] = fma((double)a4.z, xv[2][c], acc[r]);
+                  acc[r] = fma((double)a4.w, xv[3][c], acc[r]);
+                }
+          }
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    if (row < n_brows && lane == 0)
+      {
+#pragma unroll
+        for (int r = 0; r < R; ++r) y[row * R + r] = acc[r];
+      }
+  }
+
   void spmv_fp32(Context &ctx, const Bcsr &A, const double *x, double *y)
   {
     if (!A.val32.p) throw std::runtime_error("spmv_fp32: no fp32 copy (call make_fp32_copy)");
+    const int n_rows = A.n_brows_spmv >= 0 ? A.n_brows_spmv : A.n_brows;
+    if (!n_rows) return;
     const int key = A.R * 10 + A.C;
-    switch (key)
-      {
-      case 11: spmv_launch<1, 1>(ctx, A, A.val32.p, x, y, false); break;
-      case 22: spmv_launch<2, 2>(ctx, A, A.val32.p, x, y, false); break;
-      case 33: spmv_launch<3, 3>(ctx, A, A.val32.p, x, y, false); break;
-      default: throw std::runtime_error("spmv_fp32: unsupported block shape");
-      }
+    // lanes per row / min CTAs per SM: IFEM_SPMV32_VARIANT = 10 * lanes + minb (default 8 lanes, 4 CTAs)
+    static const int variant = [] {
+      const char *v = std::getenv("IFEM_SPMV32_VARIANT");
+      return v ? std::atoi(v) : 84;
+    }();
+    auto launch = [&](auto r_tag, auto tpr_tag, auto m_tag) {
+      constexpr int RR = decltype(r_tag)::value, T = decltype(tpr_tag)::value, M = decltype(m_tag)::value;
+      const int64_t nblk = ((int64_t)n_rows * T + 255) / 256;
+      bcsr_spmv_f32x4_kernel<RR, RR, T, M><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y);
+    };
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    using I4 = std::integral_constant<int, 4>;
+    using I8 = std::integral_constant<int, 8>;
+    using I16 = std::integral_constant<int, 16>;
+    if (key == 33)
+      switch (variant)
+        {
+        case 42: launch(I3(), I4(), I2()); break;
+        case 44: launch(I3(), I4(), I4()); break;
+        case 82: launch(I3(), I8(), I2()); break;
+        case 83: launch(I3(), I8(), I3()); break;
+        case 162: launch(I3(), I16(), I2()); break;
+        case 164: launch(I3(), I16(), I4()); break;
+        default: launch(I3(), I8(), I4()); break;
+        }
+    else if (key == 22)
+      launch(I2(), I8(), I4());
+    else
+      throw std::runtime_error("spmv_fp32: unsupported block shape");
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
   }
 
   namespace
   {
-    __global__ void to_fp32_kernel(int64_t n, const double *__restrict__ a, float *__restrict__ b)
+    // one thread per (block row, plane, padded slot)
+    __global__ void to_fp32_padded_kernel(int n_brows, int rc, const int64_t *__restrict__ rowptr, const int64_t *__restrict__ rowptr32,
+                                          const double *__restrict__ val, float *__restrict__ val32)
     {
-      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        b[i] = (float)a[i];
+      const int row = blockIdx.x;
+      if (row >= n_brows) return;
+      const int64_t b = rowptr[row], b32 = rowptr32[row];
+      const int nb = (int)(rowptr[row + 1] - b), nbp = (int)(rowptr32[row + 1] - b32);
+      for (int t = threadIdx.x; t < rc * nbp; t += blockDim.x)
+        {
+          const int plane = t / nbp, j = t % nbp;
+          val32[b32 * rc + (int64_t)plane * nbp + j] = j < nb ? (float)val[b * rc + (int64_t)plane * nb + j] : 0.0f;
+        }
+    }
+    __global__ void pad_cols_kernel(int n_brows, const int64_t *__restrict__ rowptr, const int64_t *__restrict__ rowptr32,
+                                    const int *__restrict__ col, int *__restrict__ col32)
+    {
+      const int row = blockIdx.x;
+      if (row >= n_brows) return;
+      const int64_t b = rowptr[row], b32 = rowptr32[row];
+      const int nb = (int)(rowptr[row + 1] - b), nbp = (int)(rowptr32[row + 1] - b32);
+      for (int j = threadIdx.x; j < nbp; j += blockDim.x) col32[b32 + j] = j < nb ? col[b + j] : 0;
     }
   } // namespace
 
   void make_fp32_copy(Context &ctx, Bcsr &A)
   {
-    if (A.val32.n != A.val.n) A.val32.alloc(A.val.n);
-    if (!A.val.n) return;
-    to_fp32_kernel<<<ctx.sm_count * 16, 256, 0, ctx.stream>>>((int64_t)A.val.n, A.val.p, A.val32.p);
+    if (!A.n_brows) return;
+    if (!A.rowptr32.p)
+      {
+        // padded pattern, once (the sparsity pattern is fixed)
+        const std::vector<int64_t> rp = A.rowptr.to_host(ctx.stream);
+        std::vector<int64_t> rp32(rp.size(), 0);
+        for (int i = 0; i < A.n_brows; ++i) rp32[i + 1] = rp32[i] + ((rp[i + 1] - rp[i] + 3) / 4) * 4;
+        A.rowptr32.upload(rp32, ctx.stream);
+        A.col32.alloc(rp32[A.n_brows]);
+        A.val32.alloc((size_t)rp32[A.n_brows] * A.R * A.C);
+        pad_cols_kernel<<<A.n_brows, 32, 0, ctx.stream>>>(A.n_brows, A.rowptr.p, A.rowptr32.p, A.col.p, A.col32.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+    to_fp32_padded_kernel<<<A.n_brows, 128, 0, ctx.stream>>>(A.n_brows, A.R * A.C, A.rowptr.p, A.rowptr32.p, A.val.p, A.val32.p);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
   }

@@ -27,7 +27,12 @@ namespace ifem
     DevBuf<int64_t> rowptr;
     DevBuf<int> col;
     DevBuf<double> val;
-    DevBuf<float> val32; // optional fp32 copy of val in the same layout (inexact inner solves only)
+    // optional fp32 copy for inexact inner solves only: same row-plane layout but every block row padded to a
+    // multiple of 4 blocks (rowptr32 / col32), so that a lane streams 4 consecutive blocks of a plane with one
+    // 128-bit load (padding: value 0, column 0)
+    DevBuf<float> val32;
+    DevBuf<int64_t> rowptr32;
+    DevBuf<int> col32;
     int tpr = 32; // threads per block row chosen from the average row length
 
     void init(const Pattern &P, int R_, int C_, cudaStream_t s);

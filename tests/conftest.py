@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: long-running CPU oracle check")
 
 
+def pytest_addoption(parser):
+    parser.addoption("--runslow", action="store_true", default=False, help="also run the multi-minute oracle goldens")
+
+
+def pytest_collection_modifyitems(config, items):
+    # the slow oracle goldens (pressure-driven 80 steps, SCnsIM body force 500 steps) take minutes on CPU; they were
+    # run when the oracle was pinned (results quoted in DESIGN.md) and are opt-in: --runslow or IFEM_RUN_SLOW=1
+    if config.getoption("--runslow") or os.environ.get("IFEM_RUN_SLOW") == "1":
+        return
+    skip = pytest.mark.skip(reason="slow oracle golden: use --runslow")
+    for item in items:
+        if "slow" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

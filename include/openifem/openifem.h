@@ -20,6 +20,8 @@
 
 #include <algorithm>
 #include <array>
+#include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -148,16 +150,13 @@ namespace Fluid
 {
   namespace MPI
   {
+    // common surface of the fluid solvers (include/mpi_fluid_solver.h:99-183)
     template <int dim>
-    class InsIM
+    class FluidSolver
     {
     public:
-      InsIM(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
-      {
-        openifem_detail::check(ifem_insim_create(tria.handle(), params.handle(), &h));
-      }
-      ~InsIM() { ifem_insim_destroy(h); }
-      InsIM(const InsIM &) = delete;
+      virtual ~FluidSolver() { ifem_insim_destroy(h); }
+      FluidSolver(const FluidSolver &) = delete;
       void run() { openifem_detail::check(ifem_insim_run(h)); }
       void run_one_step(bool apply_nonzero_constraints, bool /*assemble_system*/ = true)
       {
@@ -173,8 +172,103 @@ namespace Fluid
       }
       ifem_insim *handle() const { return h; }
 
-    private:
+    protected:
+      FluidSolver() = default;
       ifem_insim *h = nullptr;
+    };
+
+    template <int dim>
+    class InsIM : public FluidSolver<dim>
+    {
+    public:
+      InsIM(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_insim_create(tria.handle(), params.handle(), &this->h));
+      }
+    };
+
+    // include/mpi_scnsim.h + the set_* hooks of include/mpi_fluid_solver.h:120-143
+    template <int dim>
+    class SCnsIM : public FluidSolver<dim>
+    {
+    public:
+      using Field = std::function<double(const dealii::Point<dim> &, const unsigned int)>;
+      SCnsIM(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_scnsim_create(tria.handle(), params.handle(), &this->h));
+      }
+      void set_body_force(const Field &f) { openifem_detail::check(ifem_scnsim_set_body_force(this->h, &thunk, keep(f))); }
+      void set_sigma_pml_field(const Field &f) { openifem_detail::check(ifem_scnsim_set_sigma_pml_field(this->h, &thunk, keep(f))); }
+      void set_initial_condition(const Field &f) { openifem_detail::check(ifem_scnsim_set_initial_condition(this->h, &thunk, keep(f))); }
+
+    private:
+      static double thunk(const double *p, unsigned int c, void *user)
+      {
+        dealii::Point<dim> x;
+        for (int d = 0; d < dim; ++d) x[d] = p[d];
+        return (*static_cast<Field *>(user))(x, c);
+      }
+      void *keep(const Field &f)
+      {
+        fields.emplace_back(new Field(f));
+        return fields.back().get();
+      }
+      std::vector<std::unique_ptr<Field>> fields;
     };
   } // namespace MPI
 } // namespace Fluid
+
+namespace Solid
+{
+  namespace MPI
+  {
+    // include/mpi_hyper_elasticity.h:96-98, include/mpi_solid_solver.h:75-79
+    template <int dim>
+    class HyperElasticity
+    {
+    public:
+      HyperElasticity(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_hyper_create(tria.handle(), params.handle(), &h));
+      }
+      ~HyperElasticity() { ifem_hyper_destroy(h); }
+      HyperElasticity(const HyperElasticity &) = delete;
+      void run() { openifem_detail::check(ifem_hyper_run(h)); }
+      void run_one_step(bool first_step) { openifem_detail::check(ifem_hyper_run_one_step(h, first_step)); }
+      std::vector<double> get_current_solution() const
+      {
+        int64_t n = 0;
+        openifem_detail::check(ifem_hyper_sizes(h, &n, nullptr, nullptr, nullptr));
+        std::vector<double> u((size_t)n);
+        openifem_detail::check(ifem_hyper_get_current_solution(h, u.data()));
+        return u;
+      }
+      ifem_hyper *handle() const { return h; }
+
+    private:
+      ifem_hyper *h = nullptr;
+    };
+  } // namespace MPI
+} // namespace Solid
+
+namespace MPI
+{
+  // include/mpi_fsi.h:39-47 - the coupling kernels of the hot path (the full run() loop is not built yet)
+  template <int dim>
+  class FSI
+  {
+  public:
+    FSI(Fluid::MPI::FluidSolver<dim> &f, Solid::MPI::HyperElasticity<dim> &s, const Parameters::AllParameters &p, bool use_dirichlet_bc = false)
+    {
+      openifem_detail::check(ifem_fsi_create(f.handle(), s.handle(), p.handle(), use_dirichlet_bc, &h));
+    }
+    ~FSI() { ifem_fsi_destroy(h); }
+    FSI(const FSI &) = delete;
+    void update_solid_box() { openifem_detail::check(ifem_fsi_update_solid_box(h, nullptr)); }
+    void update_indicator() { openifem_detail::check(ifem_fsi_update_indicator(h)); }
+    void find_fluid_bc() { openifem_detail::check(ifem_fsi_find_fluid_bc(h)); }
+
+  private:
+    ifem_fsi *h = nullptr;
+  };
+} // namespace MPI

@@ -27,6 +27,7 @@ namespace ifem
     results.alloc(64);
     IFEM_CUDA(cudaMallocHost(&h_results, 64 * sizeof(double)));
     if (const char *v = std::getenv("IFEM_SPMV_VARIANT")) spmv_variant = std::atoi(v);
+    if (const char *v = std::getenv("IFEM_SPMV_RPW")) spmv_rpw = std::atoi(v);
   }
 
   Context::~Context()
@@ -96,47 +97,54 @@ namespace ifem
   // ---------------------------------------------------------------------------
   __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
 
+  // A CTA of 256 threads = G = 256 / TPR lane groups; group g handles rows row0 + k * G + g, k < rpw, of the
+  // CTA's chunk of G * rpw consecutive rows. Consecutive rows share most of their column nodes, so walking a
+  // chunk inside one CTA turns the x gathers of later rows into L1 hits (rpw = 1: one row per group).
   template <int R, int C, int TPR, typename VT, int UNROLL = 2, int MINB = 1>
   __global__ void __launch_bounds__(256, MINB)
   bcsr_spmv_kernel(int n_brows, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
-                   const VT *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, int accumulate)
+                   const VT *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, int accumulate, int rpw)
   {
-    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t row = gt / TPR;
-    const int lane = (int)(gt % TPR);
-    double acc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.0;
-    if (row < n_brows)
+    constexpr int G = 256 / TPR;
+    const int g = threadIdx.x / TPR, lane = threadIdx.x % TPR;
+    const int64_t row0 = (int64_t)blockIdx.x * G * rpw;
+    for (int k = 0; k < rpw; ++k)
       {
-        const int64_t base = rowptr[row];
-        const int nb = (int)(rowptr[row + 1] - base);
-        const VT *v = val + base * (R * C);
-        const int *ci = col + base;
-#pragma unroll UNROLL
-        for (int j = lane; j < nb; j += TPR)
+        const int64_t row = row0 + (int64_t)k * G + g;
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.0;
+        if (row < n_brows)
           {
-            const int c0 = ld_stream(ci + j);
-            double xv[C];
+            const int64_t base = rowptr[row];
+            const int nb = (int)(rowptr[row + 1] - base);
+            const VT *v = val + base * (R * C);
+            const int *ci = col + base;
+#pragma unroll UNROLL
+            for (int j = lane; j < nb; j += TPR)
+              {
+                const int c0 = ld_stream(ci + j);
+                double xv[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) xv[c] = __ldg(x + (int64_t)c0 * C + c);
+                for (int c = 0; c < C; ++c) xv[c] = __ldg(x + (int64_t)c0 * C + c);
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+                for (int r = 0; r < R; ++r)
 #pragma unroll
-              for (int c = 0; c < C; ++c) acc[r] = fma((double)ld_stream(v + (int64_t)(r * C + c) * nb + j), xv[c], acc[r]);
+                  for (int c = 0; c < C; ++c) acc[r] = fma((double)ld_stream(v + (int64_t)(r * C + c) * nb + j), xv[c], acc[r]);
+              }
           }
-      }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int o = TPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-    if (row < n_brows && lane == 0)
-      {
 #pragma unroll
         for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int o = TPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        if (row < n_brows && lane == 0)
           {
-            double *yp = y + row * R + r;
-            *yp = accumulate ? (*yp + acc[r]) : acc[r];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              {
+                double *yp = y + row * R + r;
+                *yp = accumulate ? (*yp + acc[r]) : acc[r];
+              }
           }
       }
   }
@@ -159,9 +167,11 @@ namespace ifem
 #define IFEM_SPMV_V(T, U, M)                                                                                                    \
   case T * 100 + U * 10 + M:                                                                                                    \
     {                                                                                                                           \
-      const int64_t nblk = ((int64_t)n_rows * T + threads - 1) / threads;                                                    \
+      const int rpw = std::max(1, ctx.spmv_rpw);                                                                                \
+      const int64_t per_cta = (int64_t)(threads / T) * rpw;                                                                     \
+      const int64_t nblk = (n_rows + per_cta - 1) / per_cta;                                                                    \
       bcsr_spmv_kernel<R, C, T, VT, U, M><<<(unsigned)nblk, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, y, \
-                                                                                      accumulate ? 1 : 0);                      \
+                                                                                      accumulate ? 1 : 0, rpw);                 \
       return;                                                                                                                   \
     }
           switch (key)
@@ -175,7 +185,7 @@ namespace ifem
 #undef IFEM_SPMV_V
         }
       bcsr_spmv_kernel<R, C, TPR, VT><<<(unsigned)blocks, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, y,
-                                                                                accumulate ? 1 : 0);
+                                                                                accumulate ? 1 : 0, 1);
     };
     switch (A.tpr)
       {
@@ -211,11 +221,14 @@ namespace ifem
   template <int R, int C, int TPR, int MINB>
   __global__ void __launch_bounds__(256, MINB)
   bcsr_spmv_f32x4_kernel(int n_brows, const int64_t *__restrict__ rowptr32, const int *__restrict__ col32,
-                         const float *__restrict__ val32, const double *__restrict__ x, double *__restrict__ y)
+                         const float *__restrict__ val32, const double *__restrict__ x, double *__restrict__ y, int rpw)
   {
-    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t row = gt / TPR;
-    const int lane = (int)(gt % TPR);
+    constexpr int G = 256 / TPR;
+    const int g = threadIdx.x / TPR, lane = threadIdx.x % TPR;
+    const int64_t row0 = (int64_t)blockIdx.x * G * rpw;
+    for (int kk = 0; kk < rpw; ++kk)
+    {
+    const int64_t row = row0 + (int64_t)kk * G + g;
     double acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
@@ -256,6 +269,7 @@ namespace ifem
 #pragma unroll
         for (int r = 0; r < R; ++r) y[row * R + r] = acc[r];
       }
+    }
   }
 
   void spmv_fp32(Context &ctx, const Bcsr &A, const double *x, double *y)
@@ -271,8 +285,10 @@ namespace ifem
     }();
     auto launch = [&](auto r_tag, auto tpr_tag, auto m_tag) {
       constexpr int RR = decltype(r_tag)::value, T = decltype(tpr_tag)::value, M = decltype(m_tag)::value;
-      const int64_t nblk = ((int64_t)n_rows * T + 255) / 256;
-      bcsr_spmv_f32x4_kernel<RR, RR, T, M><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y);
+      const int rpw = std::max(1, ctx.spmv_rpw);
+      const int64_t per_cta = (int64_t)(256 / T) * rpw;
+      const int64_t nblk = (n_rows + per_cta - 1) / per_cta;
+      bcsr_spmv_f32x4_kernel<RR, RR, T, M><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, rpw);
     };
     using I2 = std::integral_constant<int, 2>;
     using I3 = std::integral_constant<int, 3>;

@@ -32,6 +32,8 @@ const char *ifem_last_error(void);
 int ifem_version(void);
 /* bind this process (= one rank) to a CUDA device; called once before any solver is created */
 int ifem_init(int device);
+/* host threads (OpenMP) used by the setup code: mesh tables, sparsity patterns, partitioning */
+int ifem_set_host_threads(int n);
 /* number of kernels launched by the library so far in this process */
 int ifem_kernel_launches(int64_t *count);
 
@@ -177,6 +179,11 @@ int ifem_hyper_get_vector(ifem_hyper *s, int which, double *host);
 int ifem_hyper_get_matrix(ifem_hyper *s, int which, int64_t *rowptr, int *col, double *val);
 /* PointHistory arrays [cell][q]: F_inv [dim*dim], tau [dim*dim], Jc [nsym*nsym] (Voigt pairs (0,0),(1,1)[,(2,2)],(0,1)[,(0,2),(1,2)]), det F */
 int ifem_hyper_get_qph(ifem_hyper *s, double *F_inv, double *tau, double *Jc, double *det_F);
+/* update_strain_and_stress() of the shared solid solvers (source/mpi_shared_hyper_elasticity.cpp:599-714);
+ * which: 0 stress, 1 strain, each [dim*dim][n_nodes] */
+int ifem_hyper_update_strain_and_stress(ifem_hyper *s);
+int ifem_hyper_get_nodal_tensor(ifem_hyper *s, int which, double *host);
+int ifem_hyper_set_nodal_tensor(ifem_hyper *s, int which, const double *host);
 int ifem_hyper_history(const ifem_hyper *s, int max_records, ifem_solid_record *out, int *n_records);
 
 /* ---- MPI::FSI<dim> immersed coupling kernels (include/mpi_fsi.h:39-47, source/mpi_fsi.cpp:95-119, 143-224,

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import IfemError, InsControl, NewtonRecord, SolidRecord, check, dptr, iptr, lptr, lib
 
 __all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Solid", "MPI", "Partition", "IfemError", "init", "init_distributed",
-           "comm_unique_id", "comm_init", "comm_finalize", "kernel_launches"]
+           "comm_unique_id", "comm_init", "comm_finalize", "kernel_launches", "set_host_threads"]
 
 
 def init(device: int = 0):
@@ -52,6 +52,8 @@ def init_distributed(local_rank: int = None):
     local_rank = int(os.environ.get("LOCAL_RANK", "0")) if local_rank is None else local_rank
     torch.cuda.set_device(local_rank)
     init(local_rank)
+    # torchrun pins OMP_NUM_THREADS=1; the host-side setup (patterns, partition) is OpenMP code
+    set_host_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
     if world > 1:
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -93,6 +95,10 @@ class Partition:
             check(lib().ifem_partition_send_list(self._h, C.c_int(which), C.c_int(k), iptr(send)))
             res.append(dict(rank=v[0].value, send_local=send, recv_offset=v[2].value, recv_count=v[3].value))
         return res
+
+
+def set_host_threads(n: int):
+    check(lib().ifem_set_host_threads(C.c_int(n)))
 
 
 def kernel_launches() -> int:
@@ -442,6 +448,22 @@ class _HyperElasticity:
         Jc, det = np.empty((nqp, nsym, nsym)), np.empty(nqp)
         check(lib().ifem_hyper_get_qph(self._h, dptr(Finv), dptr(tau), dptr(Jc), dptr(det)))
         return Finv, tau, Jc, det
+
+    def update_strain_and_stress(self):
+        check(lib().ifem_hyper_update_strain_and_stress(self._h))
+
+    def _tensor_shape(self):
+        dim = self.tria.dim
+        return (dim * dim, self.n_dofs // dim)
+
+    def get_nodal_tensor(self, which):
+        out = np.empty(self._tensor_shape())
+        check(lib().ifem_hyper_get_nodal_tensor(self._h, C.c_int(which), dptr(out)))
+        return out
+
+    def set_nodal_tensor(self, which, host):
+        host = np.ascontiguousarray(host, dtype=np.float64).reshape(self._tensor_shape())
+        check(lib().ifem_hyper_set_nodal_tensor(self._h, C.c_int(which), dptr(host)))
 
     def history(self, max_records=4096):
         buf = (SolidRecord * max_records)()

@@ -1,6 +1,8 @@
 // extern "C" layer: see include/openifem_b200.h for the contract.
 #include "../../include/openifem_b200.h"
 
+#include <omp.h>
+
 #include <cstring>
 #include <memory>
 #include <string>
@@ -151,6 +153,13 @@ int ifem_init(int device)
     IFEM_CUDA(cudaSetDevice(device));
     g_initialised = true;
     (void)default_context();
+  });
+}
+
+int ifem_set_host_threads(int n)
+{
+  return guard([&] {
+    if (n > 0) omp_set_num_threads(n);
   });
 }
 
@@ -673,6 +682,28 @@ int ifem_hyper_get_qph(ifem_hyper *s, double *F_inv, double *tau, double *Jc, do
     if (tau) ss.d_tau.download(tau, ss.d_tau.n, st);
     if (Jc) ss.d_Jc.download(Jc, ss.d_Jc.n, st);
     if (det_F) ss.d_detF.download(det_F, ss.d_detF.n, st);
+  });
+}
+int ifem_hyper_update_strain_and_stress(ifem_hyper *s)
+{
+  return guard([&] {
+    s->s->update_strain_and_stress();
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+int ifem_hyper_get_nodal_tensor(ifem_hyper *s, int which, double *host)
+{
+  return guard([&] {
+    DevBuf<double> &v = which == 0 ? s->s->stress : s->s->strain;
+    v.download(host, v.n, s->s->ctx.stream);
+  });
+}
+int ifem_hyper_set_nodal_tensor(ifem_hyper *s, int which, const double *host)
+{
+  return guard([&] {
+    DevBuf<double> &v = which == 0 ? s->s->stress : s->s->strain;
+    v.upload(host, v.n, s->s->ctx.stream);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
   });
 }
 int ifem_hyper_history(const ifem_hyper *s, int max_records, ifem_solid_record *out, int *n_records)

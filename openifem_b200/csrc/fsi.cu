@@ -1,5 +1,7 @@
 #include "fsi.h"
 
+#include "scnsim.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -360,7 +362,7 @@ namespace ifem
     {
       int n_owned_nodes, nu, n_u_dofs_offset;
       const int *n2c_ptr, *n2c_cell, *n2c_loc, *cell_un, *indicator;
-      const unsigned char *node_interior;
+      const unsigned char *node_interior, *cell_owned;
       const double *un_coords, *cell_x, *sp_tables, *present, *solid_vel, *solid_acc;
       double inv_dt;
       int use_dirichlet;
@@ -403,7 +405,7 @@ namespace ifem
       // first adjacent cell with indicator == 1
       int cell = -1, loc = 0;
       for (int k = A.n2c_ptr[node]; k < A.n2c_ptr[node + 1]; ++k)
-        if (A.indicator[A.n2c_cell[k]] == 1)
+        if (A.indicator[A.n2c_cell[k]] == 1 && A.cell_owned[A.n2c_cell[k]])
           {
             cell = A.n2c_cell[k];
             loc = A.n2c_loc[k];
@@ -481,6 +483,48 @@ namespace ifem
           // (v_s - v_f)/dt + (grad v_f) v_f - a_s   (:559-565)
           A.fsi_acc[(int64_t)DIM * node + c] = (vs[c] - v[c]) * A.inv_dt + conv - as[c];
         }
+    }
+
+    // first part of find_fluid_bc (mpi_fsi.cpp:411-476): fsi_stress[k](dof) = sigma_fluid_k(dof) - sigma_solid_k(x_dof)
+    // on the scalar FE_Q(pu) support points of owned indicator-1 cells that lie in the solid, k over (i, j <= i)
+    template <int DIM>
+    __global__ void fluid_stress_bc_kernel(SolidView S, int n_owned_nodes, const int *__restrict__ n2c_ptr, const int *__restrict__ n2c_cell,
+                                           const int *__restrict__ indicator, const unsigned char *__restrict__ cell_owned,
+                                           const double *__restrict__ un_coords, int n_unodes, const double *__restrict__ fluid_stress,
+                                           int n_snodes, const double *__restrict__ solid_stress, double *__restrict__ fsi_stress,
+                                           int *__restrict__ error_flag)
+    {
+      constexpr int NV = 1 << DIM;
+      const int node = blockIdx.x * blockDim.x + threadIdx.x;
+      if (node >= n_owned_nodes) return;
+      bool hit = false;
+      for (int k = n2c_ptr[node]; k < n2c_ptr[node + 1] && !hit; ++k)
+        hit = indicator[n2c_cell[k]] != 0 && cell_owned[n2c_cell[k]];
+      if (!hit) return;
+      const double *p = un_coords + (int64_t)node * DIM;
+      if (!point_in_solid<DIM>(S, p)) return;
+      double xi[DIM];
+      const int sc = locate<DIM>(S, p, xi);
+      if (sc < 0)
+        {
+          // GridInterpolator::point_value returns 0 when the point is not found (utilities.cpp:228-233)
+          int si = 0;
+          for (int i = 0; i < DIM; ++i)
+            for (int j = 0; j <= i; ++j, ++si) fsi_stress[(int64_t)si * n_unodes + node] = fluid_stress[(int64_t)(i * DIM + j) * n_unodes + node];
+          (void)error_flag;
+          return;
+        }
+      double N[NV], dN[NV * DIM];
+      q1_shape<DIM>(xi, N, dN);
+      int si = 0;
+      for (int i = 0; i < DIM; ++i)
+        for (int j = 0; j <= i; ++j, ++si)
+          {
+            double ss = 0.0;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) ss = fma(N[v], solid_stress[(int64_t)(i * DIM + j) * n_snodes + S.cells[(int64_t)sc * NV + v]], ss);
+            fsi_stress[(int64_t)si * n_unodes + node] = fluid_stress[(int64_t)(i * DIM + j) * n_unodes + node] - ss;
+          }
     }
 
     template <int DIM>
@@ -572,6 +616,14 @@ namespace ifem
             for (int d = 0; d < dim; ++d) in = in && fe.lattice[a][d] > 0 && fe.lattice[a][d] < fs.pu;
             if (in) interior[n] = 1;
           }
+      // is_locally_owned() of every local fluid cell: the slab rank of the cell is this rank
+      std::vector<unsigned char> owned(fs.n_cells, 1);
+      if (fs.n_ranks > 1)
+        {
+          const std::vector<int> cr = slab_cell_ranks(fluid.triangulation, fs.n_ranks);
+          for (int c = 0; c < fs.n_cells; ++c) owned[c] = cr[fs.local_cells[c]] == fs.rank;
+        }
+      d_cell_owned.upload(owned, s);
       d_n2c_ptr.upload(ptr, s);
       d_n2c_cell.upload(cell, s);
       d_n2c_loc.upload(loc, s);
@@ -698,6 +750,24 @@ namespace ifem
     d_inner_inhom.zero(s);
     DevBuf<int> err(1);
     err.zero(s);
+    if (auto *scns = dynamic_cast<SCnsIM *>(&fluid))
+      {
+        // implementing the stress part for the fsi force (:411-476); the solid's nodal Cauchy stress comes from
+        // update_strain_and_stress()
+        const int blocks_s = (fs.n_owned_unodes + 127) / 128;
+        if (dim == 2)
+          fluid_stress_bc_kernel<2><<<blocks_s, 128, 0, s>>>(S, fs.n_owned_unodes, d_n2c_ptr.p, d_n2c_cell.p, fs.d_indicator.p, d_cell_owned.p,
+                                                             d_un_coords.p, fs.un.n_nodes, scns->stress.p, solid.ss.nt.n_nodes, solid.stress.p,
+                                                             scns->fsi_stress.p, err.p);
+        else
+          fluid_stress_bc_kernel<3><<<blocks_s, 128, 0, s>>>(S, fs.n_owned_unodes, d_n2c_ptr.p, d_n2c_cell.p, fs.d_indicator.p, d_cell_owned.p,
+                                                             d_un_coords.p, fs.un.n_nodes, scns->stress.p, solid.ss.nt.n_nodes, solid.stress.p,
+                                                             scns->fsi_stress.p, err.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+        if (fs.n_ranks > 1)
+          for (int k = 0; k < dim * (dim + 1) / 2; ++k) fs.halo_p.update(ctx, scns->fsi_stress.p + (size_t)k * fs.un.n_nodes);
+      }
     FluidBcArgs A{};
     A.n_owned_nodes = fs.n_owned_unodes;
     A.nu = fs.nu;
@@ -707,6 +777,7 @@ namespace ifem
     A.cell_un = fs.d_cell_un.p;
     A.indicator = fs.d_indicator.p;
     A.node_interior = d_node_interior.p;
+    A.cell_owned = d_cell_owned.p;
     A.un_coords = d_un_coords.p;
     A.cell_x = fs.d_cell_x.p;
     A.sp_tables = d_sp_tables.p;

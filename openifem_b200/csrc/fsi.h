@@ -55,6 +55,7 @@ namespace ifem
     DevBuf<int> d_bin_start, d_bin_cursor, d_bin_items;
     // fluid velocity node -> (cell, local index) adjacency, cells ascending
     DevBuf<int> d_n2c_ptr, d_n2c_cell, d_n2c_loc;
+    DevBuf<unsigned char> d_cell_owned;    // 1 for locally owned fluid cells (is_locally_owned)
     DevBuf<unsigned char> d_node_interior; // 1 for cell-centre nodes of the Q2 element
     DevBuf<double> d_un_coords;            // support point of every local velocity node
     DevBuf<double> d_sp_tables;            // dN_u at the unit support points [nu][nu][dim] | dN_geo [nu][nv][dim]

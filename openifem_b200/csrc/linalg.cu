@@ -97,6 +97,52 @@ namespace ifem
   // ---------------------------------------------------------------------------
   __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
 
+  // one block row per lane group
+  template <int R, int C, int TPR, typename VT, int UNROLL = 2, int MINB = 1>
+  __global__ void __launch_bounds__(256, MINB)
+  bcsr_spmv_row_kernel(int n_brows, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
+                       const VT *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, int accumulate)
+  {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = gt / TPR;
+    const int lane = (int)(gt % TPR);
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    if (row < n_brows)
+      {
+        const int64_t base = rowptr[row];
+        const int nb = (int)(rowptr[row + 1] - base);
+        const VT *v = val + base * (R * C);
+        const int *ci = col + base;
+#pragma unroll UNROLL
+        for (int j = lane; j < nb; j += TPR)
+          {
+            const int c0 = ld_stream(ci + j);
+            double xv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) xv[c] = __ldg(x + (int64_t)c0 * C + c);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+              for (int c = 0; c < C; ++c) acc[r] = fma((double)ld_stream(v + (int64_t)(r * C + c) * nb + j), xv[c], acc[r]);
+          }
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    if (row < n_brows && lane == 0)
+      {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          {
+            double *yp = y + row * R + r;
+            *yp = accumulate ? (*yp + acc[r]) : acc[r];
+          }
+      }
+  }
+
   // A CTA of 256 threads = G = 256 / TPR lane groups; group g handles rows row0 + k * G + g, k < rpw, of the
   // CTA's chunk of G * rpw consecutive rows. Consecutive rows share most of their column nodes, so walking a
   // chunk inside one CTA turns the x gathers of later rows into L1 hits (rpw = 1: one row per group).
@@ -170,8 +216,12 @@ namespace ifem
       const int rpw = std::max(1, ctx.spmv_rpw);                                                                                \
       const int64_t per_cta = (int64_t)(threads / T) * rpw;                                                                     \
       const int64_t nblk = (n_rows + per_cta - 1) / per_cta;                                                                    \
-      bcsr_spmv_kernel<R, C, T, VT, U, M><<<(unsigned)nblk, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, y, \
-                                                                                      accumulate ? 1 : 0, rpw);                 \
+      if (rpw == 1)                                                                                                             \
+        bcsr_spmv_row_kernel<R, C, T, VT, U, M><<<(unsigned)nblk, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, \
+                                                                                            y, accumulate ? 1 : 0);             \
+      else                                                                                                                      \
+        bcsr_spmv_kernel<R, C, T, VT, U, M><<<(unsigned)nblk, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, y, \
+                                                                                        accumulate ? 1 : 0, rpw);               \
       return;                                                                                                                   \
     }
           switch (key)
@@ -279,10 +329,23 @@ namespace ifem
     if (!n_rows) return;
     const int key = A.R * 10 + A.C;
     // lanes per row / min CTAs per SM: IFEM_SPMV32_VARIANT = 10 * lanes + minb (default 8 lanes, 4 CTAs)
+    // IFEM_SPMV32_VARIANT: 0 (default) = one block per lane, 16 lanes per row (fastest in the round-1 sweeps:
+    // 10.3 ms at config 3); 10 * lanes + min CTAs = the 4-blocks-per-lane LDG.128 kernel
     static const int variant = [] {
       const char *v = std::getenv("IFEM_SPMV32_VARIANT");
-      return v ? std::atoi(v) : 84;
+      return v ? std::atoi(v) : 0;
     }();
+    if (variant == 0 && (key == 33 || key == 22))
+      {
+        const int64_t nblk = ((int64_t)n_rows * 16 + 255) / 256;
+        if (key == 33)
+          bcsr_spmv_row_kernel<3, 3, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
+        else
+          bcsr_spmv_row_kernel<2, 2, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+        return;
+      }
     auto launch = [&](auto r_tag, auto tpr_tag, auto m_tag) {
       constexpr int RR = decltype(r_tag)::value, T = decltype(tpr_tag)::value, M = decltype(m_tag)::value;
       const int rpw = std::max(1, ctx.spmv_rpw);

@@ -125,10 +125,29 @@ namespace ifem
       np.n_local = (int)np.local_to_global.size();
       std::vector<int> g2l(nt.n_nodes, -1);
       for (int l = 0; l < np.n_local; ++l) g2l[np.local_to_global[l]] = l;
-      // what every other rank expects from me, per layer (its ghost sets, computed from the same global data)
+      // what every other rank expects from me, per layer (its ghost sets, computed from the same global data);
+      // only ranks whose local cells contain a node I own can expect anything
+      std::vector<char> wants(size, 0);
+      {
+        const int npc = nt.nodes_per_cell;
+        for (int c = 0; c < n_cells; ++c)
+          {
+            bool mine_here = false, checked = false;
+            for (int s = 0; s < size; ++s)
+              {
+                if (s == rank || wants[s] || !layers_of_rank[s][c]) continue;
+                if (!checked)
+                  {
+                    for (int a = 0; a < npc && !mine_here; ++a) mine_here = owner[nt.cell_nodes[(size_t)c * npc + a]] == rank;
+                    checked = true;
+                  }
+                if (mine_here) wants[s] = 1;
+              }
+          }
+      }
       std::vector<GhostSets> theirs(size);
       for (int s = 0; s < size; ++s)
-        if (s != rank) theirs[s] = ghost_sets(nt, n_cells, owner, layers_of_rank[s], s);
+        if (s != rank && wants[s]) theirs[s] = ghost_sets(nt, n_cells, owner, layers_of_rank[s], s);
       for (int layer = 1; layer <= 2; ++layer)
         {
           const std::vector<int> &my_ghosts = layer == 1 ? mine.g1 : mine.g2;

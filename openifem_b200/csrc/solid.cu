@@ -332,6 +332,72 @@ namespace ifem
         }
     }
 
+    // one thread per cell (cells of one colour per launch): quadrature values -> qpt_to_dof -> nodal scatter-add
+    template <int DIM, int NPC>
+    __global__ void solid_stress_kernel(int n_list, const int *__restrict__ cell_list, int nq, const int *__restrict__ cell_nodes,
+                                        const double *__restrict__ qpt_to_dof, const double *__restrict__ Finv,
+                                        const double *__restrict__ tau, const double *__restrict__ detF, int n_nodes,
+                                        double *__restrict__ stress, double *__restrict__ strain, double *__restrict__ count)
+    {
+      const int li = blockIdx.x * blockDim.x + threadIdx.x;
+      if (li >= n_list) return;
+      const int cell = cell_list[li];
+      for (int a = 0; a < NPC; ++a)
+        {
+          const int node = cell_nodes[(int64_t)cell * NPC + a];
+          double st[DIM * DIM], sn[DIM * DIM];
+#pragma unroll
+          for (int i = 0; i < DIM * DIM; ++i) st[i] = sn[i] = 0.0;
+          for (int q = 0; q < nq; ++q)
+            {
+              const int64_t cq = (int64_t)cell * nq + q;
+              const double w = qpt_to_dof[a * nq + q], J = detF[cq];
+              // F = (F^-1)^-1
+              const double *fi = Finv + cq * DIM * DIM;
+              double F[DIM * DIM];
+              if (DIM == 2)
+                {
+                  const double d = 1.0 / (fi[0] * fi[3] - fi[1] * fi[2]);
+                  F[0] = fi[3] * d; F[1] = -fi[1] * d; F[2] = -fi[2] * d; F[3] = fi[0] * d;
+                }
+              else
+                {
+                  const double c00 = fi[4] * fi[8] - fi[5] * fi[7], c01 = fi[5] * fi[6] - fi[3] * fi[8], c02 = fi[3] * fi[7] - fi[4] * fi[6];
+                  const double d = 1.0 / (fi[0] * c00 + fi[1] * c01 + fi[2] * c02);
+                  F[0] = c00 * d; F[1] = (fi[2] * fi[7] - fi[1] * fi[8]) * d; F[2] = (fi[1] * fi[5] - fi[2] * fi[4]) * d;
+                  F[3] = c01 * d; F[4] = (fi[0] * fi[8] - fi[2] * fi[6]) * d; F[5] = (fi[2] * fi[3] - fi[0] * fi[5]) * d;
+                  F[6] = c02 * d; F[7] = (fi[1] * fi[6] - fi[0] * fi[7]) * d; F[8] = (fi[0] * fi[4] - fi[1] * fi[3]) * d;
+                }
+#pragma unroll
+              for (int i = 0; i < DIM * DIM; ++i)
+                {
+                  st[i] = fma(w, tau[cq * DIM * DIM + i] / J, st[i]);
+                  sn[i] = fma(w, F[i], sn[i]);
+                }
+            }
+#pragma unroll
+          for (int i = 0; i < DIM * DIM; ++i)
+            {
+              stress[(int64_t)i * n_nodes + node] += st[i];
+              strain[(int64_t)i * n_nodes + node] += sn[i];
+            }
+          count[node] += 1.0;
+        }
+    }
+
+    __global__ void solid_average_kernel(int n_nodes, int ncomp, const double *__restrict__ count, double *__restrict__ a, double *__restrict__ b)
+    {
+      const int i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n_nodes) return;
+      const double c = count[i];
+      if (c > 0)
+        for (int k = 0; k < ncomp; ++k)
+          {
+            a[(int64_t)k * n_nodes + i] /= c;
+            b[(int64_t)k * n_nodes + i] /= c;
+          }
+    }
+
     struct ScopedTimer
     {
       Context &ctx;
@@ -511,6 +577,48 @@ namespace ifem
         v->zero(ctx.stream);
       }
     d_binv.alloc((size_t)ss.nt.n_nodes * ss.dim * ss.dim);
+    stress.alloc((size_t)ss.dim * ss.dim * ss.nt.n_nodes);
+    strain.alloc((size_t)ss.dim * ss.dim * ss.nt.n_nodes);
+    stress.zero(ctx.stream);
+    strain.zero(ctx.stream);
+    d_count.alloc(ss.nt.n_nodes);
+    {
+      // qpt_to_dof = M^-1 Q^T W on the reference cell (FETools::compute_projection_from_quadrature_points_matrix)
+      FEQ fe(ss.dim, ss.degree);
+      Quadrature quad(ss.dim, ss.degree + 1);
+      ShapeTable tab(fe, quad.points, quad.nq);
+      const int n = fe.n, nq = quad.nq;
+      std::vector<double> M((size_t)n * n, 0.0), R((size_t)n * nq, 0.0);
+      for (int q = 0; q < nq; ++q)
+        for (int i = 0; i < n; ++i)
+          {
+            R[(size_t)i * nq + q] = tab.N[(size_t)q * n + i] * quad.weights[q];
+            for (int j = 0; j < n; ++j) M[(size_t)i * n + j] += tab.N[(size_t)q * n + i] * tab.N[(size_t)q * n + j] * quad.weights[q];
+          }
+      for (int c = 0; c < n; ++c)
+        {
+          int piv = c;
+          for (int r2 = c + 1; r2 < n; ++r2)
+            if (std::fabs(M[(size_t)r2 * n + c]) > std::fabs(M[(size_t)piv * n + c])) piv = r2;
+          if (piv != c)
+            {
+              for (int k = 0; k < n; ++k) std::swap(M[(size_t)c * n + k], M[(size_t)piv * n + k]);
+              for (int k = 0; k < nq; ++k) std::swap(R[(size_t)c * nq + k], R[(size_t)piv * nq + k]);
+            }
+          const double d = 1.0 / M[(size_t)c * n + c];
+          for (int k = 0; k < n; ++k) M[(size_t)c * n + k] *= d;
+          for (int k = 0; k < nq; ++k) R[(size_t)c * nq + k] *= d;
+          for (int r2 = 0; r2 < n; ++r2)
+            {
+              if (r2 == c) continue;
+              const double f = M[(size_t)r2 * n + c];
+              if (f == 0.0) continue;
+              for (int k = 0; k < n; ++k) M[(size_t)r2 * n + k] -= f * M[(size_t)c * n + k];
+              for (int k = 0; k < nq; ++k) R[(size_t)r2 * nq + k] -= f * R[(size_t)c * nq + k];
+            }
+        }
+      d_qpt_to_dof.upload(R, ctx.stream);
+    }
     // setup_qph (:217-239): PointHistory::setup calls update with a zero displacement gradient
     update_qph(current_displacement.p);
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -527,6 +635,32 @@ namespace ifem
     else
       update_qph_kernel<3, 8><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, c1, kappa,
                                                                            ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+  }
+
+  void HyperElasticity::update_strain_and_stress()
+  {
+    cudaStream_t s = ctx.stream;
+    stress.zero(s);
+    strain.zero(s);
+    d_count.zero(s);
+    const int n_colours = (int)ss.colour_offsets.size() - 1;
+    for (int k = 0; k < n_colours; ++k)
+      {
+        const int n = ss.colour_offsets[k + 1] - ss.colour_offsets[k];
+        if (!n) continue;
+        const int *list = ss.d_colour_order.p + ss.colour_offsets[k];
+        if (ss.dim == 2)
+          solid_stress_kernel<2, 4><<<(n + 127) / 128, 128, 0, s>>>(n, list, ss.nq, ss.d_cell_nodes.p, d_qpt_to_dof.p, ss.d_Finv.p, ss.d_tau.p,
+                                                                    ss.d_detF.p, ss.nt.n_nodes, stress.p, strain.p, d_count.p);
+        else
+          solid_stress_kernel<3, 8><<<(n + 127) / 128, 128, 0, s>>>(n, list, ss.nq, ss.d_cell_nodes.p, d_qpt_to_dof.p, ss.d_Finv.p, ss.d_tau.p,
+                                                                    ss.d_detF.p, ss.nt.n_nodes, stress.p, strain.p, d_count.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+    solid_average_kernel<<<(ss.nt.n_nodes + 255) / 256, 256, 0, s>>>(ss.nt.n_nodes, ss.dim * ss.dim, d_count.p, stress.p, strain.p);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
   }

@@ -59,6 +59,9 @@ namespace ifem
     void initialize_system();
     void update_qph(const double *u_dev);
     void assemble_system(bool initial_step);
+    // SharedHyperElasticity::update_strain_and_stress (source/mpi_shared_hyper_elasticity.cpp:599-714): Cauchy stress
+    // tau / J and deformation gradient F at the quadrature points, projected to the nodes and averaged
+    void update_strain_and_stress();
     std::pair<unsigned int, double> solve(Bcsr &A, double *x, const double *b);
 
     Context &ctx;
@@ -67,6 +70,7 @@ namespace ifem
     SolidSpace ss;
     Time time;
     bool verbose = false, dofs_ready = false;
+    DevBuf<double> stress, strain; // [dim*dim][n_nodes] nodal Cauchy stress / deformation gradient
     DevBuf<double> current_displacement, current_velocity, current_acceleration, previous_displacement, previous_velocity,
       previous_acceleration;
     struct Record
@@ -80,7 +84,7 @@ namespace ifem
 
   private:
     double get_error(const double *v);
-    DevBuf<double> d_binv, d_tmp, d_pred, d_update;
+    DevBuf<double> d_binv, d_tmp, d_pred, d_update, d_qpt_to_dof, d_count;
     VecPool pool;
   };
 } // namespace ifem

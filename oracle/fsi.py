@@ -175,6 +175,38 @@ def update_indicator(fluid_mesh: fem.BoxMesh, solid: SolidGeometry):
     return ind
 
 
+def interpolate_scalar(solid: SolidGeometry, nodal, p):
+    c, xi = solid.locate(p)
+    if c is None:
+        return 0.0  # GridInterpolator::point_value returns 0 when the point is not found
+    N, _ = q1_shape(solid.dim, xi)
+    return float(N @ nodal[solid.cells[c]])
+
+
+def find_fluid_bc_stress(fluid, solid: SolidGeometry, indicator, solid_stress, fsi_stress):
+    """First part of find_fluid_bc (mpi_fsi.cpp:411-476): fluid has .stress [dim*dim][n_unodes] and the scalar
+    FE_Q(pu) support points = velocity nodes; fsi_stress [dim(dim+1)/2][n_unodes] is updated IN PLACE (entries not
+    touched keep their values, as in the reference)."""
+    dim, d = fluid.dim, fluid.dofs
+    touched = np.zeros(d.n_unodes, dtype=bool)
+    for c in range(fluid.mesh.n_cells):
+        if indicator[c] == 0:
+            continue
+        for node in d.unodes[c]:
+            if touched[node]:
+                continue
+            touched[node] = True
+            p = d.ucoords[node]
+            if not solid.point_in_solid(p):
+                continue
+            k = 0
+            for i in range(dim):
+                for j in range(i + 1):
+                    fsi_stress[k, node] = fluid.stress[i * dim + j, node] - interpolate_scalar(solid, solid_stress[i * dim + j], p)
+                    k += 1
+    return fsi_stress
+
+
 def find_fluid_bc(fluid, solid: SolidGeometry, indicator, solid_velocity, solid_acceleration, dt, use_dirichlet_bc=False):
     """fluid: oracle.ins.InsIM (Q2/Q1). Returns fsi_acceleration [n_dofs] and, for the Dirichlet variant,
     (flags [n_dofs], inhomogeneity [n_dofs]) of the inner constraints BEFORE the merge."""

@@ -121,6 +121,25 @@ class HyperElasticity:
         grad_u = np.einsum("cai,cqak->cqik", ue, self.G)
         self.F_inv, self.tau, self.Jc, self.detF = neo_hookean_update(grad_u, self.c1, self.kappa)
 
+    # -- SharedHyperElasticity::update_strain_and_stress (mpi_shared_hyper_elasticity.cpp:599-714) ------------
+    def update_strain_and_stress(self):
+        dim, nodes = self.dim, self.dofs.nodes
+        Mref = np.einsum("qi,qj,q->ij", self.N, self.N, self.qw)
+        qpt_to_dof = np.linalg.solve(Mref, (self.N * self.qw[:, None]).T)
+        quad_stress = self.tau / self.detF[..., None, None]
+        quad_strain = np.linalg.inv(self.F_inv)
+        cs = np.einsum("aq,cqij->cija", qpt_to_dof, quad_stress)
+        ce = np.einsum("aq,cqij->cija", qpt_to_dof, quad_strain)
+        n = self.dofs.n_nodes
+        stress, strain, count = np.zeros((dim * dim, n)), np.zeros((dim * dim, n)), np.zeros(n)
+        np.add.at(count, nodes.ravel(), 1.0)
+        for i in range(dim):
+            for j in range(dim):
+                np.add.at(stress[i * dim + j], nodes.ravel(), cs[:, i, j, :].ravel())
+                np.add.at(strain[i * dim + j], nodes.ravel(), ce[:, i, j, :].ravel())
+        self.stress, self.strain = stress / count, strain / count
+        return self.stress, self.strain
+
     # -- assemble_system (:317-535) ---------------------------------------------
     def local_matrices(self, initial_step):
         dim, nc, npc, nq = self.dim, self.mesh.n_cells, self.npc, self.nq

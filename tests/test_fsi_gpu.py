@@ -127,3 +127,59 @@ def test_find_fluid_bc_dirichlet(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, di
     assert ref_con.sum() > 0
     assert np.array_equal(flags, ref_con)
     assert _rel(inhom, ref_inhom) < 1e-10
+
+
+@pytest.mark.parametrize("dim,f_reps,s_reps,s_lo,s_hi,disp", [
+    (2, (12, 12), (5, 7), (0.3, 0.2), (0.6, 0.9), SHEAR2),
+    (3, (6, 6, 6), (3, 4, 5), (0.2, 0.25, 0.1), (0.7, 0.8, 0.85), BEND3),
+])
+def test_find_fluid_bc_stress_part_scnsim(golden_dir, dim, f_reps, s_reps, s_lo, s_hi, disp):
+    """first part of find_fluid_bc (mpi_fsi.cpp:411-476) with the slightly compressible fluid solver: fsi_stress =
+    fluid nodal stress - interpolated solid nodal stress, plus the acceleration part on the same run"""
+    import openifem_b200 as ifem
+    from oracle import fem, fsi, prm, scns
+    from test_scns_gpu import scns_prm
+
+    lo, hi = (0.0,) * dim, (1.0,) * dim
+    text = scns_prm(dim)
+    o_fluid = scns.SCnsIM(fem.BoxMesh(f_reps, lo, hi), prm.Params(text, is_text=True))
+    s_mesh = fem.BoxMesh(s_reps, s_lo, s_hi)
+    rng = np.random.default_rng(21)
+    d = disp(s_mesh.vertices).ravel()
+    vel, acc = rng.uniform(-1, 1, d.size), rng.uniform(-1, 1, d.size)
+    present = rng.uniform(-1, 1, o_fluid.n)
+    o_fluid.present[:] = present
+    o_fluid.update_stress()
+    solid_stress = rng.uniform(-1, 1, (dim * dim, s_mesh.vertices.shape[0]))
+    geo = fsi.SolidGeometry(s_mesh, d)
+
+    ftria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(ftria, f_reps, lo, hi, True)
+    fluid = ifem.Fluid.MPI.SCnsIM(ftria, ifem.Parameters.AllParameters(text=text))
+    fluid.setup()
+    fluid.set_vector(fluid.PRESENT, present)
+    fluid.update_stress()
+    stria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(stria, s_reps, s_lo, s_hi, True)
+    solid = ifem.Solid.MPI.HyperElasticity(stria, ifem.Parameters.AllParameters(_solid_prm(golden_dir, dim)))
+    solid.setup()
+    solid.set_vector(solid.CUR_U, d)
+    solid.set_vector(solid.CUR_V, vel)
+    solid.set_vector(solid.CUR_A, acc)
+    solid.set_nodal_tensor(0, solid_stress)
+    coupling = ifem.MPI.FSI(fluid, solid, ifem.Parameters.AllParameters(text=text), False)
+    coupling.update_solid_box()
+    ind = coupling.update_indicator()
+    assert ind.sum() > 0
+    ref = fsi.find_fluid_bc_stress(o_fluid, geo, ind, solid_stress, np.zeros_like(o_fluid.fsi_stress))
+    got_acc = coupling.find_fluid_bc()
+    got = fluid.get_field(1)
+    assert np.count_nonzero(ref) > 0
+    assert _rel(got, ref) < 1e-10
+    # acceleration part with the Q1/Q1 fluid
+    class _F:  # adapter: the oracle's find_fluid_bc needs these attributes of the fluid solver
+        pass
+    f = _F()
+    f.dim, f.dofs, f.feu, f.n, f.n_u, f.mesh, f.present = dim, o_fluid.dofs, o_fluid.feu, o_fluid.n, o_fluid.n_u, o_fluid.mesh, o_fluid.present
+    ref_acc, _, _ = fsi.find_fluid_bc(f, geo, ind, vel, acc, o_fluid.dt)
+    assert _rel(got_acc, ref_acc) < 1e-10

@@ -85,3 +85,18 @@ def test_beam_bending_reference_golden_on_gpu(golden_dir, dim, reps, hi, umin, u
     u = s.get_current_solution()
     assert abs((u.min() - umin) / umin) < 1e-3
     assert abs((u.max() - umax) / umax) < 1e-3
+
+
+@pytest.mark.parametrize("dim,reps,hi", [(2, (10, 3), (10.0, 1.0)), (3, (6, 2, 3), (10.0, 1.0, 1.2))])
+def test_update_strain_and_stress_matches_oracle(golden_dir, dim, reps, hi):
+    """SharedHyperElasticity::update_strain_and_stress (source/mpi_shared_hyper_elasticity.cpp:599-714)"""
+    o, g = _make(golden_dir, dim, reps, hi)
+    rng = np.random.default_rng(12)
+    u = 0.05 * rng.uniform(-1, 1, o.n)
+    o.update_qph(u)
+    g.set_vector(g.CUR_U, u)
+    g.update_qph()
+    stress, strain = o.update_strain_and_stress()
+    g.update_strain_and_stress()
+    assert _rel(g.get_nodal_tensor(0), stress) < 1e-12
+    assert _rel(g.get_nodal_tensor(1), strain) < 1e-12

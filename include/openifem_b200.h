@@ -184,6 +184,8 @@ int ifem_hyper_get_qph(ifem_hyper *s, double *F_inv, double *tau, double *Jc, do
 int ifem_hyper_update_strain_and_stress(ifem_hyper *s);
 int ifem_hyper_get_nodal_tensor(ifem_hyper *s, int which, double *host);
 int ifem_hyper_set_nodal_tensor(ifem_hyper *s, int which, const double *host);
+/* what MPI::FSI::find_solid_bc wrote: fsi_stress_rows [dim][n_dofs], fluid_velocity [n_dofs], fluid_pressure [n_nodes] */
+int ifem_hyper_get_fsi_inputs(ifem_hyper *s, double *fsi_stress_rows, double *fluid_velocity, double *fluid_pressure);
 int ifem_hyper_history(const ifem_hyper *s, int max_records, ifem_solid_record *out, int *n_records);
 
 /* ---- MPI::FSI<dim> immersed coupling kernels (include/mpi_fsi.h:39-47, source/mpi_fsi.cpp:95-119, 143-224,
@@ -208,6 +210,11 @@ int ifem_fsi_point_in_solid(ifem_fsi *f, int n, const double *points, int *insid
 /* GridInterpolator::point_value of a solid field (0 velocity, 1 acceleration, 2 displacement): values [n][dim],
  * found[n] = index of the solid cell used or -1 (value 0, as utilities.cpp:228-233) */
 int ifem_fsi_interpolate(ifem_fsi *f, int which, int n, const double *points, double *values, int *found);
+/* find_solid_bc() (source/mpi_fsi.cpp:666-867): fills the solid's fsi_stress_rows / fluid_velocity / fluid_pressure */
+int ifem_fsi_find_solid_bc(ifem_fsi *f);
+/* one pass of the time loop of FSI::run (source/mpi_fsi.cpp:1172-1214) / the whole loop (no refinement, no checkpoints) */
+int ifem_fsi_run_one_step(ifem_fsi *f, int first_step);
+int ifem_fsi_run(ifem_fsi *f);
 int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms);
 
 /* ---- measurement hooks (bench.py): device-resident, CUDA-event timed on the library's stream ---- */

@@ -452,6 +452,13 @@ class _HyperElasticity:
     def update_strain_and_stress(self):
         check(lib().ifem_hyper_update_strain_and_stress(self._h))
 
+    def get_fsi_inputs(self):
+        dim = self.tria.dim
+        n = self.n_dofs
+        rows, vel, pres = np.empty((dim, n)), np.empty(n), np.empty(n // dim)
+        check(lib().ifem_hyper_get_fsi_inputs(self._h, dptr(rows), dptr(vel), dptr(pres)))
+        return rows, vel, pres
+
     def _tensor_shape(self):
         dim = self.tria.dim
         return (dim * dim, self.n_dofs // dim)
@@ -498,6 +505,16 @@ class _FSI:
 
     def _n_local_cells(self):
         raise NotImplementedError("indicator download on multi-rank runs: use the C ABI with the local cell count")
+
+    def find_solid_bc(self):
+        check(lib().ifem_fsi_find_solid_bc(self._h))
+        return self.solid.get_fsi_inputs()
+
+    def run_one_step(self, first_step: bool):
+        check(lib().ifem_fsi_run_one_step(self._h, C.c_int(1 if first_step else 0)))
+
+    def run(self):
+        check(lib().ifem_fsi_run(self._h))
 
     def find_fluid_bc(self):
         check(lib().ifem_fsi_find_fluid_bc(self._h))

@@ -706,6 +706,15 @@ int ifem_hyper_set_nodal_tensor(ifem_hyper *s, int which, const double *host)
     IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
   });
 }
+int ifem_hyper_get_fsi_inputs(ifem_hyper *s, double *rows, double *vel, double *pres)
+{
+  return guard([&] {
+    HyperElasticity &m = *s->s;
+    if (rows) m.fsi_stress_rows.download(rows, m.fsi_stress_rows.n, m.ctx.stream);
+    if (vel) m.fluid_velocity.download(vel, m.fluid_velocity.n, m.ctx.stream);
+    if (pres) m.fluid_pressure.download(pres, m.fluid_pressure.n, m.ctx.stream);
+  });
+}
 int ifem_hyper_history(const ifem_hyper *s, int max_records, ifem_solid_record *out, int *n_records)
 {
   return guard([&] {
@@ -773,6 +782,21 @@ int ifem_fsi_point_in_solid(ifem_fsi *f, int n, const double *points, int *insid
 int ifem_fsi_interpolate(ifem_fsi *f, int which, int n, const double *points, double *values, int *found)
 {
   return guard([&] { f->f->interpolate(which, n, points, values, found); });
+}
+int ifem_fsi_find_solid_bc(ifem_fsi *f)
+{
+  return guard([&] {
+    f->f->find_solid_bc();
+    IFEM_CUDA(cudaStreamSynchronize(f->f->ctx.stream));
+  });
+}
+int ifem_fsi_run_one_step(ifem_fsi *f, int first_step)
+{
+  return guard([&] { f->f->run_one_step(first_step != 0); });
+}
+int ifem_fsi_run(ifem_fsi *f)
+{
+  return guard([&] { f->f->run(); });
 }
 int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms)
 {

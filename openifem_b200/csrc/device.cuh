@@ -99,6 +99,7 @@ namespace ifem
     double *h_results = nullptr; // pinned
     Comm *comm = nullptr;
     int spmv_variant = 0; // 0 = default kernel; see linalg.cu
+    int spmv_l2hint = 0;  // 1: x gathers carry an L2 evict_last policy (IFEM_SPMV_L2HINT)
     int spmv_rpw = 1;     // rows per lane group and CTA chunk (x reuse through L1); IFEM_SPMV_RPW
     long long kernel_launches = 0; // counted by every launcher (bench "gpu_launches")
     Context();

@@ -1,5 +1,6 @@
 #include "fsi.h"
 
+#include "comm.h"
 #include "scnsim.h"
 
 #include <algorithm>
@@ -527,6 +528,214 @@ namespace ifem
           }
     }
 
+    // ---- locating a point in the (static) fluid mesh: GridInterpolator on the fluid DoFHandler -------------------
+    struct FluidView
+    {
+      const double *cell_x; // [n_cells][2^dim][dim]
+      const unsigned char *cell_owned;
+      const double *box;    // [2*dim]
+      int nbin[3];
+      const int *bin_start, *bin_items;
+    };
+
+    template <int DIM>
+    __device__ bool point_in_fluid_cell(const double *V, const double *p, double *xi_out)
+    {
+      constexpr int NV = 1 << DIM;
+      double lo[DIM], hi[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        {
+          lo[d] = 1e300;
+          hi[d] = -1e300;
+        }
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+          {
+            lo[d] = fmin(lo[d], V[v * DIM + d]);
+            hi[d] = fmax(hi[d], V[v * DIM + d]);
+          }
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        if (p[d] < lo[d] - kBoxSlack || p[d] > hi[d] + kBoxSlack) return false;
+      double xi[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) xi[d] = 0.5;
+      bool converged = false;
+      for (int it = 0; it < 30 && !converged; ++it)
+        {
+          double N[NV], dN[NV * DIM], r[DIM], J[DIM * DIM], dx[DIM];
+          q1_shape<DIM>(xi, N, dN);
+#pragma unroll
+          for (int i = 0; i < DIM; ++i)
+            {
+              double sacc = -p[i];
+#pragma unroll
+              for (int v = 0; v < NV; ++v) sacc += N[v] * V[v * DIM + i];
+              r[i] = sacc;
+#pragma unroll
+              for (int j = 0; j < DIM; ++j)
+                {
+                  double t = 0.0;
+#pragma unroll
+                  for (int v = 0; v < NV; ++v) t += V[v * DIM + i] * dN[v * DIM + j];
+                  J[i * DIM + j] = t;
+                }
+            }
+          if (!solve_small<DIM>(J, r, dx)) return false;
+          double n2 = 0.0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+            {
+              xi[d] -= dx[d];
+              n2 += dx[d] * dx[d];
+            }
+          converged = sqrt(n2) < 1e-13;
+        }
+      if (!converged) return false;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        if (xi[d] < -kUnitTol || xi[d] > 1.0 + kUnitTol) return false;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) xi_out[d] = fmin(fmax(xi[d], 0.0), 1.0);
+      return true;
+    }
+
+    // lowest-numbered local fluid cell containing p, -1 if none
+    template <int DIM>
+    __device__ int locate_fluid(const FluidView &F, const double *p, double *xi)
+    {
+      constexpr int NV = 1 << DIM;
+      int b = 0, stride = 1;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        {
+          if (p[d] < F.box[2 * d] - kBoxSlack || p[d] > F.box[2 * d + 1] + kBoxSlack) return -1;
+          const double ext = F.box[2 * d + 1] - F.box[2 * d];
+          int k = ext > 0 ? (int)floor((p[d] - F.box[2 * d]) / ext * F.nbin[d]) : 0;
+          k = min(max(k, 0), F.nbin[d] - 1);
+          b += k * stride;
+          stride *= F.nbin[d];
+        }
+      int best = -1;
+      for (int k = F.bin_start[b]; k < F.bin_start[b + 1]; ++k)
+        {
+          const int c = F.bin_items[k];
+          if (best >= 0 && c > best) continue;
+          double t[DIM];
+          if (point_in_fluid_cell<DIM>(F.cell_x + (int64_t)c * NV * DIM, p, t))
+            {
+              best = c;
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) xi[d] = t[d];
+            }
+        }
+      return best;
+    }
+
+    // FE_Q(p) shape values at xi, p = 1 or 2, nodes lexicographic (x fastest)
+    template <int DIM>
+    __device__ void lagrange_shape(int p, const double *xi, double *N)
+    {
+      double L[DIM][3];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        {
+          const double x = xi[d];
+          if (p == 1)
+            {
+              L[d][0] = 1.0 - x;
+              L[d][1] = x;
+              L[d][2] = 0.0;
+            }
+          else
+            {
+              L[d][0] = 2.0 * (x - 0.5) * (x - 1.0);
+              L[d][1] = -4.0 * x * (x - 1.0);
+              L[d][2] = 2.0 * x * (x - 0.5);
+            }
+        }
+      const int n1 = p + 1;
+      int n = 1;
+      for (int d = 0; d < DIM; ++d) n *= n1;
+      for (int a = 0; a < n; ++a)
+        {
+          int r = a;
+          double v = 1.0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+            {
+              v *= L[d][r % n1];
+              r /= n1;
+            }
+          N[a] = v;
+        }
+    }
+
+    struct SolidBcArgs
+    {
+      int n_bvert;
+      const int *bvert;
+      const double *x; // deformed solid vertices
+      int pu, pp, nu, np;
+      const int *cell_un, *cell_pn;
+      int64_t n_u;
+      int n_unodes;
+      const double *present, *fluid_stress; // fluid_stress may be null
+      int64_t n_sdofs;
+      double *rows, *fluid_velocity, *fluid_pressure;
+    };
+
+    // find_solid_bc (mpi_fsi.cpp:704-806): one thread per vertex of the solid's non-fixed boundary faces
+    template <int DIM>
+    __global__ void solid_bc_kernel(FluidView F, SolidBcArgs A)
+    {
+      const int k = blockIdx.x * blockDim.x + threadIdx.x;
+      if (k >= A.n_bvert) return;
+      const int node = A.bvert[k];
+      const double *p = A.x + (int64_t)node * DIM;
+      double xi[DIM];
+      const int cell = locate_fluid<DIM>(F, p, xi);
+      // not found, or found in a cell another rank owns: contributes zero (utilities.cpp:228-233) and the
+      // all-reduce over ranks fills it in
+      if (cell < 0 || !F.cell_owned[cell]) return;
+      double Nu[27], Np[27];
+      lagrange_shape<DIM>(A.pu, xi, Nu);
+      lagrange_shape<DIM>(A.pp, xi, Np);
+      double v[DIM], pr = 0.0, visc[DIM * DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) v[d] = 0.0;
+#pragma unroll
+      for (int i = 0; i < DIM * DIM; ++i) visc[i] = 0.0;
+      for (int b = 0; b < A.nu; ++b)
+        {
+          const int un = A.cell_un[(int64_t)cell * A.nu + b];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) v[d] = fma(Nu[b], A.present[(int64_t)DIM * un + d], v[d]);
+          if (A.fluid_stress)
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+              for (int j = i; j < DIM; ++j) visc[i * DIM + j] = fma(Nu[b], A.fluid_stress[(int64_t)(i * DIM + j) * A.n_unodes + un], visc[i * DIM + j]);
+        }
+      for (int j = 0; j < A.np; ++j) pr = fma(Np[j], A.present[A.n_u + A.cell_pn[(int64_t)cell * A.np + j]], pr);
+      // sigma = -p I + viscous (symmetric)
+#pragma unroll
+      for (int d1 = 0; d1 < DIM; ++d1)
+        {
+#pragma unroll
+          for (int d2 = 0; d2 < DIM; ++d2)
+            {
+              const double sv = d1 <= d2 ? visc[d1 * DIM + d2] : visc[d2 * DIM + d1];
+              A.rows[(int64_t)d1 * A.n_sdofs + (int64_t)DIM * node + d2] = sv - (d1 == d2 ? pr : 0.0);
+            }
+          A.fluid_velocity[(int64_t)DIM * node + d1] = v[d1];
+        }
+      A.fluid_pressure[node] = pr;
+    }
+
     template <int DIM>
     __global__ void query_kernel(SolidView S, int n, const double *__restrict__ pts, int *__restrict__ inside, const double *field,
                                  double *__restrict__ values, int *__restrict__ found)
@@ -571,7 +780,8 @@ namespace ifem
   // ===========================================================================
   FsiCoupling::FsiCoupling(Context &ctx_, InsIM &fluid_, HyperElasticity &solid_, const Parameters::AllParameters &params,
                            bool use_dirichlet_bc_)
-    : ctx(ctx_), fluid(fluid_), solid(solid_), parameters(params), use_dirichlet_bc(use_dirichlet_bc_)
+    : ctx(ctx_), fluid(fluid_), solid(solid_), parameters(params), use_dirichlet_bc(use_dirichlet_bc_),
+      time(params.end_time, params.time_step, params.output_interval, params.refinement_interval, params.save_interval)
   {
     if (!fluid.dofs_ready || !solid.dofs_ready) throw std::runtime_error("FSI: set up the fluid and solid solvers first");
     dim = fluid.fs.dim;
@@ -642,7 +852,194 @@ namespace ifem
     }
     d_inner_con.alloc(fs.n_dofs);
     d_inner_inhom.alloc(fs.n_dofs);
+    // vertices of the solid's boundary faces that are not fully fixed (mpi_fsi.cpp:690-703)
+    {
+      const Triangulation &st = solid.triangulation;
+      const unsigned fixed = (1u << dim) - 1;
+      std::vector<int> bv;
+      for (int f = 0; f < st.n_boundary_faces(); ++f)
+        {
+          auto bc = parameters.solid_dirichlet_bcs.find((unsigned)st.boundary_faces[3 * f + 2]);
+          if (bc != parameters.solid_dirichlet_bcs.end() && bc->second == fixed) continue;
+          const int cell = st.boundary_faces[3 * f], face = st.boundary_faces[3 * f + 1];
+          for (int a : face_local_nodes(dim, 1, face)) bv.push_back(ss.nt.cell_nodes[(size_t)cell * ss.npc + a]);
+        }
+      std::sort(bv.begin(), bv.end());
+      bv.erase(std::unique(bv.begin(), bv.end()), bv.end());
+      n_solid_bvert = (int)bv.size();
+      if (n_solid_bvert) d_solid_bvert.upload(bv, s);
+    }
+    build_fluid_bins();
     IFEM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  void FsiCoupling::build_fluid_bins()
+  {
+    const FluidSpace &fs = fluid.fs;
+    const Triangulation &ft = fluid.triangulation;
+    const int nv = fs.nv;
+    // bounding box and per-cell boxes of the local fluid cells
+    for (int d = 0; d < 3; ++d)
+      {
+        fluid_box[2 * d] = 1e300;
+        fluid_box[2 * d + 1] = -1e300;
+      }
+    std::vector<double> lo((size_t)fs.n_cells * dim), hi((size_t)fs.n_cells * dim);
+    for (int c = 0; c < fs.n_cells; ++c)
+      for (int d = 0; d < dim; ++d)
+        {
+          double a = 1e300, b = -1e300;
+          for (int v = 0; v < nv; ++v)
+            {
+              const double x = ft.vertices[(size_t)ft.cells[(size_t)fs.local_cells[c] * nv + v] * dim + d];
+              a = std::min(a, x);
+              b = std::max(b, x);
+            }
+          lo[(size_t)c * dim + d] = a;
+          hi[(size_t)c * dim + d] = b;
+          fluid_box[2 * d] = std::min(fluid_box[2 * d], a);
+          fluid_box[2 * d + 1] = std::max(fluid_box[2 * d + 1], b);
+        }
+    double vol = 1.0, ext[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d)
+      {
+        ext[d] = std::max(fluid_box[2 * d + 1] - fluid_box[2 * d], 1e-300);
+        vol *= ext[d];
+      }
+    const double h = std::pow(vol / std::max(1, fs.n_cells), 1.0 / dim);
+    int64_t total = 1;
+    for (int d = 0; d < 3; ++d)
+      {
+        fbin[d] = d < dim ? std::max(1, std::min(512, (int)std::floor(ext[d] / h))) : 1;
+        total *= fbin[d];
+      }
+    auto range = [&](int c, int d, int &k0, int &k1) {
+      const double pad = 1e-9 * std::max(ext[d], 1.0);
+      k0 = (int)std::floor((lo[(size_t)c * dim + d] - pad - fluid_box[2 * d]) / ext[d] * fbin[d]);
+      k1 = (int)std::floor((hi[(size_t)c * dim + d] + pad - fluid_box[2 * d]) / ext[d] * fbin[d]);
+      k0 = std::min(std::max(k0, 0), fbin[d] - 1);
+      k1 = std::min(std::max(k1, 0), fbin[d] - 1);
+    };
+    std::vector<int> start((size_t)total + 1, 0);
+    for (int pass = 0; pass < 2; ++pass)
+      {
+        std::vector<int> cursor;
+        std::vector<int> items;
+        if (pass == 1)
+          {
+            for (int64_t b = 0; b < total; ++b) start[b + 1] += start[b];
+            cursor.assign(start.begin(), start.end() - 1);
+            items.resize(start[total]);
+          }
+        for (int c = 0; c < fs.n_cells; ++c)
+          {
+            int k0[3] = {0, 0, 0}, k1[3] = {0, 0, 0};
+            for (int d = 0; d < dim; ++d) range(c, d, k0[d], k1[d]);
+            for (int k = k0[2]; k <= k1[2]; ++k)
+              for (int j = k0[1]; j <= k1[1]; ++j)
+                for (int i = k0[0]; i <= k1[0]; ++i)
+                  {
+                    const int64_t b = i + (int64_t)fbin[0] * (j + (int64_t)fbin[1] * k);
+                    if (pass == 0) start[b + 1]++;
+                    else items[cursor[b]++] = c;
+                  }
+          }
+        if (pass == 1)
+          {
+            d_fbin_start.upload(start, ctx.stream);
+            d_fbin_items.upload(items, ctx.stream);
+          }
+      }
+    d_fluid_box.upload(std::vector<double>(fluid_box, fluid_box + 6), ctx.stream);
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void FsiCoupling::find_solid_bc()
+  {
+    ScopedTimer t(ctx, timer_ms["Find solid BC"]);
+    refresh_deformed(); // must use the updated solid coordinates (:669-670)
+    const FluidSpace &fs = fluid.fs;
+    SolidSpace &ss = solid.ss;
+    cudaStream_t s = ctx.stream;
+    solid.fsi_stress_rows.zero(s);
+    solid.fluid_velocity.zero(s);
+    solid.fluid_pressure.zero(s);
+    if (n_solid_bvert)
+      {
+        FluidView F{};
+        F.cell_x = fs.d_cell_x.p;
+        F.cell_owned = d_cell_owned.p;
+        F.box = d_fluid_box.p;
+        for (int d = 0; d < 3; ++d) F.nbin[d] = fbin[d];
+        F.bin_start = d_fbin_start.p;
+        F.bin_items = d_fbin_items.p;
+        SolidBcArgs A{};
+        A.n_bvert = n_solid_bvert;
+        A.bvert = d_solid_bvert.p;
+        A.x = d_x.p;
+        A.pu = fs.pu;
+        A.pp = fs.pp;
+        A.nu = fs.nu;
+        A.np = fs.np;
+        A.cell_un = fs.d_cell_un.p;
+        A.cell_pn = fs.d_cell_pn.p;
+        A.n_u = fs.n_u;
+        A.n_unodes = fs.un.n_nodes;
+        A.present = fluid.present_solution.p;
+        auto *scns = dynamic_cast<SCnsIM *>(&fluid);
+        A.fluid_stress = scns ? scns->stress.p : nullptr; // update_stress() output; InsIM keeps none
+        A.n_sdofs = ss.n_dofs;
+        A.rows = solid.fsi_stress_rows.p;
+        A.fluid_velocity = solid.fluid_velocity.p;
+        A.fluid_pressure = solid.fluid_pressure.p;
+        const int blocks = (n_solid_bvert + 127) / 128;
+        if (dim == 2) solid_bc_kernel<2><<<blocks, 128, 0, s>>>(F, A);
+        else solid_bc_kernel<3><<<blocks, 128, 0, s>>>(F, A);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+    if (fs.n_ranks > 1)
+      {
+        // Utilities::MPI::sum of the replicated solid vectors (:849-865)
+        comm_allreduce_sum(*ctx.comm, solid.fsi_stress_rows.p, (int)solid.fsi_stress_rows.n, s);
+        comm_allreduce_sum(*ctx.comm, solid.fluid_velocity.p, (int)solid.fluid_velocity.n, s);
+        comm_allreduce_sum(*ctx.comm, solid.fluid_pressure.p, (int)solid.fluid_pressure.n, s);
+      }
+  }
+
+  // one pass of the while loop of FSI::run (mpi_fsi.cpp:1172-1214)
+  void FsiCoupling::run_one_step(bool first_step)
+  {
+    find_solid_bc();
+    {
+      ScopedTimer t(ctx, timer_ms["Run solid solver"]);
+      solid.run_one_step(first_step);
+    }
+    update_solid_box();
+    update_indicator();
+    fluid.make_constraints();
+    if (!first_step)
+      {
+        // nonzero_constraints.copy_from(zero_constraints) (:1193-1198): the increments are homogeneous from now on
+        std::fill(fluid.fs.nonzero_val.begin(), fluid.fs.nonzero_val.end(), 0.0);
+        fluid.upload_constraints();
+      }
+    find_fluid_bc();
+    {
+      ScopedTimer t(ctx, timer_ms["Run fluid solver"]);
+      fluid.run_one_step(true);
+    }
+    time.increment();
+  }
+
+  void FsiCoupling::run()
+  {
+    bool first_step = true;
+    while (time.end() - time.current() > 1e-12)
+      {
+        run_one_step(first_step);
+        first_step = false;
+      }
   }
 
   void FsiCoupling::refresh_deformed()

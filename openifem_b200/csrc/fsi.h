@@ -27,6 +27,14 @@ namespace ifem
     // fluid.fsi_acceleration (and, with use_dirichlet_bc, the inner constraints merged into the fluid's)
     void find_fluid_bc();
 
+    // find_solid_bc (source/mpi_fsi.cpp:666-867): fluid stress (-p I + viscous), velocity and pressure interpolated
+    // at the vertices of the solid's non-fixed boundary faces -> solid.fsi_stress_rows / fluid_velocity / fluid_pressure
+    void find_solid_bc();
+    // one coupled time step / the time loop of FSI::run (source/mpi_fsi.cpp:1172-1226), without refinement / checkpoints
+    void run_one_step(bool first_step);
+    void run();
+    Time time;
+
     // batch queries on the current deformed solid (tests / diagnostics)
     void point_in_solid(int n, const double *pts_host, int *inside_host);
     // which: 0 current_velocity, 1 current_acceleration, 2 current_displacement
@@ -59,6 +67,14 @@ namespace ifem
     DevBuf<unsigned char> d_node_interior; // 1 for cell-centre nodes of the Q2 element
     DevBuf<double> d_un_coords;            // support point of every local velocity node
     DevBuf<double> d_sp_tables;            // dN_u at the unit support points [nu][nu][dim] | dN_geo [nu][nv][dim]
+    // uniform-grid bins of the (static) fluid cells, for locating solid vertices in the fluid mesh
+    void build_fluid_bins();
+    int fbin[3] = {1, 1, 1};
+    double fluid_box[6] = {0, 0, 0, 0, 0, 0};
+    DevBuf<double> d_fluid_box;
+    DevBuf<int> d_fbin_start, d_fbin_items;
+    DevBuf<int> d_solid_bvert; // vertices (solid nodes) of the non-fixed boundary faces, unique
+    int n_solid_bvert = 0;
     bool deformed_valid = false;
   };
 } // namespace ifem

@@ -28,6 +28,7 @@ namespace ifem
     IFEM_CUDA(cudaMallocHost(&h_results, 64 * sizeof(double)));
     if (const char *v = std::getenv("IFEM_SPMV_VARIANT")) spmv_variant = std::atoi(v);
     if (const char *v = std::getenv("IFEM_SPMV_RPW")) spmv_rpw = std::atoi(v);
+    if (const char *v = std::getenv("IFEM_SPMV_L2HINT")) spmv_l2hint = std::atoi(v);
   }
 
   Context::~Context()
@@ -97,12 +98,29 @@ namespace ifem
   // ---------------------------------------------------------------------------
   __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
 
+  // L2 residency hints: the matrix is read exactly once per product (evict_first), the x window of a sweep is
+  // re-read by the next rows / planes (evict_last), so that the 40-80 GB matrix stream does not push x out of L2
+  __device__ __forceinline__ uint64_t l2_policy_evict_last()
+  {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+  }
+  __device__ __forceinline__ double ld_x_hint(const double *p, uint64_t pol)
+  {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+  }
+
   // one block row per lane group
-  template <int R, int C, int TPR, typename VT, int UNROLL = 2, int MINB = 1>
+  template <int R, int C, int TPR, typename VT, int UNROLL = 2, int MINB = 1, bool HINT = false>
   __global__ void __launch_bounds__(256, MINB)
   bcsr_spmv_row_kernel(int n_brows, const int64_t *__restrict__ rowptr, const int *__restrict__ col,
                        const VT *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, int accumulate)
   {
+    uint64_t pol = 0;
+    if (HINT) pol = l2_policy_evict_last();
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = gt / TPR;
     const int lane = (int)(gt % TPR);
@@ -121,7 +139,7 @@ namespace ifem
             const int c0 = ld_stream(ci + j);
             double xv[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) xv[c] = __ldg(x + (int64_t)c0 * C + c);
+            for (int c = 0; c < C; ++c) xv[c] = HINT ? ld_x_hint(x + (int64_t)c0 * C + c, pol) : __ldg(x + (int64_t)c0 * C + c);
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -216,7 +234,10 @@ namespace ifem
       const int rpw = std::max(1, ctx.spmv_rpw);                                                                                \
       const int64_t per_cta = (int64_t)(threads / T) * rpw;                                                                     \
       const int64_t nblk = (n_rows + per_cta - 1) / per_cta;                                                                    \
-      if (rpw == 1)                                                                                                             \
+      if (rpw == 1 && ctx.spmv_l2hint && U == 1 && M == 4)                                                                      \
+        bcsr_spmv_row_kernel<R, C, T, VT, 1, 4, true><<<(unsigned)nblk, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, \
+                                                                                                  x, y, accumulate ? 1 : 0);   \
+      else if (rpw == 1)                                                                                                        \
         bcsr_spmv_row_kernel<R, C, T, VT, U, M><<<(unsigned)nblk, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, \
                                                                                             y, accumulate ? 1 : 0);             \
       else                                                                                                                      \
@@ -338,7 +359,9 @@ namespace ifem
     if (variant == 0 && (key == 33 || key == 22))
       {
         const int64_t nblk = ((int64_t)n_rows * 16 + 255) / 256;
-        if (key == 33)
+        if (key == 33 && ctx.spmv_l2hint)
+          bcsr_spmv_row_kernel<3, 3, 16, float, 1, 4, true><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
+        else if (key == 33)
           bcsr_spmv_row_kernel<3, 3, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
         else
           bcsr_spmv_row_kernel<2, 2, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);

@@ -279,8 +279,11 @@ namespace ifem
     __global__ void solid_neumann_kernel(int n_faces, int nqf, const int *__restrict__ faces, const double *__restrict__ vals,
                                          int is_pressure, const double *__restrict__ ftab, const int *__restrict__ cell_nodes,
                                          const double *__restrict__ node_x, const unsigned char *__restrict__ con,
-                                         double *__restrict__ rhs)
+                                         double *__restrict__ rhs, const double *__restrict__ fsi_rows, const double *__restrict__ disp,
+                                         int64_t n_dofs)
     {
+      // fsi_rows != null: FSI traction sigma_f n on the DEFORMED face (mpi_shared_hyper_elasticity.cpp:495-554),
+      // sigma_f(q) interpolated from the vertex values MPI::FSI::find_solid_bc wrote into fsi_stress_rows
       constexpr int NV = 1 << DIM;
       const int f = blockIdx.x;
       if (f >= n_faces) return;
@@ -298,9 +301,13 @@ namespace ifem
               // vertices of a Q1 cell are its nodes (degree 1): geometry from the node coordinates
               for (int v = 0; v < NV; ++v)
                 {
-                  const double *X = node_x + (int64_t)cell_nodes[(int64_t)cell * NPC + v] * DIM;
+                  const int64_t vn = cell_nodes[(int64_t)cell * NPC + v];
+                  const double *X = node_x + vn * DIM;
                   for (int ii = 0; ii < DIM; ++ii)
-                    for (int jj = 0; jj < DIM; ++jj) J[ii * DIM + jj] = fma(X[ii], Gf[(fq * NV + v) * DIM + jj], J[ii * DIM + jj]);
+                    {
+                      const double xv = X[ii] + (fsi_rows ? disp[vn * DIM + ii] : 0.0);
+                      for (int jj = 0; jj < DIM; ++jj) J[ii * DIM + jj] = fma(xv, Gf[(fq * NV + v) * DIM + jj], J[ii * DIM + jj]);
+                    }
                 }
               double nds[DIM], det;
               if (DIM == 2)
@@ -324,7 +331,20 @@ namespace ifem
               double dS = 0.0;
               for (int k = 0; k < DIM; ++k) dS += nds[k] * nds[k];
               dS = sqrt(dS);
-              const double tr = is_pressure ? nds[c] / dS * vals[f * DIM] : vals[f * DIM + c];
+              double tr;
+              if (fsi_rows)
+                {
+                  tr = 0.0;
+                  for (int d2 = 0; d2 < DIM; ++d2)
+                    {
+                      double sg = 0.0; // sigma[c][d2] at q
+                      for (int b = 0; b < NPC; ++b)
+                        sg = fma(Nf[fq * NPC + b], fsi_rows[(int64_t)c * n_dofs + (int64_t)DIM * cell_nodes[(int64_t)cell * NPC + b] + d2], sg);
+                      tr = fma(sg, nds[d2] / dS, tr);
+                    }
+                }
+              else
+                tr = is_pressure ? nds[c] / dS * vals[f * DIM] : vals[f * DIM + c];
               r = fma(Nf[fq * NPC + a] * tr, dS * qwf[q], r);
             }
           const int64_t g = (int64_t)DIM * cell_nodes[(int64_t)cell * NPC + a] + c;
@@ -490,7 +510,17 @@ namespace ifem
     std::vector<int> nf;
     std::vector<double> nfv;
     neumann_is_pressure = prm.solid_neumann_bc_type == "Pressure";
-    if (prm.simulation_type != "FSI")
+    if (prm.simulation_type == "FSI")
+      {
+        // every boundary face carries the fluid traction (rows of constrained dofs are dropped in the scatter)
+        for (int f = 0; f < tria.n_boundary_faces(); ++f)
+          {
+            nf.push_back(tria.boundary_faces[3 * f]);
+            nf.push_back(tria.boundary_faces[3 * f + 1]);
+            for (int c = 0; c < dim; ++c) nfv.push_back(0.0);
+          }
+      }
+    else
       for (int f = 0; f < tria.n_boundary_faces(); ++f)
         {
           const unsigned id = (unsigned)tria.boundary_faces[3 * f + 2];
@@ -581,6 +611,12 @@ namespace ifem
     strain.alloc((size_t)ss.dim * ss.dim * ss.nt.n_nodes);
     stress.zero(ctx.stream);
     strain.zero(ctx.stream);
+    fsi_stress_rows.alloc((size_t)ss.dim * ss.n_dofs);
+    fluid_velocity.alloc(ss.n_dofs);
+    fluid_pressure.alloc(ss.nt.n_nodes);
+    fsi_stress_rows.zero(ctx.stream);
+    fluid_velocity.zero(ctx.stream);
+    fluid_pressure.zero(ctx.stream);
     d_count.alloc(ss.nt.n_nodes);
     {
       // qpt_to_dof = M^-1 Q^T W on the reference cell (FETools::compute_projection_from_quadrature_points_matrix)
@@ -706,12 +742,16 @@ namespace ifem
       }
     if (ss.n_nfaces)
       {
+        const bool fsi = parameters.simulation_type == "FSI";
+        const double *rows = fsi ? fsi_stress_rows.p : nullptr, *disp = fsi ? current_displacement.p : nullptr;
         if (ss.dim == 2)
           solid_neumann_kernel<2, 4><<<ss.n_nfaces, 32, 0, s>>>(ss.n_nfaces, ss.nqf, ss.d_nface.p, ss.d_nface_val.p, ss.neumann_is_pressure,
-                                                                ss.d_face_tables.p, ss.d_cell_nodes.p, ss.d_node_x.p, ss.d_con.p, ss.rhs.p);
+                                                                ss.d_face_tables.p, ss.d_cell_nodes.p, ss.d_node_x.p, ss.d_con.p, ss.rhs.p,
+                                                                rows, disp, ss.n_dofs);
         else
           solid_neumann_kernel<3, 8><<<ss.n_nfaces, 32, 0, s>>>(ss.n_nfaces, ss.nqf, ss.d_nface.p, ss.d_nface_val.p, ss.neumann_is_pressure,
-                                                                ss.d_face_tables.p, ss.d_cell_nodes.p, ss.d_node_x.p, ss.d_con.p, ss.rhs.p);
+                                                                ss.d_face_tables.p, ss.d_cell_nodes.p, ss.d_node_x.p, ss.d_con.p, ss.rhs.p,
+                                                                rows, disp, ss.n_dofs);
         IFEM_KERNEL_CHECK();
         ctx.kernel_launches++;
       }
@@ -762,7 +802,9 @@ namespace ifem
       scale(ctx, n, 1.0 / (beta * dt * dt), current_acceleration.p);
       lin3(ctx, n, current_velocity.p, previous_velocity.p, dt * (1 - gamma), previous_acceleration.p, dt * gamma, current_acceleration.p);
     };
-    while (nerr_upd > parameters.tol_d || nerr_res > parameters.tol_f)
+    // the replicated twin MPI::FSI uses also stops on a vanishing update (mpi_shared_hyper_elasticity.cpp:125-127)
+    const bool shared_twin = parameters.simulation_type == "FSI";
+    while ((nerr_upd > parameters.tol_d || nerr_res > parameters.tol_f) && (!shared_twin || err_upd > 1e-12))
       {
         if (it >= parameters.solid_max_iterations) throw std::runtime_error("Too many Newton iterations!");
         kinematics();
@@ -788,6 +830,7 @@ namespace ifem
     copy(ctx, n, current_acceleration.p, previous_acceleration.p);
     copy(ctx, n, current_velocity.p, previous_velocity.p);
     copy(ctx, n, current_displacement.p, previous_displacement.p);
+    update_strain_and_stress(); // the shared twin used by MPI::FSI does this every step (mpi_shared_hyper_elasticity.cpp:204-205)
   }
 
   void HyperElasticity::run()

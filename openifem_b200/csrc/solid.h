@@ -71,6 +71,11 @@ namespace ifem
     Time time;
     bool verbose = false, dofs_ready = false;
     DevBuf<double> stress, strain; // [dim*dim][n_nodes] nodal Cauchy stress / deformation gradient
+    // what MPI::FSI writes into the solid (include/mpi_shared_solid_solver.h: fsi_stress_rows, fluid_velocity,
+    // fluid_pressure; used by mpi_fsi.cpp:793-806 and the FSI traction term mpi_shared_hyper_elasticity.cpp:495-554)
+    DevBuf<double> fsi_stress_rows; // [dim][n_dofs]: row d1 of the fluid stress at every vertex
+    DevBuf<double> fluid_velocity;  // [n_dofs]
+    DevBuf<double> fluid_pressure;  // [n_nodes]
     DevBuf<double> current_displacement, current_velocity, current_acceleration, previous_displacement, previous_velocity,
       previous_acceleration;
     struct Record

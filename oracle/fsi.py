@@ -267,3 +267,85 @@ def find_fluid_bc(fluid, solid: SolidGeometry, indicator, solid_velocity, solid_
                     con[g] = 1
                     inhom[g] = vs[comp] - present[g]
     return fsi_acc, con, inhom
+
+
+# ----------------------------------------------------------------------------------------------------------
+# find_solid_bc (mpi_fsi.cpp:666-867) and the coupled time loop (mpi_fsi.cpp:1172-1214)
+# ----------------------------------------------------------------------------------------------------------
+def locate_in_fluid(fluid_mesh: fem.BoxMesh, p):
+    """lowest-index fluid cell containing p (GridInterpolator on the fluid DoFHandler) and unit coordinates"""
+    for c in range(fluid_mesh.n_cells):
+        ok, xi = point_in_cell(fluid_mesh.vertices[fluid_mesh.cells[c]], p)
+        if ok:
+            return c, np.clip(xi, 0.0, 1.0)
+    return None, None
+
+
+def find_solid_bc(fluid, solid_mesh: fem.BoxMesh, displacement, solid_dirichlet_bcs, fluid_stress=None):
+    """fluid: oracle fluid solver (dofs, feu, fep, present). Returns fsi_stress_rows [dim][n_sdofs],
+    fluid_velocity [n_sdofs], fluid_pressure [n_snodes]."""
+    dim = fluid.dim
+    d = fluid.dofs
+    x = deformed(solid_mesh.vertices, displacement, dim)
+    n_sn = solid_mesh.vertices.shape[0]
+    rows = np.zeros((dim, n_sn * dim))
+    fvel = np.zeros(n_sn * dim)
+    fpre = np.zeros(n_sn)
+    fixed = (1 << dim) - 1
+    done = set()
+    for (cell, face, fid) in solid_mesh.boundary_faces:
+        if solid_dirichlet_bcs.get(int(fid)) == fixed:
+            continue
+        for a in fem.face_local_nodes(dim, 1, int(face)):
+            node = int(solid_mesh.cells[cell, a])
+            if node in done:
+                continue
+            done.add(node)
+            c, xi = locate_in_fluid(fluid.mesh, x[node])
+            if c is None:
+                continue
+            Nu = fluid.feu.eval(xi[None, :])[0][0]
+            Np = fluid.fep.eval(xi[None, :])[0][0]
+            U = fluid.present[: fluid.n_u].reshape(-1, dim)[d.unodes[c]]
+            v = Nu @ U
+            pr = float(Np @ fluid.present[fluid.n_u + d.pnodes[c]])
+            visc = np.zeros((dim, dim))
+            if fluid_stress is not None:
+                for i in range(dim):
+                    for j in range(i, dim):
+                        visc[i, j] = visc[j, i] = float(Nu @ fluid_stress[i * dim + j, d.unodes[c]])
+            sigma = -pr * np.eye(dim) + visc
+            for d1 in range(dim):
+                rows[d1, dim * node: dim * node + dim] = sigma[d1]
+            fvel[dim * node: dim * node + dim] = v
+            fpre[node] = pr
+    return rows, fvel, fpre
+
+
+class FSI:
+    """MPI::FSI<dim>::run loop with an oracle fluid (oracle.scns.SCnsIM) and solid (oracle.solid.HyperElasticity)."""
+
+    def __init__(self, fluid, solid, use_dirichlet_bc=False):
+        self.fluid, self.solid, self.use_dirichlet_bc = fluid, solid, use_dirichlet_bc
+        self.base_con, self.base_val = fluid.con.copy(), fluid.nonzero_val.copy()
+
+    def run_one_step(self, first_step):
+        f, s = self.fluid, self.solid
+        dim = f.dim
+        s.fsi_stress_rows, s.fluid_velocity, s.fluid_pressure = find_solid_bc(
+            f, s.mesh, s.cur_u, s.prm.solid_dirichlet_bcs, getattr(f, "stress", None))
+        s.run_one_step(first_step)
+        geo = SolidGeometry(s.mesh, s.cur_u)
+        f.indicator[:] = update_indicator(f.mesh, geo)
+        # make_constraints(); after the first step the nonzero constraints become the zero ones
+        f.con = self.base_con.copy()
+        f.nonzero_val = self.base_val.copy() if first_step else np.zeros_like(self.base_val)
+        if hasattr(f, "fsi_stress"):
+            find_fluid_bc_stress(f, geo, f.indicator, s.stress, f.fsi_stress)
+        acc, icon, iinh = find_fluid_bc(f, geo, f.indicator, s.cur_v, s.cur_a, f.dt, self.use_dirichlet_bc)
+        f.fsi_acceleration[:] = acc
+        if self.use_dirichlet_bc:
+            new = (icon != 0) & (f.con == 0)
+            f.con[new] = 1
+            f.nonzero_val[new] = iinh[new]
+        f.run_one_step(True)

@@ -112,6 +112,9 @@ class HyperElasticity:
         self.cur_u, self.cur_v, self.cur_a = z(), z(), z()
         self.prev_u, self.prev_v, self.prev_a = z(), z(), z()
         self.history = []
+        self.fsi_stress_rows = np.zeros((dim, self.n))
+        self.fluid_velocity = np.zeros(self.n)
+        self.fluid_pressure = np.zeros(self.dofs.n_nodes)
         self.update_qph(self.cur_u)
 
     # -- update_qph (:241-275) ------------------------------------------------
@@ -168,6 +171,23 @@ class HyperElasticity:
             K += np.einsum("cab,ij->caibj", geo, I).reshape(nc, n, n)
         # Neumann faces (:445-505)
         p = self.prm
+        if p.simulation_type == "FSI":
+            # FSI traction sigma_f n on the deformed face (mpi_shared_hyper_elasticity.cpp:495-554)
+            rows = self.fsi_stress_rows.reshape(dim, -1, dim)  # [d1][node][d2]
+            xdef = self.mesh.vertices + self.cur_u.reshape(-1, dim)
+            for (cell, face, fid) in self.mesh.boundary_faces:
+                axis, side = face // 2, face % 2
+                cn = self.mesh.cells[cell]
+                X = xdef[cn]
+                for q in range(self.fw.size):
+                    J = np.einsum("vi,vj->ij", X, self.face_dG[face][q])
+                    nds = np.linalg.det(J) * np.linalg.inv(J)[axis, :] * (1.0 if side else -1.0)
+                    dS = np.linalg.norm(nds)
+                    sigma = np.einsum("b,ibj->ij", self.face_N[face][q], rows[:, self.dofs.nodes[cell], :])
+                    traction = sigma @ (nds / dS)
+                    for a in range(npc):
+                        for c in range(dim):
+                            rhs[cell, a * dim + c] += self.face_N[face][q, a] * traction[c] * dS * self.fw[q]
         if p.simulation_type != "FSI" and p.solid_neumann_bcs:
             for (cell, face, fid) in self.mesh.boundary_faces:
                 if fid in p.solid_dirichlet_bcs or fid not in p.solid_neumann_bcs:
@@ -240,7 +260,9 @@ class HyperElasticity:
         nerr_u = nerr_f = 1.0
         err_u0 = err_f0 = 1.0
         it = 0
-        while nerr_u > p.tol_d or nerr_f > p.tol_f:
+        shared_twin = p.simulation_type == "FSI"  # mpi_shared_hyper_elasticity.cpp:125-127
+        err_u = 1.0
+        while (nerr_u > p.tol_d or nerr_f > p.tol_f) and (not shared_twin or err_u > 1e-12):
             if it >= p.solid_max_iterations:
                 raise RuntimeError("Too many Newton iterations!")
             self.cur_a = (self.cur_u - pred) / (beta * dt * dt)
@@ -265,6 +287,7 @@ class HyperElasticity:
         self.cur_a = (self.cur_u - pred) / (beta * dt * dt)
         self.cur_v = self.prev_v + dt * (1 - gamma) * self.prev_a + dt * gamma * self.cur_a
         self.prev_a, self.prev_v, self.prev_u = self.cur_a.copy(), self.cur_v.copy(), self.cur_u.copy()
+        self.update_strain_and_stress()
 
     def run(self):
         self.run_one_step(True)

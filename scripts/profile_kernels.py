@@ -18,6 +18,7 @@ flow.setup()
 flow.assemble(True)
 if what == "spmv":
     print("uu", flow.bench_spmv_uu(3))
+    print("uu fp32", flow.bench_spmv_uu_fp32(3))
     print("block", flow.bench_vmult(2))
 else:
     print("assemble", flow.bench_assemble(2))

@@ -19,7 +19,7 @@ flow.bench_spmv_uu(3); ms, b = flow.bench_spmv_uu(20)
 flow.bench_spmv_uu_fp32(3); ms32, b32 = flow.bench_spmv_uu_fp32(20)
 print(f"f64 {ms:.3f} ms {b/ms/1e6:.0f} GB/s | f32 {ms32:.3f} ms {b32/ms32/1e6:.0f} GB/s")
 '''
-for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["1", "8", "1", "8"]):
-    env = dict(os.environ, IFEM_SPMV32_VARIANT="83", IFEM_SPMV_RPW=v)
+for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "1", "0", "1"]):
+    env = dict(os.environ, IFEM_SPMV_L2HINT=v)
     r = subprocess.run([sys.executable, "-c", code, n], env=env, capture_output=True, text=True)
     print("variant", v, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:], flush=True)

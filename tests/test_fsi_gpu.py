@@ -183,3 +183,98 @@ def test_find_fluid_bc_stress_part_scnsim(golden_dir, dim, f_reps, s_reps, s_lo,
     f.dim, f.dofs, f.feu, f.n, f.n_u, f.mesh, f.present = dim, o_fluid.dofs, o_fluid.feu, o_fluid.n, o_fluid.n_u, o_fluid.mesh, o_fluid.present
     ref_acc, _, _ = fsi.find_fluid_bc(f, geo, ind, vel, acc, o_fluid.dt)
     assert _rel(got_acc, ref_acc) < 1e-10
+
+
+# ---- find_solid_bc and the coupled loop ("next" after the named kernels) ---------------------
+FSI_SOLID_PRM = """
+subsection Solid finite element system
+  set Degree = 1
+end
+subsection Solid solver control
+  set Damping = 0.0
+  set Max Newton iterations = 10
+  set Displacement tolerance  = 1.0e-8
+  set Force tolerance  = 1.0e-8
+end
+subsection Solid Dirichlet BCs
+  set Number of Dirichlet BCs = 1
+  set Dirichlet boundary id = 2
+  set Dirichlet boundary components = {fixed}
+end
+"""
+
+
+def _fsi_text(dim, sim_type="FSI", dt=1e-3):
+    from test_scns_gpu import scns_prm
+
+    t = scns_prm(dim, dt=dt).replace("set Simulation type = Fluid", f"set Simulation type = {sim_type}")
+    return t + FSI_SOLID_PRM.format(fixed=3 if dim == 2 else 7)
+
+
+def _fsi_pair(dim, f_reps, s_reps, s_lo, s_hi, use_dirichlet=False):
+    import openifem_b200 as ifem
+    from oracle import fem, fsi, prm, scns, solid
+
+    text = _fsi_text(dim)
+    lo, hi = (0.0,) * dim, (1.0,) * dim
+    P = prm.Params(text, is_text=True)
+    o_fluid = scns.SCnsIM(fem.BoxMesh(f_reps, lo, hi), P)
+    o_solid = solid.HyperElasticity(fem.BoxMesh(s_reps, s_lo, s_hi), P)
+    ftria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(ftria, f_reps, lo, hi, True)
+    params = ifem.Parameters.AllParameters(text=text)
+    fluid = ifem.Fluid.MPI.SCnsIM(ftria, params)
+    fluid.setup()
+    stria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(stria, s_reps, s_lo, s_hi, True)
+    sol = ifem.Solid.MPI.HyperElasticity(stria, params)
+    sol.setup()
+    coupling = ifem.MPI.FSI(fluid, sol, params, use_dirichlet)
+    return o_fluid, o_solid, fluid, sol, coupling
+
+
+@pytest.mark.parametrize("dim,f_reps,s_reps,s_lo,s_hi,disp", [
+    (2, (12, 12), (4, 6), (0.3, 0.0), (0.55, 0.7), SHEAR2),
+    (3, (6, 6, 6), (3, 3, 4), (0.25, 0.0, 0.25), (0.7, 0.6, 0.75), BEND3),
+])
+def test_find_solid_bc_matches_oracle(dim, f_reps, s_reps, s_lo, s_hi, disp):
+    from oracle import fsi
+
+    o_fluid, o_solid, fluid, sol, coupling = _fsi_pair(dim, f_reps, s_reps, s_lo, s_hi)
+    rng = np.random.default_rng(31)
+    present = rng.uniform(-1, 1, o_fluid.n)
+    d = 0.3 * disp(o_solid.mesh.vertices).ravel()
+    o_fluid.present[:] = present
+    o_fluid.update_stress()
+    fluid.set_vector(fluid.PRESENT, present)
+    fluid.update_stress()
+    sol.set_vector(sol.CUR_U, d)
+    rows, vel, pres = coupling.find_solid_bc()
+    r_ref, v_ref, p_ref = fsi.find_solid_bc(o_fluid, o_solid.mesh, d, o_solid.prm.solid_dirichlet_bcs, o_fluid.stress)
+    assert np.count_nonzero(r_ref) > 0
+    assert _rel(rows, r_ref) < 1e-11
+    assert _rel(vel, v_ref) < 1e-11
+    assert _rel(pres, p_ref) < 1e-11
+
+
+@pytest.mark.parametrize("use_dirichlet", [False, True])
+@pytest.mark.parametrize("dim,f_reps,s_reps,s_lo,s_hi", [
+    (2, (12, 12), (4, 6), (0.3125, 0.0), (0.5625, 0.6875)),
+])
+def test_coupled_fsi_steps_match_oracle(dim, f_reps, s_reps, s_lo, s_hi, use_dirichlet):
+    """two passes of the FSI::run loop (find_solid_bc -> solid step -> box / indicator -> constraints -> find_fluid_bc
+    -> fluid step) against the oracle's loop"""
+    from oracle import fsi
+
+    o_fluid, o_solid, fluid, sol, coupling = _fsi_pair(dim, f_reps, s_reps, s_lo, s_hi, use_dirichlet)
+    fluid.set_control(fgmres_rel=1e-10)
+    loop = fsi.FSI(o_fluid, o_solid, use_dirichlet)
+    for k in range(2):
+        loop.run_one_step(k == 0)
+        coupling.run_one_step(k == 0)
+    us = sol.get_current_solution()
+    assert np.abs(o_solid.cur_u).max() > 0
+    assert _rel(us, o_solid.cur_u) < 1e-6
+    fsol = fluid.get_current_solution()
+    assert _rel(fsol[: o_fluid.n_u], o_fluid.velocity()) < 1e-6
+    assert _rel(fsol[o_fluid.n_u:], o_fluid.pressure()) < 1e-6

@@ -306,6 +306,16 @@ class _InsIM:
         check(lib().ifem_insim_time(self._h, C.byref(ts), C.byref(cur)))
         return ts.value, cur.value
 
+    def update_stress(self):
+        """FluidSolver::update_stress: nodal viscous stress from present_solution"""
+        check(lib().ifem_scnsim_update_stress(self._h))
+
+    def get_stress(self):
+        dim = self.tria.dim
+        out = np.empty((dim * dim, self.partition(0)[1]))
+        check(lib().ifem_scnsim_get_field(self._h, C.c_int(0), dptr(out)))
+        return out
+
     # -- measurement hooks ---------------------------------------------------
     def bench_vmult(self, reps):
         ms, b = C.c_double(), C.c_double()
@@ -359,9 +369,6 @@ class _SCnsIM(_InsIM):
 
     def set_initial_condition(self, f):
         check(lib().ifem_scnsim_set_initial_condition(self._h, self._wrap(f), None))
-
-    def update_stress(self):
-        check(lib().ifem_scnsim_update_stress(self._h))
 
     def _field_shape(self, which):
         dim = self.tria.dim

@@ -830,23 +830,23 @@ int ifem_scnsim_set_initial_condition(ifem_insim *s, ifem_field_fn f, void *user
 int ifem_scnsim_update_stress(ifem_insim *s)
 {
   return guard([&] {
-    as_scns(s).update_stress();
+    s->s->update_stress();
     IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
   });
 }
 int ifem_scnsim_get_field(ifem_insim *s, int which, double *host)
 {
   return guard([&] {
-    SCnsIM &m = as_scns(s);
-    DevBuf<double> &v = which == 0 ? m.stress : m.fsi_stress;
+    InsIM &m = *s->s;
+    DevBuf<double> &v = which == 0 ? m.stress : as_scns(s).fsi_stress;
     v.download(host, v.n, m.ctx.stream);
   });
 }
 int ifem_scnsim_set_field(ifem_insim *s, int which, const double *host)
 {
   return guard([&] {
-    SCnsIM &m = as_scns(s);
-    DevBuf<double> &v = which == 0 ? m.stress : m.fsi_stress;
+    InsIM &m = *s->s;
+    DevBuf<double> &v = which == 0 ? m.stress : as_scns(s).fsi_stress;
     v.upload(host, v.n, m.ctx.stream);
     IFEM_CUDA(cudaStreamSynchronize(m.ctx.stream));
   });

@@ -100,6 +100,7 @@ namespace ifem
     vs_p = VecSpace(n_owned_pnodes, 0, 0, n_p);
     halo_u.init(ctx, part.u, dim);
     halo_p.init(ctx, part.p, 1);
+    halo_s.init(ctx, part.u, 1); // scalar fields on the velocity nodes (nodal stress)
 
     // patterns: rows = owned nodes (they come first in the local numbering), columns = local nodes
     auto owned_rows = [](Pattern P, int n_owned) {
@@ -180,6 +181,43 @@ namespace ifem
     P_schur = product_pattern(P_pu, P_up, pn.n_nodes);
     S_m.init(P_schur, 1, 1, s);
     schur_valid = false;
+
+    // qpt_to_dof = M^-1 Q^T W on the reference cell (FETools::compute_projection_from_quadrature_points_matrix,
+    // mpi_fluid_solver.cpp:740-743) for the scalar FE_Q(pu) space
+    {
+      const int n = nu;
+      std::vector<double> M((size_t)n * n, 0.0), R((size_t)n * nq, 0.0);
+      for (int q = 0; q < nq; ++q)
+        for (int i = 0; i < n; ++i)
+          {
+            R[(size_t)i * nq + q] = tab_u.N[(size_t)q * n + i] * quad.weights[q];
+            for (int j = 0; j < n; ++j) M[(size_t)i * n + j] += tab_u.N[(size_t)q * n + i] * tab_u.N[(size_t)q * n + j] * quad.weights[q];
+          }
+      for (int c = 0; c < n; ++c) // Gauss-Jordan on [M | R]
+        {
+          int piv = c;
+          for (int r2 = c + 1; r2 < n; ++r2)
+            if (std::fabs(M[(size_t)r2 * n + c]) > std::fabs(M[(size_t)piv * n + c])) piv = r2;
+          if (piv != c)
+            {
+              for (int k = 0; k < n; ++k) std::swap(M[(size_t)c * n + k], M[(size_t)piv * n + k]);
+              for (int k = 0; k < nq; ++k) std::swap(R[(size_t)c * nq + k], R[(size_t)piv * nq + k]);
+            }
+          const double d = 1.0 / M[(size_t)c * n + c];
+          for (int k = 0; k < n; ++k) M[(size_t)c * n + k] *= d;
+          for (int k = 0; k < nq; ++k) R[(size_t)c * nq + k] *= d;
+          for (int r2 = 0; r2 < n; ++r2)
+            {
+              if (r2 == c) continue;
+              const double f = M[(size_t)r2 * n + c];
+              if (f == 0.0) continue;
+              for (int k = 0; k < n; ++k) M[(size_t)r2 * n + k] -= f * M[(size_t)c * n + k];
+              for (int k = 0; k < nq; ++k) R[(size_t)r2 * nq + k] -= f * R[(size_t)c * nq + k];
+            }
+        }
+      d_qpt_to_dof.upload(R, s);
+      d_stress_count.alloc(un.n_nodes);
+    }
 
     con.assign(n_dofs, 0);
     nonzero_val.assign(n_dofs, 0.0);
@@ -908,6 +946,119 @@ namespace ifem
       ins_assemble_dim<2>(ctx, fs, prm, eval_pt, present, fsi_acc, use_nonzero_constraints, assemble_mass, schur_pass);
     else
       ins_assemble_dim<3>(ctx, fs, prm, eval_pt, present, fsi_acc, use_nonzero_constraints, assemble_mass, schur_pass);
+  }
+
+  // ===========================================================================
+  // update_stress: one thread per (cell, node a): tau = 2 mu sym grad v at the quadrature points, projected to node a
+  // with qpt_to_dof, scatter-added (cells of one colour per launch share no node), then divided by the cell count.
+  // ===========================================================================
+  namespace
+  {
+    template <int DIM, int NU>
+    __global__ void stress_kernel(int n_list, const int *__restrict__ cell_list, const int *__restrict__ cell_un,
+                                  const double *__restrict__ cell_x, const double *__restrict__ tdN, const double *__restrict__ tdG,
+                                  const double *__restrict__ qpt_to_dof, const double *__restrict__ present, double mu, int n_unodes,
+                                  int n_owned_u, double *__restrict__ stress, double *__restrict__ count)
+    {
+      constexpr int NQ = NU, NV = 1 << DIM;
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t >= n_list * NU) return;
+      const int cell = cell_list[t / NU], a = t % NU;
+      const int un_a = cell_un[(int64_t)cell * NU + a];
+      if (un_a >= n_owned_u) return;
+      const double *X = cell_x + (int64_t)cell * NV * DIM;
+      double acc[DIM * DIM];
+#pragma unroll
+      for (int i = 0; i < DIM * DIM; ++i) acc[i] = 0.0;
+      for (int q = 0; q < NQ; ++q)
+        {
+          double J[DIM * DIM], Ji[DIM * DIM], G[DIM * DIM];
+#pragma unroll
+          for (int i = 0; i < DIM * DIM; ++i) J[i] = G[i] = 0.0;
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+              for (int j = 0; j < DIM; ++j) J[i * DIM + j] = fma(X[v * DIM + i], tdG[(q * NV + v) * DIM + j], J[i * DIM + j]);
+          double det;
+          invert<DIM>(J, Ji, det);
+          for (int b = 0; b < NU; ++b)
+            {
+              const int un = cell_un[(int64_t)cell * NU + b];
+              double g[DIM];
+#pragma unroll
+              for (int k = 0; k < DIM; ++k)
+                {
+                  double sacc = 0.0;
+#pragma unroll
+                  for (int j = 0; j < DIM; ++j) sacc = fma(tdN[(q * NU + b) * DIM + j], Ji[j * DIM + k], sacc);
+                  g[k] = sacc;
+                }
+#pragma unroll
+              for (int c = 0; c < DIM; ++c)
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) G[c * DIM + k] = fma(present[(int64_t)DIM * un + c], g[k], G[c * DIM + k]);
+            }
+          const double w = qpt_to_dof[a * NQ + q];
+#pragma unroll
+          for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) acc[i * DIM + j] = fma(w, mu * (G[i * DIM + j] + G[j * DIM + i]), acc[i * DIM + j]);
+        }
+#pragma unroll
+      for (int ij = 0; ij < DIM * DIM; ++ij) stress[(int64_t)ij * n_unodes + un_a] += acc[ij];
+      count[un_a] += 1.0;
+    }
+
+    __global__ void stress_average_kernel(int n, int ncomp, int n_unodes, const double *__restrict__ count, double *__restrict__ stress)
+    {
+      const int i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n) return;
+      const double c = count[i];
+      if (c > 0)
+        for (int k = 0; k < ncomp; ++k) stress[(int64_t)k * n_unodes + i] /= c;
+    }
+  } // namespace
+
+  void update_nodal_stress(Context &ctx, FluidSpace &fs, const double *present, double viscosity, double *stress)
+  {
+    cudaStream_t s = ctx.stream;
+    const int dim = fs.dim, nn = fs.un.n_nodes;
+    IFEM_CUDA(cudaMemsetAsync(stress, 0, (size_t)dim * dim * nn * sizeof(double), s));
+    fs.d_stress_count.zero(s);
+    const double *tdN = fs.d_tables.p + (size_t)fs.nq * fs.nu;
+    const double *tdG = tdN + (size_t)fs.nq * fs.nu * dim + (size_t)fs.nq * fs.np;
+    const int n_colours = (int)fs.colour_offsets.size() - 1;
+    for (int k = 0; k < n_colours; ++k)
+      {
+        const int n = fs.colour_n1[k]; // every cell around an owned node is a layer-1 cell
+        if (!n) continue;
+        const int *list = fs.d_colour_order.p + fs.colour_offsets[k];
+        auto go = [&](auto dim_tag, auto nu_tag) {
+          constexpr int DIM = decltype(dim_tag)::value, NU = decltype(nu_tag)::value;
+          const int total = n * NU;
+          stress_kernel<DIM, NU><<<(total + 127) / 128, 128, 0, s>>>(n, list, fs.d_cell_un.p, fs.d_cell_x.p, tdN, tdG, fs.d_qpt_to_dof.p, present,
+                                                                     viscosity, nn, fs.n_owned_unodes, stress, fs.d_stress_count.p);
+        };
+        using I2 = std::integral_constant<int, 2>;
+        using I3 = std::integral_constant<int, 3>;
+        if (dim == 2 && fs.nu == 9) go(I2(), std::integral_constant<int, 9>());
+        else if (dim == 2 && fs.nu == 4) go(I2(), std::integral_constant<int, 4>());
+        else if (dim == 3 && fs.nu == 27) go(I3(), std::integral_constant<int, 27>());
+        else if (dim == 3 && fs.nu == 8) go(I3(), std::integral_constant<int, 8>());
+        else throw std::runtime_error("update_nodal_stress: unsupported element");
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+    stress_average_kernel<<<(nn + 255) / 256, 256, 0, s>>>(nn, dim * dim, nn, fs.d_stress_count.p, stress);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+    if (fs.n_ranks > 1)
+      {
+        // relevant_partition_stress = stress (ghosted copy, mpi_scnsim.cpp:36-45): scalar halo on the velocity node set
+        Halo &h = fs.halo_s;
+        for (int k = 0; k < dim * dim; ++k) h.update(ctx, stress + (size_t)k * nn);
+      }
   }
 
   void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y)

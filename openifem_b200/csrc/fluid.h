@@ -38,7 +38,7 @@ namespace ifem
     int n_layer1_unodes = 0, n_layer1_pnodes = 0; // owned + layer-1 ghosts
     std::vector<int> colour_n1;                   // per colour: number of layer-1 cells (they come first)
     bool schur_valid = false;                     // S_m matches the current constraints (B and diag(M_u) do not depend on the solution)
-    Halo halo_u, halo_p;
+    Halo halo_u, halo_p, halo_s;
     VecSpace vs_all, vs_u, vs_p;          // owned entries of a block / velocity / pressure vector
     // refresh ghost entries of a block vector [u | p]
     void halo_update(Context &ctx, double *x) { halo_u.update(ctx, x); halo_p.update(ctx, x + n_u); }
@@ -73,6 +73,8 @@ namespace ifem
     int n_nfaces = 0, nqf = 0;
 
     Bcsr A_uu, A_up, A_pu, A_pp, M_p, S_m;
+    DevBuf<double> d_qpt_to_dof;  // [nu][nq] projection from quadrature points to the dofs of scalar FE_Q(pu)
+    DevBuf<double> d_stress_count; // [n_velocity_nodes] cells around every node (update_stress)
     DevBuf<double> diag_Mu; // [n_u]
     DevBuf<double> rhs;     // [n_dofs]
 
@@ -103,6 +105,10 @@ namespace ifem
   // pressure Neumann faces: rhs_i -= phi_i . n  p  JxW_face on unconstrained owned rows (mpi_insim.cpp:313-341,
   // mpi_scnsim.cpp:516-546)
   void neumann_faces(Context &ctx, FluidSpace &fs);
+
+  // FluidSolver::update_stress (source/mpi_fluid_solver.cpp:716-811) into stress [dim*dim][n_velocity_nodes]; ghost
+  // entries are refreshed by halo exchange
+  void update_nodal_stress(Context &ctx, FluidSpace &fs, const double *present, double viscosity, double *stress);
 
   // y = A x on the 2x2 block system (BlockSparseMatrix::vmult)
   void block_vmult(Context &ctx, const FluidSpace &fs, const double *x, double *y);

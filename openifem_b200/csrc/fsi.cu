@@ -986,8 +986,7 @@ namespace ifem
         A.n_u = fs.n_u;
         A.n_unodes = fs.un.n_nodes;
         A.present = fluid.present_solution.p;
-        auto *scns = dynamic_cast<SCnsIM *>(&fluid);
-        A.fluid_stress = scns ? scns->stress.p : nullptr; // update_stress() output; InsIM keeps none
+        A.fluid_stress = fluid.stress.p; // update_stress() output of the last fluid step
         A.n_sdofs = ss.n_dofs;
         A.rows = solid.fsi_stress_rows.p;
         A.fluid_velocity = solid.fluid_velocity.p;

@@ -91,6 +91,8 @@ namespace ifem
         v->zero(ctx.stream);
       }
     d_binv.alloc((size_t)fs.n_owned_unodes * fs.dim * fs.dim);
+    stress.alloc((size_t)fs.dim * fs.dim * fs.un.n_nodes);
+    stress.zero(ctx.stream);
     d_tmp_p.alloc(fs.n_p);
     d_utmp.alloc(fs.n_u);
     if (fs.n_ranks > 1) d_utmp2.alloc(fs.n_u);
@@ -251,6 +253,14 @@ namespace ifem
     // solution_increment = present - evaluation_point ; present = evaluation_point
     lin3(ctx, n, solution_increment.p, present_solution.p, -1.0, evaluation_point.p, 0.0, evaluation_point.p);
     copy(ctx, n, evaluation_point.p, present_solution.p);
+    update_stress(); // mpi_insim.cpp:475
+  }
+
+  void InsIM::update_stress()
+  {
+    ScopedTimer t(ctx, timer_ms["Update stress"]);
+    if (fs.n_ranks > 1) fs.halo_update(ctx, present_solution.p);
+    update_nodal_stress(ctx, fs, present_solution.p, parameters.viscosity, stress.p);
   }
 
   void InsIM::run()

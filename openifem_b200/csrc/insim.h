@@ -96,6 +96,10 @@ namespace ifem
     virtual void initialize_system();
     virtual void assemble(bool use_nonzero_constraints);
     virtual std::pair<unsigned int, double> solve(bool use_nonzero_constraints);
+    // FluidSolver::update_stress (source/mpi_fluid_solver.cpp:716-811): nodal viscous stress 2 mu sym grad v from
+    // present_solution, quadrature values projected to the dofs of FE_Q(pu) and averaged over the cells
+    void update_stress();
+    DevBuf<double> stress; // [dim*dim][n_velocity_nodes]
 
     Context &ctx;
     Triangulation &triangulation;

@@ -362,78 +362,6 @@ namespace ifem
         }
     }
 
-    // FluidSolver::update_stress (mpi_fluid_solver.cpp:753-810): 2 mu sym grad v at q -> qpt_to_dof -> scatter-add +
-    // count; one thread per cell, cells of one colour per launch; division by the count afterwards.
-    template <int DIM>
-    __global__ void stress_kernel(int n_list, const int *__restrict__ cell_list, const int *__restrict__ cell_un,
-                                  const double *__restrict__ cell_x, const double *__restrict__ tables,
-                                  const double *__restrict__ qpt_to_dof, const double *__restrict__ present, double mu, int n_unodes,
-                                  int n_owned_u, double *__restrict__ stress, double *__restrict__ count)
-    {
-      constexpr int NU = 1 << DIM, NQ = NU, NV = NU;
-      const int li = blockIdx.x * blockDim.x + threadIdx.x;
-      if (li >= n_list) return;
-      const int cell = cell_list[li];
-      const double *tdN = tables + NQ * NU, *tdG = tdN + NQ * NU * DIM + NQ * NU;
-      const double *X = cell_x + (int64_t)cell * NV * DIM;
-      double tau[NQ][DIM * DIM];
-      for (int q = 0; q < NQ; ++q)
-        {
-          double J[DIM * DIM], Ji[DIM * DIM], det, G[DIM * DIM];
-#pragma unroll
-          for (int i = 0; i < DIM * DIM; ++i) J[i] = G[i] = 0.0;
-          for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int i = 0; i < DIM; ++i)
-#pragma unroll
-              for (int j = 0; j < DIM; ++j) J[i * DIM + j] = fma(X[v * DIM + i], tdG[(q * NV + v) * DIM + j], J[i * DIM + j]);
-          invert<DIM>(J, Ji, det);
-          for (int b = 0; b < NU; ++b)
-            {
-              const int un = cell_un[(int64_t)cell * NU + b];
-              double g[DIM];
-#pragma unroll
-              for (int k = 0; k < DIM; ++k)
-                {
-                  double s = 0.0;
-#pragma unroll
-                  for (int j = 0; j < DIM; ++j) s = fma(tdN[(q * NU + b) * DIM + j], Ji[j * DIM + k], s);
-                  g[k] = s;
-                }
-#pragma unroll
-              for (int c = 0; c < DIM; ++c)
-#pragma unroll
-                for (int k = 0; k < DIM; ++k) G[c * DIM + k] = fma(present[(int64_t)DIM * un + c], g[k], G[c * DIM + k]);
-            }
-#pragma unroll
-          for (int i = 0; i < DIM; ++i)
-#pragma unroll
-            for (int j = 0; j < DIM; ++j) tau[q][i * DIM + j] = mu * (G[i * DIM + j] + G[j * DIM + i]);
-        }
-      for (int a = 0; a < NU; ++a)
-        {
-          const int un = cell_un[(int64_t)cell * NU + a];
-          if (un >= n_owned_u) continue;
-#pragma unroll
-          for (int ij = 0; ij < DIM * DIM; ++ij)
-            {
-              double s = 0.0;
-              for (int q = 0; q < NQ; ++q) s = fma(qpt_to_dof[a * NQ + q], tau[q][ij], s);
-              stress[(int64_t)ij * n_unodes + un] += s;
-            }
-          count[un] += 1.0;
-        }
-    }
-
-    __global__ void stress_average_kernel(int n, int ncomp, int n_unodes, const double *__restrict__ count, double *__restrict__ stress)
-    {
-      const int i = blockIdx.x * blockDim.x + threadIdx.x;
-      if (i >= n) return;
-      const double c = count[i];
-      if (c > 0)
-        for (int k = 0; k < ncomp; ++k) stress[(int64_t)k * n_unodes + i] /= c;
-    }
-
     // rowsum(|A_vv|)^-1 per velocity dof (mpi_supg_solver.cpp:68-118)
     template <int DIM>
     __global__ void abs_rowsum_inv_kernel(int n_brows, const int64_t *__restrict__ rp, const double *__restrict__ val, double *__restrict__ out)
@@ -521,52 +449,14 @@ namespace ifem
     InsIM::initialize_system();
     const int dim = fs.dim, nsym = dim * (dim + 1) / 2;
     cudaStream_t s = ctx.stream;
-    stress.alloc((size_t)dim * dim * fs.un.n_nodes);
-    stress.zero(s);
     fsi_stress.alloc((size_t)nsym * fs.un.n_nodes);
     fsi_stress.zero(s);
-    d_count.alloc(fs.un.n_nodes);
     d_rowsum_inv.alloc(fs.n_u);
     d_b2pp_diag_inv.alloc(fs.n_p);
     d_pt1.alloc(fs.n_p);
     d_pt2.alloc(fs.n_p);
     d_ut1.alloc(fs.n_u);
     d_ut2.alloc(fs.n_u);
-    // qpt_to_dof = M^-1 Q^T W on the reference cell (FETools::compute_projection_from_quadrature_points_matrix)
-    {
-      const int n = fs.nu, nq = fs.nq;
-      std::vector<double> M((size_t)n * n, 0.0), R((size_t)n * nq, 0.0);
-      for (int q = 0; q < nq; ++q)
-        for (int i = 0; i < n; ++i)
-          {
-            R[(size_t)i * nq + q] = fs.tab_u.N[(size_t)q * n + i] * fs.quad.weights[q];
-            for (int j = 0; j < n; ++j) M[(size_t)i * n + j] += fs.tab_u.N[(size_t)q * n + i] * fs.tab_u.N[(size_t)q * n + j] * fs.quad.weights[q];
-          }
-      // Gauss-Jordan on [M | R]
-      for (int c = 0; c < n; ++c)
-        {
-          int piv = c;
-          for (int r2 = c + 1; r2 < n; ++r2)
-            if (std::fabs(M[(size_t)r2 * n + c]) > std::fabs(M[(size_t)piv * n + c])) piv = r2;
-          if (piv != c)
-            {
-              for (int k = 0; k < n; ++k) std::swap(M[(size_t)c * n + k], M[(size_t)piv * n + k]);
-              for (int k = 0; k < nq; ++k) std::swap(R[(size_t)c * nq + k], R[(size_t)piv * nq + k]);
-            }
-          const double d = 1.0 / M[(size_t)c * n + c];
-          for (int k = 0; k < n; ++k) M[(size_t)c * n + k] *= d;
-          for (int k = 0; k < nq; ++k) R[(size_t)c * nq + k] *= d;
-          for (int r2 = 0; r2 < n; ++r2)
-            {
-              if (r2 == c) continue;
-              const double f = M[(size_t)r2 * n + c];
-              if (f == 0.0) continue;
-              for (int k = 0; k < n; ++k) M[(size_t)r2 * n + k] -= f * M[(size_t)c * n + k];
-              for (int k = 0; k < nq; ++k) R[(size_t)r2 * nq + k] -= f * R[(size_t)c * nq + k];
-            }
-        }
-      d_qpt_to_dof.upload(R, s);
-    }
     // user fields at the quadrature points of the local cells (Q1 map)
     if (sigma_pml_field || body_force)
       {
@@ -667,43 +557,6 @@ namespace ifem
         ctx.kernel_launches++;
       }
     neumann_faces(ctx, fs); // same pressure face term as InsIM (:516-546)
-  }
-
-  void SCnsIM::update_stress()
-  {
-    ScopedTimer t(ctx, timer_ms["Update stress"]);
-    cudaStream_t s = ctx.stream;
-    const int dim = fs.dim;
-    if (fs.n_ranks > 1) fs.halo_update(ctx, present_solution.p);
-    stress.zero(s);
-    d_count.zero(s);
-    // every cell around an owned node is local, so owned entries are complete without communication
-    const int n_colours = (int)fs.colour_offsets.size() - 1;
-    for (int k = 0; k < n_colours; ++k)
-      {
-        const int n = fs.colour_offsets[k + 1] - fs.colour_offsets[k];
-        if (!n) continue;
-        const int *list = fs.d_colour_order.p + fs.colour_offsets[k];
-        if (dim == 2)
-          stress_kernel<2><<<(n + 127) / 128, 128, 0, s>>>(n, list, fs.d_cell_un.p, fs.d_cell_x.p, fs.d_tables.p, d_qpt_to_dof.p,
-                                                           present_solution.p, parameters.viscosity, fs.un.n_nodes, fs.n_owned_unodes,
-                                                           stress.p, d_count.p);
-        else
-          stress_kernel<3><<<(n + 127) / 128, 128, 0, s>>>(n, list, fs.d_cell_un.p, fs.d_cell_x.p, fs.d_tables.p, d_qpt_to_dof.p,
-                                                           present_solution.p, parameters.viscosity, fs.un.n_nodes, fs.n_owned_unodes,
-                                                           stress.p, d_count.p);
-        IFEM_KERNEL_CHECK();
-        ctx.kernel_launches++;
-      }
-    stress_average_kernel<<<(fs.un.n_nodes + 255) / 256, 256, 0, s>>>(fs.un.n_nodes, dim * dim, fs.un.n_nodes, d_count.p, stress.p);
-    IFEM_KERNEL_CHECK();
-    ctx.kernel_launches++;
-    if (fs.n_ranks > 1)
-      {
-        // relevant_partition_stress = stress (ghosted copy, mpi_scnsim.cpp:36-45): one halo per component
-        // scalar halo on the Q1 node set (velocity and pressure nodes coincide for Q1/Q1)
-        for (int k = 0; k < dim * dim; ++k) fs.halo_p.update(ctx, stress.p + (size_t)k * fs.un.n_nodes);
-      }
   }
 
   // BlockIncompSchurPreconditioner::vmult (mpi_supg_solver.cpp:137-192). The two Hypre-Euclid ILU(0) factors

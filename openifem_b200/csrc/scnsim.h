@@ -25,10 +25,6 @@ namespace ifem
     void assemble(bool use_nonzero_constraints) override;
     std::pair<unsigned int, double> solve(bool use_nonzero_constraints) override;
     void run_one_step(bool apply_nonzero_constraints, bool assemble_system = true) override;
-    // FluidSolver::update_stress (source/mpi_fluid_solver.cpp:716-811)
-    void update_stress();
-
-    DevBuf<double> stress;     // [dim*dim][n_unodes] nodal viscous stress
     DevBuf<double> fsi_stress; // [dim(dim+1)/2][n_unodes]
     int tpp_its = 0;
 
@@ -36,7 +32,7 @@ namespace ifem
     void precondition_supg(const double *src, double *dst);
     std::function<double(const double *, unsigned int)> body_force, sigma_pml_field, initial_condition;
     DevBuf<double> d_sigma_pml, d_body_force; // [n_cells][nq], [n_cells][nq][dim] (empty when unset)
-    DevBuf<double> d_qpt_to_dof, d_count, d_rowsum_inv, d_b2pp_diag_inv, d_pt1, d_pt2, d_ut1, d_ut2;
+    DevBuf<double> d_rowsum_inv, d_b2pp_diag_inv, d_pt1, d_pt2, d_ut1, d_ut2;
     VecPool pool_tpp;
   };
 } // namespace ifem

@@ -191,3 +191,51 @@ def test_spmv_properties_at_scale():
     assert rel(lhs, rhs) < 1e-13
     A = g.get_matrix(0)
     assert rel(A @ x, g.vmult(x)) < 1e-13
+
+
+def test_config1_fluid_cavity_serial_twin(golden_dir):
+    """BASELINE config 1: tests/fluid_cavity (2-D lid-driven cavity, 32 x 32 cells Q2/Q1, serial Fluid::InsIM,
+    tests/fluid_cavity/fluid_cavity.cpp:28-34 with fluid_cavity.prm verbatim). The reference has no golden for it
+    (smoke test), so the device path with the serial twin's tolerances (insim.cpp:353-358) is compared with the
+    oracle in the same mode over the first 5 of the 300 steps."""
+    import os
+
+    import openifem_b200 as ifem
+    from oracle import fem, ins, prm
+
+    path = os.path.join(golden_dir, "ins_cavity_2d.prm")
+    p = prm.Params(path)
+    mesh = fem.BoxMesh((1, 1), (0, 0), (1, 1)).refine_global(p.global_refinements[0])
+    o = ins.InsIM(mesh, p, mode="serial")
+    tria = ifem.Triangulation(2)
+    ifem.GridGenerator.hyper_cube(tria, 0, 1, True)
+    tria.refine_global(p.global_refinements[0])
+    g = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(path))
+    g.setup()
+    assert g.n_dofs == 8450 + 1089
+    g.set_control(serial_twin=True, a_inv_rel=1e-10, a_inv_max_it=20000)
+    for k in range(5):
+        o.run_one_step(k == 0)
+        g.run_one_step(k == 0)
+    sol = g.get_current_solution()
+    assert rel(sol[: o.n_u], o.velocity()) < 1e-6
+    pg, po = sol[o.n_u:] - sol[o.n_u:].mean(), o.pressure() - o.pressure().mean()
+    assert rel(pg, po) < 1e-5
+    assert [(h["timestep"], h["iteration"]) for h in g.history()] == [(h[0], h[1]) for h in o.history]
+
+
+@pytest.mark.parametrize("dim,reps,hi", [(2, (5, 4), (1.0, 0.8)), (3, (3, 2, 3), (1.0, 1.2, 0.9))])
+def test_update_stress_q2_matches_oracle(dim, reps, hi):
+    """FluidSolver::update_stress (source/mpi_fluid_solver.cpp:716-811) on the Q2 velocity space of InsIM"""
+    from oracle import fem, prm, scns
+
+    text = cavity_prm(dim)
+    o = scns.SCnsIM(fem.BoxMesh(reps, (0,) * dim, hi), prm.Params(text, is_text=True))  # only its update_stress is used
+    g = make_gpu(text, reps, (0,) * dim, hi)
+    rng = np.random.default_rng(9)
+    pr = rng.uniform(-1, 1, o.n)
+    o.present[:] = pr
+    g.set_vector(g.PRESENT, pr)
+    ref = o.update_stress()
+    g.update_stress()
+    assert rel(g.get_stress(), ref) < 1e-12

@@ -138,3 +138,95 @@ def test_four_ranks_match_one_rank(tmp_path):
     assert rel(y4, y1) < 1e-13 and rel(rhs4, rhs1) < 1e-13
     nu = 3 * 9 * 9 * 25
     assert rel(sol4[:nu], sol1[:nu]) < 1e-6
+
+
+def _scns_worker(rank, size, idfile, dim, reps, steps, q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import time
+
+        import torch
+
+        torch.cuda.set_device(rank)
+        from test_scns_gpu import scns_prm
+
+        import openifem_b200 as ifem
+
+        ifem.init(rank)
+        if size > 1:
+            if rank == 0:
+                uid = ifem.comm_unique_id()
+                with open(idfile + ".tmp", "wb") as f:
+                    f.write(uid)
+                os.replace(idfile + ".tmp", idfile)
+            else:
+                while not os.path.exists(idfile):
+                    time.sleep(0.05)
+                uid = open(idfile, "rb").read()
+            ifem.comm_init(rank, size, uid)
+        tria = ifem.Triangulation(dim)
+        hi = (2.0,) + (1.0,) * (dim - 1)
+        ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, hi, True)
+        flow = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=scns_prm(dim, dt=1e-3)))
+        flow.set_body_force(lambda p, c: 5.0 if c == 0 else 0.0)
+        flow.setup()
+        flow.set_control(fgmres_rel=1e-10)
+        n_un_glob = int(np.prod([k + 1 for k in reps]))
+        loc, glo = flow.owned_global_dofs(n_un_glob)
+        for k in range(steps):
+            flow.run_one_step(k == 0)
+        sol = flow.get_current_solution()
+        ou = flow.partition(0)[0]
+        stress = flow.get_stress()[:, :ou]
+        gu = flow.local_to_global(0)[:ou]
+        hist = [(h["timestep"], h["iteration"], h["abs_res"]) for h in flow.history()]
+        q.put((rank, "ok", glo, sol[loc], gu, stress, hist))
+        if size > 1:
+            ifem.comm_finalize()
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, "fail", traceback.format_exc(), None, None, None, None))
+
+
+def _run_scns(size, dim, reps, steps, tmp_path):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    idfile = str(tmp_path / f"nccl_id_scns_{size}")
+    procs = [ctx.Process(target=_scns_worker, args=(r, size, idfile, dim, reps, steps, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert r[1] == "ok", f"rank {r[0]} failed:\n{r[2]}"
+    n = sum(len(r[2]) for r in res)
+    sol = np.zeros(n)
+    n_nodes = sum(len(r[4]) for r in res)
+    stress = np.zeros((dim * dim, n_nodes))
+    for r in res:
+        sol[r[2]] = r[3]
+        stress[:, r[4]] = r[5]
+    hist = [r for r in res if r[0] == 0][0][6]
+    return sol, stress, hist
+
+
+@pytest.mark.parametrize("dim,reps", [(3, (5, 4, 6)), (2, (10, 8))])
+def test_scnsim_two_ranks_match_one_rank(dim, reps, tmp_path):
+    """the slightly compressible solver (assembly with nodal-stress gradients, update_stress, SUPG preconditioner) on
+    two ranks against one rank"""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    sol1, st1, h1 = _run_scns(1, dim, reps, 3, tmp_path)
+    sol2, st2, h2 = _run_scns(2, dim, reps, 3, tmp_path)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert len(h1) == len(h2)
+    for a, b in zip(h2, h1):
+        assert a[:2] == b[:2]
+        assert abs(a[2] - b[2]) <= 1e-6 * max(b[2], 1e-9)
+    assert rel(sol2, sol1) < 1e-6
+    assert rel(st2, st1) < 1e-6

@@ -332,6 +332,16 @@ class _InsIM:
         check(lib().ifem_insim_bench_spmv_uu_fp32(self._h, C.c_int(reps), C.byref(ms), C.byref(b)))
         return ms.value, b.value
 
+    def set_inner_variant(self, variant):
+        check(lib().ifem_insim_set_inner_variant(self._h, C.c_int(variant)))
+
+    def bench_spmv_uu_sell(self, reps, variant=0, check_error=True):
+        """(ms, algorithmic bytes, padding ratio, max rel. error vs the fp64 product) of the fp32 SELL-32 product kernel"""
+        ms, b, pad, err = C.c_double(), C.c_double(), C.c_double(), C.c_double(-1.0)
+        check(lib().ifem_insim_bench_spmv_uu_sell(self._h, C.c_int(variant), C.c_int(reps), C.byref(ms), C.byref(b), C.byref(pad),
+                                                  C.byref(err) if check_error else None))
+        return ms.value, b.value, pad.value, err.value
+
     def bench_steps(self, n_steps, first_applies_nonzero_constraints=False):
         ms = C.c_double()
         check(lib().ifem_insim_bench_steps(self._h, C.c_int(n_steps), C.c_int(1 if first_applies_nonzero_constraints else 0), C.byref(ms)))

@@ -329,7 +329,7 @@ int ifem_insim_default_control(int serial_twin, ifem_ins_control *out)
     out->a_inv_rel = c.a_inv_rel;
     out->a_inv_max_it = c.a_inv_max_it;
     out->basis_size = c.basis_size;
-    out->a_inv_fp32 = c.a_inv_fp32 ? 1 : 0;
+    out->a_inv_fp32 = c.a_inv_fp32;
   });
 }
 int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
@@ -344,7 +344,7 @@ int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
     k.a_inv_rel = c->a_inv_rel;
     k.a_inv_max_it = c->a_inv_max_it;
     k.basis_size = c->basis_size;
-    k.a_inv_fp32 = c->a_inv_fp32 != 0;
+    k.a_inv_fp32 = c->a_inv_fp32;
   });
 }
 int ifem_insim_set_verbose(ifem_insim *s, int verbose)
@@ -579,6 +579,41 @@ int ifem_insim_bench_spmv_uu_fp32(ifem_insim *s, int reps, double *ms, double *b
     // algorithmic bytes of the fp32 stream (unpadded): 4 B per value instead of 8
     *bytes = m.fs.A_uu.spmv_bytes() - 4.0 * m.fs.A_uu.nnz();
   });
+}
+int ifem_insim_bench_spmv_uu_sell(ifem_insim *s, int variant, int reps, double *ms, double *bytes, double *padding, double *max_rel_err)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    if (!m.inner32.S.built()) m.inner32.setup(m.ctx, m.fs.A_uu, m.fs.un, m.fs.n_ranks > 1 ? &m.fs.halo_u : nullptr);
+    m.inner32.refresh(m.ctx, m.fs.A_uu, nullptr);
+    const int keep = m.inner32.variant;
+    if (variant > 0) m.inner32.variant = variant;
+    m.inner32.probe_load(m.ctx, m.fs.rhs.p);
+    for (int i = 0; i < 2; ++i) m.inner32.probe_apply(m.ctx);
+    *ms = time_reps(m.ctx, reps, [&] { m.inner32.probe_apply(m.ctx); });
+    m.inner32.variant = keep;
+    *bytes = m.inner32.S.spmv_bytes();
+    if (padding) *padding = m.inner32.S.padding();
+    if (max_rel_err)
+      {
+        // against the fp64 product on the BCSR matrix (owned rows)
+        DevBuf<double> y32(m.fs.n_u), y64(m.fs.n_u);
+        m.inner32.probe_store(m.ctx, y32.p);
+        m.fs.halo_u.update(m.ctx, m.fs.rhs.p);
+        spmv(m.ctx, m.fs.A_uu, m.fs.rhs.p, y64.p);
+        const std::vector<double> a = y32.to_host(m.ctx.stream), b = y64.to_host(m.ctx.stream);
+        const size_t n_owned = (size_t)m.fs.n_owned_unodes * m.fs.dim;
+        double scale = 0.0, err = 0.0;
+        for (size_t i = 0; i < n_owned; ++i) scale = std::max(scale, std::fabs(b[i]));
+        for (size_t i = 0; i < n_owned; ++i) err = std::max(err, std::fabs(a[i] - b[i]));
+        *max_rel_err = scale > 0.0 ? err / scale : err;
+      }
+  });
+}
+int ifem_insim_set_inner_variant(ifem_insim *s, int variant)
+{
+  s->s->inner32.variant = variant;
+  return IFEM_OK;
 }
 int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms)
 {

@@ -32,7 +32,7 @@ namespace ifem
       int (*GroupEnd)() = nullptr;
       const char *(*GetErrorString)(int) = nullptr;
     };
-    constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+    constexpr int kNcclFloat64 = 8, kNcclFloat32 = 7, kNcclSum = 0;
 
     NcclApi &api()
     {
@@ -102,6 +102,11 @@ namespace ifem
   {
     if (n_send) check(api().Send(send, (size_t)n_send, kNcclFloat64, peer, c.nccl, s), "ncclSend");
     if (n_recv) check(api().Recv(recv, (size_t)n_recv, kNcclFloat64, peer, c.nccl, s), "ncclRecv");
+  }
+  void comm_sendrecv_f32(Comm &c, int peer, const float *send, int64_t n_send, float *recv, int64_t n_recv, cudaStream_t s)
+  {
+    if (n_send) check(api().Send(send, (size_t)n_send, kNcclFloat32, peer, c.nccl, s), "ncclSend");
+    if (n_recv) check(api().Recv(recv, (size_t)n_recv, kNcclFloat32, peer, c.nccl, s), "ncclRecv");
   }
   void comm_group_start(Comm &) { check(api().GroupStart(), "ncclGroupStart"); }
   void comm_group_end(Comm &) { check(api().GroupEnd(), "ncclGroupEnd"); }

@@ -30,6 +30,7 @@ namespace ifem
   // exchange with at most two slab neighbours: send `send_lo`/`send_hi` counts from
   // packed device buffers, receive into ghost buffers
   void comm_sendrecv(Comm &c, int peer, const double *send, int64_t n_send, double *recv, int64_t n_recv, cudaStream_t s);
+  void comm_sendrecv_f32(Comm &c, int peer, const float *send, int64_t n_send, float *recv, int64_t n_recv, cudaStream_t s);
   void comm_group_start(Comm &c);
   void comm_group_end(Comm &c);
 } // namespace ifem

@@ -1,0 +1,772 @@
+#include "inner32.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <utility>
+
+#include "comm.h"
+
+namespace ifem
+{
+  namespace
+  {
+    constexpr int kT = 256;
+
+    // ---------------------------------------------------------------------------
+    // y = A32 x. One warp per slice, one lane per block row; per block slot a warp issues one coalesced load of
+    // 32 column indices, one 16-byte gather per lane and bs*bs coalesced 128-byte loads of matrix values. The
+    // matrix stream is read once (ld.global.cs: evict first), x stays in L1/L2.
+    // ---------------------------------------------------------------------------
+    template <int BS, int UNROLL>
+    __global__ void __launch_bounds__(kT)
+    sell_spmv_kernel(int n_slices, const int *__restrict__ slice_off, const int *__restrict__ col, const float *__restrict__ val,
+                     const float4 *__restrict__ x4, float *__restrict__ y)
+    {
+      const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+      const int lane = threadIdx.x & 31;
+      if (warp >= n_slices) return;
+      const int s0 = slice_off[warp];
+      const int L = slice_off[warp + 1] - s0;
+      const int *cp = col + (int64_t)s0 * 32 + lane;
+      const float *vp = val + (int64_t)s0 * (BS * BS * 32) + lane;
+      float acc[BS];
+#pragma unroll
+      for (int r = 0; r < BS; ++r) acc[r] = 0.0f;
+#pragma unroll UNROLL
+      for (int j = 0; j < L; ++j)
+        {
+          const int c = __ldcs(cp + j * 32);
+          float a[BS * BS];
+#pragma unroll
+          for (int k = 0; k < BS * BS; ++k) a[k] = __ldcs(vp + (j * BS * BS + k) * 32);
+          const float4 xv = __ldg(x4 + c);
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int r = 0; r < BS; ++r)
+#pragma unroll
+            for (int cc = 0; cc < BS; ++cc) acc[r] = fmaf(a[r * BS + cc], xs[cc], acc[r]);
+        }
+      float *yp = y + ((int64_t)warp * 32 + lane) * BS;
+#pragma unroll
+      for (int r = 0; r < BS; ++r) yp[r] = acc[r];
+    }
+
+    // Loads with a fixed issue order (volatile asm keeps its order): the compiler otherwise caps the kernel at 32
+    // registers and interleaves loads with the FFMA chain, which leaves too few bytes in flight per warp.
+    __device__ __forceinline__ float ld_cs_ordered(const float *p)
+    {
+      float v;
+      asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
+      return v;
+    }
+    __device__ __forceinline__ int ld_cs_ordered(const int *p)
+    {
+      int v;
+      asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
+      return v;
+    }
+    __device__ __forceinline__ float4 ld_nc_ordered(const float4 *p)
+    {
+      float4 v;
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+      return v;
+    }
+
+    // Software-pipelined form: NS block slots per step. All NS * bs*bs value loads of a step are issued first, then
+    // the column indices of the NEXT step (so the x gathers never wait for their index), then the NS gathers, then
+    // the FMAs: NS * (bs*bs + 1) + NS 128-byte lines in flight per warp.
+    // (col has 32 * NS ints of slack behind the last slice for the unconditional prefetch.)
+    template <int BS, int NS, int MINB>
+    __global__ void __launch_bounds__(kT, MINB)
+    sell_spmv_pipe_kernel(int n_slices, const int *__restrict__ slice_off, const int *__restrict__ col, const float *__restrict__ val,
+                          const float4 *__restrict__ x4, float *__restrict__ y)
+    {
+      constexpr int RC = BS * BS;
+      const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+      const int lane = threadIdx.x & 31;
+      if (warp >= n_slices) return;
+      const int s0 = slice_off[warp];
+      const int L = slice_off[warp + 1] - s0;
+      const int *cp = col + (int64_t)s0 * 32 + lane;
+      const float *vp = val + (int64_t)s0 * (RC * 32) + lane;
+      float acc[BS];
+#pragma unroll
+      for (int r = 0; r < BS; ++r) acc[r] = 0.0f;
+      int cn[NS];
+#pragma unroll
+      for (int u = 0; u < NS; ++u) cn[u] = ld_cs_ordered(cp + u * 32);
+      int j = 0;
+      for (; j + NS <= L; j += NS)
+        {
+          float a[NS][RC];
+#pragma unroll
+          for (int u = 0; u < NS; ++u)
+#pragma unroll
+            for (int k = 0; k < RC; ++k) a[u][k] = ld_cs_ordered(vp + (size_t)(u * RC + k) * 32);
+          vp += (size_t)NS * RC * 32;
+          int c[NS];
+#pragma unroll
+          for (int u = 0; u < NS; ++u) c[u] = cn[u];
+          cp += NS * 32;
+#pragma unroll
+          for (int u = 0; u < NS; ++u) cn[u] = ld_cs_ordered(cp + u * 32);
+          float4 xv[NS];
+#pragma unroll
+          for (int u = 0; u < NS; ++u) xv[u] = ld_nc_ordered(x4 + c[u]);
+#pragma unroll
+          for (int u = 0; u < NS; ++u)
+            {
+              const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+              for (int r = 0; r < BS; ++r)
+#pragma unroll
+                for (int cc = 0; cc < BS; ++cc) acc[r] = fmaf(a[u][r * BS + cc], xs[cc], acc[r]);
+            }
+        }
+      // tail: fewer than NS slots left, their column indices are already in cn[]
+#pragma unroll
+      for (int u = 0; u < NS - 1; ++u)
+        if (j + u < L)
+          {
+            float a[RC];
+#pragma unroll
+            for (int k = 0; k < RC; ++k) a[k] = ld_cs_ordered(vp + (size_t)(u * RC + k) * 32);
+            const float4 xq = ld_nc_ordered(x4 + cn[u]);
+            const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+            for (int r = 0; r < BS; ++r)
+#pragma unroll
+              for (int cc = 0; cc < BS; ++cc) acc[r] = fmaf(a[r * BS + cc], xs[cc], acc[r]);
+          }
+      float *yp = y + ((int64_t)warp * 32 + lane) * BS;
+#pragma unroll
+      for (int r = 0; r < BS; ++r) yp[r] = acc[r];
+    }
+
+    // ---------------------------------------------------------------------------
+    // building the copy
+    // ---------------------------------------------------------------------------
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    sell_fill_val_kernel(int n_slices, const int *__restrict__ slice_off, const int *__restrict__ perm_row,
+                         const int64_t *__restrict__ rowptr, const double *__restrict__ aval, float *__restrict__ val)
+    {
+      constexpr int RC = BS * BS;
+      const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+      const int lane = threadIdx.x & 31;
+      if (warp >= n_slices) return;
+      const int s0 = slice_off[warp];
+      const int L = slice_off[warp + 1] - s0;
+      const int row = perm_row[(int64_t)warp * 32 + lane];
+      int64_t base = 0;
+      int nb = 0;
+      if (row >= 0)
+        {
+          base = rowptr[row];
+          nb = (int)(rowptr[row + 1] - base);
+        }
+      const double *av = aval + base * RC;
+      float *vp = val + (int64_t)s0 * (RC * 32) + lane;
+      for (int k = 0; k < RC; ++k)
+        for (int j = 0; j < L; ++j) vp[(j * RC + k) * 32] = j < nb ? (float)av[(int64_t)k * nb + j] : 0.0f;
+    }
+
+    __global__ void __launch_bounds__(kT)
+    sell_fill_col_kernel(int n_slices, const int *__restrict__ slice_off, const int *__restrict__ perm_row,
+                         const int64_t *__restrict__ rowptr, const int *__restrict__ acol, const int *__restrict__ pos,
+                         int *__restrict__ col)
+    {
+      const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+      const int lane = threadIdx.x & 31;
+      if (warp >= n_slices) return;
+      const int s0 = slice_off[warp];
+      const int L = slice_off[warp + 1] - s0;
+      const int self = warp * 32 + lane;
+      const int row = perm_row[self];
+      int64_t base = 0;
+      int nb = 0;
+      if (row >= 0)
+        {
+          base = rowptr[row];
+          nb = (int)(rowptr[row + 1] - base);
+        }
+      int *cp = col + (int64_t)s0 * 32 + lane;
+      for (int j = 0; j < L; ++j) cp[j * 32] = j < nb ? pos[acol[base + j]] : self; // padding: value 0 times own x
+    }
+
+    // binv32[k][i] = binv[perm_row[i]][k]
+    __global__ void __launch_bounds__(kT)
+    binv_to_sell_kernel(int n_pad, int rc, const int *__restrict__ perm_row, const double *__restrict__ binv, float *__restrict__ out)
+    {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const int row = perm_row[i];
+          for (int k = 0; k < rc; ++k) out[(size_t)k * n_pad + i] = row >= 0 ? (float)binv[(size_t)row * rc + k] : 0.0f;
+        }
+    }
+
+    // ---------------------------------------------------------------------------
+    // vector kernels of the fp32 BiCGStab (one thread per node of the SELL numbering, grid-stride; reductions in
+    // fp64: block partials -> reduce_final_kernel -> all-reduce over the ranks)
+    // ---------------------------------------------------------------------------
+    template <int NR>
+    __device__ __forceinline__ void block_reduce_store(double (&v)[NR], double *__restrict__ partials)
+    {
+      __shared__ double sh[NR][kT / 32];
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+      for (int q = 0; q < NR; ++q)
+        {
+          const double s = warp_sum(v[q]);
+          if (l == 0) sh[q][w] = s;
+        }
+      __syncthreads();
+      if (w == 0)
+        {
+#pragma unroll
+          for (int q = 0; q < NR; ++q)
+            {
+              double s = l < kT / 32 ? sh[q][l] : 0.0;
+              s = warp_sum(s);
+              if (l == 0) partials[(size_t)blockIdx.x * NR + q] = s;
+            }
+        }
+    }
+
+    __global__ void __launch_bounds__(kT) reduce_final32_kernel(int n_blocks, int nr, const double *__restrict__ partials, double *__restrict__ out)
+    {
+      __shared__ double sh[kT / 32];
+      for (int q = 0; q < nr; ++q)
+        {
+          double s = 0.0;
+          for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) s += partials[(size_t)i * nr + q];
+          s = warp_sum(s);
+          const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+          __syncthreads();
+          if (l == 0) sh[w] = s;
+          __syncthreads();
+          if (w == 0)
+            {
+              double tsum = l < kT / 32 ? sh[l] : 0.0;
+              tsum = warp_sum(tsum);
+              if (l == 0) out[q] = tsum;
+            }
+        }
+    }
+
+    // r = r0 = src / |src| in SELL order; p = v = x = 0
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    init_kernel(int n_pad, const int *__restrict__ perm_row, const double *__restrict__ src, double scale, float *__restrict__ r,
+                float *__restrict__ r0, float *__restrict__ p, float *__restrict__ v, float *__restrict__ x, double *__restrict__ partials)
+    {
+      double acc[1] = {0.0};
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const int row = perm_row[i];
+#pragma unroll
+          for (int c = 0; c < BS; ++c)
+            {
+              const float a = row >= 0 ? (float)(src[(size_t)row * BS + c] * scale) : 0.0f;
+              const size_t k = (size_t)i * BS + c;
+              r[k] = a;
+              r0[k] = a;
+              p[k] = 0.0f;
+              v[k] = 0.0f;
+              x[k] = 0.0f;
+              acc[0] += (double)a * (double)a;
+            }
+        }
+      block_reduce_store<1>(acc, partials);
+    }
+
+    template <int BS>
+    __device__ __forceinline__ float4 apply_binv(const float *__restrict__ binv, int n_pad, int i, const float (&a)[BS])
+    {
+      float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int rr = 0; rr < BS; ++rr)
+#pragma unroll
+        for (int c = 0; c < BS; ++c) o[rr] = fmaf(binv[(size_t)(rr * BS + c) * n_pad + i], a[c], o[rr]);
+      return make_float4(o[0], o[1], o[2], o[3]);
+    }
+
+    // p = r + beta (p - omega v);  ph = D^-1 p
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    update_p_kernel(int n_pad, float beta, float omega, const float *__restrict__ r, float *__restrict__ p, const float *__restrict__ v,
+                    const float *__restrict__ binv, float4 *__restrict__ ph)
+    {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          float pc[BS];
+#pragma unroll
+          for (int c = 0; c < BS; ++c)
+            {
+              const size_t k = (size_t)i * BS + c;
+              pc[c] = fmaf(beta, fmaf(-omega, v[k], p[k]), r[k]);
+              p[k] = pc[c];
+            }
+          ph[i] = apply_binv<BS>(binv, n_pad, i, pc);
+        }
+    }
+
+    // s = r - alpha v;  sh = D^-1 s;  partial |s|^2
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    update_s_kernel(int n_pad, float alpha, const float *__restrict__ r, const float *__restrict__ v, float *__restrict__ s,
+                    const float *__restrict__ binv, float4 *__restrict__ sh, double *__restrict__ partials)
+    {
+      double acc[1] = {0.0};
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          float sc[BS];
+#pragma unroll
+          for (int c = 0; c < BS; ++c)
+            {
+              const size_t k = (size_t)i * BS + c;
+              sc[c] = fmaf(-alpha, v[k], r[k]);
+              s[k] = sc[c];
+              acc[0] += (double)sc[c] * (double)sc[c];
+            }
+          sh[i] = apply_binv<BS>(binv, n_pad, i, sc);
+        }
+      block_reduce_store<1>(acc, partials);
+    }
+
+    // x += alpha ph + omega sh;  r = s - omega t;  partials |r|^2 and r0 . r
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    update_xr_kernel(int n_pad, float alpha, float omega, float *__restrict__ x, const float4 *__restrict__ ph,
+                     const float4 *__restrict__ sh, float *__restrict__ r, const float *__restrict__ s, const float *__restrict__ t,
+                     const float *__restrict__ r0, double *__restrict__ partials)
+    {
+      double acc[2] = {0.0, 0.0};
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const float4 a4 = ph[i], b4 = sh[i];
+          const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int c = 0; c < BS; ++c)
+            {
+              const size_t k = (size_t)i * BS + c;
+              x[k] = fmaf(alpha, a[c], fmaf(omega, b[c], x[k]));
+              const float rc = fmaf(-omega, t[k], s[k]);
+              r[k] = rc;
+              acc[0] += (double)rc * (double)rc;
+              acc[1] += (double)r0[k] * (double)rc;
+            }
+        }
+      block_reduce_store<2>(acc, partials);
+    }
+
+    // out[0] = a0 . b0, out[1] = a1 . b1 (NR = 2) on flat arrays
+    template <int NR>
+    __global__ void __launch_bounds__(kT)
+    dot32_kernel(int64_t n, const float *__restrict__ a0, const float *__restrict__ b0, const float *__restrict__ a1,
+                 const float *__restrict__ b1, double *__restrict__ partials)
+    {
+      double acc[NR];
+#pragma unroll
+      for (int q = 0; q < NR; ++q) acc[q] = 0.0;
+      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        {
+          acc[0] += (double)a0[k] * (double)b0[k];
+          if (NR > 1) acc[NR - 1] += (double)a1[k] * (double)b1[k];
+        }
+      block_reduce_store<NR>(acc, partials);
+    }
+
+    // dst (fp64, original numbering) = scale * x (SELL numbering), owned rows only
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    final_kernel(int n_pad, const int *__restrict__ perm_row, const float *__restrict__ x, double scale, double *__restrict__ dst)
+    {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const int row = perm_row[i];
+          if (row < 0) continue;
+#pragma unroll
+          for (int c = 0; c < BS; ++c) dst[(size_t)row * BS + c] = scale * (double)x[(size_t)i * BS + c];
+        }
+    }
+
+    // x4 (SELL numbering, float4 per node) from a fp64 vector in the original numbering (owned nodes)
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    to_sell4_kernel(int n_pad, const int *__restrict__ perm_row, const double *__restrict__ src, float4 *__restrict__ x4)
+    {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const int row = perm_row[i];
+          float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          if (row >= 0)
+            {
+#pragma unroll
+              for (int c = 0; c < BS; ++c) o[c] = (float)src[(size_t)row * BS + c];
+            }
+          x4[i] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+
+    __global__ void __launch_bounds__(kT) halo_pack4_kernel(int n, const int *__restrict__ idx, const float4 *__restrict__ v, float4 *__restrict__ buf)
+    {
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t < n) buf[t] = v[idx[t]];
+    }
+  } // namespace
+
+  InnerSolver32::~InnerSolver32()
+  {
+    if (h_results) cudaFreeHost(h_results);
+  }
+
+  void InnerSolver32::setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo_)
+  {
+    if (A.R != A.C || (A.R != 2 && A.R != 3)) throw std::runtime_error("InnerSolver32: square 2x2 / 3x3 blocks required");
+    const int dim = nodes.dim;
+    if (const char *e = std::getenv("IFEM_SELL_VARIANT")) variant = std::atoi(e);
+    S.bs = A.R;
+    S.n_rows = A.n_brows_spmv >= 0 ? A.n_brows_spmv : A.n_brows;
+    S.n_cols = A.n_bcols;
+    if (S.n_rows > nodes.n_nodes || S.n_cols < S.n_rows) throw std::runtime_error("InnerSolver32: node table does not match the matrix");
+    const int n = S.n_rows;
+    const std::vector<int64_t> rp = A.rowptr.to_host(ctx.stream);
+
+    // ---- row order: columns of T x T nodes along the sweep axis, plane by plane, rows of one length together ----
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d) lo[d] = hi[d] = n ? nodes.coords[d] : 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int d = 0; d < dim; ++d)
+        {
+          const double c = nodes.coords[(size_t)i * dim + d];
+          lo[d] = std::min(lo[d], c);
+          hi[d] = std::max(hi[d], c);
+        }
+    double vol = 1.0;
+    int n_ext = 0;
+    for (int d = 0; d < dim; ++d)
+      if (hi[d] > lo[d])
+        {
+          vol *= hi[d] - lo[d];
+          ++n_ext;
+        }
+    const double h = n_ext && n > 1 ? std::pow(vol / n, 1.0 / n_ext) : 1.0; // node spacing estimate
+    const int T = dim == 3 ? 32 : 128;
+    const int sweep = dim - 1;
+    int nt[2] = {1, 1};
+    for (int d = 0; d < sweep; ++d) nt[d] = std::max(1, std::min(1023, (int)std::ceil((hi[d] - lo[d]) / (T * h))));
+    std::vector<std::pair<uint64_t, int>> keys((size_t)n);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i)
+      {
+        uint64_t tile = 0;
+        for (int d = sweep - 1; d >= 0; --d)
+          {
+            const int b = std::max(0, std::min(nt[d] - 1, (int)std::floor((nodes.coords[(size_t)i * dim + d] - lo[d]) / (T * h))));
+            tile = tile * (uint64_t)nt[d] + (uint64_t)b;
+          }
+        const int64_t zb = std::max<int64_t>(0, std::min<int64_t>((1 << 20) - 1, (int64_t)std::floor((nodes.coords[(size_t)i * dim + sweep] - lo[sweep]) / h + 0.5)));
+        const int64_t len = std::min<int64_t>(rp[i + 1] - rp[i], 4095);
+        keys[i] = {(tile << 32) | ((uint64_t)zb << 12) | (uint64_t)len, i};
+      }
+    std::sort(keys.begin(), keys.end());
+
+    S.n_slices = (n + 31) / 32;
+    S.n_pad = S.n_slices * 32;
+    std::vector<int> perm((size_t)S.n_pad, -1), off((size_t)S.n_slices + 1, 0);
+    S.h_pos.assign((size_t)S.n_cols, 0);
+    S.n_blocks = 0;
+    for (int i = 0; i < n; ++i)
+      {
+        perm[i] = keys[i].second;
+        S.h_pos[keys[i].second] = i;
+        S.n_blocks += rp[keys[i].second + 1] - rp[keys[i].second];
+      }
+    for (int g = n; g < S.n_cols; ++g) S.h_pos[g] = S.n_pad + (g - n);
+    int64_t slots = 0;
+    for (int sl = 0; sl < S.n_slices; ++sl)
+      {
+        int64_t L = 0;
+        for (int l = 0; l < 32; ++l)
+          {
+            const int row = perm[(size_t)sl * 32 + l];
+            if (row >= 0) L = std::max<int64_t>(L, rp[row + 1] - rp[row]);
+          }
+        slots += L;
+        if (slots > INT32_MAX) throw std::runtime_error("InnerSolver32: too many block slots for 32-bit slice offsets");
+        off[sl + 1] = (int)slots;
+      }
+    S.n_slots = slots;
+    keys.clear();
+    keys.shrink_to_fit();
+
+    S.slice_off.upload(off, ctx.stream);
+    S.perm_row.upload(perm, ctx.stream);
+    S.pos.upload(S.h_pos, ctx.stream);
+    S.col.alloc((size_t)S.n_slots * 32 + 32 * 8); // slack: the pipelined kernel prefetches up to 8 slots past a slice
+    S.col.zero(ctx.stream);
+    S.val.alloc((size_t)S.n_slots * 32 * S.bs * S.bs);
+    const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
+    if (S.n_slices)
+      {
+        sell_fill_col_kernel<<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.col.p, S.pos.p, S.col.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+
+    // ---- vectors ----
+    const size_t nv = (size_t)S.n_pad * S.bs;
+    for (DevBuf<float> *b : {&r, &r0, &p, &v, &s, &t, &x})
+      {
+        b->alloc(nv);
+        b->zero(ctx.stream);
+      }
+    const size_t n4 = ((size_t)S.n_pad + (size_t)(S.n_cols - S.n_rows)) * 4;
+    ph.alloc(n4);
+    ph.zero(ctx.stream);
+    sh.alloc(n4);
+    sh.zero(ctx.stream);
+    binv.alloc((size_t)S.bs * S.bs * S.n_pad);
+    grid = std::max(1, std::min((S.n_pad + kT - 1) / kT, ctx.sm_count * 8));
+    partials.alloc((size_t)grid * 2);
+    results.alloc(4);
+    if (!h_results) IFEM_CUDA(cudaMallocHost(&h_results, 4 * sizeof(double)));
+
+    // ---- halo plan in SELL numbering ----
+    halo_plan = (halo_ && halo_->active()) ? halo_ : nullptr;
+    if (halo_plan)
+      {
+        if (halo_plan->n_owned != S.n_rows) throw std::runtime_error("InnerSolver32: halo plan does not match the matrix rows");
+        if (halo_plan->n_send_total)
+          {
+            const std::vector<int> idx = halo_plan->d_send_idx.to_host(ctx.stream);
+            std::vector<int> sp(idx.size());
+            for (size_t k = 0; k < idx.size(); ++k) sp[k] = S.h_pos[idx[k]];
+            send_pos.upload(sp, ctx.stream);
+            send_buf.alloc((size_t)halo_plan->n_send_total * 4);
+          }
+      }
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void InnerSolver32::refresh(Context &ctx, const Bcsr &A, const double *binv64)
+  {
+    if (!S.built()) throw std::runtime_error("InnerSolver32::refresh before setup");
+    const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
+    if (S.bs == 3)
+      sell_fill_val_kernel<3><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.val.p, S.val.p);
+    else
+      sell_fill_val_kernel<2><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.val.p, S.val.p);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+    if (binv64)
+      {
+        binv_to_sell_kernel<<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.bs * S.bs, S.perm_row.p, binv64, binv.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+  }
+
+  void InnerSolver32::spmv(Context &ctx, const float *x4, float *y)
+  {
+    const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
+    const float4 *xp = reinterpret_cast<const float4 *>(x4);
+#define IFEM_SELL_LAUNCH(B, U) \
+  sell_spmv_kernel<B, U><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.col.p, S.val.p, xp, y)
+#define IFEM_SELL_PIPE(B, NS, M) \
+  sell_spmv_pipe_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.col.p, S.val.p, xp, y)
+    // variant: 1..4 = plain kernel with that unroll depth; 10 * NS + MINB = pipelined kernel with NS slots per step
+    // and MINB resident CTAs per SM
+    if (S.bs == 3)
+      switch (variant)
+        {
+        case 1: IFEM_SELL_LAUNCH(3, 1); break;
+        case 2: IFEM_SELL_LAUNCH(3, 2); break;
+        case 4: IFEM_SELL_LAUNCH(3, 4); break;
+        case 13: IFEM_SELL_PIPE(3, 1, 3); break;
+        case 16: IFEM_SELL_PIPE(3, 1, 6); break;
+        case 23: IFEM_SELL_PIPE(3, 2, 3); break;
+        case 26: IFEM_SELL_PIPE(3, 2, 6); break;
+        case 42: IFEM_SELL_PIPE(3, 4, 2); break;
+        case 43: IFEM_SELL_PIPE(3, 4, 3); break;
+        default: IFEM_SELL_PIPE(3, 2, 4); break; // 24
+        }
+    else
+      switch (variant)
+        {
+        case 1: IFEM_SELL_LAUNCH(2, 1); break;
+        case 2: IFEM_SELL_LAUNCH(2, 2); break;
+        case 4: IFEM_SELL_LAUNCH(2, 4); break;
+        default: IFEM_SELL_PIPE(2, 2, 4); break;
+        }
+#undef IFEM_SELL_LAUNCH
+#undef IFEM_SELL_PIPE
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+  }
+
+  void InnerSolver32::halo(Context &ctx, float *x4)
+  {
+    if (!halo_plan) return;
+    if (!ctx.comm) throw std::runtime_error("InnerSolver32::halo: no communicator");
+    const Halo &H = *halo_plan;
+    if (H.n_send_total)
+      {
+        halo_pack4_kernel<<<(H.n_send_total + kT - 1) / kT, kT, 0, ctx.stream>>>(H.n_send_total, send_pos.p, reinterpret_cast<const float4 *>(x4),
+                                                                              reinterpret_cast<float4 *>(send_buf.p));
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+    comm_group_start(*ctx.comm);
+    for (size_t k = 0; k < H.neighbours.size(); ++k)
+      comm_sendrecv_f32(*ctx.comm, H.neighbours[k], send_buf.p + (size_t)H.send_off[k] * 4, (int64_t)H.send_cnt[k] * 4,
+                        x4 + ((size_t)S.n_pad + (size_t)(H.recv_off[k] - S.n_rows)) * 4, (int64_t)H.recv_cnt[k] * 4, ctx.stream);
+    comm_group_end(*ctx.comm);
+  }
+
+  void InnerSolver32::reduce(Context &ctx, int nr, double *out)
+  {
+    reduce_final32_kernel<<<1, kT, 0, ctx.stream>>>(grid, nr, partials.p, results.p);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+    if (ctx.comm && ctx.comm->size > 1) comm_allreduce_sum(*ctx.comm, results.p, nr, ctx.stream);
+    IFEM_CUDA(cudaMemcpyAsync(h_results, results.p, nr * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+    for (int q = 0; q < nr; ++q) out[q] = h_results[q];
+  }
+
+  template <int BS>
+  static SolveResult solve_impl(Context &ctx, InnerSolver32 &I, const Sell32 &S, int grid, const double *src, double src_norm, double *dst,
+                                double rel_tol, int max_it, float *r, float *r0, float *p, float *v, float *s, float *t, float *x, float *ph,
+                                float *sh, const float *binv, double *partials, const std::function<void(const float *, float *)> &A,
+                                const std::function<void(int, double *)> &reduce)
+  {
+    (void)I;
+    SolveResult out;
+    const int n_pad = S.n_pad;
+    const int64_t nflat = (int64_t)n_pad * BS;
+    float4 *ph4 = reinterpret_cast<float4 *>(ph), *sh4 = reinterpret_cast<float4 *>(sh);
+    auto count = [&](int k = 1) { ctx.kernel_launches += k; };
+    if (!(src_norm > 0.0))
+      {
+        // A^-1 0 = 0
+        final_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x, 0.0, dst);
+        IFEM_KERNEL_CHECK();
+        count();
+        out.converged = true;
+        return out;
+      }
+    double red[2];
+    init_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, r, r0, p, v, x, partials);
+    IFEM_KERNEL_CHECK();
+    count();
+    reduce(1, red);
+    double rho_new = red[0]; // r0 . r = |r|^2 (~1)
+    out.residual = std::sqrt(red[0]);
+    double rho = 1.0, alpha = 1.0, omega = 1.0;
+    const double tol = rel_tol;
+    while (out.iterations < max_it)
+      {
+        const double beta = (rho_new / rho) * (alpha / omega);
+        update_p_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)beta, (float)omega, r, p, v, binv, ph4);
+        IFEM_KERNEL_CHECK();
+        count();
+        A(ph, v);
+        dot32_kernel<1><<<grid, kT, 0, ctx.stream>>>(nflat, r0, v, r0, v, partials);
+        IFEM_KERNEL_CHECK();
+        count();
+        reduce(1, red);
+        if (red[0] == 0.0 || !std::isfinite(red[0])) break;
+        alpha = rho_new / red[0];
+        update_s_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)alpha, r, v, s, binv, sh4, partials);
+        IFEM_KERNEL_CHECK();
+        count();
+        reduce(1, red);
+        out.iterations++;
+        out.residual = std::sqrt(red[0]);
+        if (out.residual <= tol)
+          {
+            // x += alpha ph
+            update_xr_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)alpha, 0.0f, x, ph4, sh4, r, s, t, r0, partials);
+            IFEM_KERNEL_CHECK();
+            count();
+            out.converged = true;
+            break;
+          }
+        A(sh, t);
+        dot32_kernel<2><<<grid, kT, 0, ctx.stream>>>(nflat, t, s, t, t, partials);
+        IFEM_KERNEL_CHECK();
+        count();
+        reduce(2, red);
+        if (red[1] == 0.0 || !std::isfinite(red[1]))
+          {
+            update_xr_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)alpha, 0.0f, x, ph4, sh4, r, s, t, r0, partials);
+            IFEM_KERNEL_CHECK();
+            count();
+            break;
+          }
+        omega = red[0] / red[1];
+        update_xr_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)alpha, (float)omega, x, ph4, sh4, r, s, t, r0, partials);
+        IFEM_KERNEL_CHECK();
+        count();
+        reduce(2, red);
+        out.residual = std::sqrt(red[0]);
+        rho = rho_new;
+        rho_new = red[1];
+        if (out.residual <= tol)
+          {
+            out.converged = true;
+            break;
+          }
+        if (rho_new == 0.0 || omega == 0.0 || !std::isfinite(rho_new)) break;
+      }
+    final_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x, src_norm, dst);
+    IFEM_KERNEL_CHECK();
+    count();
+    out.residual *= src_norm;
+    return out;
+  }
+
+  SolveResult InnerSolver32::solve(Context &ctx, const double *src, double src_norm, double *dst, double rel_tol, int max_it)
+  {
+    if (!S.built()) throw std::runtime_error("InnerSolver32::solve before setup");
+    std::function<void(const float *, float *)> A = [&](const float *in4, float *out) {
+      halo(ctx, const_cast<float *>(in4));
+      spmv(ctx, in4, out);
+    };
+    std::function<void(int, double *)> red = [&](int nr, double *o) { reduce(ctx, nr, o); };
+    if (S.bs == 3)
+      return solve_impl<3>(ctx, *this, S, grid, src, src_norm, dst, rel_tol, max_it, r.p, r0.p, p.p, v.p, s.p, t.p, x.p, ph.p, sh.p, binv.p,
+                           partials.p, A, red);
+    return solve_impl<2>(ctx, *this, S, grid, src, src_norm, dst, rel_tol, max_it, r.p, r0.p, p.p, v.p, s.p, t.p, x.p, ph.p, sh.p, binv.p,
+                         partials.p, A, red);
+  }
+
+  void InnerSolver32::probe_load(Context &ctx, const double *xin)
+  {
+    if (!S.built()) throw std::runtime_error("InnerSolver32::probe_load before setup");
+    float4 *ph4 = reinterpret_cast<float4 *>(ph.p);
+    if (S.bs == 3)
+      to_sell4_kernel<3><<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.perm_row.p, xin, ph4);
+    else
+      to_sell4_kernel<2><<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.perm_row.p, xin, ph4);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+    halo(ctx, ph.p);
+  }
+
+  void InnerSolver32::probe_apply(Context &ctx) { spmv(ctx, ph.p, v.p); }
+
+  void InnerSolver32::probe_store(Context &ctx, double *yout)
+  {
+    if (S.bs == 3)
+      final_kernel<3><<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.perm_row.p, v.p, 1.0, yout);
+    else
+      final_kernel<2><<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.perm_row.p, v.p, 1.0, yout);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+  }
+} // namespace ifem

@@ -1,0 +1,81 @@
+// Mixed-precision inner solver for the velocity block: the stand-in for the MUMPS
+// factorisation of system_matrix.block(0,0) inside BlockSchurPreconditioner::vmult
+// (reference source/mpi_insim.cpp:111-127; Krylov-for-A~ precedent
+// source/mpi_insimex.cpp:114-124). FGMRES is flexible, so the preconditioner may be
+// any approximate inverse: here BiCGStab + node-block Jacobi run entirely in fp32 on
+// a copy of A_uu laid out for streaming (the operator, residuals and Krylov basis of
+// the outer FGMRES stay fp64 on the row-plane BCSR matrix).
+//
+// Layout of the copy ("sliced ELL of bs x bs blocks", SELL-32):
+//   * block rows are re-ordered: the domain is cut into columns of T x T nodes along
+//     the sweep axis (last coordinate), inside a column rows are sorted by plane and
+//     then by row length, and 32 consecutive rows form a slice. Rows of equal length
+//     share slices (padding 0.5 % at config 3) and everything a wave of CTAs touches
+//     in x is a few MB, so x is read from HBM once;
+//   * slice s with L_s block slots stores col[(off_s + j) * 32 + lane] and
+//     val[((off_s + j) * bs*bs + k) * 32 + lane]: one lane per row, every load of a
+//     warp is one full 128-byte line of a purely sequential stream;
+//   * the solver's vectors live in the same permuted ("SELL") numbering, so the
+//     product is written coalesced and the x gathers of a slice hit runs of
+//     consecutive nodes; gather sources are padded to float4 per node.
+#pragma once
+#include "halo.h"
+#include "krylov.h"
+#include "linalg.h"
+
+namespace ifem
+{
+  struct Sell32
+  {
+    int bs = 0;
+    int n_rows = 0;              // owned block rows (= rows of a product)
+    int n_cols = 0;              // local block columns (owned + ghosts)
+    int n_slices = 0, n_pad = 0; // n_pad = 32 * n_slices >= n_rows
+    int64_t n_slots = 0;         // sum of slice lengths
+    int64_t n_blocks = 0;        // blocks of the owned rows (unpadded)
+    DevBuf<int> slice_off;       // [n_slices + 1]
+    DevBuf<int> perm_row;        // [n_pad] original block row of a SELL row, -1 = padding row
+    DevBuf<int> pos;             // [n_cols] SELL position of an original node (ghosts: n_pad + ghost no.)
+    DevBuf<int> col;             // [n_slots * 32] SELL position of the column node
+    DevBuf<float> val;           // [n_slots * bs * bs * 32]
+    std::vector<int> h_pos;
+    bool built() const { return n_slices > 0; }
+    // bytes one product has to move: values + column index + slice offsets, x (float4) read once, y written once
+    double spmv_bytes() const { return 4.0 * n_blocks * bs * bs + 4.0 * n_blocks + 4.0 * (n_slices + 1) + 16.0 * n_cols + 4.0 * bs * n_rows; }
+    double padding() const { return n_blocks ? double(n_slots) * 32.0 / double(n_blocks) : 1.0; }
+  };
+
+  class InnerSolver32
+  {
+  public:
+    ~InnerSolver32();
+    // pattern-only work, once per sparsity pattern: row order, slices, column map, halo plan in SELL numbering
+    void setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo);
+    // values of A and of the inverted diagonal blocks (row-major bs x bs per node) -> fp32, every solve
+    void refresh(Context &ctx, const Bcsr &A, const double *binv);
+    // dst ~= A^-1 src to |r| <= rel_tol * |src| (recurrence residual), x0 = 0; src_norm = |src| over all ranks
+    SolveResult solve(Context &ctx, const double *src, double src_norm, double *dst, double rel_tol, int max_it);
+    // y = A32 x with x, y fp64 vectors in the original numbering (tests, kernel timing): load x into the gather
+    // buffer (ghosts exchanged), apply the product kernel, store the result
+    void probe_load(Context &ctx, const double *x);
+    void probe_apply(Context &ctx);
+    void probe_store(Context &ctx, double *y);
+    Sell32 S;
+    int variant = 24; // product kernel (see InnerSolver32::spmv): 10 * slots per step + CTAs per SM of the pipelined form
+
+  private:
+    void spmv(Context &ctx, const float *x4, float *y);
+    void halo(Context &ctx, float *x4);
+    void reduce(Context &ctx, int n_results, double *out);
+    DevBuf<float> r, r0, p, v, s, t, x; // [n_pad * bs]
+    DevBuf<float> ph, sh;               // [(n_pad + n_ghost) * 4], gather sources
+    DevBuf<float> binv;                 // [bs * bs][n_pad]
+    DevBuf<double> partials, results;
+    double *h_results = nullptr;
+    int grid = 0;
+    // halo plan in SELL numbering
+    const Halo *halo_plan = nullptr;
+    DevBuf<int> send_pos;
+    DevBuf<float> send_buf;
+  };
+} // namespace ifem

@@ -172,11 +172,13 @@ namespace ifem
       ScopedTimer t(ctx, timer_ms["A_inv"]);
       LinOp Auu = [&](const double *x, double *y) {
         fs.halo_u.update(ctx, const_cast<double *>(x));
-        if (control.a_inv_fp32) spmv_fp32(ctx, fs.A_uu, x, y); else spmv(ctx, fs.A_uu, x, y);
+        if (control.a_inv_fp32 == 1) spmv_fp32(ctx, fs.A_uu, x, y); else spmv(ctx, fs.A_uu, x, y);
       };
       LinOp jac = [&](const double *x, double *y) { block_diag_apply(ctx, fs.n_owned_unodes, fs.dim, d_binv.p, x, y); };
       const double unrm = nrm2(ctx, vu, utmp);
-      const SolveResult r = bicgstab(ctx, vu, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);
+      const SolveResult r = control.a_inv_fp32 == 2
+                              ? inner32.solve(ctx, utmp, unrm, dst_u, control.a_inv_rel, control.a_inv_max_it)
+                              : bicgstab(ctx, vu, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);
       cur.a_inv_its += r.iterations;
     }
     cur.precond_applies++;
@@ -203,7 +205,13 @@ namespace ifem
         fs.schur_valid = true;
       }
     block_diag_inverse(ctx, fs.A_uu, d_binv.p);
-    if (control.a_inv_fp32) make_fp32_copy(ctx, fs.A_uu);
+    if (control.a_inv_fp32 == 2)
+      {
+        if (!inner32.S.built()) inner32.setup(ctx, fs.A_uu, fs.un, fs.n_ranks > 1 ? &fs.halo_u : nullptr);
+        inner32.refresh(ctx, fs.A_uu, d_binv.p);
+      }
+    else if (control.a_inv_fp32 == 1)
+      make_fp32_copy(ctx, fs.A_uu);
     const VecSpace &va = fs.vs_all;
     const double nrm = nrm2(ctx, va, fs.rhs.p);
     const double tol = std::max(control.fgmres_floor, control.fgmres_rel * nrm);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "fluid.h"
+#include "inner32.h"
 #include "krylov.h"
 
 namespace ifem
@@ -65,7 +66,9 @@ namespace ifem
     // the node-block Jacobi preconditioner, run to a_inv_rel * |src| (hard part 2)
     double a_inv_rel = 1e-3;
     int a_inv_max_it = 2000;
-    bool a_inv_fp32 = false; // stream A_uu as fp32 inside the inner solve (legal: FGMRES is flexible)
+    // 0: fp64 BiCGStab on the BCSR matrix; 1: same, A_uu streamed as fp32; 2: fp32 BiCGStab on the sliced copy of
+    // A_uu (inner32.h). Legal because FGMRES is flexible; operator, residuals and Krylov basis stay fp64
+    int a_inv_fp32 = 0;
     int basis_size = 30;
     static InsSolverControl serial()
     {
@@ -120,6 +123,11 @@ namespace ifem
     DevBuf<double> d_binv, d_con_vals, d_tmp_p, d_utmp, d_utmp2;
     int64_t n_dofs_global = 0, n_p_global = 0;
     VecPool pool_fgmres, pool_cg, pool_ainv;
+
+  public:
+    InnerSolver32 inner32;
+
+  protected:
     NewtonRecord cur{};
   };
 } // namespace ifem

@@ -1,0 +1,54 @@
+"""GPU tests of the mixed-precision inner solver (openifem_b200/csrc/inner32.*): the fp32 SELL-32 copy of the
+velocity block and the fp32 BiCGStab that stands in for the reference's MUMPS factorisation of
+system_matrix.block(0,0) (source/mpi_insim.cpp:111-127).
+
+Tolerances: product kernel against the fp64 BCSR product 2e-6 of max|y| (fp32 rounding of ~100 terms);
+converged Newton states against the oracle 1e-6 relative, as in tests/test_ins_gpu.py - the inner solve is only
+a preconditioner of the flexible GMRES, so its precision must not show in converged quantities."""
+import numpy as np
+import pytest
+
+from util import cavity_prm, make_gpu, make_oracle, rel
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [1, 2, 4, 13, 16, 23, 24, 26, 42, 43]
+
+
+@pytest.mark.parametrize("dim,reps,hi", [(3, (5, 4, 6), (1.0, 1.2, 0.9)), (2, (9, 7), (1.0, 0.8)), (3, (12, 12, 12), (1, 1, 1))])
+def test_sell_product_matches_fp64_product(dim, reps, hi):
+    g = make_gpu(cavity_prm(dim), reps, (0,) * dim, hi)
+    rng = np.random.default_rng(11)
+    ev = rng.uniform(-1, 1, g.n_dofs)
+    g.set_vector(g.EVALUATION_POINT, ev)
+    g.set_vector(g.PRESENT, 0.5 * ev)
+    g.assemble(True)
+    g.set_vector(g.SYSTEM_RHS, rng.uniform(-1, 1, g.n_dofs))  # x of the product
+    for v in VARIANTS:
+        ms, nbytes, pad, err = g.bench_spmv_uu_sell(1, variant=v)
+        assert 1.0 <= pad < 2.5
+        assert 0.0 <= err < 2e-6, (v, err)
+
+
+@pytest.mark.parametrize("dim,reps,steps", [(3, (4, 4, 4), 2), (2, (8, 8), 3)])
+def test_time_steps_with_fp32_inner_solver_match_oracle(dim, reps, steps):
+    prm = cavity_prm(dim, newton_tol=1e-9)
+    o = make_oracle(prm, reps, (0,) * dim, (1,) * dim)
+    g = make_gpu(prm, reps, (0,) * dim, (1,) * dim)
+    o.fgmres_rel = 1e-9
+    g.set_control(a_inv_rel=1e-3, a_inv_max_it=500, fgmres_rel=1e-9, a_inv_fp32=2)
+    for k in range(steps):
+        o.run_one_step(k == 0)
+        g.run_one_step(k == 0)
+    sol = g.get_current_solution()
+    nu = o.n_u
+    assert rel(sol[:nu], o.velocity()) < 1e-6
+    pg, po = sol[nu:] - sol[nu:].mean(), o.pressure() - o.pressure().mean()
+    assert rel(pg, po) < 1e-6
+    hg, ho = g.history(), o.history
+    assert [(a["timestep"], a["iteration"]) for a in hg] == [(b[0], b[1]) for b in ho]
+    # residual norms below ~1e-11 are set by the linear-solver tolerance (1e-9 x the previous residual), not by the
+    # discretisation: compare them with that absolute floor
+    for a, b in zip(hg, ho):
+        assert abs(a["abs_res"] - b[2]) <= 1e-6 * b[2] + 1e-11
+    assert all(h["a_inv_its"] > 0 for h in hg)

@@ -181,7 +181,8 @@ def run_ours(args):
     params = ifem.Parameters.AllParameters(text=cavity_prm(3))
     flow = ifem.Fluid.MPI.InsIM(tria, params)
     flow.setup()
-    flow.set_control(a_inv_rel=1e-1, a_inv_fp32=2)  # fp32 inner solver on the SELL-32 copy of A_uu (preconditioner only)
+    # fp32 inner solver on the SELL-32 copy of A_uu with row-scaled fp16 matrix values (preconditioner only)
+    flow.set_control(a_inv_rel=1e-1, a_inv_fp32=args.inner_mode)
     barrier()
     t_setup = time.perf_counter() - t_setup
     n_u, n_p, nnz_local, _, _ = flow.sizes()
@@ -223,7 +224,10 @@ def run_ours(args):
     #    (~70 % of a step)
     #  * the FGMRES operator SpMV on the same block in fp64 (north_star's ">= 40 % of HBM roofline" kernel)
     ms_uu, bytes_uu = flow.bench_spmv_uu(20)
-    ms_32, bytes_32, sell_padding, sell_err = flow.bench_spmv_uu_sell(20, check_error=False)
+    if args.inner_mode >= 2:
+        ms_32, bytes_32, sell_padding, sell_err = flow.bench_spmv_uu_sell(20, check_error=False)
+    else:
+        (ms_32, bytes_32), sell_padding = (flow.bench_spmv_uu_fp32(20) if args.inner_mode == 1 else (ms_uu, bytes_uu)), 1.0
     ms_blk, bytes_blk = flow.bench_vmult(10)
     peak, peak_src = _peaks()
     achieved = bytes_32 / (ms_32 * 1e-3) / 1e9
@@ -258,18 +262,23 @@ def run_ours(args):
         "config": {"workload": f"3D INS lid-driven cavity {n}^3 hex cells Q2/Q1 (config 3): {n_dofs} DoF, {nnz} matrix entries, "
                                f"Re 100, dt 1e-2, from rest; step = run_one_step (Newton x (assembly + FGMRES/Schur))",
                    "l2": "inputs larger than L2 (A_uu alone is %.1f GB per GPU)" % (bytes_uu / 1e9),
-                   "a_inv": "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1 in fp32 on a sliced-ELL copy of A_uu, inside the "
-                            "preconditioner only (FGMRES operator, residuals and basis fp64; converged fields equal the "
-                            "oracle's to 1e-6, tests/test_inner32_gpu.py)",
+                   "a_inv": {0: "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1 in fp64 on the BCSR matrix",
+                             1: "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1, A_uu streamed as fp32 (BCSR)",
+                             2: "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1 in fp32 on a sliced-ELL (SELL-32) copy of A_uu",
+                             3: "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1 in fp32 on a sliced-ELL (SELL-32) copy of A_uu "
+                                "whose values are stored as row-scaled fp16"}[args.inner_mode]
+                            + "; inside the preconditioner only - FGMRES operator, residuals and basis are fp64, Newton/FGMRES "
+                              "iteration counts and converged fields equal the fp64 path's (tests/test_inner32_gpu.py: 1e-6 vs oracle)",
                    "parallelism": f"{world} z-slab(s), one rank per GPU; NCCL: ghost halos + dot-product all-reduces only",
                    "setup_s": round(t_setup, 1), "newton_its_last_step": len(last),
                    "fgmres_its_last_step": [h["gmres_its"] for h in last], "section_ms_total": sections},
         "e2e": {"value": sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d},
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "sell_spmv_pipe_kernel<3,2,4> (product of the fp32 inner A~^-1 solves on the SELL-32 "
-                                               "copy of A_uu; dominant kernel of a step), per GPU (rank 0's rows)",
+        "roofline": {"bound": "hbm", "kernel": ("sell_spmv_h_kernel<3,2,4>" if args.inner_mode == 3 else "sell_spmv_pipe_kernel<3,2,4>")
+                                               + " (product of the fp32 inner A~^-1 solves on the SELL-32 copy of A_uu; dominant "
+                                                 "kernel of a step), per GPU (rank 0's rows)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic.get("sell_spmv_pipe_kernel") if world == 1 and n == 128 else None,
+                     "traffic": traffic.get("sell_spmv_h_kernel" if args.inner_mode == 3 else "sell_spmv_pipe_kernel") if world == 1 and n == 128 else None,
                      "algorithmic_bytes": bytes_32, "ms": ms_32, "sell_padding": sell_padding,
                      "fgmres_operator_spmv": {"kernel": "bcsr_spmv_kernel<3,3,32,double> (A_uu, fp64 operator of FGMRES)", "ms": ms_uu,
                                               "algorithmic_bytes": bytes_uu, "achieved": achieved64, "frac": achieved64 / peak,
@@ -291,6 +300,8 @@ def main():
     ap.add_argument("--cells", type=int, default=128, help="cells per direction (config 3 = 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inner-mode", type=int, default=3, choices=[0, 1, 2, 3],
+                    help="A~^-1 inner solve: 0 fp64 BCSR, 1 fp32-streamed BCSR, 2 fp32 SELL-32, 3 fp32 solver on fp16 SELL-32 values")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -80,7 +80,8 @@ typedef struct
   int a_inv_max_it;
   int basis_size;     /* SolverFGMRES max_basis_size (deal.II default 30) */
   int a_inv_fp32;     /* inner solve: 0 fp64; 1 fp64 BiCGStab, A_uu streamed as fp32; 2 fp32 BiCGStab on the sliced (SELL-32)
-                         copy of A_uu. Preconditioner only - operator, residuals and FGMRES basis stay fp64 */
+                         copy of A_uu; 3 as 2, matrix values of the copy stored as row-scaled fp16. Preconditioner only -
+                         operator, residuals and FGMRES basis stay fp64 */
 } ifem_ins_control;
 
 typedef struct
@@ -226,13 +227,13 @@ int ifem_insim_bench_vmult(ifem_insim *s, int reps, double *ms_per_apply, double
 int ifem_insim_bench_spmv_uu(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
 /* fp32-streamed copy of A_uu (inner solve only) */
 int ifem_insim_bench_spmv_uu_fp32(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
-/* the product kernel of the fp32 inner solver on the sliced (SELL-32) copy of A_uu (a_inv_fp32 = 2); variant = unroll
- * depth of the slot loop (0: default); padding = stored / actual blocks; max_rel_err (may be NULL) = max |y32 - y64| /
- * max |y64| against the fp64 product with the present rhs as x */
 /* product kernel the fp32 inner solver uses from now on (tuning hook; see InnerSolver32::spmv for the encoding) */
 int ifem_insim_set_inner_variant(ifem_insim *s, int variant);
-int ifem_insim_bench_spmv_uu_sell(ifem_insim *s, int variant, int reps, double *ms_per_apply, double *bytes_per_apply,
-                                  double *padding, double *max_rel_err);
+/* the product kernel of the fp32 inner solver on the sliced (SELL-32) copy of A_uu (a_inv_fp32 = 2 / 3); precision = 32
+ * or 16 (storage of the matrix values; 0: as built); variant = kernel shape (0: default); padding = stored / actual
+ * blocks; max_rel_err (may be NULL) = max |y32 - y64| / max |y64| against the fp64 product with the present rhs as x */
+int ifem_insim_bench_spmv_uu_sell(ifem_insim *s, int precision, int variant, int reps, double *ms_per_apply,
+                                  double *bytes_per_apply, double *padding, double *max_rel_err);
 int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms_per_assembly);
 /* n_steps calls of run_one_step bracketed by CUDA events on the library's stream; total device ms */
 int ifem_insim_bench_steps(ifem_insim *s, int n_steps, int first_applies_nonzero_constraints, double *ms_total);

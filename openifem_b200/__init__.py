@@ -335,10 +335,11 @@ class _InsIM:
     def set_inner_variant(self, variant):
         check(lib().ifem_insim_set_inner_variant(self._h, C.c_int(variant)))
 
-    def bench_spmv_uu_sell(self, reps, variant=0, check_error=True):
-        """(ms, algorithmic bytes, padding ratio, max rel. error vs the fp64 product) of the fp32 SELL-32 product kernel"""
+    def bench_spmv_uu_sell(self, reps, variant=0, check_error=True, precision=0):
+        """(ms, algorithmic bytes, padding ratio, max rel. error vs the fp64 product) of the SELL-32 product kernel of the
+        fp32 inner solver; precision = storage of the matrix values (32, 16; 0 = as built)"""
         ms, b, pad, err = C.c_double(), C.c_double(), C.c_double(), C.c_double(-1.0)
-        check(lib().ifem_insim_bench_spmv_uu_sell(self._h, C.c_int(variant), C.c_int(reps), C.byref(ms), C.byref(b), C.byref(pad),
+        check(lib().ifem_insim_bench_spmv_uu_sell(self._h, C.c_int(precision), C.c_int(variant), C.c_int(reps), C.byref(ms), C.byref(b), C.byref(pad),
                                                   C.byref(err) if check_error else None))
         return ms.value, b.value, pad.value, err.value
 

@@ -580,11 +580,14 @@ int ifem_insim_bench_spmv_uu_fp32(ifem_insim *s, int reps, double *ms, double *b
     *bytes = m.fs.A_uu.spmv_bytes() - 4.0 * m.fs.A_uu.nnz();
   });
 }
-int ifem_insim_bench_spmv_uu_sell(ifem_insim *s, int variant, int reps, double *ms, double *bytes, double *padding, double *max_rel_err)
+int ifem_insim_bench_spmv_uu_sell(ifem_insim *s, int precision, int variant, int reps, double *ms, double *bytes, double *padding,
+                                  double *max_rel_err)
 {
   return guard([&] {
     InsIM &m = *s->s;
-    if (!m.inner32.S.built()) m.inner32.setup(m.ctx, m.fs.A_uu, m.fs.un, m.fs.n_ranks > 1 ? &m.fs.halo_u : nullptr);
+    if (precision == 0) precision = m.inner32.S.built() ? m.inner32.S.precision : 32;
+    if (!m.inner32.S.built() || m.inner32.S.precision != precision)
+      m.inner32.setup(m.ctx, m.fs.A_uu, m.fs.un, m.fs.n_ranks > 1 ? &m.fs.halo_u : nullptr, precision);
     m.inner32.refresh(m.ctx, m.fs.A_uu, nullptr);
     const int keep = m.inner32.variant;
     if (variant > 0) m.inner32.variant = variant;

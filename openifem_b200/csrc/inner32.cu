@@ -1,5 +1,7 @@
 #include "inner32.h"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -145,6 +147,100 @@ namespace ifem
       for (int r = 0; r < BS; ++r) yp[r] = acc[r];
     }
 
+    __device__ __forceinline__ int2 ld_cs_ordered(const int2 *p)
+    {
+      int2 v;
+      asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+      return v;
+    }
+    __device__ __forceinline__ float2 ld_cs_half2(const __half2 *p)
+    {
+      unsigned int v;
+      asm volatile("ld.global.cs.b32 %0, [%1];" : "=r"(v) : "l"(p));
+      return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+    }
+
+    // fp16 storage: the values of a row are scaled by 1 / max|row| (per scalar row) and stored as half2 = two
+    // consecutive block slots of the same row, so a warp still reads full 128-byte lines; the column indices of
+    // the two slots travel as one int2. 22 instead of 40 bytes per block; products and sums in fp32.
+    template <int BS, int NS, int MINB>
+    __global__ void __launch_bounds__(kT, MINB)
+    sell_spmv_h_kernel(int n_slices, const int *__restrict__ hoff, const int2 *__restrict__ col2, const __half2 *__restrict__ valh,
+                       const float *__restrict__ row_scale, const float4 *__restrict__ x4, float *__restrict__ y)
+    {
+      constexpr int RC = BS * BS;
+      const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+      const int lane = threadIdx.x & 31;
+      if (warp >= n_slices) return;
+      const int h0 = hoff[warp];
+      const int L = hoff[warp + 1] - h0; // double slots
+      const int2 *cp = col2 + (int64_t)h0 * 32 + lane;
+      const __half2 *vp = valh + (int64_t)h0 * (RC * 32) + lane;
+      float acc[BS];
+#pragma unroll
+      for (int r = 0; r < BS; ++r) acc[r] = 0.0f;
+      int2 cn[NS];
+#pragma unroll
+      for (int u = 0; u < NS; ++u) cn[u] = ld_cs_ordered(cp + u * 32);
+      int j = 0;
+      for (; j + NS <= L; j += NS)
+        {
+          float2 a[NS][RC];
+#pragma unroll
+          for (int u = 0; u < NS; ++u)
+#pragma unroll
+            for (int k = 0; k < RC; ++k) a[u][k] = ld_cs_half2(vp + (size_t)(u * RC + k) * 32);
+          vp += (size_t)NS * RC * 32;
+          int2 c[NS];
+#pragma unroll
+          for (int u = 0; u < NS; ++u) c[u] = cn[u];
+          cp += NS * 32;
+#pragma unroll
+          for (int u = 0; u < NS; ++u) cn[u] = ld_cs_ordered(cp + u * 32);
+          float4 xa[NS], xb[NS];
+#pragma unroll
+          for (int u = 0; u < NS; ++u)
+            {
+              xa[u] = ld_nc_ordered(x4 + c[u].x);
+              xb[u] = ld_nc_ordered(x4 + c[u].y);
+            }
+#pragma unroll
+          for (int u = 0; u < NS; ++u)
+            {
+              const float xs[4] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w}, xt[4] = {xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+#pragma unroll
+              for (int r = 0; r < BS; ++r)
+#pragma unroll
+                for (int cc = 0; cc < BS; ++cc)
+                  {
+                    acc[r] = fmaf(a[u][r * BS + cc].x, xs[cc], acc[r]);
+                    acc[r] = fmaf(a[u][r * BS + cc].y, xt[cc], acc[r]);
+                  }
+            }
+        }
+#pragma unroll
+      for (int u = 0; u < NS - 1; ++u)
+        if (j + u < L)
+          {
+            float2 a[RC];
+#pragma unroll
+            for (int k = 0; k < RC; ++k) a[k] = ld_cs_half2(vp + (size_t)(u * RC + k) * 32);
+            const float4 xq = ld_nc_ordered(x4 + cn[u].x), xw = ld_nc_ordered(x4 + cn[u].y);
+            const float xs[4] = {xq.x, xq.y, xq.z, xq.w}, xt[4] = {xw.x, xw.y, xw.z, xw.w};
+#pragma unroll
+            for (int r = 0; r < BS; ++r)
+#pragma unroll
+              for (int cc = 0; cc < BS; ++cc)
+                {
+                  acc[r] = fmaf(a[r * BS + cc].x, xs[cc], acc[r]);
+                  acc[r] = fmaf(a[r * BS + cc].y, xt[cc], acc[r]);
+                }
+          }
+      const int64_t self = (int64_t)warp * 32 + lane;
+#pragma unroll
+      for (int r = 0; r < BS; ++r) y[self * BS + r] = acc[r] * row_scale[self * BS + r];
+    }
+
     // ---------------------------------------------------------------------------
     // building the copy
     // ---------------------------------------------------------------------------
@@ -194,6 +290,79 @@ namespace ifem
         }
       int *cp = col + (int64_t)s0 * 32 + lane;
       for (int j = 0; j < L; ++j) cp[j * 32] = j < nb ? pos[acol[base + j]] : self; // padding: value 0 times own x
+    }
+
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    sell_fill_valh_kernel(int n_slices, const int *__restrict__ hoff, const int *__restrict__ perm_row,
+                          const int64_t *__restrict__ rowptr, const double *__restrict__ aval, __half2 *__restrict__ valh,
+                          float *__restrict__ row_scale)
+    {
+      constexpr int RC = BS * BS;
+      const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+      const int lane = threadIdx.x & 31;
+      if (warp >= n_slices) return;
+      const int h0 = hoff[warp];
+      const int L = hoff[warp + 1] - h0;
+      const int64_t self = (int64_t)warp * 32 + lane;
+      const int row = perm_row[self];
+      int64_t base = 0;
+      int nb = 0;
+      if (row >= 0)
+        {
+          base = rowptr[row];
+          nb = (int)(rowptr[row + 1] - base);
+        }
+      const double *av = aval + base * RC;
+      double inv[BS];
+#pragma unroll
+      for (int r = 0; r < BS; ++r)
+        {
+          double m = 0.0;
+          for (int cc = 0; cc < BS; ++cc)
+            for (int j = 0; j < nb; ++j) m = fmax(m, fabs(av[(int64_t)(r * BS + cc) * nb + j]));
+          row_scale[self * BS + r] = (float)m;
+          inv[r] = m > 0.0 ? 1.0 / m : 0.0;
+        }
+      __half2 *vp = valh + (int64_t)h0 * (RC * 32) + lane;
+      for (int k = 0; k < RC; ++k)
+        {
+          const double sc = inv[k / BS];
+          for (int jj = 0; jj < L; ++jj)
+            {
+              const int j0 = 2 * jj, j1 = 2 * jj + 1;
+              const float lo = j0 < nb ? (float)(av[(int64_t)k * nb + j0] * sc) : 0.0f;
+              const float hi = j1 < nb ? (float)(av[(int64_t)k * nb + j1] * sc) : 0.0f;
+              vp[(jj * RC + k) * 32] = __floats2half2_rn(lo, hi);
+            }
+        }
+    }
+
+    __global__ void __launch_bounds__(kT)
+    sell_fill_col2_kernel(int n_slices, const int *__restrict__ hoff, const int *__restrict__ perm_row,
+                          const int64_t *__restrict__ rowptr, const int *__restrict__ acol, const int *__restrict__ pos,
+                          int2 *__restrict__ col2)
+    {
+      const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+      const int lane = threadIdx.x & 31;
+      if (warp >= n_slices) return;
+      const int h0 = hoff[warp];
+      const int L = hoff[warp + 1] - h0;
+      const int self = warp * 32 + lane;
+      const int row = perm_row[self];
+      int64_t base = 0;
+      int nb = 0;
+      if (row >= 0)
+        {
+          base = rowptr[row];
+          nb = (int)(rowptr[row + 1] - base);
+        }
+      int2 *cp = col2 + (int64_t)h0 * 32 + lane;
+      for (int jj = 0; jj < L; ++jj)
+        {
+          const int j0 = 2 * jj, j1 = 2 * jj + 1;
+          cp[jj * 32] = make_int2(j0 < nb ? pos[acol[base + j0]] : self, j1 < nb ? pos[acol[base + j1]] : self);
+        }
     }
 
     // binv32[k][i] = binv[perm_row[i]][k]
@@ -423,8 +592,10 @@ namespace ifem
     if (h_results) cudaFreeHost(h_results);
   }
 
-  void InnerSolver32::setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo_)
+  void InnerSolver32::setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo_, int precision)
   {
+    if (precision != 32 && precision != 16) throw std::runtime_error("InnerSolver32: precision must be 32 or 16");
+    S.precision = precision;
     if (A.R != A.C || (A.R != 2 && A.R != 3)) throw std::runtime_error("InnerSolver32: square 2x2 / 3x3 blocks required");
     const int dim = nodes.dim;
     if (const char *e = std::getenv("IFEM_SELL_VARIANT")) variant = std::atoi(e);
@@ -476,7 +647,7 @@ namespace ifem
 
     S.n_slices = (n + 31) / 32;
     S.n_pad = S.n_slices * 32;
-    std::vector<int> perm((size_t)S.n_pad, -1), off((size_t)S.n_slices + 1, 0);
+    std::vector<int> perm((size_t)S.n_pad, -1), off((size_t)S.n_slices + 1, 0), hoff((size_t)S.n_slices + 1, 0);
     S.h_pos.assign((size_t)S.n_cols, 0);
     S.n_blocks = 0;
     for (int i = 0; i < n; ++i)
@@ -498,23 +669,48 @@ namespace ifem
         slots += L;
         if (slots > INT32_MAX) throw std::runtime_error("InnerSolver32: too many block slots for 32-bit slice offsets");
         off[sl + 1] = (int)slots;
+        hoff[sl + 1] = hoff[sl] + (int)((L + 1) / 2);
       }
     S.n_slots = slots;
+    S.n_hslots = hoff[S.n_slices];
     keys.clear();
     keys.shrink_to_fit();
 
     S.slice_off.upload(off, ctx.stream);
     S.perm_row.upload(perm, ctx.stream);
     S.pos.upload(S.h_pos, ctx.stream);
-    S.col.alloc((size_t)S.n_slots * 32 + 32 * 8); // slack: the pipelined kernel prefetches up to 8 slots past a slice
-    S.col.zero(ctx.stream);
-    S.val.alloc((size_t)S.n_slots * 32 * S.bs * S.bs);
     const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
-    if (S.n_slices)
+    S.col.release();
+    S.val.release();
+    S.col2.release();
+    S.valh.release();
+    S.row_scale.release();
+    if (precision == 32)
       {
-        sell_fill_col_kernel<<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.col.p, S.pos.p, S.col.p);
-        IFEM_KERNEL_CHECK();
-        ctx.kernel_launches++;
+        S.col.alloc((size_t)S.n_slots * 32 + 32 * 8); // slack: the pipelined kernel prefetches up to 8 slots past a slice
+        S.col.zero(ctx.stream);
+        S.val.alloc((size_t)S.n_slots * 32 * S.bs * S.bs);
+        if (S.n_slices)
+          {
+            sell_fill_col_kernel<<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.col.p, S.pos.p, S.col.p);
+            IFEM_KERNEL_CHECK();
+            ctx.kernel_launches++;
+          }
+      }
+    else
+      {
+        S.hoff.upload(hoff, ctx.stream);
+        S.col2.alloc(((size_t)S.n_hslots * 32 + 32 * 8) * 2);
+        S.col2.zero(ctx.stream);
+        S.valh.alloc((size_t)S.n_hslots * 32 * S.bs * S.bs);
+        S.row_scale.alloc((size_t)S.n_pad * S.bs);
+        if (S.n_slices)
+          {
+            sell_fill_col2_kernel<<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.hoff.p, S.perm_row.p, A.rowptr.p, A.col.p, S.pos.p,
+                                                              reinterpret_cast<int2 *>(S.col2.p));
+            IFEM_KERNEL_CHECK();
+            ctx.kernel_launches++;
+          }
       }
 
     // ---- vectors ----
@@ -556,7 +752,15 @@ namespace ifem
   {
     if (!S.built()) throw std::runtime_error("InnerSolver32::refresh before setup");
     const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
-    if (S.bs == 3)
+    if (S.precision == 16)
+      {
+        __half2 *vh = reinterpret_cast<__half2 *>(S.valh.p);
+        if (S.bs == 3)
+          sell_fill_valh_kernel<3><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.hoff.p, S.perm_row.p, A.rowptr.p, A.val.p, vh, S.row_scale.p);
+        else
+          sell_fill_valh_kernel<2><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.hoff.p, S.perm_row.p, A.rowptr.p, A.val.p, vh, S.row_scale.p);
+      }
+    else if (S.bs == 3)
       sell_fill_val_kernel<3><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.val.p, S.val.p);
     else
       sell_fill_val_kernel<2><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.val.p, S.val.p);
@@ -574,6 +778,29 @@ namespace ifem
   {
     const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
     const float4 *xp = reinterpret_cast<const float4 *>(x4);
+    if (S.precision == 16)
+      {
+        const int2 *c2 = reinterpret_cast<const int2 *>(S.col2.p);
+        const __half2 *vh = reinterpret_cast<const __half2 *>(S.valh.p);
+#define IFEM_SELL_H(B, NS, M) \
+  sell_spmv_h_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.hoff.p, c2, vh, S.row_scale.p, xp, y)
+        if (S.bs == 3)
+          switch (variant)
+            {
+            case 13: IFEM_SELL_H(3, 1, 3); break;
+            case 16: IFEM_SELL_H(3, 1, 6); break;
+            case 23: IFEM_SELL_H(3, 2, 3); break;
+            case 26: IFEM_SELL_H(3, 2, 6); break;
+            case 43: IFEM_SELL_H(3, 4, 3); break;
+            default: IFEM_SELL_H(3, 2, 4); break; // 24
+            }
+        else
+          IFEM_SELL_H(2, 2, 4);
+#undef IFEM_SELL_H
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+        return;
+      }
 #define IFEM_SELL_LAUNCH(B, U) \
   sell_spmv_kernel<B, U><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.col.p, S.val.p, xp, y)
 #define IFEM_SELL_PIPE(B, NS, M) \

@@ -31,18 +31,33 @@ namespace ifem
     int n_rows = 0;              // owned block rows (= rows of a product)
     int n_cols = 0;              // local block columns (owned + ghosts)
     int n_slices = 0, n_pad = 0; // n_pad = 32 * n_slices >= n_rows
+    int precision = 32;          // storage of the matrix values: 32 = float, 16 = row-scaled half
     int64_t n_slots = 0;         // sum of slice lengths
+    int64_t n_hslots = 0;        // sum of ceil(slice length / 2): double slots of the fp16 storage
     int64_t n_blocks = 0;        // blocks of the owned rows (unpadded)
     DevBuf<int> slice_off;       // [n_slices + 1]
     DevBuf<int> perm_row;        // [n_pad] original block row of a SELL row, -1 = padding row
     DevBuf<int> pos;             // [n_cols] SELL position of an original node (ghosts: n_pad + ghost no.)
     DevBuf<int> col;             // [n_slots * 32] SELL position of the column node
     DevBuf<float> val;           // [n_slots * bs * bs * 32]
+    // fp16 storage: half2 = two consecutive slots of a row, int2 = their column indices, one scale per scalar row
+    DevBuf<int> hoff;            // [n_slices + 1] double-slot offsets
+    DevBuf<int> col2;            // [n_hslots * 32] int2
+    DevBuf<unsigned int> valh;   // [n_hslots * bs * bs * 32] half2
+    DevBuf<float> row_scale;     // [n_pad * bs]
     std::vector<int> h_pos;
     bool built() const { return n_slices > 0; }
     // bytes one product has to move: values + column index + slice offsets, x (float4) read once, y written once
-    double spmv_bytes() const { return 4.0 * n_blocks * bs * bs + 4.0 * n_blocks + 4.0 * (n_slices + 1) + 16.0 * n_cols + 4.0 * bs * n_rows; }
-    double padding() const { return n_blocks ? double(n_slots) * 32.0 / double(n_blocks) : 1.0; }
+    double spmv_bytes() const
+    {
+      const double per_value = precision == 16 ? 2.0 : 4.0, scales = precision == 16 ? 4.0 * bs * n_rows : 0.0;
+      return per_value * n_blocks * bs * bs + 4.0 * n_blocks + 4.0 * (n_slices + 1) + 16.0 * n_cols + 4.0 * bs * n_rows + scales;
+    }
+    double padding() const
+    {
+      if (!n_blocks) return 1.0;
+      return (precision == 16 ? 2.0 * double(n_hslots) : double(n_slots)) * 32.0 / double(n_blocks);
+    }
   };
 
   class InnerSolver32
@@ -50,7 +65,8 @@ namespace ifem
   public:
     ~InnerSolver32();
     // pattern-only work, once per sparsity pattern: row order, slices, column map, halo plan in SELL numbering
-    void setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo);
+    // precision: 32 (float values) or 16 (half values scaled per scalar row)
+    void setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo, int precision = 32);
     // values of A and of the inverted diagonal blocks (row-major bs x bs per node) -> fp32, every solve
     void refresh(Context &ctx, const Bcsr &A, const double *binv);
     // dst ~= A^-1 src to |r| <= rel_tol * |src| (recurrence residual), x0 = 0; src_norm = |src| over all ranks

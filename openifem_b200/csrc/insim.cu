@@ -176,7 +176,7 @@ namespace ifem
       };
       LinOp jac = [&](const double *x, double *y) { block_diag_apply(ctx, fs.n_owned_unodes, fs.dim, d_binv.p, x, y); };
       const double unrm = nrm2(ctx, vu, utmp);
-      const SolveResult r = control.a_inv_fp32 == 2
+      const SolveResult r = control.a_inv_fp32 >= 2
                               ? inner32.solve(ctx, utmp, unrm, dst_u, control.a_inv_rel, control.a_inv_max_it)
                               : bicgstab(ctx, vu, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);
       cur.a_inv_its += r.iterations;
@@ -205,9 +205,11 @@ namespace ifem
         fs.schur_valid = true;
       }
     block_diag_inverse(ctx, fs.A_uu, d_binv.p);
-    if (control.a_inv_fp32 == 2)
+    if (control.a_inv_fp32 >= 2)
       {
-        if (!inner32.S.built()) inner32.setup(ctx, fs.A_uu, fs.un, fs.n_ranks > 1 ? &fs.halo_u : nullptr);
+        const int precision = control.a_inv_fp32 == 3 ? 16 : 32;
+        if (!inner32.S.built() || inner32.S.precision != precision)
+          inner32.setup(ctx, fs.A_uu, fs.un, fs.n_ranks > 1 ? &fs.halo_u : nullptr, precision);
         inner32.refresh(ctx, fs.A_uu, d_binv.p);
       }
     else if (control.a_inv_fp32 == 1)

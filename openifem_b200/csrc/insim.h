@@ -67,7 +67,8 @@ namespace ifem
     double a_inv_rel = 1e-3;
     int a_inv_max_it = 2000;
     // 0: fp64 BiCGStab on the BCSR matrix; 1: same, A_uu streamed as fp32; 2: fp32 BiCGStab on the sliced copy of
-    // A_uu (inner32.h). Legal because FGMRES is flexible; operator, residuals and Krylov basis stay fp64
+    // A_uu (inner32.h); 3: as 2 with the matrix values of the copy stored as row-scaled fp16. Legal because FGMRES
+    // is flexible; operator, residuals and Krylov basis stay fp64
     int a_inv_fp32 = 0;
     int basis_size = 30;
     static InsSolverControl serial()

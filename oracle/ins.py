@@ -301,6 +301,11 @@ class InsIM:
             a_inverse = lambda v: lu.solve(v)
         else:
             _, rel, max_it = self.a_inv
+            # a_inv_filter: optional perturbation of the matrix the INNER solve sees (experiments with reduced-precision
+            # copies of A_uu inside the preconditioner; the operator of FGMRES is never touched)
+            filt = getattr(self, "a_inv_filter", None)
+            if filt is not None:
+                Auu = filt(Auu).tocsr()
             A_op = CsrOp(Auu)
             dim = self.dim
             # block-Jacobi: invert the dim x dim diagonal block of every velocity node

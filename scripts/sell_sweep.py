@@ -22,17 +22,22 @@ print(f"setup {time.perf_counter() - t0:.1f} s", flush=True)
 flow.bench_spmv_uu(3)
 ms, b = flow.bench_spmv_uu(10)
 print(f"f64 BCSR  {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s", flush=True)
-t0 = time.perf_counter()
-best = (1e9, 0)
-for k, v in enumerate([24, 1, 2, 4, 13, 16, 23, 26, 42, 43, 24]):
-    ms, b, pad, err = flow.bench_spmv_uu_sell(20, variant=v, check_error=(k < 2))
-    if k == 0:
-        print(f"SELL setup + first product {time.perf_counter() - t0:.1f} s, padding {pad:.4f}", flush=True)
-    print(f"sell variant {v:3d}  {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s  err {err:.2e}", flush=True)
-    best = min(best, (ms, v))
+mode = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+best = {}
+for prec, variants in [(32, [24, 13]), (16, [24, 13, 16, 23, 26, 43, 24])]:
+    if mode == 2 and prec == 16:
+        continue
+    t0 = time.perf_counter()
+    best[prec] = (1e9, 0)
+    for k, v in enumerate(variants):
+        ms, b, pad, err = flow.bench_spmv_uu_sell(20, variant=v, check_error=(k == 0), precision=prec)
+        if k == 0:
+            print(f"SELL({prec}) setup + first product {time.perf_counter() - t0:.1f} s, padding {pad:.4f}", flush=True)
+        print(f"sell{prec} variant {v:3d}  {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s  err {err:.2e}", flush=True)
+        best[prec] = min(best[prec], (ms, v))
 print("best", best, flush=True)
-flow.set_inner_variant(best[1])
-flow.set_control(a_inv_rel=1e-1, a_inv_fp32=2)
+flow.set_inner_variant(best[16 if mode == 3 else 32][1])
+flow.set_control(a_inv_rel=1e-1, a_inv_fp32=mode)
 flow.set_verbose(True)
 for k in range(steps):
     t0 = time.perf_counter()

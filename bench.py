@@ -182,7 +182,7 @@ def run_ours(args):
     flow = ifem.Fluid.MPI.InsIM(tria, params)
     flow.setup()
     # fp32 inner solver on the SELL-32 copy of A_uu with row-scaled fp16 matrix values (preconditioner only)
-    flow.set_control(a_inv_rel=1e-1, a_inv_fp32=args.inner_mode)
+    flow.set_control(a_inv_rel=1e-1, a_inv_fp32=args.inner_mode, cg_sm_fp32=args.sm_mode)
     barrier()
     t_setup = time.perf_counter() - t_setup
     n_u, n_p, nnz_local, _, _ = flow.sizes()
@@ -267,6 +267,8 @@ def run_ours(args):
                              2: "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1 in fp32 on a sliced-ELL (SELL-32) copy of A_uu",
                              3: "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1 in fp32 on a sliced-ELL (SELL-32) copy of A_uu "
                                 "whose values are stored as row-scaled fp16"}[args.inner_mode]
+                            + {0: "; CG for Sm in fp64", 1: "; CG for Sm in fp32 on a SELL-32 copy of S_m",
+                               2: "; CG for Sm in fp32 on a SELL-32 copy of S_m with row-scaled fp16 values"}[args.sm_mode]
                             + "; inside the preconditioner only - FGMRES operator, residuals and basis are fp64, Newton/FGMRES "
                               "iteration counts and converged fields equal the fp64 path's (tests/test_inner32_gpu.py: 1e-6 vs oracle)",
                    "parallelism": f"{world} z-slab(s), one rank per GPU; NCCL: ghost halos + dot-product all-reduces only",
@@ -300,6 +302,8 @@ def main():
     ap.add_argument("--cells", type=int, default=128, help="cells per direction (config 3 = 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sm-mode", type=int, default=2, choices=[0, 1, 2],
+                    help="'CG for Sm': 0 fp64 CG on CSR, 1 fp32 CG on SELL-32, 2 fp32 CG on fp16 SELL-32 values")
     ap.add_argument("--inner-mode", type=int, default=3, choices=[0, 1, 2, 3],
                     help="A~^-1 inner solve: 0 fp64 BCSR, 1 fp32-streamed BCSR, 2 fp32 SELL-32, 3 fp32 solver on fp16 SELL-32 values")
     args = ap.parse_args()

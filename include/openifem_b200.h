@@ -82,6 +82,8 @@ typedef struct
   int a_inv_fp32;     /* inner solve: 0 fp64; 1 fp64 BiCGStab, A_uu streamed as fp32; 2 fp32 BiCGStab on the sliced (SELL-32)
                          copy of A_uu; 3 as 2, matrix values of the copy stored as row-scaled fp16. Preconditioner only -
                          operator, residuals and FGMRES basis stay fp64 */
+  int cg_sm_fp32;     /* "CG for Sm" (mpi_insim.cpp:88-109): 0 fp64 CG on the CSR matrix; 1 fp32 CG on a SELL-32 copy of S_m;
+                         2 as 1 with row-scaled fp16 matrix values. Preconditioner only, as above */
 } ifem_ins_control;
 
 typedef struct
@@ -227,6 +229,10 @@ int ifem_insim_bench_vmult(ifem_insim *s, int reps, double *ms_per_apply, double
 int ifem_insim_bench_spmv_uu(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
 /* fp32-streamed copy of A_uu (inner solve only) */
 int ifem_insim_bench_spmv_uu_fp32(ifem_insim *s, int reps, double *ms_per_apply, double *bytes_per_apply);
+/* "CG for Sm" on its own (test hook): x = S_m^-1 b to rel_tol * |b| in cg_sm_fp32 mode 0 / 1 / 2; b, x host vectors of
+ * the local pressure size. S_m must exist (ifem_insim_solve has run) */
+int ifem_insim_solve_mass_schur(ifem_insim *s, int mode, const double *b, double rel_tol, int max_it, double *x, int *its,
+                                double *residual);
 /* product kernel the fp32 inner solver uses from now on (tuning hook; see InnerSolver32::spmv for the encoding) */
 int ifem_insim_set_inner_variant(ifem_insim *s, int variant);
 /* the product kernel of the fp32 inner solver on the sliced (SELL-32) copy of A_uu (a_inv_fp32 = 2 / 3); precision = 32

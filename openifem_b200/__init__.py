@@ -332,6 +332,15 @@ class _InsIM:
         check(lib().ifem_insim_bench_spmv_uu_fp32(self._h, C.c_int(reps), C.byref(ms), C.byref(b)))
         return ms.value, b.value
 
+    def solve_mass_schur(self, b, mode=0, rel_tol=1e-3, max_it=100000):
+        """'CG for Sm' on its own: (x, iterations, residual) with S_m x = b in cg_sm_fp32 mode 0 / 1 / 2"""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        its, res = C.c_int(), C.c_double()
+        check(lib().ifem_insim_solve_mass_schur(self._h, C.c_int(mode), dptr(b), C.c_double(rel_tol), C.c_int(max_it), dptr(x),
+                                                C.byref(its), C.byref(res)))
+        return x, its.value, res.value
+
     def set_inner_variant(self, variant):
         check(lib().ifem_insim_set_inner_variant(self._h, C.c_int(variant)))
 

@@ -330,6 +330,7 @@ int ifem_insim_default_control(int serial_twin, ifem_ins_control *out)
     out->a_inv_max_it = c.a_inv_max_it;
     out->basis_size = c.basis_size;
     out->a_inv_fp32 = c.a_inv_fp32;
+    out->cg_sm_fp32 = c.cg_sm_fp32;
   });
 }
 int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
@@ -345,6 +346,7 @@ int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
     k.a_inv_max_it = c->a_inv_max_it;
     k.basis_size = c->basis_size;
     k.a_inv_fp32 = c->a_inv_fp32;
+    k.cg_sm_fp32 = c->cg_sm_fp32;
   });
 }
 int ifem_insim_set_verbose(ifem_insim *s, int verbose)
@@ -589,12 +591,12 @@ int ifem_insim_bench_spmv_uu_sell(ifem_insim *s, int precision, int variant, int
     if (!m.inner32.S.built() || m.inner32.S.precision != precision)
       m.inner32.setup(m.ctx, m.fs.A_uu, m.fs.un, m.fs.n_ranks > 1 ? &m.fs.halo_u : nullptr, precision);
     m.inner32.refresh(m.ctx, m.fs.A_uu, nullptr);
-    const int keep = m.inner32.variant;
-    if (variant > 0) m.inner32.variant = variant;
+    const int keep = m.inner32.S.variant;
+    if (variant > 0) m.inner32.S.variant = variant;
     m.inner32.probe_load(m.ctx, m.fs.rhs.p);
     for (int i = 0; i < 2; ++i) m.inner32.probe_apply(m.ctx);
     *ms = time_reps(m.ctx, reps, [&] { m.inner32.probe_apply(m.ctx); });
-    m.inner32.variant = keep;
+    m.inner32.S.variant = keep;
     *bytes = m.inner32.S.spmv_bytes();
     if (padding) *padding = m.inner32.S.padding();
     if (max_rel_err)
@@ -613,9 +615,25 @@ int ifem_insim_bench_spmv_uu_sell(ifem_insim *s, int precision, int variant, int
       }
   });
 }
+int ifem_insim_solve_mass_schur(ifem_insim *s, int mode, const double *b, double rel_tol, int max_it, double *x, int *its, double *residual)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    if (!m.fs.schur_valid) throw std::runtime_error("solve_mass_schur: S_m has not been formed yet (call solve first)");
+    const size_t n = (size_t)m.fs.n_p;
+    DevBuf<double> db(n), dx(n);
+    db.upload(b, n, m.ctx.stream);
+    dx.zero(m.ctx.stream);
+    const double nrm = nrm2(m.ctx, m.fs.vs_p, db.p);
+    const SolveResult r = m.solve_mass_schur(mode, db.p, nrm, dx.p, rel_tol * nrm, max_it);
+    dx.download(x, n, m.ctx.stream);
+    if (its) *its = r.iterations;
+    if (residual) *residual = r.residual;
+  });
+}
 int ifem_insim_set_inner_variant(ifem_insim *s, int variant)
 {
-  s->s->inner32.variant = variant;
+  s->s->inner32.S.variant = variant;
   return IFEM_OK;
 }
 int ifem_insim_bench_assemble(ifem_insim *s, int reps, double *ms)

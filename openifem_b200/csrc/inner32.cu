@@ -16,47 +16,8 @@ namespace ifem
   {
     constexpr int kT = 256;
 
-    // ---------------------------------------------------------------------------
-    // y = A32 x. One warp per slice, one lane per block row; per block slot a warp issues one coalesced load of
-    // 32 column indices, one 16-byte gather per lane and bs*bs coalesced 128-byte loads of matrix values. The
-    // matrix stream is read once (ld.global.cs: evict first), x stays in L1/L2.
-    // ---------------------------------------------------------------------------
-    template <int BS, int UNROLL>
-    __global__ void __launch_bounds__(kT)
-    sell_spmv_kernel(int n_slices, const int *__restrict__ slice_off, const int *__restrict__ col, const float *__restrict__ val,
-                     const float4 *__restrict__ x4, float *__restrict__ y)
-    {
-      const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-      const int lane = threadIdx.x & 31;
-      if (warp >= n_slices) return;
-      const int s0 = slice_off[warp];
-      const int L = slice_off[warp + 1] - s0;
-      const int *cp = col + (int64_t)s0 * 32 + lane;
-      const float *vp = val + (int64_t)s0 * (BS * BS * 32) + lane;
-      float acc[BS];
-#pragma unroll
-      for (int r = 0; r < BS; ++r) acc[r] = 0.0f;
-#pragma unroll UNROLL
-      for (int j = 0; j < L; ++j)
-        {
-          const int c = __ldcs(cp + j * 32);
-          float a[BS * BS];
-#pragma unroll
-          for (int k = 0; k < BS * BS; ++k) a[k] = __ldcs(vp + (j * BS * BS + k) * 32);
-          const float4 xv = __ldg(x4 + c);
-          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-          for (int r = 0; r < BS; ++r)
-#pragma unroll
-            for (int cc = 0; cc < BS; ++cc) acc[r] = fmaf(a[r * BS + cc], xs[cc], acc[r]);
-        }
-      float *yp = y + ((int64_t)warp * 32 + lane) * BS;
-#pragma unroll
-      for (int r = 0; r < BS; ++r) yp[r] = acc[r];
-    }
-
-    // Loads with a fixed issue order (volatile asm keeps its order): the compiler otherwise caps the kernel at 32
-    // registers and interleaves loads with the FFMA chain, which leaves too few bytes in flight per warp.
+    // Loads of the product kernels as explicit PTX: matrix values and column indices are read once
+    // (ld.global.cs = evict first), x gathers go through the read-only path and stay in L1 / L2.
     __device__ __forceinline__ float ld_cs_ordered(const float *p)
     {
       float v;
@@ -69,23 +30,60 @@ namespace ifem
       asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
       return v;
     }
-    __device__ __forceinline__ float4 ld_nc_ordered(const float4 *p)
+    __device__ __forceinline__ int2 ld_cs_ordered(const int2 *p)
     {
-      float4 v;
-      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+      int2 v;
+      asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
       return v;
     }
+    __device__ __forceinline__ float2 ld_cs_half2(const __half2 *p)
+    {
+      unsigned int v;
+      asm volatile("ld.global.cs.b32 %0, [%1];" : "=r"(v) : "l"(p));
+      return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+    }
 
-    // Software-pipelined form: NS block slots per step. All NS * bs*bs value loads of a step are issued first, then
-    // the column indices of the NEXT step (so the x gathers never wait for their index), then the NS gathers, then
-    // the FMAs: NS * (bs*bs + 1) + NS 128-byte lines in flight per warp.
-    // (col has 32 * NS ints of slack behind the last slice for the unconditional prefetch.)
+    // gather source: float4 per node for bs = 2, 3 (one 16-byte load), float per node for bs = 1
+    template <int BS>
+    struct XGather
+    {
+      using T = float4;
+      static __device__ __forceinline__ T load(const float *x, int c)
+      {
+        float4 v;
+        asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(reinterpret_cast<const float4 *>(x) + c));
+        return v;
+      }
+      static __device__ __forceinline__ float get(const T &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+    };
+    template <>
+    struct XGather<1>
+    {
+      using T = float;
+      static __device__ __forceinline__ T load(const float *x, int c)
+      {
+        float v;
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(x + c));
+        return v;
+      }
+      static __device__ __forceinline__ float get(const T &v, int) { return v; }
+    };
+
+    // ---------------------------------------------------------------------------
+    // y = A32 x. One warp per slice, one lane per block row; per block slot a warp issues one coalesced load of
+    // 32 column indices, one gather per lane and bs*bs coalesced 128-byte loads of matrix values.
+    // Software-pipelined: NS block slots per step. All NS * bs*bs value loads of a step are issued first, then the
+    // column indices of the NEXT step (so the x gathers never wait for their index), then the NS gathers, then the
+    // FMAs: NS * (bs*bs + 2) 128-byte lines in flight per warp.
+    // (col has slack behind the last slice for the unconditional prefetch.)
+    // ---------------------------------------------------------------------------
     template <int BS, int NS, int MINB>
     __global__ void __launch_bounds__(kT, MINB)
     sell_spmv_pipe_kernel(int n_slices, const int *__restrict__ slice_off, const int *__restrict__ col, const float *__restrict__ val,
-                          const float4 *__restrict__ x4, float *__restrict__ y)
+                          const float *__restrict__ x, float *__restrict__ y)
     {
       constexpr int RC = BS * BS;
+      using G = XGather<BS>;
       const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
       const int lane = threadIdx.x & 31;
       if (warp >= n_slices) return;
@@ -114,18 +112,15 @@ namespace ifem
           cp += NS * 32;
 #pragma unroll
           for (int u = 0; u < NS; ++u) cn[u] = ld_cs_ordered(cp + u * 32);
-          float4 xv[NS];
+          typename G::T xv[NS];
 #pragma unroll
-          for (int u = 0; u < NS; ++u) xv[u] = ld_nc_ordered(x4 + c[u]);
+          for (int u = 0; u < NS; ++u) xv[u] = G::load(x, c[u]);
 #pragma unroll
           for (int u = 0; u < NS; ++u)
-            {
-              const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
 #pragma unroll
-              for (int r = 0; r < BS; ++r)
+            for (int r = 0; r < BS; ++r)
 #pragma unroll
-                for (int cc = 0; cc < BS; ++cc) acc[r] = fmaf(a[u][r * BS + cc], xs[cc], acc[r]);
-            }
+              for (int cc = 0; cc < BS; ++cc) acc[r] = fmaf(a[u][r * BS + cc], G::get(xv[u], cc), acc[r]);
         }
       // tail: fewer than NS slots left, their column indices are already in cn[]
 #pragma unroll
@@ -135,40 +130,27 @@ namespace ifem
             float a[RC];
 #pragma unroll
             for (int k = 0; k < RC; ++k) a[k] = ld_cs_ordered(vp + (size_t)(u * RC + k) * 32);
-            const float4 xq = ld_nc_ordered(x4 + cn[u]);
-            const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+            const typename G::T xq = G::load(x, cn[u]);
 #pragma unroll
             for (int r = 0; r < BS; ++r)
 #pragma unroll
-              for (int cc = 0; cc < BS; ++cc) acc[r] = fmaf(a[r * BS + cc], xs[cc], acc[r]);
+              for (int cc = 0; cc < BS; ++cc) acc[r] = fmaf(a[r * BS + cc], G::get(xq, cc), acc[r]);
           }
       float *yp = y + ((int64_t)warp * 32 + lane) * BS;
 #pragma unroll
       for (int r = 0; r < BS; ++r) yp[r] = acc[r];
     }
 
-    __device__ __forceinline__ int2 ld_cs_ordered(const int2 *p)
-    {
-      int2 v;
-      asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-      return v;
-    }
-    __device__ __forceinline__ float2 ld_cs_half2(const __half2 *p)
-    {
-      unsigned int v;
-      asm volatile("ld.global.cs.b32 %0, [%1];" : "=r"(v) : "l"(p));
-      return __half22float2(*reinterpret_cast<const __half2 *>(&v));
-    }
-
     // fp16 storage: the values of a row are scaled by 1 / max|row| (per scalar row) and stored as half2 = two
     // consecutive block slots of the same row, so a warp still reads full 128-byte lines; the column indices of
-    // the two slots travel as one int2. 22 instead of 40 bytes per block; products and sums in fp32.
+    // the two slots travel as one int2. 22 instead of 40 bytes per 3x3 block; products and sums in fp32.
     template <int BS, int NS, int MINB>
     __global__ void __launch_bounds__(kT, MINB)
     sell_spmv_h_kernel(int n_slices, const int *__restrict__ hoff, const int2 *__restrict__ col2, const __half2 *__restrict__ valh,
-                       const float *__restrict__ row_scale, const float4 *__restrict__ x4, float *__restrict__ y)
+                       const float *__restrict__ row_scale, const float *__restrict__ x, float *__restrict__ y)
     {
       constexpr int RC = BS * BS;
+      using G = XGather<BS>;
       const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
       const int lane = threadIdx.x & 31;
       if (warp >= n_slices) return;
@@ -197,26 +179,23 @@ namespace ifem
           cp += NS * 32;
 #pragma unroll
           for (int u = 0; u < NS; ++u) cn[u] = ld_cs_ordered(cp + u * 32);
-          float4 xa[NS], xb[NS];
+          typename G::T xa[NS], xb[NS];
 #pragma unroll
           for (int u = 0; u < NS; ++u)
             {
-              xa[u] = ld_nc_ordered(x4 + c[u].x);
-              xb[u] = ld_nc_ordered(x4 + c[u].y);
+              xa[u] = G::load(x, c[u].x);
+              xb[u] = G::load(x, c[u].y);
             }
 #pragma unroll
           for (int u = 0; u < NS; ++u)
-            {
-              const float xs[4] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w}, xt[4] = {xb[u].x, xb[u].y, xb[u].z, xb[u].w};
 #pragma unroll
-              for (int r = 0; r < BS; ++r)
+            for (int r = 0; r < BS; ++r)
 #pragma unroll
-                for (int cc = 0; cc < BS; ++cc)
-                  {
-                    acc[r] = fmaf(a[u][r * BS + cc].x, xs[cc], acc[r]);
-                    acc[r] = fmaf(a[u][r * BS + cc].y, xt[cc], acc[r]);
-                  }
-            }
+              for (int cc = 0; cc < BS; ++cc)
+                {
+                  acc[r] = fmaf(a[u][r * BS + cc].x, G::get(xa[u], cc), acc[r]);
+                  acc[r] = fmaf(a[u][r * BS + cc].y, G::get(xb[u], cc), acc[r]);
+                }
         }
 #pragma unroll
       for (int u = 0; u < NS - 1; ++u)
@@ -225,15 +204,14 @@ namespace ifem
             float2 a[RC];
 #pragma unroll
             for (int k = 0; k < RC; ++k) a[k] = ld_cs_half2(vp + (size_t)(u * RC + k) * 32);
-            const float4 xq = ld_nc_ordered(x4 + cn[u].x), xw = ld_nc_ordered(x4 + cn[u].y);
-            const float xs[4] = {xq.x, xq.y, xq.z, xq.w}, xt[4] = {xw.x, xw.y, xw.z, xw.w};
+            const typename G::T xq = G::load(x, cn[u].x), xw = G::load(x, cn[u].y);
 #pragma unroll
             for (int r = 0; r < BS; ++r)
 #pragma unroll
               for (int cc = 0; cc < BS; ++cc)
                 {
-                  acc[r] = fmaf(a[r * BS + cc].x, xs[cc], acc[r]);
-                  acc[r] = fmaf(a[r * BS + cc].y, xt[cc], acc[r]);
+                  acc[r] = fmaf(a[r * BS + cc].x, G::get(xq, cc), acc[r]);
+                  acc[r] = fmaf(a[r * BS + cc].y, G::get(xw, cc), acc[r]);
                 }
           }
       const int64_t self = (int64_t)warp * 32 + lane;
@@ -242,7 +220,7 @@ namespace ifem
     }
 
     // ---------------------------------------------------------------------------
-    // building the copy
+    // building the copy (one warp per slice, one lane per row)
     // ---------------------------------------------------------------------------
     template <int BS>
     __global__ void __launch_bounds__(kT)
@@ -266,7 +244,7 @@ namespace ifem
       const double *av = aval + base * RC;
       float *vp = val + (int64_t)s0 * (RC * 32) + lane;
       for (int k = 0; k < RC; ++k)
-        for (int j = 0; j < L; ++j) vp[(j * RC + k) * 32] = j < nb ? (float)av[(int64_t)k * nb + j] : 0.0f;
+        for (int j = 0; j < L; ++j) vp[(size_t)(j * RC + k) * 32] = j < nb ? (float)av[(int64_t)k * nb + j] : 0.0f;
     }
 
     __global__ void __launch_bounds__(kT)
@@ -289,7 +267,7 @@ namespace ifem
           nb = (int)(rowptr[row + 1] - base);
         }
       int *cp = col + (int64_t)s0 * 32 + lane;
-      for (int j = 0; j < L; ++j) cp[j * 32] = j < nb ? pos[acol[base + j]] : self; // padding: value 0 times own x
+      for (int j = 0; j < L; ++j) cp[(size_t)j * 32] = j < nb ? pos[acol[base + j]] : self; // padding: value 0 times own x
     }
 
     template <int BS>
@@ -333,7 +311,7 @@ namespace ifem
               const int j0 = 2 * jj, j1 = 2 * jj + 1;
               const float lo = j0 < nb ? (float)(av[(int64_t)k * nb + j0] * sc) : 0.0f;
               const float hi = j1 < nb ? (float)(av[(int64_t)k * nb + j1] * sc) : 0.0f;
-              vp[(jj * RC + k) * 32] = __floats2half2_rn(lo, hi);
+              vp[(size_t)(jj * RC + k) * 32] = __floats2half2_rn(lo, hi);
             }
         }
     }
@@ -361,7 +339,7 @@ namespace ifem
       for (int jj = 0; jj < L; ++jj)
         {
           const int j0 = 2 * jj, j1 = 2 * jj + 1;
-          cp[jj * 32] = make_int2(j0 < nb ? pos[acol[base + j0]] : self, j1 < nb ? pos[acol[base + j1]] : self);
+          cp[(size_t)jj * 32] = make_int2(j0 < nb ? pos[acol[base + j0]] : self, j1 < nb ? pos[acol[base + j1]] : self);
         }
     }
 
@@ -580,30 +558,109 @@ namespace ifem
         }
     }
 
-    __global__ void __launch_bounds__(kT) halo_pack4_kernel(int n, const int *__restrict__ idx, const float4 *__restrict__ v, float4 *__restrict__ buf)
+    // pack the owned entries a neighbour needs: xs floats per node
+    __global__ void __launch_bounds__(kT) halo_pack32_kernel(int n, int xs, const int *__restrict__ idx, const float *__restrict__ v, float *__restrict__ buf)
     {
       const int t = blockIdx.x * blockDim.x + threadIdx.x;
-      if (t < n) buf[t] = v[idx[t]];
+      if (t < n * xs) buf[t] = v[(size_t)idx[t / xs] * xs + t % xs];
+    }
+
+    // ---------------------------------------------------------------------------
+    // fp32 CG on a scalar matrix, driven from device-resident scalars
+    // ---------------------------------------------------------------------------
+    struct CgState
+    {
+      double rr_cur, pAp, rr_new, beta, tol2, its, done;
+    };
+
+    // r = p = src / |src| in SELL order, x = 0; partial |r|^2
+    __global__ void __launch_bounds__(kT)
+    cg_init_kernel(int n_pad, const int *__restrict__ perm_row, const double *__restrict__ src, double scale, float *__restrict__ r,
+                   float *__restrict__ p, float *__restrict__ x, double *__restrict__ partials)
+    {
+      double acc[1] = {0.0};
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const int row = perm_row[i];
+          const float a = row >= 0 ? (float)(src[row] * scale) : 0.0f;
+          r[i] = a;
+          p[i] = a;
+          x[i] = 0.0f;
+          acc[0] += (double)a * (double)a;
+        }
+      block_reduce_store<1>(acc, partials);
+    }
+
+    __global__ void cg_start_kernel(CgState *st, double tol2)
+    {
+      st->rr_cur = st->rr_new;
+      st->tol2 = tol2;
+      st->its = 0.0;
+      st->beta = 0.0;
+      st->pAp = 1.0;
+      st->done = st->rr_cur <= tol2 ? 1.0 : 0.0;
+    }
+
+    __global__ void __launch_bounds__(kT)
+    cg_dot_kernel(int n_pad, const float *__restrict__ p, const float *__restrict__ ap, double *__restrict__ partials)
+    {
+      double acc[1] = {0.0};
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) acc[0] += (double)p[i] * (double)ap[i];
+      block_reduce_store<1>(acc, partials);
+    }
+
+    // x += alpha p; r -= alpha Ap; partial |r|^2   (alpha = rr / pAp from the device state)
+    __global__ void __launch_bounds__(kT)
+    cg_xr_kernel(int n_pad, const CgState *__restrict__ st, float *__restrict__ x, const float *__restrict__ p, float *__restrict__ r,
+                 const float *__restrict__ ap, double *__restrict__ partials)
+    {
+      if (st->done != 0.0) return;
+      const float alpha = (float)(st->rr_cur / st->pAp);
+      double acc[1] = {0.0};
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          x[i] = fmaf(alpha, p[i], x[i]);
+          const float rc = fmaf(-alpha, ap[i], r[i]);
+          r[i] = rc;
+          acc[0] += (double)rc * (double)rc;
+        }
+      block_reduce_store<1>(acc, partials);
+    }
+
+    __global__ void cg_advance_kernel(CgState *st)
+    {
+      if (st->done != 0.0) return;
+      const double rr_new = st->rr_new;
+      st->beta = rr_new / st->rr_cur;
+      st->rr_cur = rr_new;
+      st->its += 1.0;
+      if (!(rr_new > st->tol2) || !isfinite(rr_new) || !isfinite(st->beta)) st->done = 1.0;
+    }
+
+    // p = r + beta p
+    __global__ void __launch_bounds__(kT) cg_p_kernel(int n_pad, const CgState *__restrict__ st, const float *__restrict__ r, float *__restrict__ p)
+    {
+      if (st->done != 0.0) return;
+      const float beta = (float)st->beta;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) p[i] = fmaf(beta, p[i], r[i]);
     }
   } // namespace
 
-  InnerSolver32::~InnerSolver32()
+  // ---------------------------------------------------------------------------
+  // Sell32
+  // ---------------------------------------------------------------------------
+  void Sell32::build(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo_, int precision_)
   {
-    if (h_results) cudaFreeHost(h_results);
-  }
-
-  void InnerSolver32::setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo_, int precision)
-  {
-    if (precision != 32 && precision != 16) throw std::runtime_error("InnerSolver32: precision must be 32 or 16");
-    S.precision = precision;
-    if (A.R != A.C || (A.R != 2 && A.R != 3)) throw std::runtime_error("InnerSolver32: square 2x2 / 3x3 blocks required");
+    if (A.R != A.C || A.R < 1 || A.R > 3) throw std::runtime_error("Sell32: square blocks of size 1..3 required");
+    if (precision_ != 32 && precision_ != 16) throw std::runtime_error("Sell32: precision must be 32 or 16");
+    precision = precision_;
     const int dim = nodes.dim;
     if (const char *e = std::getenv("IFEM_SELL_VARIANT")) variant = std::atoi(e);
-    S.bs = A.R;
-    S.n_rows = A.n_brows_spmv >= 0 ? A.n_brows_spmv : A.n_brows;
-    S.n_cols = A.n_bcols;
-    if (S.n_rows > nodes.n_nodes || S.n_cols < S.n_rows) throw std::runtime_error("InnerSolver32: node table does not match the matrix");
-    const int n = S.n_rows;
+    bs = A.R;
+    n_rows = A.n_brows_spmv >= 0 ? A.n_brows_spmv : A.n_brows;
+    n_cols = A.n_bcols;
+    if (n_rows > nodes.n_nodes || n_cols < n_rows) throw std::runtime_error("Sell32: node table does not match the matrix");
+    const int n = n_rows;
     const std::vector<int64_t> rp = A.rowptr.to_host(ctx.stream);
 
     // ---- row order: columns of T x T nodes along the sweep axis, plane by plane, rows of one length together ----
@@ -645,20 +702,20 @@ namespace ifem
       }
     std::sort(keys.begin(), keys.end());
 
-    S.n_slices = (n + 31) / 32;
-    S.n_pad = S.n_slices * 32;
-    std::vector<int> perm((size_t)S.n_pad, -1), off((size_t)S.n_slices + 1, 0), hoff((size_t)S.n_slices + 1, 0);
-    S.h_pos.assign((size_t)S.n_cols, 0);
-    S.n_blocks = 0;
+    n_slices = (n + 31) / 32;
+    n_pad = n_slices * 32;
+    std::vector<int> perm((size_t)n_pad, -1), off((size_t)n_slices + 1, 0), ho((size_t)n_slices + 1, 0);
+    h_pos.assign((size_t)n_cols, 0);
+    n_blocks = 0;
     for (int i = 0; i < n; ++i)
       {
         perm[i] = keys[i].second;
-        S.h_pos[keys[i].second] = i;
-        S.n_blocks += rp[keys[i].second + 1] - rp[keys[i].second];
+        h_pos[keys[i].second] = i;
+        n_blocks += rp[keys[i].second + 1] - rp[keys[i].second];
       }
-    for (int g = n; g < S.n_cols; ++g) S.h_pos[g] = S.n_pad + (g - n);
+    for (int g = n; g < n_cols; ++g) h_pos[g] = n_pad + (g - n);
     int64_t slots = 0;
-    for (int sl = 0; sl < S.n_slices; ++sl)
+    for (int sl = 0; sl < n_slices; ++sl)
       {
         int64_t L = 0;
         for (int l = 0; l < 32; ++l)
@@ -667,124 +724,100 @@ namespace ifem
             if (row >= 0) L = std::max<int64_t>(L, rp[row + 1] - rp[row]);
           }
         slots += L;
-        if (slots > INT32_MAX) throw std::runtime_error("InnerSolver32: too many block slots for 32-bit slice offsets");
+        if (slots > INT32_MAX) throw std::runtime_error("Sell32: too many block slots for 32-bit slice offsets");
         off[sl + 1] = (int)slots;
-        hoff[sl + 1] = hoff[sl] + (int)((L + 1) / 2);
+        ho[sl + 1] = ho[sl] + (int)((L + 1) / 2);
       }
-    S.n_slots = slots;
-    S.n_hslots = hoff[S.n_slices];
+    n_slots = slots;
+    n_hslots = ho[n_slices];
     keys.clear();
     keys.shrink_to_fit();
 
-    S.slice_off.upload(off, ctx.stream);
-    S.perm_row.upload(perm, ctx.stream);
-    S.pos.upload(S.h_pos, ctx.stream);
-    const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
-    S.col.release();
-    S.val.release();
-    S.col2.release();
-    S.valh.release();
-    S.row_scale.release();
+    slice_off.upload(off, ctx.stream);
+    perm_row.upload(perm, ctx.stream);
+    pos.upload(h_pos, ctx.stream);
+    const int wgrid = (n_slices + kT / 32 - 1) / (kT / 32);
+    col.release();
+    val.release();
+    col2.release();
+    valh.release();
+    row_scale.release();
     if (precision == 32)
       {
-        S.col.alloc((size_t)S.n_slots * 32 + 32 * 8); // slack: the pipelined kernel prefetches up to 8 slots past a slice
-        S.col.zero(ctx.stream);
-        S.val.alloc((size_t)S.n_slots * 32 * S.bs * S.bs);
-        if (S.n_slices)
+        col.alloc((size_t)n_slots * 32 + 32 * 8); // slack: the pipelined kernel prefetches up to 8 slots past a slice
+        col.zero(ctx.stream);
+        val.alloc((size_t)n_slots * 32 * bs * bs);
+        if (n_slices)
           {
-            sell_fill_col_kernel<<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.col.p, S.pos.p, S.col.p);
+            sell_fill_col_kernel<<<wgrid, kT, 0, ctx.stream>>>(n_slices, slice_off.p, perm_row.p, A.rowptr.p, A.col.p, pos.p, col.p);
             IFEM_KERNEL_CHECK();
             ctx.kernel_launches++;
           }
       }
     else
       {
-        S.hoff.upload(hoff, ctx.stream);
-        S.col2.alloc(((size_t)S.n_hslots * 32 + 32 * 8) * 2);
-        S.col2.zero(ctx.stream);
-        S.valh.alloc((size_t)S.n_hslots * 32 * S.bs * S.bs);
-        S.row_scale.alloc((size_t)S.n_pad * S.bs);
-        if (S.n_slices)
+        hoff.upload(ho, ctx.stream);
+        col2.alloc(((size_t)n_hslots * 32 + 32 * 8) * 2);
+        col2.zero(ctx.stream);
+        valh.alloc((size_t)n_hslots * 32 * bs * bs);
+        row_scale.alloc((size_t)n_pad * bs);
+        if (n_slices)
           {
-            sell_fill_col2_kernel<<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.hoff.p, S.perm_row.p, A.rowptr.p, A.col.p, S.pos.p,
-                                                              reinterpret_cast<int2 *>(S.col2.p));
+            sell_fill_col2_kernel<<<wgrid, kT, 0, ctx.stream>>>(n_slices, hoff.p, perm_row.p, A.rowptr.p, A.col.p, pos.p,
+                                                              reinterpret_cast<int2 *>(col2.p));
             IFEM_KERNEL_CHECK();
             ctx.kernel_launches++;
           }
       }
-
-    // ---- vectors ----
-    const size_t nv = (size_t)S.n_pad * S.bs;
-    for (DevBuf<float> *b : {&r, &r0, &p, &v, &s, &t, &x})
-      {
-        b->alloc(nv);
-        b->zero(ctx.stream);
-      }
-    const size_t n4 = ((size_t)S.n_pad + (size_t)(S.n_cols - S.n_rows)) * 4;
-    ph.alloc(n4);
-    ph.zero(ctx.stream);
-    sh.alloc(n4);
-    sh.zero(ctx.stream);
-    binv.alloc((size_t)S.bs * S.bs * S.n_pad);
-    grid = std::max(1, std::min((S.n_pad + kT - 1) / kT, ctx.sm_count * 8));
-    partials.alloc((size_t)grid * 2);
-    results.alloc(4);
-    if (!h_results) IFEM_CUDA(cudaMallocHost(&h_results, 4 * sizeof(double)));
 
     // ---- halo plan in SELL numbering ----
     halo_plan = (halo_ && halo_->active()) ? halo_ : nullptr;
     if (halo_plan)
       {
-        if (halo_plan->n_owned != S.n_rows) throw std::runtime_error("InnerSolver32: halo plan does not match the matrix rows");
+        if (halo_plan->n_owned != n_rows) throw std::runtime_error("Sell32: halo plan does not match the matrix rows");
         if (halo_plan->n_send_total)
           {
             const std::vector<int> idx = halo_plan->d_send_idx.to_host(ctx.stream);
             std::vector<int> sp(idx.size());
-            for (size_t k = 0; k < idx.size(); ++k) sp[k] = S.h_pos[idx[k]];
+            for (size_t k = 0; k < idx.size(); ++k) sp[k] = h_pos[idx[k]];
             send_pos.upload(sp, ctx.stream);
-            send_buf.alloc((size_t)halo_plan->n_send_total * 4);
+            send_buf.alloc((size_t)halo_plan->n_send_total * xs());
           }
       }
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
 
-  void InnerSolver32::refresh(Context &ctx, const Bcsr &A, const double *binv64)
+  void Sell32::refresh(Context &ctx, const Bcsr &A)
   {
-    if (!S.built()) throw std::runtime_error("InnerSolver32::refresh before setup");
-    const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
-    if (S.precision == 16)
+    if (!built()) throw std::runtime_error("Sell32::refresh before build");
+    const int wgrid = (n_slices + kT / 32 - 1) / (kT / 32);
+    if (precision == 16)
       {
-        __half2 *vh = reinterpret_cast<__half2 *>(S.valh.p);
-        if (S.bs == 3)
-          sell_fill_valh_kernel<3><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.hoff.p, S.perm_row.p, A.rowptr.p, A.val.p, vh, S.row_scale.p);
-        else
-          sell_fill_valh_kernel<2><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.hoff.p, S.perm_row.p, A.rowptr.p, A.val.p, vh, S.row_scale.p);
+        __half2 *vh = reinterpret_cast<__half2 *>(valh.p);
+#define IFEM_FILL_H(B) sell_fill_valh_kernel<B><<<wgrid, kT, 0, ctx.stream>>>(n_slices, hoff.p, perm_row.p, A.rowptr.p, A.val.p, vh, row_scale.p)
+        if (bs == 3) IFEM_FILL_H(3); else if (bs == 2) IFEM_FILL_H(2); else IFEM_FILL_H(1);
+#undef IFEM_FILL_H
       }
-    else if (S.bs == 3)
-      sell_fill_val_kernel<3><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.val.p, S.val.p);
     else
-      sell_fill_val_kernel<2><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.perm_row.p, A.rowptr.p, A.val.p, S.val.p);
+      {
+#define IFEM_FILL(B) sell_fill_val_kernel<B><<<wgrid, kT, 0, ctx.stream>>>(n_slices, slice_off.p, perm_row.p, A.rowptr.p, A.val.p, val.p)
+        if (bs == 3) IFEM_FILL(3); else if (bs == 2) IFEM_FILL(2); else IFEM_FILL(1);
+#undef IFEM_FILL
+      }
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
-    if (binv64)
-      {
-        binv_to_sell_kernel<<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.bs * S.bs, S.perm_row.p, binv64, binv.p);
-        IFEM_KERNEL_CHECK();
-        ctx.kernel_launches++;
-      }
   }
 
-  void InnerSolver32::spmv(Context &ctx, const float *x4, float *y)
+  void Sell32::apply(Context &ctx, const float *x, float *y) const
   {
-    const int wgrid = (S.n_slices + kT / 32 - 1) / (kT / 32);
-    const float4 *xp = reinterpret_cast<const float4 *>(x4);
-    if (S.precision == 16)
+    const int wgrid = (n_slices + kT / 32 - 1) / (kT / 32);
+    // variant = 10 * NS + MINB: NS slots per step, MINB resident CTAs per SM
+    if (precision == 16)
       {
-        const int2 *c2 = reinterpret_cast<const int2 *>(S.col2.p);
-        const __half2 *vh = reinterpret_cast<const __half2 *>(S.valh.p);
-#define IFEM_SELL_H(B, NS, M) \
-  sell_spmv_h_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.hoff.p, c2, vh, S.row_scale.p, xp, y)
-        if (S.bs == 3)
+        const int2 *c2 = reinterpret_cast<const int2 *>(col2.p);
+        const __half2 *vh = reinterpret_cast<const __half2 *>(valh.p);
+#define IFEM_SELL_H(B, NS, M) sell_spmv_h_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(n_slices, hoff.p, c2, vh, row_scale.p, x, y)
+        if (bs == 3)
           switch (variant)
             {
             case 13: IFEM_SELL_H(3, 1, 3); break;
@@ -794,64 +827,106 @@ namespace ifem
             case 43: IFEM_SELL_H(3, 4, 3); break;
             default: IFEM_SELL_H(3, 2, 4); break; // 24
             }
-        else
+        else if (bs == 2)
           IFEM_SELL_H(2, 2, 4);
+        else
+          switch (variant)
+            {
+            case 26: IFEM_SELL_H(1, 2, 6); break;
+            case 44: IFEM_SELL_H(1, 4, 4); break;
+            case 84: IFEM_SELL_H(1, 8, 4); break;
+            default: IFEM_SELL_H(1, 4, 6); break;
+            }
 #undef IFEM_SELL_H
-        IFEM_KERNEL_CHECK();
-        ctx.kernel_launches++;
-        return;
       }
-#define IFEM_SELL_LAUNCH(B, U) \
-  sell_spmv_kernel<B, U><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.col.p, S.val.p, xp, y)
-#define IFEM_SELL_PIPE(B, NS, M) \
-  sell_spmv_pipe_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(S.n_slices, S.slice_off.p, S.col.p, S.val.p, xp, y)
-    // variant: 1..4 = plain kernel with that unroll depth; 10 * NS + MINB = pipelined kernel with NS slots per step
-    // and MINB resident CTAs per SM
-    if (S.bs == 3)
-      switch (variant)
-        {
-        case 1: IFEM_SELL_LAUNCH(3, 1); break;
-        case 2: IFEM_SELL_LAUNCH(3, 2); break;
-        case 4: IFEM_SELL_LAUNCH(3, 4); break;
-        case 13: IFEM_SELL_PIPE(3, 1, 3); break;
-        case 16: IFEM_SELL_PIPE(3, 1, 6); break;
-        case 23: IFEM_SELL_PIPE(3, 2, 3); break;
-        case 26: IFEM_SELL_PIPE(3, 2, 6); break;
-        case 42: IFEM_SELL_PIPE(3, 4, 2); break;
-        case 43: IFEM_SELL_PIPE(3, 4, 3); break;
-        default: IFEM_SELL_PIPE(3, 2, 4); break; // 24
-        }
     else
-      switch (variant)
-        {
-        case 1: IFEM_SELL_LAUNCH(2, 1); break;
-        case 2: IFEM_SELL_LAUNCH(2, 2); break;
-        case 4: IFEM_SELL_LAUNCH(2, 4); break;
-        default: IFEM_SELL_PIPE(2, 2, 4); break;
-        }
-#undef IFEM_SELL_LAUNCH
+      {
+#define IFEM_SELL_PIPE(B, NS, M) sell_spmv_pipe_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(n_slices, slice_off.p, col.p, val.p, x, y)
+        if (bs == 3)
+          switch (variant)
+            {
+            case 13: IFEM_SELL_PIPE(3, 1, 3); break;
+            case 16: IFEM_SELL_PIPE(3, 1, 6); break;
+            case 23: IFEM_SELL_PIPE(3, 2, 3); break;
+            case 26: IFEM_SELL_PIPE(3, 2, 6); break;
+            case 43: IFEM_SELL_PIPE(3, 4, 3); break;
+            default: IFEM_SELL_PIPE(3, 2, 4); break; // 24
+            }
+        else if (bs == 2)
+          IFEM_SELL_PIPE(2, 2, 4);
+        else
+          switch (variant)
+            {
+            case 26: IFEM_SELL_PIPE(1, 2, 6); break;
+            case 44: IFEM_SELL_PIPE(1, 4, 4); break;
+            case 84: IFEM_SELL_PIPE(1, 8, 4); break;
+            default: IFEM_SELL_PIPE(1, 4, 6); break;
+            }
 #undef IFEM_SELL_PIPE
+      }
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
   }
 
-  void InnerSolver32::halo(Context &ctx, float *x4)
+  void Sell32::halo(Context &ctx, float *x)
   {
     if (!halo_plan) return;
-    if (!ctx.comm) throw std::runtime_error("InnerSolver32::halo: no communicator");
+    if (!ctx.comm) throw std::runtime_error("Sell32::halo: no communicator");
     const Halo &H = *halo_plan;
+    const int w = xs();
     if (H.n_send_total)
       {
-        halo_pack4_kernel<<<(H.n_send_total + kT - 1) / kT, kT, 0, ctx.stream>>>(H.n_send_total, send_pos.p, reinterpret_cast<const float4 *>(x4),
-                                                                              reinterpret_cast<float4 *>(send_buf.p));
+        const int total = H.n_send_total * w;
+        halo_pack32_kernel<<<(total + kT - 1) / kT, kT, 0, ctx.stream>>>(H.n_send_total, w, send_pos.p, x, send_buf.p);
         IFEM_KERNEL_CHECK();
         ctx.kernel_launches++;
       }
     comm_group_start(*ctx.comm);
     for (size_t k = 0; k < H.neighbours.size(); ++k)
-      comm_sendrecv_f32(*ctx.comm, H.neighbours[k], send_buf.p + (size_t)H.send_off[k] * 4, (int64_t)H.send_cnt[k] * 4,
-                        x4 + ((size_t)S.n_pad + (size_t)(H.recv_off[k] - S.n_rows)) * 4, (int64_t)H.recv_cnt[k] * 4, ctx.stream);
+      comm_sendrecv_f32(*ctx.comm, H.neighbours[k], send_buf.p + (size_t)H.send_off[k] * w, (int64_t)H.send_cnt[k] * w,
+                        x + ((size_t)n_pad + (size_t)(H.recv_off[k] - n_rows)) * w, (int64_t)H.recv_cnt[k] * w, ctx.stream);
     comm_group_end(*ctx.comm);
+  }
+
+  // ---------------------------------------------------------------------------
+  // InnerSolver32: BiCGStab + node-block Jacobi
+  // ---------------------------------------------------------------------------
+  InnerSolver32::~InnerSolver32()
+  {
+    if (h_results) cudaFreeHost(h_results);
+  }
+
+  void InnerSolver32::setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo_, int precision)
+  {
+    if (A.R != 2 && A.R != 3) throw std::runtime_error("InnerSolver32: 2x2 / 3x3 blocks required");
+    S.build(ctx, A, nodes, halo_, precision);
+    const size_t nv = (size_t)S.n_pad * S.bs;
+    for (DevBuf<float> *b : {&r, &r0, &p, &v, &s, &t, &x})
+      {
+        b->alloc(nv);
+        b->zero(ctx.stream);
+      }
+    ph.alloc(S.x_len());
+    ph.zero(ctx.stream);
+    sh.alloc(S.x_len());
+    sh.zero(ctx.stream);
+    binv.alloc((size_t)S.bs * S.bs * S.n_pad);
+    grid = std::max(1, std::min((S.n_pad + kT - 1) / kT, ctx.sm_count * 8));
+    partials.alloc((size_t)grid * 2);
+    results.alloc(4);
+    if (!h_results) IFEM_CUDA(cudaMallocHost(&h_results, 4 * sizeof(double)));
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void InnerSolver32::refresh(Context &ctx, const Bcsr &A, const double *binv64)
+  {
+    S.refresh(ctx, A);
+    if (binv64)
+      {
+        binv_to_sell_kernel<<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.bs * S.bs, S.perm_row.p, binv64, binv.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
   }
 
   void InnerSolver32::reduce(Context &ctx, int nr, double *out)
@@ -961,8 +1036,8 @@ namespace ifem
   {
     if (!S.built()) throw std::runtime_error("InnerSolver32::solve before setup");
     std::function<void(const float *, float *)> A = [&](const float *in4, float *out) {
-      halo(ctx, const_cast<float *>(in4));
-      spmv(ctx, in4, out);
+      S.halo(ctx, const_cast<float *>(in4));
+      S.apply(ctx, in4, out);
     };
     std::function<void(int, double *)> red = [&](int nr, double *o) { reduce(ctx, nr, o); };
     if (S.bs == 3)
@@ -982,10 +1057,10 @@ namespace ifem
       to_sell4_kernel<2><<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.perm_row.p, xin, ph4);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
-    halo(ctx, ph.p);
+    S.halo(ctx, ph.p);
   }
 
-  void InnerSolver32::probe_apply(Context &ctx) { spmv(ctx, ph.p, v.p); }
+  void InnerSolver32::probe_apply(Context &ctx) { S.apply(ctx, ph.p, v.p); }
 
   void InnerSolver32::probe_store(Context &ctx, double *yout)
   {
@@ -995,5 +1070,95 @@ namespace ifem
       final_kernel<2><<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.perm_row.p, v.p, 1.0, yout);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
+  }
+
+  // ---------------------------------------------------------------------------
+  // InnerCG32
+  // ---------------------------------------------------------------------------
+  InnerCG32::~InnerCG32()
+  {
+    if (h_state) cudaFreeHost(h_state);
+  }
+
+  void InnerCG32::setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo_, int precision)
+  {
+    if (A.R != 1) throw std::runtime_error("InnerCG32: scalar matrix required");
+    S.build(ctx, A, nodes, halo_, precision);
+    for (DevBuf<float> *b : {&r, &ap, &x})
+      {
+        b->alloc((size_t)S.n_pad);
+        b->zero(ctx.stream);
+      }
+    p.alloc(S.x_len());
+    p.zero(ctx.stream);
+    grid = std::max(1, std::min((S.n_pad + kT - 1) / kT, ctx.sm_count * 4));
+    partials.alloc((size_t)grid);
+    state.alloc(sizeof(CgState) / sizeof(double));
+    state.zero(ctx.stream);
+    if (!h_state) IFEM_CUDA(cudaMallocHost(&h_state, sizeof(CgState)));
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  SolveResult InnerCG32::solve(Context &ctx, const double *src, double src_norm, double *dst, double tol_abs, int max_it)
+  {
+    if (!S.built()) throw std::runtime_error("InnerCG32::solve before setup");
+    SolveResult out;
+    const int n_pad = S.n_pad;
+    CgState *st = reinterpret_cast<CgState *>(state.p);
+    const bool multi = ctx.comm && ctx.comm->size > 1;
+    auto launched = [&](int k = 1) {
+      IFEM_KERNEL_CHECK();
+      ctx.kernel_launches += k;
+    };
+    if (!(src_norm > 0.0))
+      {
+        final_kernel<1><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x.p, 0.0, dst);
+        launched();
+        out.converged = true;
+        return out;
+      }
+    const double tol_rel = tol_abs / src_norm;
+    cg_init_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, r.p, p.p, x.p, partials.p);
+    launched();
+    reduce_final32_kernel<<<1, kT, 0, ctx.stream>>>(grid, 1, partials.p, &st->rr_new);
+    launched();
+    if (multi) comm_allreduce_sum(*ctx.comm, &st->rr_new, 1, ctx.stream);
+    cg_start_kernel<<<1, 1, 0, ctx.stream>>>(st, tol_rel * tol_rel);
+    launched();
+    const CgState *h = reinterpret_cast<const CgState *>(h_state);
+    int enqueued = 0;
+    while (true)
+      {
+        const int chunk = std::max(1, std::min(check_every, max_it - enqueued));
+        for (int k = 0; k < chunk; ++k)
+          {
+            S.halo(ctx, p.p);
+            S.apply(ctx, p.p, ap.p);
+            cg_dot_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, p.p, ap.p, partials.p);
+            launched();
+            reduce_final32_kernel<<<1, kT, 0, ctx.stream>>>(grid, 1, partials.p, &st->pAp);
+            launched();
+            if (multi) comm_allreduce_sum(*ctx.comm, &st->pAp, 1, ctx.stream);
+            cg_xr_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, x.p, p.p, r.p, ap.p, partials.p);
+            launched();
+            reduce_final32_kernel<<<1, kT, 0, ctx.stream>>>(grid, 1, partials.p, &st->rr_new);
+            launched();
+            if (multi) comm_allreduce_sum(*ctx.comm, &st->rr_new, 1, ctx.stream);
+            cg_advance_kernel<<<1, 1, 0, ctx.stream>>>(st);
+            launched();
+            cg_p_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, r.p, p.p);
+            launched();
+          }
+        enqueued += chunk;
+        IFEM_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CgState), cudaMemcpyDeviceToHost, ctx.stream));
+        IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+        if (h->done != 0.0 || enqueued >= max_it) break;
+      }
+    out.iterations = (int)h->its;
+    out.residual = std::sqrt(std::max(0.0, h->rr_cur)) * src_norm;
+    out.converged = h->rr_cur <= h->tol2;
+    final_kernel<1><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x.p, src_norm, dst);
+    launched();
+    return out;
   }
 } // namespace ifem

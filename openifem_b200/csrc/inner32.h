@@ -1,10 +1,14 @@
-// Mixed-precision inner solver for the velocity block: the stand-in for the MUMPS
-// factorisation of system_matrix.block(0,0) inside BlockSchurPreconditioner::vmult
-// (reference source/mpi_insim.cpp:111-127; Krylov-for-A~ precedent
-// source/mpi_insimex.cpp:114-124). FGMRES is flexible, so the preconditioner may be
-// any approximate inverse: here BiCGStab + node-block Jacobi run entirely in fp32 on
-// a copy of A_uu laid out for streaming (the operator, residuals and Krylov basis of
-// the outer FGMRES stay fp64 on the row-plane BCSR matrix).
+// Mixed-precision inner solvers of the block Schur preconditioner
+// (BlockSchurPreconditioner::vmult, reference source/mpi_insim.cpp:56-128):
+//   * InnerSolver32: the stand-in for the MUMPS factorisation of
+//     system_matrix.block(0,0) (mpi_insim.cpp:111-127; Krylov-for-A~ precedent
+//     source/mpi_insimex.cpp:114-124) - BiCGStab + node-block Jacobi;
+//   * InnerCG32: "CG for Sm", the unpreconditioned CG on B diag(M_u)^-1 B^T
+//     (mpi_insim.cpp:88-109).
+// FGMRES is flexible, so the preconditioner may be any approximate inverse: both run
+// entirely in fp32 on a copy of their matrix laid out for streaming (the operator,
+// residuals and Krylov basis of the outer FGMRES stay fp64 on the row-plane BCSR
+// matrices, and converged Newton states do not depend on the inner precision).
 //
 // Layout of the copy ("sliced ELL of bs x bs blocks", SELL-32):
 //   * block rows are re-ordered: the domain is cut into columns of T x T nodes along
@@ -15,9 +19,12 @@
 //   * slice s with L_s block slots stores col[(off_s + j) * 32 + lane] and
 //     val[((off_s + j) * bs*bs + k) * 32 + lane]: one lane per row, every load of a
 //     warp is one full 128-byte line of a purely sequential stream;
-//   * the solver's vectors live in the same permuted ("SELL") numbering, so the
+//   * precision 16: values scaled by 1 / max|row| per scalar row and stored as half2 =
+//     two consecutive slots of a row (int2 = their column indices): 22 instead of 40
+//     bytes per 3x3 block, products and sums in fp32;
+//   * the solvers' vectors live in the same permuted ("SELL") numbering, so the
 //     product is written coalesced and the x gathers of a slice hit runs of
-//     consecutive nodes; gather sources are padded to float4 per node.
+//     consecutive nodes; gather sources of bs > 1 are padded to float4 per node.
 #pragma once
 #include "halo.h"
 #include "krylov.h"
@@ -28,10 +35,10 @@ namespace ifem
   struct Sell32
   {
     int bs = 0;
+    int precision = 32;          // storage of the matrix values: 32 = float, 16 = row-scaled half
     int n_rows = 0;              // owned block rows (= rows of a product)
     int n_cols = 0;              // local block columns (owned + ghosts)
     int n_slices = 0, n_pad = 0; // n_pad = 32 * n_slices >= n_rows
-    int precision = 32;          // storage of the matrix values: 32 = float, 16 = row-scaled half
     int64_t n_slots = 0;         // sum of slice lengths
     int64_t n_hslots = 0;        // sum of ceil(slice length / 2): double slots of the fp16 storage
     int64_t n_blocks = 0;        // blocks of the owned rows (unpadded)
@@ -46,12 +53,28 @@ namespace ifem
     DevBuf<unsigned int> valh;   // [n_hslots * bs * bs * 32] half2
     DevBuf<float> row_scale;     // [n_pad * bs]
     std::vector<int> h_pos;
+    int variant = 24;            // kernel shape: 10 * slots per step + resident CTAs per SM
+    // halo plan in SELL numbering
+    const Halo *halo_plan = nullptr;
+    DevBuf<int> send_pos;
+    DevBuf<float> send_buf;
+
     bool built() const { return n_slices > 0; }
-    // bytes one product has to move: values + column index + slice offsets, x (float4) read once, y written once
+    int xs() const { return bs == 1 ? 1 : 4; } // floats per node of a gather source
+    size_t x_len() const { return ((size_t)n_pad + (size_t)(n_cols - n_rows)) * xs(); }
+    // pattern-only work, once per sparsity pattern: row order, slices, column map, halo plan in SELL numbering
+    void build(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo, int precision);
+    // values of A -> the copy
+    void refresh(Context &ctx, const Bcsr &A);
+    // y (bs floats per SELL row) = A x, x a gather source of x_len() floats with up-to-date ghosts
+    void apply(Context &ctx, const float *x, float *y) const;
+    // refresh the ghost entries of a gather source from their owners
+    void halo(Context &ctx, float *x);
+    // bytes one product has to move: values + column index + slice offsets, x read once, y written once
     double spmv_bytes() const
     {
       const double per_value = precision == 16 ? 2.0 : 4.0, scales = precision == 16 ? 4.0 * bs * n_rows : 0.0;
-      return per_value * n_blocks * bs * bs + 4.0 * n_blocks + 4.0 * (n_slices + 1) + 16.0 * n_cols + 4.0 * bs * n_rows + scales;
+      return per_value * n_blocks * bs * bs + 4.0 * n_blocks + 4.0 * (n_slices + 1) + 4.0 * xs() * n_cols + 4.0 * bs * n_rows + scales;
     }
     double padding() const
     {
@@ -64,7 +87,6 @@ namespace ifem
   {
   public:
     ~InnerSolver32();
-    // pattern-only work, once per sparsity pattern: row order, slices, column map, halo plan in SELL numbering
     // precision: 32 (float values) or 16 (half values scaled per scalar row)
     void setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo, int precision = 32);
     // values of A and of the inverted diagonal blocks (row-major bs x bs per node) -> fp32, every solve
@@ -77,21 +99,36 @@ namespace ifem
     void probe_apply(Context &ctx);
     void probe_store(Context &ctx, double *y);
     Sell32 S;
-    int variant = 24; // product kernel (see InnerSolver32::spmv): 10 * slots per step + CTAs per SM of the pipelined form
 
   private:
-    void spmv(Context &ctx, const float *x4, float *y);
-    void halo(Context &ctx, float *x4);
     void reduce(Context &ctx, int n_results, double *out);
     DevBuf<float> r, r0, p, v, s, t, x; // [n_pad * bs]
-    DevBuf<float> ph, sh;               // [(n_pad + n_ghost) * 4], gather sources
+    DevBuf<float> ph, sh;               // [x_len], gather sources
     DevBuf<float> binv;                 // [bs * bs][n_pad]
     DevBuf<double> partials, results;
     double *h_results = nullptr;
     int grid = 0;
-    // halo plan in SELL numbering
-    const Halo *halo_plan = nullptr;
-    DevBuf<int> send_pos;
-    DevBuf<float> send_buf;
+  };
+
+  // Unpreconditioned CG in fp32 on the SELL-32 copy of a scalar (1 x 1) matrix, x0 = 0, absolute tolerance. The
+  // iteration is driven from device-resident scalars (no host round trip per dot product): the host enqueues
+  // `check_every` iterations, then reads the state; iterations past convergence are no-ops.
+  class InnerCG32
+  {
+  public:
+    ~InnerCG32();
+    void setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo, int precision = 32);
+    void refresh(Context &ctx, const Bcsr &A) { S.refresh(ctx, A); }
+    // dst ~= A^-1 src to |r| <= tol_abs; src_norm = |src| over all ranks
+    SolveResult solve(Context &ctx, const double *src, double src_norm, double *dst, double tol_abs, int max_it);
+    Sell32 S;
+    int check_every = 10;
+
+  private:
+    DevBuf<float> r, ap, x; // [n_pad]
+    DevBuf<float> p;        // [x_len] gather source
+    DevBuf<double> partials, state; // state: see CgState in inner32.cu
+    double *h_state = nullptr;
+    int grid = 0;
   };
 } // namespace ifem

@@ -154,12 +154,7 @@ namespace ifem
     }
     {
       ScopedTimer t(ctx, timer_ms["CG for Sm"]);
-      fill(ctx, vp, 0.0, dst_p);
-      LinOp Sm = [&](const double *x, double *y) {
-        fs.halo_p.update(ctx, const_cast<double *>(x)); // both ghost layers: S_m reaches two cells deep
-        spmv(ctx, fs.S_m, x, y);
-      };
-      const SolveResult r = cg(ctx, vp, Sm, src_p, dst_p, true, std::max(control.cg_floor, control.cg_sm_rel * nrm), max_p_its, pool_cg);
+      const SolveResult r = solve_mass_schur(control.cg_sm_fp32, src_p, nrm, dst_p, std::max(control.cg_floor, control.cg_sm_rel * nrm), max_p_its);
       cur.cg_sm_its += r.iterations;
       // dst_p = -rho/dt * dst_p + tmp
       axpby(ctx, vp, 1.0, tmp, -parameters.fluid_rho / time.get_delta_t(), dst_p);
@@ -184,6 +179,33 @@ namespace ifem
     cur.precond_applies++;
   }
 
+  // "CG for Sm" (mpi_insim.cpp:88-109): x = S_m^-1 b to |r| <= tol_abs, x0 = 0
+  SolveResult InsIM::solve_mass_schur(int mode, const double *b, double b_norm, double *x, double tol_abs, int max_it)
+  {
+    const VecSpace &vp = fs.vs_p;
+    if (mode == 0)
+      {
+        fill(ctx, vp, 0.0, x);
+        LinOp Sm = [&](const double *in, double *out) {
+          fs.halo_p.update(ctx, const_cast<double *>(in)); // both ghost layers: S_m reaches two cells deep
+          spmv(ctx, fs.S_m, in, out);
+        };
+        return cg(ctx, vp, Sm, b, x, true, tol_abs, max_it, pool_cg);
+      }
+    const int precision = mode == 2 ? 16 : 32;
+    if (!inner_sm.S.built() || inner_sm.S.precision != precision)
+      {
+        inner_sm.setup(ctx, fs.S_m, fs.pn, fs.n_ranks > 1 ? &fs.halo_p : nullptr, precision);
+        sm_copy_valid = false;
+      }
+    if (!sm_copy_valid)
+      {
+        inner_sm.refresh(ctx, fs.S_m);
+        sm_copy_valid = true;
+      }
+    return inner_sm.solve(ctx, b, b_norm, x, tol_abs, max_it);
+  }
+
   std::pair<unsigned int, double> InsIM::solve(bool use_nonzero_constraints)
   {
     ScopedTimer t(ctx, timer_ms["Solve linear system"]);
@@ -203,6 +225,7 @@ namespace ifem
           }
         compute_mass_schur(ctx, fs);
         fs.schur_valid = true;
+        sm_copy_valid = false;
       }
     block_diag_inverse(ctx, fs.A_uu, d_binv.p);
     if (control.a_inv_fp32 >= 2)

@@ -70,6 +70,9 @@ namespace ifem
     // A_uu (inner32.h); 3: as 2 with the matrix values of the copy stored as row-scaled fp16. Legal because FGMRES
     // is flexible; operator, residuals and Krylov basis stay fp64
     int a_inv_fp32 = 0;
+    // "CG for Sm": 0 fp64 CG on the CSR matrix (reference arithmetic); 1 fp32 CG on a SELL-32 copy of S_m, driven from
+    // device-resident scalars; 2 as 1 with row-scaled fp16 matrix values
+    int cg_sm_fp32 = 0;
     int basis_size = 30;
     static InsSolverControl serial()
     {
@@ -127,8 +130,12 @@ namespace ifem
 
   public:
     InnerSolver32 inner32;
+    InnerCG32 inner_sm;
+    // "CG for Sm": x = S_m^-1 b (pressure vectors on the device) in the given cg_sm_fp32 mode; b_norm = |b| over all ranks
+    SolveResult solve_mass_schur(int mode, const double *b, double b_norm, double *x, double tol_abs, int max_it);
 
   protected:
     NewtonRecord cur{};
+    bool sm_copy_valid = false; // inner_sm holds the current S_m
   };
 } // namespace ifem

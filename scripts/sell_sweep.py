@@ -24,7 +24,7 @@ ms, b = flow.bench_spmv_uu(10)
 print(f"f64 BCSR  {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s", flush=True)
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 best = {}
-for prec, variants in [(32, [24, 13]), (16, [24, 13, 16, 23, 26, 43, 24])]:
+for prec, variants in [(32, [24]), (16, [24])]:
     if mode == 2 and prec == 16:
         continue
     t0 = time.perf_counter()
@@ -37,7 +37,8 @@ for prec, variants in [(32, [24, 13]), (16, [24, 13, 16, 23, 26, 43, 24])]:
         best[prec] = min(best[prec], (ms, v))
 print("best", best, flush=True)
 flow.set_inner_variant(best[16 if mode == 3 else 32][1])
-flow.set_control(a_inv_rel=1e-1, a_inv_fp32=mode)
+sm_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+flow.set_control(a_inv_rel=1e-1, a_inv_fp32=mode, cg_sm_fp32=sm_mode)
 flow.set_verbose(True)
 for k in range(steps):
     t0 = time.perf_counter()

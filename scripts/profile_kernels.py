@@ -16,7 +16,12 @@ ifem.GridGenerator.subdivided_hyper_rectangle(tria, (n, n, n), (0, 0, 0), (1, 1,
 flow = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(text=cavity_prm(3)))
 flow.setup()
 flow.assemble(True)
-if what == "spmv":
+if what == "sell":
+    # product kernels of the fp32 inner solvers (SELL-32 copies of A_uu): fp16 values, then fp32 values
+    print("sell16", flow.bench_spmv_uu_sell(3, precision=16, check_error=False))
+    print("sell32", flow.bench_spmv_uu_sell(3, precision=32, check_error=False))
+    print("uu f64", flow.bench_spmv_uu(3))
+elif what == "spmv":
     print("uu", flow.bench_spmv_uu(3))
     print("uu fp32", flow.bench_spmv_uu_fp32(3))
     print("block", flow.bench_vmult(2))

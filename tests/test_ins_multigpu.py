@@ -49,9 +49,10 @@ def _worker(rank, size, idfile, dim, reps, steps, q, inner_mode=0):
         ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
         flow = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(text=cavity_prm(dim, newton_tol=1e-9)))
         flow.setup()
-        if inner_mode == 2:
-            # fp32 inner solver on the sliced copy of A_uu: fp32 cannot reach 1e-10, FGMRES (flexible) still converges
-            flow.set_control(a_inv_rel=1e-3, a_inv_max_it=500, fgmres_rel=1e-9, a_inv_fp32=2)
+        if inner_mode >= 2:
+            # fp32 inner solvers on the sliced copies of A_uu / S_m (2: fp32 values, 3: fp16 values): fp32 cannot reach
+            # 1e-10, FGMRES (flexible) still converges
+            flow.set_control(a_inv_rel=1e-3, a_inv_max_it=500, fgmres_rel=1e-9, a_inv_fp32=inner_mode, cg_sm_fp32=inner_mode - 1)
         else:
             flow.set_control(a_inv_rel=1e-10, a_inv_max_it=5000, fgmres_rel=1e-9)
         n_un_glob = int(np.prod([2 * k + 1 for k in reps]))
@@ -133,14 +134,15 @@ def test_two_ranks_match_one_rank(dim, reps, size, tmp_path):
     assert rel(p2, p1) < 1e-6
 
 
-@pytest.mark.parametrize("dim,reps", [(3, (4, 4, 6)), (2, (6, 8))])
-def test_fp32_inner_solver_two_ranks_match_one_rank(dim, reps, tmp_path):
-    """a_inv_fp32 = 2 (fp32 BiCGStab on the SELL-32 copy of A_uu, halo exchange in the permuted numbering) on two
-    ranks against the fp64 inner solve on one rank: same converged Newton states to 1e-6"""
+@pytest.mark.parametrize("dim,reps,inner_mode", [(3, (4, 4, 6), 3), (2, (6, 8), 2)])
+def test_fp32_inner_solver_two_ranks_match_one_rank(dim, reps, inner_mode, tmp_path):
+    """a_inv_fp32 = 2 / 3 and cg_sm_fp32 = 1 / 2 (fp32 BiCGStab and CG on the SELL-32 copies of A_uu and S_m, halo
+    exchange in the permuted numbering) on two ranks against the fp64 inner solves on one rank: same converged Newton
+    states to 1e-6"""
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     _, _, sol1, h1 = _run(1, dim, reps, 2, tmp_path)
-    _, _, sol2, h2 = _run(2, dim, reps, 2, tmp_path, inner_mode=2)
+    _, _, sol2, h2 = _run(2, dim, reps, 2, tmp_path, inner_mode=inner_mode)
     rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
     assert [a[:2] for a in h2] == [b[:2] for b in h1]
     for a, b in zip(h2, h1):

@@ -182,7 +182,7 @@ def run_ours(args):
     flow = ifem.Fluid.MPI.InsIM(tria, params)
     flow.setup()
     # fp32 inner solver on the SELL-32 copy of A_uu with row-scaled fp16 matrix values (preconditioner only)
-    flow.set_control(a_inv_rel=1e-1, a_inv_fp32=args.inner_mode, cg_sm_fp32=args.sm_mode)
+    flow.set_control(a_inv_rel=1e-1, a_inv_fp32=args.inner_mode, cg_sm_fp32=args.sm_mode, a_inv_max_it=400)
     barrier()
     t_setup = time.perf_counter() - t_setup
     n_u, n_p, nnz_local, _, _ = flow.sizes()
@@ -235,7 +235,8 @@ def run_ours(args):
     traffic = _ncu_traffic()
     hist = flow.history()
     last = [h for h in hist if h["timestep"] == hist[-1]["timestep"]]
-    sections = {k: flow.timer_ms(k) for k in ["Assemble system", "Solve linear system", "CG for Mp", "CG for Sm", "A_inv"]}
+    sections = {k: flow.timer_ms(k) for k in ["Assemble system", "Solve linear system", "CG for Mp", "CG for Sm", "A_inv",
+                                              "CG for Sm fp64 fallbacks (count)"]}
 
     if world > 1:
         ms_uu, ms_blk, ms_32 = max_over_ranks(ms_uu), max_over_ranks(ms_blk), max_over_ranks(ms_32)
@@ -302,7 +303,7 @@ def main():
     ap.add_argument("--cells", type=int, default=128, help="cells per direction (config 3 = 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sm-mode", type=int, default=2, choices=[0, 1, 2],
+    ap.add_argument("--sm-mode", type=int, default=1, choices=[0, 1, 2],
                     help="'CG for Sm': 0 fp64 CG on CSR, 1 fp32 CG on SELL-32, 2 fp32 CG on fp16 SELL-32 values")
     ap.add_argument("--inner-mode", type=int, default=3, choices=[0, 1, 2, 3],
                     help="A~^-1 inner solve: 0 fp64 BCSR, 1 fp32-streamed BCSR, 2 fp32 SELL-32, 3 fp32 solver on fp16 SELL-32 values")

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <utility>
 
@@ -540,6 +541,26 @@ namespace ifem
         }
     }
 
+    // dst (fp64, original numbering) = scale * D^-1 r (one block-Jacobi step), owned rows only
+    template <int BS>
+    __global__ void __launch_bounds__(kT)
+    jacobi_out_kernel(int n_pad, const int *__restrict__ perm_row, const float *__restrict__ r, const float *__restrict__ binv, double scale,
+                      double *__restrict__ dst)
+    {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const int row = perm_row[i];
+          if (row < 0) continue;
+          float rc[BS];
+#pragma unroll
+          for (int c = 0; c < BS; ++c) rc[c] = r[(size_t)i * BS + c];
+          const float4 q = apply_binv<BS>(binv, n_pad, i, rc);
+          const float a[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int c = 0; c < BS; ++c) dst[(size_t)row * BS + c] = scale * (double)a[c];
+        }
+    }
+
     // x4 (SELL numbering, float4 per node) from a fp64 vector in the original numbering (owned nodes)
     template <int BS>
     __global__ void __launch_bounds__(kT)
@@ -1025,6 +1046,18 @@ namespace ifem
           }
         if (rho_new == 0.0 || omega == 0.0 || !std::isfinite(rho_new)) break;
       }
+    static const bool debug = std::getenv("IFEM_INNER_DEBUG") != nullptr;
+    if (debug) std::fprintf(stderr, "[inner32] bicgstab its %d rel.res %.3e converged %d\n", out.iterations, out.residual, (int)out.converged);
+    if (!std::isfinite(out.residual) || out.residual >= 1.0)
+      {
+        // no progress over x = 0 (breakdown in fp32): hand back one block-Jacobi step D^-1 src, which is always a
+        // valid (if weak) preconditioner application for the flexible outer iteration. r0 still holds src / |src|.
+        jacobi_out_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, r0, binv, src_norm, dst);
+        IFEM_KERNEL_CHECK();
+        count();
+        out.residual = src_norm;
+        return out;
+      }
     final_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x, src_norm, dst);
     IFEM_KERNEL_CHECK();
     count();
@@ -1154,6 +1187,8 @@ namespace ifem
         IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
         if (h->done != 0.0 || enqueued >= max_it) break;
       }
+    static const bool debug = std::getenv("IFEM_INNER_DEBUG") != nullptr;
+    if (debug) std::fprintf(stderr, "[inner32] cg its %d rel.res %.3e done %d\n", (int)h->its, std::sqrt(std::max(0.0, h->rr_cur)), (int)h->done);
     out.iterations = (int)h->its;
     out.residual = std::sqrt(std::max(0.0, h->rr_cur)) * src_norm;
     out.converged = h->rr_cur <= h->tol2;

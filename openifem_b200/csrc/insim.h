@@ -137,5 +137,10 @@ namespace ifem
   protected:
     NewtonRecord cur{};
     bool sm_copy_valid = false; // inner_sm holds the current S_m
+
+  public:
+    long long sm_fallbacks = 0; // fp32 "CG for Sm" applications redone in fp64 (see solve_mass_schur)
+
+  protected:
   };
 } // namespace ifem

@@ -155,6 +155,7 @@ namespace ifem
           }
         first = false;
         const double beta = nrm2(ctx, n, aux);
+        if (!std::isfinite(beta)) throw std::runtime_error("FGMRES: non-finite residual (the preconditioner returned NaN/Inf)");
         out.residual = beta;
         if (beta <= tol_abs)
           {
@@ -180,6 +181,7 @@ namespace ifem
             h(0) = dot(ctx, n, aux, V(0));
             for (int i = 1; i <= j; ++i) h(i) = add_and_dot(ctx, n, aux, -h(i - 1), V(i - 1), V(i));
             a = std::sqrt(add_and_dot(ctx, n, aux, -h(j), V(j), aux));
+            if (!std::isfinite(a)) throw std::runtime_error("FGMRES: non-finite Arnoldi vector (the preconditioner returned NaN/Inf)");
             h(j + 1) = a;
             // least squares on the (j+1) x j block = all columns before this one:
             // rotate the new column with the previous rotations, residual = |g[j]|

@@ -38,7 +38,7 @@ for prec, variants in [(32, [24]), (16, [24])]:
 print("best", best, flush=True)
 flow.set_inner_variant(best[16 if mode == 3 else 32][1])
 sm_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 2
-flow.set_control(a_inv_rel=1e-1, a_inv_fp32=mode, cg_sm_fp32=sm_mode)
+flow.set_control(a_inv_rel=1e-1, a_inv_fp32=mode, cg_sm_fp32=sm_mode, a_inv_max_it=int(sys.argv[5]) if len(sys.argv) > 5 else 2000)
 flow.set_verbose(True)
 for k in range(steps):
     t0 = time.perf_counter()

@@ -142,6 +142,12 @@ private:
 
 namespace Utils
 {
+  // Utils::GridCreator<dim>::flow_around_cylinder (include/utilities.h, source/utilities.cpp:343-574)
+  template <int dim>
+  struct GridCreator
+  {
+    static void flow_around_cylinder(dealii::Triangulation<dim> &tria) { openifem_detail::check(ifem_tria_flow_around_cylinder(tria.handle())); }
+  };
   inline double PETScVectorMax(const std::vector<double> &v) { return *std::max_element(v.begin(), v.end()); }
   inline double PETScVectorMin(const std::vector<double> &v) { return *std::min_element(v.begin(), v.end()); }
 } // namespace Utils
@@ -170,11 +176,27 @@ namespace Fluid
         openifem_detail::check(ifem_insim_get_current_solution(h, all.data()));
         return BlockVector(std::vector<double>(all.begin(), all.begin() + n_u), std::vector<double>(all.begin() + n_u, all.end()));
       }
+      // include/mpi_fluid_solver.h:104-108
+      using BoundaryValue = std::function<double(const dealii::Point<dim> &, const unsigned int, const double)>;
+      void add_hard_coded_boundary_condition(const int id, const BoundaryValue &f)
+      {
+        bcs.emplace_back(new BoundaryValue(f));
+        openifem_detail::check(ifem_insim_add_hard_coded_boundary_condition(h, id, &bc_thunk, bcs.back().get()));
+      }
       ifem_insim *handle() const { return h; }
 
     protected:
       FluidSolver() = default;
       ifem_insim *h = nullptr;
+
+    private:
+      static double bc_thunk(const double *p, unsigned int c, double time, void *user)
+      {
+        dealii::Point<dim> x;
+        for (int d = 0; d < dim; ++d) x[d] = p[d];
+        return (*static_cast<BoundaryValue *>(user))(x, c, time);
+      }
+      std::vector<std::unique_ptr<BoundaryValue>> bcs;
     };
 
     template <int dim>

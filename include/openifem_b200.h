@@ -65,6 +65,13 @@ int ifem_tria_subdivided_hyper_rectangle(ifem_tria *t, const unsigned int *repet
 int ifem_tria_hyper_cube(ifem_tria *t, double left, double right, int colorize);
 int ifem_tria_refine_global(ifem_tria *t, int times);
 int ifem_tria_counts(const ifem_tria *t, int64_t *n_vertices, int64_t *n_cells, int64_t *n_boundary_faces);
+/* Utils::GridCreator<dim>::flow_around_cylinder(tria) (source/utilities.cpp:343-574; dim of the handle): the mesh of
+ * tests/fluid_cylinder_mpi*. In 2-D the cells around the hole carry their polar / transfinite charts, which
+ * ifem_tria_refine_global honours like deal.II's manifolds; the 3-D mesh is the extruded one and refines flat. */
+int ifem_tria_flow_around_cylinder(ifem_tria *t);
+/* copy the mesh out: vertices [n_vertices][dim], cells [n_cells][2^dim] (lexicographic corners), boundary_faces
+ * [n_boundary_faces][3] = (cell, face_no = 2*axis+side, boundary id); any pointer may be NULL */
+int ifem_tria_get_mesh(const ifem_tria *t, double *vertices, int *cells, int *boundary_faces);
 
 /* ---- Parameters::AllParameters(prm_file) (include/parameters.h:191, source/parameters.cpp:618-658) ---- */
 int ifem_params_from_file(const char *prm_file, ifem_params **out);
@@ -99,6 +106,11 @@ typedef struct
  * (mpi_fluid_solver.h:187) and a copy of the parameters (:222) */
 int ifem_insim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out);
 int ifem_insim_destroy(ifem_insim *s);
+/* FluidSolver::add_hard_coded_boundary_condition(id, f(point, component, time)) (include/mpi_fluid_solver.h:104-108): used
+ * by make_constraints for the Dirichlet ids of the .prm when "Use hard-coded boundary values = 1" semantics are wanted;
+ * call before ifem_insim_setup / ifem_insim_run */
+typedef double (*ifem_bc_fn)(const double *point, unsigned int component, double time, void *user);
+int ifem_insim_add_hard_coded_boundary_condition(ifem_insim *s, int boundary_id, ifem_bc_fn f, void *user);
 int ifem_insim_default_control(int serial_twin, ifem_ins_control *out);
 int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c);
 int ifem_insim_set_verbose(ifem_insim *s, int verbose);

@@ -124,6 +124,15 @@ class Triangulation:
     def n_vertices(self):
         return self._counts()[0]
 
+    def get_mesh(self):
+        """(vertices [nv][dim], cells [nc][2^dim], boundary_faces [nbf][3] = (cell, face_no, boundary id))"""
+        nv, nc, nbf = self._counts()
+        v = np.empty((nv, self.dim))
+        c = np.empty((nc, 1 << self.dim), dtype=np.int32)
+        b = np.empty((nbf, 3), dtype=np.int32)
+        check(lib().ifem_tria_get_mesh(self._h, dptr(v), iptr(c), iptr(b)))
+        return v, c, b
+
     def n_active_cells(self):
         return self._counts()[1]
 
@@ -131,6 +140,14 @@ class Triangulation:
         if getattr(self, "_h", None) and _lib._lib is not None:
             _lib._lib.ifem_tria_destroy(self._h)
             self._h = None
+
+
+class GridCreator:
+    """Utils::GridCreator<dim> (reference source/utilities.cpp:343-574)"""
+
+    @staticmethod
+    def flow_around_cylinder(tria: Triangulation):
+        check(lib().ifem_tria_flow_around_cylinder(tria._h))
 
 
 class GridGenerator:
@@ -161,6 +178,9 @@ class Parameters:
                 self._h = None
 
 
+BC_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_uint, C.c_double, C.c_void_p)
+
+
 class _InsIM:
     """Fluid::MPI::InsIM<dim>(triangulation, parameters)."""
 
@@ -179,6 +199,15 @@ class _InsIM:
     # -- reference surface --------------------------------------------------
     def run(self):
         check(lib().ifem_insim_run(self._h))
+
+    def add_hard_coded_boundary_condition(self, boundary_id: int, f):
+        """FluidSolver::add_hard_coded_boundary_condition(id, f(point, component, time)); call before setup() / run()"""
+        dim = self.tria.dim
+        cb = BC_FN(lambda p, c, t, _u: float(f([p[i] for i in range(dim)], int(c), float(t))))
+        if not hasattr(self, "_keep_bc"):
+            self._keep_bc = []
+        self._keep_bc.append(cb)  # the library calls it later: keep the trampoline alive
+        check(lib().ifem_insim_add_hard_coded_boundary_condition(self._h, C.c_int(boundary_id), cb, None))
 
     def run_one_step(self, apply_nonzero_constraints: bool, assemble_system: bool = True):
         check(lib().ifem_insim_run_one_step(self._h, C.c_int(1 if apply_nonzero_constraints else 0)))

@@ -272,6 +272,18 @@ int ifem_tria_refine_global(ifem_tria *t, int times)
 {
   return guard([&] { t->t.refine_global(times); });
 }
+int ifem_tria_flow_around_cylinder(ifem_tria *t)
+{
+  return guard([&] { GridCreator::flow_around_cylinder(t->t, t->t.dim); });
+}
+int ifem_tria_get_mesh(const ifem_tria *t, double *vertices, int *cells, int *boundary_faces)
+{
+  return guard([&] {
+    if (vertices) std::copy(t->t.vertices.begin(), t->t.vertices.end(), vertices);
+    if (cells) std::copy(t->t.cells.begin(), t->t.cells.end(), cells);
+    if (boundary_faces) std::copy(t->t.boundary_faces.begin(), t->t.boundary_faces.end(), boundary_faces);
+  });
+}
 int ifem_tria_counts(const ifem_tria *t, int64_t *nv, int64_t *nc, int64_t *nbf)
 {
   return guard([&] {
@@ -316,6 +328,12 @@ int ifem_insim_destroy(ifem_insim *s)
 {
   delete s;
   return IFEM_OK;
+}
+int ifem_insim_add_hard_coded_boundary_condition(ifem_insim *s, int boundary_id, ifem_bc_fn f, void *user)
+{
+  return guard([&] {
+    s->s->add_hard_coded_boundary_condition(boundary_id, [f, user](const double *p, unsigned int c, double time) { return f(p, c, time, user); });
+  });
 }
 int ifem_insim_default_control(int serial_twin, ifem_ins_control *out)
 {

@@ -1,5 +1,7 @@
 #include "mesh.h"
 
+#include <map>
+
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -60,6 +62,200 @@ namespace ifem
                     tria.boundary_faces.push_back(colorize ? 2 * axis + side : 0);
                   }
           }
+  }
+
+  void PolarArcChart::init()
+  {
+    const double d0[2] = {v[0][0] - c[0], v[0][1] - c[1]}, d1[2] = {v[1][0] - c[0], v[1][1] - c[1]};
+    r0 = std::hypot(d0[0], d0[1]);
+    r1 = std::hypot(d1[0], d1[1]);
+    a0 = std::atan2(d0[1], d0[0]);
+    da = std::atan2(d1[1], d1[0]) - a0;
+    const double pi = 3.14159265358979323846;
+    while (da > pi) da -= 2 * pi; // the shortest way round: the polar manifold is periodic in the angle
+    while (da < -pi) da += 2 * pi;
+  }
+
+  void PolarArcChart::eval(double s, double t, double *x) const
+  {
+    const double r = (1 - s) * r0 + s * r1, a = a0 + s * da;
+    const double B[2] = {c[0] + r * std::cos(a), c[1] + r * std::sin(a)};
+    for (int d = 0; d < 2; ++d)
+      {
+        const double T = (1 - s) * v[2][d] + s * v[3][d], L = (1 - t) * v[0][d] + t * v[2][d], R = (1 - t) * v[1][d] + t * v[3][d];
+        x[d] = (1 - s) * L + s * R + (1 - t) * B[d] + t * T
+               - ((1 - s) * (1 - t) * v[0][d] + s * (1 - t) * v[1][d] + (1 - s) * t * v[2][d] + s * t * v[3][d]);
+      }
+  }
+
+  namespace
+  {
+    // the 2-D mesh of flow_around_cylinder_2d (utilities.cpp:343-486); boundary ids of GridCreator<2>
+    void cylinder_2d(Triangulation &tria, bool compute_in_2d, bool with_charts)
+    {
+      tria = Triangulation();
+      tria.dim = 2;
+      const double left = compute_in_2d ? 0.0 : -0.3;
+      const int nx = compute_in_2d ? 22 : 25, ny = 4;
+      std::vector<double> xs(nx + 1), ys(ny + 1);
+      for (int i = 0; i <= nx; ++i) xs[i] = left + i * ((2.2 - left) / nx);
+      for (int j = 0; j <= ny; ++j) ys[j] = j * (0.41 / ny);
+      xs[nx] = 2.2;
+      ys[ny] = 0.41;
+      std::vector<int> vid((size_t)(nx + 1) * (ny + 1), -1);
+      auto vertex = [&](int i, int j) {
+        int &id = vid[(size_t)j * (nx + 1) + i];
+        if (id < 0)
+          {
+            id = tria.n_vertices();
+            tria.vertices.push_back(xs[i]);
+            tria.vertices.push_back(ys[j]);
+          }
+        return id;
+      };
+      // bulk cells whose centre is closer than 0.15 to (0.2, 0.2) are removed (the 2 x 2 block around the hole)
+      int i0 = nx, j0 = ny, n_removed = 0;
+      for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i)
+          {
+            const double cx = 0.5 * (xs[i] + xs[i + 1]) - 0.2, cy = 0.5 * (ys[j] + ys[j + 1]) - 0.2;
+            if (std::hypot(cx, cy) < 0.15)
+              {
+                i0 = std::min(i0, i);
+                j0 = std::min(j0, j);
+                ++n_removed;
+                continue;
+              }
+            const int cv[4] = {vertex(i, j), vertex(i + 1, j), vertex(i, j + 1), vertex(i + 1, j + 1)};
+            tria.cells.insert(tria.cells.end(), cv, cv + 4);
+          }
+      if (n_removed != 4) throw std::runtime_error("flow_around_cylinder: unexpected hole in the bulk mesh");
+      const int n_bulk = tria.n_cells();
+      // hyper_cube_with_cylindrical_hole(0.05, 0.41 / 4): 8 cells; its outer ring is merged onto the bulk lattice
+      // (merge_triangulations keeps the bulk coordinates), ring vertex k sits at the angle k * 45 degrees
+      const int ring[8][2] = {{2, 1}, {2, 2}, {1, 2}, {0, 2}, {0, 1}, {0, 0}, {1, 0}, {2, 0}};
+      int outer[8], inner[8];
+      for (int k = 0; k < 8; ++k) outer[k] = vertex(i0 + ring[k][0], j0 + ring[k][1]);
+      const double pi = 3.14159265358979323846;
+      for (int k = 0; k < 8; ++k)
+        {
+          inner[k] = tria.n_vertices();
+          // the circle's vertices are re-centred at (0.2, 0.2) (utilities.cpp:452-480)
+          tria.vertices.push_back(0.2 + 0.05 * std::cos(2 * pi * k / 8));
+          tria.vertices.push_back(0.2 + 0.05 * std::sin(2 * pi * k / 8));
+        }
+      if (with_charts)
+        {
+          tria.chart_of_cell.assign(n_bulk, -1);
+          tria.chart_box.assign((size_t)n_bulk * 4, 0.0);
+        }
+      for (int k = 0; k < 8; ++k)
+        {
+          const int k1 = (k + 1) % 8;
+          int cv[4] = {inner[k1], inner[k], outer[k1], outer[k]}; // arc = edge v0 -> v1 (local face 2)
+          auto X = [&](int v, int d) { return tria.vertices[(size_t)cv[v] * 2 + d]; };
+          const double area = (X(1, 0) - X(0, 0)) * (X(2, 1) - X(0, 1)) - (X(2, 0) - X(0, 0)) * (X(1, 1) - X(0, 1));
+          if (area < 0)
+            {
+              std::swap(cv[0], cv[1]);
+              std::swap(cv[2], cv[3]);
+            }
+          tria.cells.insert(tria.cells.end(), cv, cv + 4);
+          const int c = tria.n_cells() - 1;
+          const int bf[3] = {c, 2, 4};
+          tria.boundary_faces.insert(tria.boundary_faces.end(), bf, bf + 3);
+          if (with_charts)
+            {
+              PolarArcChart ch;
+              for (int v = 0; v < 4; ++v)
+                for (int d = 0; d < 2; ++d) ch.v[v][d] = tria.vertices[(size_t)cv[v] * 2 + d];
+              ch.c[0] = ch.c[1] = 0.2;
+              ch.init();
+              tria.charts.push_back(ch);
+              tria.chart_of_cell.push_back(k);
+              const double box[4] = {0.0, 0.0, 1.0, 1.0};
+              tria.chart_box.insert(tria.chart_box.end(), box, box + 4);
+            }
+        }
+      tria.material_id.assign(tria.n_cells(), 1);
+      // boundary faces of the bulk: edges that belong to one cell only
+      const int fv[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
+      std::map<std::pair<int, int>, std::pair<int, int>> edges; // edge -> (owner count, cell * 4 + face)
+      for (int c = 0; c < tria.n_cells(); ++c)
+        for (int f = 0; f < 4; ++f)
+          {
+            int a = tria.cells[(size_t)c * 4 + fv[f][0]], b = tria.cells[(size_t)c * 4 + fv[f][1]];
+            if (a > b) std::swap(a, b);
+            auto &e = edges[{a, b}];
+            e.first++;
+            e.second = c * 4 + f;
+          }
+      for (const auto &kv : edges)
+        {
+          if (kv.second.first != 1) continue;
+          const int c = kv.second.second / 4, f = kv.second.second % 4;
+          if (c >= n_bulk) continue; // the arcs were added with their cells
+          const double mx = 0.5 * (tria.vertices[(size_t)kv.first.first * 2] + tria.vertices[(size_t)kv.first.second * 2]);
+          const double my = 0.5 * (tria.vertices[(size_t)kv.first.first * 2 + 1] + tria.vertices[(size_t)kv.first.second * 2 + 1]);
+          int id = 4;
+          if (std::fabs(mx - 2.2) < 1e-12) id = 1;
+          else if (std::fabs(mx - left) < 1e-12) id = 0;
+          else if (std::fabs(my - 0.41) < 1e-12) id = 3;
+          else if (std::fabs(my) < 1e-12) id = 2;
+          const int bf[3] = {c, f, id};
+          tria.boundary_faces.insert(tria.boundary_faces.end(), bf, bf + 3);
+        }
+    }
+  } // namespace
+
+  void GridCreator::flow_around_cylinder(Triangulation &tria, int dim)
+  {
+    if (dim == 2)
+      {
+        cylinder_2d(tria, true, true);
+        return;
+      }
+    if (dim != 3) throw std::runtime_error("flow_around_cylinder: dim must be 2 or 3");
+    // GridGenerator::extrude_triangulation(tria_2d, 9, 0.41, tria): 9 slices = 8 layers; manifolds are not copied, so
+    // the 3-D mesh refines flat
+    Triangulation t2;
+    cylinder_2d(t2, false, false);
+    const int nv2 = t2.n_vertices(), nc2 = t2.n_cells(), layers = 8;
+    tria = Triangulation();
+    tria.dim = 3;
+    tria.vertices.reserve((size_t)nv2 * (layers + 1) * 3);
+    for (int k = 0; k <= layers; ++k)
+      for (int v = 0; v < nv2; ++v)
+        {
+          tria.vertices.push_back(t2.vertices[(size_t)v * 2]);
+          tria.vertices.push_back(t2.vertices[(size_t)v * 2 + 1]);
+          tria.vertices.push_back(k == layers ? 0.41 : k * (0.41 / layers));
+        }
+    for (int k = 0; k < layers; ++k)
+      for (int c = 0; c < nc2; ++c)
+        {
+          for (int up = 0; up < 2; ++up)
+            for (int v = 0; v < 4; ++v) tria.cells.push_back((k + up) * nv2 + t2.cells[(size_t)c * 4 + v]);
+          const int c3 = k * nc2 + c;
+          if (k == 0)
+            {
+              const int bf[3] = {c3, 4, 4};
+              tria.boundary_faces.insert(tria.boundary_faces.end(), bf, bf + 3);
+            }
+          if (k == layers - 1)
+            {
+              const int bf[3] = {c3, 5, 5};
+              tria.boundary_faces.insert(tria.boundary_faces.end(), bf, bf + 3);
+            }
+        }
+    for (int k = 0; k < layers; ++k)
+      for (int f = 0; f < t2.n_boundary_faces(); ++f)
+        {
+          const int id2 = t2.boundary_faces[3 * f + 2];
+          const int bf[3] = {k * nc2 + t2.boundary_faces[3 * f], t2.boundary_faces[3 * f + 1], id2 == 4 ? 6 : id2};
+          tria.boundary_faces.insert(tria.boundary_faces.end(), bf, bf + 3);
+        }
+    tria.material_id.assign(tria.n_cells(), 1);
   }
 
   void GridGenerator::hyper_cube(Triangulation &tria, int dim, double left, double right, bool colorize)
@@ -293,7 +489,39 @@ namespace ifem
                   new_bf.push_back(id);
                 }
           }
-        vertices = nt.coords;
+        std::vector<double> new_vertices = nt.coords;
+        if (dim == 2 && !chart_of_cell.empty())
+          {
+            // curved placement: lattice point (i, j) of a chart cell lies at chart(s0 + i/2 ds, t0 + j/2 dt)
+            std::vector<int> new_chart((size_t)nc * vpc);
+            std::vector<double> new_box((size_t)nc * vpc * 4);
+            for (int c = 0; c < nc; ++c)
+              {
+                const int ch = chart_of_cell[c];
+                const double *b = &chart_box[(size_t)c * 4];
+                const double ds = 0.5 * (b[2] - b[0]), dt = 0.5 * (b[3] - b[1]);
+                if (ch >= 0)
+                  for (int j = 0; j < 3; ++j)
+                    for (int i = 0; i < 3; ++i)
+                      {
+                        if (i != 1 && j != 1) continue; // corners exist already
+                        charts[ch].eval(b[0] + i * ds, b[1] + j * dt, &new_vertices[(size_t)nt.cell_nodes[(size_t)c * fe.n + i + 3 * j] * 2]);
+                      }
+                for (int child = 0; child < vpc; ++child)
+                  {
+                    const int cx = child & 1, cy = child >> 1;
+                    new_chart[(size_t)c * vpc + child] = ch;
+                    double *nb = &new_box[((size_t)c * vpc + child) * 4];
+                    nb[0] = b[0] + cx * ds;
+                    nb[1] = b[1] + cy * dt;
+                    nb[2] = b[0] + (cx + 1) * ds;
+                    nb[3] = b[1] + (cy + 1) * dt;
+                  }
+              }
+            chart_of_cell.swap(new_chart);
+            chart_box.swap(new_box);
+          }
+        vertices.swap(new_vertices);
         cells.swap(new_cells);
         material_id.swap(new_mat);
         boundary_faces.swap(new_bf);

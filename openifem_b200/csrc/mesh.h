@@ -17,6 +17,17 @@
 
 namespace ifem
 {
+  // Chart of one coarse cell next to a circular hole (2-D): corners v[0..3] in lexicographic order, the edge t = 0
+  // (v0 -> v1) is an arc about c (PolarManifold: linear in radius and angle), the other three edges are straight;
+  // points inside follow the transfinite interpolation of the four edges (TransfiniteInterpolationManifold).
+  struct PolarArcChart
+  {
+    double v[4][2], c[2];
+    double r0 = 0, r1 = 0, a0 = 0, da = 0;
+    void init();
+    void eval(double s, double t, double *x) const;
+  };
+
   struct Triangulation
   {
     int dim = 0;
@@ -24,6 +35,11 @@ namespace ifem
     std::vector<int> cells;          // [n_cells][2^dim], lexicographic (x fastest) vertex order
     std::vector<int> boundary_faces; // [n_bfaces][3] = (cell, face_no = 2*axis+side, boundary id)
     std::vector<int> material_id;    // [n_cells]
+    // optional curved description honoured by refine_global (2-D): a cell with chart_of_cell >= 0 occupies the
+    // rectangle chart_box = (s0, t0, s1, t1) of that chart and places its new vertices on it
+    std::vector<int> chart_of_cell;  // [n_cells] or empty
+    std::vector<double> chart_box;   // [n_cells][4]
+    std::vector<PolarArcChart> charts;
 
     int n_vertices() const { return dim ? (int)(vertices.size() / dim) : 0; }
     int verts_per_cell() const { return 1 << dim; }
@@ -40,6 +56,15 @@ namespace ifem
                                     const double *p2, bool colorize);
     void hyper_cube(Triangulation &tria, int dim, double left, double right, bool colorize);
   } // namespace GridGenerator
+
+  // Utils::GridCreator<dim>::flow_around_cylinder (reference source/utilities.cpp:343-574): channel
+  // [0, 2.2] x [0, 0.41] (3-D: [-0.3, 2.2] x [0, 0.41]^2, the 2-D mesh extruded in 8 layers, flat refinement) around
+  // a cylinder of diameter 0.1 about (0.2, 0.2). Boundary ids 2-D: 0 inflow, 1 outflow, 2 y = 0, 3 y = 0.41,
+  // 4 cylinder; 3-D: 0 / 1 x, 2 / 3 y, 4 / 5 z, 6 cylinder.
+  namespace GridCreator
+  {
+    void flow_around_cylinder(Triangulation &tria, int dim);
+  }
 
   // FE_Q(p) node numbering on a triangulation: nodes are unique geometric entities
   // (vertices, edge / face / cell midpoints for p = 2), numbered in lexicographic

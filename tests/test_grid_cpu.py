@@ -1,0 +1,49 @@
+"""Host-side mesh generation of the product (no GPU needed): Utils::GridCreator<dim>::flow_around_cylinder
+(reference source/utilities.cpp:343-574) and the manifold-aware refine_global against the oracle's restatement
+(oracle/grid.py), which reproduces the reference goldens of tests/fluid_cylinder_mpi* on that mesh."""
+import numpy as np
+import pytest
+
+import openifem_b200 as ifem
+from oracle import grid
+
+
+def _sorted(a):
+    return a[np.lexsort(a.T[::-1])]
+
+
+@pytest.mark.parametrize("level", [0, 1, 3])
+def test_cylinder_mesh_2d_matches_oracle(level):
+    t = ifem.Triangulation(2)
+    ifem.GridCreator.flow_around_cylinder(t)
+    t.refine_global(level)
+    v, c, b = t.get_mesh()
+    m = grid.flow_around_cylinder_2d(True).refine_global(level)
+    assert c.shape == m.cells.shape == (92 * 4 ** level, 4)
+    assert np.abs(_sorted(v) - _sorted(m.vertices)).max() < 1e-14
+    assert np.abs(_sorted(v[c].mean(axis=1)) - _sorted(m.vertices[m.cells].mean(axis=1))).max() < 1e-14
+    assert sorted(zip(*np.unique(b[:, 2], return_counts=True))) == sorted(zip(*np.unique(m.boundary_faces[:, 2], return_counts=True)))
+    # positively oriented cells, area of the channel minus the polygonal hole, vertices of the cylinder ON the circle
+    p = v[c]
+    area = 0.5 * ((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1]))
+    assert area.min() > 0
+    on_cyl = np.unique(np.concatenate([c[cell, [0, 1]] for cell, face, bid in b if bid == 4]))
+    assert len(on_cyl) == 8 * 2 ** level
+    assert np.abs(np.hypot(*(v[on_cyl] - 0.2).T) - 0.05).max() < 1e-14
+
+
+def test_cylinder_mesh_3d_extruded():
+    """GridCreator<3>: the 2-D mesh with left = -0.3 (25 x 4 bulk cells) extruded in 8 layers, boundary ids 0..6"""
+    t = ifem.Triangulation(3)
+    ifem.GridCreator.flow_around_cylinder(t)
+    v, c, b = t.get_mesh()
+    assert c.shape == ((25 * 4 - 4 + 8) * 8, 8)
+    assert v[:, 0].min() == -0.3 and v[:, 0].max() == 2.2 and v[:, 2].max() == 0.41
+    ids = dict(zip(*np.unique(b[:, 2], return_counts=True)))
+    assert ids == {0: 4 * 8, 1: 4 * 8, 2: 25 * 8, 3: 25 * 8, 4: 104, 5: 104, 6: 8 * 8}
+    # positive Jacobian at the first corner of every cell
+    p = v[c]
+    e1, e2, e3 = p[:, 1] - p[:, 0], p[:, 2] - p[:, 0], p[:, 4] - p[:, 0]
+    assert np.einsum("ij,ij->i", np.cross(e1, e2), e3).min() > 0
+    t.refine_global(1)
+    assert t.n_active_cells() == 832 * 8

@@ -239,3 +239,65 @@ def test_update_stress_q2_matches_oracle(dim, reps, hi):
     ref = o.update_stress()
     g.update_stress()
     assert rel(g.get_stress(), ref) < 1e-12
+
+
+def _cylinder_pair(prm_path, level, oracle_cls, **okw):
+    """the product's flow_around_cylinder mesh at a refinement level and an oracle solver on the SAME mesh arrays"""
+    import openifem_b200 as ifem
+    from oracle import grid, prm
+
+    tria = ifem.Triangulation(2)
+    ifem.GridCreator.flow_around_cylinder(tria)
+    tria.refine_global(level)
+    v, c, b = tria.get_mesh()
+    return tria, oracle_cls(grid.QuadMesh(v, c, b), prm.Params(prm_path), **okw)
+
+
+def test_assembly_on_cylinder_mesh_matches_oracle(golden_dir):
+    """mpi_insim.cpp:152-362 on NON-AFFINE cells (the O-grid around the cylinder, refined once on its polar /
+    transfinite charts): assembled system, rhs, diag(M_u), M_p and the block SpMV against the oracle, 1e-12"""
+    import os
+
+    import openifem_b200 as ifem
+    from oracle import ins
+
+    path = os.path.join(golden_dir, "ins_cylinder_2d.prm")
+    tria, o = _cylinder_pair(path, 1, ins.InsIM, mode="mpi")
+    g = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(path))
+    g.setup()
+    assert g.n_dofs == o.n
+    assert np.allclose(g.support_points(), o.dofs.support_points(), atol=1e-14)
+    rng = np.random.default_rng(21)
+    ev, pr = rng.uniform(-1, 1, o.n), rng.uniform(-1, 1, o.n)
+    o.evaluation_point[:], o.present[:] = ev, pr
+    g.set_vector(g.EVALUATION_POINT, ev)
+    g.set_vector(g.PRESENT, pr)
+    A_ref, M_ref, rhs_ref = o.assemble(True)
+    g.assemble(True)
+    assert _mat_rel(g.get_matrix(0), A_ref) < TOL_ASM
+    assert rel(g.get_vector(g.SYSTEM_RHS), rhs_ref) < TOL_ASM
+    assert rel(g.get_vector(g.DIAG_MU), M_ref.diagonal()[: o.n_u]) < TOL_ASM
+    assert _mat_rel(g.get_matrix(1), M_ref[o.n_u:, o.n_u:]) < TOL_ASM
+    x = rng.uniform(-1, 1, o.n)
+    assert rel(g.vmult(x), A_ref @ x) < 1e-12
+
+
+def test_cylinder_flow_golden_on_gpu(golden_dir):
+    """reference golden tests/fluid_cylinder_mpi/fluid_cylinder_mpi.cpp:83-93 through the device path (BASELINE config 2's
+    2-D twin): GridCreator<2>::flow_around_cylinder, Global refinements = 3, hard-coded parabolic inflow on id 0, one
+    time step; max velocity 0.374235 and max pressure 46.5226 to 1e-3"""
+    import os
+
+    import openifem_b200 as ifem
+
+    tria = ifem.Triangulation(2)
+    ifem.GridCreator.flow_around_cylinder(tria)
+    flow = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(os.path.join(golden_dir, "ins_cylinder_2d.prm")))
+    umax = 3 * 0.2 / 2
+    flow.add_hard_coded_boundary_condition(0, lambda p, c, t: 4 * umax * p[1] * (0.41 - p[1]) / 0.41 ** 2 if c == 0 and abs(p[0]) < 1e-10 else 0.0)
+    flow.run()
+    assert tria.n_active_cells() == 92 * 64
+    sol = flow.get_current_solution()
+    vmax, pmax = sol[: flow.n_u].max(), sol[flow.n_u:].max()
+    assert abs(vmax - 0.374235) / 0.374235 < 1e-3, vmax
+    assert abs(pmax - 46.5226) / 46.5226 < 1e-3, pmax

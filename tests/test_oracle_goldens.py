@@ -8,6 +8,11 @@ this path; everything else is checked GPU-vs-oracle.
                         reference tests/fluid_gravity/fluid_gravity.cpp:37-41
   fluid_pressure_driven (serial InsIM, 100x10 r=1, Neumann face term): max v = 2.5e-2 +-1e-3
                         reference tests/fluid_pressure_driven/fluid_pressure_driven.cpp:42-44
+  fluid_cylinder_mpi    (Fluid::MPI::InsIM on GridCreator<2>::flow_around_cylinder refined 3 times = 5 888 non-affine
+                        cells, hard-coded parabolic inflow, 1 step): max v = 0.374235, max p = 46.5226, +-1e-3
+                        reference tests/fluid_cylinder_mpi/fluid_cylinder_mpi.cpp:83-93
+  fluid_cylinder_mpi_scnsim (Fluid::MPI::SCnsIM, same mesh, Q1/Q1, 1 step): max v = 4.5, max p = 1.03544, +-1e-3
+                        reference tests/fluid_cylinder_mpi_scnsim/fluid_cylinder_mpi_scnsim.cpp:75-85
 """
 import os
 
@@ -42,6 +47,39 @@ def test_fluid_pressure_driven_golden(golden_dir):
     s = _run(golden_dir, "ins_pressure_driven_2d.prm", (100, 10), (0, 0), (2.0, 0.2), "serial")
     vmax = s.velocity().max()
     assert abs(vmax - 2.5e-2) / 2.5e-2 < 1e-3
+
+
+def cylinder_inflow(umax, t_end=None):
+    """the inflow_bc lambdas of tests/fluid_cylinder_mpi*.cpp (2-D): parabolic u_x on x = 0"""
+    def f(pt, c, t):
+        if c == 0 and abs(pt[0]) < 1e-10 and (t_end is None or t < t_end):
+            return 4 * umax * pt[1] * (0.41 - pt[1]) / (0.41 * 0.41)
+        return 0.0
+    return f
+
+
+def test_fluid_cylinder_mpi_golden(golden_dir):
+    from oracle import grid
+
+    p = prm.Params(os.path.join(golden_dir, "ins_cylinder_2d.prm"))
+    mesh = grid.flow_around_cylinder_2d(True).refine_global(p.global_refinements[0])
+    assert mesh.n_cells == 92 * 64
+    s = ins.InsIM(mesh, p, mode="mpi", hard_coded={0: cylinder_inflow(3 * 0.2 / 2)})
+    s.run()
+    # the oracle reproduces both numbers to the digits the reference prints (7.8e-7, 4.5e-7)
+    assert abs(s.velocity().max() - 0.374235) / 0.374235 < 1e-5
+    assert abs(s.pressure().max() - 46.5226) / 46.5226 < 1e-5
+
+
+def test_fluid_cylinder_mpi_scnsim_golden(golden_dir):
+    from oracle import grid, scns
+
+    p = prm.Params(os.path.join(golden_dir, "scns_cylinder_2d.prm"))
+    mesh = grid.flow_around_cylinder_2d(True).refine_global(p.global_refinements[0])
+    s = scns.SCnsIM(mesh, p, hard_coded={0: cylinder_inflow(3 * 3 / 2, t_end=2 * p.time_step)})
+    s.run()
+    assert abs(s.present[: s.n_u].max() - 4.5) / 4.5 < 1e-3
+    assert abs(s.present[s.n_u:].max() - 1.03544) / 1.03544 < 1e-4  # 4e-6 in fact; the golden has 6 digits
 
 
 # ---- Solid::MPI::HyperElasticity + NeoHookean (oracle/solid.py) ------------------------------------

@@ -202,3 +202,23 @@ def test_body_force_reference_golden(golden_dir):
     flow.run()
     p = flow.get_current_solution()[flow.n_u:]
     assert abs((p.max() - p.min()) - 1e3) / 1e3 < 1e-3
+
+
+def test_cylinder_flow_scnsim_golden_on_gpu(golden_dir):
+    """reference golden tests/fluid_cylinder_mpi_scnsim/fluid_cylinder_mpi_scnsim.cpp:75-85 through the device path:
+    SCnsIM Q1/Q1 on GridCreator<2>::flow_around_cylinder refined 3 times, hard-coded inflow (active while t < 2 dt), one
+    time step; max velocity 4.5, max pressure 1.03544 to 1e-3"""
+    import openifem_b200 as ifem
+
+    tria = ifem.Triangulation(2)
+    ifem.GridCreator.flow_around_cylinder(tria)
+    params = ifem.Parameters.AllParameters(os.path.join(golden_dir, "scns_cylinder_2d.prm"))
+    flow = ifem.Fluid.MPI.SCnsIM(tria, params)
+    dt = 1e-2
+    flow.add_hard_coded_boundary_condition(
+        0, lambda p, c, t: 4 * 4.5 * p[1] * (0.41 - p[1]) / 0.41 ** 2 if c == 0 and abs(p[0]) < 1e-10 and t < 2 * dt else 0.0)
+    flow.run()
+    sol = flow.get_current_solution()
+    vmax, pmax = sol[: flow.n_u].max(), sol[flow.n_u:].max()
+    assert abs(vmax - 4.5) / 4.5 < 1e-3, vmax
+    assert abs(pmax - 1.03544) / 1.03544 < 1e-3, pmax

@@ -222,7 +222,7 @@ extern "C" int oracle_ins_assemble(
 extern "C" void oracle_spmv_csr(int64_t n_rows, const int64_t *rowptr, const int *col, const double *val, const double *x,
                                 double *y)
 {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n_rows > 100000)
   for (int64_t r = 0; r < n_rows; ++r)
     {
       double s = 0;

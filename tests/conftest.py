@@ -20,8 +20,8 @@ def pytest_addoption(parser):
 
 
 def pytest_collection_modifyitems(config, items):
-    # the slow oracle goldens (pressure-driven 80 steps, SCnsIM body force 500 steps) take minutes on CPU; they were
-    # run when the oracle was pinned (results quoted in DESIGN.md) and are opt-in: --runslow or IFEM_RUN_SLOW=1
+    # the slow oracle golden (SCnsIM body force, 500 steps) takes minutes on CPU; it was
+    # run when the oracle was pinned (result quoted in DESIGN.md) and is opt-in: --runslow or IFEM_RUN_SLOW=1
     if config.getoption("--runslow") or os.environ.get("IFEM_RUN_SLOW") == "1":
         return
     skip = pytest.mark.skip(reason="slow oracle golden: use --runslow")

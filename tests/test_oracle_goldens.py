@@ -42,7 +42,6 @@ def test_fluid_gravity_golden(golden_dir):
     assert abs((p.max() - p.min()) - 20) / 20 < 1e-3
 
 
-@pytest.mark.slow
 def test_fluid_pressure_driven_golden(golden_dir):
     s = _run(golden_dir, "ins_pressure_driven_2d.prm", (100, 10), (0, 0), (2.0, 0.2), "serial")
     vmax = s.velocity().max()

@@ -328,13 +328,68 @@ class FSI:
     def __init__(self, fluid, solid, use_dirichlet_bc=False):
         self.fluid, self.solid, self.use_dirichlet_bc = fluid, solid, use_dirichlet_bc
         self.base_con, self.base_val = fluid.con.copy(), fluid.nonzero_val.copy()
+        self.penetration_criterion, self.penetration_direction = None, None
+        self.contact_iterations = 0
+
+    def set_penetration_criterion(self, criterion, direction):
+        """FSI::set_penetration_criterion (mpi_fsi.cpp:1229-1237): criterion(point) > 1e-5 means the point penetrates"""
+        self.penetration_criterion = criterion
+        self.penetration_direction = np.asarray(direction, dtype=float)
+
+    def apply_contact_model(self, first_step):
+        """FSI::apply_contact_model (mpi_fsi.cpp:869-970): repeat the solid step, each time adding a stress
+        multiplier * penetration along the penetration direction to fsi_stress_rows at the penetrating boundary
+        vertices (once per (cell, boundary face, face vertex) visit), until no boundary vertex penetrates"""
+        s = self.solid
+        dim = s.dim
+        mult = s.prm.contact_force_multiplier
+        dirn = self.penetration_direction
+        cached = [v.copy() for v in (s.cur_a, s.cur_v, s.cur_u, s.prev_a, s.prev_v, s.prev_u)]
+        still = True
+        while still:
+            still = False
+            s.run_one_step(first_step)
+            self.contact_iterations += 1
+            x = deformed(s.mesh.vertices, s.cur_u, dim)
+            for (cell, face, fid) in s.mesh.boundary_faces:
+                axis, side = int(face) // 2, int(face) % 2
+                cn = s.mesh.cells[cell]
+                J = np.einsum("vi,vj->ij", x[cn], s.face_dG[face][0])
+                nds = np.linalg.det(J) * np.linalg.inv(J)[axis, :] * (1.0 if side else -1.0)
+                normal = nds / np.linalg.norm(nds)  # fe_face_values.normal_vector(0) on the moved mesh
+                for a in fem.face_local_nodes(dim, 1, int(face)):
+                    node = int(cn[a])
+                    pen = self.penetration_criterion(x[node])
+                    if not pen > 1e-5:
+                        continue
+                    still = True
+                    traction = mult * pen / np.linalg.norm(dirn) * dirn
+                    for d1 in range(dim):
+                        extra = traction[d1] / normal[d1] if normal[d1] > 1e-5 else 0.0
+                        s.fsi_stress_rows[d1, dim * node + dim - 1] += extra
+            if still:
+                s.cur_a, s.cur_v, s.cur_u, s.prev_a, s.prev_v, s.prev_u = [v.copy() for v in cached]
+                s.time -= s.dt
+                s.timestep -= 1
+
+    def run(self):
+        """the time loop of FSI::run (mpi_fsi.cpp:1172-1226) without refinement / checkpoints"""
+        p = self.fluid.prm
+        t, first = 0.0, True
+        while p.end_time - t > 1e-12:
+            self.run_one_step(first)
+            first = False
+            t += p.time_step
 
     def run_one_step(self, first_step):
         f, s = self.fluid, self.solid
         dim = f.dim
         s.fsi_stress_rows, s.fluid_velocity, s.fluid_pressure = find_solid_bc(
             f, s.mesh, s.cur_u, s.prm.solid_dirichlet_bcs, getattr(f, "stress", None))
-        s.run_one_step(first_step)
+        if self.penetration_criterion is not None:
+            self.apply_contact_model(first_step)
+        else:
+            s.run_one_step(first_step)
         geo = SolidGeometry(s.mesh, s.cur_u)
         f.indicator[:] = update_indicator(f.mesh, geo)
         # make_constraints(); after the first step the nonzero constraints become the zero ones

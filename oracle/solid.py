@@ -63,7 +63,10 @@ class SolidDofs:
         self.cell_dofs = (self.nodes[:, :, None] * dim + np.arange(dim)[None, None, :]).reshape(mesh.n_cells, npc * dim).astype(np.int32)
 
 
-class HyperElasticity:
+class SolidBase:
+    """what Solid::MPI::SolidSolver / SharedSolidSolver set up for every material (mpi_solid_solver.cpp:43-161,
+    mpi_shared_solid_solver.cpp:45-234): FE_Q(1)^dim, QGauss(2), homogeneous Dirichlet constraints, Newmark vectors"""
+
     def __init__(self, mesh: fem.BoxMesh, params, verbose=False):
         self.mesh, self.prm, self.verbose = mesh, params, verbose
         dim = mesh.dim
@@ -104,8 +107,7 @@ class HyperElasticity:
                     for c in comps:
                         self.con[dim * self.dofs.nodes[cell, a] + c] = 1
         self.rowptr, self.col = fem.full_pattern(self.dofs.cell_dofs, self.n)
-        c = params.C[0]
-        self.c1, self.kappa, self.rho = c[0], c[1], params.solid_rho
+        self.rho = params.solid_rho
         self.dt = params.time_step
         self.time, self.timestep = 0.0, 0
         z = lambda: np.zeros(self.n)
@@ -115,6 +117,100 @@ class HyperElasticity:
         self.fsi_stress_rows = np.zeros((dim, self.n))
         self.fluid_velocity = np.zeros(self.n)
         self.fluid_pressure = np.zeros(self.dofs.n_nodes)
+        # initial velocity (mpi_shared_solid_solver.cpp:152-196, mpi_solid_solver.cpp:116-137), constraints distributed
+        iv = np.asarray(list(params.initial_velocity)[:dim], dtype=float)
+        if np.any(iv != 0):
+            self.prev_v = np.tile(iv, self.dofs.n_nodes)
+            self.prev_v[self.con != 0] = 0.0
+            self.cur_v = self.prev_v.copy()
+
+    # -- Neumann faces: traction / pressure w.r.t. the reference configuration, or (FSI) sigma_f n on the deformed face --
+    def face_rhs(self, rhs):
+        dim, npc, p = self.dim, self.npc, self.prm
+        if p.simulation_type == "FSI":
+            # FSI traction sigma_f n on the deformed face (mpi_shared_hyper_elasticity.cpp:495-554,
+            # mpi_shared_linear_elasticity.cpp:193-271)
+            rows = self.fsi_stress_rows.reshape(dim, -1, dim)  # [d1][node][d2]
+            xdef = self.mesh.vertices + self.cur_u.reshape(-1, dim)
+            for (cell, face, fid) in self.mesh.boundary_faces:
+                axis, side = face // 2, face % 2
+                cn = self.mesh.cells[cell]
+                X = xdef[cn]
+                for q in range(self.fw.size):
+                    J = np.einsum("vi,vj->ij", X, self.face_dG[face][q])
+                    nds = np.linalg.det(J) * np.linalg.inv(J)[axis, :] * (1.0 if side else -1.0)
+                    dS = np.linalg.norm(nds)
+                    sigma = np.einsum("b,ibj->ij", self.face_N[face][q], rows[:, self.dofs.nodes[cell], :])
+                    traction = sigma @ (nds / dS)
+                    for a in range(npc):
+                        for c in range(dim):
+                            rhs[cell, a * dim + c] += self.face_N[face][q, a] * traction[c] * dS * self.fw[q]
+        if p.simulation_type != "FSI" and p.solid_neumann_bcs:
+            for (cell, face, fid) in self.mesh.boundary_faces:
+                if (self.skip_dirichlet_faces and fid in p.solid_dirichlet_bcs) or fid not in p.solid_neumann_bcs:
+                    continue
+                axis, side = face // 2, face % 2
+                X = self.mesh.vertices[self.mesh.cells[cell]]
+                val = p.solid_neumann_bcs[fid]
+                for q in range(self.fw.size):
+                    J = np.einsum("vi,vj->ij", X, self.face_dG[face][q])
+                    nds = np.linalg.det(J) * np.linalg.inv(J)[axis, :] * (1.0 if side else -1.0)  # n dS / w
+                    dS = np.linalg.norm(nds)
+                    if p.solid_neumann_bc_type == "Traction":
+                        traction = np.asarray(val[:dim], dtype=float)
+                    else:
+                        traction = (nds / dS) * val[0]
+                    for a in range(npc):
+                        for c in range(dim):
+                            rhs[cell, a * dim + c] += self.face_N[face][q, a] * traction[c] * dS * self.fw[q]
+
+    skip_dirichlet_faces = True  # mpi_hyper_elasticity.cpp:452-456 skips faces with a Dirichlet id; the linear solvers do not
+
+    def scatter(self, K, f):
+        """constraints.distribute_local_to_global with homogeneous constraints: constrained rows keep |K_ii| on the
+        diagonal, constrained columns are dropped; K [nc][n][n] or None, f [nc][n] or None"""
+        cd = self.dofs.cell_dofs
+        n = cd.shape[1]
+        con = self.con
+        A = rhs = None
+        if K is not None:
+            rows = np.repeat(cd, n, axis=1).ravel()
+            cols = np.tile(cd, (1, n)).ravel()
+            vals = K.reshape(-1).copy()
+            rc, cc = con[rows] != 0, con[cols] != 0
+            diag = rows == cols
+            loc_diag = np.tile(np.eye(n, dtype=bool).ravel(), cd.shape[0])
+            keep = (~rc & ~cc) | (rc & diag & loc_diag)
+            vals = np.where(rc & diag & loc_diag, np.abs(vals), vals)
+            A = sp.coo_matrix((vals[keep], (rows[keep], cols[keep])), shape=(self.n, self.n)).tocsr()
+        if f is not None:
+            rhs = np.zeros(self.n)
+            fr = f.ravel().copy()
+            fr[con[cd.ravel()] != 0] = 0.0
+            np.add.at(rhs, cd.ravel(), fr)
+        return A, rhs
+
+    def solve(self, A, b):
+        x = spla.spsolve(A.tocsc(), b)
+        x[self.con != 0] = 0.0  # constraints.distribute
+        return x
+
+    def get_error(self, v):
+        t = v.copy()
+        t[self.con != 0] = 0.0
+        return np.linalg.norm(t)
+
+    def run(self):
+        self.run_one_step(True)
+        while self.prm.end_time - self.time > 1e-12:
+            self.run_one_step(False)
+
+
+class HyperElasticity(SolidBase):
+    def __init__(self, mesh: fem.BoxMesh, params, verbose=False):
+        super().__init__(mesh, params, verbose)
+        c = params.C[0]
+        self.c1, self.kappa = c[0], c[1]
         self.update_qph(self.cur_u)
 
     # -- update_qph (:241-275) ------------------------------------------------
@@ -169,81 +265,18 @@ class HyperElasticity:
             # geometric term for equal components: g_a . tau . g_b
             geo = np.einsum("cqak,cqkl,cqbl,cq->cab", g, self.tau, g, w, optimize=True)
             K += np.einsum("cab,ij->caibj", geo, I).reshape(nc, n, n)
-        # Neumann faces (:445-505)
-        p = self.prm
-        if p.simulation_type == "FSI":
-            # FSI traction sigma_f n on the deformed face (mpi_shared_hyper_elasticity.cpp:495-554)
-            rows = self.fsi_stress_rows.reshape(dim, -1, dim)  # [d1][node][d2]
-            xdef = self.mesh.vertices + self.cur_u.reshape(-1, dim)
-            for (cell, face, fid) in self.mesh.boundary_faces:
-                axis, side = face // 2, face % 2
-                cn = self.mesh.cells[cell]
-                X = xdef[cn]
-                for q in range(self.fw.size):
-                    J = np.einsum("vi,vj->ij", X, self.face_dG[face][q])
-                    nds = np.linalg.det(J) * np.linalg.inv(J)[axis, :] * (1.0 if side else -1.0)
-                    dS = np.linalg.norm(nds)
-                    sigma = np.einsum("b,ibj->ij", self.face_N[face][q], rows[:, self.dofs.nodes[cell], :])
-                    traction = sigma @ (nds / dS)
-                    for a in range(npc):
-                        for c in range(dim):
-                            rhs[cell, a * dim + c] += self.face_N[face][q, a] * traction[c] * dS * self.fw[q]
-        if p.simulation_type != "FSI" and p.solid_neumann_bcs:
-            for (cell, face, fid) in self.mesh.boundary_faces:
-                if fid in p.solid_dirichlet_bcs or fid not in p.solid_neumann_bcs:
-                    continue
-                axis, side = face // 2, face % 2
-                X = self.mesh.vertices[self.mesh.cells[cell]]
-                val = p.solid_neumann_bcs[fid]
-                for q in range(self.fw.size):
-                    J = np.einsum("vi,vj->ij", X, self.face_dG[face][q])
-                    nds = np.linalg.det(J) * np.linalg.inv(J)[axis, :] * (1.0 if side else -1.0)  # n dS / w
-                    dS = np.linalg.norm(nds)
-                    if p.solid_neumann_bc_type == "Traction":
-                        traction = np.asarray(val[:dim], dtype=float)
-                    else:
-                        traction = (nds / dS) * val[0]
-                    for a in range(npc):
-                        for c in range(dim):
-                            rhs[cell, a * dim + c] += self.face_N[face][q, a] * traction[c] * dS * self.fw[q]
+        self.face_rhs(rhs)  # Neumann faces (:445-505)
         return K, rhs
 
     def assemble_system(self, initial_step):
         K, f = self.local_matrices(initial_step)
-        cd = self.dofs.cell_dofs
-        n = cd.shape[1]
-        con = self.con
-        # distribute_local_to_global with homogeneous constraints: constrained rows keep |K_ii| on the
-        # diagonal, constrained columns are dropped
-        rows = np.repeat(cd, n, axis=1).ravel()
-        cols = np.tile(cd, (1, n)).ravel()
-        vals = K.reshape(-1).copy()
-        rc, cc = con[rows] != 0, con[cols] != 0
-        diag = rows == cols
-        loc_diag = np.tile(np.eye(n, dtype=bool).ravel(), cd.shape[0])
-        keep = (~rc & ~cc) | (rc & diag & loc_diag)
-        vals = np.where(rc & diag & loc_diag, np.abs(vals), vals)
-        A = sp.coo_matrix((vals[keep], (rows[keep], cols[keep])), shape=(self.n, self.n)).tocsr()
-        rhs = np.zeros(self.n)
-        fr = f.ravel().copy()
-        fr[con[cd.ravel()] != 0] = 0.0
-        np.add.at(rhs, cd.ravel(), fr)
+        A, rhs = self.scatter(K, f)
         if initial_step:
             self.mass_matrix = A
         else:
             self.system_matrix = A
         self.system_rhs = rhs
         return A, rhs
-
-    def solve(self, A, b):
-        x = spla.spsolve(A.tocsc(), b)
-        x[self.con != 0] = 0.0  # constraints.distribute
-        return x
-
-    def get_error(self, v):
-        t = v.copy()
-        t[self.con != 0] = 0.0
-        return np.linalg.norm(t)
 
     # -- run_one_step (:83-207) --------------------------------------------------
     def run_one_step(self, first_step):
@@ -289,7 +322,129 @@ class HyperElasticity:
         self.prev_a, self.prev_v, self.prev_u = self.cur_a.copy(), self.cur_v.copy(), self.cur_u.copy()
         self.update_strain_and_stress()
 
-    def run(self):
-        self.run_one_step(True)
-        while self.prm.end_time - self.time > 1e-12:
-            self.run_one_step(False)
+
+# ------------------------------------------------------------------------------------------------------------------
+# Solid::MPI::LinearElasticity (source/mpi_linear_elasticity.cpp) and Solid::MPI::SharedLinearElasticity
+# (source/mpi_shared_linear_elasticity.cpp), material source/linear_elastic_material.cpp:5-62
+# ------------------------------------------------------------------------------------------------------------------
+def linear_elastic_tensors(dim, E, nu, eta):
+    """LinearElasticMaterial::get_elasticity / get_viscosity (linear_elastic_material.cpp:16-62)"""
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    mu = E / (2 * (1 + nu))
+    I = np.eye(dim)
+    ikjl, iljk, ijkl = np.einsum("ik,jl->ijkl", I, I), np.einsum("il,jk->ijkl", I, I), np.einsum("ij,kl->ijkl", I, I)
+    return mu * (ikjl + iljk) + lam * ijkl, 0.5 * eta * (ikjl + iljk)
+
+
+class LinearElasticity(SolidBase):
+    """shared = False: Solid::MPI::LinearElasticity (p4est twin used stand-alone): gamma = 1/2 + damping, beta = gamma / 2,
+                       system = M + beta dt^2 K (mpi_linear_elasticity.cpp:31-32, 96-121), Neumann faces only.
+       shared = True : Solid::MPI::SharedLinearElasticity (the twin MPI::FSI drives): alpha = -damping, gamma = 1/2 - alpha,
+                       beta = (1 + alpha)^2 / 4 in assemble_system but (1 - alpha)^2 / 4 in run_one_step - the reference's
+                       own inconsistency, kept (mpi_shared_linear_elasticity.cpp:30-32, 305-307); viscous damping matrix
+                       from eta; FSI traction on the deformed faces; nodal strain / stress recovery every step."""
+
+    skip_dirichlet_faces = False
+
+    def __init__(self, mesh: fem.BoxMesh, params, shared=False, verbose=False):
+        super().__init__(mesh, params, verbose)
+        self.shared = shared
+        eta = params.eta[0] if getattr(params, "eta", None) else 0.0
+        self.elasticity, self.viscosity = linear_elastic_tensors(self.dim, params.E[0], params.nu[0], eta)
+        n_nodes = self.dofs.n_nodes
+        self.stress = np.zeros((self.dim * self.dim, n_nodes))
+        self.strain = np.zeros((self.dim * self.dim, n_nodes))
+
+    def _forms(self):
+        dim, nc, npc, nq = self.dim, self.mesh.n_cells, self.npc, self.nq
+        n = npc * dim
+        I = np.eye(dim)
+        gp = np.einsum("ir,cqak->cqairk", I, self.G)  # grad phi_(a,i) [r][k] = delta(r,i) G[a][k]
+        sgp = (0.5 * (gp + np.swapaxes(gp, -1, -2))).reshape(nc, nq, n, dim, dim)
+        phi = np.einsum("qa,ir->qair", self.N, I).reshape(nq, n, dim)
+        return sgp, phi
+
+    def assemble_system(self, is_initial):
+        p, dt, w = self.prm, self.dt, self.JxW
+        sgp, phi = self._forms()
+        grav = np.asarray(p.gravity[: self.dim], dtype=float)
+        f = self.rho * np.einsum("qir,r,cq->ci", phi, grav, w)
+        self.face_rhs(f)
+        mass = lambda: self.rho * np.einsum("qir,qjr,cq->cij", phi, phi, w)
+        stiff = lambda C: np.einsum("cqirs,rstu,cqjtu,cq->cij", sgp, C, sgp, w, optimize=True)
+        if not self.shared:
+            gamma = 0.5 + p.damping
+            beta = gamma / 2
+            if is_initial:
+                self.system_matrix, self.system_rhs = self.scatter(mass(), f)
+                self.stiffness_matrix = sp.csr_matrix((self.n, self.n))
+            else:
+                Ke = stiff(self.elasticity)
+                self.system_matrix, self.system_rhs = self.scatter(mass() + beta * dt * dt * Ke, f)
+                self.stiffness_matrix, _ = self.scatter(Ke, None)
+            return
+        alpha = -p.damping
+        gamma = 0.5 - alpha
+        beta = (1 + alpha) ** 2 / 4
+        if is_initial:
+            M, Ke, Ce = mass(), stiff(self.elasticity), stiff(self.viscosity)
+            self.mass_matrix, _ = self.scatter(M, None)
+            self.system_matrix, _ = self.scatter(M + Ce * gamma * dt * (1 + alpha) + Ke * beta * dt * dt * (1 + alpha), None)
+            self.stiffness_matrix, _ = self.scatter(Ke, None)
+            self.damping_matrix, _ = self.scatter(Ce, None)
+        _, self.system_rhs = self.scatter(None, f)
+
+    def run_one_step(self, first_step):
+        p, dt = self.prm, self.dt
+        if not self.shared:
+            gamma = 0.5 + p.damping
+            beta = gamma / 2
+            if first_step:
+                self.assemble_system(True)
+                self.prev_a = self.solve(self.system_matrix, self.system_rhs)
+                self.assemble_system(False)
+            self.time += dt
+            self.timestep += 1
+            tmp2 = self.prev_u + dt * self.prev_v + (0.5 - beta) * dt * dt * self.prev_a
+            tmp1 = self.system_rhs - self.stiffness_matrix @ tmp2
+        else:
+            alpha = -p.damping
+            gamma = 0.5 - alpha
+            beta = (1 - alpha) ** 2 / 4
+            if first_step:
+                self.assemble_system(True)
+                self.prev_a = self.solve(self.mass_matrix, self.system_rhs)
+            elif p.simulation_type == "FSI":
+                self.assemble_system(False)
+            self.time += dt
+            self.timestep += 1
+            tmp2 = self.prev_u + (1 + alpha) * dt * self.prev_v + (0.5 - beta) * dt * dt * (1 + alpha) * self.prev_a
+            tmp4 = self.prev_v + (1 + alpha) * (1 - gamma) * dt * self.prev_a
+            tmp1 = self.system_rhs - self.stiffness_matrix @ tmp2 - self.damping_matrix @ tmp4
+        self.cur_a = self.solve(self.system_matrix, tmp1)
+        self.cur_v = self.prev_v + dt * (1 - gamma) * self.prev_a + dt * gamma * self.cur_a
+        self.cur_u = self.prev_u + dt * self.prev_v + dt * dt * (0.5 - beta) * self.prev_a + dt * dt * beta * self.cur_a
+        self.prev_a, self.prev_v, self.prev_u = self.cur_a.copy(), self.cur_v.copy(), self.cur_u.copy()
+        if self.shared:
+            self.update_strain_and_stress()
+
+    # -- SharedLinearElasticity::update_strain_and_stress (mpi_shared_linear_elasticity.cpp:401-531) ----------------
+    def update_strain_and_stress(self):
+        dim, nodes = self.dim, self.dofs.nodes
+        Mref = np.einsum("qi,qj,q->ij", self.N, self.N, self.qw)
+        qpt_to_dof = np.linalg.solve(Mref, (self.N * self.qw[:, None]).T)
+        ue = self.cur_u[self.dofs.cell_dofs].reshape(self.mesh.n_cells, self.npc, dim)
+        grad_u = np.einsum("cai,cqak->cqik", ue, self.G)
+        quad_strain = 0.5 * (grad_u + np.swapaxes(grad_u, -1, -2))
+        quad_stress = np.einsum("ijkl,cqkl->cqij", self.elasticity, quad_strain)
+        cs = np.einsum("aq,cqij->cija", qpt_to_dof, quad_stress)
+        ce = np.einsum("aq,cqij->cija", qpt_to_dof, quad_strain)
+        n = self.dofs.n_nodes
+        stress, strain, count = np.zeros((dim * dim, n)), np.zeros((dim * dim, n)), np.zeros(n)
+        np.add.at(count, nodes.ravel(), 1.0)
+        for i in range(dim):
+            for j in range(dim):
+                np.add.at(stress[i * dim + j], nodes.ravel(), cs[:, i, j, :].ravel())
+                np.add.at(strain[i * dim + j], nodes.ravel(), ce[:, i, j, :].ravel())
+        self.stress, self.strain = stress / count, strain / count
+        return self.stress, self.strain

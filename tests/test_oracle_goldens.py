@@ -13,6 +13,11 @@ this path; everything else is checked GPU-vs-oracle.
                         reference tests/fluid_cylinder_mpi/fluid_cylinder_mpi.cpp:83-93
   fluid_cylinder_mpi_scnsim (Fluid::MPI::SCnsIM, same mesh, Q1/Q1, 1 step): max v = 4.5, max p = 1.03544, +-1e-3
                         reference tests/fluid_cylinder_mpi_scnsim/fluid_cylinder_mpi_scnsim.cpp:75-85
+  solid_beam_bending_mpi_linearelastic / _shared_linearelastic (Solid::MPI::LinearElasticity and SharedLinearElasticity,
+                        64 x 8 Q1 cells, 200 steps): u_min = -0.1337 +-1e-3
+                        reference tests/solid_beam_bending_mpi_linearelastic/solid_beam_bending_mpi_linearelastic.cpp:50-53
+  fsi_contact_model_mpi (MPI::FSI<2> = SCnsIM Q1/Q1 + SharedLinearElasticity + apply_contact_model, 1 step): solid
+                        u_min = -0.01999 +-1e-3; reference tests/fsi_contact_model_mpi/fsi_contact_model_mpi.cpp:46-60
 """
 import os
 
@@ -137,3 +142,57 @@ def test_scns_body_force_golden(golden_dir):
     s.run()
     pr = s.pressure()
     assert abs((pr.max() - pr.min()) - 1e3) / 1e3 < 1e-3
+
+
+# ---- Solid::MPI::LinearElasticity / SharedLinearElasticity (oracle/solid.py) -----------------------------------
+@pytest.mark.parametrize("shared", [False, True])
+def test_solid_beam_bending_linearelastic_golden(golden_dir, shared):
+    from oracle import solid
+
+    p = prm.Params(os.path.join(golden_dir, "solid_beam_linearelastic_2d.prm"))
+    mesh = fem.BoxMesh((32, 4), (0, 0), (8.0, 1.0)).refine_global(p.global_refinements[1])
+    s = solid.LinearElasticity(mesh, p, shared=shared)
+    s.run()
+    assert s.timestep == 200
+    assert abs(s.cur_u.min() + 0.1337) / 0.1337 < 1e-3  # -0.133703 in fact; the golden has 4 digits
+
+
+def test_solid_free_fall_linearelastic():
+    """the physics of tests/solid_gravity_linearelastic (unconstrained body under gravity -10 for 1 s: u_min = -5.0 +-1e-3,
+    solid_gravity_linearelastic.cpp:54-56) on a box instead of GridCreator::sphere: Newmark(beta = 1/4) integrates a constant
+    acceleration exactly, so the fall is -g t^2 / 2 whatever the mesh"""
+    from oracle import solid
+
+    text = open(os.path.join(golden_dir_path(), "solid_beam_linearelastic_2d.prm")).read()
+    text = text.replace("Global refinements = 0, 1", "Global refinements = 0, 0").replace("End time = 2e2", "End time = 1")
+    text = text.replace("Time step size = 1e0", "Time step size = 0.2").replace("Gravity = 0.0, 0.0", "Gravity = 0.0, -10")
+    text = text.replace("Number of Dirichlet BCs = 1", "Number of Dirichlet BCs = 0").replace("Number of Neumann BCs = 1", "Number of Neumann BCs = 0")
+    text = text.replace("Solid density = 1", "Solid density = 1225").replace("Young's modulus = 2.5", "Young's modulus = 5.25e2")
+    p = prm.Params(text, is_text=True)
+    s = solid.LinearElasticity(fem.BoxMesh((6, 6), (-0.25, -0.25), (0.25, 0.25)), p)
+    s.run()
+    assert abs(s.cur_u.min() + 5.0) / 5.0 < 1e-10
+
+
+def golden_dir_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def contact_problem(golden_dir):
+    """the meshes, solvers and penetration criterion of tests/fsi_contact_model_mpi/fsi_contact_model_mpi.cpp:28-50"""
+    from oracle import fsi, scns, solid
+
+    p = prm.Params(os.path.join(golden_dir, "fsi_contact_model_2d.prm"))
+    fluid = scns.SCnsIM(fem.BoxMesh((50, 25), (0, 0), (2.0, 1.0)), p)
+    sol = solid.LinearElasticity(fem.BoxMesh((10, 11), (0.25, 0.0), (1.25, 1.02)), p, shared=True)  # shifted by (0.25, 0)
+    c = fsi.FSI(fluid, sol)
+    c.set_penetration_criterion(lambda pt: pt[1] - 1.0, [0.0, -1.0])
+    return c
+
+
+def test_fsi_contact_model_mpi_golden(golden_dir):
+    c = contact_problem(golden_dir)
+    c.run()
+    umin = c.solid.cur_u.min()
+    assert abs(umin + 0.01999) / 0.01999 < 1e-3  # -0.0199930: the top ends 9.5e-6 above the wall after 38 contact iterations
+    assert c.contact_iterations == 38

@@ -53,6 +53,33 @@ namespace dealii
     std::array<double, dim> x;
   };
 
+  // Tensor<1, dim> as the drivers use it: brace-initialised from a list, indexed, norm()
+  template <int rank, int dim>
+  class Tensor
+  {
+    static_assert(rank == 1, "only Tensor<1, dim> is provided");
+
+  public:
+    Tensor() { x.fill(0.0); }
+    Tensor(std::initializer_list<double> v)
+    {
+      x.fill(0.0);
+      unsigned i = 0;
+      for (double a : v)
+        if (i < (unsigned)dim) x[i++] = a;
+    }
+    double operator[](unsigned i) const { return x[i]; }
+    double &operator[](unsigned i) { return x[i]; }
+    const double *data() const { return x.data(); }
+
+  private:
+    std::array<double, dim> x;
+  };
+
+  // Vector<double>(solid.get_current_solution()) in the FSI drivers
+  template <typename T>
+  using Vector = std::vector<T>;
+
   template <int dim>
   class Triangulation
   {
@@ -98,6 +125,15 @@ namespace dealii
     }
   } // namespace GridGenerator
 
+  namespace GridTools
+  {
+    template <int dim>
+    void shift(const Tensor<1, dim> &offset, Triangulation<dim> &tria)
+    {
+      openifem_detail::check(ifem_tria_shift(tria.handle(), offset.data()));
+    }
+  } // namespace GridTools
+
   namespace Utilities
   {
     namespace MPI
@@ -112,6 +148,12 @@ namespace dealii
 } // namespace dealii
 
 namespace parallel = dealii::parallel;
+using dealii::Point;
+using dealii::Tensor;
+using dealii::Triangulation;
+using dealii::Vector;
+namespace GridGenerator = dealii::GridGenerator;
+namespace GridTools = dealii::GridTools;
 
 namespace Parameters
 {
@@ -244,17 +286,13 @@ namespace Solid
 {
   namespace MPI
   {
-    // include/mpi_hyper_elasticity.h:96-98, include/mpi_solid_solver.h:75-79
+    // include/mpi_solid_solver.h:75-79, include/mpi_shared_solid_solver.h:91-101: run(), get_current_solution()
     template <int dim>
-    class HyperElasticity
+    class SolidSolver
     {
     public:
-      HyperElasticity(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
-      {
-        openifem_detail::check(ifem_hyper_create(tria.handle(), params.handle(), &h));
-      }
-      ~HyperElasticity() { ifem_hyper_destroy(h); }
-      HyperElasticity(const HyperElasticity &) = delete;
+      ~SolidSolver() { ifem_hyper_destroy(h); }
+      SolidSolver(const SolidSolver &) = delete;
       void run() { openifem_detail::check(ifem_hyper_run(h)); }
       void run_one_step(bool first_step) { openifem_detail::check(ifem_hyper_run_one_step(h, first_step)); }
       std::vector<double> get_current_solution() const
@@ -267,30 +305,105 @@ namespace Solid
       }
       ifem_hyper *handle() const { return h; }
 
-    private:
+    protected:
+      SolidSolver() = default;
       ifem_hyper *h = nullptr;
+    };
+    template <int dim>
+    using SharedSolidSolver = SolidSolver<dim>;
+
+    // include/mpi_hyper_elasticity.h:96-98 (and the replicated twin include/mpi_shared_hyper_elasticity.h)
+    template <int dim>
+    class HyperElasticity : public SolidSolver<dim>
+    {
+    public:
+      HyperElasticity(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_hyper_create(tria.handle(), params.handle(), &this->h));
+      }
+    };
+    template <int dim>
+    using SharedHyperElasticity = HyperElasticity<dim>;
+
+    // include/mpi_linear_elasticity.h
+    template <int dim>
+    class LinearElasticity : public SolidSolver<dim>
+    {
+    public:
+      LinearElasticity(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_linear_elasticity_create(tria.handle(), params.handle(), 0, &this->h));
+      }
+    };
+
+    // include/mpi_shared_linear_elasticity.h
+    template <int dim>
+    class SharedLinearElasticity : public SolidSolver<dim>
+    {
+    public:
+      SharedLinearElasticity(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_linear_elasticity_create(tria.handle(), params.handle(), 1, &this->h));
+      }
     };
   } // namespace MPI
 } // namespace Solid
 
 namespace MPI
 {
-  // include/mpi_fsi.h:39-47 - the coupling kernels of the hot path (the full run() loop is not built yet)
+  // include/mpi_fsi.h:39-47: FSI(fluid, solid, parameters, use_dirichlet_bc), run(), set_penetration_criterion()
   template <int dim>
   class FSI
   {
   public:
-    FSI(Fluid::MPI::FluidSolver<dim> &f, Solid::MPI::HyperElasticity<dim> &s, const Parameters::AllParameters &p, bool use_dirichlet_bc = false)
+    FSI(Fluid::MPI::FluidSolver<dim> &f, Solid::MPI::SolidSolver<dim> &s, const Parameters::AllParameters &p, bool use_dirichlet_bc = false)
+      : fluid(f), solid(s), params(p), dirichlet(use_dirichlet_bc)
     {
-      openifem_detail::check(ifem_fsi_create(f.handle(), s.handle(), p.handle(), use_dirichlet_bc, &h));
     }
-    ~FSI() { ifem_fsi_destroy(h); }
+    ~FSI()
+    {
+      if (h) ifem_fsi_destroy(h);
+    }
     FSI(const FSI &) = delete;
-    void update_solid_box() { openifem_detail::check(ifem_fsi_update_solid_box(h, nullptr)); }
-    void update_indicator() { openifem_detail::check(ifem_fsi_update_indicator(h)); }
-    void find_fluid_bc() { openifem_detail::check(ifem_fsi_find_fluid_bc(h)); }
+    // source/mpi_fsi.cpp:1120-1227: refine both meshes, set up both solvers, then the coupled time loop
+    void run()
+    {
+      ensure();
+      openifem_detail::check(ifem_fsi_run(h));
+    }
+    void set_penetration_criterion(const std::function<double(const dealii::Point<dim> &)> &c, dealii::Tensor<1, dim> direction)
+    {
+      criterion = c;
+      dir = direction;
+      has_criterion = true;
+    }
+    void update_solid_box() { ensure(); openifem_detail::check(ifem_fsi_update_solid_box(h, nullptr)); }
+    void update_indicator() { ensure(); openifem_detail::check(ifem_fsi_update_indicator(h)); }
+    void find_fluid_bc() { ensure(); openifem_detail::check(ifem_fsi_find_fluid_bc(h)); }
 
   private:
+    // the reference's FSI::run sets the solvers up itself (:1127-1143); the coupling object needs them set up, so it is
+    // created on first use
+    void ensure()
+    {
+      if (h) return;
+      openifem_detail::check(ifem_hyper_setup_with_refinement(solid.handle()));
+      openifem_detail::check(ifem_insim_setup_with_refinement(fluid.handle()));
+      openifem_detail::check(ifem_fsi_create(fluid.handle(), solid.handle(), params.handle(), dirichlet, &h));
+      if (has_criterion) openifem_detail::check(ifem_fsi_set_penetration_criterion(h, &thunk, this, dir.data()));
+    }
+    static double thunk(const double *p, void *user)
+    {
+      dealii::Point<dim> x;
+      for (int d = 0; d < dim; ++d) x[d] = p[d];
+      return static_cast<FSI *>(user)->criterion(x);
+    }
+    Fluid::MPI::FluidSolver<dim> &fluid;
+    Solid::MPI::SolidSolver<dim> &solid;
+    const Parameters::AllParameters &params;
+    bool dirichlet, has_criterion = false;
+    std::function<double(const dealii::Point<dim> &)> criterion;
+    dealii::Tensor<1, dim> dir;
     ifem_fsi *h = nullptr;
   };
 } // namespace MPI

@@ -64,6 +64,8 @@ int ifem_tria_subdivided_hyper_rectangle(ifem_tria *t, const unsigned int *repet
                                          int colorize);
 int ifem_tria_hyper_cube(ifem_tria *t, double left, double right, int colorize);
 int ifem_tria_refine_global(ifem_tria *t, int times);
+/* GridTools::shift(offset, tria): offset [dim] added to every vertex */
+int ifem_tria_shift(ifem_tria *t, const double *offset);
 int ifem_tria_counts(const ifem_tria *t, int64_t *n_vertices, int64_t *n_cells, int64_t *n_boundary_faces);
 /* Utils::GridCreator<dim>::flow_around_cylinder(tria) (source/utilities.cpp:343-574; dim of the handle): the mesh of
  * tests/fluid_cylinder_mpi*. In 2-D the cells around the hole carry their polar / transfinite charts, which
@@ -116,6 +118,9 @@ int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c);
 int ifem_insim_set_verbose(ifem_insim *s, int verbose);
 /* setup_dofs(); make_constraints(); initialize_system();  (mpi_insim.cpp:504-506) - no refinement */
 int ifem_insim_setup(ifem_insim *s);
+/* what FSI::run does to the fluid before its loop (source/mpi_fsi.cpp:1136-1142): refine_global(Global refinements[0]),
+ * setup_dofs(), make_constraints(), initialize_system(); a no-op when the solver is already set up */
+int ifem_insim_setup_with_refinement(ifem_insim *s);
 /* run(): refine_global(Global refinements[0]) + setup + time loop (mpi_insim.cpp:492-519) */
 int ifem_insim_run(ifem_insim *s);
 /* run_one_step(apply_nonzero_constraints) (mpi_insim.cpp:397-490) */
@@ -172,10 +177,18 @@ typedef struct
   int cg_its;
 } ifem_solid_record;
 int ifem_hyper_create(ifem_tria *tria, const ifem_params *params, ifem_hyper **out);
+/* Solid::MPI::LinearElasticity<dim>(tria, params) (shared = 0; include/mpi_linear_elasticity.h, source/mpi_linear_elasticity.cpp)
+ * or Solid::MPI::SharedLinearElasticity<dim>(tria, params) (shared = 1, the replicated twin MPI::FSI takes;
+ * source/mpi_shared_linear_elasticity.cpp). The handle is the common solid-solver handle: every ifem_hyper_* entry point
+ * applies except update_qph / get_qph (hyperelastic only). */
+int ifem_linear_elasticity_create(ifem_tria *tria, const ifem_params *params, int shared, ifem_hyper **out);
 int ifem_hyper_destroy(ifem_hyper *s);
 int ifem_hyper_set_verbose(ifem_hyper *s, int verbose);
 /* setup_dofs(); initialize_system() (incl. setup_qph) - no refinement */
 int ifem_hyper_setup(ifem_hyper *s);
+/* what FSI::run does to the solid before its loop (source/mpi_fsi.cpp:1127, 1134-1135): refine_global(Global
+ * refinements[1]), setup_dofs(), initialize_system(); a no-op when the solver is already set up */
+int ifem_hyper_setup_with_refinement(ifem_hyper *s);
 /* run(): refine_global(Global refinements[1]) + setup + time loop (mpi_solid_solver.cpp:316-328) */
 int ifem_hyper_run(ifem_hyper *s);
 /* run_one_step(first_step) (mpi_hyper_elasticity.cpp:83-207) */
@@ -191,7 +204,7 @@ int ifem_hyper_get_current_solution(ifem_hyper *s, double *host);
  *        4 previous_velocity 5 previous_acceleration 6 system_rhs */
 int ifem_hyper_set_vector(ifem_hyper *s, int which, const double *host);
 int ifem_hyper_get_vector(ifem_hyper *s, int which, double *host);
-/* which: 0 system_matrix, 1 mass_matrix; scalar CSR on the host */
+/* which: 0 system_matrix, 1 mass_matrix, 2 stiffness_matrix, 3 damping_matrix (2, 3: linear elasticity only); scalar CSR on the host */
 int ifem_hyper_get_matrix(ifem_hyper *s, int which, int64_t *rowptr, int *col, double *val);
 /* PointHistory arrays [cell][q]: F_inv [dim*dim], tau [dim*dim], Jc [nsym*nsym] (Voigt pairs (0,0),(1,1)[,(2,2)],(0,1)[,(0,2),(1,2)]), det F */
 int ifem_hyper_get_qph(ifem_hyper *s, double *F_inv, double *tau, double *Jc, double *det_F);
@@ -229,6 +242,12 @@ int ifem_fsi_interpolate(ifem_fsi *f, int which, int n, const double *points, do
 /* find_solid_bc() (source/mpi_fsi.cpp:666-867): fills the solid's fsi_stress_rows / fluid_velocity / fluid_pressure */
 int ifem_fsi_find_solid_bc(ifem_fsi *f);
 /* one pass of the time loop of FSI::run (source/mpi_fsi.cpp:1172-1214) / the whole loop (no refinement, no checkpoints) */
+/* FSI::set_penetration_criterion(criterion, direction) (include/mpi_fsi.h:44-47, source/mpi_fsi.cpp:1229-1237): with a
+ * criterion set, the solid step of the time loop goes through apply_contact_model (:869-970); direction [dim] */
+typedef double (*ifem_point_fn)(const double *point, void *user);
+int ifem_fsi_set_penetration_criterion(ifem_fsi *f, ifem_point_fn criterion, void *user, const double *direction);
+/* solid steps taken inside apply_contact_model so far */
+int ifem_fsi_contact_iterations(const ifem_fsi *f, int *n);
 int ifem_fsi_run_one_step(ifem_fsi *f, int first_step);
 int ifem_fsi_run(ifem_fsi *f);
 int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms);

@@ -535,6 +535,28 @@ class _HyperElasticity:
         return [{f: getattr(buf[i], f) for f, _ in SolidRecord._fields_} for i in range(min(n.value, max_records))]
 
 
+class _LinearElasticity(_HyperElasticity):
+    """Solid::MPI::LinearElasticity<dim>(triangulation, parameters): small-strain elasticity, Newmark-beta in
+    acceleration form. Same handle type as the other solid solvers (update_qph / get_qph do not apply)."""
+
+    SHARED = False
+    SYSTEM, MASS, STIFFNESS, DAMPING = range(4)
+
+    def __init__(self, tria: Triangulation, params: "Parameters.AllParameters"):
+        self.tria, self.params = tria, params
+        self._h = C.c_void_p()
+        check(lib().ifem_linear_elasticity_create(tria._h, params._h, C.c_int(1 if self.SHARED else 0), C.byref(self._h)))
+
+
+class _SharedLinearElasticity(_LinearElasticity):
+    """Solid::MPI::SharedLinearElasticity<dim>(triangulation, parameters): the replicated twin MPI::FSI drives."""
+
+    SHARED = True
+
+
+POINT_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)
+
+
 class _FSI:
     """MPI::FSI<dim>(fluid_solver, solid_solver, parameters, use_dirichlet_bc) - coupling kernels."""
 
@@ -571,6 +593,19 @@ class _FSI:
 
     def run(self):
         check(lib().ifem_fsi_run(self._h))
+
+    def set_penetration_criterion(self, criterion, direction):
+        """FSI::set_penetration_criterion(criterion(point) -> double, direction): enables apply_contact_model"""
+        dim = self.fluid.tria.dim
+        cb = POINT_FN(lambda p, _u: float(criterion([p[i] for i in range(dim)])))
+        self._keep_criterion = cb  # the library calls it during run(): keep the trampoline alive
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        check(lib().ifem_fsi_set_penetration_criterion(self._h, cb, None, dptr(d)))
+
+    def contact_iterations(self):
+        n = C.c_int()
+        check(lib().ifem_fsi_contact_iterations(self._h, C.byref(n)))
+        return n.value
 
     def find_fluid_bc(self):
         check(lib().ifem_fsi_find_fluid_bc(self._h))
@@ -614,3 +649,5 @@ class Fluid:
 class Solid:
     class MPI:
         HyperElasticity = _HyperElasticity
+        LinearElasticity = _LinearElasticity
+        SharedLinearElasticity = _SharedLinearElasticity

@@ -30,7 +30,7 @@ struct ifem_insim
 };
 struct ifem_hyper
 {
-  std::unique_ptr<HyperElasticity> s;
+  std::unique_ptr<SolidSolver> s; // HyperElasticity or LinearElasticity
 };
 struct ifem_fsi
 {
@@ -115,7 +115,7 @@ static DevBuf<double> *pick_vector(InsIM &m, int which, int64_t &n)
     default: throw std::runtime_error("unknown vector id");
     }
 }
-static DevBuf<double> *pick_solid_vector(HyperElasticity &m, int which)
+static DevBuf<double> *pick_solid_vector(SolidSolver &m, int which)
 {
   switch (which)
     {
@@ -128,6 +128,13 @@ static DevBuf<double> *pick_solid_vector(HyperElasticity &m, int which)
     case 6: return &m.ss.rhs;
     default: throw std::runtime_error("unknown vector id");
     }
+}
+
+static HyperElasticity &as_hyper(ifem_hyper *s)
+{
+  auto *p = dynamic_cast<HyperElasticity *>(s->s.get());
+  if (!p) throw std::runtime_error("this solid solver is not a HyperElasticity");
+  return *p;
 }
 
 static SCnsIM &as_scns(ifem_insim *s)
@@ -272,6 +279,13 @@ int ifem_tria_refine_global(ifem_tria *t, int times)
 {
   return guard([&] { t->t.refine_global(times); });
 }
+int ifem_tria_shift(ifem_tria *t, const double *offset)
+{
+  return guard([&] {
+    const int dim = t->t.dim;
+    for (size_t i = 0; i < t->t.vertices.size(); ++i) t->t.vertices[i] += offset[i % dim];
+  });
+}
 int ifem_tria_flow_around_cylinder(ifem_tria *t)
 {
   return guard([&] { GridCreator::flow_around_cylinder(t->t, t->t.dim); });
@@ -378,6 +392,17 @@ int ifem_insim_setup(ifem_insim *s)
     s->s->setup_dofs();
     s->s->make_constraints();
     s->s->initialize_system();
+  });
+}
+int ifem_insim_setup_with_refinement(ifem_insim *s)
+{
+  return guard([&] {
+    InsIM &m = *s->s;
+    if (m.dofs_ready) return;
+    m.triangulation.refine_global(m.parameters.global_refinements.empty() ? 0 : m.parameters.global_refinements[0]);
+    m.setup_dofs();
+    m.make_constraints();
+    m.initialize_system();
   });
 }
 int ifem_insim_run(ifem_insim *s)
@@ -671,6 +696,15 @@ int ifem_hyper_create(ifem_tria *tria, const ifem_params *params, ifem_hyper **o
     *out = h;
   });
 }
+int ifem_linear_elasticity_create(ifem_tria *tria, const ifem_params *params, int shared, ifem_hyper **out)
+{
+  return guard([&] {
+    require_device();
+    auto *h = new ifem_hyper;
+    h->s.reset(new LinearElasticity(default_context(), tria->t, *params->p, shared != 0));
+    *out = h;
+  });
+}
 int ifem_hyper_destroy(ifem_hyper *s)
 {
   delete s;
@@ -688,6 +722,16 @@ int ifem_hyper_setup(ifem_hyper *s)
     s->s->initialize_system();
   });
 }
+int ifem_hyper_setup_with_refinement(ifem_hyper *s)
+{
+  return guard([&] {
+    SolidSolver &m = *s->s;
+    if (m.dofs_ready) return;
+    m.triangulation.refine_global(m.parameters.global_refinements.size() > 1 ? m.parameters.global_refinements[1] : 0);
+    m.setup_dofs();
+    m.initialize_system();
+  });
+}
 int ifem_hyper_run(ifem_hyper *s)
 {
   return guard([&] { s->s->run(); });
@@ -699,7 +743,7 @@ int ifem_hyper_run_one_step(ifem_hyper *s, int first)
 int ifem_hyper_update_qph(ifem_hyper *s)
 {
   return guard([&] {
-    s->s->update_qph(s->s->current_displacement.p);
+    as_hyper(s).update_qph(s->s->current_displacement.p);
     IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
   });
 }
@@ -741,7 +785,16 @@ int ifem_hyper_get_matrix(ifem_hyper *s, int which, int64_t *rowptr, int *col, d
     std::vector<int64_t> rp;
     std::vector<int> ci;
     std::vector<double> v;
-    (which == 0 ? s->s->ss.K : s->s->ss.M).to_host_csr(s->s->ctx.stream, rp, ci, v);
+    Bcsr *A = which == 0 ? &s->s->ss.K : which == 1 ? &s->s->ss.M : nullptr;
+    if (which == 2 || which == 3)
+      {
+        auto *lin = dynamic_cast<LinearElasticity *>(s->s.get());
+        if (!lin) throw std::runtime_error("stiffness / damping matrices exist for LinearElasticity only");
+        A = which == 2 ? &lin->stiffness_matrix : &lin->damping_matrix;
+        if (which == 3 && !lin->shared) throw std::runtime_error("the damping matrix exists for SharedLinearElasticity only");
+      }
+    if (!A) throw std::runtime_error("unknown matrix id");
+    A->to_host_csr(s->s->ctx.stream, rp, ci, v);
     std::copy(rp.begin(), rp.end(), rowptr);
     std::copy(ci.begin(), ci.end(), col);
     std::copy(v.begin(), v.end(), val);
@@ -783,7 +836,7 @@ int ifem_hyper_set_nodal_tensor(ifem_hyper *s, int which, const double *host)
 int ifem_hyper_get_fsi_inputs(ifem_hyper *s, double *rows, double *vel, double *pres)
 {
   return guard([&] {
-    HyperElasticity &m = *s->s;
+    SolidSolver &m = *s->s;
     if (rows) m.fsi_stress_rows.download(rows, m.fsi_stress_rows.n, m.ctx.stream);
     if (vel) m.fluid_velocity.download(vel, m.fluid_velocity.n, m.ctx.stream);
     if (pres) m.fluid_pressure.download(pres, m.fluid_pressure.n, m.ctx.stream);
@@ -863,6 +916,14 @@ int ifem_fsi_find_solid_bc(ifem_fsi *f)
     f->f->find_solid_bc();
     IFEM_CUDA(cudaStreamSynchronize(f->f->ctx.stream));
   });
+}
+int ifem_fsi_set_penetration_criterion(ifem_fsi *f, ifem_point_fn criterion, void *user, const double *direction)
+{
+  return guard([&] { f->f->set_penetration_criterion([criterion, user](const double *p) { return criterion(p, user); }, direction); });
+}
+int ifem_fsi_contact_iterations(const ifem_fsi *f, int *n)
+{
+  return guard([&] { *n = f->f->contact_iterations; });
 }
 int ifem_fsi_run_one_step(ifem_fsi *f, int first_step)
 {

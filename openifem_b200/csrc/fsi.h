@@ -10,6 +10,8 @@
 // of the Q1 map -> unit-cell test. The 2-D crossing-number test is kept statement for statement (its
 // on-edge / on-vertex rules are exact floating-point comparisons).
 #pragma once
+#include <functional>
+
 #include "insim.h"
 #include "solid.h"
 
@@ -18,7 +20,7 @@ namespace ifem
   class FsiCoupling
   {
   public:
-    FsiCoupling(Context &ctx, InsIM &fluid, HyperElasticity &solid, const Parameters::AllParameters &params, bool use_dirichlet_bc);
+    FsiCoupling(Context &ctx, InsIM &fluid, SolidSolver &solid, const Parameters::AllParameters &params, bool use_dirichlet_bc);
 
     // bounding box of the deformed solid, [min0, max0, min1, max1, ...] (host copy returned)
     std::vector<double> update_solid_box();
@@ -34,6 +36,12 @@ namespace ifem
     void run_one_step(bool first_step);
     void run();
     Time time;
+    // FSI::set_penetration_criterion (source/mpi_fsi.cpp:1229-1237) / apply_contact_model (:869-970): while a boundary
+    // vertex of the moved solid penetrates (criterion > 1e-5), the solid step is redone with an extra stress
+    // Contact force multiplier * penetration along `direction` added to fsi_stress_rows at that vertex
+    void set_penetration_criterion(std::function<double(const double *)> criterion, const double *direction);
+    void apply_contact_model(bool first_step);
+    int contact_iterations = 0; // solid steps taken inside apply_contact_model so far
 
     // batch queries on the current deformed solid (tests / diagnostics)
     void point_in_solid(int n, const double *pts_host, int *inside_host);
@@ -42,7 +50,7 @@ namespace ifem
 
     Context &ctx;
     InsIM &fluid;
-    HyperElasticity &solid;
+    SolidSolver &solid;
     Parameters::AllParameters parameters;
     bool use_dirichlet_bc;
     std::vector<double> solid_box; // host mirror
@@ -52,6 +60,8 @@ namespace ifem
     std::map<std::string, double> timer_ms;
 
   private:
+    std::function<double(const double *)> penetration_criterion;
+    double penetration_direction[3] = {0, 0, 0};
     void refresh_deformed();
     void build_bins();
     int dim;

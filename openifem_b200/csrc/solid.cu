@@ -418,6 +418,157 @@ namespace ifem
           }
     }
 
+    // ---- LinearElasticity / SharedLinearElasticity ---------------------------------------------------------------
+    struct LinearArgs
+    {
+      int n_list;
+      const int *cell_list, *cell_nodes;
+      const unsigned char *slots, *con;
+      const double *N, *G, *JxW;
+      int nq;
+      double rho, lambda, mu, eta, grav[3];
+      // system = c_mass * M + c_damp * C + c_stiff * K; any of sys / mass / stiff / damp may be null (not assembled)
+      double c_mass, c_damp, c_stiff;
+      const int64_t *rowptr;
+      double *sys, *mass, *stiff, *damp, *rhs;
+    };
+
+    // cell loop of [Shared]LinearElasticity::assemble_system (mpi_linear_elasticity.cpp:73-130,
+    // mpi_shared_linear_elasticity.cpp:94-152): one thread per (cell, row node a, column node b), cells of one colour per
+    // launch. With sym grad phi_(a,c) = sym(e_c x g_a) and C = mu (ik jl + il jk) + lambda ij kl:
+    //   sym_(a,c) : C : sym_(b,d) = mu (delta_cd g_a.g_b + g_a[d] g_b[c]) + lambda g_a[c] g_b[d]
+    // and with the viscosity tensor eta/2 (ik jl + il jk):  eta/2 (delta_cd g_a.g_b + g_a[d] g_b[c]).
+    template <int DIM, int NPC>
+    __global__ void __launch_bounds__(64) linear_assemble_kernel(const LinearArgs A)
+    {
+      constexpr int PAIRS = NPC * NPC, CPB = 64 / PAIRS;
+      const int li = blockIdx.x * CPB + threadIdx.x / PAIRS;
+      if (li >= A.n_list) return;
+      const int cell = A.cell_list[li];
+      const int pr = threadIdx.x % PAIRS, a = pr / NPC, b = pr % NPC;
+      double m = 0.0, gg = 0.0, outer[DIM * DIM], r[DIM];
+#pragma unroll
+      for (int i = 0; i < DIM * DIM; ++i) outer[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) r[i] = 0.0;
+      for (int q = 0; q < A.nq; ++q)
+        {
+          const int64_t cq = (int64_t)cell * A.nq + q;
+          const double w = A.JxW[cq];
+          const double *g0 = A.G + cq * NPC * DIM;
+          const double Na = A.N[q * NPC + a], Nb = A.N[q * NPC + b];
+          m = fma(A.rho * Na * Nb, w, m);
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < DIM; ++k) s = fma(g0[a * DIM + k], g0[b * DIM + k], s);
+          gg = fma(s, w, gg);
+#pragma unroll
+          for (int c = 0; c < DIM; ++c)
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) outer[c * DIM + d] = fma(g0[a * DIM + c] * g0[b * DIM + d], w, outer[c * DIM + d]);
+          if (b == 0)
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) r[c] = fma(w, A.rho * A.grav[c] * Na, r[c]);
+        }
+      const int nA = A.cell_nodes[(int64_t)cell * NPC + a], nB = A.cell_nodes[(int64_t)cell * NPC + b];
+      const int64_t rp = A.rowptr[nA];
+      const int nb = (int)(A.rowptr[nA + 1] - rp);
+      const int slot = A.slots[(int64_t)cell * PAIRS + pr];
+      const int64_t base = rp * DIM * DIM + slot;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c)
+        {
+          const int rc = A.con[(int64_t)DIM * nA + c];
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+            {
+              const int cc = A.con[(int64_t)DIM * nB + d];
+              const double sym = (c == d ? gg : 0.0) + outer[d * DIM + c];
+              const double ke = A.mu * sym + A.lambda * outer[c * DIM + d];
+              const double ce = 0.5 * A.eta * sym;
+              const double me = c == d ? m : 0.0;
+              const double se = A.c_mass * me + A.c_damp * ce + A.c_stiff * ke;
+              const int64_t at = base + (int64_t)(c * DIM + d) * nb;
+              if (rc)
+                {
+                  // constrained row: distribute_local_to_global keeps |local diagonal| on the diagonal
+                  if (a == b && c == d)
+                    {
+                      if (A.sys) A.sys[at] += fabs(se);
+                      if (A.mass) A.mass[at] += fabs(me);
+                      if (A.stiff) A.stiff[at] += fabs(ke);
+                      if (A.damp) A.damp[at] += fabs(ce);
+                    }
+                }
+              else if (!cc)
+                {
+                  if (A.sys) A.sys[at] += se;
+                  if (A.mass) A.mass[at] += me;
+                  if (A.stiff) A.stiff[at] += ke;
+                  if (A.damp) A.damp[at] += ce;
+                }
+            }
+          if (b == 0 && !rc && A.rhs) A.rhs[(int64_t)DIM * nA + c] += r[c];
+        }
+    }
+
+    // SharedLinearElasticity::update_strain_and_stress (mpi_shared_linear_elasticity.cpp:401-531): one thread per cell
+    // (cells of one colour per launch): strain = sym grad u, stress = C : strain at the quadrature points -> qpt_to_dof ->
+    // nodal scatter-add; the average over the surrounding cells is taken by solid_average_kernel
+    template <int DIM, int NPC>
+    __global__ void linear_stress_kernel(int n_list, const int *__restrict__ cell_list, int nq, const int *__restrict__ cell_nodes,
+                                         const double *__restrict__ qpt_to_dof, const double *__restrict__ G,
+                                         const double *__restrict__ u, double lambda, double mu, int n_nodes,
+                                         double *__restrict__ stress, double *__restrict__ strain, double *__restrict__ count)
+    {
+      const int li = blockIdx.x * blockDim.x + threadIdx.x;
+      if (li >= n_list) return;
+      const int cell = cell_list[li];
+      double ue[NPC * DIM];
+      for (int b = 0; b < NPC; ++b)
+        for (int c = 0; c < DIM; ++c) ue[b * DIM + c] = u[(int64_t)DIM * cell_nodes[(int64_t)cell * NPC + b] + c];
+      for (int a = 0; a < NPC; ++a)
+        {
+          double st[DIM * DIM], sn[DIM * DIM];
+#pragma unroll
+          for (int i = 0; i < DIM * DIM; ++i) st[i] = sn[i] = 0.0;
+          for (int q = 0; q < nq; ++q)
+            {
+              const int64_t cq = (int64_t)cell * nq + q;
+              const double *g = G + cq * NPC * DIM;
+              double gu[DIM * DIM];
+#pragma unroll
+              for (int i = 0; i < DIM * DIM; ++i) gu[i] = 0.0;
+              for (int b = 0; b < NPC; ++b)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c)
+#pragma unroll
+                  for (int k = 0; k < DIM; ++k) gu[c * DIM + k] = fma(ue[b * DIM + c], g[b * DIM + k], gu[c * DIM + k]);
+              double tr = 0.0;
+#pragma unroll
+              for (int i = 0; i < DIM; ++i) tr += gu[i * DIM + i];
+              const double w = qpt_to_dof[a * nq + q];
+#pragma unroll
+              for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j)
+                  {
+                    const double e = 0.5 * (gu[i * DIM + j] + gu[j * DIM + i]);
+                    sn[i * DIM + j] = fma(w, e, sn[i * DIM + j]);
+                    st[i * DIM + j] = fma(w, 2.0 * mu * e + (i == j ? lambda * tr : 0.0), st[i * DIM + j]);
+                  }
+            }
+          const int node = cell_nodes[(int64_t)cell * NPC + a];
+#pragma unroll
+          for (int i = 0; i < DIM * DIM; ++i)
+            {
+              stress[(int64_t)i * n_nodes + node] += st[i];
+              strain[(int64_t)i * n_nodes + node] += sn[i];
+            }
+          count[node] += 1.0;
+        }
+    }
+
     struct ScopedTimer
     {
       Context &ctx;
@@ -524,7 +675,7 @@ namespace ifem
       for (int f = 0; f < tria.n_boundary_faces(); ++f)
         {
           const unsigned id = (unsigned)tria.boundary_faces[3 * f + 2];
-          if (prm.solid_dirichlet_bcs.count(id)) continue;
+          if (neumann_skips_dirichlet_faces && prm.solid_dirichlet_bcs.count(id)) continue;
           auto it = prm.solid_neumann_bcs.find(id);
           if (it == prm.solid_neumann_bcs.end()) continue;
           nf.push_back(tria.boundary_faces[3 * f]);
@@ -584,21 +735,19 @@ namespace ifem
   }
 
   // ===========================================================================
-  HyperElasticity::HyperElasticity(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params)
+  SolidSolver::SolidSolver(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params)
     : ctx(ctx_), triangulation(tria), parameters(params),
       time(params.end_time, params.time_step, params.output_interval, params.refinement_interval, params.save_interval)
   {
-    if (parameters.solid_type != "NeoHookean") throw std::runtime_error("HyperElasticity: only the NeoHookean material is implemented on the device");
-    if (parameters.C.empty() || parameters.C[0].size() < 2) throw std::runtime_error("HyperElasticity: NeoHookean requires C1, kappa");
   }
 
-  void HyperElasticity::setup_dofs()
+  void SolidSolver::setup_dofs()
   {
     ss.setup(ctx, triangulation, parameters);
     dofs_ready = true;
   }
 
-  void HyperElasticity::initialize_system()
+  void SolidSolver::initialize_system()
   {
     for (DevBuf<double> *v : {&current_displacement, &current_velocity, &current_acceleration, &previous_displacement,
                               &previous_velocity, &previous_acceleration, &d_tmp, &d_pred, &d_update})
@@ -655,6 +804,88 @@ namespace ifem
         }
       d_qpt_to_dof.upload(R, ctx.stream);
     }
+    // initial velocity (mpi_solid_solver.cpp:116-137, mpi_shared_solid_solver.cpp:152-196), constraints distributed
+    bool any = false;
+    for (int c = 0; c < ss.dim && c < (int)parameters.initial_velocity.size(); ++c) any = any || parameters.initial_velocity[c] != 0.0;
+    if (any)
+      {
+        std::vector<double> v(ss.n_dofs, 0.0);
+        for (int64_t g = 0; g < ss.n_dofs; ++g)
+          if (!ss.con[g] && (int)(g % ss.dim) < (int)parameters.initial_velocity.size()) v[g] = parameters.initial_velocity[g % ss.dim];
+        previous_velocity.upload(v, ctx.stream);
+        current_velocity.upload(v, ctx.stream);
+      }
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void SolidSolver::neumann_rhs()
+  {
+    cudaStream_t s = ctx.stream;
+    if (ss.n_nfaces)
+      {
+        const bool fsi = parameters.simulation_type == "FSI";
+        const double *rows = fsi ? fsi_stress_rows.p : nullptr, *disp = fsi ? current_displacement.p : nullptr;
+        if (ss.dim == 2)
+          solid_neumann_kernel<2, 4><<<ss.n_nfaces, 32, 0, s>>>(ss.n_nfaces, ss.nqf, ss.d_nface.p, ss.d_nface_val.p, ss.neumann_is_pressure,
+                                                                ss.d_face_tables.p, ss.d_cell_nodes.p, ss.d_node_x.p, ss.d_con.p, ss.rhs.p,
+                                                                rows, disp, ss.n_dofs);
+        else
+          solid_neumann_kernel<3, 8><<<ss.n_nfaces, 32, 0, s>>>(ss.n_nfaces, ss.nqf, ss.d_nface.p, ss.d_nface_val.p, ss.neumann_is_pressure,
+                                                                ss.d_face_tables.p, ss.d_cell_nodes.p, ss.d_node_x.p, ss.d_con.p, ss.rhs.p,
+                                                                rows, disp, ss.n_dofs);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+  }
+
+  // SolidSolver::solve (mpi_solid_solver.cpp:143-161): CG to 1e-8 |b|; the reference's per-rank ILU(0) block
+  // Jacobi is replaced by the node-block Jacobi preconditioner (rank-count independent).
+  std::pair<unsigned int, double> SolidSolver::solve(Bcsr &A, double *x, const double *b)
+  {
+    ScopedTimer t(ctx, timer_ms["Solve linear system"]);
+    const VecSpace n(ss.n_dofs);
+    block_diag_inverse(ctx, A, d_binv.p);
+    LinOp op = [&](const double *v, double *y) { spmv(ctx, A, v, y); };
+    LinOp pc = [&](const double *v, double *y) { block_diag_apply(ctx, ss.nt.n_nodes, ss.dim, d_binv.p, v, y); };
+    const double tol = 1e-8 * nrm2(ctx, n, b);
+    const SolveResult r = pcg(ctx, n, op, pc, b, x, tol, (int)ss.n_dofs, pool);
+    if (ss.n_con) set_indexed(ctx, ss.n_con, ss.d_con_idx.p, nullptr, x); // constraints.distribute (homogeneous)
+    return {(unsigned)r.iterations, r.residual};
+  }
+
+  double SolidSolver::get_error(const double *v)
+  {
+    const VecSpace n(ss.n_dofs);
+    copy(ctx, n, v, d_tmp.p);
+    if (ss.n_con) set_indexed(ctx, ss.n_con, ss.d_con_idx.p, nullptr, d_tmp.p);
+    return nrm2(ctx, n, d_tmp.p);
+  }
+
+  void SolidSolver::run()
+  {
+    if (!dofs_ready)
+      {
+        triangulation.refine_global(parameters.global_refinements.size() > 1 ? parameters.global_refinements[1] : 0);
+        setup_dofs();
+        initialize_system();
+      }
+    run_one_step(true);
+    while (time.end() - time.current() > 1e-12) run_one_step(false);
+  }
+
+  std::vector<double> SolidSolver::get_current_solution() { return current_displacement.to_host(ctx.stream); }
+
+  // ===========================================================================
+  HyperElasticity::HyperElasticity(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params)
+    : SolidSolver(ctx_, tria, params)
+  {
+    if (parameters.solid_type != "NeoHookean") throw std::runtime_error("HyperElasticity: only the NeoHookean material is implemented on the device");
+    if (parameters.C.empty() || parameters.C[0].size() < 2) throw std::runtime_error("HyperElasticity: NeoHookean requires C1, kappa");
+  }
+
+  void HyperElasticity::initialize_system()
+  {
+    SolidSolver::initialize_system();
     // setup_qph (:217-239): PointHistory::setup calls update with a zero displacement gradient
     update_qph(current_displacement.p);
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -740,44 +971,7 @@ namespace ifem
         IFEM_KERNEL_CHECK();
         ctx.kernel_launches++;
       }
-    if (ss.n_nfaces)
-      {
-        const bool fsi = parameters.simulation_type == "FSI";
-        const double *rows = fsi ? fsi_stress_rows.p : nullptr, *disp = fsi ? current_displacement.p : nullptr;
-        if (ss.dim == 2)
-          solid_neumann_kernel<2, 4><<<ss.n_nfaces, 32, 0, s>>>(ss.n_nfaces, ss.nqf, ss.d_nface.p, ss.d_nface_val.p, ss.neumann_is_pressure,
-                                                                ss.d_face_tables.p, ss.d_cell_nodes.p, ss.d_node_x.p, ss.d_con.p, ss.rhs.p,
-                                                                rows, disp, ss.n_dofs);
-        else
-          solid_neumann_kernel<3, 8><<<ss.n_nfaces, 32, 0, s>>>(ss.n_nfaces, ss.nqf, ss.d_nface.p, ss.d_nface_val.p, ss.neumann_is_pressure,
-                                                                ss.d_face_tables.p, ss.d_cell_nodes.p, ss.d_node_x.p, ss.d_con.p, ss.rhs.p,
-                                                                rows, disp, ss.n_dofs);
-        IFEM_KERNEL_CHECK();
-        ctx.kernel_launches++;
-      }
-  }
-
-  // SolidSolver::solve (mpi_solid_solver.cpp:143-161): CG to 1e-8 |b|; the reference's per-rank ILU(0) block
-  // Jacobi is replaced by the node-block Jacobi preconditioner (rank-count independent).
-  std::pair<unsigned int, double> HyperElasticity::solve(Bcsr &A, double *x, const double *b)
-  {
-    ScopedTimer t(ctx, timer_ms["Solve linear system"]);
-    const VecSpace n(ss.n_dofs);
-    block_diag_inverse(ctx, A, d_binv.p);
-    LinOp op = [&](const double *v, double *y) { spmv(ctx, A, v, y); };
-    LinOp pc = [&](const double *v, double *y) { block_diag_apply(ctx, ss.nt.n_nodes, ss.dim, d_binv.p, v, y); };
-    const double tol = 1e-8 * nrm2(ctx, n, b);
-    const SolveResult r = pcg(ctx, n, op, pc, b, x, tol, (int)ss.n_dofs, pool);
-    if (ss.n_con) set_indexed(ctx, ss.n_con, ss.d_con_idx.p, nullptr, x); // constraints.distribute (homogeneous)
-    return {(unsigned)r.iterations, r.residual};
-  }
-
-  double HyperElasticity::get_error(const double *v)
-  {
-    const VecSpace n(ss.n_dofs);
-    copy(ctx, n, v, d_tmp.p);
-    if (ss.n_con) set_indexed(ctx, ss.n_con, ss.d_con_idx.p, nullptr, d_tmp.p);
-    return nrm2(ctx, n, d_tmp.p);
+    neumann_rhs();
   }
 
   void HyperElasticity::run_one_step(bool first_step)
@@ -833,17 +1027,185 @@ namespace ifem
     update_strain_and_stress(); // the shared twin used by MPI::FSI does this every step (mpi_shared_hyper_elasticity.cpp:204-205)
   }
 
-  void HyperElasticity::run()
+  // ===========================================================================
+  LinearElasticity::LinearElasticity(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params, bool shared_)
+    : SolidSolver(ctx_, tria, params), shared(shared_)
   {
-    if (!dofs_ready)
-      {
-        triangulation.refine_global(parameters.global_refinements.size() > 1 ? parameters.global_refinements[1] : 0);
-        setup_dofs();
-        initialize_system();
-      }
-    run_one_step(true);
-    while (time.end() - time.current() > 1e-12) run_one_step(false);
+    if (parameters.solid_type != "LinearElastic") throw std::runtime_error("LinearElasticity: Solid type must be LinearElastic");
+    if (parameters.E.empty() || parameters.nu.empty()) throw std::runtime_error("LinearElasticity: Young's modulus and Poisson's ratio are required");
+    if (parameters.n_solid_parts != 1) throw std::runtime_error("LinearElasticity: one solid part only on the device");
+    // LinearElasticMaterial (linear_elastic_material.cpp:5-14)
+    const double E = parameters.E[0], nu = parameters.nu[0];
+    lambda = E * nu / ((1 + nu) * (1 - 2 * nu));
+    mu = E / (2 * (1 + nu));
+    eta = parameters.eta.empty() ? 0.0 : parameters.eta[0];
+    // the linear solvers integrate every face with a Neumann id (mpi_linear_elasticity.cpp:139-142); the hyperelastic one
+    // skips faces that also carry a Dirichlet id (mpi_hyper_elasticity.cpp:452-456)
+    ss.neumann_skips_dirichlet_faces = false;
   }
 
-  std::vector<double> HyperElasticity::get_current_solution() { return current_displacement.to_host(ctx.stream); }
+  void LinearElasticity::initialize_system()
+  {
+    SolidSolver::initialize_system();
+    stiffness_matrix.init(ss.P, ss.dim, ss.dim, ctx.stream);
+    if (shared) damping_matrix.init(ss.P, ss.dim, ss.dim, ctx.stream);
+    d_tmp2.alloc(ss.n_dofs);
+    d_tmp3.alloc(ss.n_dofs);
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  void LinearElasticity::assemble_system(bool is_initial)
+  {
+    ScopedTimer t(ctx, timer_ms["Assemble system"]);
+    cudaStream_t s = ctx.stream;
+    const double dt = time.get_delta_t();
+    LinearArgs a;
+    a.cell_nodes = ss.d_cell_nodes.p;
+    a.slots = ss.d_slots.p;
+    a.con = ss.d_con.p;
+    a.N = ss.d_N.p;
+    a.G = ss.d_G.p;
+    a.JxW = ss.d_JxW.p;
+    a.nq = ss.nq;
+    a.rho = parameters.solid_rho;
+    a.lambda = lambda;
+    a.mu = mu;
+    a.eta = eta;
+    for (int d = 0; d < 3; ++d) a.grav[d] = d < (int)parameters.gravity.size() ? parameters.gravity[d] : 0.0;
+    a.rowptr = ss.K.rowptr.p;
+    a.sys = a.mass = a.stiff = a.damp = nullptr;
+    a.c_mass = 1.0;
+    a.c_damp = a.c_stiff = 0.0;
+    a.rhs = ss.rhs.p;
+    ss.rhs.zero(s);
+    if (!shared)
+      {
+        // mpi_linear_elasticity.cpp:31-36, 96-121: is_initial -> system_matrix = mass; else system = M + beta dt^2 K and K
+        const double gamma = 0.5 + parameters.damping, beta = gamma / 2;
+        ss.K.zero(s);
+        stiffness_matrix.zero(s);
+        a.sys = ss.K.val.p;
+        if (!is_initial)
+          {
+            a.stiff = stiffness_matrix.val.p;
+            a.c_stiff = beta * dt * dt;
+          }
+      }
+    else if (is_initial)
+      {
+        // mpi_shared_linear_elasticity.cpp:30-40, 126-149: the four matrices are assembled once; beta = (1 + alpha)^2 / 4 HERE
+        const double alpha = -parameters.damping, gamma = 0.5 - alpha, beta = (1 + alpha) * (1 + alpha) / 4;
+        ss.K.zero(s);
+        ss.M.zero(s);
+        stiffness_matrix.zero(s);
+        damping_matrix.zero(s);
+        a.sys = ss.K.val.p;
+        a.mass = ss.M.val.p;
+        a.stiff = stiffness_matrix.val.p;
+        a.damp = damping_matrix.val.p;
+        a.c_damp = gamma * dt * (1 + alpha);
+        a.c_stiff = beta * dt * dt * (1 + alpha);
+      }
+    const int n_colours = (int)ss.colour_offsets.size() - 1;
+    for (int k = 0; k < n_colours; ++k)
+      {
+        a.n_list = ss.colour_offsets[k + 1] - ss.colour_offsets[k];
+        a.cell_list = ss.d_colour_order.p + ss.colour_offsets[k];
+        if (!a.n_list) continue;
+        if (ss.dim == 2)
+          linear_assemble_kernel<2, 4><<<(a.n_list + 3) / 4, 64, 0, s>>>(a);
+        else
+          linear_assemble_kernel<3, 8><<<a.n_list, 64, 0, s>>>(a);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+    neumann_rhs();
+  }
+
+  void LinearElasticity::run_one_step(bool first_step)
+  {
+    const VecSpace n(ss.n_dofs);
+    const double dt = time.get_delta_t();
+    double gamma, beta;
+    if (!shared)
+      {
+        // mpi_linear_elasticity.cpp:199-262
+        gamma = 0.5 + parameters.damping;
+        beta = gamma / 2;
+        if (first_step)
+          {
+            assemble_system(true);
+            solve(ss.K, previous_acceleration.p, ss.rhs.p); // M a_0 = F
+            assemble_system(false);
+          }
+        time.increment();
+        // tmp1 = rhs - K (u_n + dt v_n + (1/2 - beta) dt^2 a_n)
+        lin3(ctx, n, d_tmp2.p, previous_displacement.p, dt, previous_velocity.p, (0.5 - beta) * dt * dt, previous_acceleration.p);
+        spmv(ctx, stiffness_matrix, d_tmp2.p, d_tmp3.p);
+        copy(ctx, n, ss.rhs.p, d_tmp.p);
+        axpy(ctx, n, -1.0, d_tmp3.p, d_tmp.p);
+      }
+    else
+      {
+        // mpi_shared_linear_elasticity.cpp:300-348; beta = (1 - alpha)^2 / 4 HERE (the reference's own inconsistency, kept)
+        const double alpha = -parameters.damping;
+        gamma = 0.5 - alpha;
+        beta = (1 - alpha) * (1 - alpha) / 4;
+        if (first_step)
+          {
+            assemble_system(true);
+            solve(ss.M, previous_acceleration.p, ss.rhs.p);
+          }
+        else if (parameters.simulation_type == "FSI")
+          assemble_system(false);
+        time.increment();
+        lin3(ctx, n, d_tmp2.p, previous_displacement.p, (1 + alpha) * dt, previous_velocity.p, (0.5 - beta) * dt * dt * (1 + alpha),
+             previous_acceleration.p);
+        spmv(ctx, stiffness_matrix, d_tmp2.p, d_tmp3.p);
+        copy(ctx, n, ss.rhs.p, d_tmp.p);
+        axpy(ctx, n, -1.0, d_tmp3.p, d_tmp.p);
+        lin3(ctx, n, d_tmp2.p, previous_velocity.p, (1 + alpha) * (1 - gamma) * dt, previous_acceleration.p, 0.0, previous_acceleration.p);
+        spmv(ctx, damping_matrix, d_tmp2.p, d_tmp3.p);
+        axpy(ctx, n, -1.0, d_tmp3.p, d_tmp.p);
+      }
+    const auto lin = solve(ss.K, current_acceleration.p, d_tmp.p);
+    // v_{n+1} = v_n + (1 - gamma) dt a_n + gamma dt a_{n+1};  u_{n+1} = u_n + dt v_n + dt^2 ((1/2 - beta) a_n + beta a_{n+1})
+    lin3(ctx, n, current_velocity.p, previous_velocity.p, dt * (1 - gamma), previous_acceleration.p, dt * gamma, current_acceleration.p);
+    lin3(ctx, n, current_displacement.p, previous_displacement.p, dt, previous_velocity.p, dt * dt * (0.5 - beta), previous_acceleration.p);
+    axpy(ctx, n, dt * dt * beta, current_acceleration.p, current_displacement.p);
+    copy(ctx, n, current_acceleration.p, previous_acceleration.p);
+    copy(ctx, n, current_velocity.p, previous_velocity.p);
+    copy(ctx, n, current_displacement.p, previous_displacement.p);
+    history.push_back({time.get_timestep(), 0u, lin.second, 0.0, (int)lin.first});
+    if (verbose) std::printf(" CG iteration: %u CG residual: %.6e\n", lin.first, lin.second);
+    if (shared) update_strain_and_stress();
+  }
+
+  void LinearElasticity::update_strain_and_stress()
+  {
+    cudaStream_t s = ctx.stream;
+    stress.zero(s);
+    strain.zero(s);
+    d_count.zero(s);
+    const int n_colours = (int)ss.colour_offsets.size() - 1;
+    for (int k = 0; k < n_colours; ++k)
+      {
+        const int n = ss.colour_offsets[k + 1] - ss.colour_offsets[k];
+        if (!n) continue;
+        const int *list = ss.d_colour_order.p + ss.colour_offsets[k];
+        if (ss.dim == 2)
+          linear_stress_kernel<2, 4><<<(n + 127) / 128, 128, 0, s>>>(n, list, ss.nq, ss.d_cell_nodes.p, d_qpt_to_dof.p, ss.d_G.p,
+                                                                     current_displacement.p, lambda, mu, ss.nt.n_nodes, stress.p, strain.p,
+                                                                     d_count.p);
+        else
+          linear_stress_kernel<3, 8><<<(n + 127) / 128, 128, 0, s>>>(n, list, ss.nq, ss.d_cell_nodes.p, d_qpt_to_dof.p, ss.d_G.p,
+                                                                     current_displacement.p, lambda, mu, ss.nt.n_nodes, stress.p, strain.p,
+                                                                     d_count.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+      }
+    solid_average_kernel<<<(ss.nt.n_nodes + 255) / 256, 256, 0, s>>>(ss.nt.n_nodes, ss.dim * ss.dim, d_count.p, stress.p, strain.p);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+  }
 } // namespace ifem

@@ -1,4 +1,4 @@
-// Solid::MPI::HyperElasticity<dim> on the device (reference include/mpi_hyper_elasticity.h,
+// Solid::MPI::HyperElasticity<dim> and Solid::MPI::[Shared]LinearElasticity<dim> on the device (reference include/mpi_hyper_elasticity.h,
 // source/mpi_hyper_elasticity.cpp; base class source/mpi_solid_solver.cpp): total-Lagrangian
 // NeoHookean solid, Newmark-beta time integration, Newton iteration, CG linear solves.
 //
@@ -42,26 +42,28 @@ namespace ifem
     DevBuf<double> d_nface_val; // dim values per face (traction) or 1 (pressure)
     DevBuf<double> d_face_tables;
     int n_nfaces = 0, nqf = 0, neumann_is_pressure = 0;
+    bool neumann_skips_dirichlet_faces = true; // mpi_hyper_elasticity.cpp:452-456; the linear solvers integrate them
     Bcsr K, M;
     DevBuf<double> rhs;
 
     void setup(Context &ctx, const Triangulation &tria, const Parameters::AllParameters &prm);
   };
 
-  class HyperElasticity
+  // What Solid::MPI::SolidSolver / SharedSolidSolver hold for every material (include/mpi_solid_solver.h:75-160,
+  // include/mpi_shared_solid_solver.h:91-185): the space, the Newmark vectors, the linear solver and what MPI::FSI
+  // reads and writes in the solid.
+  class SolidSolver
   {
   public:
-    HyperElasticity(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params);
+    SolidSolver(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params);
+    virtual ~SolidSolver() = default;
     void run();
-    void run_one_step(bool first_step);
+    virtual void run_one_step(bool first_step) = 0;
+    virtual void assemble_system(bool initial_step) = 0;
+    virtual void update_strain_and_stress() = 0;
     std::vector<double> get_current_solution();
     void setup_dofs();
-    void initialize_system();
-    void update_qph(const double *u_dev);
-    void assemble_system(bool initial_step);
-    // SharedHyperElasticity::update_strain_and_stress (source/mpi_shared_hyper_elasticity.cpp:599-714): Cauchy stress
-    // tau / J and deformation gradient F at the quadrature points, projected to the nodes and averaged
-    void update_strain_and_stress();
+    virtual void initialize_system();
     std::pair<unsigned int, double> solve(Bcsr &A, double *x, const double *b);
 
     Context &ctx;
@@ -70,7 +72,7 @@ namespace ifem
     SolidSpace ss;
     Time time;
     bool verbose = false, dofs_ready = false;
-    DevBuf<double> stress, strain; // [dim*dim][n_nodes] nodal Cauchy stress / deformation gradient
+    DevBuf<double> stress, strain; // [dim*dim][n_nodes] nodal stress / strain (hyperelastic: Cauchy stress, deformation gradient)
     // what MPI::FSI writes into the solid (include/mpi_shared_solid_solver.h: fsi_stress_rows, fluid_velocity,
     // fluid_pressure; used by mpi_fsi.cpp:793-806 and the FSI traction term mpi_shared_hyper_elasticity.cpp:495-554)
     DevBuf<double> fsi_stress_rows; // [dim][n_dofs]: row d1 of the fluid stress at every vertex
@@ -87,9 +89,47 @@ namespace ifem
     std::vector<Record> history;
     std::map<std::string, double> timer_ms;
 
-  private:
+  protected:
     double get_error(const double *v);
+    // traction / pressure faces, or (FSI) the fluid traction on the deformed faces, added to ss.rhs
+    void neumann_rhs();
     DevBuf<double> d_binv, d_tmp, d_pred, d_update, d_qpt_to_dof, d_count;
     VecPool pool;
+  };
+
+  class HyperElasticity : public SolidSolver
+  {
+  public:
+    HyperElasticity(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params);
+    void run_one_step(bool first_step) override;
+    void initialize_system() override;
+    void update_qph(const double *u_dev);
+    void assemble_system(bool initial_step) override;
+    // SharedHyperElasticity::update_strain_and_stress (source/mpi_shared_hyper_elasticity.cpp:599-714): Cauchy stress
+    // tau / J and deformation gradient F at the quadrature points, projected to the nodes and averaged
+    void update_strain_and_stress() override;
+  };
+
+  // Solid::MPI::LinearElasticity<dim> (source/mpi_linear_elasticity.cpp; shared = false) and
+  // Solid::MPI::SharedLinearElasticity<dim> (source/mpi_shared_linear_elasticity.cpp; shared = true, the twin MPI::FSI
+  // drives): small-strain elasticity with the material of source/linear_elastic_material.cpp, Newmark-beta in
+  // acceleration form - the matrices are assembled once, every step is two products and one CG solve.
+  class LinearElasticity : public SolidSolver
+  {
+  public:
+    LinearElasticity(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params, bool shared);
+    void run_one_step(bool first_step) override;
+    void initialize_system() override;
+    void assemble_system(bool is_initial) override;
+    // mpi_shared_linear_elasticity.cpp:401-531: sym grad u and C : sym grad u at the quadrature points -> nodes, averaged
+    void update_strain_and_stress() override;
+
+    const bool shared;
+    // system_matrix = ss.K, mass_matrix = ss.M (shared twin only)
+    Bcsr stiffness_matrix, damping_matrix;
+
+  private:
+    double lambda = 0, mu = 0, eta = 0;
+    DevBuf<double> d_tmp2, d_tmp3;
   };
 } // namespace ifem

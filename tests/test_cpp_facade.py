@@ -55,3 +55,16 @@ def test_cpp_cylinder_driver_reference_golden(golden_dir):
     _build("fluid_cylinder_mpi")
     r = subprocess.run([EXE_CYL, os.path.join(golden_dir, "ins_cylinder_2d.prm")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr + r.stdout
+
+
+def test_cpp_contact_driver_compiles_and_fails_loudly_without_gpu(golden_dir):
+    """tests/fsi_contact_model_mpi through the facade (SCnsIM + SharedLinearElasticity + MPI::FSI with a penetration
+    criterion, GridTools::shift, Tensor<1, dim>): the host side compiles and runs; the solver construction needs the device"""
+    _build("fsi_contact_model_mpi")
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "fsi_contact_model_mpi")
+    r = subprocess.run([exe, os.path.join(golden_dir, "fsi_contact_model_2d.prm")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr

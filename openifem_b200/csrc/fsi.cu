@@ -1,5 +1,7 @@
 #include "fsi.h"
 
+#include "contact.h"
+
 #include "comm.h"
 #include "scnsim.h"
 
@@ -1050,9 +1052,6 @@ namespace ifem
     cudaStream_t s = ctx.stream;
     const VecSpace n(ss.n_dofs);
     const double force_increment = parameters.contact_force_multiplier;
-    double dir_norm = 0.0;
-    for (int d = 0; d < dim; ++d) dir_norm += penetration_direction[d] * penetration_direction[d];
-    dir_norm = std::sqrt(dir_norm);
     // cache the six Newmark vectors
     DevBuf<double> cache[6];
     DevBuf<double> *vecs[6] = {&solid.current_acceleration, &solid.current_velocity, &solid.current_displacement,
@@ -1062,18 +1061,7 @@ namespace ifem
         cache[k].alloc(ss.n_dofs);
         copy(ctx, n, vecs[k]->p, cache[k].p);
       }
-    // geometry tables of the first face quadrature point of every face (fe_face_values.normal_vector(0))
-    const int nv = 1 << dim;
-    FEQ feg(dim, 1);
-    Quadrature fq(dim - 1, ss.degree + 1);
-    std::vector<double> dG((size_t)2 * dim * nv * dim), Ntmp(nv);
-    for (int face = 0; face < 2 * dim; ++face)
-      {
-        double xi[3];
-        int k = 0;
-        for (int d = 0; d < dim; ++d) xi[d] = (d == face / 2) ? double(face % 2) : fq.points[k++];
-        feg.eval(xi, Ntmp.data(), &dG[(size_t)face * nv * dim]);
-      }
+    const ContactScan scan(dim, ss.degree);
     bool still_penetrate = true;
     while (still_penetrate)
       {
@@ -1082,54 +1070,8 @@ namespace ifem
         ++contact_iterations;
         const std::vector<double> u = solid.current_displacement.to_host(s);
         std::vector<double> rows = solid.fsi_stress_rows.to_host(s);
-        for (int f = 0; f < st.n_boundary_faces(); ++f)
-          {
-            const int cell = st.boundary_faces[3 * f], face = st.boundary_faces[3 * f + 1], axis = face / 2, side = face % 2;
-            const int *cn = &ss.nt.cell_nodes[(size_t)cell * ss.npc];
-            // normal of the moved face at its first quadrature point: row `axis` of det(J) J^-1, outward
-            double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, nds[3] = {0, 0, 0};
-            for (int v = 0; v < nv; ++v)
-              for (int i = 0; i < dim; ++i)
-                {
-                  const double xv = ss.nt.coords[(size_t)cn[v] * dim + i] + u[(size_t)cn[v] * dim + i];
-                  for (int j = 0; j < dim; ++j) J[i * dim + j] += xv * dG[((size_t)face * nv + v) * dim + j];
-                }
-            const double sgn = side ? 1.0 : -1.0;
-            if (dim == 2)
-              {
-                // det * Jinv = [[J11, -J01], [-J10, J00]]
-                const double adj[4] = {J[3], -J[1], -J[2], J[0]};
-                for (int k = 0; k < 2; ++k) nds[k] = adj[axis * 2 + k] * sgn;
-              }
-            else
-              {
-                const int r1 = (axis + 1) % 3, r2 = (axis + 2) % 3;
-                for (int k = 0; k < 3; ++k)
-                  {
-                    const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-                    nds[k] = (J[k1 * 3 + r1] * J[k2 * 3 + r2] - J[k1 * 3 + r2] * J[k2 * 3 + r1]) * sgn;
-                  }
-              }
-            double dS = 0.0;
-            for (int k = 0; k < dim; ++k) dS += nds[k] * nds[k];
-            dS = std::sqrt(dS);
-            for (int a : face_local_nodes(dim, ss.degree, face))
-              {
-                const int node = cn[a];
-                double x[3] = {0, 0, 0};
-                for (int d = 0; d < dim; ++d) x[d] = ss.nt.coords[(size_t)node * dim + d] + u[(size_t)node * dim + d];
-                const double penetration_value = penetration_criterion(x);
-                if (!(penetration_value > 1e-5)) continue;
-                still_penetrate = true;
-                for (int d1 = 0; d1 < dim; ++d1)
-                  {
-                    const double traction = force_increment * penetration_value / dir_norm * penetration_direction[d1];
-                    const double nd = nds[d1] / dS;
-                    const double extra = nd > 1e-5 ? traction / nd : 0.0; // extra_stress[d1][dim - 1]
-                    rows[(size_t)d1 * ss.n_dofs + (size_t)dim * node + dim - 1] += extra;
-                  }
-              }
-          }
+        still_penetrate = scan.run(st.n_boundary_faces(), st.boundary_faces.data(), ss.nt.cell_nodes.data(), ss.npc, ss.nt.coords.data(),
+                                   u.data(), ss.n_dofs, penetration_criterion, penetration_direction, force_increment, rows.data());
         if (still_penetrate)
           {
             solid.fsi_stress_rows.upload(rows, s);

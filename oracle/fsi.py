@@ -341,36 +341,43 @@ class FSI:
         multiplier * penetration along the penetration direction to fsi_stress_rows at the penetrating boundary
         vertices (once per (cell, boundary face, face vertex) visit), until no boundary vertex penetrates"""
         s = self.solid
-        dim = s.dim
-        mult = s.prm.contact_force_multiplier
-        dirn = self.penetration_direction
         cached = [v.copy() for v in (s.cur_a, s.cur_v, s.cur_u, s.prev_a, s.prev_v, s.prev_u)]
         still = True
         while still:
-            still = False
             s.run_one_step(first_step)
             self.contact_iterations += 1
-            x = deformed(s.mesh.vertices, s.cur_u, dim)
-            for (cell, face, fid) in s.mesh.boundary_faces:
-                axis, side = int(face) // 2, int(face) % 2
-                cn = s.mesh.cells[cell]
-                J = np.einsum("vi,vj->ij", x[cn], s.face_dG[face][0])
-                nds = np.linalg.det(J) * np.linalg.inv(J)[axis, :] * (1.0 if side else -1.0)
-                normal = nds / np.linalg.norm(nds)  # fe_face_values.normal_vector(0) on the moved mesh
-                for a in fem.face_local_nodes(dim, 1, int(face)):
-                    node = int(cn[a])
-                    pen = self.penetration_criterion(x[node])
-                    if not pen > 1e-5:
-                        continue
-                    still = True
-                    traction = mult * pen / np.linalg.norm(dirn) * dirn
-                    for d1 in range(dim):
-                        extra = traction[d1] / normal[d1] if normal[d1] > 1e-5 else 0.0
-                        s.fsi_stress_rows[d1, dim * node + dim - 1] += extra
+            still = self.contact_scan()
             if still:
                 s.cur_a, s.cur_v, s.cur_u, s.prev_a, s.prev_v, s.prev_u = [v.copy() for v in cached]
                 s.time -= s.dt
                 s.timestep -= 1
+
+    def contact_scan(self):
+        """the penetration scan of apply_contact_model (mpi_fsi.cpp:897-956) on the solid's current displacement; adds the
+        extra stresses to solid.fsi_stress_rows and returns still_penetrate"""
+        s = self.solid
+        dim = s.dim
+        mult = s.prm.contact_force_multiplier
+        dirn = self.penetration_direction
+        still = False
+        x = deformed(s.mesh.vertices, s.cur_u, dim)
+        for (cell, face, fid) in s.mesh.boundary_faces:
+            axis, side = int(face) // 2, int(face) % 2
+            cn = s.mesh.cells[cell]
+            J = np.einsum("vi,vj->ij", x[cn], s.face_dG[face][0])
+            nds = np.linalg.det(J) * np.linalg.inv(J)[axis, :] * (1.0 if side else -1.0)
+            normal = nds / np.linalg.norm(nds)  # fe_face_values.normal_vector(0) on the moved mesh
+            for a in fem.face_local_nodes(dim, 1, int(face)):
+                node = int(cn[a])
+                pen = self.penetration_criterion(x[node])
+                if not pen > 1e-5:
+                    continue
+                still = True
+                traction = mult * pen / np.linalg.norm(dirn) * dirn
+                for d1 in range(dim):
+                    extra = traction[d1] / normal[d1] if normal[d1] > 1e-5 else 0.0
+                    s.fsi_stress_rows[d1, dim * node + dim - 1] += extra
+        return still
 
     def run(self):
         """the time loop of FSI::run (mpi_fsi.cpp:1172-1226) without refinement / checkpoints"""

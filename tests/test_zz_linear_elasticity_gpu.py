@@ -2,8 +2,7 @@
 against the CPU oracle (oracle/solid.py, oracle/fsi.py), and the reference's own goldens through the device path:
 solid_beam_bending_mpi_linearelastic / _shared_linearelastic (u_min = -0.1337) and fsi_contact_model_mpi (u_min = -0.01999).
 
-STATUS: written when the round's GPU budget was spent - the oracle side is pinned on the goldens on the CPU, the device side
-compiles for sm_100a but has not run on a B200 yet. The file sorts last so that the verified suites run first.
+STATUS: 14 passed on a B200 (profiles/r01f_linear_elasticity_contact_gpu_tests.txt).
 
 Tolerances: assembled matrices / rhs / nodal stress 1e-12 relative; displacement after time steps 1e-7 relative (linear
 solves: CG to 1e-8 |b| on the device, sparse direct in the oracle); goldens 1e-3 as in the reference's drivers."""

@@ -251,6 +251,17 @@ namespace Fluid
       }
     };
 
+    // include/mpi_insimex.h: the implicit-explicit twin (same public surface as InsIM)
+    template <int dim>
+    class InsIMEX : public FluidSolver<dim>
+    {
+    public:
+      InsIMEX(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_insimex_create(tria.handle(), params.handle(), &this->h));
+      }
+    };
+
     // include/mpi_scnsim.h + the set_* hooks of include/mpi_fluid_solver.h:120-143
     template <int dim>
     class SCnsIM : public FluidSolver<dim>

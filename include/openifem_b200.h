@@ -152,6 +152,18 @@ int ifem_insim_time(const ifem_insim *s, unsigned int *timestep, double *current
 int ifem_insim_partition(const ifem_insim *s, int which, int *n_owned_nodes, int *n_local_nodes);
 int ifem_insim_local_to_global(const ifem_insim *s, int which, int *global_node_ids);
 
+/* ---- Fluid::MPI::InsIMEX<dim> (include/mpi_insimex.h, source/mpi_insimex.cpp): implicit-explicit twin of InsIM, Q2/Q1.
+ *      The handle is an ifem_insim: setup, run (the time loop of mpi_insimex.cpp:449-480), vectors, matrices, history and
+ *      timers apply; newton_update holds solution_time_increment. The entry points below carry the reference's second
+ *      argument `assemble_system` (matrix + preconditioner rebuilt, or right-hand side only). ---- */
+int ifem_insimex_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out);
+/* InsIMEX::assemble(use_nonzero_constraints, assemble_system) (source/mpi_insimex.cpp:150-355) */
+int ifem_insimex_assemble(ifem_insim *s, int use_nonzero_constraints, int assemble_system);
+/* InsIMEX::solve(use_nonzero_constraints, assemble_system) (:357-386): FGMRES iterations and residual */
+int ifem_insimex_solve(ifem_insim *s, int use_nonzero_constraints, int assemble_system, unsigned int *iterations, double *residual);
+/* InsIMEX::run_one_step(apply_nonzero_constraints, assemble_system) (:388-447) */
+int ifem_insimex_run_one_step(ifem_insim *s, int apply_nonzero_constraints, int assemble_system);
+
 /* ---- Fluid::MPI::SCnsIM<dim> (include/mpi_scnsim.h, source/mpi_scnsim.cpp:15-568) on SUPGFluidSolver
  *      (source/mpi_supg_solver.cpp). The handle is an ifem_insim: every ifem_insim_* entry point (setup, run,
  *      run_one_step, assemble, solve, vectors, matrices, history) applies. Q1/Q1 elements. ---- */

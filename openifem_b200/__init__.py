@@ -395,6 +395,29 @@ class _InsIM:
 FIELD_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_uint, C.c_void_p)
 
 
+class _InsIMEX(_InsIM):
+    """Fluid::MPI::InsIMEX<dim>(triangulation, parameters): implicit-explicit twin of InsIM (source/mpi_insimex.cpp); shares
+    the InsIM handle API, NEWTON_UPDATE holds solution_time_increment."""
+
+    def __init__(self, tria, params):
+        self.tria, self.params = tria, params
+        self._h = C.c_void_p()
+        check(lib().ifem_insimex_create(tria._h, params._h, C.byref(self._h)))
+
+    def assemble(self, use_nonzero_constraints: bool, assemble_system: bool = True):
+        check(lib().ifem_insimex_assemble(self._h, C.c_int(1 if use_nonzero_constraints else 0), C.c_int(1 if assemble_system else 0)))
+
+    def solve(self, use_nonzero_constraints: bool, assemble_system: bool = True):
+        its, res = C.c_uint(), C.c_double()
+        check(lib().ifem_insimex_solve(self._h, C.c_int(1 if use_nonzero_constraints else 0), C.c_int(1 if assemble_system else 0),
+                                       C.byref(its), C.byref(res)))
+        return its.value, res.value
+
+    def run_one_step(self, apply_nonzero_constraints: bool, assemble_system: bool = True):
+        check(lib().ifem_insimex_run_one_step(self._h, C.c_int(1 if apply_nonzero_constraints else 0),
+                                              C.c_int(1 if assemble_system else 0)))
+
+
 class _SCnsIM(_InsIM):
     """Fluid::MPI::SCnsIM<dim>(triangulation, parameters); shares the InsIM handle API."""
 
@@ -643,6 +666,7 @@ class MPI:
 class Fluid:
     class MPI:
         InsIM = _InsIM
+        InsIMEX = _InsIMEX
         SCnsIM = _SCnsIM
 
 

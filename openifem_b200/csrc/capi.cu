@@ -10,6 +10,7 @@
 #include "comm.h"
 #include "fsi.h"
 #include "insim.h"
+#include "insimex.h"
 #include "partition.h"
 #include "scnsim.h"
 #include "solid.h"
@@ -939,6 +940,43 @@ int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms)
     auto it = f->f->timer_ms.find(section);
     *ms = it == f->f->timer_ms.end() ? 0.0 : it->second;
   });
+}
+
+int ifem_insimex_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out)
+{
+  return guard([&] {
+    require_device();
+    auto *h = new ifem_insim;
+    h->s.reset(new InsIMEX(default_context(), tria->t, *params->p));
+    *out = h;
+  });
+}
+static InsIMEX &as_imex(ifem_insim *s)
+{
+  auto *p = dynamic_cast<InsIMEX *>(s->s.get());
+  if (!p) throw std::runtime_error("this fluid solver is not an InsIMEX");
+  return *p;
+}
+int ifem_insimex_assemble(ifem_insim *s, int nz, int assemble_system)
+{
+  return guard([&] {
+    as_imex(s).assemble(nz != 0, assemble_system != 0);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+int ifem_insimex_solve(ifem_insim *s, int nz, int assemble_system, unsigned int *its, double *res)
+{
+  return guard([&] {
+    fill(s->s->ctx, s->s->fs.n_dofs, 0.0, s->s->newton_update.p);
+    const auto r = as_imex(s).solve(nz != 0, assemble_system != 0);
+    IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+    if (its) *its = r.first;
+    if (res) *res = r.second;
+  });
+}
+int ifem_insimex_run_one_step(ifem_insim *s, int nz, int assemble_system)
+{
+  return guard([&] { as_imex(s).run_one_step(nz != 0, assemble_system != 0); });
 }
 
 int ifem_scnsim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out)

@@ -400,6 +400,9 @@ namespace ifem
       BcsrView uu, up, pu, mp;
       double *diag_Mu, *rhs;
       int assemble_mass;
+      // InsIMEX (mpi_insimex.cpp:150-355): convection stays out of the matrix; rhs_only = the `assemble_system == false`
+      // pass (no matrix entry is touched, constrained rows receive nothing)
+      int explicit_convection, rhs_only;
     };
 
     template <int DIM>
@@ -438,6 +441,7 @@ namespace ifem
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
       WarpScratch<DIM> &S = *reinterpret_cast<WarpScratch<DIM> *>(smem + ((T::TAB + 1) & ~1) + (size_t)warp * (sizeof(WarpScratch<DIM>) / 8));
       const double mu = a.mu, rho = a.rho, gam_rho = a.gamma * a.rho, rho_dt = a.rho * a.inv_dt;
+      const double rho_conv = a.explicit_convection ? 0.0 : a.rho; // matrix side of the convection terms
       constexpr int SPC = NU * NU + 2 * NU * NP + NP * NP;
 
       for (int li = blockIdx.x * T::WARPS + warp; li < a.n_list; li += gridDim.x * T::WARPS)
@@ -603,7 +607,7 @@ namespace ifem
           __syncwarp();
           const unsigned char *slots = a.slots + (int64_t)cell * SPC;
           // ---- phase 5: velocity-velocity blocks (:263-273), lane = column node b, 3 row nodes per pass ----
-          if (a.do_uu)
+          if (a.do_uu && !a.rhs_only)
           {
             const int b = lane < NU ? lane : NU - 1;
             int cb[DIM];
@@ -630,8 +634,8 @@ namespace ifem
 #pragma unroll
                     for (int k = 0; k < DIM; ++k) gb[k] = S.g[q][b][k];
 #pragma unroll
-                    for (int i = 0; i < DIM * DIM; ++i) wG[i] = w * rho * S.G[q][i];
-                    const double c1 = w * rho * ugb, c2 = w * rho_dt * Nb;
+                    for (int i = 0; i < DIM * DIM; ++i) wG[i] = w * rho_conv * S.G[q][i];
+                    const double c1 = w * rho_conv * ugb, c2 = w * rho_dt * Nb;
 #pragma unroll
                     for (int t = 0; t < TA; ++t)
                       {
@@ -712,7 +716,7 @@ namespace ifem
           }
           __syncwarp();
           // ---- phase 6: velocity-pressure coupling  -div(phi_i) psi_j  and its transpose (lane = a) ----
-          if (lane < NU)
+          if (lane < NU && !a.rhs_only)
             {
               const int aN = lane;
               double B[NP][DIM];
@@ -866,7 +870,12 @@ namespace ifem
     using T = InsT<DIM>;
     if (fs.nu != T::NU || fs.np != T::NP) throw std::runtime_error("ins_assemble: only Q2/Q1 elements are supported");
     cudaStream_t s = ctx.stream;
-    if (schur_pass)
+    if (prm.rhs_only)
+      {
+        fs.rhs.zero(s);
+        assemble_mass = false;
+      }
+    else if (schur_pass)
       {
         // only the solution-independent coupling blocks and diag(M_u), on the rows of owned + layer-1 nodes
         fs.A_up.zero(s);
@@ -909,7 +918,9 @@ namespace ifem
     a.inv_dt = 1.0 / prm.dt;
     for (int d = 0; d < 3; ++d) a.grav[d] = prm.gravity[d];
     a.con = fs.d_con.p;
-    a.inhom = use_nonzero ? fs.d_nonzero_val.p : nullptr;
+    a.inhom = use_nonzero && !prm.rhs_only ? fs.d_nonzero_val.p : nullptr;
+    a.explicit_convection = prm.explicit_convection;
+    a.rhs_only = prm.rhs_only;
     a.uu = {fs.A_uu.rowptr.p, fs.A_uu.val.p};
     a.up = {fs.A_up.rowptr.p, fs.A_up.val.p};
     a.pu = {fs.A_pu.rowptr.p, fs.A_pu.val.p};

@@ -93,6 +93,8 @@ namespace ifem
   {
     double viscosity, gamma, rho, dt;
     double gravity[3];
+    // InsIMEX: matrix without the convection terms / right-hand side only (mpi_insimex.cpp:150-355)
+    int explicit_convection = 0, rhs_only = 0;
   };
 
   // Fluid::MPI::InsIM<dim>::assemble (reference source/mpi_insim.cpp:152-362).

@@ -56,7 +56,7 @@ namespace ifem
       hc = [this](int id, const double *pt, int c, double &v) {
         auto it = hard_coded.find(id);
         if (it == hard_coded.end()) return false;
-        v = it->second(pt, (unsigned)c, time.current());
+        v = it->second(pt, (unsigned)c, bc_time);
         return true;
       };
     fs.make_constraints(ctx, triangulation, parameters.fluid_dirichlet_bcs, hc);
@@ -171,6 +171,15 @@ namespace ifem
       };
       LinOp jac = [&](const double *x, double *y) { block_diag_apply(ctx, fs.n_owned_unodes, fs.dim, d_binv.p, x, y); };
       const double unrm = nrm2(ctx, vu, utmp);
+      if (control.a_inv_solver == 1)
+        {
+          fill(ctx, vu, 0.0, dst_u);
+          const int max_u_its = (int)std::min<int64_t>(n_dofs_global - n_p_global, (int64_t)control.a_inv_max_it);
+          const SolveResult r = cg(ctx, vu, Auu, utmp, dst_u, true, std::max(control.a_inv_floor, control.a_inv_rel * unrm), max_u_its, pool_ainv);
+          cur.a_inv_its += r.iterations;
+          cur.precond_applies++;
+          return;
+        }
       const SolveResult r = control.a_inv_fp32 >= 2
                               ? inner32.solve(ctx, utmp, unrm, dst_u, control.a_inv_rel, control.a_inv_max_it)
                               : bicgstab(ctx, vu, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);

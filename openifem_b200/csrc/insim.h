@@ -66,6 +66,10 @@ namespace ifem
     // the node-block Jacobi preconditioner, run to a_inv_rel * |src| (hard part 2)
     double a_inv_rel = 1e-3;
     int a_inv_max_it = 2000;
+    // 0: BiCGStab + node-block Jacobi (InsIM); 1: plain CG to max(a_inv_floor, a_inv_rel |src|), the "CG for A" of
+    // InsIMEX (mpi_insimex.cpp:118-131; A_uu is symmetric positive definite there)
+    int a_inv_solver = 0;
+    double a_inv_floor = 0.0;
     // 0: fp64 BiCGStab on the BCSR matrix; 1: same, A_uu streamed as fp32; 2: fp32 BiCGStab on the sliced copy of
     // A_uu (inner32.h); 3: as 2 with the matrix values of the copy stored as row-scaled fp16. Legal because FGMRES
     // is flexible; operator, residuals and Krylov basis stay fp64
@@ -90,7 +94,7 @@ namespace ifem
     InsIM(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params, bool taylor_hood_only = true);
     virtual ~InsIM() = default;
 
-    void run();
+    virtual void run();
     virtual void run_one_step(bool apply_nonzero_constraints, bool assemble_system = true);
     // BlockVector of n_u + n_p doubles, copied to the host
     std::vector<double> get_current_solution();
@@ -118,6 +122,9 @@ namespace ifem
     DevBuf<double> present_solution, evaluation_point, solution_increment, newton_update, fsi_acceleration;
     std::vector<NewtonRecord> history;
     std::map<int, std::function<double(const double *, unsigned int, double)>> hard_coded;
+    // clock of the hard-coded boundary functions (Function::advance_time): InsIM::run never advances it, SUPGFluidSolver::run
+    // advances it by dt before every make_constraints() (mpi_supg_solver.cpp:438-444, 470-478)
+    double bc_time = 0.0;
     // per-section device time, keyed by the reference's TimerOutput section names
     std::map<std::string, double> timer_ms;
     bool dofs_ready = false;

@@ -680,4 +680,33 @@ namespace ifem
     copy(ctx, n, evaluation_point.p, present_solution.p);
     update_stress(); // :417
   }
+
+  // SUPGFluidSolver::run (mpi_supg_solver.cpp:427-486). With hard-coded boundary values the clock of the boundary
+  // functions runs one step ahead of the solver's (advance_time before the first make_constraints, :438-444) and every
+  // step re-makes the constraints and applies the nonzero ones (:470-480): the functions return the increment of the
+  // boundary value over the step. Only the values change between steps - flags, pattern and colouring stay.
+  void SCnsIM::run()
+  {
+    const bool time_dependent = !hard_coded.empty();
+    if (!dofs_ready)
+      {
+        if (time_dependent) bc_time += time.get_delta_t();
+        triangulation.refine_global(parameters.global_refinements.empty() ? 0 : parameters.global_refinements[0]);
+        setup_dofs();
+        make_constraints();
+        initialize_system();
+      }
+    run_one_step(true);
+    while (time.end() - time.current() > 1e-12)
+      {
+        if (time_dependent)
+          {
+            bc_time += time.get_delta_t();
+            make_constraints();
+            run_one_step(true);
+          }
+        else
+          run_one_step(false);
+      }
+  }
 } // namespace ifem

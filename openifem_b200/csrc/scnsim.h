@@ -25,6 +25,8 @@ namespace ifem
     void assemble(bool use_nonzero_constraints) override;
     std::pair<unsigned int, double> solve(bool use_nonzero_constraints) override;
     void run_one_step(bool apply_nonzero_constraints, bool assemble_system = true) override;
+    // SUPGFluidSolver::run (mpi_supg_solver.cpp:427-486): time-dependent hard-coded boundary values
+    void run() override;
     DevBuf<double> fsi_stress; // [dim(dim+1)/2][n_unodes]
     int tpp_its = 0;
 

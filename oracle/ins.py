@@ -391,3 +391,95 @@ class InsIM:
 
     def pressure(self):
         return self.present[self.n_u:]
+
+
+class InsIMEX(InsIM):
+    """Fluid::MPI::InsIMEX<dim> (reference source/mpi_insimex.cpp): the implicit-explicit twin of InsIM. One linear solve
+    per time step for the increment of the solution; the matrix (no convection) is assembled in steps 1 and 2 only
+    (nonzero, then zero constraints, :503-509); convection is explicit. BlockSchurPreconditioner (:7-133): as InsIM's
+    with "CG for A" (unpreconditioned CG to max(1e-12, 1e-4 |src|), :118-131) in place of the direct solve and mass_schur
+    formed once per matrix (:25-45). FGMRES to min(1e-9, 1e-8 |rhs|) (:370-371)."""
+
+    def __init__(self, mesh, params, hard_coded=None, verbose=False):
+        super().__init__(mesh, params, mode="mpi", a_inv="cg", hard_coded=hard_coded, verbose=verbose)
+        self._prec = None
+
+    def assemble(self, use_nonzero_constraints: bool, assemble_system: bool = True):  # :150-355
+        p = self.prm
+        rhs = np.zeros(self.n)
+        if assemble_system:
+            A, M = np.zeros(self.col.size), np.zeros(self.col.size)
+        else:
+            A = M = None
+        inhom = self.nonzero_val if use_nonzero_constraints else None
+        nids = np.asarray(sorted(p.fluid_neumann_bcs), dtype=np.int32)
+        nvals = np.asarray([p.fluid_neumann_bcs[i] for i in nids], dtype=np.float64)
+        grav = np.asarray(p.gravity, dtype=np.float64)
+        rc = lib().oracle_insimex_assemble(
+            C.c_int(self.dim), C.c_int(self.feu.n), C.c_int(self.fep.n), C.c_int(self.mesh.n_cells), _p(self.vertices),
+            _p(self.cells, C.c_int), _p(self.cell_dofs, C.c_int), C.c_int(self.nq), _p(self.qw), _p(self.Nu), _p(self.dNu),
+            _p(self.Np), _p(self.dNgeo), C.c_int(self.nqf), _p(self.qwf), _p(self.Nu_face), _p(self.dNgeo_face),
+            _p(self.present), _p(self.fsi_acceleration), _p(self.indicator, C.c_int), C.c_double(p.viscosity),
+            C.c_double(p.grad_div), C.c_double(p.fluid_rho), C.c_double(self.dt), _p(grav), C.c_int(self.bfaces.shape[0]),
+            _p(self.bfaces, C.c_int), C.c_int(nids.size), _p(nids, C.c_int), _p(nvals), _p(self.con, C.c_ubyte), _p(inhom),
+            C.c_int(1 if assemble_system else 0), _p(self.rowptr, C.c_int64), _p(self.col, C.c_int), _p(A), _p(M), _p(rhs))
+        assert rc == 0
+        if assemble_system:
+            self.system_matrix = sp.csr_matrix((A, self.col, self.rowptr), shape=(self.n, self.n))
+            self.mass_matrix = sp.csr_matrix((M, self.col, self.rowptr), shape=(self.n, self.n))
+        self.system_rhs = rhs
+        return self.system_matrix, self.mass_matrix, rhs
+
+    def _make_preconditioner(self):
+        p, nu = self.prm, self.n_u
+        S, Mm = self.system_matrix, self.mass_matrix
+        Auu, Bt, B = S[:nu, :nu].tocsr(), S[:nu, nu:].tocsr(), S[nu:, :nu].tocsr()
+        Mp = Mm[nu:, nu:].tocsr()
+        Sm = (B @ sp.diags(1.0 / Mm.diagonal()[:nu]) @ Bt).tocsr()
+        self.mass_schur = Sm
+        A_op, Mp_op, Sm_op, Bt_op = CsrOp(Auu), CsrOp(Mp), CsrOp(Sm), CsrOp(Bt)
+        stats = {"cg_mp": 0, "cg_sm": 0, "cg_a": 0, "n": 0}
+
+        def vmult(src):
+            su, spp = src[:nu], src[nu:]
+            nrm = np.linalg.norm(spp)
+            tmp, it, _ = cg(Mp_op, spp, np.zeros_like(spp), max(1e-10, 1e-6 * nrm), spp.size)
+            stats["cg_mp"] += it
+            tmp *= -(p.viscosity + p.grad_div * p.fluid_rho)
+            dp, it, _ = cg(Sm_op, spp, np.zeros_like(spp), max(1e-10, 1e-3 * nrm), spp.size)
+            stats["cg_sm"] += it
+            dp *= -p.fluid_rho / self.dt
+            dp += tmp
+            utmp = su - Bt_op(dp)
+            du, it, _ = cg(A_op, utmp, np.zeros_like(utmp), max(1e-12, 1e-4 * np.linalg.norm(utmp)), utmp.size)
+            stats["cg_a"] += it
+            stats["n"] += 1
+            return np.concatenate([du, dp])
+
+        self.precond_stats = stats
+        return vmult
+
+    def solve(self, use_nonzero_constraints: bool, assemble_system: bool = True):  # :357-386
+        if assemble_system or self._prec is None:
+            self._prec = self._make_preconditioner()
+        tol = min(1e-9, 1e-8 * np.linalg.norm(self.system_rhs))
+        x, its, res = fgmres(CsrOp(self.system_matrix), self._prec, self.system_rhs, tol, self.n)
+        x[self.con != 0] = self.nonzero_val[self.con != 0] if use_nonzero_constraints else 0.0
+        self.solution_time_increment = x
+        return its, res
+
+    def run_one_step(self, apply_nonzero_constraints: bool, assemble_system: bool = True):  # :388-447
+        self.timestep += 1
+        self.time += self.dt
+        self.assemble(apply_nonzero_constraints, assemble_system)
+        its, res = self.solve(apply_nonzero_constraints, assemble_system)
+        self.present = self.present + self.solution_time_increment
+        self.history.append((self.timestep, 0, float(np.linalg.norm(self.system_rhs)), 1.0, its, res))
+        if self.verbose:
+            print(f" step {self.timestep} GMRES_ITR = {its} GMRES_RES = {res:.6e} {self.precond_stats}", flush=True)
+
+    def run(self, max_steps=None):  # :449-480
+        k = 0
+        while self.prm.end_time - self.time > 1e-12 and (max_steps is None or k < max_steps):
+            self.run_one_step(self.timestep == 0, self.timestep < 2)
+            k += 1

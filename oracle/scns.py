@@ -64,6 +64,7 @@ class SCnsIM:
             dGf.append(feg.eval(pts)[1])
         self.Nu_face = np.ascontiguousarray(np.stack(Nuf))
         self.dNgeo_face = np.ascontiguousarray(np.stack(dGf))
+        self.hard_coded, self.bc_time = hard_coded, 0.0
         self.con, self.nonzero_val = fem.make_dirichlet_constraints(d, params.fluid_dirichlet_bcs, hard_coded)
         self.rowptr, self.col = fem.full_pattern(d.cell_dofs, self.n)
         self.h_type, self.h_node = h_shape_functions(dim, pu, pp, d.dofs_per_cell)
@@ -173,11 +174,26 @@ class SCnsIM:
         self.present = self.evaluation_point.copy()
         self.update_stress()
 
+    def make_constraints(self):
+        self.con, self.nonzero_val = fem.make_dirichlet_constraints(self.dofs, self.prm.fluid_dirichlet_bcs, self.hard_coded,
+                                                                    self.bc_time)
+
     def run(self, max_steps=None):
+        """SUPGFluidSolver::run (mpi_supg_solver.cpp:427-486): with hard-coded boundary values the functions' clock is
+        advanced by dt before every make_constraints() (:438-444, :470-478) and every step applies the nonzero
+        constraints - the functions return the *increment* of the boundary value over the step."""
+        if self.hard_coded:
+            self.bc_time += self.dt
+            self.make_constraints()
         self.run_one_step(True)
         k = 1
         while self.prm.end_time - self.time > 1e-12 and (max_steps is None or k < max_steps):
-            self.run_one_step(False)
+            if self.hard_coded:
+                self.bc_time += self.dt
+                self.make_constraints()
+                self.run_one_step(True)
+            else:
+                self.run_one_step(False)
             k += 1
 
     def velocity(self):

@@ -289,6 +289,20 @@ namespace Fluid
         return fields.back().get();
       }
       std::vector<std::unique_ptr<Field>> fields;
+
+    protected:
+      SCnsIM() = default; // for solvers sharing the SUPGFluidSolver surface
+    };
+
+    // include/mpi_insim_supg.h: stabilised incompressible solver on the SUPGFluidSolver surface
+    template <int dim>
+    class SUPGInsIM : public SCnsIM<dim>
+    {
+    public:
+      SUPGInsIM(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_supg_insim_create(tria.handle(), params.handle(), &this->h));
+      }
     };
   } // namespace MPI
 } // namespace Fluid

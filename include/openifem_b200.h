@@ -169,6 +169,10 @@ int ifem_insimex_run_one_step(ifem_insim *s, int apply_nonzero_constraints, int 
  *      run_one_step, assemble, solve, vectors, matrices, history) applies. Q1/Q1 elements. ---- */
 typedef double (*ifem_field_fn)(const double *point, unsigned int component, void *user);
 int ifem_scnsim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out);
+/* Fluid::MPI::SUPGInsIM<dim>(tria, params) (include/mpi_insim_supg.h, source/mpi_insim_supg.cpp): incompressible
+ * Navier-Stokes with SUPG / PSPG / LSIC stabilisation, Q1/Q1, on the same SUPGFluidSolver machinery; every ifem_insim_* and
+ * ifem_scnsim_set_* entry point applies (the PML field and the FSI terms have no effect in this solver) */
+int ifem_supg_insim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out);
 /* set_body_force / set_sigma_pml_field / set_initial_condition (include/mpi_fluid_solver.h:120-143); call before setup */
 int ifem_scnsim_set_body_force(ifem_insim *s, ifem_field_fn f, void *user);
 int ifem_scnsim_set_sigma_pml_field(ifem_insim *s, ifem_field_fn f, void *user);

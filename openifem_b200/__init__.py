@@ -663,11 +663,22 @@ class MPI:
     FSI = _FSI
 
 
+class _SUPGInsIM(_SCnsIM):
+    """Fluid::MPI::SUPGInsIM<dim>(triangulation, parameters): stabilised incompressible solver (source/mpi_insim_supg.cpp)."""
+
+    def __init__(self, tria, params):
+        self.tria, self.params = tria, params
+        self._h = C.c_void_p()
+        self._keep = []
+        check(lib().ifem_supg_insim_create(tria._h, params._h, C.byref(self._h)))
+
+
 class Fluid:
     class MPI:
         InsIM = _InsIM
         InsIMEX = _InsIMEX
         SCnsIM = _SCnsIM
+        SUPGInsIM = _SUPGInsIM
 
 
 class Solid:

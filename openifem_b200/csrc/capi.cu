@@ -988,6 +988,15 @@ int ifem_scnsim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **
     *out = h;
   });
 }
+int ifem_supg_insim_create(ifem_tria *tria, const ifem_params *params, ifem_insim **out)
+{
+  return guard([&] {
+    require_device();
+    auto *h = new ifem_insim;
+    h->s.reset(new SUPGInsIM(default_context(), tria->t, *params->p));
+    *out = h;
+  });
+}
 int ifem_scnsim_set_body_force(ifem_insim *s, ifem_field_fn f, void *user)
 {
   return guard([&] { as_scns(s).set_body_force([f, user](const double *p, unsigned c) { return f(p, c, user); }); });

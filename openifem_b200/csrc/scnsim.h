@@ -30,11 +30,21 @@ namespace ifem
     DevBuf<double> fsi_stress; // [dim(dim+1)/2][n_unodes]
     int tpp_its = 0;
 
-  private:
+  protected:
     void precondition_supg(const double *src, double *dst);
     std::function<double(const double *, unsigned int)> body_force, sigma_pml_field, initial_condition;
     DevBuf<double> d_sigma_pml, d_body_force; // [n_cells][nq], [n_cells][nq][dim] (empty when unset)
     DevBuf<double> d_rowsum_inv, d_b2pp_diag_inv, d_pt1, d_pt2, d_ut1, d_ut2;
     VecPool pool_tpp;
+  };
+
+  // Fluid::MPI::SUPGInsIM<dim> (reference include/mpi_insim_supg.h, source/mpi_insim_supg.cpp): incompressible
+  // Navier-Stokes with SUPG / PSPG / LSIC stabilisation on equal-order Q1/Q1 elements. Everything around the cell loop is
+  // SUPGFluidSolver (Newton loop, FGMRES + block preconditioner, update_stress, time loop) and shared with SCnsIM.
+  class SUPGInsIM : public SCnsIM
+  {
+  public:
+    SUPGInsIM(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params) : SCnsIM(ctx, tria, params) {}
+    void assemble(bool use_nonzero_constraints) override;
   };
 } // namespace ifem

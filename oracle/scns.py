@@ -201,3 +201,30 @@ class SCnsIM:
 
     def pressure(self):
         return self.present[self.n_u:]
+
+
+class SUPGInsIM(SCnsIM):
+    """Fluid::MPI::SUPGInsIM<dim> (reference source/mpi_insim_supg.cpp; cell loop in oracle/csrc/oracle_insim_supg.cpp):
+    incompressible Navier-Stokes with SUPG / PSPG / LSIC stabilisation on SUPGFluidSolver - everything but assemble() is
+    shared with SCnsIM (Newton loop, solve, update_stress, time loop)."""
+
+    def assemble(self, use_nonzero_constraints: bool):
+        p = self.prm
+        A = np.zeros(self.col.size)
+        rhs = np.zeros(self.n)
+        inhom = self.nonzero_val if use_nonzero_constraints else None
+        nids = np.asarray(sorted(p.fluid_neumann_bcs), dtype=np.int32)
+        nvals = np.asarray([p.fluid_neumann_bcs[i] for i in nids], dtype=np.float64)
+        grav = np.asarray(p.gravity, dtype=np.float64)
+        rc = lib().oracle_insim_supg_assemble(
+            C.c_int(self.dim), C.c_int(self.feu.n), C.c_int(self.fep.n), C.c_int(self.mesh.n_cells), _p(self.vertices),
+            _p(self.cells, C.c_int), _p(self.cell_dofs, C.c_int), C.c_int(self.nq), _p(self.qw), _p(self.Nu), _p(self.dNu),
+            _p(self.Np), _p(self.dNp), _p(self.dNgeo), C.c_int(self.nqf), _p(self.qwf), _p(self.Nu_face), _p(self.dNgeo_face),
+            _p(self.evaluation_point), _p(self.present), _p(self.body_force), C.c_int(self.h_type.size), _p(self.h_type, C.c_int),
+            _p(self.h_node, C.c_int), C.c_double(p.viscosity), C.c_double(p.fluid_rho), C.c_double(self.dt), _p(grav),
+            C.c_int(self.bfaces.shape[0]), _p(self.bfaces, C.c_int), C.c_int(nids.size), _p(nids, C.c_int), _p(nvals),
+            _p(self.con, C.c_ubyte), _p(inhom), _p(self.rowptr, C.c_int64), _p(self.col, C.c_int), _p(A), _p(rhs))
+        assert rc == 0
+        self.system_matrix = sp.csr_matrix((A, self.col, self.rowptr), shape=(self.n, self.n))
+        self.system_rhs = rhs
+        return self.system_matrix, rhs

@@ -20,6 +20,8 @@ this path; everything else is checked GPU-vs-oracle.
                         u_min = -0.01999 +-1e-3; reference tests/fsi_contact_model_mpi/fsi_contact_model_mpi.cpp:46-60
   fluid_cylinder_mpi_insimex (Fluid::MPI::InsIMEX, cylinder mesh, 1 step): max v = 0.374062, max p = 46.5308, +-1e-3
                         reference tests/fluid_cylinder_mpi_insimex/fluid_cylinder_mpi_insimex.cpp:83-95
+  fluid_pressure_driven_mpi_insim_supg / fluid_plane_wall_driven_mpi_insim_supg (Fluid::MPI::SUPGInsIM, Q1/Q1, 10 steps):
+                        v_max = 2.5e-2 (+-2 %, 30th largest +-1e-3) / |v|_2 = 4.7112 +-1e-3
   acoustic_duct_wave_mpi / acoustic_pml_mpi (SCnsIM with a time-dependent hard-coded boundary value, 1000 / 500 steps):
                         max v = 5.93 +-1e-3 / |max v| < 5e-2; reference tests/acoustic_duct_wave_mpi/...cpp:60-68,
                         tests/acoustic_pml_mpi/...cpp:79-85
@@ -260,3 +262,28 @@ def test_acoustic_reference_goldens_full_run(case):
         assert s.timestep == 1000 and abs(vmax - 5.93) / 5.93 < 1e-3, vmax
     else:
         assert s.timestep == 500 and abs(vmax) < 5e-2, vmax
+
+
+# ---- Fluid::MPI::SUPGInsIM (oracle/scns.py SUPGInsIM + oracle/csrc/oracle_insim_supg.cpp) --------------------------
+def test_fluid_pressure_driven_mpi_insim_supg_golden(golden_dir):
+    """reference tests/fluid_pressure_driven_mpi_insim_supg/...cpp:38-58: 100 x 10 cells refined once, 10 steps; the largest
+    velocity value within 2 % and the 30th largest within 1e-3 of P D^2 / (16 mu L) = 2.5e-2"""
+    from oracle import scns
+
+    p = prm.Params(os.path.join(golden_dir, "supg_ins_pressure_driven_2d.prm"))
+    s = scns.SUPGInsIM(fem.BoxMesh((100, 10), (0, 0), (2.0, 0.2)).refine_global(p.global_refinements[0]), p)
+    s.run()
+    v = np.sort(s.velocity())[::-1]
+    assert abs(v[0] - 2.5e-2) / 2.5e-2 < 2e-2
+    assert abs(v[29] - 2.5e-2) / 2.5e-2 < 1e-3
+
+
+def test_fluid_plane_wall_driven_mpi_insim_supg_golden(golden_dir):
+    """reference tests/fluid_plane_wall_driven_mpi_insim_supg/...cpp:42-51: 20 x 16 cells, 10 steps; l2 norm of the velocity
+    block 4.7112 +- 1e-3 (the oracle gives 4.711198)"""
+    from oracle import scns
+
+    p = prm.Params(os.path.join(golden_dir, "supg_ins_plane_wall_driven_2d.prm"))
+    s = scns.SUPGInsIM(fem.BoxMesh((20, 16), (0, 0), (2.0, 0.4)).refine_global(p.global_refinements[0]), p)
+    s.run()
+    assert abs(np.linalg.norm(s.velocity()) - 4.7112) / 4.7112 < 1e-5

@@ -1,0 +1,103 @@
+"""GPU parity of Fluid::MPI::SUPGInsIM (reference source/mpi_insim_supg.cpp) against the CPU oracle
+(oracle/scns.py SUPGInsIM + oracle/csrc/oracle_insim_supg.cpp, pinned on the reference goldens
+fluid_pressure_driven_mpi_insim_supg and fluid_plane_wall_driven_mpi_insim_supg), and both goldens through the device path.
+
+STATUS: written after the round's GPU budget was spent. The kernel bodies (openifem_b200/csrc/insim_supg.cuh) are checked
+on the CPU against the oracle to 1e-13 (tests/test_supg_kernels_cpu.py, same source compiled with g++); the launch and the
+solver around it (SCnsIM's verified SUPGFluidSolver machinery) have not run on a B200 yet. The file sorts after the verified
+suites.
+
+Tolerances: assembled matrix / rhs 1e-12 relative; fields after time steps 1e-5 (FGMRES to the reference's 1e-6 |rhs| on the
+device, sparse direct in the oracle); goldens as in the reference's drivers."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from util import cavity_prm, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(prm_text, reps, lo, hi, body_force=None):
+    import openifem_b200 as ifem
+    from oracle import fem, prm, scns
+
+    o = scns.SUPGInsIM(fem.BoxMesh(tuple(reps), lo, hi), prm.Params(prm_text, is_text=True), body_force=body_force)
+    tria = ifem.Triangulation(len(reps))
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, lo, hi, True)
+    g = ifem.Fluid.MPI.SUPGInsIM(tria, ifem.Parameters.AllParameters(text=prm_text))
+    if body_force is not None:
+        g.set_body_force(body_force)
+    g.setup()
+    return o, g
+
+
+def _q1(text):
+    return text.replace("set Velocity degree = 2", "set Velocity degree = 1")
+
+
+CASES = [
+    (_q1(cavity_prm(2)), (6, 5), (0, 0), (1.0, 0.8), None),
+    (_q1(cavity_prm(3, mu=0.05)), (3, 4, 3), (0, 0, 0), (1.0, 1.2, 0.9), None),
+    (_q1(cavity_prm(2, gravity=[10.0, -3.0], dirichlet={2: (3, [0, 0]), 3: (3, [0.5, 0])}, neumann={0: 10.0, 1: -2.5})), (7, 4), (0, 0),
+     (2.0, 0.2), lambda x, c: 0.3 * (c + 1) * x[0] - 0.2 * x[1]),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("nonzero", [True, False])
+def test_supg_insim_assembly_matches_oracle(case, nonzero):
+    """SUPGInsIM::assemble (mpi_insim_supg.cpp:15-328) on random evaluation point / present solution"""
+    text, reps, lo, hi, bf = CASES[case]
+    o, g = _pair(text, reps, lo, hi, bf)
+    assert g.n_dofs == o.n
+    rng = np.random.default_rng(30 + case)
+    ev, pr = rng.uniform(-1, 1, o.n), rng.uniform(-1, 1, o.n)
+    o.evaluation_point[:], o.present[:] = ev, pr
+    g.set_vector(g.EVALUATION_POINT, ev)
+    g.set_vector(g.PRESENT, pr)
+    A_ref, rhs_ref = o.assemble(nonzero)
+    g.assemble(nonzero)
+    A = g.get_matrix(0)
+    assert sp.linalg.norm((A - A_ref).tocsr()) / sp.linalg.norm(A_ref) < 1e-12
+    assert rel(g.get_vector(g.SYSTEM_RHS), rhs_ref) < 1e-12
+
+
+def test_supg_insim_time_steps_match_oracle():
+    """three steps of a lid-driven cavity: Newton histories and fields"""
+    o, g = _pair(_q1(cavity_prm(2, newton_tol=1e-8)), (8, 8), (0, 0), (1.0, 1.0))
+    for k in range(3):
+        o.run_one_step(k == 0)
+        g.run_one_step(k == 0)
+    sol = g.get_current_solution()
+    assert rel(sol[: o.n_u], o.velocity()) < 1e-5
+    p_g, p_o = sol[o.n_u:], o.pressure()
+    assert rel(p_g - p_g.mean(), p_o - p_o.mean()) < 1e-4
+    assert len(g.history()) == len(o.history)
+
+
+def test_pressure_driven_supg_reference_golden(golden_dir):
+    """tests/fluid_pressure_driven_mpi_insim_supg/...cpp:38-58: largest velocity within 2 %, 30th largest within 1e-3 of 2.5e-2"""
+    import openifem_b200 as ifem
+
+    tria = ifem.Triangulation(2)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, (100, 10), (0, 0), (2.0, 0.2), True)
+    flow = ifem.Fluid.MPI.SUPGInsIM(tria, ifem.Parameters.AllParameters(os.path.join(golden_dir, "supg_ins_pressure_driven_2d.prm")))
+    flow.run()
+    v = np.sort(flow.get_current_solution()[: flow.n_u])[::-1]
+    assert abs(v[0] - 2.5e-2) / 2.5e-2 < 2e-2, v[0]
+    assert abs(v[29] - 2.5e-2) / 2.5e-2 < 1e-3, v[29]
+
+
+def test_plane_wall_driven_supg_reference_golden(golden_dir):
+    """tests/fluid_plane_wall_driven_mpi_insim_supg/...cpp:42-51: l2 norm of the velocity 4.7112 +- 1e-3"""
+    import openifem_b200 as ifem
+
+    tria = ifem.Triangulation(2)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, (20, 16), (0, 0), (2.0, 0.4), True)
+    flow = ifem.Fluid.MPI.SUPGInsIM(tria, ifem.Parameters.AllParameters(os.path.join(golden_dir, "supg_ins_plane_wall_driven_2d.prm")))
+    flow.run()
+    l2 = np.linalg.norm(flow.get_current_solution()[: flow.n_u])
+    assert abs(l2 - 4.7112) / 4.7112 < 1e-3, l2

@@ -152,6 +152,32 @@ int ifem_insim_time(const ifem_insim *s, unsigned int *timestep, double *current
 int ifem_insim_partition(const ifem_insim *s, int which, int *n_owned_nodes, int *n_local_nodes);
 int ifem_insim_local_to_global(const ifem_insim *s, int which, int *global_node_ids);
 
+/* ---- result files and checkpoints (formats: openifem_b200/csrc/output.h). FluidSolver::output_results / save_checkpoint /
+ *      load_checkpoint (source/mpi_fluid_solver.cpp:491-713). Nothing is written until a directory is set; then run() and
+ *      run_one_step() write fluid_NNNNNN.pvtu + .procRRRR.vtu pieces + fluid.pvd at the output interval and
+ *      NNNNNN.fluid_checkpoint at the save interval, and run() restarts from the latest checkpoint in the directory.
+ *      dir = NULL or "" switches it off again. ---- */
+int ifem_insim_set_output_directory(ifem_insim *s, const char *dir);
+int ifem_insim_output_results(ifem_insim *s, unsigned int output_index);
+int ifem_insim_save_checkpoint(ifem_insim *s, int output_index);
+int ifem_insim_load_checkpoint(ifem_insim *s, int *loaded);
+/* time.current() and time.get_timestep() of the solver (Utils::Time) */
+int ifem_insim_get_time(const ifem_insim *s, double *time, unsigned int *timestep);
+/* host-side pieces of the formats, usable without a device: an ASCII .vtu from lexicographically ordered quad / hex cells,
+ * point fields [n_points][ncomp] and cell fields [n_cells]; a .pvd collection as Utils::PVDWriter writes it (source/
+ * utilities.cpp:38-81); deal.II Vector<double>::block_write / block_read streams (the solid checkpoint files) */
+int ifem_write_vtu(const char *path, int dim, int64_t n_points, const double *points, int64_t n_cells, const int *cells,
+                   int n_point_fields, const char *const *point_names, const int *point_ncomp, const double *const *point_data,
+                   int n_cell_fields, const char *const *cell_names, const double *const *cell_data);
+int ifem_write_pvd(const char *path, const char *pvtu_prefix, int n, const double *times, const unsigned int *timesteps);
+int ifem_block_write(const char *path, int64_t n, const double *values);
+int ifem_block_read(const char *path, int64_t capacity, double *values, int64_t *n);
+/* FluidSolver::output_results on host arrays (what ifem_insim_output_results does after downloading the solver state):
+ * the triangulation with FE_Q(pu) / FE_Q(pp) numbering of this library, present_solution / fsi_acceleration [dim n_u + n_p],
+ * indicator [n_cells] or NULL, stress [dim dim][n_velocity_nodes] or NULL -> <dir>/fluid_NNNNNN.pvtu + piece */
+int ifem_fluid_write_results_host(const ifem_tria *tria, int pu, int pp, const double *present, const double *fsi_acceleration,
+                                  const int *indicator, const double *stress, const char *dir, unsigned int output_index);
+
 /* ---- Fluid::MPI::InsIMEX<dim> (include/mpi_insimex.h, source/mpi_insimex.cpp): implicit-explicit twin of InsIM, Q2/Q1.
  *      The handle is an ifem_insim: setup, run (the time loop of mpi_insimex.cpp:449-480), vectors, matrices, history and
  *      timers apply; newton_update holds solution_time_increment. The entry points below carry the reference's second
@@ -199,6 +225,14 @@ int ifem_hyper_create(ifem_tria *tria, const ifem_params *params, ifem_hyper **o
  * applies except update_qph / get_qph (hyperelastic only). */
 int ifem_linear_elasticity_create(ifem_tria *tria, const ifem_params *params, int shared, ifem_hyper **out);
 int ifem_hyper_destroy(ifem_hyper *s);
+/* SharedSolidSolver::output_results / save_checkpoint / load_checkpoint (source/mpi_shared_solid_solver.cpp:237-337, 452-571):
+ * solid_NNNNNN.pvtu + piece + solid.pvd; NNNNNN.solid_checkpoint_{displacement,velocity,acceleration} in deal.II's
+ * block_write format. Off until a directory is set. */
+int ifem_hyper_set_output_directory(ifem_hyper *s, const char *dir);
+int ifem_hyper_output_results(ifem_hyper *s, unsigned int output_index);
+int ifem_hyper_save_checkpoint(ifem_hyper *s, int output_index);
+int ifem_hyper_load_checkpoint(ifem_hyper *s, int *loaded);
+int ifem_hyper_get_time(const ifem_hyper *s, double *time, unsigned int *timestep);
 int ifem_hyper_set_verbose(ifem_hyper *s, int verbose);
 /* setup_dofs(); initialize_system() (incl. setup_qph) - no refinement */
 int ifem_hyper_setup(ifem_hyper *s);

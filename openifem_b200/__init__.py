@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import IfemError, InsControl, NewtonRecord, SolidRecord, check, dptr, iptr, lptr, lib
 
-__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Solid", "MPI", "Partition", "IfemError", "init", "init_distributed",
+__all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Solid", "MPI", "io", "Partition", "IfemError", "init", "init_distributed",
            "comm_unique_id", "comm_init", "comm_finalize", "kernel_launches", "set_host_threads"]
 
 
@@ -216,6 +216,28 @@ class _InsIM:
         out = np.empty(self.n_dofs)
         check(lib().ifem_insim_get_current_solution(self._h, dptr(out)))
         return out
+
+    # -- result files and checkpoints (FluidSolver::output_results / save_checkpoint / load_checkpoint) ----------
+    def set_output_directory(self, directory):
+        """switches the .vtu / .pvtu / .pvd output and the checkpoints of run() / run_one_step() on (None: off)"""
+        check(lib().ifem_insim_set_output_directory(self._h, directory.encode() if directory else None))
+
+    def output_results(self, output_index: int):
+        check(lib().ifem_insim_output_results(self._h, C.c_uint(output_index)))
+
+    def save_checkpoint(self, output_index: int):
+        check(lib().ifem_insim_save_checkpoint(self._h, C.c_int(output_index)))
+
+    def load_checkpoint(self) -> bool:
+        loaded = C.c_int()
+        check(lib().ifem_insim_load_checkpoint(self._h, C.byref(loaded)))
+        return bool(loaded.value)
+
+    def get_time(self):
+        """(time.current(), time.get_timestep())"""
+        t, k = C.c_double(), C.c_uint()
+        check(lib().ifem_insim_get_time(self._h, C.byref(t), C.byref(k)))
+        return t.value, k.value
 
     def setup(self):
         """setup_dofs(); make_constraints(); initialize_system()"""
@@ -477,6 +499,26 @@ class _HyperElasticity:
     def run_one_step(self, first_step: bool):
         check(lib().ifem_hyper_run_one_step(self._h, C.c_int(1 if first_step else 0)))
 
+    # -- result files and checkpoints (SharedSolidSolver::output_results / save_checkpoint / load_checkpoint) ----
+    def set_output_directory(self, directory):
+        check(lib().ifem_hyper_set_output_directory(self._h, directory.encode() if directory else None))
+
+    def output_results(self, output_index: int):
+        check(lib().ifem_hyper_output_results(self._h, C.c_uint(output_index)))
+
+    def save_checkpoint(self, output_index: int):
+        check(lib().ifem_hyper_save_checkpoint(self._h, C.c_int(output_index)))
+
+    def load_checkpoint(self) -> bool:
+        loaded = C.c_int()
+        check(lib().ifem_hyper_load_checkpoint(self._h, C.byref(loaded)))
+        return bool(loaded.value)
+
+    def get_time(self):
+        t, k = C.c_double(), C.c_uint()
+        check(lib().ifem_hyper_get_time(self._h, C.byref(t), C.byref(k)))
+        return t.value, k.value
+
     def setup(self):
         check(lib().ifem_hyper_setup(self._h))
 
@@ -671,6 +713,56 @@ class _SUPGInsIM(_SCnsIM):
         self._h = C.c_void_p()
         self._keep = []
         check(lib().ifem_supg_insim_create(tria._h, params._h, C.byref(self._h)))
+
+
+class io:
+    """Host-side pieces of the on-disk formats (openifem_b200/csrc/output.h); no device needed."""
+
+    @staticmethod
+    def write_vtu(path, dim, points, cells, point_fields=(), cell_fields=()):
+        """points [n][dim]; cells [m][2^dim] lexicographic; point_fields [(name, array [n] or [n][k])]; cell_fields [(name, [m])]"""
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        pf = [(n, np.ascontiguousarray(a, dtype=np.float64)) for n, a in point_fields]
+        cf = [(n, np.ascontiguousarray(a, dtype=np.float64)) for n, a in cell_fields]
+
+        def pack(fields):
+            names = (C.c_char_p * max(len(fields), 1))(*[n.encode() for n, _ in fields])
+            data = (C.POINTER(C.c_double) * max(len(fields), 1))(*[dptr(a) for _, a in fields])
+            return names, data
+
+        pn, pd = pack(pf)
+        cn, cd = pack(cf)
+        nc = (C.c_int * max(len(pf), 1))(*[1 if a.ndim == 1 else a.shape[1] for _, a in pf])
+        check(lib().ifem_write_vtu(path.encode(), C.c_int(dim), C.c_int64(points.shape[0]), dptr(points), C.c_int64(cells.shape[0]),
+                                   iptr(cells), C.c_int(len(pf)), pn, nc, pd, C.c_int(len(cf)), cn, cd))
+
+    @staticmethod
+    def write_pvd(path, prefix, times, timesteps):
+        t = np.ascontiguousarray(times, dtype=np.float64)
+        k = np.ascontiguousarray(timesteps, dtype=np.uint32)
+        check(lib().ifem_write_pvd(path.encode(), prefix.encode(), C.c_int(t.size), dptr(t), k.ctypes.data_as(C.POINTER(C.c_uint))))
+
+    @staticmethod
+    def block_write(path, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        check(lib().ifem_block_write(path.encode(), C.c_int64(v.size), dptr(v)))
+
+    @staticmethod
+    def block_read(path, capacity):
+        out, n = np.empty(capacity), C.c_int64()
+        check(lib().ifem_block_read(path.encode(), C.c_int64(capacity), dptr(out), C.byref(n)))
+        return out[: n.value]
+
+    @staticmethod
+    def fluid_write_results_host(tria, pu, pp, present, fsi_acceleration=None, indicator=None, stress=None, directory=".", output_index=0):
+        present = np.ascontiguousarray(present, dtype=np.float64)
+        acc = None if fsi_acceleration is None else np.ascontiguousarray(fsi_acceleration, dtype=np.float64)
+        ind = None if indicator is None else np.ascontiguousarray(indicator, dtype=np.int32)
+        st = None if stress is None else np.ascontiguousarray(stress, dtype=np.float64)
+        check(lib().ifem_fluid_write_results_host(tria._h, C.c_int(pu), C.c_int(pp), dptr(present), None if acc is None else dptr(acc),
+                                                  None if ind is None else iptr(ind), None if st is None else dptr(st),
+                                                  directory.encode(), C.c_uint(output_index)))
 
 
 class Fluid:

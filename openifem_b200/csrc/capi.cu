@@ -11,6 +11,7 @@
 #include "fsi.h"
 #include "insim.h"
 #include "insimex.h"
+#include "output.h"
 #include "partition.h"
 #include "scnsim.h"
 #include "solid.h"
@@ -939,6 +940,101 @@ int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms)
   return guard([&] {
     auto it = f->f->timer_ms.find(section);
     *ms = it == f->f->timer_ms.end() ? 0.0 : it->second;
+  });
+}
+
+int ifem_insim_set_output_directory(ifem_insim *s, const char *dir)
+{
+  return guard([&] { s->s->set_output_directory(dir ? dir : ""); });
+}
+int ifem_insim_output_results(ifem_insim *s, unsigned int output_index)
+{
+  return guard([&] { s->s->output_results(output_index); });
+}
+int ifem_insim_save_checkpoint(ifem_insim *s, int output_index)
+{
+  return guard([&] { s->s->save_checkpoint(output_index); });
+}
+int ifem_insim_load_checkpoint(ifem_insim *s, int *loaded)
+{
+  return guard([&] { *loaded = s->s->load_checkpoint() ? 1 : 0; });
+}
+int ifem_insim_get_time(const ifem_insim *s, double *time, unsigned int *timestep)
+{
+  return guard([&] {
+    if (time) *time = s->s->time.current();
+    if (timestep) *timestep = s->s->time.get_timestep();
+  });
+}
+int ifem_write_vtu(const char *path, int dim, int64_t n_points, const double *points, int64_t n_cells, const int *cells,
+                   int n_point_fields, const char *const *point_names, const int *point_ncomp, const double *const *point_data,
+                   int n_cell_fields, const char *const *cell_names, const double *const *cell_data)
+{
+  return guard([&] {
+    if (dim != 2 && dim != 3) throw std::runtime_error("ifem_write_vtu: dim must be 2 or 3");
+    std::vector<io::Field> pd, cd;
+    for (int k = 0; k < n_point_fields; ++k)
+      pd.push_back({point_names[k], point_ncomp[k], std::vector<double>(point_data[k], point_data[k] + n_points * point_ncomp[k])});
+    for (int k = 0; k < n_cell_fields; ++k) cd.push_back({cell_names[k], 1, std::vector<double>(cell_data[k], cell_data[k] + n_cells)});
+    io::write_vtu(path, dim, std::vector<double>(points, points + n_points * dim), std::vector<int>(cells, cells + n_cells * (1 << dim)), pd, cd);
+  });
+}
+int ifem_write_pvd(const char *path, const char *pvtu_prefix, int n, const double *times, const unsigned int *timesteps)
+{
+  return guard([&] {
+    io::PVDWriter w(path);
+    for (int k = 0; k < n; ++k) w.write_current_timestep(times[k], timesteps[k], pvtu_prefix, 6);
+  });
+}
+int ifem_block_write(const char *path, int64_t n, const double *values)
+{
+  return guard([&] { io::block_write(path, std::vector<double>(values, values + n)); });
+}
+int ifem_block_read(const char *path, int64_t capacity, double *values, int64_t *n)
+{
+  return guard([&] {
+    const std::vector<double> v = io::block_read(path);
+    *n = (int64_t)v.size();
+    if ((int64_t)v.size() > capacity) throw std::runtime_error("ifem_block_read: buffer too small");
+    std::copy(v.begin(), v.end(), values);
+  });
+}
+int ifem_fluid_write_results_host(const ifem_tria *tria, int pu, int pp, const double *present, const double *fsi_acceleration,
+                                  const int *indicator, const double *stress, const char *dir, unsigned int output_index)
+{
+  return guard([&] {
+    const Triangulation &t = tria->t;
+    const NodeTable un = build_node_table(t, pu), pn = build_node_table(t, pp);
+    const size_t n = (size_t)t.dim * un.n_nodes + pn.n_nodes;
+    std::vector<int> all(t.n_cells());
+    for (int c = 0; c < t.n_cells(); ++c) all[c] = c;
+    io::write_fluid_results(dir ? dir : ".", output_index, 0, 1, t.dim, un, pn, all, std::vector<double>(present, present + n),
+                            fsi_acceleration ? std::vector<double>(fsi_acceleration, fsi_acceleration + n) : std::vector<double>(),
+                            indicator ? std::vector<int>(indicator, indicator + t.n_cells()) : std::vector<int>(),
+                            stress ? std::vector<double>(stress, stress + (size_t)t.dim * t.dim * un.n_nodes) : std::vector<double>());
+  });
+}
+int ifem_hyper_set_output_directory(ifem_hyper *s, const char *dir)
+{
+  return guard([&] { s->s->set_output_directory(dir ? dir : ""); });
+}
+int ifem_hyper_output_results(ifem_hyper *s, unsigned int output_index)
+{
+  return guard([&] { s->s->output_results(output_index); });
+}
+int ifem_hyper_save_checkpoint(ifem_hyper *s, int output_index)
+{
+  return guard([&] { s->s->save_checkpoint(output_index); });
+}
+int ifem_hyper_load_checkpoint(ifem_hyper *s, int *loaded)
+{
+  return guard([&] { *loaded = s->s->load_checkpoint() ? 1 : 0; });
+}
+int ifem_hyper_get_time(const ifem_hyper *s, double *time, unsigned int *timestep)
+{
+  return guard([&] {
+    if (time) *time = s->s->time.current();
+    if (timestep) *timestep = s->s->time.get_timestep();
   });
 }
 

@@ -271,6 +271,7 @@ namespace ifem
 
   void InsIM::run_one_step(bool apply_nonzero_constraints, bool /*assemble_system*/)
   {
+    io_before_step();
     time.increment();
     if (verbose && fs.rank == 0)
       std::printf("%s\nTime step = %u, at t = %e\n", std::string(96, '*').c_str(), time.get_timestep(), time.current());
@@ -308,6 +309,7 @@ namespace ifem
     lin3(ctx, n, solution_increment.p, present_solution.p, -1.0, evaluation_point.p, 0.0, evaluation_point.p);
     copy(ctx, n, evaluation_point.p, present_solution.p);
     update_stress(); // mpi_insim.cpp:475
+    io_after_step();
   }
 
   void InsIM::update_stress()
@@ -319,6 +321,7 @@ namespace ifem
 
   void InsIM::run()
   {
+    const bool success_load = load_checkpoint(); // mpi_insim.cpp:497-498; false unless an output directory is set
     if (!dofs_ready)
       {
         triangulation.refine_global(parameters.global_refinements.empty() ? 0 : parameters.global_refinements[0]);
@@ -326,7 +329,7 @@ namespace ifem
         make_constraints();
         initialize_system();
       }
-    run_one_step(true);
+    if (!success_load) run_one_step(true);
     while (time.end() - time.current() > 1e-12) run_one_step(false);
   }
 

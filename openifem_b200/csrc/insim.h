@@ -12,6 +12,7 @@
 #include "fluid.h"
 #include "inner32.h"
 #include "krylov.h"
+#include "output.h"
 
 namespace ifem
 {
@@ -112,6 +113,16 @@ namespace ifem
     void update_stress();
     DevBuf<double> stress; // [dim*dim][n_velocity_nodes]
 
+    // Result files and checkpoints (solver_io.cu; formats in output.h). Off until a directory is set; then run() /
+    // run_one_step() write fluid_NNNNNN.{pvtu,procRRRR.vtu} + fluid.pvd at the output interval, NNNNNN.fluid_checkpoint at
+    // the save interval, and run() restarts from the latest checkpoint found (mpi_fluid_solver.cpp:491-713)
+    void set_output_directory(const std::string &dir);
+    void output_results(unsigned int output_index);
+    void save_checkpoint(int output_index);
+    bool load_checkpoint();
+    std::string output_directory;
+    std::unique_ptr<io::PVDWriter> pvd_writer;
+
     Context &ctx;
     Triangulation &triangulation;
     Parameters::AllParameters parameters;
@@ -130,6 +141,8 @@ namespace ifem
     bool dofs_ready = false;
 
   protected:
+    void io_before_step(); // output of step 0
+    void io_after_step();  // output / checkpoint when due
     void precondition(const double *src, double *dst);
     DevBuf<double> d_binv, d_con_vals, d_tmp_p, d_utmp, d_utmp2;
     int64_t n_dofs_global = 0, n_p_global = 0;

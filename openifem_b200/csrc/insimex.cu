@@ -99,6 +99,7 @@ namespace ifem
 
   void InsIMEX::run_one_step(bool apply_nonzero_constraints, bool assemble_system)
   {
+    io_before_step();
     time.increment();
     if (verbose && fs.rank == 0)
       std::printf("%s\nTime step = %u, at t = %e\n", std::string(96, '*').c_str(), time.get_timestep(), time.current());
@@ -120,10 +121,12 @@ namespace ifem
       std::printf(" GMRES_ITR = %-3u GMRES_RES = %e  [cg_mp %d cg_sm %d cg_a %d / %d]\n", state.first, state.second, cur.cg_mp_its,
                   cur.cg_sm_its, cur.a_inv_its, cur.precond_applies);
     update_stress(); // :425
+    io_after_step();
   }
 
   void InsIMEX::run()
   {
+    const bool success_load = load_checkpoint(); // :455; false unless an output directory is set
     if (!dofs_ready)
       {
         triangulation.refine_global(parameters.global_refinements.empty() ? 0 : parameters.global_refinements[0]);
@@ -133,6 +136,6 @@ namespace ifem
       }
     // nonzero constraints at the very first time step only; the left-hand side is assembled twice: once with the
     // nonzero, once with the zero constraints (:471-479)
-    while (time.end() - time.current() > 1e-12) run_one_step(time.get_timestep() == 0, time.get_timestep() < 2);
+    while (time.end() - time.current() > 1e-12) run_one_step(time.get_timestep() == 0, time.get_timestep() < 2 || success_load);
   }
 } // namespace ifem

@@ -642,6 +642,7 @@ namespace ifem
 
   void SCnsIM::run_one_step(bool apply_nonzero_constraints, bool /*assemble_system*/)
   {
+    io_before_step();
     time.increment();
     if (verbose && fs.rank == 0)
       std::printf("%s\nTime step = %u, at t = %e\n", std::string(96, '*').c_str(), time.get_timestep(), time.current());
@@ -679,6 +680,7 @@ namespace ifem
     lin3(ctx, n, solution_increment.p, present_solution.p, -1.0, evaluation_point.p, 0.0, evaluation_point.p);
     copy(ctx, n, evaluation_point.p, present_solution.p);
     update_stress(); // :417
+    io_after_step();
   }
 
   // SUPGFluidSolver::run (mpi_supg_solver.cpp:427-486). With hard-coded boundary values the clock of the boundary
@@ -688,6 +690,7 @@ namespace ifem
   void SCnsIM::run()
   {
     const bool time_dependent = !hard_coded.empty();
+    const bool success_load = load_checkpoint(); // :433; false unless an output directory is set
     if (!dofs_ready)
       {
         if (time_dependent) bc_time += time.get_delta_t();
@@ -696,7 +699,7 @@ namespace ifem
         make_constraints();
         initialize_system();
       }
-    run_one_step(true);
+    if (!success_load) run_one_step(true);
     while (time.end() - time.current() > 1e-12)
       {
         if (time_dependent)

@@ -731,13 +731,17 @@ namespace ifem
 
   void SolidSolver::run()
   {
+    if (!dofs_ready) triangulation.refine_global(parameters.global_refinements.size() > 1 ? parameters.global_refinements[1] : 0);
+    const bool success_load = load_checkpoint(); // mpi_solid_solver.cpp:318-319; false unless an output directory is set
     if (!dofs_ready)
       {
-        triangulation.refine_global(parameters.global_refinements.size() > 1 ? parameters.global_refinements[1] : 0);
         setup_dofs();
         initialize_system();
       }
-    run_one_step(true);
+    if (!success_load)
+      run_one_step(true);
+    else
+      after_restart(); // "if we load from previous task, we need to assemble the mass matrix" (mpi_shared_solid_solver.cpp:433-437)
     while (time.end() - time.current() > 1e-12) run_one_step(false);
   }
 
@@ -844,6 +848,7 @@ namespace ifem
 
   void HyperElasticity::run_one_step(bool first_step)
   {
+    io_before_step();
     const VecSpace n(ss.n_dofs);
     const double gamma = 0.5 + parameters.damping, beta = gamma / 2;
     if (first_step)
@@ -893,6 +898,7 @@ namespace ifem
     copy(ctx, n, current_velocity.p, previous_velocity.p);
     copy(ctx, n, current_displacement.p, previous_displacement.p);
     update_strain_and_stress(); // the shared twin used by MPI::FSI does this every step (mpi_shared_hyper_elasticity.cpp:204-205)
+    io_after_step();
   }
 
   // ===========================================================================
@@ -992,6 +998,7 @@ namespace ifem
 
   void LinearElasticity::run_one_step(bool first_step)
   {
+    io_before_step();
     const VecSpace n(ss.n_dofs);
     const double dt = time.get_delta_t();
     double gamma, beta;
@@ -1047,6 +1054,7 @@ namespace ifem
     history.push_back({time.get_timestep(), 0u, lin.second, 0.0, (int)lin.first});
     if (verbose) std::printf(" CG iteration: %u CG residual: %.6e\n", lin.first, lin.second);
     if (shared) update_strain_and_stress();
+    io_after_step();
   }
 
   void LinearElasticity::update_strain_and_stress()

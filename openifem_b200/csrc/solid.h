@@ -12,6 +12,8 @@
 #include "insim.h" // Time
 #include "krylov.h"
 #include "mesh.h"
+#include "output.h"
+#include <memory>
 #include "parameters.h"
 
 namespace ifem
@@ -87,9 +89,21 @@ namespace ifem
       int cg_its;
     };
     std::vector<Record> history;
+    // Result files and checkpoints (solver_io.cu; formats in output.h): off until a directory is set
+    // (mpi_shared_solid_solver.cpp:237-337, 452-571)
+    void set_output_directory(const std::string &dir);
+    void output_results(unsigned int output_index);
+    void save_checkpoint(int output_index);
+    bool load_checkpoint();
+    // what run() does instead of the first step after a successful load: rebuild what later steps reuse
+    virtual void after_restart() { assemble_system(true); }
+    std::string output_directory;
+    std::unique_ptr<io::PVDWriter> pvd_writer;
     std::map<std::string, double> timer_ms;
 
   protected:
+    void io_before_step();
+    void io_after_step();
     double get_error(const double *v);
     // traction / pressure faces, or (FSI) the fluid traction on the deformed faces, added to ss.rhs
     void neumann_rhs();
@@ -104,6 +118,11 @@ namespace ifem
     void run_one_step(bool first_step) override;
     void initialize_system() override;
     void update_qph(const double *u_dev);
+    void after_restart() override
+    {
+      update_qph(current_displacement.p); // the point history follows the loaded displacement
+      assemble_system(true);
+    }
     void assemble_system(bool initial_step) override;
     // SharedHyperElasticity::update_strain_and_stress (source/mpi_shared_hyper_elasticity.cpp:599-714): Cauchy stress
     // tau / J and deformation gradient F at the quadrature points, projected to the nodes and averaged
@@ -123,6 +142,12 @@ namespace ifem
     void assemble_system(bool is_initial) override;
     // mpi_shared_linear_elasticity.cpp:401-531: sym grad u and C : sym grad u at the quadrature points -> nodes, averaged
     void update_strain_and_stress() override;
+
+    void after_restart() override
+    {
+      assemble_system(true);
+      if (!shared) assemble_system(false); // system = M + beta dt^2 K and K (mpi_linear_elasticity.cpp:207-214)
+    }
 
     const bool shared;
     // system_matrix = ss.K, mass_matrix = ss.M (shared twin only)

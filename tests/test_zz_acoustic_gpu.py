@@ -6,7 +6,7 @@ applies the nonzero constraints in every step. Cases: the reference's acoustic_d
 STATUS: written after the round's GPU budget was spent: SCnsIM::run is new host-side code around device paths that are
 verified (make_constraints / upload, run_one_step); not run on a B200 yet. The file sorts after the verified suites.
 
-Tolerances: fields after 100 steps 1e-5 relative (200 FGMRES solves to the reference's 1e-6 |rhs| on the device, sparse direct
+Tolerances: fields after 100 steps 1e-5 relative (200 FGMRES solves, tightened to 1e-10 |rhs| on the device, sparse direct
 in the oracle); goldens as in the reference's drivers (5.93 +- 1e-3; |v| < 5e-2)."""
 import os
 
@@ -36,6 +36,7 @@ def _flow(case, n_steps=None):
 def test_acoustic_100_steps_match_oracle(golden_dir, case):
     z = np.load(os.path.join(golden_dir, "scns_acoustic_oracle.npz"))
     flow = _flow(case, n_steps=100)
+    flow.set_control(fgmres_rel=1e-10)  # parity run: linear solves tightened as in tests/test_scns_gpu.py
     flow.run()  # refines 3 times, then 100 steps with the constraints re-made every step
     sol = flow.get_current_solution()
     ref = z[case + "_solution_100"]

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -170,16 +171,46 @@ namespace Parameters
   };
 } // namespace Parameters
 
+// PETScWrappers::MPI::Vector as the drivers use one block of a solution: size, element access, norms, and the copy into a
+// serial dealii::Vector<double> (= std::vector here; tests/fluid_pressure_driven_mpi_insim_supg/...cpp:41-46, fluid_plane_wall_driven...cpp:45-47)
+namespace PETScWrappers
+{
+  namespace MPI
+  {
+    class Vector : public std::vector<double>
+    {
+    public:
+      using std::vector<double>::vector;
+      Vector() = default;
+      Vector(std::vector<double> v) : std::vector<double>(std::move(v)) {}
+      double l2_norm() const
+      {
+        double s = 0;
+        for (double x : *this) s += x * x;
+        return std::sqrt(s);
+      }
+      double linfty_norm() const
+      {
+        double s = 0;
+        for (double x : *this) s = std::max(s, std::abs(x));
+        return s;
+      }
+      double max() const { return *std::max_element(begin(), end()); }
+      double min() const { return *std::min_element(begin(), end()); }
+    };
+  } // namespace MPI
+} // namespace PETScWrappers
+
 // PETScWrappers::MPI::BlockVector as returned by get_current_solution(): block(0) velocity, block(1) pressure
 class BlockVector
 {
 public:
-  BlockVector(std::vector<double> u, std::vector<double> p) : b{std::move(u), std::move(p)} {}
-  const std::vector<double> &block(unsigned i) const { return b[i]; }
+  BlockVector(std::vector<double> u, std::vector<double> p) : b{PETScWrappers::MPI::Vector(std::move(u)), PETScWrappers::MPI::Vector(std::move(p))} {}
+  const PETScWrappers::MPI::Vector &block(unsigned i) const { return b[i]; }
   unsigned n_blocks() const { return 2; }
 
 private:
-  std::vector<double> b[2];
+  PETScWrappers::MPI::Vector b[2];
 };
 
 namespace Utils

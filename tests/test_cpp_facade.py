@@ -68,3 +68,19 @@ def test_cpp_contact_driver_compiles_and_fails_loudly_without_gpu(golden_dir):
     exe = os.path.join(ROOT, "tests", "cpp", "_build", "fsi_contact_model_mpi")
     r = subprocess.run([exe, os.path.join(golden_dir, "fsi_contact_model_2d.prm")], capture_output=True, text=True)
     assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.parametrize("name,args", [("fluid_cylinder_mpi_insimex", ["ins_cylinder_2d.prm"]),
+                                       ("fluid_supg_insim_mpi", ["wall", "supg_ins_plane_wall_driven_2d.prm"])])
+def test_cpp_new_solver_drivers_compile_and_fail_loudly_without_gpu(golden_dir, name, args):
+    """Fluid::MPI::InsIMEX / SUPGInsIM through the facade (PETScWrappers::MPI::Vector::l2_norm, the serial Vector copy the
+    drivers sort): the host side compiles and runs; the solver construction needs the device"""
+    _build(name)
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", name)
+    argv = [a if not a.endswith(".prm") else os.path.join(golden_dir, a) for a in args]
+    r = subprocess.run([exe] + argv, capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr

@@ -113,3 +113,17 @@ def test_insimex_cylinder_reference_golden(golden_dir):
     assert abs(pmax - 46.5308) / 46.5308 < 1e-3, pmax
     # the oracle's values (tests/test_oracle_goldens.py): 0.3740616, 46.530832
     assert abs(vmax - 0.37406163) < 1e-5 and abs(pmax - 46.530832) < 1e-3, (vmax, pmax)
+
+
+def test_cpp_insimex_driver_reference_golden(golden_dir):
+    """the reference-style C++ driver (tests/cpp/fluid_cylinder_mpi_insimex.cpp) against the facade"""
+    import subprocess
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_cpp_facade import ROOT, _build
+
+    _build("fluid_cylinder_mpi_insimex")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "fluid_cylinder_mpi_insimex")
+    r = subprocess.run([exe, os.path.join(golden_dir, "ins_cylinder_2d.prm")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout

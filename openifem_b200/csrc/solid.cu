@@ -1,5 +1,6 @@
 #include "solid.h"
 
+#include "hyper_materials.cuh"
 #include "solid_linear.cuh"
 
 #include <algorithm>
@@ -104,7 +105,7 @@ namespace ifem
 
     template <int DIM, int NPC>
     __global__ void update_qph_kernel(int n_cells, int nq, const int *__restrict__ cell_nodes, const double *__restrict__ G,
-                                      const double *__restrict__ u, double c1, double kappa, double *__restrict__ Finv,
+                                      const double *__restrict__ u, int material, double c1, double kappa, double *__restrict__ Finv,
                                       double *__restrict__ tau, double *__restrict__ Jc, double *__restrict__ detF)
     {
       constexpr int NS = Voigt<DIM>::N;
@@ -127,7 +128,10 @@ namespace ifem
             }
         }
       double fi[DIM * DIM], ta[DIM * DIM], jc[NS * NS], dj;
-      neo_hookean_point<DIM>(gu, c1, kappa, fi, ta, jc, dj);
+      if (material == 0)
+        neo_hookean_point<DIM>(gu, c1, kappa, fi, ta, jc, dj);
+      else
+        kirchhoff_point<DIM>(gu, c1, kappa, fi, ta, jc, dj); // (c1, kappa) carry (Young's modulus, Poisson's ratio)
 #pragma unroll
       for (int i = 0; i < DIM * DIM; ++i)
         {
@@ -751,8 +755,15 @@ namespace ifem
   HyperElasticity::HyperElasticity(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params)
     : SolidSolver(ctx_, tria, params)
   {
-    if (parameters.solid_type != "NeoHookean") throw std::runtime_error("HyperElasticity: only the NeoHookean material is implemented on the device");
-    if (parameters.C.empty() || parameters.C[0].size() < 2) throw std::runtime_error("HyperElasticity: NeoHookean requires C1, kappa");
+    // PointHistory::setup (mpi_hyper_elasticity.cpp:8-35): NeoHookean or Kirchhoff
+    if (parameters.solid_type == "Kirchhoff")
+      {
+        if (parameters.E.empty() || parameters.nu.empty()) throw std::runtime_error("HyperElasticity: Kirchhoff requires Young's modulus and Poisson's ratio");
+      }
+    else if (parameters.solid_type != "NeoHookean")
+      throw std::runtime_error("HyperElasticity: Solid type must be NeoHookean or Kirchhoff");
+    else if (parameters.C.empty() || parameters.C[0].size() < 2)
+      throw std::runtime_error("HyperElasticity: NeoHookean requires C1, kappa");
   }
 
   void HyperElasticity::initialize_system()
@@ -767,13 +778,16 @@ namespace ifem
   {
     ScopedTimer t(ctx, timer_ms["Update QPH data"]);
     const int total = ss.n_cells * ss.nq;
-    const double c1 = parameters.C[0][0], kappa = parameters.C[0][1];
+    // NeoHookean: (C1, kappa) of "Hyperelastic parameters"; Kirchhoff: (Young's modulus, Poisson's ratio) (mpi_hyper_elasticity.cpp:13-27)
+    const bool kirchhoff = parameters.solid_type == "Kirchhoff";
+    const int material = kirchhoff ? 1 : 0;
+    const double c1 = kirchhoff ? parameters.E[0] : parameters.C[0][0], kappa = kirchhoff ? parameters.nu[0] : parameters.C[0][1];
     if (ss.dim == 2)
-      update_qph_kernel<2, 4><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, c1, kappa,
-                                                                           ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
+      update_qph_kernel<2, 4><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, material, c1,
+                                                                           kappa, ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
     else
-      update_qph_kernel<3, 8><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, c1, kappa,
-                                                                           ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
+      update_qph_kernel<3, 8><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, material, c1,
+                                                                           kappa, ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
   }

@@ -53,6 +53,23 @@ def neo_hookean_update(grad_u, c1, kappa):
     return F_inv, tau, Jc_iso + Jc_vol, J
 
 
+def kirchhoff_update(grad_u, young, poisson):
+    """PointHistory::update for solid_type = Kirchhoff (mpi_hyper_elasticity.cpp:50-58, include/kirchhoff_elastic_material.h:
+    36-76): E = (F^T F - I) / 2, S = lambda tr(E) I + 2 mu E, tau = F S F^T; Jc = lambda IxI + 2 mu S4 (constant)."""
+    dim = grad_u.shape[-1]
+    I, IxI, S4, _ = standard_tensors(dim)
+    lam = young * poisson / ((1 + poisson) * (1 - 2 * poisson))
+    mu = young / (2 * (1 + poisson))
+    F = I + grad_u
+    J = np.linalg.det(F)
+    F_inv = np.linalg.inv(F)
+    E = 0.5 * (np.einsum("...ki,...kj->...ij", F, F) - I)
+    pk2 = lam * np.einsum("...ii->...", E)[..., None, None] * I + 2 * mu * E
+    tau = np.einsum("...ik,...kl,...jl->...ij", F, pk2, F)
+    Jc = np.broadcast_to(lam * IxI + 2 * mu * S4, grad_u.shape[:-2] + (dim,) * 4).copy()
+    return F_inv, tau, Jc, J
+
+
 class SolidDofs:
     def __init__(self, mesh: fem.BoxMesh, degree: int):
         self.mesh, self.dim = mesh, mesh.dim
@@ -209,8 +226,12 @@ class SolidBase:
 class HyperElasticity(SolidBase):
     def __init__(self, mesh: fem.BoxMesh, params, verbose=False):
         super().__init__(mesh, params, verbose)
-        c = params.C[0]
-        self.c1, self.kappa = c[0], c[1]
+        self.kirchhoff = params.solid_type == "Kirchhoff"  # PointHistory::setup (mpi_hyper_elasticity.cpp:8-35)
+        if self.kirchhoff:
+            self.young, self.poisson = params.E[0], params.nu[0]
+        else:
+            c = params.C[0]
+            self.c1, self.kappa = c[0], c[1]
         self.update_qph(self.cur_u)
 
     # -- update_qph (:241-275) ------------------------------------------------
@@ -218,7 +239,10 @@ class HyperElasticity(SolidBase):
         dim = self.dim
         ue = u[self.dofs.cell_dofs].reshape(self.mesh.n_cells, self.npc, dim)  # [c][a][comp]
         grad_u = np.einsum("cai,cqak->cqik", ue, self.G)
-        self.F_inv, self.tau, self.Jc, self.detF = neo_hookean_update(grad_u, self.c1, self.kappa)
+        if self.kirchhoff:
+            self.F_inv, self.tau, self.Jc, self.detF = kirchhoff_update(grad_u, self.young, self.poisson)
+        else:
+            self.F_inv, self.tau, self.Jc, self.detF = neo_hookean_update(grad_u, self.c1, self.kappa)
 
     # -- SharedHyperElasticity::update_strain_and_stress (mpi_shared_hyper_elasticity.cpp:599-714) ------------
     def update_strain_and_stress(self):

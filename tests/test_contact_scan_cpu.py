@@ -72,7 +72,7 @@ def test_contact_scan_matches_oracle_on_a_tilted_solid(harness, dim):
     import sys
 
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    import test_zz_linear_elasticity_gpu as T
+    import test_linear_elasticity_gpu as T
     from oracle import fem, fsi, prm, solid
 
     reps, hi = ((5, 4), (1.0, 1.0)) if dim == 2 else ((3, 2, 3), (1.0, 0.8, 1.0))

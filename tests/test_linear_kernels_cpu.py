@@ -26,7 +26,7 @@ def harness():
 
 
 def _prm_text(dim, dirichlet=True):
-    import test_zz_linear_elasticity_gpu as T
+    import test_linear_elasticity_gpu as T
 
     text = T._prm(dim).replace("Number of Neumann BCs = 1", "Number of Neumann BCs = 0")
     return text if dirichlet else text.replace("Number of Dirichlet BCs = 1", "Number of Dirichlet BCs = 0")

@@ -82,7 +82,7 @@ def test_fluid_output_and_restart(tmp_path, dim):
 
 def test_solid_output_and_restart(tmp_path):
     import openifem_b200 as ifem
-    import test_zz_linear_elasticity_gpu as T
+    import test_linear_elasticity_gpu as T
 
     def make(n_steps, directory):
         text = T._prm(2).replace("set End time = 1.0", "set End time = %g" % (0.05 * n_steps)).replace(

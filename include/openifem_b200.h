@@ -114,6 +114,8 @@ int ifem_insim_destroy(ifem_insim *s);
 typedef double (*ifem_bc_fn)(const double *point, unsigned int component, double time, void *user);
 int ifem_insim_add_hard_coded_boundary_condition(ifem_insim *s, int boundary_id, ifem_bc_fn f, void *user);
 int ifem_insim_default_control(int serial_twin, ifem_ins_control *out);
+/* the tolerances the solver currently runs with (each solver class starts from the reference's values for that class) */
+int ifem_insim_get_control(const ifem_insim *s, ifem_ins_control *out);
 int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c);
 int ifem_insim_set_verbose(ifem_insim *s, int verbose);
 /* setup_dofs(); make_constraints(); initialize_system();  (mpi_insim.cpp:504-506) - no refinement */

@@ -276,8 +276,12 @@ class _InsIM:
         return pts
 
     def set_control(self, serial_twin=False, **kw):
+        """change some tolerances; the others keep the solver's current values (serial_twin: start from the serial InsIM's)"""
         c = InsControl()
-        check(lib().ifem_insim_default_control(C.c_int(1 if serial_twin else 0), C.byref(c)))
+        if serial_twin:
+            check(lib().ifem_insim_default_control(C.c_int(1), C.byref(c)))
+        else:
+            check(lib().ifem_insim_get_control(self._h, C.byref(c)))
         for k, v in kw.items():
             if not hasattr(c, k):
                 raise KeyError(k)

@@ -367,6 +367,22 @@ int ifem_insim_default_control(int serial_twin, ifem_ins_control *out)
     out->cg_sm_fp32 = c.cg_sm_fp32;
   });
 }
+int ifem_insim_get_control(const ifem_insim *s, ifem_ins_control *out)
+{
+  return guard([&] {
+    const InsSolverControl &c = s->s->control;
+    out->fgmres_rel = c.fgmres_rel;
+    out->fgmres_floor = c.fgmres_floor;
+    out->cg_mp_rel = c.cg_mp_rel;
+    out->cg_sm_rel = c.cg_sm_rel;
+    out->cg_floor = c.cg_floor;
+    out->a_inv_rel = c.a_inv_rel;
+    out->a_inv_max_it = c.a_inv_max_it;
+    out->basis_size = c.basis_size;
+    out->a_inv_fp32 = c.a_inv_fp32;
+    out->cg_sm_fp32 = c.cg_sm_fp32;
+  });
+}
 int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
 {
   return guard([&] {

@@ -436,6 +436,7 @@ namespace ifem
   {
     if (parameters.fluid_velocity_degree != 1 || parameters.fluid_pressure_degree != 1)
       throw std::runtime_error("SCnsIM: only equal-order Q1/Q1 elements are implemented on the device");
+    control.fgmres_rel = 1e-6; // SUPGFluidSolver::solve: SolverControl(m, 1e-6 * |rhs|) (mpi_supg_solver.cpp:311-312)
   }
 
   void SCnsIM::setup_dofs()

@@ -49,6 +49,9 @@ def test_acoustic_100_steps_match_oracle(golden_dir, case):
 def test_acoustic_duct_wave_reference_golden():
     """tests/acoustic_duct_wave_mpi/acoustic_duct_wave_mpi.cpp:60-68: max velocity 5.93 +- 1e-3 after 1000 steps"""
     flow = _flow("duct")
+    # the converged value (oracle: 5.93536) sits 9e-4 from the rounded golden, i.e. 1e-4 inside its tolerance: the linear solves
+    # are tightened from the reference's 1e-6 |rhs| so that solver noise over 1000 steps cannot decide the assertion
+    flow.set_control(fgmres_rel=1e-8)
     flow.run()
     vmax = flow.get_current_solution()[: flow.n_u].max()
     assert abs(vmax - 5.93) / 5.93 < 1e-3, vmax

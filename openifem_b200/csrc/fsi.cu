@@ -1012,6 +1012,7 @@ namespace ifem
   void FsiCoupling::run_one_step(bool first_step)
   {
     find_solid_bc();
+    if (restarted) solid.after_restart(); // "solid_solver.assemble_system(true)" in every pass after a restart (:1176-1179)
     {
       ScopedTimer t(ctx, timer_ms["Run solid solver"]);
       if (penetration_criterion)
@@ -1034,6 +1035,11 @@ namespace ifem
       fluid.run_one_step(true);
     }
     time.increment();
+    if (time.time_to_save() && !solid.output_directory.empty() && !fluid.output_directory.empty()) // :1219-1223
+      {
+        solid.save_checkpoint((int)time.get_timestep());
+        fluid.save_checkpoint((int)time.get_timestep());
+      }
   }
 
   void FsiCoupling::set_penetration_criterion(std::function<double(const double *)> criterion, const double *direction)
@@ -1084,7 +1090,16 @@ namespace ifem
 
   void FsiCoupling::run()
   {
-    bool first_step = true;
+    // restart (:1127-1151): when both solvers write into output directories and have not stepped yet, their latest
+    // checkpoints are restored and the coupling clock catches up
+    if (!solid.output_directory.empty() && !fluid.output_directory.empty() && solid.time.get_timestep() == 0 && fluid.time.get_timestep() == 0)
+      {
+        restarted = solid.load_checkpoint() && fluid.load_checkpoint();
+        if (solid.time.current() != fluid.time.current())
+          throw std::runtime_error("Solid and fluid restart files have different time steps. Check and remove inconsistent restart files!");
+        while (time.get_timestep() < solid.time.get_timestep()) time.increment();
+      }
+    bool first_step = !restarted;
     while (time.end() - time.current() > 1e-12)
       {
         run_one_step(first_step);

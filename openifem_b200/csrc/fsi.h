@@ -42,6 +42,7 @@ namespace ifem
     void set_penetration_criterion(std::function<double(const double *)> criterion, const double *direction);
     void apply_contact_model(bool first_step);
     int contact_iterations = 0; // solid steps taken inside apply_contact_model so far
+    bool restarted = false;     // run() restored both solvers from checkpoints (mpi_fsi.cpp:1127-1151)
 
     // batch queries on the current deformed solid (tests / diagnostics)
     void point_in_solid(int n, const double *pts_host, int *inside_host);

@@ -329,6 +329,9 @@ namespace ifem
         make_constraints();
         initialize_system();
       }
+    // Deviation: the reference calls run_one_step(true) here even after a successful load (mpi_insim.cpp:511), which adds the
+    // inhomogeneous boundary values to a solution that already carries them; SUPGFluidSolver::run (mpi_supg_solver.cpp:456-463)
+    // skips it after a restart, and so do we for every fluid solver
     if (!success_load) run_one_step(true);
     while (time.end() - time.current() > 1e-12) run_one_step(false);
   }

@@ -2,9 +2,9 @@
 (oracle/ins.py InsIMEX + oracle/csrc/oracle_insimex.cpp, pinned on the reference golden fluid_cylinder_mpi_insimex), and
 that golden through the device path.
 
-STATUS: written after the round's GPU budget was spent. The oracle side is pinned on the golden on the CPU; the device
-side reuses the verified INS cell kernel with two new switches (explicit_convection, rhs_only) and compiles for sm_100a,
-but has not run on a B200 yet. The file sorts after the verified suites.
+STATUS: written after the round's GPU budget was spent. The oracle side is pinned on the golden on the CPU; the assembly and
+time-step tests pass on the emulated device (tests/cpu_emul, DESIGN 2b: the product's kernels and host code run on the CPU
+under a SIMT emulator); nothing here has run on a B200 yet. The file sorts after the verified suites.
 
 Tolerances: assembled matrices / rhs 1e-12 relative; fields after time steps 1e-6 (FGMRES runs to min(1e-9, 1e-8 |rhs|) on
 both sides, the inner CG tolerances only shape the preconditioner); golden 1e-3 as in the reference's driver."""

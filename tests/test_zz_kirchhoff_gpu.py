@@ -4,8 +4,8 @@ The reference has no golden for this material (tests/solid_rotation_mpi_shared_K
 pin, with the momentum property of that case as a physical check (tests/test_hyper_materials_cpu.py).
 
 STATUS: written after the round's GPU budget was spent. The material point function is checked on the CPU against the oracle
-to 1e-14 (same source compiled with g++); everything around it is the verified NeoHookean path. Not run on a B200 yet; the
-file sorts after the verified suites.
+to 1e-14 and both tests pass on the emulated device (tests/cpu_emul); not run on a B200 yet. The file sorts
+after the verified suites.
 
 Tolerances: point history and assembled matrices 1e-12 relative; displacement after time steps 1e-6 (CG to 1e-8 |b| on the
 device, sparse direct in the oracle)."""

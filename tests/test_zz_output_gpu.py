@@ -2,8 +2,8 @@
 on the CPU in tests/test_output_cpu.py): FluidSolver::output_results / save_checkpoint / load_checkpoint (reference
 source/mpi_fluid_solver.cpp:491-713) and the solid's (source/mpi_shared_solid_solver.cpp:237-337, 452-571).
 
-STATUS: written after the round's GPU budget was spent; host-side file code verified on the CPU, the solver glue (download of
-the device state, restart inside run()) not run on a B200 yet. The file sorts after the verified suites.
+STATUS: written after the round's GPU budget was spent; host-side file code verified on the CPU, all three tests pass on the
+emulated device (tests/cpu_emul); not run on a B200 yet. The file sorts after the verified suites.
 
 Properties: the written velocity / pressure equal get_current_solution() at the vertices; a run restarted from the latest
 checkpoint continues to the same fields as an uninterrupted run (1e-9: a time step depends on present_solution only)."""

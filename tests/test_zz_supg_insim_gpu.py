@@ -2,10 +2,9 @@
 (oracle/scns.py SUPGInsIM + oracle/csrc/oracle_insim_supg.cpp, pinned on the reference goldens
 fluid_pressure_driven_mpi_insim_supg and fluid_plane_wall_driven_mpi_insim_supg), and both goldens through the device path.
 
-STATUS: written after the round's GPU budget was spent. The kernel bodies (openifem_b200/csrc/insim_supg.cuh) are checked
-on the CPU against the oracle to 1e-13 (tests/test_supg_kernels_cpu.py, same source compiled with g++); the launch and the
-solver around it (SCnsIM's verified SUPGFluidSolver machinery) have not run on a B200 yet. The file sorts after the verified
-suites.
+STATUS: written after the round's GPU budget was spent. The kernel bodies are checked on the CPU against the oracle to 1e-13
+(tests/test_supg_kernels_cpu.py) and the assembly / time-step tests pass on the emulated device (tests/cpu_emul, DESIGN 2b);
+nothing here has run on a B200 yet. The file sorts after the verified suites.
 
 Tolerances: assembled matrix / rhs 1e-12 relative; fields after time steps 1e-5 (FGMRES tightened to 1e-10 |rhs| on the device,
 sparse direct in the oracle); goldens as in the reference's drivers."""

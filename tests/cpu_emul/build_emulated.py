@@ -178,7 +178,8 @@ def build(force=False):
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, units))
-    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + ["-fopenmp", "-ldl"])
+    subprocess.check_call(["g++", "-shared", "-o", LIB + ".tmp"] + objs + ["-fopenmp", "-ldl"])
+    os.replace(LIB + ".tmp", LIB)  # a process that has the old file mapped keeps it
     return LIB
 
 

@@ -9,8 +9,65 @@
 
 #include <vector>
 
+#include <map>
+
 namespace cpu_emul
 {
+  namespace
+  {
+    constexpr size_t kZone = 256;
+    constexpr unsigned char kPattern = 0xA5;
+    struct Live
+    {
+      std::map<char *, size_t> m;
+      static void check(char *user, size_t n, const char *when)
+      {
+        for (size_t i = 0; i < kZone; ++i)
+          if ((unsigned char)user[-(long)kZone + (long)i] != kPattern || (unsigned char)user[n + i] != kPattern)
+            {
+              std::fprintf(stderr, "cpu_emul: RED ZONE of a %zu-byte device buffer overwritten (%s the buffer, offset %zu; found at %s)\n", n,
+                           (unsigned char)user[n + i] != kPattern ? "after" : "before", i, when);
+              std::abort();
+            }
+      }
+      ~Live()
+      {
+        for (auto &kv : m) check(kv.first, kv.second, "process exit");
+      }
+    };
+    Live &live()
+    {
+      static Live l;
+      return l;
+    }
+  } // namespace
+
+  void *guarded_alloc(size_t n)
+  {
+    const size_t padded = (n + 63) / 64 * 64;
+    char *raw = (char *)std::aligned_alloc(64, padded + 2 * kZone);
+    if (!raw) return nullptr;
+    std::memset(raw, kPattern, padded + 2 * kZone);
+    char *user = raw + kZone;
+    live().m[user] = n;
+    return user;
+  }
+
+  void guarded_free(void *p)
+  {
+    if (!p) return;
+    char *user = (char *)p;
+    auto it = live().m.find(user);
+    if (it == live().m.end())
+      {
+        std::fprintf(stderr, "cpu_emul: cudaFree of a pointer cudaMalloc did not return\n");
+        std::abort();
+      }
+    Live::check(user, it->second, "cudaFree");
+    live().m.erase(it);
+    std::free(user - kZone);
+  }
+
   Idx g_tid{0, 0, 0}, g_bid{0, 0, 0};
   dim3 g_block, g_grid;
   long long g_launches = 0, g_fiber_launches = 0;

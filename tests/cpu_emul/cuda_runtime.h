@@ -92,8 +92,15 @@ inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->multiProcessorCount = 4; std::strcpy(p->name, "cpu_emul"); p->totalGlobalMem = 1ull << 34; return cudaSuccess; }
-template <typename T> inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)std::aligned_alloc(64, (n + 63) / 64 * 64 + 64); return *p ? cudaSuccess : 2; }
-inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
+// "device" allocations carry 256-byte red zones on both sides, filled with a pattern that cudaFree and a process-exit hook
+// verify: a kernel that writes just outside a buffer is reported with the size of the buffer (a poor man's memcheck)
+namespace cpu_emul
+{
+  void *guarded_alloc(size_t n);
+  void guarded_free(void *p);
+} // namespace cpu_emul
+template <typename T> inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)cpu_emul::guarded_alloc(n); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void *p) { cpu_emul::guarded_free(p); return cudaSuccess; }
 template <typename T> inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)std::malloc(n ? n : 1); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }

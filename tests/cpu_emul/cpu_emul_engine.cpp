@@ -161,6 +161,30 @@ namespace cpu_emul
 
     void yield_to_scheduler() { cpu_emul_switch(&E.fibers[E.cur].sp, E.main_sp); }
 
+    // IFEM_EMUL_SHUFFLE=<seed>: threads of a block (and the blocks of a launch) run in a pseudo-random order instead of
+    // 0, 1, 2, ... - code that only works because a producer lane happens to run before its consumer (a missing barrier)
+    // then gives different results. A sequential schedule still cannot show lost updates of unsynchronised read-modify-writes.
+    uint64_t shuffle_seed()
+    {
+      static const uint64_t s = [] {
+        const char *e = std::getenv("IFEM_EMUL_SHUFFLE");
+        return e ? (uint64_t)std::strtoull(e, nullptr, 10) : 0ull;
+      }();
+      return s;
+    }
+    uint64_t g_rng = 0x9E3779B97F4A7C15ull;
+    void shuffle(int *a, int n)
+    {
+      for (int i = n - 1; i > 0; --i)
+        {
+          g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull + shuffle_seed();
+          const int j = (int)((g_rng >> 33) % (uint64_t)(i + 1));
+          const int t = a[i];
+          a[i] = a[j];
+          a[j] = t;
+        }
+    }
+
     void run_block_fibers(unsigned n)
     {
       if (n > (unsigned)kMaxThreads) die("block larger than 1024 threads");
@@ -187,11 +211,15 @@ namespace cpu_emul
           E.fibers[i].sp = sp;
           E.fibers[i].state = READY;
         }
+      std::vector<int> order(E.n);
+      for (int i = 0; i < E.n; ++i) order[i] = i;
       while (E.alive > 0)
         {
           bool progressed = false;
-          for (int i = 0; i < E.n; ++i)
+          if (shuffle_seed()) shuffle(order.data(), E.n); // a different thread order in every pass (IFEM_EMUL_SHUFFLE)
+          for (int k = 0; k < E.n; ++k)
             {
+              const int i = order[k];
               if (E.fibers[i].state != READY) continue;
               progressed = true;
               E.cur = i;
@@ -256,17 +284,24 @@ namespace cpu_emul
     E.body = &body;
     E.fiber_mode = uses_barriers;
     if (E.smem.size() < dyn_smem_bytes + 64) E.smem.resize(dyn_smem_bytes + 64);
-    for (unsigned b = 0; b < grid.x; ++b)
+    std::vector<int> blocks(grid.x), threads(block.x);
+    for (unsigned b = 0; b < grid.x; ++b) blocks[b] = (int)b;
+    for (unsigned t = 0; t < block.x; ++t) threads[t] = (int)t;
+    if (shuffle_seed()) shuffle(blocks.data(), (int)grid.x);
+    for (unsigned bi = 0; bi < grid.x; ++bi)
       {
-        g_bid = Idx{b, 0, 0};
+        g_bid = Idx{(unsigned)blocks[bi], 0, 0};
         if (uses_barriers)
           run_block_fibers(block.x);
         else
-          for (unsigned t = 0; t < block.x; ++t)
-            {
-              g_tid = Idx{t, 0, 0};
-              body();
-            }
+          {
+            if (shuffle_seed()) shuffle(threads.data(), (int)block.x);
+            for (unsigned t = 0; t < block.x; ++t)
+              {
+                g_tid = Idx{(unsigned)threads[t], 0, 0};
+                body();
+              }
+          }
       }
     E.body = nullptr;
     E.fiber_mode = false;

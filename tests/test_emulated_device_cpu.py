@@ -35,10 +35,24 @@ def emulated_library():
     return build_emulated.build()
 
 
+def _replay(path, expr, env=None):
+    return subprocess.run([sys.executable, RUNNER, os.path.join(ROOT, path), "-q", "-x", "-m", "gpu", "-k", expr, "-p", "no:cacheprovider"],
+                          capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, **(env or {})))
+
+
 @pytest.mark.parametrize("path,expr", SELECTION)
 def test_gpu_parity_tests_pass_on_the_emulated_device(emulated_library, path, expr):
-    r = subprocess.run([sys.executable, RUNNER, os.path.join(ROOT, path), "-q", "-x", "-m", "gpu", "-k", expr, "-p", "no:cacheprovider"],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = _replay(path, expr)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+@pytest.mark.parametrize("path,expr", [SELECTION[0], SELECTION[3], SELECTION[4]])
+def test_results_do_not_depend_on_the_thread_schedule(emulated_library, path, expr):
+    """IFEM_EMUL_SHUFFLE: threads of a block and blocks of a launch run in a pseudo-random order that changes at every
+    barrier pass - a kernel that relies on lane or block order (a missing barrier) would no longer reproduce the oracle"""
+    r = _replay(path, expr, {"IFEM_EMUL_SHUFFLE": "12345"})
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail

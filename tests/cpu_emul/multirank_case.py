@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE - NOT PRODUCT CODE. One rank of a slab-partitioned run on the emulated device (see cuda_runtime.h /
+comm_emul.cpp in this directory): what tests/test_ins_multigpu.py's worker does on a GPU, for any of the fluid solvers.
+    python multirank_case.py <rank> <size> <rendezvous dir> <out.npz> <solver> <dim> <reps...>
+Saves the owned parts of: a block mat-vec of a global vector, the right-hand side of an assembly at a global state, the
+solution after two time steps from rest, and the Newton history."""
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), HERE]
+
+import build_emulated  # noqa: E402
+import openifem_b200._lib as product_loader  # noqa: E402
+
+handle = ctypes.CDLL(build_emulated.build(), mode=ctypes.RTLD_GLOBAL)
+handle.ifem_last_error.restype = ctypes.c_char_p
+product_loader._lib = handle
+
+import openifem_b200 as ifem  # noqa: E402
+from util import cavity_prm  # noqa: E402
+
+
+def main():
+    rank, size, rdv, out, solver, dim = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4], sys.argv[5], int(sys.argv[6])
+    reps = tuple(int(a) for a in sys.argv[7:7 + dim])
+    ifem.init(0)
+    if size > 1:
+        idfile = os.path.join(rdv, "unique_id")
+        if rank == 0:
+            with open(idfile + ".tmp", "wb") as f:
+                f.write(ifem.comm_unique_id())
+            os.replace(idfile + ".tmp", idfile)
+        else:
+            while not os.path.exists(idfile):
+                time.sleep(0.02)
+        ifem.comm_init(rank, size, open(idfile, "rb").read())
+    tria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
+    q1 = solver in ("SCnsIM", "SUPGInsIM")
+    if solver == "SCnsIM":
+        from test_scns_gpu import scns_prm
+
+        text = scns_prm(dim, dt=1e-3)
+    elif solver == "SUPGInsIM":
+        full = 3 if dim == 2 else 7
+        text = cavity_prm(dim, newton_tol=1e-8, dirichlet={2: (full, [0.0] * dim), 3: (full, [0.5] + [0.0] * (dim - 1))}, neumann={0: 1.0})
+        text = text.replace("set Velocity degree = 2", "set Velocity degree = 1")
+    else:
+        text = cavity_prm(dim, newton_tol=1e-9)
+    flow = getattr(ifem.Fluid.MPI, solver)(tria, ifem.Parameters.AllParameters(text=text))
+    if solver == "SCnsIM":
+        flow.set_body_force(lambda p, c: 5.0 if c == 0 else 0.0)
+    flow.setup()
+    if solver == "InsIM":
+        flow.set_control(a_inv_rel=1e-10, a_inv_max_it=5000, fgmres_rel=1e-9)
+    elif q1:
+        flow.set_control(fgmres_rel=1e-10)
+    n_un_glob = int(np.prod([(1 if q1 else 2) * k + 1 for k in reps]))
+    n_pn_glob = int(np.prod([k + 1 for k in reps]))
+    n_glob = dim * n_un_glob + n_pn_glob
+    loc, glo = flow.owned_global_dofs(n_un_glob)
+    gu, gp = flow.local_to_global(0).astype(np.int64), flow.local_to_global(1).astype(np.int64)
+    xg = np.sin(0.11 * np.arange(n_glob)) + 0.3
+    ev = 0.1 * np.cos(0.05 * np.arange(n_glob))
+
+    def localise(vg):
+        vu = vg[(gu[:, None] * dim + np.arange(dim)[None, :]).ravel()]
+        return np.concatenate([vu, vg[dim * n_un_glob + gp]])
+
+    flow.set_vector(flow.EVALUATION_POINT, localise(ev))
+    flow.set_vector(flow.PRESENT, localise(0.5 * ev))
+    flow.assemble(True)
+    y = flow.vmult(localise(xg))
+    rhs = flow.get_vector(flow.SYSTEM_RHS)
+    zero = np.zeros(flow.n_dofs)
+    flow.set_vector(flow.EVALUATION_POINT, zero)
+    flow.set_vector(flow.PRESENT, zero)
+    for k in range(2):
+        if solver == "InsIMEX":
+            flow.run_one_step(k == 0, k < 2)
+        else:
+            flow.run_one_step(k == 0)
+    sol = flow.get_current_solution()
+    hist = np.array([(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in flow.history()], dtype=np.float64)
+    np.savez(out, glo=glo, y=y[loc], rhs=rhs[loc], sol=sol[loc], hist=hist, n_u=dim * n_un_glob)
+    if size > 1:
+        ifem.comm_finalize()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,61 @@
+"""Two ranks against one rank on the emulated device (tests/cpu_emul: the product's kernels and host code on the CPU, NCCL
+replaced by a file-based communicator with the same semantics): the slab partition, owner-computes assembly, ghost-layer halo
+exchange and all-reduced Krylov dot products of EVERY fluid solver must reproduce the single-rank run. On GPUs this is
+tests/test_ins_multigpu.py, which covers InsIM only (verified on 2 B200s); SCnsIM, SUPGInsIM and InsIMEX have no multi-GPU
+run yet - this is their first multi-rank check. Test infrastructure: nothing here is a product path.
+
+Tolerances as in tests/test_ins_multigpu.py: block mat-vec and assembled right-hand side 1e-13 relative, fields after two time
+steps 1e-6 (linear solves tightened on both sides), same Newton iteration pattern."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASE = os.path.join(ROOT, "tests", "cpu_emul", "multirank_case.py")
+
+
+def _run(size, solver, dim, reps, tmp_path):
+    rdv = tmp_path / f"rdv_{solver}_{size}"
+    rdv.mkdir()
+    outs = [str(tmp_path / f"{solver}_{size}_{r}.npz") for r in range(size)]
+    procs = [subprocess.Popen([sys.executable, CASE, str(r), str(size), str(rdv), outs[r], solver, str(dim)] + [str(k) for k in reps],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT) for r in range(size)]
+    logs = [p.communicate(timeout=1500)[0] for p in procs]
+    for p, log in zip(procs, logs):
+        assert p.returncode == 0, log[-3000:]
+    res = [np.load(o) for o in outs]
+    n = sum(r["glo"].size for r in res)
+    y, rhs, sol, seen = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n, dtype=int)
+    for r in res:
+        y[r["glo"]], rhs[r["glo"]], sol[r["glo"]] = r["y"], r["rhs"], r["sol"]
+        seen[r["glo"]] += 1
+    assert np.all(seen == 1)  # the owned dofs of the ranks tile the global vector exactly once
+    return y, rhs, sol, res[0]["hist"], int(res[0]["n_u"])
+
+
+@pytest.fixture(scope="module")
+def emulated_library():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_emul"))
+    import build_emulated
+
+    return build_emulated.build()
+
+
+@pytest.mark.parametrize("solver,dim,reps", [("InsIM", 2, (6, 8)), ("SCnsIM", 2, (8, 10)), ("SUPGInsIM", 2, (8, 10)), ("InsIMEX", 2, (6, 8)),
+                                             pytest.param("SCnsIM", 3, (4, 4, 6), marks=pytest.mark.slow)])  # passes; --runslow
+def test_two_ranks_match_one_rank_on_the_emulated_device(emulated_library, solver, dim, reps, tmp_path):
+    y1, rhs1, sol1, h1, nu = _run(1, solver, dim, reps, tmp_path)
+    y2, rhs2, sol2, h2, _ = _run(2, solver, dim, reps, tmp_path)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(y2, y1) < 1e-13
+    assert rel(rhs2, rhs1) < 1e-13
+    assert h1.shape == h2.shape and np.array_equal(h1[:, :2], h2[:, :2])  # same (time step, Newton iteration) pattern
+    assert np.all(np.abs(h2[:, 2] - h1[:, 2]) <= 1e-6 * np.maximum(h1[:, 2], 1e-9))
+    assert rel(sol2[:nu], sol1[:nu]) < 1e-6
+    p2, p1 = sol2[nu:], sol1[nu:]
+    if solver in ("InsIM", "InsIMEX"):  # closed cavity: pressure up to a constant
+        p2, p1 = p2 - p2.mean(), p1 - p1.mean()
+    assert rel(p2, p1) < 1e-6

@@ -80,6 +80,9 @@ namespace ifem
     if ((int64_t)c.present_solution.size() != fs.n_dofs) throw std::runtime_error("load_checkpoint: " + file + " has a different number of dofs");
     present_solution.upload(c.present_solution, ctx.stream);
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+    // the nodal viscous stress is a function of present_solution; the reference leaves it zero until the next step, which
+    // makes the first FSI pass after a restart (find_solid_bc reads it) differ from the uninterrupted run
+    update_stress();
     // set the current time and write a correct .pvd (:689-708); the clock of time-dependent boundary functions follows
     const int stem = std::stoi(std::filesystem::path(file).stem().string());
     for (int i = 0; i <= stem; ++i)

@@ -110,3 +110,40 @@ def test_solid_output_and_restart(tmp_path):
     c = make(6, None)
     c.run()
     assert rel(b.get_current_solution(), c.get_current_solution()) < 1e-9
+
+
+def test_fsi_restart(tmp_path):
+    """FSI::run with checkpoints of both solvers at the save interval and a restart from them (reference source/mpi_fsi.cpp:
+    1127-1151, 1176-1179, 1219-1223): four coupled steps, then a fresh pair of solvers in the same directories continues to step
+    six and must agree with six uninterrupted steps"""
+    import openifem_b200 as ifem
+    from test_fsi_gpu import _fsi_text
+
+    def pair(n_steps, dirs):
+        text = _fsi_text(2).replace("set End time = 1.0", "set End time = %g" % (n_steps * 1e-3)).replace("set Save interval = 1e6", "set Save interval = 2e-3")
+        assert "End time = %g" % (n_steps * 1e-3) in text and "Save interval = 2e-3" in text
+        params = ifem.Parameters.AllParameters(text=text)
+        ftria, stria = ifem.Triangulation(2), ifem.Triangulation(2)
+        ifem.GridGenerator.subdivided_hyper_rectangle(ftria, (12, 12), (0.0, 0.0), (1.0, 1.0), True)
+        ifem.GridGenerator.subdivided_hyper_rectangle(stria, (4, 6), (0.3125, 0.0), (0.5625, 0.6875), True)
+        fluid, solid = ifem.Fluid.MPI.SCnsIM(ftria, params), ifem.Solid.MPI.HyperElasticity(stria, params)
+        fluid.setup()
+        solid.setup()
+        fluid.set_control(fgmres_rel=1e-10)
+        if dirs:
+            fluid.set_output_directory(str(dirs[0]))
+            solid.set_output_directory(str(dirs[1]))
+        return fluid, solid, ifem.MPI.FSI(fluid, solid, params, False)
+
+    dirs = (tmp_path / "fluid", tmp_path / "solid")
+    fluid, solid, fsi = pair(4, dirs)
+    fsi.run()
+    assert "000004.fluid_checkpoint" in os.listdir(dirs[0]) and "000004.solid_checkpoint_displacement" in os.listdir(dirs[1])
+    fluid_b, solid_b, fsi_b = pair(6, dirs)
+    fsi_b.run()
+    assert fluid_b.get_time()[1] == 6 and solid_b.get_time()[1] == 6
+    fluid_c, solid_c, fsi_c = pair(6, None)
+    fsi_c.run()
+    assert np.abs(solid_c.get_current_solution()).max() > 0
+    assert rel(solid_b.get_current_solution(), solid_c.get_current_solution()) < 1e-8
+    assert rel(fluid_b.get_current_solution(), fluid_c.get_current_solution()) < 1e-8

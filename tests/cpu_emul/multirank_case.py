@@ -39,6 +39,8 @@ def main():
             while not os.path.exists(idfile):
                 time.sleep(0.02)
         ifem.comm_init(rank, size, open(idfile, "rb").read())
+    if solver == "FSI":
+        return fsi_case(rank, size, out, dim, reps)
     tria = ifem.Triangulation(dim)
     ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
     q1 = solver in ("SCnsIM", "SUPGInsIM")
@@ -88,6 +90,36 @@ def main():
     sol = flow.get_current_solution()
     hist = np.array([(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in flow.history()], dtype=np.float64)
     np.savez(out, glo=glo, y=y[loc], rhs=rhs[loc], sol=sol[loc], hist=hist, n_u=dim * n_un_glob)
+    if size > 1:
+        ifem.comm_finalize()
+
+
+def fsi_case(rank, size, out, dim, reps):
+    """two passes of the FSI::run loop (tests/test_fsi_gpu.py test_coupled_fsi_steps_match_oracle's problem): partitioned SCnsIM
+    fluid, replicated NeoHookean solid, coupling with the indicator / acceleration variant"""
+    from test_fsi_gpu import _fsi_text
+
+    params = ifem.Parameters.AllParameters(text=_fsi_text(dim))
+    ftria, stria = ifem.Triangulation(dim), ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(ftria, reps, (0.0,) * dim, (1.0,) * dim, True)
+    if dim == 2:
+        ifem.GridGenerator.subdivided_hyper_rectangle(stria, (4, 6), (0.3125, 0.0), (0.5625, 0.6875), True)
+    else:
+        ifem.GridGenerator.subdivided_hyper_rectangle(stria, (3, 3, 4), (0.25, 0.0, 0.25), (0.7, 0.6, 0.75), True)
+    fluid, solid = ifem.Fluid.MPI.SCnsIM(ftria, params), ifem.Solid.MPI.HyperElasticity(stria, params)
+    fluid.setup()
+    solid.setup()
+    fluid.set_control(fgmres_rel=1e-10)
+    coupling = ifem.MPI.FSI(fluid, solid, params, sys.argv[-1] == "dirichlet")
+    for k in range(2):
+        coupling.run_one_step(k == 0)
+    n_un_glob = int(np.prod([k + 1 for k in reps]))
+    loc, glo = fluid.owned_global_dofs(n_un_glob)
+    sol = fluid.get_current_solution()
+    acc = fluid.get_vector(fluid.FSI_ACCELERATION)
+    hist = np.array([(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in fluid.history()], dtype=np.float64)
+    np.savez(out, glo=glo, y=acc[loc], rhs=fluid.get_vector(fluid.SYSTEM_RHS)[loc], sol=sol[loc], hist=hist, n_u=dim * n_un_glob,
+             solid=solid.get_current_solution())
     if size > 1:
         ifem.comm_finalize()
 

@@ -50,12 +50,14 @@ def emulated_library():
 
 # all of these pass; the default CPU suite runs the two that have no hardware multi-GPU run and are cheapest, --runslow the rest
 SLOW = pytest.mark.slow
-@pytest.mark.parametrize("solver,dim,reps", [pytest.param("InsIM", 2, (6, 8), marks=SLOW), ("SCnsIM", 2, (8, 10)),
-                                             pytest.param("SUPGInsIM", 2, (8, 10), marks=SLOW), ("InsIMEX", 2, (6, 8)),
-                                             pytest.param("SCnsIM", 3, (4, 4, 6), marks=SLOW)])
-def test_two_ranks_match_one_rank_on_the_emulated_device(emulated_library, solver, dim, reps, tmp_path):
+@pytest.mark.parametrize("solver,dim,reps,size", [
+    pytest.param("InsIM", 2, (6, 8), 2, marks=SLOW), ("SCnsIM", 2, (8, 10), 2), pytest.param("SUPGInsIM", 2, (8, 10), 2, marks=SLOW),
+    ("InsIMEX", 2, (6, 8), 2), pytest.param("SCnsIM", 3, (4, 4, 6), 2, marks=SLOW),
+    # four z-slabs: the middle ranks have two neighbours (both halo directions inside one group)
+    pytest.param("InsIM", 3, (3, 3, 8), 4, marks=SLOW), pytest.param("SCnsIM", 3, (4, 4, 8), 4, marks=SLOW)])
+def test_two_ranks_match_one_rank_on_the_emulated_device(emulated_library, solver, dim, reps, size, tmp_path):
     y1, rhs1, sol1, h1, nu = _run(1, solver, dim, reps, tmp_path)
-    y2, rhs2, sol2, h2, _ = _run(2, solver, dim, reps, tmp_path)
+    y2, rhs2, sol2, h2, _ = _run(size, solver, dim, reps, tmp_path)
     rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
     assert rel(y2, y1) < 1e-13
     assert rel(rhs2, rhs1) < 1e-13

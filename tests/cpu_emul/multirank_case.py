@@ -41,6 +41,8 @@ def main():
         ifem.comm_init(rank, size, open(idfile, "rb").read())
     if solver == "FSI":
         return fsi_case(rank, size, out, dim, reps)
+    if solver == "OUTPUT":
+        return output_case(rank, size, out, dim, reps)
     tria = ifem.Triangulation(dim)
     ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
     q1 = solver in ("SCnsIM", "SUPGInsIM")
@@ -90,6 +92,26 @@ def main():
     sol = flow.get_current_solution()
     hist = np.array([(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in flow.history()], dtype=np.float64)
     np.savez(out, glo=glo, y=y[loc], rhs=rhs[loc], sol=sol[loc], hist=hist, n_u=dim * n_un_glob)
+    if size > 1:
+        ifem.comm_finalize()
+
+
+def output_case(rank, size, out, dim, reps):
+    """every rank writes its piece of fluid_000003 for a solution that is a known function of the position"""
+    tria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
+    flow = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(text=cavity_prm(dim)))
+    flow.setup()
+    pts = flow.support_points()
+    n_u = flow.n_u
+    present = np.empty(flow.n_dofs)
+    for c in range(dim):
+        present[c:n_u:dim] = (c + 1) * pts[c:n_u:dim, 0] - 0.5 * pts[c:n_u:dim, 1]
+    present[n_u:] = 3.0 + pts[n_u:, 0] * pts[n_u:, 1]
+    flow.set_vector(flow.PRESENT, present)
+    flow.set_output_directory(os.path.dirname(out))
+    flow.output_results(3)
+    np.savez(out, glo=np.zeros(0), y=np.zeros(0), rhs=np.zeros(0), sol=np.zeros(0), hist=np.zeros((0, 4)), n_u=0)
     if size > 1:
         ifem.comm_finalize()
 

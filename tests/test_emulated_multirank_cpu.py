@@ -85,3 +85,40 @@ def test_two_rank_fsi_loop_matches_one_rank_on_the_emulated_device(emulated_libr
     assert rel(sol2[:nu], sol1[:nu]) < 1e-6
     assert rel(sol2[nu:], sol1[nu:]) < 1e-6
     assert h1.shape == h2.shape and np.array_equal(h1[:, :2], h2[:, :2])
+
+
+def test_two_rank_output_pieces_tile_the_mesh(emulated_library, tmp_path):
+    """FluidSolver::output_results on two ranks: every rank writes the cells of its own slab (cell->is_locally_owned()), rank 0
+    the .pvtu naming both pieces; together the pieces hold every cell exactly once and the right values at every vertex"""
+    import xml.etree.ElementTree as ET
+
+    reps = (6, 8)
+    rdv = tmp_path / "rdv_out"
+    rdv.mkdir()
+    procs = [subprocess.Popen([sys.executable, CASE, str(r), "2", str(rdv), str(tmp_path / f"out_{r}.npz"), "OUTPUT", "2", "6", "8"],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT) for r in range(2)]
+    for p in procs:
+        log = p.communicate(timeout=900)[0]
+        assert p.returncode == 0, log[-3000:]
+    root = ET.parse(str(tmp_path / "fluid_000003.pvtu")).getroot()
+    pieces = [p.attrib["Source"] for p in root.iter("Piece")]
+    assert pieces == ["fluid_000003.proc0000.vtu", "fluid_000003.proc0001.vtu"]
+    centres, n_cells = set(), 0
+    for k, name in enumerate(pieces):
+        piece = ET.parse(str(tmp_path / name)).getroot().find("UnstructuredGrid/Piece")
+        arr = {}
+        for sec in ("Points", "Cells", "PointData", "CellData"):
+            for a in piece.find(sec).findall("DataArray"):
+                nc = int(a.attrib.get("NumberOfComponents", 1))
+                v = np.array(a.text.split(), dtype=np.float64)
+                arr[a.attrib.get("Name", "points")] = v.reshape(-1, nc) if nc > 1 else v
+        x = arr["points"]
+        assert np.allclose(arr["velocity"][:, 0], x[:, 0] - 0.5 * x[:, 1], atol=1e-14)
+        assert np.allclose(arr["velocity"][:, 1], 2 * x[:, 0] - 0.5 * x[:, 1], atol=1e-14)
+        assert np.allclose(arr["pressure"], 3.0 + x[:, 0] * x[:, 1], atol=1e-14)
+        assert np.all(arr["subdomain"] == k)
+        conn = arr["connectivity"].astype(int).reshape(-1, 4)
+        n_cells += conn.shape[0]
+        for c in conn:
+            centres.add(tuple(np.round(x[c, :2].mean(axis=0), 10)))
+    assert n_cells == reps[0] * reps[1] and len(centres) == n_cells  # every cell exactly once

@@ -2,8 +2,10 @@
 // load_checkpoint (reference source/mpi_fluid_solver.cpp:491-713) and SharedSolidSolver::output_results / save_checkpoint /
 // load_checkpoint (source/mpi_shared_solid_solver.cpp:237-337, 452-571). Nothing is written unless an output directory has
 // been set (the library never writes into the working directory on its own; the reference always does).
+#include <algorithm>
 #include <filesystem>
 
+#include "comm.h"
 #include "insim.h"
 #include "output.h"
 #include "partition.h"
@@ -17,7 +19,7 @@ namespace ifem
     pvd_writer.reset();
     if (dir.empty()) return;
     std::filesystem::create_directories(dir);
-    if (fs.rank == 0 || !dofs_ready) pvd_writer.reset(new io::PVDWriter((dir == "." ? std::string() : dir + "/") + "fluid.pvd"));
+    if ((ctx.comm ? ctx.comm->rank : 0) == 0) pvd_writer.reset(new io::PVDWriter((dir == "." ? std::string() : dir + "/") + "fluid.pvd"));
   }
 
   void InsIM::output_results(unsigned int output_index)
@@ -45,8 +47,6 @@ namespace ifem
   void InsIM::save_checkpoint(int output_index)
   {
     if (output_directory.empty()) throw std::runtime_error("save_checkpoint: no output directory set");
-    if (fs.n_ranks > 1) throw std::runtime_error("save_checkpoint: single-rank runs only in this version");
-    io::rotate_checkpoints(output_directory, ".fluid_checkpoint", {});
     io::FluidCheckpoint c;
     c.dim = fs.dim;
     c.timestep = time.get_timestep();
@@ -55,6 +55,24 @@ namespace ifem
     c.n_vertices = triangulation.n_vertices();
     c.n_cells = triangulation.n_cells();
     c.present_solution = present_solution.to_host(ctx.stream);
+    if (fs.n_ranks > 1)
+      {
+        // the record holds the solution in the GLOBAL numbering, so a run can be continued on any number of ranks (as the
+        // reference's p4est-based checkpoints can): every rank contributes its owned entries to a sum all-reduce
+        const int dim = fs.dim;
+        const int64_t nug = (int64_t)dim * fs.un_global.n_nodes, ng = nug + fs.pn_global.n_nodes;
+        std::vector<double> g((size_t)ng, 0.0);
+        for (int l = 0; l < fs.n_owned_unodes; ++l)
+          for (int d = 0; d < dim; ++d) g[(size_t)dim * fs.part.u.local_to_global[l] + d] = c.present_solution[(size_t)dim * l + d];
+        for (int l = 0; l < fs.n_owned_pnodes; ++l) g[(size_t)nug + fs.part.p.local_to_global[l]] = c.present_solution[(size_t)fs.n_u + l];
+        DevBuf<double> d((size_t)ng);
+        d.upload(g, ctx.stream);
+        for (int64_t off = 0; off < ng; off += (1 << 28)) // all-reduce counts are ints
+          comm_allreduce_sum(*ctx.comm, d.p + off, (int)std::min<int64_t>(ng - off, 1 << 28), ctx.stream);
+        c.present_solution = d.to_host(ctx.stream);
+      }
+    if (fs.rank != 0) return;
+    io::rotate_checkpoints(output_directory, ".fluid_checkpoint", {});
     char name[64];
     std::snprintf(name, sizeof name, "%06d.fluid_checkpoint", output_index);
     io::save_fluid_checkpoint(output_directory + "/" + name, c);
@@ -77,8 +95,23 @@ namespace ifem
         make_constraints();
         initialize_system();
       }
-    if ((int64_t)c.present_solution.size() != fs.n_dofs) throw std::runtime_error("load_checkpoint: " + file + " has a different number of dofs");
-    present_solution.upload(c.present_solution, ctx.stream);
+    if (fs.n_ranks > 1)
+      {
+        // global record -> owned and ghost entries of this rank
+        const int dim = fs.dim;
+        const int64_t nug = (int64_t)dim * fs.un_global.n_nodes, ng = nug + fs.pn_global.n_nodes;
+        if ((int64_t)c.present_solution.size() != ng) throw std::runtime_error("load_checkpoint: " + file + " has a different number of dofs");
+        std::vector<double> local((size_t)fs.n_dofs);
+        for (int l = 0; l < fs.un.n_nodes; ++l)
+          for (int d = 0; d < dim; ++d) local[(size_t)dim * l + d] = c.present_solution[(size_t)dim * fs.part.u.local_to_global[l] + d];
+        for (int l = 0; l < fs.pn.n_nodes; ++l) local[(size_t)fs.n_u + l] = c.present_solution[(size_t)nug + fs.part.p.local_to_global[l]];
+        present_solution.upload(local, ctx.stream);
+      }
+    else
+      {
+        if ((int64_t)c.present_solution.size() != fs.n_dofs) throw std::runtime_error("load_checkpoint: " + file + " has a different number of dofs");
+        present_solution.upload(c.present_solution, ctx.stream);
+      }
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
     // the nodal viscous stress is a function of present_solution; the reference leaves it zero until the next step, which
     // makes the first FSI pass after a restart (find_solid_bc reads it) differ from the uninterrupted run

@@ -43,6 +43,8 @@ def main():
         return fsi_case(rank, size, out, dim, reps)
     if solver == "OUTPUT":
         return output_case(rank, size, out, dim, reps)
+    if solver == "CKPT":
+        return checkpoint_case(rank, size, out, dim, reps)
     tria = ifem.Triangulation(dim)
     ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
     q1 = solver in ("SCnsIM", "SUPGInsIM")
@@ -112,6 +114,26 @@ def output_case(rank, size, out, dim, reps):
     flow.set_output_directory(os.path.dirname(out))
     flow.output_results(3)
     np.savez(out, glo=np.zeros(0), y=np.zeros(0), rhs=np.zeros(0), sol=np.zeros(0), hist=np.zeros((0, 4)), n_u=0)
+    if size > 1:
+        ifem.comm_finalize()
+
+
+def checkpoint_case(rank, size, out, dim, reps):
+    """InsIM::run with checkpoints: argv[-2] = number of time steps, argv[-1] = output directory or "-" (none)"""
+    n_steps, directory = int(sys.argv[-2]), sys.argv[-1]
+    text = cavity_prm(dim, dt=1e-2, end_time=n_steps * 1e-2).replace("set Save interval = 1e6", "set Save interval = 0.02")
+    tria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
+    flow = ifem.Fluid.MPI.InsIM(tria, ifem.Parameters.AllParameters(text=text))
+    if directory != "-":
+        flow.set_output_directory(directory)
+    flow.set_control(a_inv_rel=1e-10, a_inv_max_it=5000, fgmres_rel=1e-10)
+    flow.run()
+    n_un_glob = int(np.prod([2 * k + 1 for k in reps]))
+    loc, glo = flow.owned_global_dofs(n_un_glob)
+    sol = flow.get_current_solution()
+    hist = np.array([(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in flow.history()], dtype=np.float64)
+    np.savez(out, glo=glo, y=np.zeros(glo.size), rhs=np.zeros(glo.size), sol=sol[loc], hist=hist, n_u=dim * n_un_glob)
     if size > 1:
         ifem.comm_finalize()
 

@@ -17,10 +17,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASE = os.path.join(ROOT, "tests", "cpu_emul", "multirank_case.py")
 
 
+_COUNTER = [0]
+
+
 def _run(size, solver, dim, reps, tmp_path):
-    rdv = tmp_path / f"rdv_{solver}_{size}"
+    _COUNTER[0] += 1
+    tag = "%s_%d_%d" % ("".join(ch if ch.isalnum() else "_" for ch in solver)[:40], size, _COUNTER[0])
+    rdv = tmp_path / f"rdv_{tag}"
     rdv.mkdir()
-    outs = [str(tmp_path / f"{solver}_{size}_{r}.npz") for r in range(size)]
+    outs = [str(tmp_path / f"{tag}_{r}.npz") for r in range(size)]
     procs = [subprocess.Popen([sys.executable, CASE, str(r), str(size), str(rdv), outs[r], solver.split(":")[0], str(dim)] + [str(k) for k in reps] + solver.split(":")[1:],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT) for r in range(size)]
     logs = [p.communicate(timeout=1500)[0] for p in procs]
@@ -122,3 +127,27 @@ def test_two_rank_output_pieces_tile_the_mesh(emulated_library, tmp_path):
         for c in conn:
             centres.add(tuple(np.round(x[c, :2].mean(axis=0), 10)))
     assert n_cells == reps[0] * reps[1] and len(centres) == n_cells  # every cell exactly once
+
+
+@SLOW  # passes (64 s); --runslow
+def test_checkpoint_written_on_two_ranks_restarts_on_one_and_on_two(emulated_library, tmp_path):
+    """fluid checkpoints hold the solution in the global numbering (every rank contributes its owned entries through a sum
+    all-reduce, rank 0 writes): four steps on two ranks, then the run is continued to step six on ONE rank and, from a copy of
+    the directory, on TWO ranks; both must agree with six uninterrupted steps on one rank (reference: the p4est-based
+    checkpoints of source/mpi_fluid_solver.cpp:582-713 are rank-count independent as well)"""
+    import shutil
+
+    d1 = tmp_path / "ckpt"
+    _run(2, f"CKPT:4:{d1}", 2, (6, 8), tmp_path)
+    assert sorted(f for f in os.listdir(d1) if f.endswith(".fluid_checkpoint")) == ["000002.fluid_checkpoint", "000004.fluid_checkpoint"]
+    d2 = tmp_path / "ckpt_copy"
+    shutil.copytree(d1, d2)
+    _, _, straight, h0, nu = _run(1, "CKPT:6:-", 2, (6, 8), tmp_path)
+    _, _, on_one, h1, _ = _run(1, f"CKPT:6:{d1}", 2, (6, 8), tmp_path)
+    _, _, on_two, h2, _ = _run(2, f"CKPT:6:{d2}", 2, (6, 8), tmp_path)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert h1[0, 0] == 5 and h2[0, 0] == 5  # the continued runs start with time step 5
+    for cont in (on_one, on_two):
+        assert rel(cont[:nu], straight[:nu]) < 1e-8
+        p, q = cont[nu:], straight[nu:]
+        assert rel(p - p.mean(), q - q.mean()) < 1e-7

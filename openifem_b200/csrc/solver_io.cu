@@ -148,12 +148,14 @@ namespace ifem
     pvd_writer.reset();
     if (dir.empty()) return;
     std::filesystem::create_directories(dir);
-    pvd_writer.reset(new io::PVDWriter((dir == "." ? std::string() : dir + "/") + "solid.pvd"));
+    // the solid is replicated on every rank: only rank 0 writes (mpi_shared_solid_solver.cpp:243-246, :460)
+    if ((ctx.comm ? ctx.comm->rank : 0) == 0) pvd_writer.reset(new io::PVDWriter((dir == "." ? std::string() : dir + "/") + "solid.pvd"));
   }
 
   void SolidSolver::output_results(unsigned int output_index)
   {
     if (output_directory.empty()) throw std::runtime_error("output_results: no output directory set");
+    if (ctx.comm && ctx.comm->rank != 0) return;
     const std::vector<double> u = current_displacement.to_host(ctx.stream), v = current_velocity.to_host(ctx.stream);
     const std::vector<double> e = strain.n ? strain.to_host(ctx.stream) : std::vector<double>();
     const std::vector<double> s = stress.n ? stress.to_host(ctx.stream) : std::vector<double>();
@@ -164,6 +166,7 @@ namespace ifem
   void SolidSolver::save_checkpoint(int output_index)
   {
     if (output_directory.empty()) throw std::runtime_error("save_checkpoint: no output directory set");
+    if (ctx.comm && ctx.comm->rank != 0) return;
     io::rotate_checkpoints(output_directory, ".solid_checkpoint_displacement", {".solid_checkpoint_velocity", ".solid_checkpoint_acceleration"});
     char stem[32];
     std::snprintf(stem, sizeof stem, "%06d", output_index);

@@ -45,6 +45,8 @@ def main():
         return output_case(rank, size, out, dim, reps)
     if solver == "CKPT":
         return checkpoint_case(rank, size, out, dim, reps)
+    if solver == "ACOUSTIC":
+        return acoustic_case(rank, size, out)
     tria = ifem.Triangulation(dim)
     ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
     q1 = solver in ("SCnsIM", "SUPGInsIM")
@@ -134,6 +136,28 @@ def checkpoint_case(rank, size, out, dim, reps):
     sol = flow.get_current_solution()
     hist = np.array([(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in flow.history()], dtype=np.float64)
     np.savez(out, glo=glo, y=np.zeros(glo.size), rhs=np.zeros(glo.size), sol=sol[loc], hist=hist, n_u=dim * n_un_glob)
+    if size > 1:
+        ifem.comm_finalize()
+
+
+def acoustic_case(rank, size, out):
+    """the reference's acoustic_duct_wave_mpi case (tests/acoustic_cases.py), first 20 steps through SCnsIM::run: the
+    time-dependent hard-coded boundary value re-makes the constraints on every rank in every step"""
+    import acoustic_cases
+
+    c = acoustic_cases.CASES["duct"]
+    text = acoustic_cases.prm_text("duct", 20).replace("set Global refinements = 3, 0", "set Global refinements = 2, 0")
+    tria = ifem.Triangulation(2)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, c["reps"], (0, 0), c["hi"], True)
+    flow = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=text))
+    flow.add_hard_coded_boundary_condition(0, acoustic_cases.gaussian_pulse("duct", 1e-7))
+    flow.set_control(fgmres_rel=1e-10)
+    flow.run()
+    n_un_glob = (c["reps"][0] * 4 + 1) * (c["reps"][1] * 4 + 1)
+    loc, glo = flow.owned_global_dofs(n_un_glob)
+    sol = flow.get_current_solution()
+    hist = np.array([(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in flow.history()], dtype=np.float64)
+    np.savez(out, glo=glo, y=np.zeros(glo.size), rhs=np.zeros(glo.size), sol=sol[loc], hist=hist, n_u=2 * n_un_glob)
     if size > 1:
         ifem.comm_finalize()
 

@@ -151,3 +151,15 @@ def test_checkpoint_written_on_two_ranks_restarts_on_one_and_on_two(emulated_lib
         assert rel(cont[:nu], straight[:nu]) < 1e-8
         p, q = cont[nu:], straight[nu:]
         assert rel(p - p.mean(), q - q.mean()) < 1e-7
+
+
+@SLOW  # passes; --runslow
+def test_time_dependent_boundary_values_on_two_ranks(emulated_library, tmp_path):
+    """SUPGFluidSolver::run with a time-dependent hard-coded boundary value (the acoustic duct, 20 steps, one refinement less):
+    the constraints are re-made on every rank in every step; two ranks reproduce one rank"""
+    _, _, sol1, h1, nu = _run(1, "ACOUSTIC", 2, (8, 2), tmp_path)
+    _, _, sol2, h2, _ = _run(2, "ACOUSTIC", 2, (8, 2), tmp_path)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert h1[-1, 0] == 20 and np.array_equal(h1[:, :2], h2[:, :2])
+    assert np.abs(sol1[:nu]).max() > 0
+    assert rel(sol2[:nu], sol1[:nu]) < 1e-6 and rel(sol2[nu:], sol1[nu:]) < 1e-6

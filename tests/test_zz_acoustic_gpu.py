@@ -3,8 +3,9 @@ source/mpi_supg_solver.cpp:427-486) advances the clock of the boundary functions
 applies the nonzero constraints in every step. Cases: the reference's acoustic_duct_wave_mpi and acoustic_pml_mpi
 (tests/acoustic_cases.py), checked against the oracle fixture tests/golden/scns_acoustic_oracle.npz and the reference goldens.
 
-STATUS: written after the round's GPU budget was spent. On the emulated device (tests/cpu_emul) both 100-step parity
-runs and the acoustic_pml_mpi golden (500 steps) pass; nothing here has run on a B200 yet. The file sorts after the verified suites.
+STATUS: written after the round's GPU budget was spent. On the emulated device (tests/cpu_emul) all four tests pass -
+both 100-step parity runs, the acoustic_duct_wave_mpi golden (1000 steps, 53 min there) and the acoustic_pml_mpi golden (500
+steps); nothing here has run on a B200 yet. The file sorts after the verified suites.
 
 Tolerances: fields after 100 steps 1e-5 relative (200 FGMRES solves, tightened to 1e-10 |rhs| on the device, sparse direct
 in the oracle); goldens as in the reference's drivers (5.93 +- 1e-3; |v| < 5e-2)."""

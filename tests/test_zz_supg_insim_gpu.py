@@ -119,3 +119,22 @@ def test_cpp_supg_driver_reference_goldens(golden_dir, which, prm_name):
     exe = os.path.join(ROOT, "tests", "cpp", "_build", "fluid_supg_insim_mpi")
     r = subprocess.run([exe, which, os.path.join(golden_dir, prm_name)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr + r.stdout
+
+
+def test_pressure_driven_supg_coarse_run_matches_oracle(golden_dir):
+    """the pressure-driven case of the reference (Neumann inlet, no-slip walls, open outlet) at a quarter of its resolution,
+    all ten time steps through run(): device fields against the oracle's (1e-6; passes at 1e-15 on the emulated device)"""
+    import openifem_b200 as ifem
+    from oracle import fem, prm, scns
+
+    text = open(os.path.join(golden_dir, "supg_ins_pressure_driven_2d.prm")).read().replace("set Global refinements = 1, 0", "set Global refinements = 0, 0")
+    tria = ifem.Triangulation(2)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, (50, 5), (0, 0), (2.0, 0.2), True)
+    flow = ifem.Fluid.MPI.SUPGInsIM(tria, ifem.Parameters.AllParameters(text=text))
+    flow.run()
+    assert flow.get_time()[1] == 10
+    o = scns.SUPGInsIM(fem.BoxMesh((50, 5), (0, 0), (2.0, 0.2)), prm.Params(text, is_text=True))
+    o.run()
+    sol = flow.get_current_solution()
+    assert rel(sol[: o.n_u], o.velocity()) < 1e-6
+    assert rel(sol[o.n_u:], o.pressure()) < 1e-6

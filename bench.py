@@ -14,7 +14,8 @@ N = 1 : config 3 on one B200.  N > 1 : the same mesh (strong scaling) split into
 launched by torch.distributed.run; NCCL carries only ghost-DoF halos and Krylov dot products.
 `--impl reference` times the reference's CPU path: /root/reference cannot be built (deal.II / PETSc /
 p4est absent), so this arm runs oracle/ - the CPU restatement of the same algorithm - on all host cores on
-a bounded sample (a 16^3-cell cavity step), scaled linearly in the number of cells.
+bounded samples of the same workload (one time step at 24^3, 32^3 and 48^3 cells), fits the growth exponent of
+s/step in the number of cells and extrapolates to 128^3 with it (the line says so: same_config false).
 """
 from __future__ import annotations
 
@@ -32,7 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "time_step_wall_s (3D INS cavity 128^3 cells Q2/Q1, 53.07M DoF)"
 UNIT = "s/step"
-SAMPLE_CELLS = 16  # CPU baseline sample: 16^3 cells
+CPU_BASELINE_CELLS = [16, 24]  # cpu_baseline leg of the default run (bounded); --impl reference: --ref-cells
 
 
 def _peaks():
@@ -103,10 +104,13 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
 
 
-def cpu_reference_step(cells, steps=1, warmup=0):
-    """The oracle (CPU restatement of mpi_insim.cpp) on all host cores: seconds per time step on a cells^3 cavity."""
+def cpu_reference_step(cells, steps=1, warmup=0, threads=None):
+    """The oracle (CPU restatement of mpi_insim.cpp) on all host cores: seconds per time step on a cells^3 cavity, same .prm and
+    same solver settings as the GPU arm (A~^-1 = BiCGStab + node-block Jacobi to 1e-1). Returns (s/step, oracle, team size)."""
+    from oracle import ins as oracle_ins
     from util import cavity_prm, make_oracle
 
+    team = oracle_ins.set_threads(threads)  # torchrun exports OMP_NUM_THREADS=1: ask the runtime explicitly
     o = make_oracle(cavity_prm(3), (cells,) * 3, (0, 0, 0), (1, 1, 1), a_inv=("bicgstab", 1e-1, 2000))
     k = 0
     for _ in range(warmup):
@@ -116,28 +120,50 @@ def cpu_reference_step(cells, steps=1, warmup=0):
     for _ in range(steps):
         o.run_one_step(k == 0)
         k += 1
-    return (time.perf_counter() - t0) / steps, o
+    return (time.perf_counter() - t0) / steps, o, team
+
+
+def cpu_reference_fit(sizes, target_cells, threads=None):
+    """Time one step at each sample size, fit s/step = c * cells^(3 p) by least squares in log space and extrapolate to
+    target_cells^3. Returns (value, description, team size, per-size seconds, p)."""
+    import math
+
+    secs, team = [], 0
+    for c in sizes:
+        sec, o, team = cpu_reference_step(c, threads=threads)
+        secs.append(sec)
+        del o
+    xs = [3.0 * math.log(c) for c in sizes]
+    ys = [math.log(t) for t in secs]
+    if len(sizes) > 1:
+        mx, my = sum(xs) / len(xs), sum(ys) / len(ys)
+        p = sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / sum((x - mx) ** 2 for x in xs)
+    else:
+        p = 1.0
+    value = secs[-1] * (target_cells / sizes[-1]) ** (3.0 * p)
+    desc = ("one time step (step 1 from rest: 3 Newton iterations, nothing cached) of the same cavity .prm at "
+            + ", ".join(f"{c}^3 cells: {t:.1f} s" for c, t in zip(sizes, secs))
+            + f" with oracle/ (CPU restatement of mpi_insim.cpp, same inner solvers and tolerances as the GPU arm) on an OpenMP team of "
+              f"{team} threads; fitted s/step ~ cells^{p:.3f}; value = {secs[-1]:.1f} s x ({target_cells}/{sizes[-1]})^(3 x {p:.3f}) "
+              f"- an extrapolation, the {target_cells}^3 system (135 GB of CSR) is not run on the CPU")
+    return value, desc, team, secs, p
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    # bounded sample: every "step" is one time step on SAMPLE_CELLS^3 cells, scaled linearly in cells
-    sec, o = cpu_reference_step(SAMPLE_CELLS, steps=max(1, args.steps), warmup=min(args.warmup, 1))
-    scale = (args.cells / SAMPLE_CELLS) ** 3
-    value = sec * scale
-    sample = (f"{max(1, args.steps)} time step(s) of the {SAMPLE_CELLS}^3-cell cavity (same prm, oracle/ CPU restatement, "
-              f"OpenMP on {cores} cores: {sec:.2f} s/step), scaled x{scale:.0f} linearly in cells to {args.cells}^3 "
-              f"(optimistic for the CPU: Krylov iteration counts grow with refinement)")
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # unconditional: torchrun sets it to 1 for N > 1
+    sizes = [int(c) for c in args.ref_cells.split(",")]
+    value, sample, team, secs, p = cpu_reference_fit(sizes, args.cells, threads=cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D INS lid-driven cavity {args.cells}^3 hex cells Q2/Q1 (config 3), one time step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"3D INS lid-driven cavity {args.cells}^3 hex cells Q2/Q1 (config 3), one time step",
+                   "same_config": False, "extrapolated": True, "sample_cells": sizes, "sample_seconds": secs, "fitted_exponent": p},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": team, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -249,12 +275,9 @@ def run_ours(args):
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count()
-        sec, _ = cpu_reference_step(SAMPLE_CELLS)
-        scale = (n / SAMPLE_CELLS) ** 3
-        cpu = {"value": sec * scale, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 time step of the {SAMPLE_CELLS}^3-cell cavity with the oracle (same algorithm, OpenMP {cores} cores): "
-                         f"{sec:.2f} s, scaled x{scale:.0f} linearly in cells"}
+        # bounded sample (about 20-30 s of CPU work); the reference arm (--impl reference) runs the larger sizes
+        v, sample, team, _, _ = cpu_reference_fit(CPU_BASELINE_CELLS, n, threads=os.cpu_count())
+        cpu = {"value": v, "unit": UNIT, "cores": team, "kind": "port", "sample": sample}
 
     line = {
         "metric": METRIC, "value": sec_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -303,6 +326,8 @@ def main():
     ap.add_argument("--cells", type=int, default=128, help="cells per direction (config 3 = 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-cells", default="24,32,48",
+                    help="--impl reference: cells per direction of the timed samples (the fit is extrapolated to --cells)")
     ap.add_argument("--sm-mode", type=int, default=1, choices=[0, 1, 2],
                     help="'CG for Sm': 0 fp64 CG on CSR, 1 fp32 CG on SELL-32, 2 fp32 CG on fp16 SELL-32 values")
     ap.add_argument("--inner-mode", type=int, default=3, choices=[0, 1, 2, 3],

@@ -74,7 +74,75 @@ class CsrOp:
 # ----------------------------------------------------------------------------
 # Krylov solvers restated
 # ----------------------------------------------------------------------------
+class BlockJacobi:
+    """Node-block Jacobi preconditioner: inverse bs x bs diagonal blocks, applied per node."""
+
+    def __init__(self, binv):
+        self.binv = np.ascontiguousarray(binv, dtype=np.float64)
+        self.nn, self.bs = self.binv.shape[0], self.binv.shape[1]
+
+    def __call__(self, v):
+        return np.einsum("nce,ne->nc", self.binv, v.reshape(self.nn, self.bs)).ravel()
+
+
 def cg(op, b, x0, tol_abs, max_it):
+    """CG on all host cores (oracle/csrc/oracle_krylov.cpp) for CSR operators; the numpy statement of the same loop is cg_py."""
+    if not isinstance(op, CsrOp):
+        return cg_py(op, b, x0, tol_abs, max_it)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    res = C.c_double()
+    f = lib().oracle_cg
+    f.restype = C.c_int
+    it = f(C.c_int64(op.shape[0]), _p(op.rp, C.c_int64), _p(op.ci, C.c_int), _p(op.A.data), _p(b), _p(x), C.c_int(0 if np.any(x) else 1),
+           C.c_double(tol_abs), C.c_int64(int(max_it)), C.byref(res))
+    op.n_apply += it
+    return x, it, res.value
+
+
+def bicgstab(op, prec, b, tol_abs, max_it):
+    """BiCGStab on all host cores for a CSR operator with a BlockJacobi (or no) preconditioner; numpy statement: bicgstab_py."""
+    if not isinstance(op, CsrOp) or not (prec is None or isinstance(prec, BlockJacobi)):
+        return bicgstab_py(op, prec, b, tol_abs, max_it)
+    x = np.empty(b.size)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    res = C.c_double()
+    f = lib().oracle_bicgstab
+    f.restype = C.c_int
+    it = f(C.c_int64(op.shape[0]), _p(op.rp, C.c_int64), _p(op.ci, C.c_int), _p(op.A.data), C.c_int(prec.bs if prec else 0),
+           _p(prec.binv) if prec else None, _p(b), _p(x), C.c_double(tol_abs), C.c_int64(int(max_it)), C.byref(res))
+    op.n_apply += 2 * it
+    return x, it, res.value
+
+
+def set_threads(n=None):
+    """Size of the OpenMP team standing in for the reference's MPI ranks (default: every host core). torchrun exports
+    OMP_NUM_THREADS=1, so a launcher that wants the host cores has to ask for them here. Returns the team size the
+    OpenMP runtime reports."""
+    f = lib().oracle_set_threads
+    f.restype = C.c_int
+    return f(C.c_int(int(n if n else (os.cpu_count() or 1))))
+
+
+def csr_split(S: sp.csr_matrix, nu: int):
+    """The four blocks of the [u | p] system as separate CSR matrices (the reference stores them separately)."""
+    n = S.shape[0]
+    rp = S.indptr.astype(np.int64)
+    ci = S.indices.astype(np.int32)
+    v = S.data
+    rps = [np.zeros(nu + 1, np.int64), np.zeros(nu + 1, np.int64), np.zeros(n - nu + 1, np.int64), np.zeros(n - nu + 1, np.int64)]
+    f = lib().oracle_csr_split
+    f.restype = None
+    args = [C.c_int64(n), C.c_int64(nu), _p(rp, C.c_int64), _p(ci, C.c_int), _p(v)]
+    f(*args, C.c_int(1), *[_p(r, C.c_int64) for r in rps], *([None] * 8))
+    cis = [np.empty(r[-1], np.int32) for r in rps]
+    vs = [np.empty(r[-1]) for r in rps]
+    f(*args, C.c_int(0), *[_p(r, C.c_int64) for r in rps], *[x for k in range(4) for x in (_p(cis[k], C.c_int), _p(vs[k]))])
+    shapes = [(nu, nu), (nu, n - nu), (n - nu, nu), (n - nu, n - nu)]
+    return [sp.csr_matrix((vs[k], cis[k], rps[k]), shape=shapes[k]) for k in range(4)]
+
+
+def cg_py(op, b, x0, tol_abs, max_it):
     """Plain CG with absolute residual tolerance (deal.II SolverControl driving
     PETSc KSPCG + PCNONE; call sites mpi_insim.cpp:73-83, 88-109)."""
     x = x0.copy()
@@ -100,7 +168,7 @@ def cg(op, b, x0, tol_abs, max_it):
     return x, it, res
 
 
-def bicgstab(op, prec, b, tol_abs, max_it):
+def bicgstab_py(op, prec, b, tol_abs, max_it):
     """Right-preconditioned BiCGStab, x0 = 0. Used as the *inexact* A~^{-1}
     where the reference's MUMPS LU (mpi_insim.cpp:124-127) is infeasible
     (hard part 2; in-tree precedent mpi_insimex.cpp:114-124)."""
@@ -119,7 +187,7 @@ def bicgstab(op, prec, b, tol_abs, max_it):
         rho_new = r0 @ r
         beta = (rho_new / rho) * (alpha / omega)
         p = r + beta * (p - omega * v)
-        ph = prec(p)
+        ph = prec(p) if prec else p
         v = op(ph)
         alpha = rho_new / (r0 @ v)
         s = r - alpha * v
@@ -128,7 +196,7 @@ def bicgstab(op, prec, b, tol_abs, max_it):
         if res <= tol_abs:
             x += alpha * ph
             break
-        sh = prec(s)
+        sh = prec(s) if prec else s
         t = op(sh)
         omega = (t @ s) / (t @ t)
         x += alpha * ph + omega * sh
@@ -284,11 +352,9 @@ class InsIM:
         p = self.prm
         nu = self.n_u
         S = self.system_matrix
-        Auu = S[:nu, :nu].tocsr()
-        Bt = S[:nu, nu:].tocsr()
-        B = S[nu:, :nu].tocsr()
+        Auu, Bt, B, _ = csr_split(S, nu)
         Mm = self.mass_matrix
-        Mp = Mm[nu:, nu:].tocsr()
+        Mp = csr_split(Mm, nu)[3]
         inv_diag_Mu = 1.0 / Mm.diagonal()[:nu]
         Sm = (B @ sp.diags(inv_diag_Mu) @ Bt).tocsr()  # mass_schur (:44-49)
         self.mass_schur = Sm
@@ -314,8 +380,7 @@ class InsIM:
             for c in range(dim):
                 for e in range(dim):
                     blocks[:, c, e] = np.asarray(Auu[np.arange(nn) * dim + c, np.arange(nn) * dim + e]).ravel()
-            binv = np.linalg.inv(blocks)
-            prec = lambda v: np.einsum("nce,ne->nc", binv, v.reshape(nn, dim)).ravel()
+            prec = BlockJacobi(np.linalg.inv(blocks))
 
             def a_inverse(v):
                 x, it, _ = bicgstab(A_op, prec, v, rel * np.linalg.norm(v), max_it)

@@ -8,6 +8,7 @@
 #include <string>
 
 #include "comm.h"
+#include "peer.h"
 #include "fsi.h"
 #include "insim.h"
 #include "insimex.h"
@@ -189,6 +190,7 @@ int ifem_comm_init(int rank, int size, const unsigned char id[128])
   return guard([&] {
     require_device();
     Context &ctx = default_context();
+    peer_link_reset();
     if (ctx.comm) comm_destroy(ctx.comm);
     ctx.comm = comm_create(rank, size, id);
   });
@@ -198,6 +200,7 @@ int ifem_comm_finalize(void)
   return guard([&] {
     if (!g_initialised) return;
     Context &ctx = default_context();
+    peer_link_reset();
     if (ctx.comm) comm_destroy(ctx.comm);
     ctx.comm = nullptr;
   });

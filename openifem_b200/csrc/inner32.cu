@@ -10,6 +10,7 @@
 #include <utility>
 
 #include "comm.h"
+#include "peer_dev.cuh"
 
 namespace ifem
 {
@@ -81,10 +82,11 @@ namespace ifem
     template <int BS, int NS, int MINB>
     __global__ void __launch_bounds__(kT, MINB)
     sell_spmv_pipe_kernel(int n_slices, const int *__restrict__ slice_off, const int *__restrict__ col, const float *__restrict__ val,
-                          const float *__restrict__ x, float *__restrict__ y)
+                          const float *__restrict__ x, float *__restrict__ y, const int *__restrict__ skip)
     {
       constexpr int RC = BS * BS;
       using G = XGather<BS>;
+      if (skip != nullptr && *skip) return; // the solver that enqueued this product has finished (device-resident state)
       const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
       const int lane = threadIdx.x & 31;
       if (warp >= n_slices) return;
@@ -148,10 +150,11 @@ namespace ifem
     template <int BS, int NS, int MINB>
     __global__ void __launch_bounds__(kT, MINB)
     sell_spmv_h_kernel(int n_slices, const int *__restrict__ hoff, const int2 *__restrict__ col2, const __half2 *__restrict__ valh,
-                       const float *__restrict__ row_scale, const float *__restrict__ x, float *__restrict__ y)
+                       const float *__restrict__ row_scale, const float *__restrict__ x, float *__restrict__ y, const int *__restrict__ skip)
     {
       constexpr int RC = BS * BS;
       using G = XGather<BS>;
+      if (skip != nullptr && *skip) return;
       const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
       const int lane = threadIdx.x & 31;
       if (warp >= n_slices) return;
@@ -356,59 +359,115 @@ namespace ifem
     }
 
     // ---------------------------------------------------------------------------
-    // vector kernels of the fp32 BiCGStab (one thread per node of the SELL numbering, grid-stride; reductions in
-    // fp64: block partials -> reduce_final_kernel -> all-reduce over the ranks)
+    // Vector kernels of the fp32 solvers: one thread per node of the SELL numbering, grid-stride. Reductions are summed
+    // in fp64 and finished inside the producing kernel (finish_reduce, peer_dev.cuh); the scalars of the recurrences live
+    // in a device-resident state that the last CTA advances (`adv` = 1) or, when an NCCL all-reduce has to follow the
+    // kernel (several ranks without a peer link), a one-thread kernel advances after it.
     // ---------------------------------------------------------------------------
-    template <int NR>
-    __device__ __forceinline__ void block_reduce_store(double (&v)[NR], double *__restrict__ partials)
+    struct BicgState
     {
-      __shared__ double sh[NR][kT / 32];
-      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-#pragma unroll
-      for (int q = 0; q < NR; ++q)
+      double rho, rho_new, alpha, omega, res2, tol2;
+      int its, max_it;
+      int done;      // the solve is over: every later kernel of the stream returns at once
+      int skip2;     // done, or the second half of the current iteration is not needed (converged at s / breakdown)
+      int early;     // x += alpha ph only, then done
+      int converged, breakdown, pad;
+    };
+    enum BicgStage { kBInit, kBDot1, kBS, kBDot2, kBXR };
+
+    __device__ __forceinline__ void bicg_advance(int stage, BicgState *st, const double *red)
+    {
+      if (stage == kBInit)
         {
-          const double s = warp_sum(v[q]);
-          if (l == 0) sh[q][w] = s;
-        }
-      __syncthreads();
-      if (w == 0)
-        {
-#pragma unroll
-          for (int q = 0; q < NR; ++q)
+          st->rho_new = red[0]; // r0 . r = |r|^2
+          st->res2 = red[0];
+          if (!(red[0] > st->tol2))
             {
-              double s = l < kT / 32 ? sh[q][l] : 0.0;
-              s = warp_sum(s);
-              if (l == 0) partials[(size_t)blockIdx.x * NR + q] = s;
+              st->done = 1;
+              st->skip2 = 1;
+              st->converged = red[0] <= st->tol2 ? 1 : 0;
             }
+          return;
+        }
+      if (st->done) return;
+      if (stage == kBDot1)
+        {
+          if (red[0] == 0.0 || !isfinite(red[0]))
+            {
+              st->done = 1;
+              st->skip2 = 1;
+              st->breakdown = 1;
+            }
+          else
+            st->alpha = st->rho_new / red[0];
+        }
+      else if (stage == kBS)
+        {
+          st->its += 1;
+          st->res2 = red[0];
+          if (red[0] <= st->tol2)
+            {
+              st->early = 1;
+              st->skip2 = 1;
+            }
+        }
+      else if (stage == kBDot2)
+        {
+          if (st->skip2) return;
+          if (red[1] == 0.0 || !isfinite(red[1]))
+            {
+              st->early = 1;
+              st->skip2 = 1;
+              st->breakdown = 1;
+            }
+          else
+            st->omega = red[0] / red[1];
+        }
+      else // kBXR
+        {
+          if (st->early)
+            {
+              st->done = 1;
+              st->converged = st->breakdown ? 0 : 1;
+              return;
+            }
+          st->res2 = red[0];
+          st->rho = st->rho_new;
+          st->rho_new = red[1];
+          if (red[0] <= st->tol2)
+            {
+              st->done = 1;
+              st->converged = 1;
+            }
+          else if (red[1] == 0.0 || st->omega == 0.0 || !isfinite(red[1]) || !isfinite(red[0]))
+            {
+              st->done = 1;
+              st->breakdown = 1;
+            }
+          else if (st->its >= st->max_it)
+            st->done = 1;
+          if (st->done) st->skip2 = 1;
         }
     }
 
-    __global__ void __launch_bounds__(kT) reduce_final32_kernel(int n_blocks, int nr, const double *__restrict__ partials, double *__restrict__ out)
+    __global__ void bicg_advance_kernel(int stage, BicgState *st, const double *red) { bicg_advance(stage, st, red); }
+
+    __global__ void bicg_begin_kernel(BicgState *st, double tol2, int max_it)
     {
-      __shared__ double sh[kT / 32];
-      for (int q = 0; q < nr; ++q)
-        {
-          double s = 0.0;
-          for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) s += partials[(size_t)i * nr + q];
-          s = warp_sum(s);
-          const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-          __syncthreads();
-          if (l == 0) sh[w] = s;
-          __syncthreads();
-          if (w == 0)
-            {
-              double tsum = l < kT / 32 ? sh[l] : 0.0;
-              tsum = warp_sum(tsum);
-              if (l == 0) out[q] = tsum;
-            }
-        }
+      st->rho = st->alpha = st->omega = 1.0;
+      st->rho_new = st->res2 = 0.0;
+      st->tol2 = tol2;
+      st->its = 0;
+      st->max_it = max_it;
+      st->done = st->skip2 = st->early = st->converged = st->breakdown = 0;
     }
 
     // r = r0 = src / |src| in SELL order; p = v = x = 0
     template <int BS>
     __global__ void __launch_bounds__(kT)
     init_kernel(int n_pad, const int *__restrict__ perm_row, const double *__restrict__ src, double scale, float *__restrict__ r,
-                float *__restrict__ r0, float *__restrict__ p, float *__restrict__ v, float *__restrict__ x, double *__restrict__ partials)
+                float *__restrict__ r0, float *__restrict__ p, float *__restrict__ v, float *__restrict__ x, BicgState *st,
+                double *__restrict__ partials, unsigned int *__restrict__ counter, double *__restrict__ red, PeerDev pd, int adv)
     {
       double acc[1] = {0.0};
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
@@ -427,7 +486,7 @@ namespace ifem
               acc[0] += (double)a * (double)a;
             }
         }
-      block_reduce_store<1>(acc, partials);
+      if (finish_reduce<1>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) bicg_advance(kBInit, st, acc);
     }
 
     template <int BS>
@@ -441,12 +500,15 @@ namespace ifem
       return make_float4(o[0], o[1], o[2], o[3]);
     }
 
-    // p = r + beta (p - omega v);  ph = D^-1 p
+    // p = r + beta (p - omega v), beta = (rho_new / rho) (alpha / omega);  ph = D^-1 p
     template <int BS>
     __global__ void __launch_bounds__(kT)
-    update_p_kernel(int n_pad, float beta, float omega, const float *__restrict__ r, float *__restrict__ p, const float *__restrict__ v,
+    update_p_kernel(int n_pad, const BicgState *__restrict__ st, const float *__restrict__ r, float *__restrict__ p, const float *__restrict__ v,
                     const float *__restrict__ binv, float4 *__restrict__ ph)
     {
+      if (st->done) return;
+      const float omega = (float)st->omega;
+      const float beta = (float)((st->rho_new / st->rho) * (st->alpha / st->omega));
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
         {
           float pc[BS];
@@ -461,12 +523,27 @@ namespace ifem
         }
     }
 
-    // s = r - alpha v;  sh = D^-1 s;  partial |s|^2
+    // alpha = rho_new / (r0 . v)
+    __global__ void __launch_bounds__(kT)
+    dot1_kernel(int64_t n, const float *__restrict__ r0, const float *__restrict__ v, BicgState *st, double *__restrict__ partials,
+                unsigned int *__restrict__ counter, double *__restrict__ red, PeerDev pd, int adv)
+    {
+      if (st->done) return;
+      double acc[1] = {0.0};
+      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        acc[0] += (double)r0[k] * (double)v[k];
+      if (finish_reduce<1>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) bicg_advance(kBDot1, st, acc);
+    }
+
+    // s = r - alpha v;  sh = D^-1 s;  |s|^2
     template <int BS>
     __global__ void __launch_bounds__(kT)
-    update_s_kernel(int n_pad, float alpha, const float *__restrict__ r, const float *__restrict__ v, float *__restrict__ s,
-                    const float *__restrict__ binv, float4 *__restrict__ sh, double *__restrict__ partials)
+    update_s_kernel(int n_pad, BicgState *st, const float *__restrict__ r, const float *__restrict__ v, float *__restrict__ s,
+                    const float *__restrict__ binv, float4 *__restrict__ sh, double *__restrict__ partials, unsigned int *__restrict__ counter,
+                    double *__restrict__ red, PeerDev pd, int adv)
     {
+      if (st->done) return;
+      const float alpha = (float)st->alpha;
       double acc[1] = {0.0};
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
         {
@@ -481,16 +558,35 @@ namespace ifem
             }
           sh[i] = apply_binv<BS>(binv, n_pad, i, sc);
         }
-      block_reduce_store<1>(acc, partials);
+      if (finish_reduce<1>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) bicg_advance(kBS, st, acc);
     }
 
-    // x += alpha ph + omega sh;  r = s - omega t;  partials |r|^2 and r0 . r
+    // omega = (t . s) / (t . t)
+    __global__ void __launch_bounds__(kT)
+    dot2_kernel(int64_t n, const float *__restrict__ t, const float *__restrict__ s, BicgState *st, double *__restrict__ partials,
+                unsigned int *__restrict__ counter, double *__restrict__ red, PeerDev pd, int adv)
+    {
+      if (st->skip2) return;
+      double acc[2] = {0.0, 0.0};
+      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        {
+          const double tk = (double)t[k];
+          acc[0] += tk * (double)s[k];
+          acc[1] += tk * tk;
+        }
+      if (finish_reduce<2>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) bicg_advance(kBDot2, st, acc);
+    }
+
+    // x += alpha ph + omega sh;  r = s - omega t;  |r|^2 and r0 . r   (omega = 0 when the iteration ends at s)
     template <int BS>
     __global__ void __launch_bounds__(kT)
-    update_xr_kernel(int n_pad, float alpha, float omega, float *__restrict__ x, const float4 *__restrict__ ph,
-                     const float4 *__restrict__ sh, float *__restrict__ r, const float *__restrict__ s, const float *__restrict__ t,
-                     const float *__restrict__ r0, double *__restrict__ partials)
+    update_xr_kernel(int n_pad, BicgState *st, float *__restrict__ x, const float4 *__restrict__ ph, const float4 *__restrict__ sh,
+                     float *__restrict__ r, const float *__restrict__ s, const float *__restrict__ t, const float *__restrict__ r0,
+                     double *__restrict__ partials, unsigned int *__restrict__ counter, double *__restrict__ red, PeerDev pd, int adv)
     {
+      if (st->done) return;
+      const float alpha = (float)st->alpha;
+      const float omega = st->early ? 0.0f : (float)st->omega;
       double acc[2] = {0.0, 0.0};
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
         {
@@ -507,24 +603,7 @@ namespace ifem
               acc[1] += (double)r0[k] * (double)rc;
             }
         }
-      block_reduce_store<2>(acc, partials);
-    }
-
-    // out[0] = a0 . b0, out[1] = a1 . b1 (NR = 2) on flat arrays
-    template <int NR>
-    __global__ void __launch_bounds__(kT)
-    dot32_kernel(int64_t n, const float *__restrict__ a0, const float *__restrict__ b0, const float *__restrict__ a1,
-                 const float *__restrict__ b1, double *__restrict__ partials)
-    {
-      double acc[NR];
-#pragma unroll
-      for (int q = 0; q < NR; ++q) acc[q] = 0.0;
-      for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
-        {
-          acc[0] += (double)a0[k] * (double)b0[k];
-          if (NR > 1) acc[NR - 1] += (double)a1[k] * (double)b1[k];
-        }
-      block_reduce_store<NR>(acc, partials);
+      if (finish_reduce<2>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) bicg_advance(kBXR, st, acc);
     }
 
     // dst (fp64, original numbering) = scale * x (SELL numbering), owned rows only
@@ -579,7 +658,7 @@ namespace ifem
         }
     }
 
-    // pack the owned entries a neighbour needs: xs floats per node
+    // pack the owned entries a neighbour needs: xs floats per node (NCCL path)
     __global__ void __launch_bounds__(kT) halo_pack32_kernel(int n, int xs, const int *__restrict__ idx, const float *__restrict__ v, float *__restrict__ buf)
     {
       const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -587,17 +666,68 @@ namespace ifem
     }
 
     // ---------------------------------------------------------------------------
-    // fp32 CG on a scalar matrix, driven from device-resident scalars
+    // fp32 CG on a scalar matrix
     // ---------------------------------------------------------------------------
     struct CgState
     {
-      double rr_cur, pAp, rr_new, beta, tol2, its, done;
+      double rr, alpha, beta, tol2;
+      int its, max_it, done, converged;
     };
+    enum CgStage { kCInit, kCDot, kCXR };
 
-    // r = p = src / |src| in SELL order, x = 0; partial |r|^2
+    __device__ __forceinline__ void cg_advance(int stage, CgState *st, const double *red)
+    {
+      if (stage == kCInit)
+        {
+          st->rr = red[0];
+          if (!(red[0] > st->tol2))
+            {
+              st->done = 1;
+              st->converged = red[0] <= st->tol2 ? 1 : 0;
+            }
+          return;
+        }
+      if (st->done) return;
+      if (stage == kCDot)
+        {
+          if (!(red[0] > 0.0) || !isfinite(red[0]))
+            st->done = 1; // p^T A p <= 0: not positive definite in fp32 (or breakdown)
+          else
+            st->alpha = st->rr / red[0];
+        }
+      else
+        {
+          const double rr_new = red[0];
+          st->beta = rr_new / st->rr;
+          st->rr = rr_new;
+          st->its += 1;
+          if (!(rr_new > st->tol2) || !isfinite(rr_new) || !isfinite(st->beta))
+            {
+              st->done = 1;
+              st->converged = rr_new <= st->tol2 ? 1 : 0;
+            }
+          else if (st->its >= st->max_it)
+            st->done = 1;
+        }
+    }
+
+    __global__ void cg_advance_kernel(int stage, CgState *st, const double *red) { cg_advance(stage, st, red); }
+
+    __global__ void cg_begin_kernel(CgState *st, double tol2, int max_it)
+    {
+      st->rr = 0.0;
+      st->alpha = st->beta = 0.0;
+      st->tol2 = tol2;
+      st->its = 0;
+      st->max_it = max_it;
+      st->done = st->converged = 0;
+    }
+
+    // r = p = src / |src| in SELL order, x = 0; |r|^2
     __global__ void __launch_bounds__(kT)
     cg_init_kernel(int n_pad, const int *__restrict__ perm_row, const double *__restrict__ src, double scale, float *__restrict__ r,
-                   float *__restrict__ p, float *__restrict__ x, double *__restrict__ partials)
+                   float *__restrict__ p, float *__restrict__ x, CgState *st, double *__restrict__ partials, unsigned int *__restrict__ counter,
+                   double *__restrict__ red, PeerDev pd, int adv)
     {
       double acc[1] = {0.0};
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
@@ -609,34 +739,27 @@ namespace ifem
           x[i] = 0.0f;
           acc[0] += (double)a * (double)a;
         }
-      block_reduce_store<1>(acc, partials);
+      if (finish_reduce<1>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) cg_advance(kCInit, st, acc);
     }
 
-    __global__ void cg_start_kernel(CgState *st, double tol2)
-    {
-      st->rr_cur = st->rr_new;
-      st->tol2 = tol2;
-      st->its = 0.0;
-      st->beta = 0.0;
-      st->pAp = 1.0;
-      st->done = st->rr_cur <= tol2 ? 1.0 : 0.0;
-    }
-
+    // alpha = rr / (p . Ap)
     __global__ void __launch_bounds__(kT)
-    cg_dot_kernel(int n_pad, const float *__restrict__ p, const float *__restrict__ ap, double *__restrict__ partials)
+    cg_dot_kernel(int n_pad, const float *__restrict__ p, const float *__restrict__ ap, CgState *st, double *__restrict__ partials,
+                  unsigned int *__restrict__ counter, double *__restrict__ red, PeerDev pd, int adv)
     {
+      if (st->done) return;
       double acc[1] = {0.0};
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) acc[0] += (double)p[i] * (double)ap[i];
-      block_reduce_store<1>(acc, partials);
+      if (finish_reduce<1>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) cg_advance(kCDot, st, acc);
     }
 
-    // x += alpha p; r -= alpha Ap; partial |r|^2   (alpha = rr / pAp from the device state)
+    // x += alpha p; r -= alpha Ap; |r|^2
     __global__ void __launch_bounds__(kT)
-    cg_xr_kernel(int n_pad, const CgState *__restrict__ st, float *__restrict__ x, const float *__restrict__ p, float *__restrict__ r,
-                 const float *__restrict__ ap, double *__restrict__ partials)
+    cg_xr_kernel(int n_pad, CgState *st, float *__restrict__ x, const float *__restrict__ p, float *__restrict__ r, const float *__restrict__ ap,
+                 double *__restrict__ partials, unsigned int *__restrict__ counter, double *__restrict__ red, PeerDev pd, int adv)
     {
-      if (st->done != 0.0) return;
-      const float alpha = (float)(st->rr_cur / st->pAp);
+      if (st->done) return;
+      const float alpha = (float)st->alpha;
       double acc[1] = {0.0};
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
         {
@@ -645,23 +768,13 @@ namespace ifem
           r[i] = rc;
           acc[0] += (double)rc * (double)rc;
         }
-      block_reduce_store<1>(acc, partials);
-    }
-
-    __global__ void cg_advance_kernel(CgState *st)
-    {
-      if (st->done != 0.0) return;
-      const double rr_new = st->rr_new;
-      st->beta = rr_new / st->rr_cur;
-      st->rr_cur = rr_new;
-      st->its += 1.0;
-      if (!(rr_new > st->tol2) || !isfinite(rr_new) || !isfinite(st->beta)) st->done = 1.0;
+      if (finish_reduce<1>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) cg_advance(kCXR, st, acc);
     }
 
     // p = r + beta p
     __global__ void __launch_bounds__(kT) cg_p_kernel(int n_pad, const CgState *__restrict__ st, const float *__restrict__ r, float *__restrict__ p)
     {
-      if (st->done != 0.0) return;
+      if (st->done) return;
       const float beta = (float)st->beta;
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) p[i] = fmaf(beta, p[i], r[i]);
     }
@@ -806,6 +919,43 @@ namespace ifem
           }
       }
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+    setup_peer_halo(ctx);
+  }
+
+  // Collective over the ranks: where does my message land in each neighbour's gather source, and the arrival flags.
+  void Sell32::setup_peer_halo(Context &ctx)
+  {
+    const bool was = peer_halo;
+    peer_halo = false;
+    if (!ctx.comm || ctx.comm->size < 2) return;
+    PeerLink &link = peer_link(ctx);
+    if (!link.active) return;
+    const int size = link.size;
+    // row of this rank: float offset of the segment that receives rank s's message (-1: not a neighbour), then an ok flag
+    std::vector<int64_t> row((size_t)size + 1, -1);
+    bool ok = halo_plan != nullptr && (int)halo_plan->neighbours.size() <= kPeerMaxNeighbours;
+    if (ok)
+      for (size_t k = 0; k < halo_plan->neighbours.size(); ++k)
+        row[halo_plan->neighbours[k]] = ((int64_t)n_pad + (int64_t)(halo_plan->recv_off[k] - n_rows)) * xs();
+    row[size] = ok ? 1 : 0;
+    const std::vector<int64_t> all = comm_allgather_i64(ctx, row);
+    ghost_off.assign((size_t)size * size, -1);
+    bool all_ok = true;
+    for (int r = 0; r < size; ++r)
+      {
+        all_ok = all_ok && all[(size_t)r * (size + 1) + size] == 1;
+        for (int s2 = 0; s2 < size; ++s2) ghost_off[(size_t)r * size + s2] = all[(size_t)r * (size + 1) + s2];
+      }
+    if (!all_ok) return;
+    if (!was || flag_peers.empty())
+      {
+        flag_peers = link.alloc_shared(ctx, sizeof(unsigned int) * kPeerMaxRanks);
+        if (flag_peers.empty()) return;
+        halo_state.alloc(2);
+        halo_state.zero(ctx.stream);
+        IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+      }
+    peer_halo = true;
   }
 
   void Sell32::refresh(Context &ctx, const Bcsr &A)
@@ -829,7 +979,7 @@ namespace ifem
     ctx.kernel_launches++;
   }
 
-  void Sell32::apply(Context &ctx, const float *x, float *y) const
+  void Sell32::apply(Context &ctx, const float *x, float *y, const int *skip) const
   {
     const int wgrid = (n_slices + kT / 32 - 1) / (kT / 32);
     // variant = 10 * NS + MINB: NS slots per step, MINB resident CTAs per SM
@@ -837,7 +987,7 @@ namespace ifem
       {
         const int2 *c2 = reinterpret_cast<const int2 *>(col2.p);
         const __half2 *vh = reinterpret_cast<const __half2 *>(valh.p);
-#define IFEM_SELL_H(B, NS, M) sell_spmv_h_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(n_slices, hoff.p, c2, vh, row_scale.p, x, y)
+#define IFEM_SELL_H(B, NS, M) sell_spmv_h_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(n_slices, hoff.p, c2, vh, row_scale.p, x, y, skip)
         if (bs == 3)
           switch (variant)
             {
@@ -862,7 +1012,7 @@ namespace ifem
       }
     else
       {
-#define IFEM_SELL_PIPE(B, NS, M) sell_spmv_pipe_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(n_slices, slice_off.p, col.p, val.p, x, y)
+#define IFEM_SELL_PIPE(B, NS, M) sell_spmv_pipe_kernel<B, NS, M><<<wgrid, kT, 0, ctx.stream>>>(n_slices, slice_off.p, col.p, val.p, x, y, skip)
         if (bs == 3)
           switch (variant)
             {
@@ -889,12 +1039,73 @@ namespace ifem
     ctx.kernel_launches++;
   }
 
-  void Sell32::halo(Context &ctx, float *x)
+  float *Sell32::gather_source(Context &ctx, int slot)
+  {
+    if (slot < 0 || slot >= 4) throw std::runtime_error("Sell32::gather_source: slot out of range");
+    const size_t len = x_len();
+    if (peer_halo)
+      {
+        // collective: every rank asks for its sources in the same order
+        if ((int)sources.size() <= slot) sources.resize(slot + 1);
+        Source &src = sources[slot];
+        if (!src.local)
+          {
+            PeerLink &link = peer_link(ctx);
+            // one length for all ranks (the mapping is by base address; the ghost offsets are per rank)
+            int64_t max_len = 0;
+            for (int64_t v : comm_allgather_i64(ctx, {(int64_t)len})) max_len = std::max(max_len, v);
+            src.peers = link.alloc_shared(ctx, (size_t)max_len * sizeof(float));
+            if (src.peers.empty())
+              peer_halo = false; // every rank reached the same verdict inside alloc_shared
+            else
+              src.local = static_cast<float *>(src.peers[link.rank]);
+          }
+        if (src.local)
+          {
+            IFEM_CUDA(cudaMemsetAsync(src.local, 0, len * sizeof(float), ctx.stream));
+            return src.local;
+          }
+      }
+    plain_sources[slot].alloc(len);
+    plain_sources[slot].zero(ctx.stream);
+    return plain_sources[slot].p;
+  }
+
+  void Sell32::halo(Context &ctx, float *x, const int *skip)
   {
     if (!halo_plan) return;
     if (!ctx.comm) throw std::runtime_error("Sell32::halo: no communicator");
     const Halo &H = *halo_plan;
     const int w = xs();
+    if (peer_halo)
+      for (const Source &src : sources)
+        if (src.local == x)
+          {
+            PeerLink &link = peer_link(ctx);
+            PeerHaloDev<float> h;
+            h.n_nb = (int)H.neighbours.size();
+            h.width = w;
+            for (int k = 0; k < h.n_nb; ++k)
+              {
+                const int nb = H.neighbours[k];
+                h.send_off[k] = H.send_off[k];
+                h.dst[k] = static_cast<float *>(src.peers[nb]) + ghost_off[(size_t)nb * link.size + link.rank];
+                h.flag[k] = static_cast<unsigned int *>(flag_peers[nb]) + link.rank;
+                h.nb_rank[k] = nb;
+              }
+            h.send_off[h.n_nb] = H.n_send_total;
+            h.my_flags = static_cast<const unsigned int *>(flag_peers[link.rank]);
+            h.epoch = halo_state.p;
+            h.counter = halo_state.p + 1;
+            const int total = H.n_send_total * w;
+            const int grid = std::max(1, std::min((total + kT * 8 - 1) / (kT * 8), ctx.sm_count));
+            peer_halo_push_kernel<float><<<grid, kT, 0, ctx.stream>>>(h, send_pos.p, x, skip);
+            IFEM_KERNEL_CHECK();
+            peer_halo_wait_kernel<float><<<1, 32, 0, ctx.stream>>>(h, skip);
+            IFEM_KERNEL_CHECK();
+            ctx.kernel_launches += 2;
+            return;
+          }
     if (H.n_send_total)
       {
         const int total = H.n_send_total * w;
@@ -914,7 +1125,7 @@ namespace ifem
   // ---------------------------------------------------------------------------
   InnerSolver32::~InnerSolver32()
   {
-    if (h_results) cudaFreeHost(h_results);
+    if (h_state) cudaFreeHost(h_state);
   }
 
   void InnerSolver32::setup(Context &ctx, const Bcsr &A, const NodeTable &nodes, const Halo *halo_, int precision)
@@ -927,15 +1138,18 @@ namespace ifem
         b->alloc(nv);
         b->zero(ctx.stream);
       }
-    ph.alloc(S.x_len());
-    ph.zero(ctx.stream);
-    sh.alloc(S.x_len());
-    sh.zero(ctx.stream);
+    ph = S.gather_source(ctx, 0);
+    sh = S.gather_source(ctx, 1);
     binv.alloc((size_t)S.bs * S.bs * S.n_pad);
     grid = std::max(1, std::min((S.n_pad + kT - 1) / kT, ctx.sm_count * 8));
     partials.alloc((size_t)grid * 2);
-    results.alloc(4);
-    if (!h_results) IFEM_CUDA(cudaMallocHost(&h_results, 4 * sizeof(double)));
+    red.alloc(kPeerMaxVals);
+    red.zero(ctx.stream);
+    counter.alloc(1);
+    counter.zero(ctx.stream);
+    state.alloc((sizeof(BicgState) + sizeof(int) - 1) / sizeof(int));
+    state.zero(ctx.stream);
+    if (!h_state) IFEM_CUDA(cudaMallocHost(&h_state, sizeof(BicgState)));
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
 
@@ -950,117 +1164,92 @@ namespace ifem
       }
   }
 
-  void InnerSolver32::reduce(Context &ctx, int nr, double *out)
-  {
-    reduce_final32_kernel<<<1, kT, 0, ctx.stream>>>(grid, nr, partials.p, results.p);
-    IFEM_KERNEL_CHECK();
-    ctx.kernel_launches++;
-    if (ctx.comm && ctx.comm->size > 1) comm_allreduce_sum(*ctx.comm, results.p, nr, ctx.stream);
-    IFEM_CUDA(cudaMemcpyAsync(h_results, results.p, nr * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
-    for (int q = 0; q < nr; ++q) out[q] = h_results[q];
-  }
-
   template <int BS>
-  static SolveResult solve_impl(Context &ctx, InnerSolver32 &I, const Sell32 &S, int grid, const double *src, double src_norm, double *dst,
-                                double rel_tol, int max_it, float *r, float *r0, float *p, float *v, float *s, float *t, float *x, float *ph,
-                                float *sh, const float *binv, double *partials, const std::function<void(const float *, float *)> &A,
-                                const std::function<void(int, double *)> &reduce)
+  SolveResult InnerSolver32::solve_impl(Context &ctx, const double *src, double src_norm, double *dst, double rel_tol, int max_it)
   {
-    (void)I;
     SolveResult out;
     const int n_pad = S.n_pad;
     const int64_t nflat = (int64_t)n_pad * BS;
     float4 *ph4 = reinterpret_cast<float4 *>(ph), *sh4 = reinterpret_cast<float4 *>(sh);
-    auto count = [&](int k = 1) { ctx.kernel_launches += k; };
+    BicgState *st = reinterpret_cast<BicgState *>(state.p);
+    const BicgState *h = static_cast<const BicgState *>(h_state);
+    auto launched = [&](int k = 1) {
+      IFEM_KERNEL_CHECK();
+      ctx.kernel_launches += k;
+    };
     if (!(src_norm > 0.0))
       {
         // A^-1 0 = 0
-        final_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x, 0.0, dst);
-        IFEM_KERNEL_CHECK();
-        count();
+        final_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x.p, 0.0, dst);
+        launched();
         out.converged = true;
         return out;
       }
-    double red[2];
-    init_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, r, r0, p, v, x, partials);
-    IFEM_KERNEL_CHECK();
-    count();
-    reduce(1, red);
-    double rho_new = red[0]; // r0 . r = |r|^2 (~1)
-    out.residual = std::sqrt(red[0]);
-    double rho = 1.0, alpha = 1.0, omega = 1.0;
-    const double tol = rel_tol;
-    while (out.iterations < max_it)
+    const ReduceMode m = reduce_mode(ctx);
+    // several ranks without a peer link: the sums of the kernel are local; NCCL adds them up, then the state advances
+    auto after = [&](int stage, int nr) {
+      if (!m.nccl) return;
+      comm_allreduce_sum(*ctx.comm, red.p, nr, ctx.stream);
+      bicg_advance_kernel<<<1, 1, 0, ctx.stream>>>(stage, st, red.p);
+      launched();
+    };
+    bicg_begin_kernel<<<1, 1, 0, ctx.stream>>>(st, rel_tol * rel_tol, max_it);
+    launched();
+    init_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, r.p, r0.p, p.p, v.p, x.p, st, partials.p, counter.p,
+                                                 red.p, m.pd, m.adv);
+    launched();
+    after(kBInit, 1);
+    int enqueued = 0;
+    while (true)
       {
-        const double beta = (rho_new / rho) * (alpha / omega);
-        update_p_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)beta, (float)omega, r, p, v, binv, ph4);
-        IFEM_KERNEL_CHECK();
-        count();
-        A(ph, v);
-        dot32_kernel<1><<<grid, kT, 0, ctx.stream>>>(nflat, r0, v, r0, v, partials);
-        IFEM_KERNEL_CHECK();
-        count();
-        reduce(1, red);
-        if (red[0] == 0.0 || !std::isfinite(red[0])) break;
-        alpha = rho_new / red[0];
-        update_s_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)alpha, r, v, s, binv, sh4, partials);
-        IFEM_KERNEL_CHECK();
-        count();
-        reduce(1, red);
-        out.iterations++;
-        out.residual = std::sqrt(red[0]);
-        if (out.residual <= tol)
+        const int chunk = std::max(1, std::min(check_every, max_it - enqueued));
+        for (int k = 0; k < chunk; ++k)
           {
-            // x += alpha ph
-            update_xr_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)alpha, 0.0f, x, ph4, sh4, r, s, t, r0, partials);
-            IFEM_KERNEL_CHECK();
-            count();
-            out.converged = true;
-            break;
+            update_p_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, st, r.p, p.p, v.p, binv.p, ph4);
+            launched();
+            S.halo(ctx, ph, &st->done);
+            S.apply(ctx, ph, v.p, &st->done);
+            dot1_kernel<<<grid, kT, 0, ctx.stream>>>(nflat, r0.p, v.p, st, partials.p, counter.p, red.p, m.pd, m.adv);
+            launched();
+            after(kBDot1, 1);
+            update_s_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, st, r.p, v.p, s.p, binv.p, sh4, partials.p, counter.p, red.p, m.pd, m.adv);
+            launched();
+            after(kBS, 1);
+            S.halo(ctx, sh, &st->skip2);
+            S.apply(ctx, sh, t.p, &st->skip2);
+            dot2_kernel<<<grid, kT, 0, ctx.stream>>>(nflat, t.p, s.p, st, partials.p, counter.p, red.p, m.pd, m.adv);
+            launched();
+            after(kBDot2, 2);
+            update_xr_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, st, x.p, ph4, sh4, r.p, s.p, t.p, r0.p, partials.p, counter.p, red.p, m.pd,
+                                                              m.adv);
+            launched();
+            after(kBXR, 2);
           }
-        A(sh, t);
-        dot32_kernel<2><<<grid, kT, 0, ctx.stream>>>(nflat, t, s, t, t, partials);
-        IFEM_KERNEL_CHECK();
-        count();
-        reduce(2, red);
-        if (red[1] == 0.0 || !std::isfinite(red[1]))
-          {
-            update_xr_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)alpha, 0.0f, x, ph4, sh4, r, s, t, r0, partials);
-            IFEM_KERNEL_CHECK();
-            count();
-            break;
-          }
-        omega = red[0] / red[1];
-        update_xr_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, (float)alpha, (float)omega, x, ph4, sh4, r, s, t, r0, partials);
-        IFEM_KERNEL_CHECK();
-        count();
-        reduce(2, red);
-        out.residual = std::sqrt(red[0]);
-        rho = rho_new;
-        rho_new = red[1];
-        if (out.residual <= tol)
-          {
-            out.converged = true;
-            break;
-          }
-        if (rho_new == 0.0 || omega == 0.0 || !std::isfinite(rho_new)) break;
+        enqueued += chunk;
+        IFEM_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(BicgState), cudaMemcpyDeviceToHost, ctx.stream));
+        IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+        if (h->done || enqueued >= max_it) break;
       }
+    out.iterations = h->its;
+    out.residual = std::sqrt(std::max(0.0, h->res2));
+    out.converged = h->converged != 0;
     static const bool debug = std::getenv("IFEM_INNER_DEBUG") != nullptr;
-    if (debug) std::fprintf(stderr, "[inner32] bicgstab its %d rel.res %.3e converged %d\n", out.iterations, out.residual, (int)out.converged);
+    if (debug)
+      std::fprintf(stderr, "[inner32] bicgstab its %d rel.res %.3e converged %d breakdown %d\n", out.iterations, out.residual, (int)out.converged,
+                   h->breakdown);
     if (!std::isfinite(out.residual) || out.residual >= 1.0)
       {
         // no progress over x = 0 (breakdown in fp32): hand back one block-Jacobi step D^-1 src, which is always a
         // valid (if weak) preconditioner application for the flexible outer iteration. r0 still holds src / |src|.
-        jacobi_out_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, r0, binv, src_norm, dst);
-        IFEM_KERNEL_CHECK();
-        count();
+        jacobi_out_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, r0.p, binv.p, src_norm, dst);
+        launched();
         out.residual = src_norm;
+        out.converged = false;
+        n_fallbacks++;
         return out;
       }
-    final_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x, src_norm, dst);
-    IFEM_KERNEL_CHECK();
-    count();
+    final_kernel<BS><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x.p, src_norm, dst);
+    launched();
     out.residual *= src_norm;
     return out;
   }
@@ -1068,32 +1257,24 @@ namespace ifem
   SolveResult InnerSolver32::solve(Context &ctx, const double *src, double src_norm, double *dst, double rel_tol, int max_it)
   {
     if (!S.built()) throw std::runtime_error("InnerSolver32::solve before setup");
-    std::function<void(const float *, float *)> A = [&](const float *in4, float *out) {
-      S.halo(ctx, const_cast<float *>(in4));
-      S.apply(ctx, in4, out);
-    };
-    std::function<void(int, double *)> red = [&](int nr, double *o) { reduce(ctx, nr, o); };
-    if (S.bs == 3)
-      return solve_impl<3>(ctx, *this, S, grid, src, src_norm, dst, rel_tol, max_it, r.p, r0.p, p.p, v.p, s.p, t.p, x.p, ph.p, sh.p, binv.p,
-                           partials.p, A, red);
-    return solve_impl<2>(ctx, *this, S, grid, src, src_norm, dst, rel_tol, max_it, r.p, r0.p, p.p, v.p, s.p, t.p, x.p, ph.p, sh.p, binv.p,
-                         partials.p, A, red);
+    if (S.bs == 3) return solve_impl<3>(ctx, src, src_norm, dst, rel_tol, max_it);
+    return solve_impl<2>(ctx, src, src_norm, dst, rel_tol, max_it);
   }
 
   void InnerSolver32::probe_load(Context &ctx, const double *xin)
   {
     if (!S.built()) throw std::runtime_error("InnerSolver32::probe_load before setup");
-    float4 *ph4 = reinterpret_cast<float4 *>(ph.p);
+    float4 *ph4 = reinterpret_cast<float4 *>(ph);
     if (S.bs == 3)
       to_sell4_kernel<3><<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.perm_row.p, xin, ph4);
     else
       to_sell4_kernel<2><<<grid, kT, 0, ctx.stream>>>(S.n_pad, S.perm_row.p, xin, ph4);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
-    S.halo(ctx, ph.p);
+    S.halo(ctx, ph);
   }
 
-  void InnerSolver32::probe_apply(Context &ctx) { S.apply(ctx, ph.p, v.p); }
+  void InnerSolver32::probe_apply(Context &ctx) { S.apply(ctx, ph, v.p); }
 
   void InnerSolver32::probe_store(Context &ctx, double *yout)
   {
@@ -1122,11 +1303,14 @@ namespace ifem
         b->alloc((size_t)S.n_pad);
         b->zero(ctx.stream);
       }
-    p.alloc(S.x_len());
-    p.zero(ctx.stream);
+    p = S.gather_source(ctx, 0);
     grid = std::max(1, std::min((S.n_pad + kT - 1) / kT, ctx.sm_count * 4));
     partials.alloc((size_t)grid);
-    state.alloc(sizeof(CgState) / sizeof(double));
+    red.alloc(kPeerMaxVals);
+    red.zero(ctx.stream);
+    counter.alloc(1);
+    counter.zero(ctx.stream);
+    state.alloc((sizeof(CgState) + sizeof(int) - 1) / sizeof(int));
     state.zero(ctx.stream);
     if (!h_state) IFEM_CUDA(cudaMallocHost(&h_state, sizeof(CgState)));
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -1138,7 +1322,7 @@ namespace ifem
     SolveResult out;
     const int n_pad = S.n_pad;
     CgState *st = reinterpret_cast<CgState *>(state.p);
-    const bool multi = ctx.comm && ctx.comm->size > 1;
+    const CgState *h = static_cast<const CgState *>(h_state);
     auto launched = [&](int k = 1) {
       IFEM_KERNEL_CHECK();
       ctx.kernel_launches += k;
@@ -1150,48 +1334,47 @@ namespace ifem
         out.converged = true;
         return out;
       }
+    const ReduceMode m = reduce_mode(ctx);
+    auto after = [&](int stage) {
+      if (!m.nccl) return;
+      comm_allreduce_sum(*ctx.comm, red.p, 1, ctx.stream);
+      cg_advance_kernel<<<1, 1, 0, ctx.stream>>>(stage, st, red.p);
+      launched();
+    };
     const double tol_rel = tol_abs / src_norm;
-    cg_init_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, r.p, p.p, x.p, partials.p);
+    cg_begin_kernel<<<1, 1, 0, ctx.stream>>>(st, tol_rel * tol_rel, max_it);
     launched();
-    reduce_final32_kernel<<<1, kT, 0, ctx.stream>>>(grid, 1, partials.p, &st->rr_new);
+    cg_init_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, r.p, p, x.p, st, partials.p, counter.p, red.p, m.pd,
+                                                m.adv);
     launched();
-    if (multi) comm_allreduce_sum(*ctx.comm, &st->rr_new, 1, ctx.stream);
-    cg_start_kernel<<<1, 1, 0, ctx.stream>>>(st, tol_rel * tol_rel);
-    launched();
-    const CgState *h = reinterpret_cast<const CgState *>(h_state);
+    after(kCInit);
     int enqueued = 0;
     while (true)
       {
         const int chunk = std::max(1, std::min(check_every, max_it - enqueued));
         for (int k = 0; k < chunk; ++k)
           {
-            S.halo(ctx, p.p);
-            S.apply(ctx, p.p, ap.p);
-            cg_dot_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, p.p, ap.p, partials.p);
+            S.halo(ctx, p, &st->done);
+            S.apply(ctx, p, ap.p, &st->done);
+            cg_dot_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, p, ap.p, st, partials.p, counter.p, red.p, m.pd, m.adv);
             launched();
-            reduce_final32_kernel<<<1, kT, 0, ctx.stream>>>(grid, 1, partials.p, &st->pAp);
+            after(kCDot);
+            cg_xr_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, x.p, p, r.p, ap.p, partials.p, counter.p, red.p, m.pd, m.adv);
             launched();
-            if (multi) comm_allreduce_sum(*ctx.comm, &st->pAp, 1, ctx.stream);
-            cg_xr_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, x.p, p.p, r.p, ap.p, partials.p);
-            launched();
-            reduce_final32_kernel<<<1, kT, 0, ctx.stream>>>(grid, 1, partials.p, &st->rr_new);
-            launched();
-            if (multi) comm_allreduce_sum(*ctx.comm, &st->rr_new, 1, ctx.stream);
-            cg_advance_kernel<<<1, 1, 0, ctx.stream>>>(st);
-            launched();
-            cg_p_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, r.p, p.p);
+            after(kCXR);
+            cg_p_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, r.p, p);
             launched();
           }
         enqueued += chunk;
         IFEM_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CgState), cudaMemcpyDeviceToHost, ctx.stream));
         IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
-        if (h->done != 0.0 || enqueued >= max_it) break;
+        if (h->done || enqueued >= max_it) break;
       }
     static const bool debug = std::getenv("IFEM_INNER_DEBUG") != nullptr;
-    if (debug) std::fprintf(stderr, "[inner32] cg its %d rel.res %.3e done %d\n", (int)h->its, std::sqrt(std::max(0.0, h->rr_cur)), (int)h->done);
-    out.iterations = (int)h->its;
-    out.residual = std::sqrt(std::max(0.0, h->rr_cur)) * src_norm;
-    out.converged = h->rr_cur <= h->tol2;
+    if (debug) std::fprintf(stderr, "[inner32] cg its %d rel.res %.3e done %d\n", h->its, std::sqrt(std::max(0.0, h->rr)), h->done);
+    out.iterations = h->its;
+    out.residual = std::sqrt(std::max(0.0, h->rr)) * src_norm;
+    out.converged = h->rr <= h->tol2;
     final_kernel<1><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x.p, src_norm, dst);
     launched();
     return out;

@@ -29,6 +29,7 @@
 #include "halo.h"
 #include "krylov.h"
 #include "linalg.h"
+#include "peer.h"
 
 namespace ifem
 {
@@ -58,6 +59,19 @@ namespace ifem
     const Halo *halo_plan = nullptr;
     DevBuf<int> send_pos;
     DevBuf<float> send_buf;
+    // peer-memory halo (peer.h): gather sources live in IPC-shared allocations, the pack kernel writes straight into the
+    // neighbours' ghost segments. sources[k] = {own pointer, the same buffer of every rank}
+    struct Source
+    {
+      float *local = nullptr;
+      std::vector<void *> peers;
+    };
+    std::vector<Source> sources;
+    DevBuf<float> plain_sources[4];        // gather sources when there is no peer link
+    bool peer_halo = false;
+    std::vector<int64_t> ghost_off;        // [size * size]: float offset in rank r's source where rank s's message lands (-1: none)
+    std::vector<void *> flag_peers;        // arrival flags of every rank ([kPeerMaxRanks] unsigned per rank)
+    DevBuf<unsigned int> halo_state;       // [0] pushes carried out, [1] CTA counter of the push kernel
 
     bool built() const { return n_slices > 0; }
     int xs() const { return bs == 1 ? 1 : 4; } // floats per node of a gather source
@@ -67,9 +81,13 @@ namespace ifem
     // values of A -> the copy
     void refresh(Context &ctx, const Bcsr &A);
     // y (bs floats per SELL row) = A x, x a gather source of x_len() floats with up-to-date ghosts
-    void apply(Context &ctx, const float *x, float *y) const;
-    // refresh the ghost entries of a gather source from their owners
-    void halo(Context &ctx, float *x);
+    void apply(Context &ctx, const float *x, float *y, const int *skip = nullptr) const;
+    // refresh the ghost entries of a gather source from their owners; with `skip` (device flag) set the exchange is a no-op
+    // on every rank (peer mode only - NCCL exchanges always run)
+    void halo(Context &ctx, float *x, const int *skip = nullptr);
+    // a zeroed vector of x_len() floats whose ghost segment the neighbours can write (slot: 0..3, reused on rebuild)
+    float *gather_source(Context &ctx, int slot);
+    void setup_peer_halo(Context &ctx);
     // bytes one product has to move: values + column index + slice offsets, x read once, y written once
     double spmv_bytes() const
     {
@@ -100,19 +118,27 @@ namespace ifem
     void probe_store(Context &ctx, double *y);
     Sell32 S;
 
+    int check_every = 6;       // iterations enqueued between two looks at the device state
+    long long n_fallbacks = 0; // applications that fell back to one block-Jacobi step (no progress in fp32)
+
   private:
-    void reduce(Context &ctx, int n_results, double *out);
+    template <int BS>
+    SolveResult solve_impl(Context &ctx, const double *src, double src_norm, double *dst, double rel_tol, int max_it);
     DevBuf<float> r, r0, p, v, s, t, x; // [n_pad * bs]
-    DevBuf<float> ph, sh;               // [x_len], gather sources
+    float *ph = nullptr, *sh = nullptr; // [x_len], gather sources (S.gather_source)
     DevBuf<float> binv;                 // [bs * bs][n_pad]
-    DevBuf<double> partials, results;
-    double *h_results = nullptr;
+    DevBuf<double> partials, red;       // CTA partial sums; the reduced (all-rank) values of the last reduction
+    DevBuf<unsigned int> counter;       // CTA arrival counter of the reducing kernels
+    DevBuf<int> state;                  // BicgState (inner32.cu)
+    void *h_state = nullptr;            // pinned mirror
     int grid = 0;
   };
 
-  // Unpreconditioned CG in fp32 on the SELL-32 copy of a scalar (1 x 1) matrix, x0 = 0, absolute tolerance. The
-  // iteration is driven from device-resident scalars (no host round trip per dot product): the host enqueues
-  // `check_every` iterations, then reads the state; iterations past convergence are no-ops.
+  // Unpreconditioned CG in fp32 on the SELL-32 copy of a scalar (1 x 1) matrix, x0 = 0, absolute tolerance.
+  // Both solvers are driven from device-resident scalars: every dot product is finished inside the kernel that produced
+  // its partial sums (last CTA; summed over the ranks through the peer link, peer.h), the coefficients of the recurrences
+  // are computed there and read by the next kernel, so there is no host round trip and no collective launch inside an
+  // iteration. The host enqueues `check_every` iterations, then reads the state; iterations past convergence are no-ops.
   class InnerCG32
   {
   public:
@@ -126,9 +152,11 @@ namespace ifem
 
   private:
     DevBuf<float> r, ap, x; // [n_pad]
-    DevBuf<float> p;        // [x_len] gather source
-    DevBuf<double> partials, state; // state: see CgState in inner32.cu
-    double *h_state = nullptr;
+    float *p = nullptr;     // [x_len] gather source (S.gather_source)
+    DevBuf<double> partials, red;
+    DevBuf<unsigned int> counter;
+    DevBuf<int> state;      // CgState (inner32.cu)
+    void *h_state = nullptr;
     int grid = 0;
   };
 } // namespace ifem

@@ -143,12 +143,11 @@ namespace ifem
     const int max_p_its = (int)std::min<int64_t>(n_p_global, 1 << 30);
     {
       ScopedTimer t(ctx, timer_ms["CG for Mp"]);
-      fill(ctx, vp, 0.0, tmp);
       LinOp Mp = [&](const double *x, double *y) {
         fs.halo_p.update(ctx, const_cast<double *>(x));
         spmv(ctx, fs.M_p, x, y);
       };
-      const SolveResult r = cg(ctx, vp, Mp, src_p, tmp, true, std::max(control.cg_floor, control.cg_mp_rel * nrm), max_p_its, pool_cg);
+      const SolveResult r = cg_mp_dev.solve(ctx, vp, Mp, src_p, tmp, std::max(control.cg_floor, control.cg_mp_rel * nrm), max_p_its);
       cur.cg_mp_its += r.iterations;
       scale(ctx, vp, -(parameters.viscosity + parameters.grad_div * parameters.fluid_rho), tmp);
     }

@@ -151,6 +151,7 @@ namespace ifem
   public:
     InnerSolver32 inner32;
     InnerCG32 inner_sm;
+    DeviceCG64 cg_mp_dev; // "CG for Mp"
     // "CG for Sm": x = S_m^-1 b (pressure vectors on the device) in the given cg_sm_fp32 mode; b_norm = |b| over all ranks
     SolveResult solve_mass_schur(int mode, const double *b, double b_norm, double *x, double tol_abs, int max_it);
 

@@ -56,3 +56,25 @@ namespace ifem
   SolveResult fgmres(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
                      int64_t max_it, int basis_size, VecPool &pool);
 } // namespace ifem
+
+namespace ifem
+{
+  // Plain CG in fp64 with x0 = 0 and an absolute tolerance, driven from device-resident scalars like the fp32 inner solvers
+  // (inner32.h): the two dot products of an iteration are finished inside the kernels that produce them (summed over the ranks
+  // through the peer link when there is one, peer.h), alpha and beta never visit the host, and the host looks at the state
+  // only every few iterations. Replaces the host-driven cg() where the same small system is solved many times per time step:
+  // "CG for Mp" (PETSc KSPCG at reference source/mpi_insim.cpp:73-83). `A` only enqueues work on ctx.stream.
+  class DeviceCG64
+  {
+  public:
+    ~DeviceCG64();
+    SolveResult solve(Context &ctx, const VecSpace &n, const LinOp &A, const double *b, double *x, double tol_abs, int max_it);
+
+  private:
+    DevBuf<double> r, p, ap, partials, red;
+    DevBuf<unsigned int> counter;
+    DevBuf<int> state;
+    void *h_state = nullptr;
+    int last_its = 0; // iterations of the previous solve: that many are enqueued before the first look at the state
+  };
+} // namespace ifem

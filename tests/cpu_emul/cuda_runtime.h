@@ -69,6 +69,11 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask, int = 32)
 }
 template <typename T> inline T __ldcs(const T *p) { return *p; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+template <typename T> inline T __ldcg(const T *p) { return *p; }
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, 8); return r; }
+inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
@@ -116,6 +121,12 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+// no peer memory between emulated ranks: the product falls back to its communicator path (peer.h)
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return 1; }
+inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return 1; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 
 // CUDA puts these in the global namespace
 template <typename T> inline T min(T a, T b) { return b < a ? b : a; }

@@ -64,7 +64,11 @@ def main():
     if solver == "SCnsIM":
         flow.set_body_force(lambda p, c: 5.0 if c == 0 else 0.0)
     flow.setup()
-    if solver == "InsIM":
+    if solver == "InsIM" and "inner32" in sys.argv[7 + dim:]:
+        # device-resident fp32 inner solvers (BiCGStab on the fp16 SELL copy of A_uu, CG on the SELL copy of S_m): on emulated ranks
+        # their reductions and halos go through the communicator between the kernels (no peer memory there)
+        flow.set_control(a_inv_rel=1e-3, a_inv_max_it=500, fgmres_rel=1e-9, a_inv_fp32=3, cg_sm_fp32=1)
+    elif solver == "InsIM":
         flow.set_control(a_inv_rel=1e-10, a_inv_max_it=5000, fgmres_rel=1e-9)
     elif q1:
         flow.set_control(fgmres_rel=1e-10)

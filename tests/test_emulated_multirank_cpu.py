@@ -56,7 +56,7 @@ def emulated_library():
 # all of these pass; the default CPU suite runs the two that have no hardware multi-GPU run and are cheapest, --runslow the rest
 SLOW = pytest.mark.slow
 @pytest.mark.parametrize("solver,dim,reps,size", [
-    pytest.param("InsIM", 2, (6, 8), 2, marks=SLOW), ("SCnsIM", 2, (8, 10), 2), pytest.param("SUPGInsIM", 2, (8, 10), 2, marks=SLOW),
+    pytest.param("InsIM", 2, (6, 8), 2, marks=SLOW), ("InsIM:inner32", 2, (6, 8), 2), ("SCnsIM", 2, (8, 10), 2), pytest.param("SUPGInsIM", 2, (8, 10), 2, marks=SLOW),
     ("InsIMEX", 2, (6, 8), 2), pytest.param("SCnsIM", 3, (4, 4, 6), 2, marks=SLOW),
     # four z-slabs: the middle ranks have two neighbours (both halo directions inside one group)
     pytest.param("InsIM", 3, (3, 3, 8), 4, marks=SLOW), pytest.param("SCnsIM", 3, (4, 4, 8), 4, marks=SLOW)])
@@ -70,7 +70,7 @@ def test_two_ranks_match_one_rank_on_the_emulated_device(emulated_library, solve
     assert np.all(np.abs(h2[:, 2] - h1[:, 2]) <= 1e-6 * np.maximum(h1[:, 2], 1e-9))
     assert rel(sol2[:nu], sol1[:nu]) < 1e-6
     p2, p1 = sol2[nu:], sol1[nu:]
-    if solver in ("InsIM", "InsIMEX"):  # closed cavity: pressure up to a constant
+    if solver.split(":")[0] in ("InsIM", "InsIMEX"):  # closed cavity: pressure up to a constant
         p2, p1 = p2 - p2.mean(), p1 - p1.mean()
     assert rel(p2, p1) < 1e-6
 

@@ -262,7 +262,24 @@ def run_ours(args):
     hist = flow.history()
     last = [h for h in hist if h["timestep"] == hist[-1]["timestep"]]
     sections = {k: flow.timer_ms(k) for k in ["Assemble system", "Solve linear system", "CG for Mp", "CG for Sm", "A_inv",
-                                              "CG for Sm fp64 fallbacks (count)"]}
+                                              "CG for Sm fp64 fallbacks (count)", "A_inv block-Jacobi fallbacks (count)"]}
+    # parity pins, computed outside the timed region in fp64: true residual |b - A x| / |b| of every linear solve of the timed
+    # steps (recomputed with the fp64 operator), the Newton residual the reference prints (mpi_insim.cpp:456-460), and norms of
+    # the final fields summed over the owned dofs of all ranks - comparable across N = 1 / 2 / 4 / 8 and with an all-fp64 run
+    sol = host_np  # solution after the last timed step
+    u_own, p_own = sol[:3 * ou], sol[n_u:n_u + op]
+    su2, sp1, sp2, cnt = (sum_over_ranks(float(v)) for v in (np.dot(u_own, u_own), p_own.sum(), np.dot(p_own, p_own), p_own.size))
+    timed = [h for h in hist if h["timestep"] > args.warmup]
+    pins = {"u_l2": su2 ** 0.5, "p_meanfree_l2": max(0.0, sp2 - sp1 * sp1 / cnt) ** 0.5,
+            "final_newton_abs_res": last[-1]["abs_res"], "final_newton_rel_res": last[-1]["rel_res"],
+            "max_true_res_timed_steps": max(h["true_res"] for h in timed) if timed else None,
+            "last_step": [{"newton_it": h["iteration"], "abs_res": h["abs_res"], "fgmres_its": h["gmres_its"], "fgmres_res": h["gmres_res"],
+                           "true_res": h["true_res"], "a_inv_its": h["a_inv_its"], "cg_sm_its": h["cg_sm_its"], "cg_mp_its": h["cg_mp_its"]}
+                          for h in last],
+            "a_inv_block_jacobi_fallbacks": int(sections["A_inv block-Jacobi fallbacks (count)"]),
+            "cg_sm_fp64_fallbacks": int(sections["CG for Sm fp64 fallbacks (count)"]),
+            "note": "true_res = |b - A x|_2 / |b|_2 with the fp64 block operator after FGMRES returned (tolerance 1e-4); "
+                    "field norms over all owned dofs after the last timed step"}
 
     if world > 1:
         ms_uu, ms_blk, ms_32 = max_over_ranks(ms_uu), max_over_ranks(ms_blk), max_over_ranks(ms_32)
@@ -296,7 +313,8 @@ def run_ours(args):
                             + "; inside the preconditioner only - FGMRES operator, residuals and basis are fp64, Newton/FGMRES "
                               "iteration counts and converged fields equal the fp64 path's (tests/test_inner32_gpu.py: 1e-6 vs oracle)",
                    "parallelism": f"{world} z-slab(s), one rank per GPU; NCCL: ghost halos + dot-product all-reduces only",
-                   "setup_s": round(t_setup, 1), "newton_its_last_step": len(last),
+                   "setup_s": round(t_setup, 1), "setup_note": "mesh, patterns, partition and the SELL-32 layouts are built once before the "
+                   "warm-up steps and are outside `value`; the per-solve refresh of the SELL copies from the assembled matrix is inside", "newton_its_last_step": len(last),
                    "fgmres_its_last_step": [h["gmres_its"] for h in last], "section_ms_total": sections},
         "e2e": {"value": sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d},
         "gpu_launches": launches, "clocks": clocks,
@@ -305,13 +323,15 @@ def run_ours(args):
                                                  "kernel of a step), per GPU (rank 0's rows)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic.get("sell_spmv_h_kernel" if args.inner_mode == 3 else "sell_spmv_pipe_kernel") if world == 1 and n == 128 else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this "
+                                       "config (profiles/ncu_traffic.json names the capture); not re-measured in this run",
                      "algorithmic_bytes": bytes_32, "ms": ms_32, "sell_padding": sell_padding,
-                     "fgmres_operator_spmv": {"kernel": "bcsr_spmv_kernel<3,3,32,double> (A_uu, fp64 operator of FGMRES)", "ms": ms_uu,
+                     "fgmres_operator_spmv": {"kernel": "bcsr_spmv_row_kernel<3,3,32,double,1,4,0> (A_uu, fp64 operator of FGMRES)", "ms": ms_uu,
                                               "algorithmic_bytes": bytes_uu, "achieved": achieved64, "frac": achieved64 / peak,
                                               "traffic": traffic.get("bcsr_spmv_kernel<3,3,32,double>") if world == 1 and n == 128 else None},
                      "block_vmult": {"ms": ms_blk, "bytes": bytes_blk, "GB/s": bytes_blk / (ms_blk * 1e-3) / 1e9,
                                      "csr_equivalent_bytes_per_gpu": 12.0 * nnz_local + 20.0 * (3 * ou + op)}},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "parity_pins": pins,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

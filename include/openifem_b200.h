@@ -66,6 +66,9 @@ int ifem_tria_hyper_cube(ifem_tria *t, double left, double right, int colorize);
 int ifem_tria_refine_global(ifem_tria *t, int times);
 /* GridTools::shift(offset, tria): offset [dim] added to every vertex */
 int ifem_tria_shift(ifem_tria *t, const double *offset);
+/* cell->set_material_id() for every active cell (1-based part numbers; the solid solvers pick the material parameters of a cell's
+ * part, source/mpi_hyper_elasticity.cpp:226-228); n must equal the number of active cells */
+int ifem_tria_set_material_ids(ifem_tria *t, const int *ids, int64_t n);
 int ifem_tria_counts(const ifem_tria *t, int64_t *n_vertices, int64_t *n_cells, int64_t *n_boundary_faces);
 /* Utils::GridCreator<dim>::flow_around_cylinder(tria) (source/utilities.cpp:343-574; dim of the handle): the mesh of
  * tests/fluid_cylinder_mpi*. In 2-D the cells around the hole carry their polar / transfinite charts, which
@@ -102,6 +105,8 @@ typedef struct
   int gmres_its;
   double gmres_res;
   int cg_mp_its, cg_sm_its, a_inv_its, precond_applies;
+  double true_res; /* |b - A x|_2 / |b|_2 of the linear solve, recomputed in fp64 with the operator after FGMRES returned
+                      (the parity pin of the inexact / reduced-precision inner solves: they act inside the preconditioner only) */
 } ifem_newton_record;
 
 /* InsIM(tria, parameters): the solver keeps a reference to the caller-owned triangulation

@@ -116,6 +116,11 @@ class Triangulation:
     def refine_global(self, times: int):
         check(lib().ifem_tria_refine_global(self._h, C.c_int(times)))
 
+    def set_material_ids(self, ids):
+        """cell->set_material_id() of every active cell (1-based solid part numbers)"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        check(lib().ifem_tria_set_material_ids(self._h, iptr(ids), C.c_int64(ids.size)))
+
     def _counts(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib().ifem_tria_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))

@@ -21,7 +21,7 @@ class InsControl(C.Structure):
 class NewtonRecord(C.Structure):
     _fields_ = [("timestep", C.c_uint), ("iteration", C.c_uint), ("abs_res", C.c_double), ("rel_res", C.c_double),
                 ("gmres_its", C.c_int), ("gmres_res", C.c_double), ("cg_mp_its", C.c_int), ("cg_sm_its", C.c_int),
-                ("a_inv_its", C.c_int), ("precond_applies", C.c_int)]
+                ("a_inv_its", C.c_int), ("precond_applies", C.c_int), ("true_res", C.c_double)]
 
 
 class SolidRecord(C.Structure):

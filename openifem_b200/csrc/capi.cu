@@ -291,6 +291,13 @@ int ifem_tria_shift(ifem_tria *t, const double *offset)
     for (size_t i = 0; i < t->t.vertices.size(); ++i) t->t.vertices[i] += offset[i % dim];
   });
 }
+int ifem_tria_set_material_ids(ifem_tria *t, const int *ids, int64_t n)
+{
+  return guard([&] {
+    if (n != (int64_t)t->t.n_cells()) throw std::runtime_error("ifem_tria_set_material_ids: one id per active cell expected");
+    t->t.material_id.assign(ids, ids + n);
+  });
+}
 int ifem_tria_flow_around_cylinder(ifem_tria *t)
 {
   return guard([&] { GridCreator::flow_around_cylinder(t->t, t->t.dim); });
@@ -567,7 +574,7 @@ int ifem_insim_history(const ifem_insim *s, int max_records, ifem_newton_record 
         ifem_newton_record &r = out[i - first];
         r.timestep = h[i].timestep; r.iteration = h[i].iteration; r.abs_res = h[i].abs_res; r.rel_res = h[i].rel_res;
         r.gmres_its = h[i].gmres_its; r.gmres_res = h[i].gmres_res; r.cg_mp_its = h[i].cg_mp_its; r.cg_sm_its = h[i].cg_sm_its;
-        r.a_inv_its = h[i].a_inv_its; r.precond_applies = h[i].precond_applies;
+        r.a_inv_its = h[i].a_inv_its; r.precond_applies = h[i].precond_applies; r.true_res = h[i].true_res;
       }
   });
 }

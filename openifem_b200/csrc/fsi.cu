@@ -1231,7 +1231,10 @@ namespace ifem
           for (int k = 0; k < dim * (dim + 1) / 2; ++k) fs.halo_p.update(ctx, scns->fsi_stress.p + (size_t)k * fs.un.n_nodes);
       }
     FluidBcArgs A{};
-    A.n_owned_nodes = fs.n_owned_unodes;
+    // Dirichlet variant: the test is purely geometric on a replicated solid, so every LOCAL node (owned and ghost) is
+    // flagged - the assembly reads the constraint of ghost column nodes too (column elimination, lifting), and a ghost copy
+    // left unconstrained would make the assembled system depend on the partition
+    A.n_owned_nodes = use_dirichlet_bc ? fs.un.n_nodes : fs.n_owned_unodes;
     A.nu = fs.nu;
     A.n2c_ptr = d_n2c_ptr.p;
     A.n2c_cell = d_n2c_cell.p;
@@ -1252,7 +1255,7 @@ namespace ifem
     A.inner_con = d_inner_con.p;
     A.inner_inhom = d_inner_inhom.p;
     A.error_flag = err.p;
-    const int blocks = (fs.n_owned_unodes + 127) / 128;
+    const int blocks = (A.n_owned_nodes + 127) / 128;
     if (dim == 2) fluid_bc_kernel<2><<<blocks, 128, 0, s>>>(S, A);
     else fluid_bc_kernel<3><<<blocks, 128, 0, s>>>(S, A);
     IFEM_KERNEL_CHECK();

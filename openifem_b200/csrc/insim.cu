@@ -183,6 +183,7 @@ namespace ifem
                               ? inner32.solve(ctx, utmp, unrm, dst_u, control.a_inv_rel, control.a_inv_max_it)
                               : bicgstab(ctx, vu, Auu, jac, utmp, dst_u, control.a_inv_rel * unrm, control.a_inv_max_it, pool_ainv);
       cur.a_inv_its += r.iterations;
+      timer_ms["A_inv block-Jacobi fallbacks (count)"] = (double)inner32.n_fallbacks; // readable through ifem_insim_timer_ms
     }
     cur.precond_applies++;
   }
@@ -263,6 +264,13 @@ namespace ifem
     LinOp A = [&](const double *x, double *y) { block_vmult(ctx, fs, x, y); };
     LinOp P = [&](const double *x, double *y) { precondition(x, y); };
     const SolveResult r = fgmres(ctx, va, A, P, fs.rhs.p, newton_update.p, tol, n_dofs_global, control.basis_size, pool_fgmres);
+    {
+      // the pin of the inexact inner solves: residual of the returned update under the fp64 operator
+      double *res = pool_fgmres.get(0, va.n_alloc);
+      block_vmult(ctx, fs, newton_update.p, res); // refreshes the ghost entries of its argument
+      axpby(ctx, va, 1.0, fs.rhs.p, -1.0, res);
+      cur.true_res = nrm > 0.0 ? nrm2(ctx, va, res) / nrm : 0.0;
+    }
     // constraints_used.distribute(newton_update)
     if (fs.n_con) set_indexed(ctx, fs.n_con, fs.d_con_idx.p, use_nonzero_constraints ? d_con_vals.p : nullptr, newton_update.p);
     return {(unsigned)r.iterations, r.residual};

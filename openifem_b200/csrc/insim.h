@@ -54,6 +54,7 @@ namespace ifem
     int gmres_its;
     double gmres_res;
     int cg_mp_its, cg_sm_its, a_inv_its, precond_applies;
+    double true_res; // |b - A x| / |b| recomputed with the fp64 operator after the solve
   };
 
   // Tolerances of the linear solvers; defaults = Fluid::MPI::InsIM

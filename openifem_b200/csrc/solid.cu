@@ -105,7 +105,7 @@ namespace ifem
 
     template <int DIM, int NPC>
     __global__ void update_qph_kernel(int n_cells, int nq, const int *__restrict__ cell_nodes, const double *__restrict__ G,
-                                      const double *__restrict__ u, int material, double c1, double kappa, double *__restrict__ Finv,
+                                      const double *__restrict__ u, int material, const double *__restrict__ cell_mat, double *__restrict__ Finv,
                                       double *__restrict__ tau, double *__restrict__ Jc, double *__restrict__ detF)
     {
       constexpr int NS = Voigt<DIM>::N;
@@ -128,6 +128,8 @@ namespace ifem
             }
         }
       double fi[DIM * DIM], ta[DIM * DIM], jc[NS * NS], dj;
+      // material of the cell: parameters of part cell->material_id() (mpi_hyper_elasticity.cpp:226-228)
+      const double c1 = cell_mat[2 * cell], kappa = cell_mat[2 * cell + 1];
       if (material == 0)
         neo_hookean_point<DIM>(gu, c1, kappa, fi, ta, jc, dj);
       else
@@ -781,13 +783,27 @@ namespace ifem
     // NeoHookean: (C1, kappa) of "Hyperelastic parameters"; Kirchhoff: (Young's modulus, Poisson's ratio) (mpi_hyper_elasticity.cpp:13-27)
     const bool kirchhoff = parameters.solid_type == "Kirchhoff";
     const int material = kirchhoff ? 1 : 0;
-    const double c1 = kirchhoff ? parameters.E[0] : parameters.C[0][0], kappa = kirchhoff ? parameters.nu[0] : parameters.C[0][1];
+    if ((int)d_cell_mat.n != 2 * ss.n_cells)
+      {
+        // (C1, kappa) or (E, nu) of every cell from its material id; one part: id 1 for all cells (:226-228)
+        std::vector<double> cm((size_t)2 * ss.n_cells);
+        const size_t n_parts = kirchhoff ? std::min(parameters.E.size(), parameters.nu.size()) : parameters.C.size();
+        for (int c = 0; c < ss.n_cells; ++c)
+          {
+            unsigned int mat_id = parameters.n_solid_parts == 1 ? 1u : (unsigned int)triangulation.material_id[c];
+            if (mat_id < 1 || mat_id > n_parts) throw std::runtime_error("HyperElasticity: no material parameters for material id " + std::to_string(mat_id));
+            if (!kirchhoff && parameters.C[mat_id - 1].size() < 2) throw std::runtime_error("HyperElasticity: NeoHookean needs two parameters per part");
+            cm[2 * c] = kirchhoff ? parameters.E[mat_id - 1] : parameters.C[mat_id - 1][0];
+            cm[2 * c + 1] = kirchhoff ? parameters.nu[mat_id - 1] : parameters.C[mat_id - 1][1];
+          }
+        d_cell_mat.upload(cm, ctx.stream);
+      }
     if (ss.dim == 2)
-      update_qph_kernel<2, 4><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, material, c1,
-                                                                           kappa, ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
+      update_qph_kernel<2, 4><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, material, d_cell_mat.p,
+                                                                           ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
     else
-      update_qph_kernel<3, 8><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, material, c1,
-                                                                           kappa, ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
+      update_qph_kernel<3, 8><<<(total + 127) / 128, 128, 0, ctx.stream>>>(ss.n_cells, ss.nq, ss.d_cell_nodes.p, ss.d_G.p, u, material, d_cell_mat.p,
+                                                                           ss.d_Finv.p, ss.d_tau.p, ss.d_Jc.p, ss.d_detF.p);
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches++;
   }

@@ -127,6 +127,9 @@ namespace ifem
     // SharedHyperElasticity::update_strain_and_stress (source/mpi_shared_hyper_elasticity.cpp:599-714): Cauchy stress
     // tau / J and deformation gradient F at the quadrature points, projected to the nodes and averaged
     void update_strain_and_stress() override;
+
+  private:
+    DevBuf<double> d_cell_mat; // [n_cells][2]: material parameters of every cell from its material id
   };
 
   // Solid::MPI::LinearElasticity<dim> (source/mpi_linear_elasticity.cpp; shared = false) and

@@ -224,14 +224,13 @@ class SolidBase:
 
 
 class HyperElasticity(SolidBase):
-    def __init__(self, mesh: fem.BoxMesh, params, verbose=False):
+    def __init__(self, mesh: fem.BoxMesh, params, verbose=False, material_id=None):
+        """material_id: cell->material_id() of every cell (1-based part number); None = part 1 everywhere. With
+        `Number of solid parts = 1` every cell uses part 1 whatever its id (mpi_hyper_elasticity.cpp:226-228)."""
         super().__init__(mesh, params, verbose)
         self.kirchhoff = params.solid_type == "Kirchhoff"  # PointHistory::setup (mpi_hyper_elasticity.cpp:8-35)
-        if self.kirchhoff:
-            self.young, self.poisson = params.E[0], params.nu[0]
-        else:
-            c = params.C[0]
-            self.c1, self.kappa = c[0], c[1]
+        ids = np.ones(mesh.n_cells, dtype=int) if material_id is None or params.n_solid_parts == 1 else np.asarray(material_id, dtype=int)
+        self.material_id = ids
         self.update_qph(self.cur_u)
 
     # -- update_qph (:241-275) ------------------------------------------------
@@ -239,10 +238,16 @@ class HyperElasticity(SolidBase):
         dim = self.dim
         ue = u[self.dofs.cell_dofs].reshape(self.mesh.n_cells, self.npc, dim)  # [c][a][comp]
         grad_u = np.einsum("cai,cqak->cqik", ue, self.G)
-        if self.kirchhoff:
-            self.F_inv, self.tau, self.Jc, self.detF = kirchhoff_update(grad_u, self.young, self.poisson)
-        else:
-            self.F_inv, self.tau, self.Jc, self.detF = neo_hookean_update(grad_u, self.c1, self.kappa)
+        nc, nq = grad_u.shape[:2]
+        self.F_inv, self.tau = np.empty((nc, nq, dim, dim)), np.empty((nc, nq, dim, dim))
+        self.Jc, self.detF = np.empty((nc, nq) + (dim,) * 4), np.empty((nc, nq))
+        for m in np.unique(self.material_id):  # the material of a point is that of its cell's part
+            sel = self.material_id == m
+            if self.kirchhoff:
+                out = kirchhoff_update(grad_u[sel], self.prm.E[m - 1], self.prm.nu[m - 1])
+            else:
+                out = neo_hookean_update(grad_u[sel], self.prm.C[m - 1][0], self.prm.C[m - 1][1])
+            self.F_inv[sel], self.tau[sel], self.Jc[sel], self.detF[sel] = out
 
     # -- SharedHyperElasticity::update_strain_and_stress (mpi_shared_hyper_elasticity.cpp:599-714) ------------
     def update_strain_and_stress(self):

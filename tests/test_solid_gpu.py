@@ -100,3 +100,46 @@ def test_update_strain_and_stress_matches_oracle(golden_dir, dim, reps, hi):
     g.update_strain_and_stress()
     assert _rel(g.get_nodal_tensor(0), stress) < 1e-12
     assert _rel(g.get_nodal_tensor(1), strain) < 1e-12
+
+
+def test_two_solid_parts_pick_the_material_of_the_cell(golden_dir, tmp_path):
+    """`Number of solid parts = 2`: every cell takes the (C1, kappa) of its material id (mpi_hyper_elasticity.cpp:226-228,
+    8-20) - the point history and the tangent matrix must follow the oracle with the same per-cell parts."""
+    import openifem_b200 as ifem
+    from oracle import fem, prm, solid
+
+    dim, reps, hi = 2, (8, 3), (8.0, 1.0)
+    text = open(os.path.join(golden_dir, "solid_beam_neohookean_2d.prm")).read()
+    c = prm.Params(os.path.join(golden_dir, "solid_beam_neohookean_2d.prm")).C[0]
+    import re
+    text, n = re.subn(r"set Hyperelastic parameters\s*=.*", f"set Hyperelastic parameters = {c[0]}, {c[1]}, {3.0 * c[0]}, {0.5 * c[1]}\n"
+                      "  set Number of solid parts = 2\n  set Viscosity = 0, 0", text)
+    assert n == 1
+    for key in ("Young's modulus", "Poisson's ratio"):
+        text, n = re.subn(rf"(set {key}\s*=\s*)([^\n,]+)\n", r"\1\2, \2\n", text)
+        assert n == 1
+    path = tmp_path / "two_parts.prm"
+    path.write_text(text)
+    mesh = fem.BoxMesh(reps, (0,) * dim, hi)
+    ids = np.where(mesh.vertices[mesh.cells].mean(axis=1)[:, 0] < 4.0, 1, 2).astype(np.int32)
+    o = solid.HyperElasticity(mesh, prm.Params(str(path)), material_id=ids)
+    tria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, hi, True)
+    tria.set_material_ids(ids)
+    g = ifem.Solid.MPI.HyperElasticity(tria, ifem.Parameters.AllParameters(str(path)))
+    g.setup()
+    u = 0.05 * np.random.default_rng(5).uniform(-1, 1, o.n)
+    o.cur_u = u.copy()
+    o.update_qph(u)
+    g.set_vector(g.CUR_U, u)
+    g.update_qph()
+    _, tau, _, _ = g.get_qph()
+    assert _rel(tau, o.tau.reshape(-1, dim, dim)) < 1e-12
+    A_ref, rhs_ref = o.assemble_system(False)
+    g.assemble_system(False)
+    assert sp.linalg.norm(g.get_matrix(0) - A_ref) / sp.linalg.norm(A_ref) < 1e-12
+    assert _rel(g.get_vector(g.SYSTEM_RHS), rhs_ref) < 1e-12
+    # and the two parts really differ: the same state with one part gives another stress
+    o1 = solid.HyperElasticity(mesh, prm.Params(os.path.join(golden_dir, "solid_beam_neohookean_2d.prm")))
+    o1.update_qph(u)
+    assert _rel(o1.tau, o.tau) > 1e-2

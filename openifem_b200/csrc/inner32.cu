@@ -929,7 +929,7 @@ namespace ifem
     peer_halo = false;
     if (!ctx.comm || ctx.comm->size < 2) return;
     PeerLink &link = peer_link(ctx);
-    if (!link.active) return;
+    if (!link.active || !(link.mask & 2)) return;
     const int size = link.size;
     // row of this rank: float offset of the segment that receives rank s's message (-1: not a neighbour), then an ok flag
     std::vector<int64_t> row((size_t)size + 1, -1);

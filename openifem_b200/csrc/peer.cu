@@ -102,8 +102,8 @@ namespace ifem
     size = ctx.comm ? ctx.comm->size : 1;
     active = false;
     if (size < 2 || size > kPeerMaxRanks) return;
-    if (const char *e = std::getenv("IFEM_PEER"))
-      if (std::atoi(e) == 0) return;
+    if (const char *e = std::getenv("IFEM_PEER")) mask = std::atoi(e) & 3;
+    if (mask == 0) return;
     active = true; // tentatively: alloc_shared clears it on any failure
     ll_peers = alloc_shared(ctx, sizeof(unsigned long long) * 2 * kPeerMaxRanks * kPeerWords);
     if (!active) return;
@@ -146,9 +146,10 @@ namespace ifem
     if (ctx.comm && ctx.comm->size > 1)
       {
         PeerLink &link = peer_link(ctx);
-        m.pd = link.dev();
-        m.nccl = !link.active;
-        m.adv = link.active ? 1 : 0;
+        const bool on = link.active && (link.mask & 1);
+        if (on) m.pd = link.dev();
+        m.nccl = !on;
+        m.adv = on ? 1 : 0;
       }
     return m;
   }

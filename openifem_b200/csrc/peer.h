@@ -38,6 +38,7 @@ namespace ifem
   {
     int rank = 0, size = 1;
     bool active = false;
+    int mask = 3; // IFEM_PEER: bit 0 = all-reduces through the link, bit 1 = halos through the link (0 switches the link off)
     unsigned long long *ll = nullptr; // own LL buffer (shared)
     unsigned int *epoch = nullptr;
     std::vector<void *> ll_peers;

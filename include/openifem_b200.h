@@ -36,6 +36,10 @@ int ifem_init(int device);
 int ifem_set_host_threads(int n);
 /* number of kernels launched by the library so far in this process */
 int ifem_kernel_launches(int64_t *count);
+/* collective self test of the peer-memory link between the ranks of one node (csrc/peer.h): shared buffers written by kernels of
+ * the peers and `rounds` in-kernel all-reduces of known values; *mismatches = 0 when everything arrived, -1 when the link is
+ * inactive (one rank, IPC unavailable, IFEM_PEER=0) */
+int ifem_peer_selftest(int rounds, int64_t *mismatches);
 
 /* ---- ranks: one process per GPU. Rank 0 creates the NCCL unique id, the launcher broadcasts the 128 bytes
  *      (torch.distributed / MPI / files) and every rank calls ifem_comm_init before creating solvers.

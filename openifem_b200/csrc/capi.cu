@@ -181,6 +181,14 @@ int ifem_kernel_launches(int64_t *count)
   });
 }
 
+int ifem_peer_selftest(int rounds, int64_t *mismatches)
+{
+  return guard([&] {
+    require_device();
+    *mismatches = peer_selftest(default_context(), rounds);
+  });
+}
+
 int ifem_comm_unique_id(unsigned char id[128])
 {
   return guard([&] { comm_get_unique_id(id); });

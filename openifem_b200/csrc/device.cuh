@@ -116,6 +116,39 @@ namespace ifem
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   }
+  // One bulk copy global -> shared through the TMA engine (cp.async.bulk, 1-D form) for tables every CTA stages once:
+  // thread 0 arms an mbarrier with the byte count and issues the copy, every thread waits on the barrier phase. dst, src and
+  // bytes must be multiples of 16; `bar` is an 8-byte shared-memory word of the CTA, used once (phase 0).
+  __device__ __forceinline__ void tma_stage_1d(void *smem_dst, const void *gmem_src, unsigned int bytes, unsigned long long *bar)
+  {
+#ifdef IFEM_EMULATED_DEVICE
+    for (unsigned int i = threadIdx.x; i < bytes / 8; i += blockDim.x)
+      static_cast<double *>(smem_dst)[i] = static_cast<const double *>(gmem_src)[i];
+    (void)bar;
+    __syncthreads();
+#else
+    const unsigned int bar_s = (unsigned int)__cvta_generic_to_shared(bar), dst_s = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    if (threadIdx.x == 0)
+      {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(gmem_src),
+                     "r"(bytes), "r"(bar_s)
+                     : "memory");
+      }
+    __syncthreads(); // the barrier is initialised before anybody polls it
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "IFEM_TMA_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                 "@p bra IFEM_TMA_DONE;\n"
+                 "bra IFEM_TMA_WAIT;\n"
+                 "IFEM_TMA_DONE:\n"
+                 "}" ::"r"(bar_s)
+                 : "memory");
+#endif
+  }
   // streaming (read-once) loads: keep the matrix stream from evicting x out of L2
   __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
   __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }

@@ -146,6 +146,13 @@ namespace ifem
       t.insert(t.end(), tab_geo.dN.begin(), tab_geo.dN.end());
       t.insert(t.end(), quad.weights.begin(), quad.weights.end());
       d_tables.upload(t, s);
+      std::vector<double> ts;
+      ts.insert(ts.end(), tab_u.N.begin(), tab_u.N.end());
+      ts.insert(ts.end(), tab_p.N.begin(), tab_p.N.end());
+      ts.insert(ts.end(), tab_geo.dN.begin(), tab_geo.dN.end());
+      ts.insert(ts.end(), quad.weights.begin(), quad.weights.end());
+      if (ts.size() % 2) ts.push_back(0.0);
+      d_tables_s.upload(ts, s);
       IFEM_CUDA(cudaStreamSynchronize(s));
     }
     A_uu.init(P_uu, dim, dim, s);
@@ -341,9 +348,10 @@ namespace ifem
   }
 
   // ===========================================================================
-  // INS cell assembly kernel: one cell per warp, cells of one colour per launch
-  // (no two cells of a colour share a velocity node, so the scatter is a plain
-  // read-modify-write and the result is bitwise reproducible).
+  // INS cell assembly kernel: one cell per team of warps (3-D: three warps, 2-D: one), cells of one colour per launch (no
+  // two cells of a colour share a velocity node, so the scatter is a plain read-modify-write and the result is bitwise
+  // reproducible). Shape values / pressure shape values / geometry gradients / weights are staged in shared memory by one
+  // TMA bulk copy per CTA; the per-cell scratch (physical gradients, fields at the quadrature points) is shared by the team.
   // ===========================================================================
   namespace
   {
@@ -355,19 +363,23 @@ namespace ifem
       static constexpr int NQ = NU;
       static constexpr int NV = 1 << DIM;
       static constexpr int DPC = NU * DIM + NP;
-      static constexpr int WARPS = DIM == 2 ? 8 : 5;
-      static constexpr int TAB = NQ * NU + NQ * NU * DIM + NQ * NP + NQ * NV * DIM + NQ; // doubles
+      // a TEAM of warps works on one cell (the cell's scratch in shared memory is shared by the team), CELLS cells per CTA
+      static constexpr int TEAM = DIM == 2 ? 1 : 3;
+      static constexpr int CELLS = DIM == 2 ? 8 : 3;
+      static constexpr int THREADS = TEAM * CELLS * 32;
+      static constexpr int MIN_CTAS = DIM == 2 ? 1 : 2;
+      static constexpr int TAB = NQ * NU + NQ * NU * DIM + NQ * NP + NQ * NV * DIM + NQ; // doubles, layout of FluidSpace::d_tables
+      static constexpr int STAB = (NQ * NU + NQ * NP + NQ * NV * DIM + NQ + 1) & ~1;     // staged in shared memory (d_tables_s)
     };
 
     template <int DIM>
-    struct WarpScratch
+    struct CellScratch
     {
       using T = InsT<DIM>;
       double g[T::NQ][T::NU][DIM]; // physical gradients of the velocity shape functions
-      double ug[T::NQ][T::NU];     // u(q) . grad N_b(q)
       double Jinv[T::NQ][DIM * DIM];
       double JxW[T::NQ];
-      double u[T::NQ][DIM], G[T::NQ][DIM * DIM], p[T::NQ], du[T::NQ][DIM], acc[T::NQ][DIM], divu[T::NQ];
+      double u[T::NQ][DIM], G[T::NQ][DIM * DIM], p[T::NQ], du[T::NQ][DIM], acc[T::NQ][DIM];
       double Ue[T::NU][DIM], Up[T::NU][DIM], Ua[T::NU][DIM], Pe[T::NP];
       double lrhs[T::DPC], ldiag[T::DPC], inh[T::DPC];
       int con[T::DPC];
@@ -386,7 +398,8 @@ namespace ifem
       const int *cell_list;
       const int *cell_un, *cell_pn;
       const double *cell_x;
-      const double *tables;
+      const double *tables;   // FluidSpace::d_tables (global: the reference gradients dN are read from here)
+      const double *tables_s; // FluidSpace::d_tables_s (staged in shared memory)
       const unsigned char *slots;
       const double *eval_pt, *present, *fsi_acc;
       const int *indicator;
@@ -425,329 +438,343 @@ namespace ifem
         }
     }
 
+    // The cells of a CTA move through the phases in lock step (every team reaches every barrier, also a team without a cell
+    // in the last round), so one CTA-wide barrier separates the phases; a single-warp team only needs the warp barrier.
+    template <int TEAM>
+    __device__ __forceinline__ void team_sync()
+    {
+      if (TEAM == 1)
+        __syncwarp();
+      else
+        __syncthreads();
+    }
+
+    // One cell per team of warps. Phases (tl = thread of the team, TT threads):
+    //   0  node ids, local dof values, constraints (items = local dofs) | geometry at the quadrature points (items = q)
+    //   2  physical gradients g[q][b][k]                                  (items = (q, b))
+    //   3  u, u - u_present, fsi acceleration, grad u, p at q             (items = (q, component))
+    //   4  local right-hand side, diag(M_u)                               (items = (node, component))
+    //   5  velocity-velocity blocks: lane = column node b, a warp takes three row nodes per pass; K accumulates over q in
+    //      registers and goes straight to the BCSR planes of its row (read-modify-write: cells of a colour share no node)
+    //   6  velocity-pressure coupling and M_p                             (items = (node, pressure node))
+    //   8  local rhs through the constraints
     template <int DIM>
-    __global__ void __launch_bounds__(InsT<DIM>::WARPS * 32) ins_assemble_kernel(const InsArgs a)
+    __global__ void __launch_bounds__(InsT<DIM>::THREADS, InsT<DIM>::MIN_CTAS) ins_assemble_kernel(const InsArgs a)
     {
       using T = InsT<DIM>;
-      constexpr int NU = T::NU, NP = T::NP, NQ = T::NQ, NV = T::NV;
+      constexpr int NU = T::NU, NP = T::NP, NQ = T::NQ, NV = T::NV, TEAM = T::TEAM, TT = T::TEAM * 32;
       extern __shared__ double smem[];
-      double *tN = smem;                    // [NQ][NU]
-      double *tdN = tN + NQ * NU;           // [NQ][NU][DIM]
-      double *tNp = tdN + NQ * NU * DIM;    // [NQ][NP]
-      double *tdG = tNp + NQ * NP;          // [NQ][NV][DIM]
-      double *tqw = tdG + NQ * NV * DIM;    // [NQ]
-      for (int i = threadIdx.x; i < T::TAB; i += blockDim.x) smem[i] = a.tables[i];
-      __syncthreads();
+      __shared__ unsigned long long tma_bar;
+      const double *tN = smem;                  // [NQ][NU]
+      const double *tNp = tN + NQ * NU;         // [NQ][NP]
+      const double *tdG = tNp + NQ * NP;        // [NQ][NV][DIM]
+      const double *tqw = tdG + NQ * NV * DIM;  // [NQ]
+      const double *tdN = a.tables + NQ * NU;   // [NQ][NU][DIM], global (phase 2 only)
+      tma_stage_1d(smem, a.tables_s, T::STAB * (unsigned int)sizeof(double), &tma_bar);
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      WarpScratch<DIM> &S = *reinterpret_cast<WarpScratch<DIM> *>(smem + ((T::TAB + 1) & ~1) + (size_t)warp * (sizeof(WarpScratch<DIM>) / 8));
+      const int team = warp / TEAM, tw = warp % TEAM, tl = tw * 32 + lane;
+      CellScratch<DIM> &S = *reinterpret_cast<CellScratch<DIM> *>(smem + T::STAB + (size_t)team * ((sizeof(CellScratch<DIM>) + 7) / 8));
       const double mu = a.mu, rho = a.rho, gam_rho = a.gamma * a.rho, rho_dt = a.rho * a.inv_dt;
       const double rho_conv = a.explicit_convection ? 0.0 : a.rho; // matrix side of the convection terms
       constexpr int SPC = NU * NU + 2 * NU * NP + NP * NP;
 
-      for (int li = blockIdx.x * T::WARPS + warp; li < a.n_list; li += gridDim.x * T::WARPS)
+      for (int base_li = blockIdx.x * T::CELLS; base_li < a.n_list; base_li += gridDim.x * T::CELLS)
         {
-          const int cell = a.cell_list[li];
-          const int ind = a.indicator ? a.indicator[cell] : 0;
-          // ---- phase 0: cell tables and local dof values ----
-          if (lane < NU) S.un[lane] = a.cell_un[(int64_t)cell * NU + lane];
-          if (lane < NP) S.pn[lane] = a.cell_pn[(int64_t)cell * NP + lane];
-          __syncwarp();
-          for (int i = lane; i < NU * DIM; i += 32)
+          const int li = base_li + team;
+          const bool active = li < a.n_list;
+          const int cell = active ? a.cell_list[li] : 0;
+          const int ind = (active && a.indicator) ? a.indicator[cell] : 0;
+          const unsigned char *slots = a.slots + (int64_t)cell * SPC;
+          // ---- phase 0: node ids | geometry at the quadrature points ----
+          if (active)
             {
-              const int b = i / DIM, c = i % DIM;
-              const int64_t g = (int64_t)DIM * S.un[b] + c;
-              S.Ue[b][c] = a.eval_pt[g];
-              S.Up[b][c] = a.present[g];
-              S.Ua[b][c] = (ind && a.fsi_acc) ? a.fsi_acc[g] : 0.0;
-              const int cf = a.con[g];
-              S.con[i] = cf;
-              S.inh[i] = (cf && a.inhom) ? a.inhom[g] : 0.0;
-              S.lrhs[i] = 0.0;
-              S.ldiag[i] = 0.0;
-            }
-          if (lane < NP)
-            {
-              const int64_t g = a.n_u + S.pn[lane];
-              S.Pe[lane] = a.eval_pt[g];
-              const int cf = a.con[g];
-              S.con[NU * DIM + lane] = cf;
-              S.inh[NU * DIM + lane] = (cf && a.inhom) ? a.inhom[g] : 0.0;
-              S.lrhs[NU * DIM + lane] = 0.0;
-              S.ldiag[NU * DIM + lane] = 0.0;
-            }
-          // ---- phase 1: geometry at the quadrature points (lane = q) ----
-          if (lane < NQ)
-            {
-              const int q = lane;
-              const double *X = a.cell_x + (int64_t)cell * NV * DIM;
-              double J[DIM * DIM];
-#pragma unroll
-              for (int i = 0; i < DIM * DIM; ++i) J[i] = 0.0;
-              for (int v = 0; v < NV; ++v)
-#pragma unroll
-                for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                  for (int j = 0; j < DIM; ++j) J[i * DIM + j] = fma(X[v * DIM + i], tdG[(q * NV + v) * DIM + j], J[i * DIM + j]);
-              double Ji[DIM * DIM], det;
-              invert<DIM>(J, Ji, det);
-#pragma unroll
-              for (int i = 0; i < DIM * DIM; ++i) S.Jinv[q][i] = Ji[i];
-              S.JxW[q] = det * tqw[q];
-            }
-          __syncwarp();
-          // ---- phase 2: physical gradients g[q][b][k] = sum_j dN[q][b][j] Jinv[j][k] (lane = b) ----
-          if (lane < NU)
-            for (int q = 0; q < NQ; ++q)
-              {
-                double r[DIM];
-#pragma unroll
-                for (int j = 0; j < DIM; ++j) r[j] = tdN[(q * NU + lane) * DIM + j];
-#pragma unroll
-                for (int k = 0; k < DIM; ++k)
-                  {
-                    double s = 0.0;
-#pragma unroll
-                    for (int j = 0; j < DIM; ++j) s = fma(r[j], S.Jinv[q][j * DIM + k], s);
-                    S.g[q][lane][k] = s;
-                  }
-              }
-          __syncwarp();
-          // ---- phase 3: field values at q (lane = q): get_function_values / gradients (:219-232) ----
-          if (lane < NQ)
-            {
-              const int q = lane;
-              double u[DIM], up[DIM], ac[DIM], G[DIM * DIM], p = 0.0;
-#pragma unroll
-              for (int c = 0; c < DIM; ++c) u[c] = up[c] = ac[c] = 0.0;
-#pragma unroll
-              for (int i = 0; i < DIM * DIM; ++i) G[i] = 0.0;
-              for (int b = 0; b < NU; ++b)
+              if (tl < NU) S.un[tl] = a.cell_un[(int64_t)cell * NU + tl];
+              if (tl < NP) S.pn[tl] = a.cell_pn[(int64_t)cell * NP + tl];
+              // the last warp of the team takes the geometry (one lane per quadrature point)
+              if (tw == TEAM - 1 && lane < NQ)
                 {
-                  const double N = tN[q * NU + b];
+                  const int q = lane;
+                  const double *X = a.cell_x + (int64_t)cell * NV * DIM;
+                  double J[DIM * DIM];
 #pragma unroll
-                  for (int c = 0; c < DIM; ++c)
+                  for (int i = 0; i < DIM * DIM; ++i) J[i] = 0.0;
+                  for (int v = 0; v < NV; ++v)
+#pragma unroll
+                    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                      for (int j = 0; j < DIM; ++j) J[i * DIM + j] = fma(X[v * DIM + i], tdG[(q * NV + v) * DIM + j], J[i * DIM + j]);
+                  double Ji[DIM * DIM], det;
+                  invert<DIM>(J, Ji, det);
+#pragma unroll
+                  for (int i = 0; i < DIM * DIM; ++i) S.Jinv[q][i] = Ji[i];
+                  S.JxW[q] = det * tqw[q];
+                }
+            }
+          team_sync<TEAM>();
+          // ---- phase 1: local dof values and constraints | phase 2: physical gradients ----
+          if (active)
+            {
+              for (int i = tl; i < NU * DIM; i += TT)
+                {
+                  const int b = i / DIM, c = i % DIM;
+                  const int64_t g = (int64_t)DIM * S.un[b] + c;
+                  S.Ue[b][c] = a.eval_pt[g];
+                  S.Up[b][c] = a.present[g];
+                  S.Ua[b][c] = (ind && a.fsi_acc) ? a.fsi_acc[g] : 0.0;
+                  const int cf = a.con[g];
+                  S.con[i] = cf;
+                  S.inh[i] = (cf && a.inhom) ? a.inhom[g] : 0.0;
+                  S.lrhs[i] = 0.0;
+                  S.ldiag[i] = 0.0;
+                }
+              if (tl < NP)
+                {
+                  const int64_t g = a.n_u + S.pn[tl];
+                  S.Pe[tl] = a.eval_pt[g];
+                  const int cf = a.con[g];
+                  S.con[NU * DIM + tl] = cf;
+                  S.inh[NU * DIM + tl] = (cf && a.inhom) ? a.inhom[g] : 0.0;
+                  S.lrhs[NU * DIM + tl] = 0.0;
+                  S.ldiag[NU * DIM + tl] = 0.0;
+                }
+              // g[q][b][k] = sum_j dN[q][b][j] Jinv[q][j][k]
+              for (int i = tl; i < NQ * NU; i += TT)
+                {
+                  const int q = i / NU;
+                  double r[DIM];
+#pragma unroll
+                  for (int j = 0; j < DIM; ++j) r[j] = __ldg(tdN + (size_t)i * DIM + j);
+#pragma unroll
+                  for (int k = 0; k < DIM; ++k)
                     {
-                      const double ue = S.Ue[b][c];
-                      u[c] = fma(N, ue, u[c]);
-                      up[c] = fma(N, S.Up[b][c], up[c]);
-                      ac[c] = fma(N, S.Ua[b][c], ac[c]);
+                      double s = 0.0;
 #pragma unroll
-                      for (int k = 0; k < DIM; ++k) G[c * DIM + k] = fma(ue, S.g[q][b][k], G[c * DIM + k]);
+                      for (int j = 0; j < DIM; ++j) s = fma(r[j], S.Jinv[q][j * DIM + k], s);
+                      (&S.g[0][0][0])[(size_t)i * DIM + k] = s;
                     }
                 }
-              for (int j = 0; j < NP; ++j) p = fma(tNp[q * NP + j], S.Pe[j], p);
-              double div = 0.0;
-#pragma unroll
-              for (int c = 0; c < DIM; ++c)
-                {
-                  S.u[q][c] = u[c];
-                  S.du[q][c] = u[c] - up[c];
-                  S.acc[q][c] = ac[c];
-                  div += G[c * DIM + c];
-                }
-#pragma unroll
-              for (int i = 0; i < DIM * DIM; ++i) S.G[q][i] = G[i];
-              S.p[q] = p;
-              S.divu[q] = div;
             }
-          __syncwarp();
-          if (lane < NU)
-            for (int q = 0; q < NQ; ++q)
-              {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < DIM; ++k) s = fma(S.u[q][k], S.g[q][lane][k], s);
-                S.ug[q][lane] = s;
-              }
-          __syncwarp();
-          // ---- phase 4: local rhs (:281-304) and diag(M_u) (lane = a), pressure rows (lane = j) ----
-          if (lane < NU)
+          team_sync<TEAM>();
+          // ---- phase 3: field values at q: get_function_values / gradients (:219-232), one item per (q, component) ----
+          if (active)
             {
-              const int aN = lane;
-              double r[DIM], m = 0.0;
-#pragma unroll
-              for (int c = 0; c < DIM; ++c) r[c] = 0.0;
-              for (int q = 0; q < NQ; ++q)
+              for (int i = tl; i < NQ * DIM; i += TT)
                 {
-                  const double w = S.JxW[q], N = tN[q * NU + aN];
-                  m = fma(w * N, N, m);
-                  double ga[DIM];
+                  const int q = i / DIM, c = i % DIM;
+                  double u = 0.0, up = 0.0, ac = 0.0, G[DIM];
 #pragma unroll
-                  for (int k = 0; k < DIM; ++k) ga[k] = S.g[q][aN][k];
-                  const double pd = S.p[q] - gam_rho * S.divu[q];
-#pragma unroll
-                  for (int c = 0; c < DIM; ++c)
+                  for (int k = 0; k < DIM; ++k) G[k] = 0.0;
+                  for (int b = 0; b < NU; ++b)
                     {
+                      const double N = tN[q * NU + b];
+                      const double ue = S.Ue[b][c];
+                      u = fma(N, ue, u);
+                      up = fma(N, S.Up[b][c], up);
+                      ac = fma(N, S.Ua[b][c], ac);
+#pragma unroll
+                      for (int k = 0; k < DIM; ++k) G[k] = fma(ue, S.g[q][b][k], G[k]);
+                    }
+                  S.u[q][c] = u;
+                  S.du[q][c] = u - up;
+                  S.acc[q][c] = ac;
+#pragma unroll
+                  for (int k = 0; k < DIM; ++k) S.G[q][c * DIM + k] = G[k];
+                }
+              // pressure at q (the items above leave the tail of the last pass idle: give it to the threads from the end)
+              for (int i = TT - 1 - tl; i < NQ; i += TT)
+                {
+                  double p = 0.0;
+                  for (int j = 0; j < NP; ++j) p = fma(tNp[i * NP + j], S.Pe[j], p);
+                  S.p[i] = p;
+                }
+            }
+          team_sync<TEAM>();
+          // ---- phase 4: local rhs (:281-304) and diag(M_u), one item per (node, component); pressure rows ----
+          if (active)
+            {
+              for (int i = tl; i < NU * DIM; i += TT)
+                {
+                  const int aN = i / DIM, c = i % DIM;
+                  double r = 0.0, m = 0.0;
+                  for (int q = 0; q < NQ; ++q)
+                    {
+                      const double w = S.JxW[q], N = tN[q * NU + aN];
+                      m = fma(w * N, N, m);
+                      double div = 0.0;
+#pragma unroll
+                      for (int k = 0; k < DIM; ++k) div += S.G[q][k * DIM + k];
+                      const double pd = S.p[q] - gam_rho * div;
                       double t = 0.0, conv = 0.0;
 #pragma unroll
                       for (int k = 0; k < DIM; ++k)
                         {
-                          t = fma(S.G[q][c * DIM + k], ga[k], t);         // grad u : grad phi_i
-                          conv = fma(S.G[q][c * DIM + k], S.u[q][k], conv); // (grad u) u
+                          t = fma(S.G[q][c * DIM + k], S.g[q][aN][k], t);    // grad u : grad phi_i
+                          conv = fma(S.G[q][c * DIM + k], S.u[q][k], conv);  // (grad u) u
                         }
-                      double v = -mu * t + pd * ga[c] + N * (-rho * conv - rho_dt * S.du[q][c] + rho * a.grav[c]);
+                      double v = -mu * t + pd * S.g[q][aN][c] + N * (-rho * conv - rho_dt * S.du[q][c] + rho * a.grav[c]);
                       if (ind == 1) v += rho * S.acc[q][c] * N;
-                      r[c] = fma(w, v, r[c]);
+                      r = fma(w, v, r);
                     }
+                  S.lrhs[i] = r;
+                  if (a.assemble_mass && S.un[aN] < a.lim_diag) a.diag_Mu[(int64_t)DIM * S.un[aN] + c] += m;
                 }
-#pragma unroll
-              for (int c = 0; c < DIM; ++c) S.lrhs[aN * DIM + c] = r[c];
-              if (a.assemble_mass && S.un[aN] < a.lim_diag)
+              for (int i = TT - 1 - tl; i < NP; i += TT)
                 {
-#pragma unroll
-                  for (int c = 0; c < DIM; ++c) a.diag_Mu[(int64_t)DIM * S.un[aN] + c] += m;
-                }
-            }
-          if (lane < NP)
-            {
-              double r = 0.0;
-              for (int q = 0; q < NQ; ++q) r = fma(S.JxW[q] * S.divu[q], tNp[q * NP + lane], r);
-              S.lrhs[NU * DIM + lane] = r;
-            }
-          __syncwarp();
-          const unsigned char *slots = a.slots + (int64_t)cell * SPC;
-          // ---- phase 5: velocity-velocity blocks (:263-273), lane = column node b, 3 row nodes per pass ----
-          if (a.do_uu && !a.rhs_only)
-          {
-            const int b = lane < NU ? lane : NU - 1;
-            int cb[DIM];
-            double ib[DIM];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d)
-              {
-                cb[d] = S.con[b * DIM + d];
-                ib[d] = S.inh[b * DIM + d];
-              }
-            constexpr int TA = 3;
-            for (int a0 = 0; a0 < NU; a0 += TA)
-              {
-                double K[TA][DIM * DIM];
-#pragma unroll
-                for (int t = 0; t < TA; ++t)
-#pragma unroll
-                  for (int i = 0; i < DIM * DIM; ++i) K[t][i] = 0.0;
-                for (int q = 0; q < NQ; ++q)
-                  {
-                    const double w = S.JxW[q];
-                    const double Nb = tN[q * NU + b], ugb = S.ug[q][b];
-                    double gb[DIM], wG[DIM * DIM];
-#pragma unroll
-                    for (int k = 0; k < DIM; ++k) gb[k] = S.g[q][b][k];
-#pragma unroll
-                    for (int i = 0; i < DIM * DIM; ++i) wG[i] = w * rho_conv * S.G[q][i];
-                    const double c1 = w * rho_conv * ugb, c2 = w * rho_dt * Nb;
-#pragma unroll
-                    for (int t = 0; t < TA; ++t)
-                      {
-                        const int aN = a0 + t;
-                        const double Na = tN[q * NU + aN];
-                        double ga[DIM];
-#pragma unroll
-                        for (int k = 0; k < DIM; ++k) ga[k] = S.g[q][aN][k];
-                        double gg = 0.0;
-#pragma unroll
-                        for (int k = 0; k < DIM; ++k) gg = fma(ga[k], gb[k], gg);
-                        const double s = fma(w * mu, gg, Na * (c1 + c2));
-                        const double NaNb = Na * Nb;
-#pragma unroll
-                        for (int c = 0; c < DIM; ++c)
-                          {
-                            const double wga = w * gam_rho * ga[c];
-#pragma unroll
-                            for (int d = 0; d < DIM; ++d)
-                              {
-                                double v = fma(NaNb, wG[c * DIM + d], wga * gb[d]);
-                                if (c == d) v += s;
-                                K[t][c * DIM + d] += v;
-                              }
-                          }
-                      }
-                  }
-                // scatter the TA x (DIM x DIM) blocks of this lane
-#pragma unroll
-                for (int t = 0; t < TA; ++t)
-                  {
-                    const int aN = a0 + t;
-                    const int A = S.un[aN];
-                    if (A >= a.n_owned_u) continue; // warp-uniform
-                    const int64_t rp = a.uu.rowptr[A];
-                    const int nb = (int)(a.uu.rowptr[A + 1] - rp);
-                    double *base = a.uu.val + rp * (DIM * DIM);
-                    const int slot = slots[aN * NU + b];
-                    double corr[DIM];
-#pragma unroll
-                    for (int c = 0; c < DIM; ++c) corr[c] = 0.0;
-                    if (lane < NU)
-                      {
-#pragma unroll
-                        for (int c = 0; c < DIM; ++c)
-                          {
-                            const int rc = S.con[aN * DIM + c];
-#pragma unroll
-                            for (int d = 0; d < DIM; ++d)
-                              {
-                                const double v = K[t][c * DIM + d];
-                                if (rc)
-                                  {
-                                    if (b == aN && c == d)
-                                      {
-                                        base[(int64_t)(c * DIM + d) * nb + slot] += fabs(v);
-                                        S.ldiag[aN * DIM + c] = fabs(v);
-                                      }
-                                  }
-                                else if (cb[d])
-                                  corr[c] = fma(v, ib[d], corr[c]);
-                                else
-                                  base[(int64_t)(c * DIM + d) * nb + slot] += v;
-                              }
-                          }
-                      }
-                    if (a.inhom)
-                      {
-#pragma unroll
-                        for (int c = 0; c < DIM; ++c)
-                          {
-                            const double sc = warp_sum(corr[c]);
-                            if (lane == 0) S.lrhs[aN * DIM + c] -= sc;
-                          }
-                      }
-                  }
-              }
-          }
-          __syncwarp();
-          // ---- phase 6: velocity-pressure coupling  -div(phi_i) psi_j  and its transpose (lane = a) ----
-          if (lane < NU && !a.rhs_only)
-            {
-              const int aN = lane;
-              double B[NP][DIM];
-#pragma unroll
-              for (int j = 0; j < NP; ++j)
-#pragma unroll
-                for (int c = 0; c < DIM; ++c) B[j][c] = 0.0;
-              for (int q = 0; q < NQ; ++q)
-                {
-                  const double w = -S.JxW[q];
-                  double ga[DIM];
-#pragma unroll
-                  for (int k = 0; k < DIM; ++k) ga[k] = w * S.g[q][aN][k];
-#pragma unroll
-                  for (int j = 0; j < NP; ++j)
+                  double r = 0.0;
+                  for (int q = 0; q < NQ; ++q)
                     {
-                      const double psi = tNp[q * NP + j];
+                      double div = 0.0;
 #pragma unroll
-                      for (int c = 0; c < DIM; ++c) B[j][c] = fma(ga[c], psi, B[j][c]);
+                      for (int k = 0; k < DIM; ++k) div += S.G[q][k * DIM + k];
+                      r = fma(S.JxW[q] * div, tNp[q * NP + i], r);
+                    }
+                  S.lrhs[NU * DIM + i] = r;
+                }
+            }
+          team_sync<TEAM>();
+          // ---- phase 5: velocity-velocity blocks (:263-273), lane = column node b, 3 row nodes per pass and warp ----
+          //   K_ab[c][d] = sum_q  delta_cd (w mu ga.gb + Na (w rho u.gb + w rho/dt Nb)) + (Na Nb) (w rho G[c][d]) + ga[c] (w gamma rho gb[d])
+          if (active && a.do_uu && !a.rhs_only)
+            {
+              const int b = lane < NU ? lane : NU - 1;
+              int cb[DIM];
+              double ib[DIM];
+#pragma unroll
+              for (int d = 0; d < DIM; ++d)
+                {
+                  cb[d] = S.con[b * DIM + d];
+                  ib[d] = S.inh[b * DIM + d];
+                }
+              constexpr int TA = 3;
+              for (int a0 = tw * TA; a0 < NU; a0 += TEAM * TA)
+                {
+                  double K[TA][DIM * DIM], sK[TA];
+#pragma unroll
+                  for (int t = 0; t < TA; ++t)
+                    {
+                      sK[t] = 0.0;
+#pragma unroll
+                      for (int i = 0; i < DIM * DIM; ++i) K[t][i] = 0.0;
+                    }
+                  for (int q = 0; q < NQ; ++q)
+                    {
+                      const double w = S.JxW[q];
+                      const double Nb = tN[q * NU + b];
+                      double gb[DIM], wmg[DIM], wgg[DIM], wG[DIM * DIM];
+                      double ugb = 0.0;
+#pragma unroll
+                      for (int k = 0; k < DIM; ++k)
+                        {
+                          gb[k] = S.g[q][b][k];
+                          ugb = fma(S.u[q][k], gb[k], ugb);
+                        }
+                      const double wm = w * mu, wg = w * gam_rho, wr = w * rho_conv;
+#pragma unroll
+                      for (int k = 0; k < DIM; ++k)
+                        {
+                          wmg[k] = wm * gb[k];
+                          wgg[k] = wg * gb[k];
+                        }
+#pragma unroll
+                      for (int i = 0; i < DIM * DIM; ++i) wG[i] = wr * S.G[q][i];
+                      const double c12 = fma(wr, ugb, w * rho_dt * Nb);
+#pragma unroll
+                      for (int t = 0; t < TA; ++t)
+                        {
+                          const int aN = a0 + t;
+                          const double Na = tN[q * NU + aN];
+                          double ga[DIM];
+#pragma unroll
+                          for (int k = 0; k < DIM; ++k) ga[k] = S.g[q][aN][k];
+                          double s = fma(Na, c12, sK[t]);
+#pragma unroll
+                          for (int k = 0; k < DIM; ++k) s = fma(ga[k], wmg[k], s);
+                          sK[t] = s;
+                          const double NaNb = Na * Nb;
+#pragma unroll
+                          for (int c = 0; c < DIM; ++c)
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d)
+                              K[t][c * DIM + d] = fma(ga[c], wgg[d], fma(NaNb, wG[c * DIM + d], K[t][c * DIM + d]));
+                        }
+                    }
+                  // scatter the TA x (DIM x DIM) blocks of this lane
+#pragma unroll
+                  for (int t = 0; t < TA; ++t)
+                    {
+                      const int aN = a0 + t;
+                      const int A = S.un[aN];
+                      if (A >= a.n_owned_u) continue; // warp-uniform
+#pragma unroll
+                      for (int c = 0; c < DIM; ++c) K[t][c * DIM + c] += sK[t];
+                      const int64_t rp = a.uu.rowptr[A];
+                      const int nb = (int)(a.uu.rowptr[A + 1] - rp);
+                      double *base = a.uu.val + rp * (DIM * DIM);
+                      const int slot = slots[aN * NU + b];
+                      double corr[DIM];
+#pragma unroll
+                      for (int c = 0; c < DIM; ++c) corr[c] = 0.0;
+                      if (lane < NU)
+                        {
+#pragma unroll
+                          for (int c = 0; c < DIM; ++c)
+                            {
+                              const int rc = S.con[aN * DIM + c];
+#pragma unroll
+                              for (int d = 0; d < DIM; ++d)
+                                {
+                                  const double v = K[t][c * DIM + d];
+                                  if (rc)
+                                    {
+                                      if (b == aN && c == d)
+                                        {
+                                          base[(int64_t)(c * DIM + d) * nb + slot] += fabs(v);
+                                          S.ldiag[aN * DIM + c] = fabs(v);
+                                        }
+                                    }
+                                  else if (cb[d])
+                                    corr[c] = fma(v, ib[d], corr[c]);
+                                  else
+                                    base[(int64_t)(c * DIM + d) * nb + slot] += v;
+                                }
+                            }
+                        }
+                      if (a.inhom)
+                        {
+#pragma unroll
+                          for (int c = 0; c < DIM; ++c)
+                            {
+                              const double sc = warp_sum(corr[c]);
+                              if (lane == 0) S.lrhs[aN * DIM + c] -= sc;
+                            }
+                        }
                     }
                 }
-              const int A = S.un[aN];
-              const bool own_row = A < a.lim_up;
-              const int64_t rp = own_row ? a.up.rowptr[A] : 0;
-              const int nb = own_row ? (int)(a.up.rowptr[A + 1] - rp) : 0;
-              double *base = a.up.val + rp * DIM;
+            }
+          team_sync<TEAM>();
+          // ---- phase 6: velocity-pressure coupling  -div(phi_i) psi_j  and its transpose, one item per (a, j);
+          //      phase 7: pressure mass matrix (:274-276), one item per (i, j) ----
+          if (active && !a.rhs_only)
+            {
               const unsigned char *s_up = slots + NU * NU;
               const unsigned char *s_pu = slots + NU * NU + NU * NP;
-#pragma unroll
-              for (int j = 0; j < NP; ++j)
+              for (int i = tl; i < NU * NP; i += TT)
                 {
+                  const int aN = i / NP, j = i % NP;
+                  double B[DIM];
+#pragma unroll
+                  for (int c = 0; c < DIM; ++c) B[c] = 0.0;
+                  for (int q = 0; q < NQ; ++q)
+                    {
+                      const double wpsi = -S.JxW[q] * tNp[q * NP + j];
+#pragma unroll
+                      for (int c = 0; c < DIM; ++c) B[c] = fma(wpsi, S.g[q][aN][c], B[c]);
+                    }
+                  const int A = S.un[aN];
+                  const bool own_row = A < a.lim_up;
+                  const int64_t rp = own_row ? a.up.rowptr[A] : 0;
+                  const int nb = own_row ? (int)(a.up.rowptr[A + 1] - rp) : 0;
+                  double *base = a.up.val + rp * DIM;
                   const int slot = s_up[aN * NP + j];
                   const int pc = S.con[NU * DIM + j];
                   // row = pressure node j, column = velocity node a
@@ -761,7 +788,7 @@ namespace ifem
                   for (int c = 0; c < DIM; ++c)
                     {
                       const int uc = S.con[aN * DIM + c];
-                      const double v = B[j][c];
+                      const double v = B[c];
                       if (!uc && !pc)
                         {
                           if (own_row) base[(int64_t)c * nb + slot] += v;   // A_up block row a, plane c
@@ -771,34 +798,32 @@ namespace ifem
                         atomicAdd(&S.lrhs[NU * DIM + j], -v * S.inh[aN * DIM + c]); // column (a,c) constrained
                     }
                 }
+              if (a.assemble_mass && a.do_rhs)
+                for (int e = TT - 1 - tl; e < NP * NP; e += TT)
+                  {
+                    const int i = e / NP, j = e % NP;
+                    double m = 0.0;
+                    for (int q = 0; q < NQ; ++q) m = fma(S.JxW[q] * tNp[q * NP + i], tNp[q * NP + j], m);
+                    const int Pn = S.pn[i];
+                    if (Pn >= a.n_owned_p) continue;
+                    const int64_t rp = a.mp.rowptr[Pn];
+                    a.mp.val[rp + slots[NU * NU + 2 * NU * NP + e]] += m;
+                  }
             }
-          __syncwarp();
-          // ---- phase 7: pressure mass matrix (:274-276) ----
-          if (a.assemble_mass && a.do_rhs)
-            for (int e = lane; e < NP * NP; e += 32)
-              {
-                const int i = e / NP, j = e % NP;
-                double m = 0.0;
-                for (int q = 0; q < NQ; ++q) m = fma(S.JxW[q] * tNp[q * NP + i], tNp[q * NP + j], m);
-                const int Pn = S.pn[i];
-                if (Pn >= a.n_owned_p) continue;
-                const int64_t rp = a.mp.rowptr[Pn];
-                a.mp.val[rp + slots[NU * NU + 2 * NU * NP + e]] += m;
-              }
-          __syncwarp();
+          team_sync<TEAM>();
           // ---- scatter local rhs through the constraints (distribute_local_to_global) ----
-          if (a.do_rhs)
-          for (int i = lane; i < T::DPC; i += 32)
-            {
-              const bool own = i < NU * DIM ? S.un[i / DIM] < a.n_owned_u : S.pn[i - NU * DIM] < a.n_owned_p;
-              if (!own) continue;
-              const int64_t g = i < NU * DIM ? (int64_t)DIM * S.un[i / DIM] + i % DIM : a.n_u + S.pn[i - NU * DIM];
-              if (!S.con[i])
-                a.rhs[g] += S.lrhs[i];
-              else if (a.inhom)
-                a.rhs[g] += S.ldiag[i] * S.inh[i];
-            }
-          __syncwarp();
+          if (active && a.do_rhs)
+            for (int i = tl; i < T::DPC; i += TT)
+              {
+                const bool own = i < NU * DIM ? S.un[i / DIM] < a.n_owned_u : S.pn[i - NU * DIM] < a.n_owned_p;
+                if (!own) continue;
+                const int64_t g = i < NU * DIM ? (int64_t)DIM * S.un[i / DIM] + i % DIM : a.n_u + S.pn[i - NU * DIM];
+                if (!S.con[i])
+                  a.rhs[g] += S.lrhs[i];
+                else if (a.inhom)
+                  a.rhs[g] += S.ldiag[i] * S.inh[i];
+              }
+          team_sync<TEAM>();
         }
     }
 
@@ -900,6 +925,7 @@ namespace ifem
     a.cell_pn = fs.d_cell_pn.p;
     a.cell_x = fs.d_cell_x.p;
     a.tables = fs.d_tables.p;
+    a.tables_s = fs.d_tables_s.p;
     a.slots = fs.d_slots.p;
     a.eval_pt = eval_pt;
     a.present = present;
@@ -928,7 +954,7 @@ namespace ifem
     a.diag_Mu = fs.diag_Mu.p;
     a.rhs = fs.rhs.p;
     a.assemble_mass = assemble_mass ? 1 : 0;
-    const size_t smem = (size_t)((T::TAB + 1) & ~1) * 8 + (size_t)T::WARPS * sizeof(WarpScratch<DIM>);
+    const size_t smem = (size_t)T::STAB * 8 + (size_t)T::CELLS * (((sizeof(CellScratch<DIM>) + 7) / 8) * 8);
     static bool attr_set[4] = {false, false, false, false};
     if (!attr_set[DIM])
       {
@@ -942,8 +968,9 @@ namespace ifem
         a.n_list = schur_pass ? fs.colour_offsets[k + 1] - fs.colour_offsets[k] : fs.colour_n1[k];
         a.cell_list = fs.d_colour_order.p + fs.colour_offsets[k];
         if (a.n_list == 0) continue;
-        const int blocks = std::min((a.n_list + T::WARPS - 1) / T::WARPS, ctx.sm_count * (DIM == 2 ? 4 : 1));
-        ins_assemble_kernel<DIM><<<blocks, T::WARPS * 32, smem, s>>>(a);
+        // persistent CTAs: as many as fit on the device at once (shared memory bound), each loops over its share of the colour
+        const int blocks = std::min((a.n_list + T::CELLS - 1) / T::CELLS, ctx.sm_count * (DIM == 2 ? 4 : T::MIN_CTAS));
+        ins_assemble_kernel<DIM><<<blocks, T::THREADS, smem, s>>>(a);
         IFEM_KERNEL_CHECK();
         ctx.kernel_launches++;
       }

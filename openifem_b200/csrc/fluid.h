@@ -60,6 +60,7 @@ namespace ifem
     DevBuf<int> d_cell_un, d_cell_pn, d_colour_order;
     DevBuf<double> d_cell_x;  // [n_cells][nv][dim]
     DevBuf<double> d_tables;  // N[nq][nu] | dN[nq][nu][dim] | Np[nq][np] | dNgeo[nq][nv][dim] | qw[nq]
+    DevBuf<double> d_tables_s; // what the INS assembly stages in shared memory (one TMA bulk copy): N | Np | dNgeo | qw, padded to 16 B
     DevBuf<unsigned char> d_slots; // per cell: uu[nu][nu] | up[nu][np] | pu[np][nu] | pp[np][np]
     DevBuf<unsigned char> d_con;
     DevBuf<double> d_nonzero_val;

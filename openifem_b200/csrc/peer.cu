@@ -1,10 +1,12 @@
 #include "peer.h"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 
 #include "comm.h"
+#include "peer_dev.cuh"
 
 namespace ifem
 {
@@ -152,5 +154,128 @@ namespace ifem
         m.adv = on ? 1 : 0;
       }
     return m;
+  }
+} // namespace ifem
+
+namespace ifem
+{
+  namespace
+  {
+    // dst[off + i] = tag + i
+    __global__ void selftest_write_kernel(float *dst, int64_t off, int64_t n, float tag)
+    {
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[off + i] = tag + (float)(i % 1024);
+    }
+    __global__ void selftest_check_kernel(const float *buf, int64_t off, int64_t n, float tag, unsigned long long *bad)
+    {
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (buf[off + i] != tag + (float)(i % 1024)) atomicAdd(bad, 1ull);
+    }
+    __global__ void selftest_reduce_kernel(double a, double b, double *partials, unsigned int *counter, double *red, PeerDev pd)
+    {
+      double acc[2] = {threadIdx.x == 0 && blockIdx.x == 0 ? a : 0.0, threadIdx.x == 1 && blockIdx.x == gridDim.x - 1 ? b : 0.0};
+      finish_reduce<2>(acc, partials, counter, red, pd);
+    }
+  } // namespace
+
+  int64_t peer_selftest(Context &ctx, int rounds)
+  {
+    PeerLink &link = peer_link(ctx);
+    if (!link.active) return -1;
+    const int rank = link.rank, size = link.size;
+    int64_t bad_total = 0;
+    DevBuf<unsigned long long> bad(1);
+    bad.zero(ctx.stream);
+    for (size_t bytes : {size_t(1) << 20, size_t(5) << 20, size_t(300) << 20})
+      {
+        const std::vector<void *> bufs = link.alloc_shared(ctx, bytes);
+        if (bufs.empty()) return -1;
+        const int64_t seg = (int64_t)(bytes / sizeof(float)) / size; // every rank owns one segment of every copy
+        for (int r = 0; r < size; ++r)
+          selftest_write_kernel<<<64, 256, 0, ctx.stream>>>(static_cast<float *>(bufs[r]), seg * rank, seg, (float)(100 * rank + r));
+        IFEM_KERNEL_CHECK();
+        IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+        comm_allgather_i64(ctx, {1}); // everybody has written
+        for (int r = 0; r < size; ++r)
+          selftest_check_kernel<<<64, 256, 0, ctx.stream>>>(static_cast<const float *>(bufs[rank]), seg * r, seg, (float)(100 * r + rank), bad.p);
+        IFEM_KERNEL_CHECK();
+        bad_total += (int64_t)bad.to_host(ctx.stream)[0];
+        bad.zero(ctx.stream);
+        comm_allgather_i64(ctx, {1}); // nobody rewrites a buffer that is still being checked
+      }
+    // ghost push: every rank sends 100 000 "nodes" of width 4 to every other rank with the halo kernels; rank s's message lands
+    // at float offset (8 + s) * 2^20 of the receiver's buffer; three rounds with fresh values
+    if (size <= kPeerMaxNeighbours + 1)
+      {
+        const int n_nodes = 100000, w = 4;
+        const std::vector<void *> src = link.alloc_shared(ctx, size_t(64) << 20), flg = link.alloc_shared(ctx, sizeof(unsigned int) * kPeerMaxRanks);
+        if (src.empty() || flg.empty()) return -1;
+        DevBuf<unsigned int> hs(2);
+        hs.zero(ctx.stream);
+        std::vector<int> pos;
+        for (int nb = 0; nb < size - 1; ++nb)
+          for (int k = 0; k < n_nodes; ++k) pos.push_back((k * 7) % n_nodes);
+        DevBuf<int> d_pos;
+        d_pos.upload(pos, ctx.stream);
+        PeerHaloDev<float> h;
+        h.n_nb = size - 1;
+        h.width = w;
+        int k = 0;
+        for (int r = 0; r < size; ++r)
+          if (r != rank)
+            {
+              h.send_off[k] = k * n_nodes;
+              h.dst[k] = static_cast<float *>(src[r]) + (int64_t)(8 + rank) * (1 << 20);
+              h.flag[k] = static_cast<unsigned int *>(flg[r]) + rank;
+              h.nb_rank[k] = r;
+              ++k;
+            }
+        h.send_off[h.n_nb] = h.n_nb * n_nodes;
+        h.my_flags = static_cast<const unsigned int *>(flg[rank]);
+        h.epoch = hs.p;
+        h.counter = hs.p + 1;
+        float *mine = static_cast<float *>(src[rank]);
+        DevBuf<float> got((size_t)n_nodes * w);
+        for (int round = 1; round <= 3; ++round)
+          {
+            selftest_write_kernel<<<64, 256, 0, ctx.stream>>>(mine, 0, (int64_t)n_nodes * w, (float)(1000 * round + rank));
+            peer_halo_push_kernel<float><<<32, 256, 0, ctx.stream>>>(h, d_pos.p, mine, nullptr);
+            peer_halo_wait_kernel<float><<<1, 32, 0, ctx.stream>>>(h, nullptr);
+            IFEM_KERNEL_CHECK();
+            IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+            for (int r = 0; r < size; ++r)
+              if (r != rank)
+                {
+                  // node k of rank r's message = node (7 k mod n) of r's vector = tag + ((4 (7k mod n) + c) mod 1024)
+                  const std::vector<float> hgot = [&] {
+                    IFEM_CUDA(cudaMemcpyAsync(got.p, mine + (int64_t)(8 + r) * (1 << 20), got.n * sizeof(float), cudaMemcpyDeviceToDevice, ctx.stream));
+                    return got.to_host(ctx.stream);
+                  }();
+                  for (int kk = 0; kk < n_nodes; ++kk)
+                    for (int c = 0; c < w; ++c)
+                      if (hgot[(size_t)kk * w + c] != (float)(1000 * round + r) + (float)(((int64_t)((kk * 7) % n_nodes) * w + c) % 1024)) ++bad_total;
+                }
+            comm_allgather_i64(ctx, {1});
+          }
+      }
+    // all-reduces: rank r contributes (r + 1) * k and 0.5^k
+    DevBuf<double> partials(64 * 2), red(kPeerMaxVals);
+    DevBuf<unsigned int> counter(1);
+    counter.zero(ctx.stream);
+    const PeerDev pd = link.dev();
+    for (int k = 1; k <= rounds; ++k)
+      {
+        selftest_reduce_kernel<<<32, 256, 0, ctx.stream>>>((double)(rank + 1) * k, std::ldexp(1.0, -(k % 40)), partials.p, counter.p, red.p, pd);
+        IFEM_KERNEL_CHECK();
+        if (k % 97 == 0 || k == rounds)
+          {
+            const std::vector<double> h = red.to_host(ctx.stream);
+            const double want0 = 0.5 * size * (size + 1) * k, want1 = size * std::ldexp(1.0, -(k % 40));
+            if (h[0] != want0 || h[1] != want1) ++bad_total;
+          }
+      }
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+    return bad_total;
   }
 } // namespace ifem

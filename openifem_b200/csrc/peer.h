@@ -57,6 +57,10 @@ namespace ifem
   // the link of this process (created on first use after the communicator exists; inactive on a single rank)
   PeerLink &peer_link(Context &ctx);
   void peer_link_reset(); // communicator torn down
+  // collective self test of the link (tests, diagnostics): every rank shares three buffers of different sizes, writes a
+  // rank-specific pattern into every peer's copy with a kernel, and checks what the peers wrote into its own; then runs
+  // `rounds` all-reduces of known values. Returns the number of mismatches on this rank (0 = fine, -1 = link inactive).
+  int64_t peer_selftest(Context &ctx, int rounds);
 
   // collective helper on the existing communicator: every rank contributes n int64 values, all get the size x n table
   std::vector<int64_t> comm_allgather_i64(Context &ctx, const std::vector<int64_t> &mine);

@@ -141,6 +141,8 @@ ASM_LOAD = re.compile(r'asm volatile\("ld\.global[^"]*"\s*:\s*"=\w"\((\w+)(?:\.\
 def rewrite(text, barriers, fname):
     text = text.replace('#include "../../include/openifem_b200.h"', "#include <openifem_b200.h>")
     text = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1 *\2 = reinterpret_cast<\1 *>(cpu_emul::dyn_smem());", text)
+    # code that exists in two forms: `#ifdef IFEM_EMULATED_DEVICE <plain C++> #else <inline PTX> #endif` keeps the plain form
+    text = re.sub(r"#ifdef IFEM_EMULATED_DEVICE\n(.*?)#else\n.*?#endif\n", r"\1", text, flags=re.S)
     text = ASM_LOAD.sub(lambda m: f"std::memcpy(&{m.group(1)}, (const void *)({m.group(2)}), sizeof({m.group(1)}));", text)
     text = re.sub(r'asm volatile\("createpolicy[^;]*;"\s*:\s*"=l"\((\w+)\)\);', r"\1 = 0;", text)
     if "asm volatile" in text:
@@ -167,7 +169,7 @@ def build(force=False):
     units.append(os.path.join(HERE, "cpu_emul_engine.cpp"))
     units.append(os.path.join(HERE, "comm_emul.cpp"))
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-deprecated", "-w",
-             "-D__CUDACC__", "-include", os.path.join(HERE, "cuda_runtime.h"), "-I", HERE, "-I", os.path.join(OUT, "src"), "-I", os.path.join(ROOT, "include")]
+             "-D__CUDACC__", "-DIFEM_EMULATED_DEVICE", "-include", os.path.join(HERE, "cuda_runtime.h"), "-I", HERE, "-I", os.path.join(OUT, "src"), "-I", os.path.join(ROOT, "include")]
 
     def compile_one(src):
         obj = os.path.join(OUT, os.path.basename(src) + ".o")

@@ -36,6 +36,9 @@ int ifem_init(int device);
 int ifem_set_host_threads(int n);
 /* number of kernels launched by the library so far in this process */
 int ifem_kernel_launches(int64_t *count);
+/* measured FP64 FMA throughput of the device (register-only FMA chains, TFLOP/s): the compute-side denominator of the assembly
+ * kernels' roofline (bench.py) */
+int ifem_bench_fp64_peak(double *tflops);
 /* collective self test of the peer-memory link between the ranks of one node (csrc/peer.h): shared buffers written by kernels of
  * the peers and `rounds` in-kernel all-reduces of known values; *mismatches = 0 when everything arrived, -1 when the link is
  * inactive (one rank, IPC unavailable, IFEM_PEER=0) */

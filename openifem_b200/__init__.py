@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import IfemError, InsControl, NewtonRecord, SolidRecord, check, dptr, iptr, lptr, lib
 
 __all__ = ["Triangulation", "GridGenerator", "Parameters", "Fluid", "Solid", "MPI", "io", "Partition", "IfemError", "init", "init_distributed",
-           "comm_unique_id", "comm_init", "comm_finalize", "peer_selftest", "kernel_launches", "set_host_threads"]
+           "comm_unique_id", "comm_init", "comm_finalize", "peer_selftest", "bench_fp64_peak", "kernel_launches", "set_host_threads"]
 
 
 def init(device: int = 0):
@@ -34,6 +34,13 @@ def comm_init(rank: int, size: int, unique_id: bytes):
     """One process per GPU: join the NCCL communicator (replaces MPI_COMM_WORLD of the reference)."""
     buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
     check(lib().ifem_comm_init(C.c_int(rank), C.c_int(size), buf))
+
+
+def bench_fp64_peak():
+    """measured FP64 FMA throughput of the device in TFLOP/s (register-only FMA chains)"""
+    v = C.c_double()
+    check(lib().ifem_bench_fp64_peak(C.byref(v)))
+    return v.value
 
 
 def peer_selftest(rounds=200):

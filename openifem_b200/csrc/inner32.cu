@@ -931,20 +931,37 @@ namespace ifem
     PeerLink &link = peer_link(ctx);
     if (!link.active || !(link.mask & 2)) return;
     const int size = link.size;
-    // row of this rank: float offset of the segment that receives rank s's message (-1: not a neighbour), then an ok flag
-    std::vector<int64_t> row((size_t)size + 1, -1);
-    bool ok = halo_plan != nullptr && (int)halo_plan->neighbours.size() <= kPeerMaxNeighbours;
+    // row of this rank: for every rank s the float offsets of the segments that receive s's messages, in message order
+    // (the halo plan has one entry per ghost layer and neighbour; as with ncclSend / ncclRecv an empty side of an entry is
+    // skipped, so the j-th non-empty send of s to this rank meets its j-th non-empty receive from s), then an ok flag
+    std::vector<int64_t> row((size_t)size * kPeerMaxMsgs + 1, -1);
+    bool ok = halo_plan != nullptr;
     if (ok)
-      for (size_t k = 0; k < halo_plan->neighbours.size(); ++k)
-        row[halo_plan->neighbours[k]] = ((int64_t)n_pad + (int64_t)(halo_plan->recv_off[k] - n_rows)) * xs();
-    row[size] = ok ? 1 : 0;
+      {
+        std::vector<int> n_recv((size_t)size, 0), n_send((size_t)size, 0), distinct;
+        int n_msgs = 0;
+        for (size_t k = 0; k < halo_plan->neighbours.size(); ++k)
+          {
+            const int s2 = halo_plan->neighbours[k];
+            if (std::find(distinct.begin(), distinct.end(), s2) == distinct.end()) distinct.push_back(s2);
+            if (halo_plan->recv_cnt[k] > 0)
+              {
+                if (n_recv[s2] >= kPeerMaxMsgs) { ok = false; break; }
+                row[(size_t)s2 * kPeerMaxMsgs + n_recv[s2]++] = ((int64_t)n_pad + (int64_t)(halo_plan->recv_off[k] - n_rows)) * xs();
+              }
+            if (halo_plan->send_cnt[k] > 0) ++n_msgs;
+          }
+        ok = ok && (int)distinct.size() <= kPeerMaxNeighbours && n_msgs <= kPeerMaxMsgs;
+      }
+    row[(size_t)size * kPeerMaxMsgs] = ok ? 1 : 0;
     const std::vector<int64_t> all = comm_allgather_i64(ctx, row);
-    ghost_off.assign((size_t)size * size, -1);
+    const size_t stride = (size_t)size * kPeerMaxMsgs + 1;
+    ghost_off.assign((size_t)size * size * kPeerMaxMsgs, -1);
     bool all_ok = true;
     for (int r = 0; r < size; ++r)
       {
-        all_ok = all_ok && all[(size_t)r * (size + 1) + size] == 1;
-        for (int s2 = 0; s2 < size; ++s2) ghost_off[(size_t)r * size + s2] = all[(size_t)r * (size + 1) + s2];
+        all_ok = all_ok && all[(size_t)r * stride + (size_t)size * kPeerMaxMsgs] == 1;
+        for (size_t e = 0; e < (size_t)size * kPeerMaxMsgs; ++e) ghost_off[(size_t)r * size * kPeerMaxMsgs + e] = all[(size_t)r * stride + e];
       }
     if (!all_ok) return;
     if (!was || flag_peers.empty())
@@ -1083,17 +1100,26 @@ namespace ifem
           {
             PeerLink &link = peer_link(ctx);
             PeerHaloDev<float> h;
-            h.n_nb = (int)H.neighbours.size();
             h.width = w;
-            for (int k = 0; k < h.n_nb; ++k)
+            std::vector<int> sent((size_t)link.size, 0);
+            for (size_t k = 0; k < H.neighbours.size(); ++k)
               {
                 const int nb = H.neighbours[k];
-                h.send_off[k] = H.send_off[k];
-                h.dst[k] = static_cast<float *>(src.peers[nb]) + ghost_off[(size_t)nb * link.size + link.rank];
-                h.flag[k] = static_cast<unsigned int *>(flag_peers[nb]) + link.rank;
-                h.nb_rank[k] = nb;
+                bool seen = false;
+                for (int j = 0; j < h.n_nb; ++j) seen = seen || h.nb_rank[j] == nb;
+                if (!seen)
+                  {
+                    h.flag[h.n_nb] = static_cast<unsigned int *>(flag_peers[nb]) + link.rank;
+                    h.nb_rank[h.n_nb++] = nb;
+                  }
+                if (H.send_cnt[k] <= 0) continue;
+                // my j-th non-empty message to nb lands in nb's j-th non-empty receive segment from me
+                const int64_t off = ghost_off[((size_t)nb * link.size + link.rank) * kPeerMaxMsgs + sent[nb]++];
+                if (off < 0) throw std::runtime_error("Sell32::halo: the neighbour has no receive segment for this message");
+                h.send_off[h.n_msg] = H.send_off[k];
+                h.dst[h.n_msg++] = static_cast<float *>(src.peers[nb]) + off;
               }
-            h.send_off[h.n_nb] = H.n_send_total;
+            h.send_off[h.n_msg] = H.n_send_total;
             h.my_flags = static_cast<const unsigned int *>(flag_peers[link.rank]);
             h.epoch = halo_state.p;
             h.counter = halo_state.p + 1;

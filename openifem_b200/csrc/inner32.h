@@ -69,7 +69,7 @@ namespace ifem
     std::vector<Source> sources;
     DevBuf<float> plain_sources[4];        // gather sources when there is no peer link
     bool peer_halo = false;
-    std::vector<int64_t> ghost_off;        // [size * size]: float offset in rank r's source where rank s's message lands (-1: none)
+    std::vector<int64_t> ghost_off;        // [size][size][kPeerMaxMsgs]: float offsets in rank r's source where rank s's messages land (-1: none)
     std::vector<void *> flag_peers;        // arrival flags of every rank ([kPeerMaxRanks] unsigned per rank)
     DevBuf<unsigned int> halo_state;       // [0] pushes carried out, [1] CTA counter of the push kernel
 

@@ -219,7 +219,7 @@ namespace ifem
         DevBuf<int> d_pos;
         d_pos.upload(pos, ctx.stream);
         PeerHaloDev<float> h;
-        h.n_nb = size - 1;
+        h.n_nb = h.n_msg = size - 1;
         h.width = w;
         int k = 0;
         for (int r = 0; r < size; ++r)
@@ -231,7 +231,7 @@ namespace ifem
               h.nb_rank[k] = r;
               ++k;
             }
-        h.send_off[h.n_nb] = h.n_nb * n_nodes;
+        h.send_off[h.n_msg] = h.n_msg * n_nodes;
         h.my_flags = static_cast<const unsigned int *>(flg[rank]);
         h.epoch = hs.p;
         h.counter = hs.p + 1;

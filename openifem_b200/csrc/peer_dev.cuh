@@ -121,15 +121,16 @@ namespace ifem
   }
 
   // ---- ghost push --------------------------------------------------------------------------------------------------
-  constexpr int kPeerMaxNeighbours = 4;
+  constexpr int kPeerMaxNeighbours = 4; // distinct neighbour ranks
+  constexpr int kPeerMaxMsgs = 8;       // messages: a neighbour may receive several segments (one per ghost layer)
 
   template <typename T>
   struct PeerHaloDev
   {
-    int n_nb = 0;
-    int width = 1;                         // values per node
-    int send_off[kPeerMaxNeighbours + 1];  // in nodes, into send_pos
-    T *dst[kPeerMaxNeighbours];            // where this rank's message lands in the neighbour's vector
+    int n_msg = 0, n_nb = 0;
+    int width = 1;                          // values per node
+    int send_off[kPeerMaxMsgs + 1];         // in nodes, into send_pos: message m covers [send_off[m], send_off[m + 1])
+    T *dst[kPeerMaxMsgs];                   // where message m lands in the receiver's vector
     unsigned int *flag[kPeerMaxNeighbours]; // the neighbour's arrival flag for this rank
     int nb_rank[kPeerMaxNeighbours];
     const unsigned int *my_flags = nullptr; // [kPeerMaxRanks] arrival flags of this rank, indexed by sender
@@ -144,13 +145,13 @@ namespace ifem
                                                                 const int *__restrict__ skip)
   {
     if (skip && *skip) return;
-    const int total = h.send_off[h.n_nb] * h.width;
+    const int total = h.send_off[h.n_msg] * h.width;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
       {
         const int k = t / h.width, c = t - k * h.width;
-        int nb = 0;
-        while (nb + 1 < h.n_nb && k >= h.send_off[nb + 1]) ++nb;
-        h.dst[nb][(size_t)(k - h.send_off[nb]) * h.width + c] = x[(size_t)send_pos[k] * h.width + c];
+        int m = 0;
+        while (m + 1 < h.n_msg && k >= h.send_off[m + 1]) ++m;
+        h.dst[m][(size_t)(k - h.send_off[m]) * h.width + c] = x[(size_t)send_pos[k] * h.width + c];
       }
     __threadfence_system();
     __syncthreads();

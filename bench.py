@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "time_step_wall_s (3D INS cavity 128^3 cells Q2/Q1, 53.07M DoF)"
+METRIC2 = "time_step_wall_s (3D flow past cylinder, InsIM Q2/Q1, ~1.35M DoF)"
 UNIT = "s/step"
 CPU_BASELINE_CELLS = [16, 24]  # cpu_baseline leg of the default run (bounded); --impl reference: --ref-cells
 
@@ -104,6 +105,49 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
 
 
+CYL_H, CYL_UMAX = 0.41, 9 * 0.2 / 4
+
+
+def cylinder_inflow(p, c, t):
+    """3-D Schaefer-Turek inflow profile on x = -0.3 (boundary id 0), see tests/test_zz_config2_gpu.py"""
+    return 16 * CYL_UMAX * p[1] * (CYL_H - p[1]) * p[2] * (CYL_H - p[2]) / CYL_H ** 4 if c == 0 and abs(p[0] + 0.3) < 1e-10 else 0.0
+
+
+def cylinder_prm_path():
+    return os.path.join(ROOT, "tests", "golden", "ins_cylinder_3d.prm")
+
+
+def cpu_cylinder_fit(levels, target_level, threads=None):
+    """config 2 on the CPU: one time step of the oracle on the 3-D cylinder mesh at each refinement level of `levels`, extrapolated to
+    target_level with the fitted exponent of s/step in the number of cells (8x cells per level)."""
+    import math
+
+    import openifem_b200 as ifem
+    from oracle import grid, ins as oracle_ins, prm
+
+    team = oracle_ins.set_threads(threads)
+    secs, cells = [], []
+    for lv in levels:
+        tria = ifem.Triangulation(3)  # host-side mesh generator of the product (no device work): the same mesh arrays as the GPU arm
+        ifem.GridCreator.flow_around_cylinder(tria)
+        tria.refine_global(lv)
+        v, c, b = tria.get_mesh()
+        o = oracle_ins.InsIM(grid.HexMesh(v, c, b), prm.Params(cylinder_prm_path()), mode="mpi", hard_coded={0: cylinder_inflow},
+                             a_inv=("bicgstab", 1e-1, 2000))
+        t0 = time.perf_counter()
+        o.run_one_step(True)
+        secs.append(time.perf_counter() - t0)
+        cells.append(c.shape[0])
+    p = math.log(secs[-1] / secs[0]) / math.log(cells[-1] / cells[0]) if len(levels) > 1 else 1.0
+    target_cells = 832 * 8 ** target_level
+    value = secs[-1] * (target_cells / cells[-1]) ** p
+    desc = ("one time step (from rest, hard-coded inflow) of the 3-D cylinder case at "
+            + ", ".join(f"refinement {lv} ({n} cells): {t:.1f} s" for lv, n, t in zip(levels, cells, secs))
+            + f" with oracle/ on an OpenMP team of {team} threads; fitted s/step ~ cells^{p:.3f}; extrapolated to refinement {target_level} "
+              f"({target_cells} cells)")
+    return value, desc, team, secs, p
+
+
 def cpu_reference_step(cells, steps=1, warmup=0, threads=None):
     """The oracle (CPU restatement of mpi_insim.cpp) on all host cores: seconds per time step on a cells^3 cavity, same .prm and
     same solver settings as the GPU arm (A~^-1 = BiCGStab + node-block Jacobi to 1e-1). Returns (s/step, oracle, team size)."""
@@ -155,13 +199,18 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(cores)  # unconditional: torchrun sets it to 1 for N > 1
-    sizes = [int(c) for c in args.ref_cells.split(",")]
-    value, sample, team, secs, p = cpu_reference_fit(sizes, args.cells, threads=cores)
+    if args.config == 2:
+        sizes = [0, 1]
+        value, sample, team, secs, p = cpu_cylinder_fit(sizes, args.refine, threads=cores)
+    else:
+        sizes = [int(c) for c in args.ref_cells.split(",")]
+        value, sample, team, secs, p = cpu_reference_fit(sizes, args.cells, threads=cores)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC if args.config == 3 else METRIC2, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D INS lid-driven cavity {args.cells}^3 hex cells Q2/Q1 (config 3), one time step",
+        "config": {"workload": (f"3D INS lid-driven cavity {args.cells}^3 hex cells Q2/Q1 (config 3), one time step" if args.config == 3 else
+                                f"3D flow past a cylinder, InsIM Q2/Q1, Global refinements = {args.refine} (config 2), one time step"),
                    "same_config": False, "extrapolated": True, "sample_cells": sizes, "sample_seconds": secs, "fitted_exponent": p},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": team, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,10 +252,18 @@ def run_ours(args):
     n = args.cells
     t_setup = time.perf_counter()
     tria = ifem.Triangulation(3)
-    ifem.GridGenerator.subdivided_hyper_rectangle(tria, (n, n, n), (0, 0, 0), (1, 1, 1), True)
-    params = ifem.Parameters.AllParameters(text=cavity_prm(3))
-    flow = ifem.Fluid.MPI.InsIM(tria, params)
+    if args.config == 2:
+        ifem.GridCreator.flow_around_cylinder(tria)
+        tria.refine_global(args.refine)
+        params = ifem.Parameters.AllParameters(cylinder_prm_path())
+        flow = ifem.Fluid.MPI.InsIM(tria, params)
+        flow.add_hard_coded_boundary_condition(0, cylinder_inflow)
+    else:
+        ifem.GridGenerator.subdivided_hyper_rectangle(tria, (n, n, n), (0, 0, 0), (1, 1, 1), True)
+        params = ifem.Parameters.AllParameters(text=cavity_prm(3))
+        flow = ifem.Fluid.MPI.InsIM(tria, params)
     flow.setup()
+    n_cells_global = tria.n_active_cells()
     # fp32 inner solver on the SELL-32 copy of A_uu with row-scaled fp16 matrix values (preconditioner only)
     flow.set_control(a_inv_rel=1e-1, a_inv_fp32=args.inner_mode, cg_sm_fp32=args.sm_mode, a_inv_max_it=400)
     barrier()
@@ -255,6 +312,15 @@ def run_ours(args):
     else:
         (ms_32, bytes_32), sell_padding = (flow.bench_spmv_uu_fp32(20) if args.inner_mode == 1 else (ms_uu, bytes_uu)), 1.0
     ms_blk, bytes_blk = flow.bench_vmult(10)
+    # cell-loop assembly (InsIM::assemble, all colours + Neumann faces + zeroing of the matrices), timed live; algorithmic work per
+    # cell: 27^3 (row node, column node, quadrature point) triples x 25 FMA for the velocity-velocity blocks + ~3e4
+    # FMA for the other phases; 89^2 matrix entries read-modify-written (16 B each)
+    flow.bench_assemble(1)
+    ms_asm = flow.bench_assemble(3)
+    n_cells_local = n_cells_global // world  # cells a rank owns (the duplicated interface layer of the owner-computes scheme is overhead)
+    asm_flop = n_cells_local * (27 ** 3 * 25 * 2 + 60000.0)
+    asm_bytes = n_cells_local * 89 * 89 * 16.0
+    fp64_peak = ifem.bench_fp64_peak()
     peak, peak_src = _peaks()
     achieved = bytes_32 / (ms_32 * 1e-3) / 1e9
     achieved64 = bytes_uu / (ms_uu * 1e-3) / 1e9
@@ -282,7 +348,7 @@ def run_ours(args):
                     "field norms over all owned dofs after the last timed step"}
 
     if world > 1:
-        ms_uu, ms_blk, ms_32 = max_over_ranks(ms_uu), max_over_ranks(ms_blk), max_over_ranks(ms_32)
+        ms_uu, ms_blk, ms_32, ms_asm = max_over_ranks(ms_uu), max_over_ranks(ms_blk), max_over_ranks(ms_32), max_over_ranks(ms_asm)
         achieved = bytes_32 / (ms_32 * 1e-3) / 1e9
         achieved64 = bytes_uu / (ms_uu * 1e-3) / 1e9
         dist.barrier()
@@ -293,15 +359,21 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         # bounded sample (about 20-30 s of CPU work); the reference arm (--impl reference) runs the larger sizes
-        v, sample, team, _, _ = cpu_reference_fit(CPU_BASELINE_CELLS, n, threads=os.cpu_count())
+        if args.config == 2:
+            v, sample, team, _, _ = cpu_cylinder_fit([0, 1], args.refine, threads=os.cpu_count())
+        else:
+            v, sample, team, _, _ = cpu_reference_fit(CPU_BASELINE_CELLS, n, threads=os.cpu_count())
         cpu = {"value": v, "unit": UNIT, "cores": team, "kind": "port", "sample": sample}
 
     line = {
-        "metric": METRIC, "value": sec_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if args.config == 3 else METRIC2, "value": sec_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec_dev * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"3D INS lid-driven cavity {n}^3 hex cells Q2/Q1 (config 3): {n_dofs} DoF, {nnz} matrix entries, "
-                               f"Re 100, dt 1e-2, from rest; step = run_one_step (Newton x (assembly + FGMRES/Schur))",
+        "config": {"workload": (f"3D INS lid-driven cavity {n}^3 hex cells Q2/Q1 (config 3): {n_dofs} DoF, {nnz} matrix entries, "
+                                f"Re 100, dt 1e-2, from rest; step = run_one_step (Newton x (assembly + FGMRES/Schur))" if args.config == 3 else
+                                f"3D flow past a cylinder (config 2): GridCreator<3>::flow_around_cylinder, Global refinements = {args.refine}, "
+                                f"{n_cells_global} cells, {n_dofs} DoF, {nnz} matrix entries, InsIM Q2/Q1, hard-coded parabolic inflow, mu 1e-3, "
+                                f"gamma 0.1, dt 1e-2, from rest; step = run_one_step"),
                    "l2": "inputs larger than L2 (A_uu alone is %.1f GB per GPU)" % (bytes_uu / 1e9),
                    "a_inv": {0: "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1 in fp64 on the BCSR matrix",
                              1: "A~^-1 = BiCGStab(node-block Jacobi) to 1e-1, A_uu streamed as fp32 (BCSR)",
@@ -322,13 +394,19 @@ def run_ours(args):
                                                + " (product of the fp32 inner A~^-1 solves on the SELL-32 copy of A_uu; dominant "
                                                  "kernel of a step), per GPU (rank 0's rows)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic.get("sell_spmv_h_kernel" if args.inner_mode == 3 else "sell_spmv_pipe_kernel") if world == 1 and n == 128 else None,
+                     "traffic": traffic.get("sell_spmv_h_kernel" if args.inner_mode == 3 else "sell_spmv_pipe_kernel") if world == 1 and n == 128 and args.config == 3 else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this "
                                        "config (profiles/ncu_traffic.json names the capture); not re-measured in this run",
                      "algorithmic_bytes": bytes_32, "ms": ms_32, "sell_padding": sell_padding,
                      "fgmres_operator_spmv": {"kernel": "bcsr_spmv_row_kernel<3,3,32,double,1,4,0> (A_uu, fp64 operator of FGMRES)", "ms": ms_uu,
                                               "algorithmic_bytes": bytes_uu, "achieved": achieved64, "frac": achieved64 / peak,
-                                              "traffic": traffic.get("bcsr_spmv_kernel<3,3,32,double>") if world == 1 and n == 128 else None},
+                                              "traffic": traffic.get("bcsr_spmv_kernel<3,3,32,double>") if world == 1 and n == 128 and args.config == 3 else None},
+                     "assembly": {"kernel": "ins_assemble_kernel<3> (team of 3 warps per cell, 8 colour launches) + zeroing + Neumann faces",
+                                  "ms": ms_asm, "bound": "fp64 + hbm (matrix read-modify-write)", "algorithmic_flop": asm_flop,
+                                  "achieved_tflops": asm_flop / (ms_asm * 1e-3) / 1e12, "fp64_peak_tflops": fp64_peak,
+                                  "fp64_peak_source": "measured in this run (register-only FMA chains, ifem_bench_fp64_peak)",
+                                  "frac_fp64": asm_flop / (ms_asm * 1e-3) / 1e12 / fp64_peak, "rmw_bytes": asm_bytes,
+                                  "rmw_GBps": asm_bytes / (ms_asm * 1e-3) / 1e9, "frac_hbm": asm_bytes / (ms_asm * 1e-3) / 1e9 / peak},
                      "block_vmult": {"ms": ms_blk, "bytes": bytes_blk, "GB/s": bytes_blk / (ms_blk * 1e-3) / 1e9,
                                      "csr_equivalent_bytes_per_gpu": 12.0 * nnz_local + 20.0 * (3 * ou + op)}},
         "cpu_baseline": cpu, "parity_pins": pins,
@@ -345,6 +423,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cells", type=int, default=128, help="cells per direction (config 3 = 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3],
+                    help="BASELINE config: 3 = 3-D cavity 128^3 (the metric's config, default), 2 = 3-D flow past a cylinder (~1.35 M dofs, 1 GPU)")
+    ap.add_argument("--refine", type=int, default=2, help="config 2: Global refinements of the cylinder mesh")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cells", default="24,32,48",
                     help="--impl reference: cells per direction of the timed samples (the fit is extrapolated to --cells)")

@@ -273,3 +273,61 @@ def flow_around_cylinder_2d(compute_in_2d=True):
         bfaces.append((c, f, bid))
     return QuadMesh(verts, cells, np.asarray(bfaces, dtype=np.int32),
                     (np.asarray(chart_of, dtype=np.int32), np.asarray(box, dtype=np.float64), charts))
+
+
+class HexMesh:
+    """Unstructured hexahedral mesh from plain arrays (test infrastructure): vertices [nv][3], cells [nc][8] in lexicographic corner
+    order, boundary_faces [(cell, face_no = 2 * axis + side, boundary id)]. FE_Q(p) nodes are the geometric entities of the cells
+    (vertices, edge / face / cell midpoints = means of the corners they interpolate: the support points of the default Q1 mapping,
+    reference source/mpi_insim.cpp:167), numbered in lexicographic (z, y, x) order of their quantised position like QuadMesh."""
+
+    dim = 3
+
+    def __init__(self, vertices, cells, boundary_faces):
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
+        self.cells = np.ascontiguousarray(cells, dtype=np.int32)
+        self.boundary_faces = np.ascontiguousarray(boundary_faces, dtype=np.int32).reshape(-1, 3)
+        self.n_cells = self.cells.shape[0]
+
+    def _entities(self):
+        nc = self.n_cells
+        # local Q2 node (i, j, k) on {0,1,2}^3 -> the corners it averages
+        loc = []
+        for k in range(3):
+            for j in range(3):
+                for i in range(3):
+                    sel = [(0,) if t == 0 else (1,) if t == 2 else (0, 1) for t in (i, j, k)]
+                    loc.append([x + 2 * y + 4 * z for z in sel[2] for y in sel[1] for x in sel[0]])
+        ids, pos = {}, []
+        tab = np.zeros((nc, 27), dtype=np.int64)
+        for c in range(nc):
+            cv = self.cells[c]
+            for a in range(27):
+                key = tuple(sorted(int(cv[v]) for v in loc[a]))
+                n = ids.get(key)
+                if n is None:
+                    n = ids[key] = len(pos)
+                    pos.append(self.vertices[list(key)].mean(axis=0))
+                tab[c, a] = n
+        return tab, np.asarray(pos)
+
+    @staticmethod
+    def _spatial_renumber(tab, coords):
+        lo, hi = coords.min(axis=0), coords.max(axis=0)
+        ext = np.where(hi > lo, hi - lo, 1.0)
+        Q = float((1 << 21) - 1)
+        q = np.rint((coords - lo) / ext * Q).astype(np.int64)
+        key = (q[:, 2] << 42) | (q[:, 1] << 21) | q[:, 0]
+        order = np.argsort(key, kind="stable")
+        new_id = np.empty_like(order)
+        new_id[order] = np.arange(order.size)
+        return new_id[tab].astype(np.int32), coords[order]
+
+    def node_table(self, p: int):
+        if p == 1:
+            tab, coords = self._spatial_renumber(self.cells.astype(np.int64), self.vertices)
+        elif p == 2:
+            tab, coords = self._spatial_renumber(*self._entities())
+        else:
+            raise ValueError("FE_Q(1) and FE_Q(2) only")
+        return tab, coords.shape[0], coords

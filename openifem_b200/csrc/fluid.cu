@@ -365,9 +365,9 @@ namespace ifem
       static constexpr int DPC = NU * DIM + NP;
       // a TEAM of warps works on one cell (the cell's scratch in shared memory is shared by the team), CELLS cells per CTA
       static constexpr int TEAM = DIM == 2 ? 1 : 3;
-      static constexpr int CELLS = DIM == 2 ? 8 : 3;
+      static constexpr int CELLS = DIM == 2 ? 8 : 5;
       static constexpr int THREADS = TEAM * CELLS * 32;
-      static constexpr int MIN_CTAS = DIM == 2 ? 1 : 2;
+      static constexpr int MIN_CTAS = 1;
       static constexpr int TAB = NQ * NU + NQ * NU * DIM + NQ * NP + NQ * NV * DIM + NQ; // doubles, layout of FluidSpace::d_tables
       static constexpr int STAB = (NQ * NU + NQ * NP + NQ * NV * DIM + NQ + 1) & ~1;     // staged in shared memory (d_tables_s)
     };
@@ -709,13 +709,16 @@ namespace ifem
                       for (int c = 0; c < DIM; ++c) K[t][c * DIM + c] += sK[t];
                       const int64_t rp = a.uu.rowptr[A];
                       const int nb = (int)(a.uu.rowptr[A + 1] - rp);
-                      double *base = a.uu.val + rp * (DIM * DIM);
-                      const int slot = slots[aN * NU + b];
+                      double *base = a.uu.val + rp * (DIM * DIM) + slots[aN * NU + b];
                       double corr[DIM];
 #pragma unroll
                       for (int c = 0; c < DIM; ++c) corr[c] = 0.0;
                       if (lane < NU)
                         {
+                          // what goes into plane (c, d) of this block: the entry, |diagonal| of a constrained row, or nothing
+                          // (constrained row off the diagonal; constrained column: lifted to the right-hand side)
+                          double add[DIM * DIM];
+                          bool put[DIM * DIM];
 #pragma unroll
                           for (int c = 0; c < DIM; ++c)
                             {
@@ -724,20 +727,31 @@ namespace ifem
                               for (int d = 0; d < DIM; ++d)
                                 {
                                   const double v = K[t][c * DIM + d];
+                                  add[c * DIM + d] = v;
+                                  put[c * DIM + d] = false;
                                   if (rc)
                                     {
                                       if (b == aN && c == d)
                                         {
-                                          base[(int64_t)(c * DIM + d) * nb + slot] += fabs(v);
+                                          add[c * DIM + d] = fabs(v);
+                                          put[c * DIM + d] = true;
                                           S.ldiag[aN * DIM + c] = fabs(v);
                                         }
                                     }
                                   else if (cb[d])
                                     corr[c] = fma(v, ib[d], corr[c]);
                                   else
-                                    base[(int64_t)(c * DIM + d) * nb + slot] += v;
+                                    put[c * DIM + d] = true;
                                 }
                             }
+                          // read-modify-write of the DIM x DIM planes: all loads of the block in flight before the first store
+                          // (the planes of a block never alias; written as one chain the compiler has to serialise them)
+                          double old[DIM * DIM];
+#pragma unroll
+                          for (int i = 0; i < DIM * DIM; ++i) old[i] = put[i] ? __ldcg(base + (int64_t)i * nb) : 0.0;
+#pragma unroll
+                          for (int i = 0; i < DIM * DIM; ++i)
+                            if (put[i]) __stcg(base + (int64_t)i * nb, old[i] + add[i]);
                         }
                       if (a.inhom)
                         {
@@ -784,15 +798,25 @@ namespace ifem
                   const int nbq = own_p ? (int)(a.pu.rowptr[Pn + 1] - rq) : 0;
                   double *baseq = a.pu.val + rq * DIM;
                   const int slotq = s_pu[j * NU + aN];
+                  // both read-modify-writes of every component in flight before the first store (see phase 5)
+                  bool put[DIM];
+                  double old_up[DIM], old_pu[DIM];
+#pragma unroll
+                  for (int c = 0; c < DIM; ++c)
+                    {
+                      put[c] = !S.con[aN * DIM + c] && !pc;
+                      old_up[c] = (put[c] && own_row) ? __ldcg(base + (int64_t)c * nb + slot) : 0.0;
+                      old_pu[c] = (put[c] && own_p) ? __ldcg(baseq + (int64_t)c * nbq + slotq) : 0.0;
+                    }
 #pragma unroll
                   for (int c = 0; c < DIM; ++c)
                     {
                       const int uc = S.con[aN * DIM + c];
                       const double v = B[c];
-                      if (!uc && !pc)
+                      if (put[c])
                         {
-                          if (own_row) base[(int64_t)c * nb + slot] += v;   // A_up block row a, plane c
-                          if (own_p) baseq[(int64_t)c * nbq + slotq] += v;  // A_pu row j, plane c
+                          if (own_row) __stcg(base + (int64_t)c * nb + slot, old_up[c] + v);   // A_up block row a, plane c
+                          if (own_p) __stcg(baseq + (int64_t)c * nbq + slotq, old_pu[c] + v);  // A_pu row j, plane c
                         }
                       else if (uc && !pc && a.inhom)
                         atomicAdd(&S.lrhs[NU * DIM + j], -v * S.inh[aN * DIM + c]); // column (a,c) constrained

@@ -335,11 +335,14 @@ class HyperElasticity(SolidBase):
             err_f = self.get_error(self.system_rhs)
             if it == 0:
                 err_f0 = err_f
-            nerr_f = err_f / err_f0
             err_u = self.get_error(du)
             if it == 0:
                 err_u0 = err_u
-            nerr_u = err_u / err_u0
+            # a solid at rest with no load has err_0 = 0: the reference divides all the same (mpi_hyper_elasticity.cpp:150-166), the
+            # IEEE NaN compares false against the tolerances and the loop ends after this iteration - same here, without the warning
+            with np.errstate(invalid="ignore", divide="ignore"):
+                nerr_f = np.float64(err_f) / np.float64(err_f0)
+                nerr_u = np.float64(err_u) / np.float64(err_u0)
             self.cur_u = self.cur_u + du
             self.update_qph(self.cur_u)
             self.history.append((self.timestep, it, err_f, err_u))

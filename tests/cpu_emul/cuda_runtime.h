@@ -70,6 +70,7 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask, int = 32)
 template <typename T> inline T __ldcs(const T *p) { return *p; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcg(const T *p) { return *p; }
+template <typename T> inline void __stcg(T *p, T v) { *p = v; }
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, 8); return r; }

@@ -260,6 +260,8 @@ def test_find_solid_bc_matches_oracle(dim, f_reps, s_reps, s_lo, s_hi, disp):
 @pytest.mark.parametrize("use_dirichlet", [False, True])
 @pytest.mark.parametrize("dim,f_reps,s_reps,s_lo,s_hi", [
     (2, (12, 12), (4, 6), (0.3125, 0.0), (0.5625, 0.6875)),
+    # 3-D (BASELINE config 5's path at test size): binned point-in-cell search in the solid and in the fluid, 3-D traction faces
+    (3, (6, 6, 6), (3, 3, 4), (0.25, 0.0, 0.25), (0.7, 0.6, 0.75)),
 ])
 def test_coupled_fsi_steps_match_oracle(dim, f_reps, s_reps, s_lo, s_hi, use_dirichlet):
     """two passes of the FSI::run loop (find_solid_bc -> solid step -> box / indicator -> constraints -> find_fluid_bc

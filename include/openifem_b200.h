@@ -313,6 +313,9 @@ int ifem_fsi_set_penetration_criterion(ifem_fsi *f, ifem_point_fn criterion, voi
 /* solid steps taken inside apply_contact_model so far */
 int ifem_fsi_contact_iterations(const ifem_fsi *f, int *n);
 int ifem_fsi_run_one_step(ifem_fsi *f, int first_step);
+/* the same pass up to and including find_fluid_bc, without the fluid time step: the constraints, indicator, fsi_stress and
+ * fsi_acceleration the fluid solver is about to see (tests compare them and the assembled system with the oracle) */
+int ifem_fsi_prepare_fluid_step(ifem_fsi *f, int first_step);
 int ifem_fsi_run(ifem_fsi *f);
 int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms);
 

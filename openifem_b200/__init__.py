@@ -679,6 +679,10 @@ class _FSI:
     def run_one_step(self, first_step: bool):
         check(lib().ifem_fsi_run_one_step(self._h, C.c_int(1 if first_step else 0)))
 
+    def prepare_fluid_step(self, first_step: bool):
+        """run_one_step up to and including find_fluid_bc, without the fluid time step"""
+        check(lib().ifem_fsi_prepare_fluid_step(self._h, C.c_int(1 if first_step else 0)))
+
     def run(self):
         check(lib().ifem_fsi_run(self._h))
 

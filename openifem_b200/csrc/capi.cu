@@ -1000,6 +1000,10 @@ int ifem_fsi_run_one_step(ifem_fsi *f, int first_step)
 {
   return guard([&] { f->f->run_one_step(first_step != 0); });
 }
+int ifem_fsi_prepare_fluid_step(ifem_fsi *f, int first_step)
+{
+  return guard([&] { f->f->run_one_step(first_step != 0, true); });
+}
 int ifem_fsi_run(ifem_fsi *f)
 {
   return guard([&] { f->f->run(); });

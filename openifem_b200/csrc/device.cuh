@@ -149,6 +149,16 @@ namespace ifem
                  : "memory");
 #endif
   }
+  // start moving the line at p into L2 (no register, no dependency): issued ahead of a read-modify-write whose operands are
+  // being computed
+  __device__ __forceinline__ void prefetch_l2(const void *p)
+  {
+#ifdef IFEM_EMULATED_DEVICE
+    (void)p;
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+  }
   // streaming (read-once) loads: keep the matrix stream from evicting x out of L2
   __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
   __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }

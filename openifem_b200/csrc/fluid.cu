@@ -649,6 +649,21 @@ namespace ifem
               for (int a0 = tw * TA; a0 < NU; a0 += TEAM * TA)
                 {
                   double K[TA][DIM * DIM], sK[TA];
+                  // the planes this pass will read-modify-write: on their way to L2 while K is being summed
+                  if (lane < NU)
+                    {
+#pragma unroll
+                      for (int t = 0; t < TA; ++t)
+                        {
+                          const int A = S.un[a0 + t];
+                          if (A >= a.n_owned_u) continue;
+                          const int64_t rp = a.uu.rowptr[A];
+                          const int nb = (int)(a.uu.rowptr[A + 1] - rp);
+                          const double *base = a.uu.val + rp * (DIM * DIM) + slots[(a0 + t) * NU + b];
+#pragma unroll
+                          for (int i = 0; i < DIM * DIM; ++i) prefetch_l2(base + (int64_t)i * nb);
+                        }
+                    }
 #pragma unroll
                   for (int t = 0; t < TA; ++t)
                     {

@@ -1009,7 +1009,7 @@ namespace ifem
   }
 
   // one pass of the while loop of FSI::run (mpi_fsi.cpp:1172-1214)
-  void FsiCoupling::run_one_step(bool first_step)
+  void FsiCoupling::run_one_step(bool first_step, bool stop_before_fluid_step)
   {
     find_solid_bc();
     if (restarted) solid.after_restart(); // "solid_solver.assemble_system(true)" in every pass after a restart (:1176-1179)
@@ -1030,6 +1030,7 @@ namespace ifem
         fluid.upload_constraints();
       }
     find_fluid_bc();
+    if (stop_before_fluid_step) return; // tests: the state the fluid solver is about to see
     {
       ScopedTimer t(ctx, timer_ms["Run fluid solver"]);
       fluid.run_one_step(true);

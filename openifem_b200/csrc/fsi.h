@@ -33,7 +33,7 @@ namespace ifem
     // at the vertices of the solid's non-fixed boundary faces -> solid.fsi_stress_rows / fluid_velocity / fluid_pressure
     void find_solid_bc();
     // one coupled time step / the time loop of FSI::run (source/mpi_fsi.cpp:1172-1226), without refinement / checkpoints
-    void run_one_step(bool first_step);
+    void run_one_step(bool first_step, bool stop_before_fluid_step = false);
     void run();
     Time time;
     // FSI::set_penetration_criterion (source/mpi_fsi.cpp:1229-1237) / apply_contact_model (:869-970): while a boundary

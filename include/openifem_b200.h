@@ -73,6 +73,13 @@ int ifem_tria_hyper_cube(ifem_tria *t, double left, double right, int colorize);
 int ifem_tria_refine_global(ifem_tria *t, int times);
 /* GridTools::shift(offset, tria): offset [dim] added to every vertex */
 int ifem_tria_shift(ifem_tria *t, const double *offset);
+/* cell->set_refine_flag() on the cells with flags[cell] != 0 followed by execute_coarsening_and_refinement()
+ * (tests/fsi_leaflet_mpi/fsi_leaflet_mpi.cpp:66-76, tests/fsi-wall-3D/fsi-wall-3D.cpp:47-53): the flagged cells are replaced by their
+ * children, hanging vertices appear on the interface (one level of difference only). n = number of active cells. */
+int ifem_tria_execute_refinement(ifem_tria *t, const unsigned char *flags, int64_t n);
+/* hanging vertices of the active mesh: vertex[k] carries the mean of its n_masters[k] (2 or 4) master vertices masters[4 k ..];
+ * call with NULL arrays to get the count */
+int ifem_tria_get_hanging(const ifem_tria *t, int64_t *n_hanging, int *vertex, int *n_masters, int *masters);
 /* cell->set_material_id() for every active cell (1-based part numbers; the solid solvers pick the material parameters of a cell's
  * part, source/mpi_hyper_elasticity.cpp:226-228); n must equal the number of active cells */
 int ifem_tria_set_material_ids(ifem_tria *t, const int *ids, int64_t n);

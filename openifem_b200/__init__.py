@@ -130,6 +130,20 @@ class Triangulation:
     def refine_global(self, times: int):
         check(lib().ifem_tria_refine_global(self._h, C.c_int(times)))
 
+    def execute_refinement(self, flags):
+        """set_refine_flag() on the cells with a nonzero flag + execute_coarsening_and_refinement()"""
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        check(lib().ifem_tria_execute_refinement(self._h, flags.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int64(flags.size)))
+
+    def hanging(self):
+        """(vertex [n], n_masters [n], masters [n][4]) of the hanging vertices of the active mesh"""
+        n = C.c_int64()
+        check(lib().ifem_tria_get_hanging(self._h, C.byref(n), None, None, None))
+        v, k, m = np.empty(n.value, np.int32), np.empty(n.value, np.int32), np.empty((n.value, 4), np.int32)
+        if n.value:
+            check(lib().ifem_tria_get_hanging(self._h, C.byref(n), iptr(v), iptr(k), iptr(m)))
+        return v, k, m
+
     def set_material_ids(self, ids):
         """cell->set_material_id() of every active cell (1-based solid part numbers)"""
         ids = np.ascontiguousarray(ids, dtype=np.int32)

@@ -299,6 +299,27 @@ int ifem_tria_shift(ifem_tria *t, const double *offset)
     for (size_t i = 0; i < t->t.vertices.size(); ++i) t->t.vertices[i] += offset[i % dim];
   });
 }
+int ifem_tria_execute_refinement(ifem_tria *t, const unsigned char *flags, int64_t n)
+{
+  return guard([&] {
+    if (n != (int64_t)t->t.n_cells()) throw std::runtime_error("ifem_tria_execute_refinement: one flag per active cell expected");
+    t->t.execute_refinement(std::vector<unsigned char>(flags, flags + n));
+  });
+}
+int ifem_tria_get_hanging(const ifem_tria *t, int64_t *n_hanging, int *vertex, int *n_masters, int *masters)
+{
+  return guard([&] {
+    const auto &h = t->t.hanging;
+    *n_hanging = (int64_t)h.size();
+    if (!vertex) return;
+    for (size_t k = 0; k < h.size(); ++k)
+      {
+        vertex[k] = h[k].vertex;
+        n_masters[k] = h[k].n_masters;
+        for (int j = 0; j < 4; ++j) masters[4 * k + j] = h[k].master[j];
+      }
+  });
+}
 int ifem_tria_set_material_ids(ifem_tria *t, const int *ids, int64_t n)
 {
   return guard([&] {

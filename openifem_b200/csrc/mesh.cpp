@@ -3,6 +3,7 @@
 #include <map>
 
 #include <algorithm>
+#include <unordered_map>
 #include <cmath>
 #include <numeric>
 #include <stdexcept>
@@ -525,7 +526,178 @@ namespace ifem
         cells.swap(new_cells);
         material_id.swap(new_mat);
         boundary_faces.swap(new_bf);
+        if (!cell_level.empty())
+          {
+            std::vector<int> lv((size_t)nc * vpc);
+            for (int c = 0; c < nc; ++c)
+              for (int child = 0; child < vpc; ++child) lv[(size_t)c * vpc + child] = cell_level[c] + 1;
+            cell_level.swap(lv);
+          }
+        if (!hanging.empty()) find_hanging_vertices();
       }
+  }
+
+  void Triangulation::execute_refinement(const std::vector<unsigned char> &flags)
+  {
+    const int vpc = verts_per_cell(), nc = n_cells();
+    if ((int)flags.size() != nc) throw std::runtime_error("execute_refinement: one flag per active cell expected");
+    if (!chart_of_cell.empty()) throw std::runtime_error("execute_refinement: local refinement of meshes with curved charts is not implemented");
+    bool any = false;
+    for (unsigned char f : flags) any = any || f;
+    if (!any) return;
+    const NodeTable nt = build_node_table(*this, 2);
+    FEQ fe(dim, 2);
+    // Q2 nodes that become vertices: the corners of every cell and all nodes of the flagged cells
+    std::vector<int> new_id((size_t)nt.n_nodes, -1);
+    std::vector<char> used((size_t)nt.n_nodes, 0);
+    auto is_corner = [&](int a) {
+      for (int d = 0; d < dim; ++d)
+        if (fe.lattice[a][d] == 1) return false;
+      return true;
+    };
+    for (int c = 0; c < nc; ++c)
+      for (int a = 0; a < fe.n; ++a)
+        if (flags[c] || is_corner(a)) used[nt.cell_nodes[(size_t)c * fe.n + a]] = 1;
+    int nv_new = 0;
+    for (int i = 0; i < nt.n_nodes; ++i)
+      if (used[i]) new_id[i] = nv_new++;
+    std::vector<double> new_vertices((size_t)nv_new * dim);
+    for (int i = 0; i < nt.n_nodes; ++i)
+      if (used[i])
+        for (int d = 0; d < dim; ++d) new_vertices[(size_t)new_id[i] * dim + d] = nt.coords[(size_t)i * dim + d];
+    std::vector<int> new_cells, new_mat, new_level, first_child((size_t)nc, -1);
+    if (cell_level.empty()) cell_level.assign((size_t)nc, 0);
+    for (int c = 0; c < nc; ++c)
+      {
+        first_child[c] = (int)new_mat.size();
+        if (!flags[c])
+          {
+            for (int v = 0; v < vpc; ++v)
+              {
+                int a = 0, stride = 1;
+                for (int d = 0; d < dim; ++d)
+                  {
+                    a += 2 * ((v >> d) & 1) * stride;
+                    stride *= 3;
+                  }
+                new_cells.push_back(new_id[nt.cell_nodes[(size_t)c * fe.n + a]]);
+              }
+            new_mat.push_back(material_id[c]);
+            new_level.push_back(cell_level[c]);
+            continue;
+          }
+        for (int child = 0; child < vpc; ++child)
+          {
+            for (int v = 0; v < vpc; ++v)
+              {
+                int a = 0, stride = 1;
+                for (int d = 0; d < dim; ++d)
+                  {
+                    a += (((child >> d) & 1) + ((v >> d) & 1)) * stride;
+                    stride *= 3;
+                  }
+                new_cells.push_back(new_id[nt.cell_nodes[(size_t)c * fe.n + a]]);
+              }
+            new_mat.push_back(material_id[c]);
+            new_level.push_back(cell_level[c] + 1);
+          }
+      }
+    std::vector<int> new_bf;
+    for (int f = 0; f < n_boundary_faces(); ++f)
+      {
+        const int c = boundary_faces[3 * f], face = boundary_faces[3 * f + 1], id = boundary_faces[3 * f + 2];
+        const int axis = face / 2, side = face % 2;
+        if (!flags[c])
+          {
+            new_bf.insert(new_bf.end(), {first_child[c], face, id});
+            continue;
+          }
+        for (int child = 0; child < vpc; ++child)
+          if (((child >> axis) & 1) == side) new_bf.insert(new_bf.end(), {first_child[c] + child, face, id});
+      }
+    vertices.swap(new_vertices);
+    cells.swap(new_cells);
+    material_id.swap(new_mat);
+    cell_level.swap(new_level);
+    boundary_faces.swap(new_bf);
+    find_hanging_vertices();
+  }
+
+  void Triangulation::find_hanging_vertices()
+  {
+    hanging.clear();
+    const int nv = n_vertices(), vpc = verts_per_cell(), nc = n_cells();
+    if (!nv) return;
+    // vertex lookup by quantised position
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d) lo[d] = hi[d] = vertices[d];
+    for (int i = 0; i < nv; ++i)
+      for (int d = 0; d < dim; ++d)
+        {
+          lo[d] = std::min(lo[d], vertices[(size_t)i * dim + d]);
+          hi[d] = std::max(hi[d], vertices[(size_t)i * dim + d]);
+        }
+    const double Q = double((1u << 20) - 1);
+    auto key_of = [&](const double *x) {
+      uint64_t key = 0;
+      for (int d = dim - 1; d >= 0; --d)
+        {
+          const double ext = hi[d] - lo[d];
+          const double t = ext > 0 ? (x[d] - lo[d]) / ext : 0.0;
+          key = (key << 21) | (uint64_t)std::llround(t * Q * 2.0); // half steps: a midpoint never rounds onto a vertex of its edge
+        }
+      return key;
+    };
+    std::unordered_map<uint64_t, int> at;
+    at.reserve((size_t)nv * 2);
+    for (int i = 0; i < nv; ++i) at.emplace(key_of(&vertices[(size_t)i * dim]), i);
+    std::unordered_map<int, Hanging> found;
+    auto consider = [&](const int *ids, int n) {
+      double x[3] = {0, 0, 0};
+      for (int k = 0; k < n; ++k)
+        for (int d = 0; d < dim; ++d) x[d] += vertices[(size_t)ids[k] * dim + d];
+      for (int d = 0; d < dim; ++d) x[d] /= n;
+      auto it = at.find(key_of(x));
+      if (it == at.end()) return;
+      const int h = it->second;
+      for (int k = 0; k < n; ++k)
+        if (ids[k] == h) return;
+      Hanging hn;
+      hn.vertex = h;
+      hn.n_masters = n;
+      for (int k = 0; k < n; ++k) hn.master[k] = ids[k];
+      std::sort(hn.master, hn.master + n);
+      auto ins = found.emplace(h, hn);
+      if (!ins.second && ins.first->second.n_masters < n) ins.first->second = hn; // (cannot happen on a 2:1 mesh)
+    };
+    for (int c = 0; c < nc; ++c)
+      {
+        const int *cv = &cells[(size_t)c * vpc];
+        // edges: pairs of corners that differ in one direction
+        for (int v = 0; v < vpc; ++v)
+          for (int d = 0; d < dim; ++d)
+            if (!((v >> d) & 1))
+              {
+                const int e[2] = {cv[v], cv[v | (1 << d)]};
+                consider(e, 2);
+              }
+        if (dim == 3)
+          for (int face = 0; face < 6; ++face)
+            {
+              const int axis = face / 2, side = face % 2;
+              int f[4], k = 0;
+              for (int v = 0; v < 8; ++v)
+                if (((v >> axis) & 1) == side) f[k++] = cv[v];
+              consider(f, 4);
+            }
+      }
+    for (auto &kv : found) hanging.push_back(kv.second);
+    std::sort(hanging.begin(), hanging.end(), [](const Hanging &a, const Hanging &b) { return a.vertex < b.vertex; });
+    for (const Hanging &h : hanging)
+      for (int k = 0; k < h.n_masters; ++k)
+        if (found.count(h.master[k]))
+          throw std::runtime_error("local refinement: a hanging vertex would depend on another hanging vertex (more than one level of "
+                                   "difference across an edge); refine the neighbouring cells as well");
   }
 
   // ---------------------------------------------------------------------------

@@ -47,7 +47,25 @@ namespace ifem
     int n_boundary_faces() const { return (int)(boundary_faces.size() / 3); }
     int n_active_cells() const { return n_cells(); }
 
+    // Hanging vertices of a locally refined mesh (one level of difference across an edge / face, as deal.II keeps it): vertex h
+    // sits at the midpoint of a coarse edge (2 masters) or at the centre of a coarse face (3-D, 4 masters) and carries the mean of
+    // its masters in a continuous FE_Q(1) field (DoFTools::make_hanging_node_constraints, source/mpi_fluid_solver.cpp:182-184)
+    struct Hanging
+    {
+      int vertex = -1, n_masters = 0;
+      int master[4] = {-1, -1, -1, -1};
+    };
+    std::vector<Hanging> hanging;
+    std::vector<int> cell_level; // [n_cells] refinement level of every active cell (empty: all 0)
+
     void refine_global(int times);
+    // cell->set_refine_flag() on the flagged cells + execute_coarsening_and_refinement() (tests/fsi_leaflet_mpi/fsi_leaflet_mpi.cpp:
+    // 66-76): flagged cells are replaced by their 2^dim children, the others stay; straight-sided meshes only (no charts).
+    // Throws if the result would put a hanging vertex on a master that is itself hanging (deal.II would refine further cells
+    // to keep the 2:1 balance; callers here flag whole bands).
+    void execute_refinement(const std::vector<unsigned char> &refine_flags);
+    // recompute `hanging` from the geometry of the active cells
+    void find_hanging_vertices();
   };
 
   namespace GridGenerator

@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -125,58 +127,94 @@ namespace oracle
     return (it != e && *it == c) ? (it - col) : -1;
   }
 
-  // AffineConstraints::distribute_local_to_global for constraints that are pure
-  // Dirichlet lines (no hanging nodes): unconstrained row i gets its
-  // unconstrained columns, rhs_i -= sum_j(constrained) K_ij * inhomogeneity_j;
-  // a constrained row only receives |K_ii| (or the average |diag| of the local
-  // matrix if that is zero) on the diagonal and, when
-  // use_inhomogeneities_for_rhs, rhs_i += diag * inhomogeneity_i.
+  // Constraint lines with masters (hanging nodes of a locally refined mesh, DoFTools::make_hanging_node_constraints at
+  // reference source/mpi_fluid_solver.cpp:182-184), already resolved as AffineConstraints::close() leaves them: a dof g with
+  // con[g] == 2 equals sum_k weight[k] * x[master[k]] + inhom[g] over ptr[g] <= k < ptr[g + 1], every master unconstrained.
+  // Set through oracle_set_constraint_lines (oracle_ins.cpp) before an assembly; empty = pure Dirichlet lines only.
+  struct ConstraintLines
+  {
+    std::vector<int64_t> ptr;
+    std::vector<int> master;
+    std::vector<double> weight;
+  };
+  inline ConstraintLines &constraint_lines()
+  {
+    static ConstraintLines lines;
+    return lines;
+  }
+
+  // AffineConstraints::distribute_local_to_global: an unconstrained local row i goes to its global row, a row with a
+  // hanging-node line (con == 2) to the rows of its masters with their weights, a Dirichlet row (con == 1) nowhere;
+  // columns likewise, and every constrained column j moves K_ij * inhomogeneity_j to the right-hand side of the target
+  // rows. A constrained row itself only receives |K_ii| (or the average |diag| of the local matrix if that is zero) on
+  // the diagonal and, when use_inhomogeneities_for_rhs, rhs_i += diag * inhomogeneity_i.
   // Restated from deal.II's documented algorithm
-  // (affine_constraints.templates.h, set_matrix_diagonals / resolve_vector_entry);
-  // call sites: reference mpi_insim.cpp:348-355, mpi_hyper_elasticity.cpp:507-522.
+  // (affine_constraints.templates.h, make_sorted_row_list / set_matrix_diagonals / resolve_vector_entry);
+  // call sites: reference mpi_insim.cpp:348-355, mpi_scnsim.cpp:548-560, mpi_hyper_elasticity.cpp:507-522.
   inline void distribute_local_to_global(int n, const double *K, const double *f, const int *dofs,
                                          const unsigned char *con, const double *inhom,
                                          const int64_t *rowptr, const int *col, double *A, double *rhs,
                                          bool use_inhomogeneities_for_rhs)
   {
+    const ConstraintLines &L = constraint_lines();
+    auto add = [&](int r, int c, double v) {
+      const int64_t p = csr_find(rowptr, col, r, c);
+      if (p < 0)
+        {
+          std::fprintf(stderr, "oracle: entry (%d, %d) is missing from the sparsity pattern\n", r, c);
+          std::abort();
+        }
+#pragma omp atomic
+      A[p] += v;
+    };
     double average_diagonal = 0;
     for (int i = 0; i < n; ++i) average_diagonal += std::fabs(K[i * n + i]);
     average_diagonal /= n;
     for (int i = 0; i < n; ++i)
       {
         const int gi = dofs[i];
+        int n_rows = 1, one_row = gi;
+        const int *rows = &one_row;
+        double one_w = 1.0;
+        const double *row_w = &one_w;
         if (con[gi])
           {
             const double d = std::fabs(K[i * n + i]) != 0 ? std::fabs(K[i * n + i]) : average_diagonal;
-            const int64_t p = csr_find(rowptr, col, gi, gi);
-#pragma omp atomic
-            A[p] += d;
+            add(gi, gi, d);
             if (rhs && use_inhomogeneities_for_rhs && inhom)
               {
 #pragma omp atomic
                 rhs[gi] += d * inhom[gi];
               }
-            continue;
+            if (con[gi] != 2) continue;
+            n_rows = (int)(L.ptr[gi + 1] - L.ptr[gi]);
+            rows = L.master.data() + L.ptr[gi];
+            row_w = L.weight.data() + L.ptr[gi];
           }
-        double fi = f ? f[i] : 0.0;
-        for (int j = 0; j < n; ++j)
+        for (int t = 0; t < n_rows; ++t)
           {
-            const int gj = dofs[j];
-            const double kij = K[i * n + j];
-            if (con[gj])
+            const int r = rows[t];
+            const double wr = row_w[t];
+            double fi = f ? wr * f[i] : 0.0;
+            for (int j = 0; j < n; ++j)
               {
-                if (inhom) fi -= kij * inhom[gj];
-                continue;
+                const int gj = dofs[j];
+                const double kij = K[i * n + j];
+                if (con[gj])
+                  {
+                    if (inhom) fi -= wr * kij * inhom[gj];
+                    if (con[gj] == 2 && kij != 0.0)
+                      for (int64_t k = L.ptr[gj]; k < L.ptr[gj + 1]; ++k) add(r, L.master[k], wr * L.weight[k] * kij);
+                    continue;
+                  }
+                if (kij == 0.0) continue; // deal.II elides exact zeros
+                add(r, gj, wr * kij);
               }
-            if (kij == 0.0) continue; // deal.II elides exact zeros
-            const int64_t p = csr_find(rowptr, col, gi, gj);
+            if (rhs)
+              {
 #pragma omp atomic
-            A[p] += kij;
-          }
-        if (rhs)
-          {
-#pragma omp atomic
-            rhs[gi] += fi;
+                rhs[r] += fi;
+              }
           }
       }
   }

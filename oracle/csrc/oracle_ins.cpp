@@ -219,6 +219,20 @@ extern "C" int oracle_ins_assemble(
 
 // y = A x, CSR, one OpenMP thread team standing in for the MPI ranks of
 // PETSc MatMult (reference call sites: mpi_insim.cpp:388 via SolverFGMRES, :117).
+// Constraint lines with masters for the next assemblies of every oracle cell loop (n_dofs = 0 clears them); see
+// oracle_common.h ConstraintLines.
+extern "C" void oracle_set_constraint_lines(int64_t n_dofs, const int64_t *ptr, const int *master, const double *weight)
+{
+  oracle::ConstraintLines &L = oracle::constraint_lines();
+  L.ptr.clear();
+  L.master.clear();
+  L.weight.clear();
+  if (n_dofs <= 0) return;
+  L.ptr.assign(ptr, ptr + n_dofs + 1);
+  L.master.assign(master, master + ptr[n_dofs]);
+  L.weight.assign(weight, weight + ptr[n_dofs]);
+}
+
 extern "C" void oracle_spmv_csr(int64_t n_rows, const int64_t *rowptr, const int *col, const double *val, const double *x,
                                 double *y)
 {

@@ -170,12 +170,105 @@ class FluidDofs:
         pdofs = self.n_u + self.pnodes
         self.cell_dofs = np.concatenate([udofs, pdofs], axis=1).astype(np.int32)
         self.dofs_per_cell = self.cell_dofs.shape[1]
+        # hanging nodes of a locally refined mesh (DoFTools::make_hanging_node_constraints, mpi_fluid_solver.cpp:182-184)
+        self.hanging_u, self.hanging_p = {}, {}
+        if not isinstance(mesh, BoxMesh):  # a box mesh is uniform by construction
+            if pu == 1 and pp == 1:
+                self.hanging_u = hanging_nodes(self.unodes, self.ucoords)
+                self.hanging_p = hanging_nodes(self.pnodes, self.pcoords)
+            elif hanging_nodes(*mesh.node_table(1)[::2]):
+                raise NotImplementedError("hanging-node constraints are restated for FE_Q(1) velocity and pressure only")
+        self.hanging_dofs = {}  # dof -> (master dofs, weights), same component as the slave
+        for h, (ms, w) in self.hanging_u.items():
+            for c in range(dim):
+                self.hanging_dofs[dim * h + c] = (dim * ms + c, w)
+        for h, (ms, w) in self.hanging_p.items():
+            self.hanging_dofs[self.n_u + h] = (self.n_u + ms, w)
+        self.is_hanging = np.zeros(self.n_dofs, dtype=bool)
+        self.is_hanging[list(self.hanging_dofs)] = True
 
     def support_points(self):
         pts = np.zeros((self.n_dofs, self.dim))
         pts[: self.n_u] = np.repeat(self.ucoords, self.dim, axis=0)
         pts[self.n_u:] = self.pcoords
         return pts
+
+
+def hanging_nodes(tab, coords):
+    """Hanging nodes of FE_Q(1) on a mesh with at most one level of difference between neighbouring cells, found from the
+    geometry alone: a node that sits at the midpoint of another cell's edge is constrained to the mean of the two edge ends,
+    one at the centre of another cell's face (3-D) to the mean of the four face corners - the constraint lines
+    DoFTools::make_hanging_node_constraints writes for Q1 (reference source/mpi_fluid_solver.cpp:182-184). Returns
+    {node: (masters, weight)}; tab is the FE_Q(1) node table. FE_Q(2) on locally refined meshes is not restated."""
+    dim = coords.shape[1]
+    lo, hi = coords.min(axis=0), coords.max(axis=0)
+    ext = np.where(hi > lo, hi - lo, 1.0)
+
+    def keys(x):  # half steps of a 2^20 lattice: a midpoint never rounds onto an end of its edge
+        q = np.rint((x - lo) / ext * float((1 << 21) - 2)).astype(np.int64)
+        k = np.zeros(q.shape[0], dtype=np.int64)
+        for d in range(dim - 1, -1, -1):
+            k = (k << 21) | q[:, d]
+        return k
+
+    node_key = keys(coords)
+    order = np.argsort(node_key)
+    sorted_key = node_key[order]
+    out = {}
+    groups = []
+    for v in range(1 << dim):
+        for d in range(dim):
+            if not (v >> d) & 1:
+                groups.append((v, v | (1 << d)))
+    if dim == 3:
+        for axis in range(3):
+            for side in (0, 1):
+                groups.append(tuple(v for v in range(8) if ((v >> axis) & 1) == side))
+    for g in groups:
+        ids = tab[:, list(g)]  # [nc][2 or 4]
+        k = keys(coords[ids].mean(axis=1))
+        pos = np.minimum(np.searchsorted(sorted_key, k), sorted_key.size - 1)
+        hit = sorted_key[pos] == k
+        for c in np.nonzero(hit)[0]:
+            h = int(order[pos[c]])
+            if h in ids[c]:
+                continue
+            if h not in out or len(out[h][0]) < ids.shape[1]:
+                out[h] = (np.sort(ids[c]).astype(np.int64), 1.0 / ids.shape[1])
+    for h, (ms, _) in out.items():
+        assert not any(int(m) in out for m in ms), "a hanging node depends on another hanging node"
+    return out
+
+
+def resolve_constraints(dofs, con, val):
+    """AffineConstraints::close() for the lines of one constraint object: hanging-node lines whose masters carry a Dirichlet
+    value have that master replaced by its value (it adds weight * value to the line's inhomogeneity). Returns
+    (flag [n_dofs]: 0 free, 1 line without masters, 2 line with masters; inhomogeneity [n_dofs]; ptr, master, weight of
+    the lines in CSR form over all dofs)."""
+    con2, val2 = con.copy(), val.copy()
+    ptr = np.zeros(dofs.n_dofs + 1, dtype=np.int64)
+    masters, weights = {}, {}
+    for g, (ms, w) in dofs.hanging_dofs.items():
+        assert not con[g], "a hanging dof carries its hanging-node line only (interpolate_boundary_values skips constrained dofs)"
+        keep = [int(m) for m in ms if not con[m]]
+        val2[g] = sum(w * val[m] for m in ms if con[m])
+        con2[g] = 2 if keep else 1
+        masters[g], weights[g] = keep, [w] * len(keep)
+        ptr[g + 1] = len(keep)
+    ptr = np.cumsum(ptr)
+    master = np.zeros(max(1, int(ptr[-1])), dtype=np.int32)
+    weight = np.zeros(max(1, int(ptr[-1])))
+    for g in masters:
+        master[ptr[g]:ptr[g + 1]] = masters[g]
+        weight[ptr[g]:ptr[g + 1]] = weights[g]
+    return con2, val2, ptr, master, weight
+
+
+def distribute(dofs, x):
+    """AffineConstraints::distribute for the hanging-node lines, after the Dirichlet entries of x were set"""
+    for g, (ms, w) in dofs.hanging_dofs.items():
+        x[g] = w * x[ms].sum()
+    return x
 
 
 def component_mask(flag: int, dim: int):
@@ -204,7 +297,7 @@ def make_dirichlet_constraints(dofs: FluidDofs, dirichlet_bcs: dict, hard_coded=
                 node = dofs.unodes[cell, a]
                 for c in comps:
                     g = dim * node + c
-                    if con[g]:
+                    if con[g] or dofs.is_hanging[g]:  # an existing line (also a hanging-node one) is never overwritten
                         continue
                     con[g] = 1
                     if hard_coded is not None and bid in hard_coded:
@@ -214,14 +307,27 @@ def make_dirichlet_constraints(dofs: FluidDofs, dirichlet_bcs: dict, hard_coded=
     return con, val
 
 
-def full_pattern(cell_dofs, n_dofs):
+def full_pattern(cell_dofs, n_dofs, hanging_dofs=None):
     """DoFTools::make_sparsity_pattern without coupling table: every dof of a
-    cell couples with every other (mpi_fluid_solver.cpp:311-312). CSR, sorted."""
+    cell couples with every other (mpi_fluid_solver.cpp:311-312); with hanging-node lines the masters of a cell's
+    hanging dofs couple with the cell's dofs and with each other as well. CSR, sorted."""
     import scipy.sparse as sp
 
     nc, k = cell_dofs.shape
     rows = np.repeat(cell_dofs, k, axis=1).ravel()
     cols = np.tile(cell_dofs, (1, k)).ravel()
+    if hanging_dofs:
+        er, ec = [], []
+        for cd in cell_dofs:
+            extra = [int(m) for g in cd if int(g) in hanging_dofs for m in hanging_dofs[int(g)][0]]
+            if not extra:
+                continue
+            full = np.unique(np.concatenate([cd, extra]))
+            er.append(np.repeat(full, full.size))
+            ec.append(np.tile(full, full.size))
+        if er:
+            rows = np.concatenate([rows] + er)
+            cols = np.concatenate([cols] + ec)
     A = sp.coo_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)), shape=(n_dofs, n_dofs)).tocsr()
     A.sort_indices()
     return A.indptr.astype(np.int64), A.indices.astype(np.int32)

@@ -407,7 +407,7 @@ class FSI:
         acc, icon, iinh = find_fluid_bc(f, geo, f.indicator, s.cur_v, s.cur_a, f.dt, self.use_dirichlet_bc)
         f.fsi_acceleration[:] = acc
         if self.use_dirichlet_bc:
-            new = (icon != 0) & (f.con == 0)
+            new = (icon != 0) & (f.con == 0) & ~f.dofs.is_hanging  # merge(..., left_object_wins): existing lines stay
             f.con[new] = 1
             f.nonzero_val[new] = iinh[new]
         f.run_one_step(True)

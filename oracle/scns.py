@@ -66,7 +66,7 @@ class SCnsIM:
         self.dNgeo_face = np.ascontiguousarray(np.stack(dGf))
         self.hard_coded, self.bc_time = hard_coded, 0.0
         self.con, self.nonzero_val = fem.make_dirichlet_constraints(d, params.fluid_dirichlet_bcs, hard_coded)
-        self.rowptr, self.col = fem.full_pattern(d.cell_dofs, self.n)
+        self.rowptr, self.col = fem.full_pattern(d.cell_dofs, self.n, d.hanging_dofs)
         self.h_type, self.h_node = h_shape_functions(dim, pu, pp, d.dofs_per_cell)
         self.present = np.zeros(self.n)
         self.evaluation_point = np.zeros(self.n)
@@ -101,11 +101,25 @@ class SCnsIM:
         Mref = np.einsum("qi,qj,q->ij", self.Nu, self.Nu, self.qw)
         self.qpt_to_dof = np.linalg.solve(Mref, (self.Nu * self.qw[:, None]).T)
 
+    def _closed_constraints(self, use_nonzero_constraints: bool):
+        """(flags, inhomogeneities or None) of nonzero_constraints / zero_constraints after close(); hanging-node lines
+        (locally refined meshes) are handed to the C cell loops through oracle_set_constraint_lines"""
+        if not self.dofs.hanging_dofs:
+            return self.con, (self.nonzero_val if use_nonzero_constraints else None)
+        val = self.nonzero_val if use_nonzero_constraints else np.zeros(self.n)
+        con, inhom, ptr, master, weight = fem.resolve_constraints(self.dofs, self.con, val)
+        lib().oracle_set_constraint_lines(C.c_int64(self.n), _p(ptr, C.c_int64), _p(master, C.c_int), _p(weight))
+        return con, (np.ascontiguousarray(inhom) if use_nonzero_constraints else None)
+
+    def _release_constraints(self):
+        if self.dofs.hanging_dofs:
+            lib().oracle_set_constraint_lines(C.c_int64(0), None, None, None)
+
     def assemble(self, use_nonzero_constraints: bool):
         p = self.prm
         A = np.zeros(self.col.size)
         rhs = np.zeros(self.n)
-        inhom = self.nonzero_val if use_nonzero_constraints else None
+        con, inhom = self._closed_constraints(use_nonzero_constraints)
         nids = np.asarray(sorted(p.fluid_neumann_bcs), dtype=np.int32)
         nvals = np.asarray([p.fluid_neumann_bcs[i] for i in nids], dtype=np.float64)
         grav = np.asarray(p.gravity, dtype=np.float64)
@@ -119,8 +133,9 @@ class SCnsIM:
             _p(self.indicator, C.c_int), _p(stress), _p(fsis), C.c_int(self.dofs.n_unodes), _p(self.sigma_pml), _p(self.body_force),
             C.c_int(self.h_type.size), _p(self.h_type, C.c_int), _p(self.h_node, C.c_int), C.c_double(p.viscosity),
             C.c_double(p.fluid_rho), C.c_double(p.solid_rho), C.c_double(self.dt), _p(grav), C.c_int(self.bfaces.shape[0]),
-            _p(self.bfaces, C.c_int), C.c_int(nids.size), _p(nids, C.c_int), _p(nvals), _p(self.con, C.c_ubyte), _p(inhom),
+            _p(self.bfaces, C.c_int), C.c_int(nids.size), _p(nids, C.c_int), _p(nvals), _p(con, C.c_ubyte), _p(inhom),
             _p(self.rowptr, C.c_int64), _p(self.col, C.c_int), _p(A), _p(rhs))
+        self._release_constraints()
         assert rc == 0
         self.system_matrix = sp.csr_matrix((A, self.col, self.rowptr), shape=(self.n, self.n))
         self.system_rhs = rhs
@@ -129,6 +144,7 @@ class SCnsIM:
     def solve(self, use_nonzero_constraints: bool):
         x = spla.spsolve(self.system_matrix.tocsc(), self.system_rhs)
         x[self.con != 0] = self.nonzero_val[self.con != 0] if use_nonzero_constraints else 0.0
+        fem.distribute(self.dofs, x)  # constraints.distribute(newton_update), mpi_supg_solver.cpp:323-325
         self.newton_update = x
         return 0, 0.0
 
@@ -212,7 +228,7 @@ class SUPGInsIM(SCnsIM):
         p = self.prm
         A = np.zeros(self.col.size)
         rhs = np.zeros(self.n)
-        inhom = self.nonzero_val if use_nonzero_constraints else None
+        con, inhom = self._closed_constraints(use_nonzero_constraints)
         nids = np.asarray(sorted(p.fluid_neumann_bcs), dtype=np.int32)
         nvals = np.asarray([p.fluid_neumann_bcs[i] for i in nids], dtype=np.float64)
         grav = np.asarray(p.gravity, dtype=np.float64)
@@ -223,7 +239,8 @@ class SUPGInsIM(SCnsIM):
             _p(self.evaluation_point), _p(self.present), _p(self.body_force), C.c_int(self.h_type.size), _p(self.h_type, C.c_int),
             _p(self.h_node, C.c_int), C.c_double(p.viscosity), C.c_double(p.fluid_rho), C.c_double(self.dt), _p(grav),
             C.c_int(self.bfaces.shape[0]), _p(self.bfaces, C.c_int), C.c_int(nids.size), _p(nids, C.c_int), _p(nvals),
-            _p(self.con, C.c_ubyte), _p(inhom), _p(self.rowptr, C.c_int64), _p(self.col, C.c_int), _p(A), _p(rhs))
+            _p(con, C.c_ubyte), _p(inhom), _p(self.rowptr, C.c_int64), _p(self.col, C.c_int), _p(A), _p(rhs))
+        self._release_constraints()
         assert rc == 0
         self.system_matrix = sp.csr_matrix((A, self.col, self.rowptr), shape=(self.n, self.n))
         self.system_rhs = rhs

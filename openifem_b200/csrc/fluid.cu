@@ -109,12 +109,18 @@ namespace ifem
       P.col.resize(P.rowptr[n_owned]);
       return P;
     };
-    P_uu = owned_rows(build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, un.cell_nodes.data(), nu, un.n_nodes), n_owned_unodes);
+    // locally refined mesh: the masters of a cell's hanging nodes couple with the cell's nodes (extended per-cell lists)
+    std::vector<int> ext_un, ext_pn;
+    int ext_w = 0;
+    hanging.find(tria, *this, ext_un, ext_pn, ext_w);
+    const int *tu = hanging.active ? ext_un.data() : un.cell_nodes.data(), *tp = hanging.active ? ext_pn.data() : pn.cell_nodes.data();
+    const int wu = hanging.active ? ext_w : nu, wp = hanging.active ? ext_w : np;
+    P_uu = owned_rows(build_pattern(n_cells, tu, wu, un.n_nodes, tu, wu, un.n_nodes), n_owned_unodes);
     // A_up keeps the rows of the layer-1 ghost velocity nodes as well: B^T rows the explicit Schur complement of
     // the owned pressure rows needs (complete, because every cell around a layer-1 node is local)
-    P_up = owned_rows(build_pattern(n_cells, un.cell_nodes.data(), nu, un.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes), n_layer1_unodes);
-    P_pu = owned_rows(build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, un.cell_nodes.data(), nu, un.n_nodes), n_owned_pnodes);
-    P_pp = owned_rows(build_pattern(n_cells, pn.cell_nodes.data(), np, pn.n_nodes, pn.cell_nodes.data(), np, pn.n_nodes), n_owned_pnodes);
+    P_up = owned_rows(build_pattern(n_cells, tu, wu, un.n_nodes, tp, wp, pn.n_nodes), n_layer1_unodes);
+    P_pu = owned_rows(build_pattern(n_cells, tp, wp, pn.n_nodes, tu, wu, un.n_nodes), n_owned_pnodes);
+    P_pp = owned_rows(build_pattern(n_cells, tp, wp, pn.n_nodes, tp, wp, pn.n_nodes), n_owned_pnodes);
     colour_cells(n_cells, un.cell_nodes.data(), nu, un.n_nodes, colour_order, colour_offsets);
     // inside every colour: cells that touch an owned node first (the ones every assembly visits)
     colour_n1.assign(colour_offsets.size() - 1, 0);
@@ -183,6 +189,7 @@ namespace ifem
     launch(np, nu, d_cell_pn, d_cell_un, A_pu, nu * nu + nu * np);
     launch(np, np, d_cell_pn, d_cell_pn, M_p, nu * nu + 2 * nu * np);
     if (err.to_host(s)[0]) throw std::runtime_error("FluidSpace::setup: a matrix row has more than 256 block columns");
+    hanging.plan(ctx, *this);
 
     // pattern of B B^T on the owned pressure rows (compute_mmult_pattern, mpi_fluid_solver.cpp:326-329)
     P_schur = product_pattern(P_pu, P_up, pn.n_nodes);
@@ -241,6 +248,7 @@ namespace ifem
     // triangulation), so "first boundary id wins" cannot depend on the partition; the flags are then
     // restricted to the local dofs.
     const NodeTable &g = n_ranks > 1 ? un_global : un;
+    const std::vector<char> hflag = hanging.active ? hanging_node_flags(tria, g) : std::vector<char>();
     std::vector<unsigned char> gcon((size_t)dim * g.n_nodes, 0);
     std::vector<double> gval((size_t)dim * g.n_nodes, 0.0);
     std::vector<std::vector<int>> face_nodes(2 * dim);
@@ -262,6 +270,7 @@ namespace ifem
             for (int a : face_nodes[face])
               {
                 const int node = g.cell_nodes[(size_t)cell * nu + a];
+                if (!hflag.empty() && hflag[node]) continue; // keeps its hanging-node line (made first, mpi_fluid_solver.cpp:182-184)
                 for (int c = 0; c < dim; ++c)
                   {
                     if (!(flag & (1u << c))) continue;

@@ -16,6 +16,7 @@
 
 #include "fe_tables.h"
 #include "halo.h"
+#include "hanging.h"
 #include "linalg.h"
 #include "mesh.h"
 #include "parameters.h"
@@ -55,6 +56,8 @@ namespace ifem
     // constraints (host mirror): flag per dof, nonzero value per dof
     std::vector<unsigned char> con;
     std::vector<double> nonzero_val;
+    // hanging-node lines of a locally refined mesh (FE_Q(1) spaces): condensed after the cell loop, see hanging.h
+    HangingConstraints hanging;
 
     // ---- device ----
     DevBuf<int> d_cell_un, d_cell_pn, d_colour_order;

@@ -1269,8 +1269,9 @@ namespace ifem
         const std::vector<unsigned char> ic = d_inner_con.to_host(s);
         const std::vector<double> ih = d_inner_inhom.to_host(s);
         bool changed = false;
+        const std::vector<char> &hanging = fs.hanging.is_hanging_dof; // an existing hanging-node line wins as well
         for (int64_t g = 0; g < fs.n_dofs; ++g)
-          if (ic[g] && !fs.con[g])
+          if (ic[g] && !fs.con[g] && (hanging.empty() || !hanging[g]))
             {
               fs.con[g] = 1;
               fs.nonzero_val[g] = ih[g];

@@ -111,5 +111,6 @@ namespace ifem
         ctx.kernel_launches++;
       }
     neumann_faces(ctx, fs); // the pressure face term of :292-321 is InsIM's
+    fs.hanging.condense(ctx, fs, a.inhom); // hanging-node lines of a locally refined mesh
   }
 } // namespace ifem

@@ -558,6 +558,7 @@ namespace ifem
         ctx.kernel_launches++;
       }
     neumann_faces(ctx, fs); // same pressure face term as InsIM (:516-546)
+    fs.hanging.condense(ctx, fs, a.inhom); // hanging-node lines of a locally refined mesh (distribute_local_to_global, :548-560)
   }
 
   // BlockIncompSchurPreconditioner::vmult (mpi_supg_solver.cpp:137-192). The two Hypre-Euclid ILU(0) factors
@@ -638,6 +639,7 @@ namespace ifem
     else
       fill(ctx, va, 0.0, newton_update.p);
     if (fs.n_con) set_indexed(ctx, fs.n_con, fs.d_con_idx.p, use_nonzero_constraints ? d_con_vals.p : nullptr, newton_update.p);
+    fs.hanging.distribute(ctx, fs, newton_update.p); // constraints.distribute(newton_update), mpi_supg_solver.cpp:323-325
     return {(unsigned)r.iterations, r.residual};
   }
 

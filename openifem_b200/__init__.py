@@ -683,6 +683,12 @@ class _FSI:
         check(lib().ifem_fsi_get_indicator(self._h, iptr(ind)))
         return ind
 
+    def get_indicator(self):
+        """CellProperty::indicator of the local fluid cells as the last update_indicator() left it"""
+        ind = np.empty(self.fluid.tria.n_active_cells() if self.fluid.partition(0)[0] == self.fluid.partition(0)[1] else self._n_local_cells(), dtype=np.int32)
+        check(lib().ifem_fsi_get_indicator(self._h, iptr(ind)))
+        return ind
+
     def _n_local_cells(self):
         raise NotImplementedError("indicator download on multi-rank runs: use the C ABI with the local cell count")
 
@@ -817,5 +823,6 @@ class Fluid:
 class Solid:
     class MPI:
         HyperElasticity = _HyperElasticity
+        SharedHyperElasticity = _HyperElasticity  # the replicated twin MPI::FSI takes (`Simulation type = FSI` selects its Newton stop)
         LinearElasticity = _LinearElasticity
         SharedLinearElasticity = _SharedLinearElasticity

@@ -7,11 +7,112 @@
 
 namespace ifem
 {
+  namespace
+  {
+    // Slabs bounded by mesh planes for a locally refined mesh. A hanging node and its masters must end up with the same
+    // owner (hanging.h: the rows of a hanging node are folded into the rows of its masters on one rank); with "a node
+    // belongs to the lowest rank of its cells" that holds when no cut plane carries a hanging node or a master and no cell
+    // straddles a cut. The slab axis is the last one along which enough such planes exist (the band-refined channels of the
+    // reference: the z planes of fsi-wall-3D except z = 2 and z = 2.4, the x planes of fsi_leaflet except x = 0.8 and 1.3).
+    bool plane_slabs(const Triangulation &tria, int size, int axis, std::vector<int> &rank_of)
+    {
+      const int dim = tria.dim, nc = tria.n_cells(), vpc = tria.verts_per_cell();
+      double lo = 1e300, hi = -1e300;
+      for (int v = 0; v < tria.n_vertices(); ++v)
+        {
+          lo = std::min(lo, tria.vertices[(size_t)v * dim + axis]);
+          hi = std::max(hi, tria.vertices[(size_t)v * dim + axis]);
+        }
+      const double Q = double((1u << 24) - 1) / std::max(hi - lo, 1e-300);
+      auto quant = [&](double x) { return (int64_t)std::llround((x - lo) * Q); };
+      std::vector<int64_t> bottom(nc), top(nc), planes;
+      for (int c = 0; c < nc; ++c)
+        {
+          double b = 1e300, t = -1e300;
+          for (int v = 0; v < vpc; ++v)
+            {
+              const double x = tria.vertices[(size_t)tria.cells[(size_t)c * vpc + v] * dim + axis];
+              b = std::min(b, x);
+              t = std::max(t, x);
+            }
+          bottom[c] = quant(b);
+          top[c] = quant(t);
+          planes.push_back(top[c]);
+        }
+      std::sort(planes.begin(), planes.end());
+      planes.erase(std::unique(planes.begin(), planes.end()), planes.end());
+      planes.pop_back(); // the far side of the domain
+      const int np = (int)planes.size();
+      if (np < size - 1) return false;
+      auto index_of = [&](int64_t q) { return (int)(std::lower_bound(planes.begin(), planes.end(), q) - planes.begin()); };
+      std::vector<int> straddle(np + 1, 0), below(np + 1, 0);
+      for (int c = 0; c < nc; ++c)
+        {
+          // planes strictly between bottom and top of the cell
+          const int a = (int)(std::upper_bound(planes.begin(), planes.end(), bottom[c]) - planes.begin());
+          const int b = index_of(top[c]);
+          if (b > a)
+            {
+              straddle[a]++;
+              straddle[b]--;
+            }
+          below[std::min(b, np)]++; // cells whose top is plane b lie below every plane >= b
+        }
+      std::vector<char> allowed(np, 1);
+      int run = 0, cum = 0;
+      std::vector<int> count_below(np, 0);
+      for (int k = 0; k < np; ++k)
+        {
+          run += straddle[k];
+          if (run > 0) allowed[k] = 0;
+          cum += below[k];
+          count_below[k] = cum;
+        }
+      for (const auto &h : tria.hanging)
+        {
+          auto forbid = [&](int vertex) {
+            const int64_t q = quant(tria.vertices[(size_t)vertex * dim + axis]);
+            const int k = index_of(q);
+            if (k < np && planes[k] == q) allowed[k] = 0;
+          };
+          forbid(h.vertex);
+          for (int k = 0; k < h.n_masters; ++k) forbid(h.master[k]);
+        }
+      std::vector<int64_t> cuts;
+      int last = -1;
+      for (int r = 1; r < size; ++r)
+        {
+          const double want = (double)nc * r / size;
+          int best = -1;
+          for (int k = last + 1; k < np; ++k)
+            if (allowed[k] && (best < 0 || std::fabs(count_below[k] - want) < std::fabs(count_below[best] - want))) best = k;
+          if (best < 0) return false;
+          cuts.push_back(planes[best]);
+          last = best;
+        }
+      rank_of.assign(nc, 0);
+      for (int c = 0; c < nc; ++c) rank_of[c] = (int)(std::upper_bound(cuts.begin(), cuts.end(), bottom[c]) - cuts.begin());
+      // every rank needs cells
+      std::vector<int> cnt(size, 0);
+      for (int c = 0; c < nc; ++c) cnt[rank_of[c]]++;
+      for (int r = 0; r < size; ++r)
+        if (!cnt[r]) return false;
+      return true;
+    }
+  } // namespace
+
   std::vector<int> slab_cell_ranks(const Triangulation &tria, int size)
   {
     const int dim = tria.dim, nc = tria.n_cells(), vpc = tria.verts_per_cell();
     std::vector<int> rank_of(nc, 0);
     if (size <= 1) return rank_of;
+    if (!tria.hanging.empty())
+      {
+        for (int axis = dim - 1; axis >= 0; --axis)
+          if (plane_slabs(tria, size, axis, rank_of)) return rank_of;
+        throw std::runtime_error("partition: no slab decomposition of the locally refined mesh keeps every hanging node with its masters "
+                                 "on one rank (fewer ranks, or a refinement band across one axis)");
+      }
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int v = 0; v < tria.n_vertices(); ++v)
       for (int d = 0; d < dim; ++d)

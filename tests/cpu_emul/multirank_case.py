@@ -50,6 +50,11 @@ def main():
     tria = ifem.Triangulation(dim)
     ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, (1,) * dim, True)
     q1 = solver in ("SCnsIM", "SUPGInsIM")
+    refined = "refined" in sys.argv[7 + dim:]
+    if refined:  # a band across the last axis refined once: hanging nodes on two planes (the meshes of BASELINE configs 4 / 5)
+        v, c, _ = tria.get_mesh()
+        z = v[c].mean(axis=1)[:, dim - 1]
+        tria.execute_refinement(((z > 0.34) & (z < 0.67)).astype(np.uint8))
     if solver == "SCnsIM":
         from test_scns_gpu import scns_prm
 
@@ -74,6 +79,8 @@ def main():
         flow.set_control(fgmres_rel=1e-10)
     n_un_glob = int(np.prod([(1 if q1 else 2) * k + 1 for k in reps]))
     n_pn_glob = int(np.prod([k + 1 for k in reps]))
+    if refined:
+        n_un_glob = n_pn_glob = tria.n_vertices()
     n_glob = dim * n_un_glob + n_pn_glob
     loc, glo = flow.owned_global_dofs(n_un_glob)
     gu, gp = flow.local_to_global(0).astype(np.int64), flow.local_to_global(1).astype(np.int64)

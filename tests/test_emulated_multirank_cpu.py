@@ -58,6 +58,8 @@ SLOW = pytest.mark.slow
 @pytest.mark.parametrize("solver,dim,reps,size", [
     pytest.param("InsIM", 2, (6, 8), 2, marks=SLOW), ("InsIM:inner32", 2, (6, 8), 2), ("SCnsIM", 2, (8, 10), 2), pytest.param("SUPGInsIM", 2, (8, 10), 2, marks=SLOW),
     ("InsIMEX", 2, (6, 8), 2), pytest.param("SCnsIM", 3, (4, 4, 6), 2, marks=SLOW),
+    # locally refined band (hanging nodes): the slabs are cut along mesh planes that carry no hanging node or master
+    ("SCnsIM:refined", 2, (4, 9), 2), pytest.param("SCnsIM:refined", 3, (3, 3, 9), 2, marks=SLOW), pytest.param("SCnsIM:refined", 3, (2, 2, 12), 4, marks=SLOW),
     # four z-slabs: the middle ranks have two neighbours (both halo directions inside one group)
     pytest.param("InsIM", 3, (3, 3, 8), 4, marks=SLOW), pytest.param("SCnsIM", 3, (4, 4, 8), 4, marks=SLOW)])
 def test_two_ranks_match_one_rank_on_the_emulated_device(emulated_library, solver, dim, reps, size, tmp_path):

@@ -33,6 +33,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "time_step_wall_s (3D INS cavity 128^3 cells Q2/Q1, 53.07M DoF)"
 METRIC2 = "time_step_wall_s (3D flow past cylinder, InsIM Q2/Q1, ~1.35M DoF)"
+METRIC4 = "time_step_wall_s (fsi_leaflet_mpi 2D: SCnsIM Q1/Q1 on the band-refined channel + NeoHookean leaflet, full IFEM step)"
+METRIC5 = "time_step_wall_s (fsi-wall-3D: SCnsIM Q1/Q1 ~10M fluid DoF on the band-refined box + NeoHookean plate, full IFEM step)"
 UNIT = "s/step"
 CPU_BASELINE_CELLS = [16, 24]  # cpu_baseline leg of the default run (bounded); --impl reference: --ref-cells
 
@@ -218,6 +220,246 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# BASELINE configs 4 and 5: the immersed FSI step (find_solid_bc -> solid step -> solid box -> indicator -> constraints ->
+# find_fluid_bc -> fluid step; reference source/mpi_fsi.cpp:1172-1214)
+# ---------------------------------------------------------------------------------------------------------------------------
+LEAF_L, LEAF_H, LEAF_A, LEAF_B, LEAF_h, LEAF_U = 4.0, 1.0, 0.1, 0.4, 0.05, 1.5
+
+
+def leaflet_inflow(p, c, t):
+    return LEAF_U if c == 0 and abs(p[0]) < 1e-10 else 0.0
+
+
+def fsi_prm_path(config):
+    return os.path.join(ROOT, "tests", "golden", "fsi_leaflet_2d.prm" if config == 4 else "fsi_wall_3d.prm")
+
+
+def fsi_meshes(config, scale, solid_scale):
+    """(fluid triangulation, solid triangulation) of tests/fsi_leaflet_mpi/fsi_leaflet_mpi.cpp:47-92 (config 4; scale divides h)
+    or tests/fsi-wall-3D/fsi-wall-3D.cpp:33-57 (config 5; scale multiplies the {10,10,40} fluid subdivisions, solid_scale the
+    {20,20,8} solid ones) - host-side mesh generators of the product, the same arrays feed the oracle in the CPU legs"""
+    import numpy as np
+
+    import openifem_b200 as ifem
+
+    if config == 4:
+        h = LEAF_h / scale
+        ftria = ifem.Triangulation(2)
+        ifem.GridGenerator.subdivided_hyper_rectangle(ftria, (int(round(LEAF_L / h)), int(round(LEAF_H / h))), (0, 0), (LEAF_L, LEAF_H), True)
+        v, c, _ = ftria.get_mesh()
+        cx = v[c].mean(axis=1)[:, 0]
+        ftria.execute_refinement(((cx >= LEAF_L / 4 - 2 * LEAF_A) & (cx <= LEAF_L / 4 + 3 * LEAF_A)).astype(np.uint8))
+        stria = ifem.Triangulation(2)
+        ifem.GridGenerator.subdivided_hyper_rectangle(stria, (int(round(LEAF_A / LEAF_h)), int(round(LEAF_B / LEAF_h))), (LEAF_L / 4, 0),
+                                                      (LEAF_A + LEAF_L / 4, LEAF_B), True)
+        stria.refine_global(2)  # Global refinements = 0, 2
+        return ftria, stria
+    ftria = ifem.Triangulation(3)
+    ifem.GridGenerator.subdivided_hyper_rectangle(ftria, (10 * scale, 10 * scale, 40 * scale), (0, 0, 0), (1, 1, 4), True)
+    v, c, _ = ftria.get_mesh()
+    cz = v[c].mean(axis=1)[:, 2]
+    ftria.execute_refinement(((cz >= 2) & (cz <= 2.4)).astype(np.uint8))
+    stria = ifem.Triangulation(3)
+    ifem.GridGenerator.subdivided_hyper_rectangle(stria, (20 * solid_scale, 20 * solid_scale, 8 * solid_scale), (0, 0, 2), (1, 1, 2.4), True)
+    return ftria, stria
+
+
+def cpu_fsi_step(config, scale, solid_scale, steps=1):
+    """the oracle's coupled loop (oracle/fsi.py on oracle/scns.py + oracle/solid.py: NumPy / C restatement, one core for the Python
+    parts) on the same meshes: seconds per IFEM step"""
+    import numpy as np
+
+    from oracle import fem, fsi, grid, prm, scns, solid
+
+    ftria, stria = fsi_meshes(config, scale, solid_scale)
+    P = prm.Params(fsi_prm_path(config))
+    v, c, b = ftria.get_mesh()
+    sv, sc, _ = stria.get_mesh()
+    if config == 4:
+        o_fluid = scns.SCnsIM(grid.QuadMesh(v, c, b), P, hard_coded={0: leaflet_inflow})
+        n = (4 * int(round(LEAF_A / LEAF_h)), 4 * int(round(LEAF_B / LEAF_h)))
+        o_solid = solid.HyperElasticity(fem.BoxMesh(n, (LEAF_L / 4, 0), (LEAF_A + LEAF_L / 4, LEAF_B)), P)
+    else:
+        o_fluid = scns.SCnsIM(grid.HexMesh(v, c, b), P)
+        o_solid = solid.HyperElasticity(fem.BoxMesh((20 * solid_scale, 20 * solid_scale, 8 * solid_scale), (0, 0, 2), (1, 1, 2.4)), P)
+    loop = fsi.FSI(o_fluid, o_solid, config == 4)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        loop.run_one_step(k == 0)
+    return (time.perf_counter() - t0) / steps, c.shape[0], sc.shape[0]
+
+
+def cpu_fsi_baseline(config, scale, solid_scale):
+    if config == 4:
+        sec, nf, ns = cpu_fsi_step(4, 1, 1, steps=2)
+        return sec, (f"two IFEM steps of the fsi_leaflet_mpi case itself ({nf} fluid cells, {ns} solid cells) with oracle/ (fsi.py loop in Python / "
+                     f"NumPy, cell loops in C, sparse direct solves): {sec:.1f} s/step on one core"), 1
+    sec, nf, ns = cpu_fsi_step(5, 1, 1, steps=1)
+    target = 6800 * scale ** 3
+    return sec * target / nf, (f"one IFEM step of fsi-wall-3D at the reference's own resolution ({nf} fluid cells, {ns} solid cells) with oracle/ (fsi.py loop "
+                               f"in Python / NumPy with the reference's brute-force 3-D point_in_solid, cell loops in C, sparse direct solves): {sec:.1f} s on one "
+                               f"core; value = that x {target}/{nf} fluid cells (linear extrapolation, optimistic for the CPU)"), 1
+
+
+def run_fsi_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    value, sample, cores = cpu_fsi_baseline(args.config, args.scale, args.solid_scale)
+    line = {"impl": "reference", "metric": METRIC4 if args.config == 4 else METRIC5, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": fsi_workload(args), "same_config": args.config == 4, "extrapolated": args.config != 4},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def fsi_workload(args):
+    if args.config == 4:
+        return ("fsi_leaflet_mpi (config 4): MPI::FSI<2>(SCnsIM Q1/Q1 on the 80 x 20 channel with the band 0.8 <= x <= 1.3 refined once, "
+                "SharedHyperElasticity NeoHookean leaflet 8 x 32 cells, use_dirichlet_bc = true), reference .prm verbatim, dt 5e-3"
+                + (f", fluid h divided by {args.scale}" if args.scale != 1 else ""))
+    return (f"fsi-wall-3D (config 5): MPI::FSI<3>(SCnsIM Q1/Q1 on {{10,10,40}} x {args.scale} cells of [0,1]^2 x [0,4] with the band 2 <= z <= 2.4 "
+            f"refined once, SharedHyperElasticity NeoHookean plate {{20,20,8}} x {args.solid_scale} cells), reference .prm (solid type NeoHookean), dt 1e-6")
+
+
+def run_fsi(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import openifem_b200 as ifem
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world = ifem.init_distributed(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return t.item()
+
+    t_setup = time.perf_counter()
+    ftria, stria = fsi_meshes(args.config, args.scale, args.solid_scale)
+    params = ifem.Parameters.AllParameters(fsi_prm_path(args.config))
+    fluid = ifem.Fluid.MPI.SCnsIM(ftria, params)
+    if args.config == 4:
+        fluid.add_hard_coded_boundary_condition(0, leaflet_inflow)
+    fluid.setup()
+    solid = ifem.Solid.MPI.SharedHyperElasticity(stria, params)
+    solid.setup()
+    coupling = ifem.MPI.FSI(fluid, solid, params, args.config == 4)
+    barrier()
+    t_setup = time.perf_counter() - t_setup
+    n_cells, n_scells = ftria.n_active_cells(), stria.n_active_cells()
+    dim = 2 if args.config == 4 else 3
+    n_u, n_p, nnz_local, _, _ = fluid.sizes()
+    ou, op = fluid.partition(0)[0], fluid.partition(1)[0]
+    n_dofs = int(reduce(dim * ou + op, dist.ReduceOp.SUM))
+    nnz = int(reduce(nnz_local, dist.ReduceOp.SUM))
+    n_local = n_u + n_p
+    host = torch.zeros(n_local, dtype=torch.float64).pin_memory()
+    host_np = host.numpy()
+    sections = ["Find solid BC", "Run solid solver", "Update solid box", "Update indicator", "Find fluid BC", "Run fluid solver"]
+    fsections = ["Assemble system", "Solve linear system", "Solving Tpp"]
+
+    step_no = 0
+    for _ in range(args.warmup):
+        coupling.run_one_step(step_no == 0)
+        step_no += 1
+    host_np[:] = fluid.get_current_solution()
+    t_before = {k: coupling.timer_ms(k) for k in sections}
+    f_before = {k: fluid.timer_ms(k) for k in fsections}
+    n_hist = len(fluid.history())
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ifem.kernel_launches()
+    barrier()
+    t_e2e = t_dev_ms = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        fluid.set_vector(fluid.PRESENT, host_np)                     # H2D of the fluid state the step starts from (pinned)
+        t_dev_ms += coupling.bench_steps(1, step_no == 0)            # CUDA events on the library stream around the coupled pass
+        host_np[:] = fluid.get_current_solution()                    # D2H of the step's result
+        disp = solid.get_current_solution()
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+        step_no += 1
+    barrier()
+    launches = ifem.kernel_launches() - launches0
+    clocks = sampler.stop()
+    sec_dev = reduce(t_dev_ms * 1e-3 / args.steps, dist.ReduceOp.MAX)
+    sec_e2e = reduce(t_e2e / args.steps, dist.ReduceOp.MAX)
+    h2d = int(reduce(n_local * 8, dist.ReduceOp.SUM))
+    d2h = h2d + disp.size * 8
+    sec = {k: (coupling.timer_ms(k) - t_before[k]) / args.steps for k in sections}
+    fsec = {k: (fluid.timer_ms(k) - f_before[k]) / args.steps for k in fsections}
+    hist = fluid.history()[n_hist:]
+    ms_blk, bytes_blk = fluid.bench_vmult(20)
+    ms_blk = reduce(ms_blk, dist.ReduceOp.MAX)
+    peak, peak_src = _peaks()
+    sol = host_np
+    u_own, p_own = sol[:dim * ou], sol[n_u:n_u + op]
+    su2 = reduce(float(np.dot(u_own, u_own)), dist.ReduceOp.SUM)
+    sp2 = reduce(float(np.dot(p_own, p_own)), dist.ReduceOp.SUM)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, sample, cores = cpu_fsi_baseline(args.config, args.scale, args.solid_scale)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    nv = 1 << dim
+    # FSI kernels: algorithmic work per pass (SURVEY 8d): update_indicator tests the 2^d vertices of every local fluid cell
+    # (2^d d 8 B of coordinates in, 4 B out per cell), find_fluid_bc visits every velocity node of the indicator-1 cells
+    ind_ms = max(sec["Update indicator"], 1e-9)
+    fsi_k = {"update_indicator": {"ms": sec["Update indicator"], "points_per_s": n_cells / world * nv / (ind_ms * 1e-3),
+                                  "algorithmic_bytes": n_cells / world * (nv * dim * 8 + 4),
+                                  "GB/s": n_cells / world * (nv * dim * 8 + 4) / (ind_ms * 1e-3) / 1e9,
+                                  "note": "bounding-box reject, then binned solid-cell search (3-D) / crossing number (2-D); latency bound at these sizes"},
+             "find_fluid_bc": {"ms": sec["Find fluid BC"]}, "find_solid_bc": {"ms": sec["Find solid BC"]},
+             "update_solid_box": {"ms": sec["Update solid box"]}}
+    line = {
+        "metric": METRIC4 if args.config == 4 else METRIC5, "value": sec_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec_dev * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": fsi_workload(args) + f": {n_cells} fluid cells, {n_dofs} fluid DoF, {nnz} matrix entries, {n_scells} solid cells, "
+                                                    f"{solid.n_dofs} solid DoF (replicated on every rank)",
+                   "l2": ("inputs larger than L2 (the fluid matrix is %.2f GB per GPU)" % (bytes_blk / 1e9)) if bytes_blk > 126e6 else
+                         "the whole problem fits in L2 (%.1f MB of matrix): a launch-latency-bound step, the reference's own size" % (bytes_blk / 1e6),
+                   "parallelism": f"{world} slab(s) of the fluid along mesh planes, one rank per GPU; the solid is replicated; NCCL: ghost halos, "
+                                  "dot products and the sum of the solid-side interpolation",
+                   "setup_s": round(t_setup, 1),
+                   "section_ms_per_step": {**sec, **{"fluid: " + k: v for k, v in fsec.items()}},
+                   "newton_its_per_step": len(hist) / max(1, args.steps),
+                   "fgmres_its": [h["gmres_its"] for h in hist], "inner_tpp_its": [h["a_inv_its"] for h in hist]},
+        "e2e": {"value": sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "block SpMV of the SCnsIM system (FGMRES operator: bcsr_spmv_row_kernel on the four Q1 blocks), per GPU",
+                     "achieved": bytes_blk / (ms_blk * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": bytes_blk / (ms_blk * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": bytes_blk, "ms": ms_blk,
+                     "csr_equivalent_bytes_per_gpu": 12.0 * nnz_local + 20.0 * (dim * ou + op), "fsi_kernels": fsi_k},
+        "cpu_baseline": cpu,
+        "parity_pins": {"u_l2": su2 ** 0.5, "p_l2": sp2 ** 0.5, "solid_u_max": float(np.abs(disp).max()),
+                        "final_newton_abs_res": hist[-1]["abs_res"] if hist else None,
+                        "note": "field norms over all owned dofs after the last timed step; tests/test_zz_config4_gpu.py and test_fsi_gpu.py compare "
+                                "the same loop with the oracle to 1e-6"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -282,6 +524,9 @@ def run_ours(args):
         step_no += 1
     host_np[:] = flow.get_current_solution()
 
+    SECTIONS = ["Assemble system", "Solve linear system", "CG for Mp", "CG for Sm", "A_inv", "CG for Sm fp64 fallbacks (count)",
+                "A_inv block-Jacobi fallbacks (count)"]
+    sections_before = {k: flow.timer_ms(k) for k in SECTIONS}
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ifem.kernel_launches()
@@ -327,8 +572,8 @@ def run_ours(args):
     traffic = _ncu_traffic()
     hist = flow.history()
     last = [h for h in hist if h["timestep"] == hist[-1]["timestep"]]
-    sections = {k: flow.timer_ms(k) for k in ["Assemble system", "Solve linear system", "CG for Mp", "CG for Sm", "A_inv",
-                                              "CG for Sm fp64 fallbacks (count)", "A_inv block-Jacobi fallbacks (count)"]}
+    sections = {k: flow.timer_ms(k) for k in SECTIONS}  # totals since set-up (warm-up included)
+    sections_timed = {k: (sections[k] - sections_before[k]) / (1 if "count" in k else args.steps) for k in SECTIONS}
     # parity pins, computed outside the timed region in fp64: true residual |b - A x| / |b| of every linear solve of the timed
     # steps (recomputed with the fp64 operator), the Newton residual the reference prints (mpi_insim.cpp:456-460), and norms of
     # the final fields summed over the owned dofs of all ranks - comparable across N = 1 / 2 / 4 / 8 and with an all-fp64 run
@@ -339,6 +584,8 @@ def run_ours(args):
     pins = {"u_l2": su2 ** 0.5, "p_meanfree_l2": max(0.0, sp2 - sp1 * sp1 / cnt) ** 0.5,
             "final_newton_abs_res": last[-1]["abs_res"], "final_newton_rel_res": last[-1]["rel_res"],
             "max_true_res_timed_steps": max(h["true_res"] for h in timed) if timed else None,
+            # solves whose tolerance was the relative one, 1e-4 |rhs| (the last Newton iteration of a step runs into the absolute floor 1e-12)
+            "max_true_res_relative_tolerance_solves": max([h["true_res"] for h in timed if 1e-4 * h["abs_res"] > 1e-12] or [None]),
             "last_step": [{"newton_it": h["iteration"], "abs_res": h["abs_res"], "fgmres_its": h["gmres_its"], "fgmres_res": h["gmres_res"],
                            "true_res": h["true_res"], "a_inv_its": h["a_inv_its"], "cg_sm_its": h["cg_sm_its"], "cg_mp_its": h["cg_mp_its"]}
                           for h in last],
@@ -387,7 +634,8 @@ def run_ours(args):
                    "parallelism": f"{world} z-slab(s), one rank per GPU; NCCL: ghost halos + dot-product all-reduces only",
                    "setup_s": round(t_setup, 1), "setup_note": "mesh, patterns, partition and the SELL-32 layouts are built once before the "
                    "warm-up steps and are outside `value`; the per-solve refresh of the SELL copies from the assembled matrix is inside", "newton_its_last_step": len(last),
-                   "fgmres_its_last_step": [h["gmres_its"] for h in last], "section_ms_total": sections},
+                   "fgmres_its_last_step": [h["gmres_its"] for h in last], "section_ms_total": sections,
+                   "section_ms_per_timed_step": sections_timed},
         "e2e": {"value": sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": ("sell_spmv_h_kernel<3,2,4>" if args.inner_mode == 3 else "sell_spmv_pipe_kernel<3,2,4>")
@@ -423,8 +671,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cells", type=int, default=128, help="cells per direction (config 3 = 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=3, choices=[2, 3],
-                    help="BASELINE config: 3 = 3-D cavity 128^3 (the metric's config, default), 2 = 3-D flow past a cylinder (~1.35 M dofs, 1 GPU)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE config: 3 = 3-D cavity 128^3 (the metric's config, default), 2 = 3-D flow past a cylinder (~1.35 M dofs, 1 GPU), "
+                         "4 = fsi_leaflet_mpi (2-D FSI, 1 GPU), 5 = fsi-wall-3D scaled to ~10 M fluid dofs (3-D FSI, 8 GPUs)")
+    ap.add_argument("--scale", type=int, default=0, help="configs 4 / 5: refinement factor of the fluid mesh (default 1 for config 4, 7 for config 5)")
+    ap.add_argument("--solid-scale", type=int, default=1, help="config 5: factor on the {20,20,8} solid subdivisions")
     ap.add_argument("--refine", type=int, default=2, help="config 2: Global refinements of the cylinder mesh")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cells", default="24,32,48",
@@ -434,7 +685,10 @@ def main():
     ap.add_argument("--inner-mode", type=int, default=3, choices=[0, 1, 2, 3],
                     help="A~^-1 inner solve: 0 fp64 BCSR, 1 fp32-streamed BCSR, 2 fp32 SELL-32, 3 fp32 solver on fp16 SELL-32 values")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config in (4, 5):
+        args.scale = args.scale or (1 if args.config == 4 else 7)
+        (run_fsi_reference if args.impl == "reference" else run_fsi)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

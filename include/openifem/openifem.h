@@ -89,7 +89,11 @@ namespace dealii
     explicit Triangulation(int /*mpi_communicator*/) : Triangulation() {}
     ~Triangulation() { ifem_tria_destroy(h); }
     Triangulation(const Triangulation &) = delete;
-    void refine_global(unsigned times) { openifem_detail::check(ifem_tria_refine_global(h, (int)times)); }
+    void refine_global(unsigned times)
+    {
+      openifem_detail::check(ifem_tria_refine_global(h, (int)times));
+      flags.clear();
+    }
     unsigned n_active_cells() const
     {
       int64_t c = 0;
@@ -98,8 +102,79 @@ namespace dealii
     }
     ifem_tria *handle() const { return h; }
 
+    // What the reference's drivers do with cell iterators before handing the mesh to a solver
+    // (tests/fsi_leaflet_mpi/fsi_leaflet_mpi.cpp:66-76, tests/fsi-wall-3D/fsi-wall-3D.cpp:47-53):
+    //   for (auto cell : tria.active_cell_iterators()) if (cell->center()[0] ...) cell->set_refine_flag();
+    //   tria.execute_coarsening_and_refinement();
+    class CellAccessor
+    {
+    public:
+      CellAccessor(Triangulation *t, unsigned i) : tria(t), index(i) {}
+      Point<dim> center() const
+      {
+        Point<dim> c;
+        const int nv = 1 << dim;
+        for (int v = 0; v < nv; ++v)
+          for (int d = 0; d < dim; ++d) c[d] += tria->vertices[(size_t)tria->cells[(size_t)index * nv + v] * dim + d] / nv;
+        return c;
+      }
+      bool is_locally_owned() const { return true; } // every rank flags the whole (replicated) coarse mesh
+      void set_refine_flag() const { tria->flags[index] = 1; }
+      void clear_refine_flag() const { tria->flags[index] = 0; }
+      unsigned active_cell_index() const { return index; }
+      const CellAccessor *operator->() const { return this; }
+
+    private:
+      Triangulation *tria;
+      unsigned index;
+    };
+    class CellIterator
+    {
+    public:
+      CellIterator(Triangulation *t, unsigned i) : acc(t, i), tria(t), index(i) {}
+      const CellAccessor &operator*() const { return acc; }
+      const CellAccessor *operator->() const { return &acc; }
+      CellIterator &operator++()
+      {
+        acc = CellAccessor(tria, ++index);
+        return *this;
+      }
+      bool operator!=(const CellIterator &o) const { return index != o.index; }
+
+    private:
+      CellAccessor acc;
+      Triangulation *tria;
+      unsigned index;
+    };
+    struct CellRange
+    {
+      CellIterator b, e;
+      CellIterator begin() const { return b; }
+      CellIterator end() const { return e; }
+    };
+    CellRange active_cell_iterators()
+    {
+      int64_t nv = 0, nc = 0, nb = 0;
+      openifem_detail::check(ifem_tria_counts(h, &nv, &nc, &nb));
+      vertices.resize((size_t)nv * dim);
+      cells.resize((size_t)nc << dim);
+      std::vector<int> bf((size_t)nb * 3);
+      openifem_detail::check(ifem_tria_get_mesh(h, vertices.data(), cells.data(), bf.data()));
+      if (flags.size() != (size_t)nc) flags.assign((size_t)nc, 0);
+      return CellRange{CellIterator(this, 0), CellIterator(this, (unsigned)nc)};
+    }
+    void execute_coarsening_and_refinement()
+    {
+      if (flags.empty()) return;
+      openifem_detail::check(ifem_tria_execute_refinement(h, flags.data(), (int64_t)flags.size()));
+      flags.clear();
+    }
+
   private:
     ifem_tria *h = nullptr;
+    std::vector<double> vertices;
+    std::vector<int> cells;
+    std::vector<unsigned char> flags;
   };
 
   namespace parallel

@@ -324,6 +324,9 @@ int ifem_fsi_run_one_step(ifem_fsi *f, int first_step);
  * fsi_acceleration the fluid solver is about to see (tests compare them and the assembled system with the oracle) */
 int ifem_fsi_prepare_fluid_step(ifem_fsi *f, int first_step);
 int ifem_fsi_run(ifem_fsi *f);
+/* n_steps passes of the coupled loop (ifem_fsi_run_one_step) between two CUDA events on the library's stream: the span covers
+ * the device work and the host orchestration between the kernels (bench.py) */
+int ifem_fsi_bench_steps(ifem_fsi *f, int n_steps, int first_step, double *ms_total);
 int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms);
 
 /* ---- measurement hooks (bench.py): device-resident, CUDA-event timed on the library's stream ---- */

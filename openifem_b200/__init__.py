@@ -747,6 +747,12 @@ class _FSI:
         check(lib().ifem_fsi_timer_ms(self._h, section.encode(), C.byref(ms)))
         return ms.value
 
+    def bench_steps(self, n_steps, first_step=False):
+        """n_steps coupled passes between CUDA events on the library's stream; total milliseconds"""
+        ms = C.c_double()
+        check(lib().ifem_fsi_bench_steps(self._h, C.c_int(n_steps), C.c_int(1 if first_step else 0), C.byref(ms)))
+        return ms.value
+
 
 class MPI:
     FSI = _FSI

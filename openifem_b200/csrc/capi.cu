@@ -1029,6 +1029,14 @@ int ifem_fsi_run(ifem_fsi *f)
 {
   return guard([&] { f->f->run(); });
 }
+int ifem_fsi_bench_steps(ifem_fsi *f, int n_steps, int first_step, double *ms_total)
+{
+  return guard([&] {
+    FsiCoupling &c = *f->f;
+    int k = 0;
+    *ms_total = n_steps * time_reps(c.ctx, n_steps, [&] { c.run_one_step(first_step != 0 && k++ == 0); });
+  });
+}
 int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms)
 {
   return guard([&] {

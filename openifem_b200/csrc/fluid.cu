@@ -303,7 +303,23 @@ namespace ifem
     d_con.upload(con, s);
     d_nonzero_val.upload(nonzero_val, s);
     if (n_con) d_con_idx.upload(idx, s);
+    if (d_base_con.n != d_con.n) d_base_con.alloc(d_con.n);
+    if (d_base_val.n != d_nonzero_val.n) d_base_val.alloc(d_nonzero_val.n);
+    IFEM_CUDA(cudaMemcpyAsync(d_base_con.p, d_con.p, d_con.n, cudaMemcpyDeviceToDevice, s));
+    IFEM_CUDA(cudaMemcpyAsync(d_base_val.p, d_nonzero_val.p, d_nonzero_val.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    base_valid = true;
+    flags_merged = false;
+    schur_valid = false;
     IFEM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  void FluidSpace::restore_base_constraints(Context &ctx)
+  {
+    cudaStream_t s = ctx.stream;
+    IFEM_CUDA(cudaMemcpyAsync(d_con.p, d_base_con.p, d_con.n, cudaMemcpyDeviceToDevice, s));
+    IFEM_CUDA(cudaMemcpyAsync(d_nonzero_val.p, d_base_val.p, d_nonzero_val.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (flags_merged) schur_valid = false; // S_m was formed for flags that held merged lines
+    flags_merged = false;
   }
 
   void FluidSpace::set_neumann_faces(Context &ctx, const Triangulation &tria, const std::map<unsigned int, double> &neumann)

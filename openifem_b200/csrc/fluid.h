@@ -67,6 +67,12 @@ namespace ifem
     DevBuf<unsigned char> d_slots; // per cell: uu[nu][nu] | up[nu][np] | pu[np][nu] | pp[np][np]
     DevBuf<unsigned char> d_con;
     DevBuf<double> d_nonzero_val;
+    // the lines make_constraints() produced, kept on the device: a coupling step that re-makes the constraints every pass
+    // (MPI::FSI::run, source/mpi_fsi.cpp:1190-1198) restores them with two device copies instead of a host pass + upload
+    DevBuf<unsigned char> d_base_con;
+    DevBuf<double> d_base_val;
+    bool base_valid = false, flags_merged = false;
+    void restore_base_constraints(Context &ctx);
     DevBuf<int> d_con_idx; // list of constrained dofs
     int n_con = 0;
     DevBuf<int> d_indicator; // CellProperty::indicator

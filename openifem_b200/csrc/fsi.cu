@@ -377,6 +377,18 @@ namespace ifem
 
     // find_fluid_bc (mpi_fsi.cpp:478-638): one thread per owned fluid velocity node. The reference's
     // "first touching cell wins" (dof_touched) becomes: the lowest-numbered adjacent indicator-1 cell.
+    __global__ void merge_constraints_kernel(int64_t n, const unsigned char *__restrict__ inner_con, const double *__restrict__ inner_inhom,
+                                             const unsigned char *__restrict__ hanging, unsigned char *__restrict__ con, double *__restrict__ val)
+    {
+      const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (g >= n) return;
+      if (inner_con[g] && !con[g] && !(hanging && hanging[g]))
+        {
+          con[g] = 1;
+          val[g] = inner_inhom[g];
+        }
+    }
+
     template <int DIM>
     __global__ void fluid_bc_kernel(SolidView S, FluidBcArgs A)
     {
@@ -1023,12 +1035,7 @@ namespace ifem
     update_solid_box();
     update_indicator();
     fluid.make_constraints();
-    if (!first_step)
-      {
-        // nonzero_constraints.copy_from(zero_constraints) (:1193-1198): the increments are homogeneous from now on
-        std::fill(fluid.fs.nonzero_val.begin(), fluid.fs.nonzero_val.end(), 0.0);
-        fluid.upload_constraints();
-      }
+    if (!first_step) fluid.fs.d_nonzero_val.zero(ctx.stream); // nonzero_constraints.copy_from(zero_constraints) (:1193-1198): homogeneous increments from now on
     find_fluid_bc();
     if (stop_before_fluid_step) return; // tests: the state the fluid solver is about to see
     {
@@ -1265,19 +1272,16 @@ namespace ifem
     fs.halo_update(ctx, fluid.fsi_acceleration.p); // fsi_acceleration = tmp (ghosted), :639-640
     if (use_dirichlet_bc)
       {
-        // nonzero_constraints.merge(inner_nonzero, left_object_wins) and the same for zero_constraints (:641-651)
-        const std::vector<unsigned char> ic = d_inner_con.to_host(s);
-        const std::vector<double> ih = d_inner_inhom.to_host(s);
-        bool changed = false;
-        const std::vector<char> &hanging = fs.hanging.is_hanging_dof; // an existing hanging-node line wins as well
-        for (int64_t g = 0; g < fs.n_dofs; ++g)
-          if (ic[g] && !fs.con[g] && (hanging.empty() || !hanging[g]))
-            {
-              fs.con[g] = 1;
-              fs.nonzero_val[g] = ih[g];
-              changed = true;
-            }
-        if (changed) fluid.upload_constraints();
+        // nonzero_constraints.merge(inner_nonzero, left_object_wins) and the same for zero_constraints (:641-651), on the device:
+        // an existing line - Dirichlet or hanging-node - wins
+        const int64_t n = fs.n_dofs;
+        merge_constraints_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, d_inner_con.p, d_inner_inhom.p,
+                                                                            fs.hanging.active ? fs.hanging.d_is_hanging_dof.p : nullptr,
+                                                                            fs.d_con.p, fs.d_nonzero_val.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+        fs.flags_merged = true;
+        fs.schur_valid = false;
       }
   }
 

@@ -249,6 +249,7 @@ namespace ifem
     if (!with_pp) throw std::runtime_error("hanging-node condensation needs the pressure-pressure block (SCnsIM / SUPGInsIM)");
     upload_nodes(ctx, u, fs.dim);
     upload_nodes(ctx, p, 1);
+    d_is_hanging_dof.upload(is_hanging_dof, ctx.stream);
     make_plan(ctx, fs.P_uu, fs.n_owned_unodes, u, u, fs.un.n_nodes, fs.un.n_nodes, uu);
     make_plan(ctx, fs.P_up, fs.n_owned_unodes, u, p, fs.un.n_nodes, fs.pn.n_nodes, up);
     make_plan(ctx, fs.P_pu, fs.n_owned_pnodes, p, u, fs.pn.n_nodes, fs.un.n_nodes, pu);

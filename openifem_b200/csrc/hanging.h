@@ -56,7 +56,8 @@ namespace ifem
     HangingNodes u, p;
     FoldPlan uu, up, pu, pp;
     bool with_pp = false;
-    std::vector<char> is_hanging_dof; // [n_dofs] of the block vector (empty when inactive)
+    std::vector<unsigned char> is_hanging_dof; // [n_dofs] of the block vector (empty when inactive)
+    DevBuf<unsigned char> d_is_hanging_dof;
 
     // hanging vertices of the triangulation -> lines on the local velocity / pressure nodes; per-cell node lists extended by
     // the masters (for the sparsity patterns). Throws unless both spaces are FE_Q(1).

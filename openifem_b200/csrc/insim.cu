@@ -41,6 +41,7 @@ namespace ifem
   void InsIM::add_hard_coded_boundary_condition(int id, std::function<double(const double *, unsigned int, double)> f)
   {
     hard_coded[id] = std::move(f);
+    fs.base_valid = false;
   }
 
   void InsIM::setup_dofs()
@@ -51,6 +52,15 @@ namespace ifem
 
   void InsIM::make_constraints()
   {
+    // the lines depend on the mesh, the .prm maps and - through hard-coded boundary functions - on the functions' clock only:
+    // unchanged inputs restore the device copies (two device-to-device copies; the host mirrors fs.con / fs.nonzero_val keep
+    // these base lines as well)
+    if (fs.base_valid && (hard_coded.empty() || base_bc_time == bc_time))
+      {
+        fs.restore_base_constraints(ctx);
+        return;
+      }
+    base_bc_time = bc_time;
     std::function<bool(int, const double *, int, double &)> hc;
     if (!hard_coded.empty())
       hc = [this](int id, const double *pt, int c, double &v) {
@@ -61,24 +71,14 @@ namespace ifem
       };
     fs.make_constraints(ctx, triangulation, parameters.fluid_dirichlet_bcs, hc);
     fs.set_neumann_faces(ctx, triangulation, parameters.fluid_neumann_bcs);
-    upload_constraints();
   }
 
   void InsIM::upload_constraints()
   {
-    std::vector<int> idx;
-    for (int64_t g = 0; g < fs.n_dofs; ++g)
-      if (fs.con[g]) idx.push_back((int)g);
-    fs.n_con = (int)idx.size();
     fs.d_con.upload(fs.con, ctx.stream);
     fs.d_nonzero_val.upload(fs.nonzero_val, ctx.stream);
-    if (fs.n_con) fs.d_con_idx.upload(idx, ctx.stream);
     fs.schur_valid = false;
-    std::vector<double> vals(fs.n_con);
-    int k = 0;
-    for (int64_t g = 0; g < fs.n_dofs; ++g)
-      if (fs.con[g]) vals[k++] = fs.nonzero_val[g];
-    if (fs.n_con) d_con_vals.upload(vals, ctx.stream);
+    fs.flags_merged = true;
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
 
@@ -272,7 +272,7 @@ namespace ifem
       cur.true_res = nrm > 0.0 ? nrm2(ctx, va, res) / nrm : 0.0;
     }
     // constraints_used.distribute(newton_update)
-    if (fs.n_con) set_indexed(ctx, fs.n_con, fs.d_con_idx.p, use_nonzero_constraints ? d_con_vals.p : nullptr, newton_update.p);
+    set_flagged(ctx, fs.n_dofs, fs.d_con.p, use_nonzero_constraints ? fs.d_nonzero_val.p : nullptr, newton_update.p);
     return {(unsigned)r.iterations, r.residual};
   }
 

@@ -93,7 +93,7 @@ namespace ifem
     LinOp P = [&](const double *x, double *y) { precondition(x, y); };
     const SolveResult r = fgmres(ctx, va, A, P, fs.rhs.p, newton_update.p, tol, n_dofs_global, control.basis_size, pool_fgmres);
     // constraints_used.distribute(solution_time_increment)
-    if (fs.n_con) set_indexed(ctx, fs.n_con, fs.d_con_idx.p, use_nonzero_constraints ? d_con_vals.p : nullptr, newton_update.p);
+    set_flagged(ctx, fs.n_dofs, fs.d_con.p, use_nonzero_constraints ? fs.d_nonzero_val.p : nullptr, newton_update.p);
     return {(unsigned)r.iterations, r.residual};
   }
 

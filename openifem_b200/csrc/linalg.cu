@@ -612,6 +612,12 @@ namespace ifem
   {
     map(ctx, n_idx, [=] __device__(int64_t k) { x[idx[k]] = vals ? vals[k] : 0.0; });
   }
+  void set_flagged(Context &ctx, int64_t n, const unsigned char *flag, const double *vals, double *x)
+  {
+    map(ctx, n, [=] __device__(int64_t g) {
+      if (flag[g]) x[g] = vals ? vals[g] : 0.0;
+    });
+  }
   void hadamard(Context &ctx, const VecSpace &n, const double *d, const double *x, double *y)
   {
     map(ctx, n, [=] __device__(int64_t i) { y[i] = d[i] * x[i]; });

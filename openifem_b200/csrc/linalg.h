@@ -83,6 +83,9 @@ namespace ifem
   void lin3(Context &ctx, const VecSpace &n, double *z, const double *x, double a, const double *y, double b, const double *w);
   // x[idx[k]] = vals ? vals[k] : 0   (AffineConstraints::distribute for Dirichlet lines)
   void set_indexed(Context &ctx, int n_idx, const int *idx, const double *vals, double *x);
+  // x[g] = vals ? vals[g] : 0 on every dof with flag[g] != 0 (AffineConstraints::distribute for Dirichlet lines, flags and values
+  // resident on the device: no compacted index list to rebuild when a coupling step changes the lines)
+  void set_flagged(Context &ctx, int64_t n, const unsigned char *flag, const double *vals, double *x);
   // y[i] = d[i] * x[i]
   void hadamard(Context &ctx, const VecSpace &n, const double *d, const double *x, double *y);
   // y[i] /= d[i]

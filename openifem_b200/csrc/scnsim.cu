@@ -638,7 +638,7 @@ namespace ifem
       r = fgmres(ctx, va, A, P, fs.rhs.p, newton_update.p, tol, n_dofs_global, control.basis_size, pool_fgmres);
     else
       fill(ctx, va, 0.0, newton_update.p);
-    if (fs.n_con) set_indexed(ctx, fs.n_con, fs.d_con_idx.p, use_nonzero_constraints ? d_con_vals.p : nullptr, newton_update.p);
+    set_flagged(ctx, fs.n_dofs, fs.d_con.p, use_nonzero_constraints ? fs.d_nonzero_val.p : nullptr, newton_update.p);
     fs.hanging.distribute(ctx, fs, newton_update.p); // constraints.distribute(newton_update), mpi_supg_solver.cpp:323-325
     return {(unsigned)r.iterations, r.residual};
   }

@@ -91,6 +91,13 @@ int ifem_tria_flow_around_cylinder(ifem_tria *t);
 /* copy the mesh out: vertices [n_vertices][dim], cells [n_cells][2^dim] (lexicographic corners), boundary_faces
  * [n_boundary_faces][3] = (cell, face_no = 2*axis+side, boundary id); any pointer may be NULL */
 int ifem_tria_get_mesh(const ifem_tria *t, double *vertices, int *cells, int *boundary_faces);
+/* hand an existing mesh to the library - what a deal.II-side host does with its own Triangulation (the reference's solvers take
+ * any parallel::distributed::Triangulation, include/mpi_fluid_solver.h:99, read with GridIn in e.g. tests/fsi_*): active cells
+ * only, the arrays of ifem_tria_get_mesh; corners in deal.II's lexicographic order (GeometryInfo<dim>::vertex numbering), face_no =
+ * deal.II's face number 2*axis+side, boundary ids as set on the faces; material_ids [n_cells] or NULL. Cells must be positively
+ * oriented; hanging vertices (one level of difference) are found from the geometry. */
+int ifem_tria_set_mesh(ifem_tria *t, int64_t n_vertices, const double *vertices, int64_t n_cells, const int *cells, int64_t n_boundary_faces,
+                       const int *boundary_faces, const int *material_ids);
 
 /* ---- Parameters::AllParameters(prm_file) (include/parameters.h:191, source/parameters.cpp:618-658) ---- */
 int ifem_params_from_file(const char *prm_file, ifem_params **out);

@@ -169,6 +169,15 @@ class Triangulation:
     def n_active_cells(self):
         return self._counts()[1]
 
+    def set_mesh(self, vertices, cells, boundary_faces, material_ids=None):
+        """import a mesh from plain arrays (the layout get_mesh() returns)"""
+        v = np.ascontiguousarray(vertices, dtype=np.float64)
+        c = np.ascontiguousarray(cells, dtype=np.int32)
+        b = np.ascontiguousarray(boundary_faces, dtype=np.int32).reshape(-1, 3)
+        m = None if material_ids is None else np.ascontiguousarray(material_ids, dtype=np.int32)
+        check(lib().ifem_tria_set_mesh(self._h, C.c_int64(v.shape[0]), dptr(v), C.c_int64(c.shape[0]), iptr(c), C.c_int64(b.shape[0]),
+                                       iptr(b) if b.size else None, None if m is None else iptr(m)))
+
     def __del__(self):
         if getattr(self, "_h", None) and _lib._lib is not None:
             _lib._lib.ifem_tria_destroy(self._h)

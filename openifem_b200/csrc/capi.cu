@@ -339,6 +339,39 @@ int ifem_tria_get_mesh(const ifem_tria *t, double *vertices, int *cells, int *bo
     if (boundary_faces) std::copy(t->t.boundary_faces.begin(), t->t.boundary_faces.end(), boundary_faces);
   });
 }
+int ifem_tria_set_mesh(ifem_tria *t, int64_t n_vertices, const double *vertices, int64_t n_cells, const int *cells, int64_t n_boundary_faces,
+                       const int *boundary_faces, const int *material_ids)
+{
+  return guard([&] {
+    Triangulation &T = t->t;
+    const int dim = T.dim, vpc = 1 << dim;
+    if (n_vertices <= 0 || n_cells <= 0 || !vertices || !cells) throw std::runtime_error("ifem_tria_set_mesh: empty mesh");
+    for (int64_t k = 0; k < n_cells * vpc; ++k)
+      if (cells[k] < 0 || cells[k] >= n_vertices) throw std::runtime_error("ifem_tria_set_mesh: vertex index out of range");
+    for (int64_t f = 0; f < n_boundary_faces; ++f)
+      if (boundary_faces[3 * f] < 0 || boundary_faces[3 * f] >= n_cells || boundary_faces[3 * f + 1] < 0 || boundary_faces[3 * f + 1] >= 2 * dim)
+        throw std::runtime_error("ifem_tria_set_mesh: boundary face out of range");
+    // every cell must be positively oriented in the lexicographic corner order (the Q1 map of the assembly kernels)
+    for (int64_t c = 0; c < n_cells; ++c)
+      {
+        double e[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int d = 0; d < dim; ++d)
+          for (int k = 0; k < dim; ++k) e[d][k] = vertices[(size_t)cells[c * vpc + (1 << d)] * dim + k] - vertices[(size_t)cells[c * vpc] * dim + k];
+        const double det = dim == 2 ? e[0][0] * e[1][1] - e[0][1] * e[1][0]
+                                    : e[0][0] * (e[1][1] * e[2][2] - e[1][2] * e[2][1]) - e[0][1] * (e[1][0] * e[2][2] - e[1][2] * e[2][0]) +
+                                        e[0][2] * (e[1][0] * e[2][1] - e[1][1] * e[2][0]);
+        if (!(det > 0)) throw std::runtime_error("ifem_tria_set_mesh: cell " + std::to_string(c) + " is inverted or degenerate in lexicographic corner order");
+      }
+    T = Triangulation();
+    T.dim = dim;
+    T.vertices.assign(vertices, vertices + n_vertices * dim);
+    T.cells.assign(cells, cells + n_cells * vpc);
+    if (n_boundary_faces) T.boundary_faces.assign(boundary_faces, boundary_faces + 3 * n_boundary_faces);
+    if (material_ids) T.material_id.assign(material_ids, material_ids + n_cells);
+    else T.material_id.assign((size_t)n_cells, 1);
+    T.find_hanging_vertices(); // a mesh that arrives locally refined keeps its hanging vertices
+  });
+}
 int ifem_tria_counts(const ifem_tria *t, int64_t *nv, int64_t *nc, int64_t *nbf)
 {
   return guard([&] {

@@ -47,3 +47,31 @@ def test_cylinder_mesh_3d_extruded():
     assert np.einsum("ij,ij->i", np.cross(e1, e2), e3).min() > 0
     t.refine_global(1)
     assert t.n_active_cells() == 832 * 8
+
+
+def test_mesh_import_through_the_abi_round_trips_and_finds_hanging_vertices():
+    """ifem_tria_set_mesh: a host that owns its triangulation (deal.II in the reference) hands over plain arrays; a locally refined
+    mesh keeps its hanging vertices; inverted cells are refused"""
+    import numpy as np
+
+    import openifem_b200 as ifem
+
+    a = ifem.Triangulation(3)
+    ifem.GridGenerator.subdivided_hyper_rectangle(a, (3, 2, 4), (0, 0, 0), (1.5, 1.0, 2.0), True)
+    v, c, _ = a.get_mesh()
+    a.execute_refinement((v[c].mean(axis=1)[:, 2] > 1.0).astype(np.uint8))
+    v, c, f = a.get_mesh()
+    b = ifem.Triangulation(3)
+    b.set_mesh(v, c, f)
+    v2, c2, f2 = b.get_mesh()
+    assert np.array_equal(v, v2) and np.array_equal(c, c2) and np.array_equal(f, f2)
+    ha, hb = a.hanging(), b.hanging()
+    assert ha[0].size > 0 and all(np.array_equal(x, y) for x, y in zip(ha, hb))
+    b.refine_global(1)
+    assert b.n_active_cells() == 8 * a.n_active_cells()
+    bad = c.copy()
+    bad[0, [0, 1]] = bad[0, [1, 0]]
+    import pytest
+
+    with pytest.raises(RuntimeError, match="inverted"):
+        ifem.Triangulation(3).set_mesh(v, bad, f)

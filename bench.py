@@ -235,7 +235,7 @@ def fsi_prm_path(config):
     return os.path.join(ROOT, "tests", "golden", "fsi_leaflet_2d.prm" if config == 4 else "fsi_wall_3d.prm")
 
 
-def fsi_meshes(config, scale, solid_scale):
+def fsi_meshes(config, scale, solid_scale, half=False):
     """(fluid triangulation, solid triangulation) of tests/fsi_leaflet_mpi/fsi_leaflet_mpi.cpp:47-92 (config 4; scale divides h)
     or tests/fsi-wall-3D/fsi-wall-3D.cpp:33-57 (config 5; scale multiplies the {10,10,40} fluid subdivisions, solid_scale the
     {20,20,8} solid ones) - host-side mesh generators of the product, the same arrays feed the oracle in the CPU legs"""
@@ -256,23 +256,27 @@ def fsi_meshes(config, scale, solid_scale):
         stria.refine_global(2)  # Global refinements = 0, 2
         return ftria, stria
     ftria = ifem.Triangulation(3)
-    ifem.GridGenerator.subdivided_hyper_rectangle(ftria, (10 * scale, 10 * scale, 40 * scale), (0, 0, 0), (1, 1, 4), True)
+    if half:  # CPU sample below the reference's own resolution: {5,5,20} fluid and {10,10,4} solid subdivisions
+        fr, sr = (5, 5, 20), (10, 10, 4)
+    else:
+        fr, sr = (10 * scale, 10 * scale, 40 * scale), (20 * solid_scale, 20 * solid_scale, 8 * solid_scale)
+    ifem.GridGenerator.subdivided_hyper_rectangle(ftria, fr, (0, 0, 0), (1, 1, 4), True)
     v, c, _ = ftria.get_mesh()
     cz = v[c].mean(axis=1)[:, 2]
     ftria.execute_refinement(((cz >= 2) & (cz <= 2.4)).astype(np.uint8))
     stria = ifem.Triangulation(3)
-    ifem.GridGenerator.subdivided_hyper_rectangle(stria, (20 * solid_scale, 20 * solid_scale, 8 * solid_scale), (0, 0, 2), (1, 1, 2.4), True)
+    ifem.GridGenerator.subdivided_hyper_rectangle(stria, sr, (0, 0, 2), (1, 1, 2.4), True)
     return ftria, stria
 
 
-def cpu_fsi_step(config, scale, solid_scale, steps=1):
+def cpu_fsi_step(config, scale, solid_scale, steps=1, half=False):
     """the oracle's coupled loop (oracle/fsi.py on oracle/scns.py + oracle/solid.py: NumPy / C restatement, one core for the Python
     parts) on the same meshes: seconds per IFEM step"""
     import numpy as np
 
     from oracle import fem, fsi, grid, prm, scns, solid
 
-    ftria, stria = fsi_meshes(config, scale, solid_scale)
+    ftria, stria = fsi_meshes(config, scale, solid_scale, half)
     P = prm.Params(fsi_prm_path(config))
     v, c, b = ftria.get_mesh()
     sv, sc, _ = stria.get_mesh()
@@ -282,7 +286,8 @@ def cpu_fsi_step(config, scale, solid_scale, steps=1):
         o_solid = solid.HyperElasticity(fem.BoxMesh(n, (LEAF_L / 4, 0), (LEAF_A + LEAF_L / 4, LEAF_B)), P)
     else:
         o_fluid = scns.SCnsIM(grid.HexMesh(v, c, b), P)
-        o_solid = solid.HyperElasticity(fem.BoxMesh((20 * solid_scale, 20 * solid_scale, 8 * solid_scale), (0, 0, 2), (1, 1, 2.4)), P)
+        sr = (10, 10, 4) if half else (20 * solid_scale, 20 * solid_scale, 8 * solid_scale)
+        o_solid = solid.HyperElasticity(fem.BoxMesh(sr, (0, 0, 2), (1, 1, 2.4)), P)
     loop = fsi.FSI(o_fluid, o_solid, config == 4)
     t0 = time.perf_counter()
     for k in range(steps):
@@ -295,11 +300,13 @@ def cpu_fsi_baseline(config, scale, solid_scale):
         sec, nf, ns = cpu_fsi_step(4, 1, 1, steps=2)
         return sec, (f"two IFEM steps of the fsi_leaflet_mpi case itself ({nf} fluid cells, {ns} solid cells) with oracle/ (fsi.py loop in Python / "
                      f"NumPy, cell loops in C, sparse direct solves): {sec:.1f} s/step on one core"), 1
-    sec, nf, ns = cpu_fsi_step(5, 1, 1, steps=1)
+    sec, nf, ns = cpu_fsi_step(5, 1, 1, steps=1, half=True)
     target = 6800 * scale ** 3
-    return sec * target / nf, (f"one IFEM step of fsi-wall-3D at the reference's own resolution ({nf} fluid cells, {ns} solid cells) with oracle/ (fsi.py loop "
-                               f"in Python / NumPy with the reference's brute-force 3-D point_in_solid, cell loops in C, sparse direct solves): {sec:.1f} s on one "
-                               f"core; value = that x {target}/{nf} fluid cells (linear extrapolation, optimistic for the CPU)"), 1
+    return sec * target / nf, (f"one IFEM step of fsi-wall-3D at half the reference's resolution ({nf} fluid cells, {ns} solid cells; the reference's own "
+                               f"6800 / 3200 cells take the Python loop more than 25 min per step) with oracle/ (fsi.py loop in Python / NumPy with the "
+                               f"reference's brute-force 3-D point_in_solid, cell loops in C, sparse direct solves): {sec:.1f} s on one core; value = that x "
+                               f"{target}/{nf} fluid cells (linear extrapolation in the fluid cells only, optimistic for the CPU: the brute-force search "
+                               f"grows with fluid cells x solid cells)"), 1
 
 
 def run_fsi_reference(args):

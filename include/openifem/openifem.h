@@ -450,11 +450,19 @@ namespace Solid
     public:
       HyperElasticity(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
       {
-        openifem_detail::check(ifem_hyper_create(tria.handle(), params.handle(), &this->h));
+        openifem_detail::check(ifem_hyper_create_twin(tria.handle(), params.handle(), 0, &this->h));
       }
     };
+    // include/mpi_shared_hyper_elasticity.h: the replicated twin MPI::FSI takes
     template <int dim>
-    using SharedHyperElasticity = HyperElasticity<dim>;
+    class SharedHyperElasticity : public SolidSolver<dim>
+    {
+    public:
+      SharedHyperElasticity(dealii::Triangulation<dim> &tria, const Parameters::AllParameters &params)
+      {
+        openifem_detail::check(ifem_hyper_create_twin(tria.handle(), params.handle(), 1, &this->h));
+      }
+    };
 
     // include/mpi_linear_elasticity.h
     template <int dim>

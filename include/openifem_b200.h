@@ -247,6 +247,10 @@ typedef struct
   int cg_its;
 } ifem_solid_record;
 int ifem_hyper_create(ifem_tria *tria, const ifem_params *params, ifem_hyper **out);
+/* the class named explicitly: shared = 0 Solid::MPI::HyperElasticity<dim> (source/mpi_hyper_elasticity.cpp), shared = 1
+ * Solid::MPI::SharedHyperElasticity<dim> (source/mpi_shared_hyper_elasticity.cpp: Newton loop also stops on |update| <= 1e-12, :125-127;
+ * update_strain_and_stress after every step, :204-205). ifem_hyper_create picks the twin when `Simulation type = FSI`. */
+int ifem_hyper_create_twin(ifem_tria *tria, const ifem_params *params, int shared, ifem_hyper **out);
 /* Solid::MPI::LinearElasticity<dim>(tria, params) (shared = 0; include/mpi_linear_elasticity.h, source/mpi_linear_elasticity.cpp)
  * or Solid::MPI::SharedLinearElasticity<dim>(tria, params) (shared = 1, the replicated twin MPI::FSI takes;
  * source/mpi_shared_linear_elasticity.cpp). The handle is the common solid-solver handle: every ifem_hyper_* entry point

@@ -646,6 +646,16 @@ class _HyperElasticity:
         return [{f: getattr(buf[i], f) for f, _ in SolidRecord._fields_} for i in range(min(n.value, max_records))]
 
 
+class _SharedHyperElasticity(_HyperElasticity):
+    """Solid::MPI::SharedHyperElasticity<dim>(triangulation, parameters): the replicated twin MPI::FSI takes (extra Newton stop on a
+    vanishing update, nodal strain / stress after every step) whatever `Simulation type` says."""
+
+    def __init__(self, tria: Triangulation, params: "Parameters.AllParameters"):
+        self.tria, self.params = tria, params
+        self._h = C.c_void_p()
+        check(lib().ifem_hyper_create_twin(tria._h, params._h, C.c_int(1), C.byref(self._h)))
+
+
 class _LinearElasticity(_HyperElasticity):
     """Solid::MPI::LinearElasticity<dim>(triangulation, parameters): small-strain elasticity, Newmark-beta in
     acceleration form. Same handle type as the other solid solvers (update_qph / get_qph do not apply)."""
@@ -838,6 +848,6 @@ class Fluid:
 class Solid:
     class MPI:
         HyperElasticity = _HyperElasticity
-        SharedHyperElasticity = _HyperElasticity  # the replicated twin MPI::FSI takes (`Simulation type = FSI` selects its Newton stop)
+        SharedHyperElasticity = _SharedHyperElasticity
         LinearElasticity = _LinearElasticity
         SharedLinearElasticity = _SharedLinearElasticity

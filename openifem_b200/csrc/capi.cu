@@ -821,6 +821,15 @@ int ifem_hyper_create(ifem_tria *tria, const ifem_params *params, ifem_hyper **o
     *out = h;
   });
 }
+int ifem_hyper_create_twin(ifem_tria *tria, const ifem_params *params, int shared, ifem_hyper **out)
+{
+  return guard([&] {
+    require_device();
+    auto *h = new ifem_hyper;
+    h->s.reset(new HyperElasticity(default_context(), tria->t, *params->p, shared ? 1 : 0));
+    *out = h;
+  });
+}
 int ifem_linear_elasticity_create(ifem_tria *tria, const ifem_params *params, int shared, ifem_hyper **out)
 {
   return guard([&] {

@@ -137,6 +137,7 @@ namespace ifem
     // clock of the hard-coded boundary functions (Function::advance_time): InsIM::run never advances it, SUPGFluidSolver::run
     // advances it by dt before every make_constraints() (mpi_supg_solver.cpp:438-444, 470-478)
     double bc_time = 0.0;
+    bool bc_clock_started = false; // SUPGFluidSolver::run advanced the boundary functions' clock before the first step
     double base_bc_time = 0.0; // clock of the boundary functions the cached constraint lines were made at
     // per-section device time, keyed by the reference's TimerOutput section names
     std::map<std::string, double> timer_ms;

@@ -694,14 +694,22 @@ namespace ifem
   {
     const bool time_dependent = !hard_coded.empty();
     const bool success_load = load_checkpoint(); // :433; false unless an output directory is set
+    // the clock of the boundary functions runs one step ahead (:438-444) whether or not setup() was called before run()
+    const bool advance_clock = time_dependent && !bc_clock_started && time.get_timestep() == 0;
+    if (advance_clock)
+      {
+        bc_time += time.get_delta_t();
+        bc_clock_started = true;
+      }
     if (!dofs_ready)
       {
-        if (time_dependent) bc_time += time.get_delta_t();
         triangulation.refine_global(parameters.global_refinements.empty() ? 0 : parameters.global_refinements[0]);
         setup_dofs();
         make_constraints();
         initialize_system();
       }
+    else if (advance_clock)
+      make_constraints();
     if (!success_load) run_one_step(true);
     while (time.end() - time.current() > 1e-12)
       {

@@ -754,9 +754,10 @@ namespace ifem
   std::vector<double> SolidSolver::get_current_solution() { return current_displacement.to_host(ctx.stream); }
 
   // ===========================================================================
-  HyperElasticity::HyperElasticity(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params)
+  HyperElasticity::HyperElasticity(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params, int shared)
     : SolidSolver(ctx_, tria, params)
   {
+    shared_twin = shared < 0 ? params.simulation_type == "FSI" : shared != 0;
     // PointHistory::setup (mpi_hyper_elasticity.cpp:8-35): NeoHookean or Kirchhoff
     if (parameters.solid_type == "Kirchhoff")
       {
@@ -900,7 +901,6 @@ namespace ifem
       lin3(ctx, n, current_velocity.p, previous_velocity.p, dt * (1 - gamma), previous_acceleration.p, dt * gamma, current_acceleration.p);
     };
     // the replicated twin MPI::FSI uses also stops on a vanishing update (mpi_shared_hyper_elasticity.cpp:125-127)
-    const bool shared_twin = parameters.simulation_type == "FSI";
     while ((nerr_upd > parameters.tol_d || nerr_res > parameters.tol_f) && (!shared_twin || err_upd > 1e-12))
       {
         if (it >= parameters.solid_max_iterations) throw std::runtime_error("Too many Newton iterations!");
@@ -927,7 +927,7 @@ namespace ifem
     copy(ctx, n, current_acceleration.p, previous_acceleration.p);
     copy(ctx, n, current_velocity.p, previous_velocity.p);
     copy(ctx, n, current_displacement.p, previous_displacement.p);
-    update_strain_and_stress(); // the shared twin used by MPI::FSI does this every step (mpi_shared_hyper_elasticity.cpp:204-205)
+    if (shared_twin) update_strain_and_stress(); // the twin used by MPI::FSI does this every step (mpi_shared_hyper_elasticity.cpp:204-205)
     io_after_step();
   }
 

@@ -114,7 +114,10 @@ namespace ifem
   class HyperElasticity : public SolidSolver
   {
   public:
-    HyperElasticity(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params);
+    // shared: 1 = Solid::MPI::SharedHyperElasticity (the replicated twin MPI::FSI takes: extra Newton stop on a vanishing update,
+    // nodal strain / stress every step), 0 = Solid::MPI::HyperElasticity, -1 = pick by `Simulation type` (FSI -> the twin)
+    HyperElasticity(Context &ctx, Triangulation &tria, const Parameters::AllParameters &params, int shared = -1);
+    bool shared_twin = false;
     void run_one_step(bool first_step) override;
     void initialize_system() override;
     void update_qph(const double *u_dev);

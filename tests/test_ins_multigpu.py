@@ -175,7 +175,7 @@ def test_four_ranks_match_one_rank(tmp_path):
     assert rel(sol4[:nu], sol1[:nu]) < 1e-6
 
 
-def _scns_worker(rank, size, idfile, dim, reps, steps, q):
+def _scns_worker(rank, size, idfile, dim, reps, steps, q, mode="plain"):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -201,22 +201,44 @@ def _scns_worker(rank, size, idfile, dim, reps, steps, q):
                 uid = open(idfile, "rb").read()
             ifem.comm_init(rank, size, uid)
         tria = ifem.Triangulation(dim)
-        hi = (2.0,) + (1.0,) * (dim - 1)
-        ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, hi, True)
-        flow = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=scns_prm(dim, dt=1e-3)))
-        flow.set_body_force(lambda p, c: 5.0 if c == 0 else 0.0)
-        flow.setup()
-        flow.set_control(fgmres_rel=1e-10)
-        n_un_glob = int(np.prod([k + 1 for k in reps]))
+        solid = None
+        if mode.startswith("fsi"):
+            # the coupled loop of MPI::FSI::run (tests/test_fsi_gpu.py's 3-D problem): partitioned fluid, replicated solid
+            from test_fsi_gpu import _fsi_text
+
+            params = ifem.Parameters.AllParameters(text=_fsi_text(dim, solid_v0=(0.02, 0.0, 0.01)))
+            ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0.0,) * dim, (1.0,) * dim, True)
+            stria = ifem.Triangulation(dim)
+            ifem.GridGenerator.subdivided_hyper_rectangle(stria, (3, 3, 4), (0.25, 0.0, 0.25), (0.7, 0.6, 0.75), True)
+            flow, solid = ifem.Fluid.MPI.SCnsIM(tria, params), ifem.Solid.MPI.HyperElasticity(stria, params)
+            flow.setup()
+            solid.setup()
+            flow.set_control(fgmres_rel=1e-10)
+            coupling = ifem.MPI.FSI(flow, solid, params, mode == "fsi_dirichlet")
+        else:
+            hi = (2.0,) + (1.0,) * (dim - 1)
+            ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0,) * dim, hi, True)
+            if mode == "refined":  # a band across the last axis refined once: hanging nodes (the meshes of BASELINE configs 4 / 5)
+                v, c, _ = tria.get_mesh()
+                z = v[c].mean(axis=1)[:, dim - 1]
+                tria.execute_refinement(((z > 0.34) & (z < 0.67)).astype(np.uint8))
+            flow = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=scns_prm(dim, dt=1e-3)))
+            flow.set_body_force(lambda p, c: 5.0 if c == 0 else 0.0)
+            flow.setup()
+            flow.set_control(fgmres_rel=1e-10)
+        n_un_glob = tria.n_vertices()
         loc, glo = flow.owned_global_dofs(n_un_glob)
         for k in range(steps):
-            flow.run_one_step(k == 0)
+            if solid is not None:
+                coupling.run_one_step(k == 0)
+            else:
+                flow.run_one_step(k == 0)
         sol = flow.get_current_solution()
         ou = flow.partition(0)[0]
         stress = flow.get_stress()[:, :ou]
         gu = flow.local_to_global(0)[:ou]
         hist = [(h["timestep"], h["iteration"], h["abs_res"]) for h in flow.history()]
-        q.put((rank, "ok", glo, sol[loc], gu, stress, hist))
+        q.put((rank, "ok", glo, sol[loc], gu, stress, hist, None if solid is None else solid.get_current_solution()))
         if size > 1:
             ifem.comm_finalize()
     except Exception:  # pragma: no cover
@@ -225,13 +247,13 @@ def _scns_worker(rank, size, idfile, dim, reps, steps, q):
         q.put((rank, "fail", traceback.format_exc(), None, None, None, None, None))
 
 
-def _run_scns(size, dim, reps, steps, tmp_path):
+def _run_scns(size, dim, reps, steps, tmp_path, mode="plain"):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    idfile = str(tmp_path / f"nccl_id_scns_{size}")
-    procs = [ctx.Process(target=_scns_worker, args=(r, size, idfile, dim, reps, steps, q)) for r in range(size)]
+    idfile = str(tmp_path / f"nccl_id_scns_{mode}_{size}")
+    procs = [ctx.Process(target=_scns_worker, args=(r, size, idfile, dim, reps, steps, q, mode)) for r in range(size)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -247,6 +269,10 @@ def _run_scns(size, dim, reps, steps, tmp_path):
         sol[r[2]] = r[3]
         stress[:, r[4]] = r[5]
     hist = [r for r in res if r[0] == 0][0][6]
+    if mode.startswith("fsi"):
+        for r in res[1:]:  # the solid is replicated: every rank holds the same displacement
+            assert np.array_equal(r[7], res[0][7])
+        return sol, stress, hist, res[0][7]
     return sol, stress, hist
 
 
@@ -265,3 +291,31 @@ def test_scnsim_two_ranks_match_one_rank(dim, reps, tmp_path):
         assert abs(a[2] - b[2]) <= 1e-6 * max(b[2], 1e-9)
     assert rel(sol2, sol1) < 1e-6
     assert rel(st2, st1) < 1e-6
+
+
+@pytest.mark.parametrize("dim,reps,size", [(3, (3, 3, 9), 2), (2, (4, 9), 2), (3, (2, 2, 12), 4)])
+def test_scnsim_on_a_band_refined_mesh_ranks_match_one_rank(dim, reps, size, tmp_path):
+    """hanging nodes on several GPUs: slabs cut along mesh planes that carry no hanging node or master, condensation local to the
+    owner of a line (csrc/hanging.cu, csrc/partition.cpp plane_slabs)"""
+    if _n_gpus() < size:
+        pytest.skip(f"needs {size} GPUs")
+    sol1, st1, h1 = _run_scns(1, dim, reps, 3, tmp_path, "refined")
+    sol2, st2, h2 = _run_scns(size, dim, reps, 3, tmp_path, "refined")
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert len(h1) == len(h2)
+    for a, b in zip(h2, h1):
+        assert a[:2] == b[:2] and abs(a[2] - b[2]) <= 1e-6 * max(b[2], 1e-9)
+    assert rel(sol2, sol1) < 1e-6 and rel(st2, st1) < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["fsi", "fsi_dirichlet"])
+def test_coupled_fsi_two_ranks_match_one_rank(mode, tmp_path):
+    """the full IFEM step of BASELINE config 5's path on real NCCL: partitioned SCnsIM fluid, replicated NeoHookean solid, solid-side
+    interpolation summed over the ranks (source/mpi_fsi.cpp:849-865)"""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    sol1, _, h1, us1 = _run_scns(1, 3, (6, 6, 6), 2, tmp_path, mode)
+    sol2, _, h2, us2 = _run_scns(2, 3, (6, 6, 6), 2, tmp_path, mode)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert len(h1) == len(h2) and np.abs(us1).max() > 0
+    assert rel(sol2, sol1) < 1e-6 and rel(us2, us1) < 1e-6

@@ -117,6 +117,8 @@ typedef struct
                          operator, residuals and FGMRES basis stay fp64 */
   int cg_sm_fp32;     /* "CG for Sm" (mpi_insim.cpp:88-109): 0 fp64 CG on the CSR matrix; 1 fp32 CG on a SELL-32 copy of S_m;
                          2 as 1 with row-scaled fp16 matrix values. Preconditioner only, as above */
+  int supg_ilu;       /* SCnsIM / SUPGInsIM block preconditioner (mpi_supg_solver.cpp:35-192): 1 ILU(0) factors of A_vv and B2pp like the
+                         reference's Euclid ones (one rank), 0 Jacobi factors, -1 ILU(0) up to 60 000 velocity rows on one rank */
 } ifem_ins_control;
 
 typedef struct
@@ -339,6 +341,12 @@ int ifem_fsi_run(ifem_fsi *f);
  * the device work and the host orchestration between the kernels (bench.py) */
 int ifem_fsi_bench_steps(ifem_fsi *f, int n_steps, int first_step, double *ms_total);
 int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms);
+
+/* ILU(0) of a scalar CSR matrix (sorted columns, diagonal present) and one application x = U^-1 L^-1 b on the device - the factors
+ * behind the block preconditioner of the SUPG solvers (Hypre Euclid in the reference, source/preconditioner_pilut.cpp:124-138).
+ * factors [nnz] (L strictly lower with unit diagonal implied, U upper, in place) or NULL; level counts of the two sweeps (tests) */
+int ifem_ilu0_apply(int n, const int64_t *rowptr, const int *col, const double *val, const double *b, double *factors, double *x,
+                    int *n_levels_lower, int *n_levels_upper);
 
 /* ---- measurement hooks (bench.py): device-resident, CUDA-event timed on the library's stream ---- */
 /* reps applications of the block SpMV on resident vectors; returns mean ms per application and the

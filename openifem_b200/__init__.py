@@ -121,6 +121,20 @@ def kernel_launches() -> int:
     return n.value
 
 
+def ilu0_apply(A, b):
+    """ILU(0) of the scipy CSR matrix A on the device and x = U^-1 L^-1 b; returns (factors in A's pattern, x, (levels L, levels U))"""
+    A = A.tocsr()
+    A.sort_indices()
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    v = np.ascontiguousarray(A.data, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    f, x = np.empty_like(v), np.empty_like(b)
+    nl, nu = C.c_int(), C.c_int()
+    check(lib().ifem_ilu0_apply(C.c_int(A.shape[0]), lptr(rp), iptr(ci), dptr(v), dptr(b), dptr(f), dptr(x), C.byref(nl), C.byref(nu)))
+    return f, x, (nl.value, nu.value)
+
+
 class Triangulation:
     def __init__(self, dim: int):
         self.dim = dim

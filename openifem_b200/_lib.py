@@ -15,7 +15,7 @@ class InsControl(C.Structure):
     _fields_ = [("fgmres_rel", C.c_double), ("fgmres_floor", C.c_double), ("cg_mp_rel", C.c_double),
                 ("cg_sm_rel", C.c_double), ("cg_floor", C.c_double), ("a_inv_rel", C.c_double),
                 ("a_inv_max_it", C.c_int), ("basis_size", C.c_int), ("a_inv_fp32", C.c_int),
-                ("cg_sm_fp32", C.c_int)]
+                ("cg_sm_fp32", C.c_int), ("supg_ilu", C.c_int)]
 
 
 class NewtonRecord(C.Structure):

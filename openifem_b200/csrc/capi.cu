@@ -10,6 +10,7 @@
 #include "comm.h"
 #include "peer.h"
 #include "fsi.h"
+#include "ilu0.h"
 #include "insim.h"
 #include "insimex.h"
 #include "output.h"
@@ -437,6 +438,7 @@ int ifem_insim_default_control(int serial_twin, ifem_ins_control *out)
     out->basis_size = c.basis_size;
     out->a_inv_fp32 = c.a_inv_fp32;
     out->cg_sm_fp32 = c.cg_sm_fp32;
+    out->supg_ilu = c.supg_ilu;
   });
 }
 int ifem_insim_get_control(const ifem_insim *s, ifem_ins_control *out)
@@ -453,6 +455,7 @@ int ifem_insim_get_control(const ifem_insim *s, ifem_ins_control *out)
     out->basis_size = c.basis_size;
     out->a_inv_fp32 = c.a_inv_fp32;
     out->cg_sm_fp32 = c.cg_sm_fp32;
+    out->supg_ilu = c.supg_ilu;
   });
 }
 int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
@@ -469,6 +472,7 @@ int ifem_insim_set_control(ifem_insim *s, const ifem_ins_control *c)
     k.basis_size = c->basis_size;
     k.a_inv_fp32 = c->a_inv_fp32;
     k.cg_sm_fp32 = c->cg_sm_fp32;
+    k.supg_ilu = c->supg_ilu;
   });
 }
 int ifem_insim_set_verbose(ifem_insim *s, int verbose)
@@ -1070,6 +1074,25 @@ int ifem_fsi_prepare_fluid_step(ifem_fsi *f, int first_step)
 int ifem_fsi_run(ifem_fsi *f)
 {
   return guard([&] { f->f->run(); });
+}
+int ifem_ilu0_apply(int n, const int64_t *rowptr, const int *col, const double *val, const double *b, double *factors, double *x,
+                    int *n_levels_lower, int *n_levels_upper)
+{
+  return guard([&] {
+    require_device();
+    Context &ctx = default_context();
+    Ilu0 ilu;
+    ilu.setup(ctx, std::vector<int64_t>(rowptr, rowptr + n + 1), std::vector<int>(col, col + rowptr[n]));
+    ilu.val.upload(val, (size_t)rowptr[n], ctx.stream);
+    ilu.factor(ctx);
+    DevBuf<double> db((size_t)n), dx((size_t)n);
+    db.upload(b, (size_t)n, ctx.stream);
+    ilu.solve(ctx, db.p, dx.p);
+    if (factors) ilu.val.download(factors, (size_t)rowptr[n], ctx.stream);
+    dx.download(x, (size_t)n, ctx.stream);
+    if (n_levels_lower) *n_levels_lower = ilu.n_levels_lower;
+    if (n_levels_upper) *n_levels_upper = ilu.n_levels_upper;
+  });
 }
 int ifem_fsi_bench_steps(ifem_fsi *f, int n_steps, int first_step, double *ms_total)
 {

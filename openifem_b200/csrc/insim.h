@@ -80,6 +80,8 @@ namespace ifem
     // device-resident scalars; 2 as 1 with row-scaled fp16 matrix values
     int cg_sm_fp32 = 0;
     int basis_size = 30;
+    // SUPG solvers: ILU(0) factors for P_vv and B2pp as in the reference (1), Jacobi factors (0), or by problem size (-1)
+    int supg_ilu = -1;
     static InsSolverControl serial()
     {
       InsSolverControl c;

@@ -413,6 +413,57 @@ namespace ifem
       out[i] = d != 0.0 ? 1.0 / d : 1.0;
     }
 
+    // B2pp = A_pp - A_pv diag(rowsum|A_vv|)^-1 A_vp (mpi_supg_solver.cpp:120-127) on the pattern of A_pv A_vp (scalar CSR, the
+    // layout Ilu0 factorises); one thread per pressure row
+    template <int DIM>
+    __global__ void b2pp_matrix_kernel(int n_p, const int64_t *__restrict__ pu_rp, const int *__restrict__ pu_col,
+                                       const double *__restrict__ pu_val, const int64_t *__restrict__ up_rp,
+                                       const int *__restrict__ up_col, const double *__restrict__ up_val,
+                                       const int64_t *__restrict__ pp_rp, const int *__restrict__ pp_col,
+                                       const double *__restrict__ pp_val, const double *__restrict__ rinv, const int *__restrict__ b_rp,
+                                       const int *__restrict__ b_col, double *__restrict__ b_val)
+    {
+      const int i = blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n_p) return;
+      const int b0 = b_rp[i], b1 = b_rp[i + 1];
+      auto find = [&](int c) {
+        int lo = b0, hi = b1 - 1;
+        while (lo <= hi)
+          {
+            const int mid = (lo + hi) >> 1;
+            if (b_col[mid] == c) return mid;
+            if (b_col[mid] < c) lo = mid + 1; else hi = mid - 1;
+          }
+        return -1;
+      };
+      for (int p = b0; p < b1; ++p) b_val[p] = 0.0;
+      for (int64_t k = pp_rp[i]; k < pp_rp[i + 1]; ++k)
+        {
+          const int pos = find(pp_col[k]);
+          if (pos >= 0) b_val[pos] += pp_val[k];
+        }
+      const int64_t rb = pu_rp[i];
+      const int rn = (int)(pu_rp[i + 1] - rb);
+      for (int jk = 0; jk < rn; ++jk)
+        {
+          const int k = pu_col[rb + jk];
+          const int64_t ub = up_rp[k];
+          const int un = (int)(up_rp[k + 1] - ub);
+          double w[DIM];
+#pragma unroll
+          for (int c = 0; c < DIM; ++c) w[c] = pu_val[rb * DIM + (int64_t)c * rn + jk] * rinv[(int64_t)DIM * k + c];
+          for (int t = 0; t < un; ++t)
+            {
+              double v = 0.0;
+#pragma unroll
+              for (int c = 0; c < DIM; ++c) v += w[c] * up_val[ub * DIM + (int64_t)c * un + t];
+              if (v == 0.0) continue;
+              const int pos = find(up_col[ub + t]);
+              if (pos >= 0) b_val[pos] -= v;
+            }
+        }
+    }
+
     struct ScopedTimer
     {
       Context &ctx;
@@ -564,13 +615,24 @@ namespace ifem
   // BlockIncompSchurPreconditioner::vmult (mpi_supg_solver.cpp:137-192). The two Hypre-Euclid ILU(0) factors
   // (rank-count dependent in the reference) are replaced by rank-independent Jacobi factors: P_vv^-1 = inverse of
   // the node-diagonal blocks of A_vv, and diag(B2pp)^-1 as the preconditioner of the T_pp solve.
+  bool SCnsIM::use_ilu() const
+  {
+    constexpr int64_t kIluMaxRows = 60000; // scalar rows of A_vv up to which the one-CTA level-scheduled sweeps pay (ilu0.h)
+    if (control.supg_ilu == 0 || fs.n_ranks > 1) return false;
+    return control.supg_ilu == 1 || fs.n_u <= kIluMaxRows;
+  }
+
   void SCnsIM::precondition_supg(const double *src, double *dst)
   {
     const int64_t n_u = fs.n_u;
     const VecSpace &vu = fs.vs_u, &vp = fs.vs_p;
     const double *src_u = src, *src_p = src + n_u;
     double *dst_u = dst, *dst_p = dst + n_u;
-    auto Pvv = [&](const double *x, double *y) { block_diag_apply(ctx, fs.n_owned_unodes, fs.dim, d_binv.p, x, y); };
+    const bool ilu = use_ilu();
+    auto Pvv = [&](const double *x, double *y) {
+      if (ilu) ilu_vv.solve(ctx, x, y);
+      else block_diag_apply(ctx, fs.n_owned_unodes, fs.dim, d_binv.p, x, y);
+    };
     // ptmp = src_p - A_pv P_vv^-1 src_u
     Pvv(src_u, d_ut1.p);
     fs.halo_u.update(ctx, d_ut1.p);
@@ -588,7 +650,10 @@ namespace ifem
         spmv(ctx, fs.A_pp, x, y);
         axpy(ctx, vp, -1.0, d_pt2.p, y);
       };
-      LinOp B2 = [&](const double *x, double *y) { hadamard(ctx, vp, d_b2pp_diag_inv.p, x, y); };
+      LinOp B2 = [&](const double *x, double *y) {
+        if (ilu) ilu_b2.solve(ctx, x, y);
+        else hadamard(ctx, vp, d_b2pp_diag_inv.p, x, y);
+      };
       const double tol = 1e-3 * nrm2(ctx, vp, d_pt1.p);
       if (tol > 0)
         {
@@ -628,6 +693,32 @@ namespace ifem
       }
     IFEM_KERNEL_CHECK();
     ctx.kernel_launches += 2;
+    if (use_ilu())
+      {
+        // the reference's two Euclid factorisations (mpi_supg_solver.cpp:51, 130-133), redone for every Newton matrix
+        if (!ilu_vv.ready())
+          {
+            std::vector<int64_t> rp;
+            std::vector<int> ci;
+            scalar_pattern(fs.P_uu, fs.dim, rp, ci);
+            ilu_vv.setup(ctx, rp, ci);
+            ilu_b2.setup(ctx, fs.P_schur.rowptr, fs.P_schur.col);
+          }
+        bcsr_to_scalar(ctx, fs.A_uu, ilu_vv.rowptr.p, ilu_vv.val.p);
+        ilu_vv.factor(ctx);
+        const int np_ = fs.n_owned_pnodes;
+        if (fs.dim == 2)
+          b2pp_matrix_kernel<2><<<(np_ + 127) / 128, 128, 0, s>>>(np_, fs.A_pu.rowptr.p, fs.A_pu.col.p, fs.A_pu.val.p, fs.A_up.rowptr.p, fs.A_up.col.p,
+                                                                 fs.A_up.val.p, fs.A_pp.rowptr.p, fs.A_pp.col.p, fs.A_pp.val.p, d_rowsum_inv.p,
+                                                                 ilu_b2.rowptr.p, ilu_b2.col.p, ilu_b2.val.p);
+        else
+          b2pp_matrix_kernel<3><<<(np_ + 127) / 128, 128, 0, s>>>(np_, fs.A_pu.rowptr.p, fs.A_pu.col.p, fs.A_pu.val.p, fs.A_up.rowptr.p, fs.A_up.col.p,
+                                                                 fs.A_up.val.p, fs.A_pp.rowptr.p, fs.A_pp.col.p, fs.A_pp.val.p, d_rowsum_inv.p,
+                                                                 ilu_b2.rowptr.p, ilu_b2.col.p, ilu_b2.val.p);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+        ilu_b2.factor(ctx);
+      }
     const VecSpace &va = fs.vs_all;
     const double nrm = nrm2(ctx, va, fs.rhs.p);
     const double tol = control.fgmres_rel * nrm; // SolverControl(m, 1e-6 * |rhs|), mpi_supg_solver.cpp:311-312

@@ -5,6 +5,7 @@
 // use). Shares the FluidSpace / Newton / FGMRES machinery of InsIM; differs in the cell integrand, in
 // update_stress() after every step and in the block preconditioner (BlockIncompSchurPreconditioner).
 #pragma once
+#include "ilu0.h"
 #include "insim.h"
 
 namespace ifem
@@ -36,6 +37,10 @@ namespace ifem
     DevBuf<double> d_sigma_pml, d_body_force; // [n_cells][nq], [n_cells][nq][dim] (empty when unset)
     DevBuf<double> d_rowsum_inv, d_b2pp_diag_inv, d_pt1, d_pt2, d_ut1, d_ut2;
     VecPool pool_tpp;
+    // ILU(0) factors of A_vv and B2pp (ilu0.h) - the reference's Euclid factors; used on one rank up to kIluMaxRows scalar rows
+    // (control.supg_ilu: -1 by size, 0 never = Jacobi factors, 1 always)
+    Ilu0 ilu_vv, ilu_b2;
+    bool use_ilu() const;
   };
 
   // Fluid::MPI::SUPGInsIM<dim> (reference include/mpi_insim_supg.h, source/mpi_insim_supg.cpp): incompressible

@@ -1107,6 +1107,12 @@ namespace ifem
           throw std::runtime_error("Solid and fluid restart files have different time steps. Check and remove inconsistent restart files!");
         while (time.get_timestep() < solid.time.get_timestep()) time.increment();
       }
+    // FSI::refine_mesh (mpi_fsi.cpp:1024-1117; called twice before the first step and at every refinement interval, :1164-1168,
+    // :1215-1218) needs coarsening and solution transfer, which the mesh class does not have: fail loudly instead of running the
+    // case on a mesh the reference would not use
+    if (parameters.refinement_interval < parameters.end_time)
+      throw std::runtime_error("MPI::FSI::run: `Refinement interval` < `End time` asks for FSI::refine_mesh (adaptive refinement with solution "
+                               "transfer), which is not implemented; refine the fluid mesh before constructing the solver");
     bool first_step = !restarted;
     while (time.end() - time.current() > 1e-12)
       {

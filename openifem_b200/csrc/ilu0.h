@@ -29,6 +29,12 @@ namespace ifem
     DevBuf<double> val;                                 // A, then L (strict lower part, unit diagonal implied) and U in place
     DevBuf<int> order_lower, level_lower, order_upper, level_upper; // rows grouped by level, level offsets
     DevBuf<double> tmp;
+    // The sweeps read a second, LEVEL-ORDERED copy of the factors: the r-th row in level order keeps its strictly lower (upper)
+    // entries in w_lower (w_upper) consecutive padded slots, so every address of a sweep depends on the level counter only - none
+    // on the recurrence - and can be prefetched levels ahead; the recurrence itself runs on a work vector in shared memory.
+    int w_lower = 0, w_upper = 0;        // padded entries per row (multiples of 32)
+    DevBuf<int> lcol, lsrc, ucol, usrc;  // column of a slot, position of its value in `val` (-1 = padding)
+    DevBuf<double> lval, uval, udinv;    // packed by factor(); udinv = 1 / u_ii in level order of the upper sweep
 
     bool ready() const { return n > 0; }
     // pattern analysis: rowptr [n + 1], sorted columns; every row must hold its diagonal

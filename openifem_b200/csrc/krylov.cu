@@ -132,8 +132,11 @@ namespace ifem
   }
 
   SolveResult fgmres(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
-                     int64_t max_it, int m, VecPool &pool)
+                     int64_t max_it, int m, VecPool &pool, bool fused_orthogonalisation)
   {
+    fused_orthogonalisation = fused_orthogonalisation && m <= 64;
+    std::vector<const double *> basis;
+    std::vector<double> hcol;
     // pool slots: 0 aux, 1..m V, m+1..2m Z
     double *aux = pool.get(0, n.n_alloc);
     auto V = [&](int j) { return pool.get(1 + j, n.n_alloc); };
@@ -178,9 +181,20 @@ namespace ifem
             A(Z(j), aux);
             // modified Gram-Schmidt via add_and_dot
             auto h = [&](int i) -> double & { return H[(size_t)i * m + j]; };
-            h(0) = dot(ctx, n, aux, V(0));
-            for (int i = 1; i <= j; ++i) h(i) = add_and_dot(ctx, n, aux, -h(i - 1), V(i - 1), V(i));
-            a = std::sqrt(add_and_dot(ctx, n, aux, -h(j), V(j), aux));
+            if (fused_orthogonalisation)
+              {
+                basis.resize(j + 1);
+                hcol.resize(j + 1);
+                for (int i = 0; i <= j; ++i) basis[i] = V(i);
+                a = orthogonalise_cgs2(ctx, n, j + 1, basis.data(), aux, hcol.data());
+                for (int i = 0; i <= j; ++i) h(i) = hcol[i];
+              }
+            else
+              {
+                h(0) = dot(ctx, n, aux, V(0));
+                for (int i = 1; i <= j; ++i) h(i) = add_and_dot(ctx, n, aux, -h(i - 1), V(i - 1), V(i));
+                a = std::sqrt(add_and_dot(ctx, n, aux, -h(j), V(j), aux));
+              }
             if (!std::isfinite(a)) throw std::runtime_error("FGMRES: non-finite Arnoldi vector (the preconditioner returned NaN/Inf)");
             h(j + 1) = a;
             // least squares on the (j+1) x j block = all columns before this one:

@@ -53,8 +53,11 @@ namespace ifem
                        int max_it, VecPool &pool);
 
   // x0 = 0 is assumed (x is overwritten). Throws on failure like deal.II's NoConvergence.
+  // fused_orthogonalisation: the Arnoldi vector is orthogonalised by orthogonalise_cgs2 (three reductions and one host
+  // synchronisation per iteration) instead of deal.II's modified Gram-Schmidt loop (one of each per basis vector) - for solves
+  // INSIDE a preconditioner, where only the accuracy of the result matters (the T_pp solve of the SUPG block preconditioner)
   SolveResult fgmres(Context &ctx, const VecSpace &n, const LinOp &A, const LinOp &prec, const double *b, double *x, double tol_abs,
-                     int64_t max_it, int basis_size, VecPool &pool);
+                     int64_t max_it, int basis_size, VecPool &pool, bool fused_orthogonalisation = false);
 } // namespace ifem
 
 namespace ifem

@@ -11,6 +11,7 @@ namespace ifem
   // Context
   // ---------------------------------------------------------------------------
   static constexpr int kMaxPartials = 4096;
+  static constexpr int kOrthoMaxBasis = 64, kOrthoMaxGrid = 256; // fused Gram-Schmidt (orthogonalise_cgs2)
 
   Context::Context()
   {
@@ -23,9 +24,9 @@ namespace ifem
     IFEM_CUDA(cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
     IFEM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    partials.alloc(kMaxPartials);
-    results.alloc(64);
-    IFEM_CUDA(cudaMallocHost(&h_results, 64 * sizeof(double)));
+    partials.alloc(kOrthoMaxBasis * kOrthoMaxGrid > kMaxPartials ? kOrthoMaxBasis * kOrthoMaxGrid : kMaxPartials);
+    results.alloc(256);
+    IFEM_CUDA(cudaMallocHost(&h_results, 256 * sizeof(double)));
     if (const char *v = std::getenv("IFEM_SPMV_VARIANT")) spmv_variant = std::atoi(v);
     if (const char *v = std::getenv("IFEM_SPMV_RPW")) spmv_rpw = std::atoi(v);
     if (const char *v = std::getenv("IFEM_SPMV_L2HINT")) spmv_l2hint = std::atoi(v);
@@ -553,6 +554,100 @@ namespace ifem
       ctx.kernel_launches++;
     }
   } // namespace
+
+  // ---------------------------------------------------------------------------
+  // Fused classical Gram-Schmidt with re-orthogonalisation (CGS2) for the Arnoldi step of GMRES: all inner products of a pass
+  // come out of ONE reduction (one kernel pair, one all-reduce over the ranks) instead of one per basis vector as in the
+  // modified Gram-Schmidt loop, and the host reads the coefficients of both passes and the norm with ONE synchronisation.
+  // ---------------------------------------------------------------------------
+  namespace
+  {
+    struct BasisPtrs
+    {
+      const double *v[kOrthoMaxBasis];
+    };
+
+    // partial[t * gridDim.x + block] = sum over the block's elements of V_t[i] * aux[i], t < k
+    __global__ void __launch_bounds__(kThreads) multi_dot_partial_kernel(Seg sg, int k, BasisPtrs V, const double *__restrict__ aux,
+                                                                         double *__restrict__ partial)
+    {
+      for (int t0 = 0; t0 < k; t0 += 8)
+        {
+          double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          const int nt = min(8, k - t0);
+          for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < sg.total; e += (int64_t)gridDim.x * blockDim.x)
+            {
+              const int64_t i = sg(e);
+              const double a = aux[i];
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                if (t < nt) s[t] = fma(V.v[t0 + t][i], a, s[t]);
+            }
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            {
+              if (t >= nt) break; // uniform over the block
+              const double r = block_sum(s[t]);
+              if (threadIdx.x == 0) partial[(int64_t)(t0 + t) * gridDim.x + blockIdx.x] = r;
+            }
+        }
+    }
+
+    // out[t] = sum of the g partials of vector t; one block per t
+    __global__ void __launch_bounds__(kThreads) multi_reduce_final_kernel(int g, const double *__restrict__ partial, double *__restrict__ out)
+    {
+      double s = 0.0;
+      for (int i = threadIdx.x; i < g; i += blockDim.x) s += partial[(int64_t)blockIdx.x * g + i];
+      s = block_sum(s);
+      if (threadIdx.x == 0) out[blockIdx.x] = s;
+    }
+
+    // aux -= sum_t h[t] V_t  (h on the device: no host round trip between the reduction and the update)
+    __global__ void __launch_bounds__(kThreads) multi_axpy_kernel(Seg sg, int k, BasisPtrs V, const double *__restrict__ h, double *__restrict__ aux)
+    {
+      __shared__ double sh[kOrthoMaxBasis];
+      for (int t = threadIdx.x; t < k; t += blockDim.x) sh[t] = h[t];
+      __syncthreads();
+      for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < sg.total; e += (int64_t)gridDim.x * blockDim.x)
+        {
+          const int64_t i = sg(e);
+          double a = aux[i];
+          for (int t = 0; t < k; ++t) a = fma(-sh[t], V.v[t][i], a);
+          aux[i] = a;
+        }
+    }
+  } // namespace
+
+  double orthogonalise_cgs2(Context &ctx, const VecSpace &n, int k, const double *const *basis, double *aux, double *h)
+  {
+    if (k > kOrthoMaxBasis) throw std::runtime_error("orthogonalise_cgs2: basis larger than 64 vectors");
+    BasisPtrs V;
+    for (int t = 0; t < k; ++t) V.v[t] = basis[t];
+    const Seg sg = seg_of(n);
+    const int g = std::min(grid_for(ctx, n.n_owned()), kOrthoMaxGrid);
+    const bool many = ctx.comm && ctx.comm->size > 1;
+    double *res = ctx.results.p; // [0, k) pass 1, [k, 2k) pass 2, [2k] |aux|^2
+    for (int pass = 0; pass < 2; ++pass)
+      {
+        double *hp = res + (size_t)pass * k;
+        multi_dot_partial_kernel<<<g, kThreads, 0, ctx.stream>>>(sg, k, V, aux, ctx.partials.p);
+        multi_reduce_final_kernel<<<k, kThreads, 0, ctx.stream>>>(g, ctx.partials.p, hp);
+        IFEM_KERNEL_CHECK();
+        if (many) comm_allreduce_sum(*ctx.comm, hp, k, ctx.stream);
+        multi_axpy_kernel<<<g, kThreads, 0, ctx.stream>>>(sg, k, V, hp, aux);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches += 3;
+      }
+    dot_partial_kernel<<<g, kThreads, 0, ctx.stream>>>(sg, aux, aux, ctx.partials.p);
+    reduce_final_kernel<<<1, kThreads, 0, ctx.stream>>>(g, ctx.partials.p, res + 2 * k);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches += 2;
+    if (many) comm_allreduce_sum(*ctx.comm, res + 2 * k, 1, ctx.stream);
+    IFEM_CUDA(cudaMemcpyAsync(ctx.h_results, res, (size_t)(2 * k + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+    for (int t = 0; t < k; ++t) h[t] = ctx.h_results[t] + ctx.h_results[k + t];
+    return std::sqrt(std::max(0.0, ctx.h_results[2 * k]));
+  }
 
   double dot(Context &ctx, const VecSpace &n, const double *x, const double *y)
   {

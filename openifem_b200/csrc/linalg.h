@@ -79,6 +79,10 @@ namespace ifem
   void fill(Context &ctx, const VecSpace &n, double v, double *x);
   // aux += a V ; return aux . W   (deal.II Vector::add_and_dot, used by FGMRES' MGS)
   double add_and_dot(Context &ctx, const VecSpace &n, double *aux, double a, const double *V, const double *W);
+  // Arnoldi orthogonalisation by classical Gram-Schmidt with one re-orthogonalisation pass, fused: aux is made orthogonal to the
+  // k basis vectors (k <= 64), h[t] receives the coefficient of basis[t], the return value is |aux| afterwards. Three reductions
+  // and one host synchronisation per call whatever k is (the add_and_dot loop of the modified Gram-Schmidt needs k + 1 of each).
+  double orthogonalise_cgs2(Context &ctx, const VecSpace &n, int k, const double *const *basis, double *aux, double *h);
   // z = x + a y + b w
   void lin3(Context &ctx, const VecSpace &n, double *z, const double *x, double a, const double *y, double b, const double *w);
   // x[idx[k]] = vals ? vals[k] : 0   (AffineConstraints::distribute for Dirichlet lines)

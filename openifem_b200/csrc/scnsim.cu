@@ -657,7 +657,7 @@ namespace ifem
       const double tol = 1e-3 * nrm2(ctx, vp, d_pt1.p);
       if (tol > 0)
         {
-          const SolveResult r = fgmres(ctx, vp, Tpp, B2, d_pt1.p, dst_p, tol, n_p_global, 50, pool_tpp);
+          const SolveResult r = fgmres(ctx, vp, Tpp, B2, d_pt1.p, dst_p, tol, n_p_global, 50, pool_tpp, /*fused_orthogonalisation=*/true);
           tpp_its += r.iterations;
         }
       else

@@ -673,7 +673,7 @@ namespace ifem
       double rr, alpha, beta, tol2;
       int its, max_it, done, converged;
     };
-    enum CgStage { kCInit, kCDot, kCXR };
+    enum CgStage { kCInit, kCDot, kCXR, kCGear };
 
     __device__ __forceinline__ void cg_advance(int stage, CgState *st, const double *red)
     {
@@ -711,7 +711,95 @@ namespace ifem
         }
     }
 
-    __global__ void cg_advance_kernel(int stage, CgState *st, const double *red) { cg_advance(stage, st, red); }
+    // Single-reduction CG (Chronopoulos & Gear): with w = A r, gamma = r . r and delta = r . w come out of ONE reduction and
+    //   beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old),
+    //   p = r + beta p,  s = w + beta s (= A p),  x += alpha p,  r -= alpha s.
+    // One product, one fused reduction and one fused vector kernel per iteration instead of one product, two reductions and
+    // three vector kernels: at 8 GPUs an iteration of "CG for Sm" is latency bound (a 44 us product against two all-reduces
+    // and five launches), so the reduction count is what it costs. The residual test uses gamma, i.e. it sees the residual of
+    // the previous update (one extra product at the very end).
+    __device__ __forceinline__ void cg_gear_advance(CgState *st, const double *red)
+    {
+      if (st->done) return;
+      const double gamma = red[0], delta = red[1];
+      if (!(gamma > st->tol2) || !isfinite(gamma))
+        {
+          st->rr = gamma;
+          st->done = 1;
+          st->converged = gamma <= st->tol2 ? 1 : 0;
+          return;
+        }
+      if (st->its >= st->max_it)
+        {
+          st->rr = gamma;
+          st->done = 1;
+          return;
+        }
+      const double beta = st->its == 0 ? 0.0 : gamma / st->rr;
+      const double denom = st->its == 0 ? delta : delta - beta * gamma / st->alpha;
+      if (!(denom > 0.0) || !isfinite(denom))
+        {
+          st->rr = gamma;
+          st->done = 1; // not positive definite in fp32 (or breakdown): the caller falls back
+          return;
+        }
+      st->beta = beta;
+      st->alpha = gamma / denom;
+      st->rr = gamma;
+      st->its += 1;
+    }
+
+    __global__ void cg_advance_kernel(int stage, CgState *st, const double *red)
+    {
+      if (stage == kCGear) cg_gear_advance(st, red);
+      else cg_advance(stage, st, red);
+    }
+
+    // r = src / |src| in SELL order; x = p = s = 0
+    __global__ void __launch_bounds__(kT)
+    cg_gear_init_kernel(int n_pad, const int *__restrict__ perm_row, const double *__restrict__ src, double scale, float *__restrict__ r,
+                        float *__restrict__ p, float *__restrict__ s, float *__restrict__ x)
+    {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const int row = perm_row[i];
+          r[i] = row >= 0 ? (float)(src[row] * scale) : 0.0f;
+          p[i] = s[i] = x[i] = 0.0f;
+        }
+    }
+
+    // gamma = r . r, delta = r . w in one reduction; the last CTA advances the recurrence
+    __global__ void __launch_bounds__(kT)
+    cg_gear_dot_kernel(int n_pad, const float *__restrict__ r, const float *__restrict__ w, CgState *st, double *__restrict__ partials,
+                       unsigned int *__restrict__ counter, double *__restrict__ red, PeerDev pd, int adv)
+    {
+      if (st->done) return;
+      double acc[2] = {0.0, 0.0};
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const double ri = (double)r[i];
+          acc[0] += ri * ri;
+          acc[1] += ri * (double)w[i];
+        }
+      if (finish_reduce<2>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) cg_gear_advance(st, acc);
+    }
+
+    // p = r + beta p; s = w + beta s; x += alpha p; r -= alpha s
+    __global__ void __launch_bounds__(kT)
+    cg_gear_update_kernel(int n_pad, const CgState *__restrict__ st, float *__restrict__ r, const float *__restrict__ w, float *__restrict__ p,
+                          float *__restrict__ s, float *__restrict__ x)
+    {
+      if (st->done) return;
+      const float alpha = (float)st->alpha, beta = (float)st->beta;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const float pi = fmaf(beta, p[i], r[i]), si = fmaf(beta, s[i], w[i]);
+          p[i] = pi;
+          s[i] = si;
+          x[i] = fmaf(alpha, pi, x[i]);
+          r[i] = fmaf(-alpha, si, r[i]);
+        }
+    }
 
     __global__ void cg_begin_kernel(CgState *st, double tol2, int max_it)
     {
@@ -1324,14 +1412,16 @@ namespace ifem
   {
     if (A.R != 1) throw std::runtime_error("InnerCG32: scalar matrix required");
     S.build(ctx, A, nodes, halo_, precision);
-    for (DevBuf<float> *b : {&r, &ap, &x})
+    for (DevBuf<float> *b : {&r, &ap, &x, &pg, &sg})
       {
         b->alloc((size_t)S.n_pad);
         b->zero(ctx.stream);
       }
     p = S.gather_source(ctx, 0);
+    rg = S.gather_source(ctx, 1);
+    if (const char *e = std::getenv("IFEM_CG_SM_GEAR")) single_reduction = std::atoi(e) != 0;
     grid = std::max(1, std::min((S.n_pad + kT - 1) / kT, ctx.sm_count * 4));
-    partials.alloc((size_t)grid);
+    partials.alloc((size_t)grid * 2);
     red.alloc(kPeerMaxVals);
     red.zero(ctx.stream);
     counter.alloc(1);
@@ -1370,6 +1460,42 @@ namespace ifem
     const double tol_rel = tol_abs / src_norm;
     cg_begin_kernel<<<1, 1, 0, ctx.stream>>>(st, tol_rel * tol_rel, max_it);
     launched();
+    if (single_reduction)
+      {
+        // w lives in `ap`, r in the gather source `rg` (it is what the product reads)
+        cg_gear_init_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, rg, pg.p, sg.p, x.p);
+        launched();
+        int enqueued = 0;
+        while (true)
+          {
+            const int chunk = std::max(1, std::min(check_every, max_it + 1 - enqueued));
+            for (int k = 0; k < chunk; ++k)
+              {
+                S.halo(ctx, rg, &st->done);
+                S.apply(ctx, rg, ap.p, &st->done);
+                cg_gear_dot_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, rg, ap.p, st, partials.p, counter.p, red.p, m.pd, m.adv);
+                launched();
+                if (m.nccl)
+                  {
+                    comm_allreduce_sum(*ctx.comm, red.p, 2, ctx.stream);
+                    cg_advance_kernel<<<1, 1, 0, ctx.stream>>>(kCGear, st, red.p);
+                    launched();
+                  }
+                cg_gear_update_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, rg, ap.p, pg.p, sg.p, x.p);
+                launched();
+              }
+            enqueued += chunk;
+            IFEM_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CgState), cudaMemcpyDeviceToHost, ctx.stream));
+            IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+            if (h->done || enqueued > max_it) break;
+          }
+        out.iterations = h->its;
+        out.residual = std::sqrt(std::max(0.0, h->rr)) * src_norm;
+        out.converged = h->done && h->converged;
+        final_kernel<1><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x.p, src_norm, dst);
+        launched();
+        return out;
+      }
     cg_init_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, r.p, p, x.p, st, partials.p, counter.p, red.p, m.pd,
                                                 m.adv);
     launched();

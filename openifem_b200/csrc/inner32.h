@@ -149,10 +149,15 @@ namespace ifem
     SolveResult solve(Context &ctx, const double *src, double src_norm, double *dst, double tol_abs, int max_it);
     Sell32 S;
     int check_every = 10;
+    // single-reduction recurrence (Chronopoulos-Gear): one fused all-reduce of two values and four launches per iteration instead
+    // of two all-reduces and six launches (inner32.cu cg_gear_*); IFEM_CG_SM_GEAR=0 selects the classical recurrence
+    bool single_reduction = true;
 
   private:
     DevBuf<float> r, ap, x; // [n_pad]
+    DevBuf<float> pg, sg;   // [n_pad] search direction and its product (single-reduction variant)
     float *p = nullptr;     // [x_len] gather source (S.gather_source)
+    float *rg = nullptr;    // [x_len] gather source holding the residual (single-reduction variant)
     DevBuf<double> partials, red;
     DevBuf<unsigned int> counter;
     DevBuf<int> state;      // CgState (inner32.cu)

@@ -11,7 +11,7 @@ namespace ifem
   // Context
   // ---------------------------------------------------------------------------
   static constexpr int kMaxPartials = 4096;
-  static constexpr int kOrthoMaxBasis = 64, kOrthoMaxGrid = 256; // fused Gram-Schmidt (orthogonalise_cgs2)
+  static constexpr int kOrthoMaxBasis = 64, kOrthoMaxGrid = 2048; // fused Gram-Schmidt (orthogonalise_cgs2)
 
   Context::Context()
   {

@@ -76,7 +76,7 @@ def main():
     elif solver == "InsIM":
         flow.set_control(a_inv_rel=1e-10, a_inv_max_it=5000, fgmres_rel=1e-9)
     elif q1:
-        flow.set_control(fgmres_rel=1e-10)
+        flow.set_control(fgmres_rel=1e-10, supg_ilu=0)
     n_un_glob = int(np.prod([(1 if q1 else 2) * k + 1 for k in reps]))
     n_pn_glob = int(np.prod([k + 1 for k in reps]))
     if refined:
@@ -162,7 +162,7 @@ def acoustic_case(rank, size, out):
     ifem.GridGenerator.subdivided_hyper_rectangle(tria, c["reps"], (0, 0), c["hi"], True)
     flow = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=text))
     flow.add_hard_coded_boundary_condition(0, acoustic_cases.gaussian_pulse("duct", 1e-7))
-    flow.set_control(fgmres_rel=1e-10)
+    flow.set_control(fgmres_rel=1e-10, supg_ilu=0)
     flow.run()
     n_un_glob = (c["reps"][0] * 4 + 1) * (c["reps"][1] * 4 + 1)
     loc, glo = flow.owned_global_dofs(n_un_glob)
@@ -188,7 +188,7 @@ def fsi_case(rank, size, out, dim, reps):
     fluid, solid = ifem.Fluid.MPI.SCnsIM(ftria, params), ifem.Solid.MPI.HyperElasticity(stria, params)
     fluid.setup()
     solid.setup()
-    fluid.set_control(fgmres_rel=1e-10)
+    fluid.set_control(fgmres_rel=1e-10, supg_ilu=0)
     coupling = ifem.MPI.FSI(fluid, solid, params, sys.argv[-1] == "dirichlet")
     for k in range(2):
         coupling.run_one_step(k == 0)

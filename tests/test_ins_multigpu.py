@@ -213,7 +213,7 @@ def _scns_worker(rank, size, idfile, dim, reps, steps, q, mode="plain"):
             flow, solid = ifem.Fluid.MPI.SCnsIM(tria, params), ifem.Solid.MPI.HyperElasticity(stria, params)
             flow.setup()
             solid.setup()
-            flow.set_control(fgmres_rel=1e-10)
+            flow.set_control(fgmres_rel=1e-10, supg_ilu=0)  # the same (Jacobi) factors on one rank as on several: partition parity only
             coupling = ifem.MPI.FSI(flow, solid, params, mode == "fsi_dirichlet")
         else:
             hi = (2.0,) + (1.0,) * (dim - 1)
@@ -225,7 +225,7 @@ def _scns_worker(rank, size, idfile, dim, reps, steps, q, mode="plain"):
             flow = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=scns_prm(dim, dt=1e-3)))
             flow.set_body_force(lambda p, c: 5.0 if c == 0 else 0.0)
             flow.setup()
-            flow.set_control(fgmres_rel=1e-10)
+            flow.set_control(fgmres_rel=1e-10, supg_ilu=0)  # the same (Jacobi) factors on one rank as on several: partition parity only
         n_un_glob = tria.n_vertices()
         loc, glo = flow.owned_global_dofs(n_un_glob)
         for k in range(steps):

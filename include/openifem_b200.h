@@ -342,6 +342,9 @@ int ifem_fsi_run(ifem_fsi *f);
 int ifem_fsi_bench_steps(ifem_fsi *f, int n_steps, int first_step, double *ms_total);
 int ifem_fsi_timer_ms(const ifem_fsi *f, const char *section, double *ms);
 
+/* kernel shape of the row-plane BCSR mat-vec for short rows and the off-diagonal blocks (tuning sweeps, scripts/spmv_short_sweep.py):
+ * key = 10 * lanes per block row + unroll, 0 = default */
+int ifem_set_spmv_short_variant(int key);
 /* ILU(0) of a scalar CSR matrix (sorted columns, diagonal present) and one application x = U^-1 L^-1 b on the device - the factors
  * behind the block preconditioner of the SUPG solvers (Hypre Euclid in the reference, source/preconditioner_pilut.cpp:124-138).
  * factors [nnz] (L strictly lower with unit diagonal implied, U upper, in place) or NULL; level counts of the two sweeps (tests) */

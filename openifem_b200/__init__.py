@@ -121,6 +121,10 @@ def kernel_launches() -> int:
     return n.value
 
 
+def set_spmv_short_variant(key: int):
+    check(lib().ifem_set_spmv_short_variant(C.c_int(key)))
+
+
 def ilu0_apply(A, b):
     """ILU(0) of the scipy CSR matrix A on the device and x = U^-1 L^-1 b; returns (factors in A's pattern, x, (levels L, levels U))"""
     A = A.tocsr()

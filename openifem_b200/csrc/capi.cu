@@ -1075,6 +1075,10 @@ int ifem_fsi_run(ifem_fsi *f)
 {
   return guard([&] { f->f->run(); });
 }
+int ifem_set_spmv_short_variant(int key)
+{
+  return guard([&] { default_context().spmv_short = key; });
+}
 int ifem_ilu0_apply(int n, const int64_t *rowptr, const int *col, const double *val, const double *b, double *factors, double *x,
                     int *n_levels_lower, int *n_levels_upper)
 {

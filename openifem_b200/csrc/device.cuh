@@ -101,6 +101,7 @@ namespace ifem
     int spmv_variant = 0; // 0 = default kernel; see linalg.cu
     int spmv_l2hint = 0;  // 1: x gathers carry an L2 evict_last policy (IFEM_SPMV_L2HINT)
     int spmv_rpw = 1;     // rows per lane group and CTA chunk (x reuse through L1); IFEM_SPMV_RPW
+    int spmv_short = 0;   // kernel shape for short rows / off-diagonal blocks: 10 * lanes per row + unroll (IFEM_SPMV_SHORT)
     long long kernel_launches = 0; // counted by every launcher (bench "gpu_launches")
     Context();
     ~Context();

@@ -29,6 +29,7 @@ namespace ifem
     IFEM_CUDA(cudaMallocHost(&h_results, 256 * sizeof(double)));
     if (const char *v = std::getenv("IFEM_SPMV_VARIANT")) spmv_variant = std::atoi(v);
     if (const char *v = std::getenv("IFEM_SPMV_RPW")) spmv_rpw = std::atoi(v);
+    if (const char *v = std::getenv("IFEM_SPMV_SHORT")) spmv_short = std::atoi(v);
     if (const char *v = std::getenv("IFEM_SPMV_L2HINT")) spmv_l2hint = std::atoi(v);
   }
 
@@ -259,6 +260,38 @@ namespace ifem
       bcsr_spmv_kernel<R, C, TPR, VT><<<(unsigned)blocks, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, y,
                                                                                 accumulate ? 1 : 0, 1);
     };
+    // short rows (Q1 blocks: 9 / 27 block columns) and the off-diagonal shapes: lanes per row x unroll, 4 CTAs per SM; key =
+    // 10 * lanes per row + unroll (ifem_set_spmv_short_variant / IFEM_SPMV_SHORT; 0 = the default kernel above)
+    if (ctx.spmv_short && !(R == 3 && C == 3 && A.tpr == 32))
+      {
+        auto short_launch = [&](auto tpr_tag, auto unroll_tag) {
+          constexpr int T = decltype(tpr_tag)::value, U = decltype(unroll_tag)::value;
+          const int64_t nblk = ((int64_t)n_rows * T + threads - 1) / threads;
+          bcsr_spmv_row_kernel<R, C, T, VT, U, 4><<<(unsigned)nblk, threads, 0, ctx.stream>>>(n_rows, A.rowptr.p, A.col.p, val, x, y,
+                                                                                              accumulate ? 1 : 0);
+        };
+        using I = std::integral_constant<int, 0>;
+        (void)sizeof(I);
+        bool done = true;
+        switch (ctx.spmv_short)
+          {
+          case 41: short_launch(std::integral_constant<int, 4>(), std::integral_constant<int, 1>()); break;
+          case 44: short_launch(std::integral_constant<int, 4>(), std::integral_constant<int, 4>()); break;
+          case 48: short_launch(std::integral_constant<int, 4>(), std::integral_constant<int, 8>()); break;
+          case 81: short_launch(std::integral_constant<int, 8>(), std::integral_constant<int, 1>()); break;
+          case 84: short_launch(std::integral_constant<int, 8>(), std::integral_constant<int, 4>()); break;
+          case 161: short_launch(std::integral_constant<int, 16>(), std::integral_constant<int, 1>()); break;
+          case 162: short_launch(std::integral_constant<int, 16>(), std::integral_constant<int, 2>()); break;
+          case 321: short_launch(std::integral_constant<int, 32>(), std::integral_constant<int, 1>()); break;
+          default: done = false; break;
+          }
+        if (done)
+          {
+            IFEM_KERNEL_CHECK();
+            ctx.kernel_launches++;
+            return;
+          }
+      }
     switch (A.tpr)
       {
       case 32: launch(std::integral_constant<int, 32>()); break;

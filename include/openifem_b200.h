@@ -77,6 +77,16 @@ int ifem_tria_shift(ifem_tria *t, const double *offset);
  * (tests/fsi_leaflet_mpi/fsi_leaflet_mpi.cpp:66-76, tests/fsi-wall-3D/fsi-wall-3D.cpp:47-53): the flagged cells are replaced by their
  * children, hanging vertices appear on the interface (one level of difference only). n = number of active cells. */
 int ifem_tria_execute_refinement(ifem_tria *t, const unsigned char *flags, int64_t n);
+/* set_refine_flag() / set_coarsen_flag() on the flagged cells, prepare_coarsening_and_refinement() and
+ * execute_coarsening_and_refinement() as FSI::refine_mesh / FluidSolver::refine_mesh use them (source/mpi_fsi.cpp:1062-1088,
+ * source/mpi_fluid_solver.cpp:417-488): one level up or down per call, a family is coarsened when all its children are flagged,
+ * flags are adjusted to p4est's 2:1 balance over shared vertices. coarsen_flags may be NULL. The values of a Q1 field on the new
+ * vertices in terms of the old ones (parallel::distributed::SolutionTransfer) are kept for ifem_tria_get_transfer_plan. */
+int ifem_tria_execute_coarsening_and_refinement(ifem_tria *t, const unsigned char *refine_flags, const unsigned char *coarsen_flags, int64_t n);
+/* CSR lists new vertex -> (old vertex, weight) of the last ifem_tria_execute_coarsening_and_refinement; any pointer may be NULL */
+int ifem_tria_get_transfer_plan(const ifem_tria *t, int64_t *n_new_vertices, int64_t *n_entries, int64_t *ptr, int *old_vertex, double *weight);
+/* cell->level() of every active cell */
+int ifem_tria_get_levels(const ifem_tria *t, int *levels);
 /* hanging vertices of the active mesh: vertex[k] carries the mean of its n_masters[k] (2 or 4) master vertices masters[4 k ..];
  * call with NULL arrays to get the count */
 int ifem_tria_get_hanging(const ifem_tria *t, int64_t *n_hanging, int *vertex, int *n_masters, int *masters);

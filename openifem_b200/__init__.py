@@ -153,6 +153,24 @@ class Triangulation:
         flags = np.ascontiguousarray(flags, dtype=np.uint8)
         check(lib().ifem_tria_execute_refinement(self._h, flags.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int64(flags.size)))
 
+    def execute_coarsening_and_refinement(self, refine_flags, coarsen_flags=None):
+        """flagged refinement and coarsening with 2:1 balancing (one level per call); returns the transfer plan
+        (ptr, old_vertex, weight): value at new vertex k = sum of weight * old value over ptr[k]:ptr[k+1]"""
+        rf = np.ascontiguousarray(refine_flags, dtype=np.uint8)
+        cf = None if coarsen_flags is None else np.ascontiguousarray(coarsen_flags, dtype=np.uint8)
+        check(lib().ifem_tria_execute_coarsening_and_refinement(self._h, rf.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                                                None if cf is None else cf.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int64(rf.size)))
+        nv, ne = C.c_int64(), C.c_int64()
+        check(lib().ifem_tria_get_transfer_plan(self._h, C.byref(nv), C.byref(ne), None, None, None))
+        ptr, old, w = np.empty(nv.value + 1, np.int64), np.empty(ne.value, np.int32), np.empty(ne.value)
+        check(lib().ifem_tria_get_transfer_plan(self._h, None, None, lptr(ptr), iptr(old), dptr(w)))
+        return ptr, old, w
+
+    def levels(self):
+        out = np.empty(self.n_active_cells(), dtype=np.int32)
+        check(lib().ifem_tria_get_levels(self._h, iptr(out)))
+        return out
+
     def hanging(self):
         """(vertex [n], n_masters [n], masters [n][4]) of the hanging vertices of the active mesh"""
         n = C.c_int64()

@@ -23,6 +23,7 @@ using namespace ifem;
 struct ifem_tria
 {
   Triangulation t;
+  Triangulation::TransferPlan last_plan; // of the last ifem_tria_execute_coarsening_and_refinement
 };
 struct ifem_params
 {
@@ -305,6 +306,33 @@ int ifem_tria_execute_refinement(ifem_tria *t, const unsigned char *flags, int64
   return guard([&] {
     if (n != (int64_t)t->t.n_cells()) throw std::runtime_error("ifem_tria_execute_refinement: one flag per active cell expected");
     t->t.execute_refinement(std::vector<unsigned char>(flags, flags + n));
+  });
+}
+int ifem_tria_execute_coarsening_and_refinement(ifem_tria *t, const unsigned char *refine_flags, const unsigned char *coarsen_flags, int64_t n)
+{
+  return guard([&] {
+    if (n != (int64_t)t->t.n_cells()) throw std::runtime_error("ifem_tria_execute_coarsening_and_refinement: one flag per active cell expected");
+    std::vector<unsigned char> rf(refine_flags, refine_flags + n), cf;
+    if (coarsen_flags) cf.assign(coarsen_flags, coarsen_flags + n);
+    t->t.execute_coarsening_and_refinement(rf, cf, &t->last_plan);
+  });
+}
+int ifem_tria_get_transfer_plan(const ifem_tria *t, int64_t *n_new_vertices, int64_t *n_entries, int64_t *ptr, int *old_vertex, double *weight)
+{
+  return guard([&] {
+    const auto &p = t->last_plan;
+    if (n_new_vertices) *n_new_vertices = p.ptr.empty() ? 0 : (int64_t)p.ptr.size() - 1;
+    if (n_entries) *n_entries = (int64_t)p.old_vertex.size();
+    if (ptr) std::copy(p.ptr.begin(), p.ptr.end(), ptr);
+    if (old_vertex) std::copy(p.old_vertex.begin(), p.old_vertex.end(), old_vertex);
+    if (weight) std::copy(p.weight.begin(), p.weight.end(), weight);
+  });
+}
+int ifem_tria_get_levels(const ifem_tria *t, int *levels)
+{
+  return guard([&] {
+    const int nc = t->t.n_cells();
+    for (int c = 0; c < nc; ++c) levels[c] = t->t.cell_level.empty() ? 0 : t->t.cell_level[c];
   });
 }
 int ifem_tria_get_hanging(const ifem_tria *t, int64_t *n_hanging, int *vertex, int *n_masters, int *masters)

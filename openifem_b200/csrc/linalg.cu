@@ -262,7 +262,7 @@ namespace ifem
     };
     // short rows (Q1 blocks: 9 / 27 block columns) and the off-diagonal shapes: lanes per row x unroll, 4 CTAs per SM; key =
     // 10 * lanes per row + unroll (ifem_set_spmv_short_variant / IFEM_SPMV_SHORT; 0 = the default kernel above)
-    if (ctx.spmv_short && !(R == 3 && C == 3 && A.tpr == 32))
+    if (!(R == 3 && C == 3 && A.tpr == 32) && (A.tpr < 32 || ctx.spmv_short))
       {
         auto short_launch = [&](auto tpr_tag, auto unroll_tag) {
           constexpr int T = decltype(tpr_tag)::value, U = decltype(unroll_tag)::value;
@@ -273,7 +273,9 @@ namespace ifem
         using I = std::integral_constant<int, 0>;
         (void)sizeof(I);
         bool done = true;
-        switch (ctx.spmv_short)
+        // default 161: 16 lanes per row, unroll 1 - 4 767 GB/s on the four Q1 blocks of the config-5 system against 3 198 GB/s for the
+        // kernel above (profiles/r02_spmv_short_sweep.txt); -1 selects the kernel above
+        switch (ctx.spmv_short ? ctx.spmv_short : 161)
           {
           case 41: short_launch(std::integral_constant<int, 4>(), std::integral_constant<int, 1>()); break;
           case 44: short_launch(std::integral_constant<int, 4>(), std::integral_constant<int, 4>()); break;

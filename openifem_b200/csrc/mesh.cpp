@@ -524,15 +524,36 @@ namespace ifem
           }
         vertices.swap(new_vertices);
         cells.swap(new_cells);
-        material_id.swap(new_mat);
         boundary_faces.swap(new_bf);
-        if (!cell_level.empty())
-          {
-            std::vector<int> lv((size_t)nc * vpc);
-            for (int c = 0; c < nc; ++c)
-              for (int child = 0; child < vpc; ++child) lv[(size_t)c * vpc + child] = cell_level[c] + 1;
-            cell_level.swap(lv);
-          }
+        {
+          // every cell becomes the parent of a family
+          if (cell_level.empty()) cell_level.assign((size_t)nc, 0);
+          if (cell_family.empty())
+            {
+              cell_family.assign((size_t)nc, -1);
+              cell_child_no.assign((size_t)nc, 0);
+            }
+          std::vector<int> lv((size_t)nc * vpc), fam((size_t)nc * vpc), cno((size_t)nc * vpc);
+          for (int c = 0; c < nc; ++c)
+            {
+              Family f;
+              f.parent_family = cell_family[c];
+              f.parent_child_no = cell_child_no[c];
+              f.parent_level = cell_level[c];
+              f.material = material_id[c];
+              families.push_back(f);
+              for (int child = 0; child < vpc; ++child)
+                {
+                  lv[(size_t)c * vpc + child] = cell_level[c] + 1;
+                  fam[(size_t)c * vpc + child] = (int)families.size() - 1;
+                  cno[(size_t)c * vpc + child] = child;
+                }
+            }
+          cell_level.swap(lv);
+          cell_family.swap(fam);
+          cell_child_no.swap(cno);
+        }
+        material_id.swap(new_mat);
         if (!hanging.empty()) find_hanging_vertices();
       }
   }
@@ -565,8 +586,13 @@ namespace ifem
     for (int i = 0; i < nt.n_nodes; ++i)
       if (used[i])
         for (int d = 0; d < dim; ++d) new_vertices[(size_t)new_id[i] * dim + d] = nt.coords[(size_t)i * dim + d];
-    std::vector<int> new_cells, new_mat, new_level, first_child((size_t)nc, -1);
+    std::vector<int> new_cells, new_mat, new_level, new_fam, new_cno, first_child((size_t)nc, -1);
     if (cell_level.empty()) cell_level.assign((size_t)nc, 0);
+    if (cell_family.empty())
+      {
+        cell_family.assign((size_t)nc, -1);
+        cell_child_no.assign((size_t)nc, 0);
+      }
     for (int c = 0; c < nc; ++c)
       {
         first_child[c] = (int)new_mat.size();
@@ -584,8 +610,18 @@ namespace ifem
               }
             new_mat.push_back(material_id[c]);
             new_level.push_back(cell_level[c]);
+            new_fam.push_back(cell_family[c]);
+            new_cno.push_back(cell_child_no[c]);
             continue;
           }
+        {
+          Family f;
+          f.parent_family = cell_family[c];
+          f.parent_child_no = cell_child_no[c];
+          f.parent_level = cell_level[c];
+          f.material = material_id[c];
+          families.push_back(f);
+        }
         for (int child = 0; child < vpc; ++child)
           {
             for (int v = 0; v < vpc; ++v)
@@ -600,6 +636,8 @@ namespace ifem
               }
             new_mat.push_back(material_id[c]);
             new_level.push_back(cell_level[c] + 1);
+            new_fam.push_back((int)families.size() - 1);
+            new_cno.push_back(child);
           }
       }
     std::vector<int> new_bf;
@@ -619,6 +657,256 @@ namespace ifem
     cells.swap(new_cells);
     material_id.swap(new_mat);
     cell_level.swap(new_level);
+    cell_family.swap(new_fam);
+    cell_child_no.swap(new_cno);
+    boundary_faces.swap(new_bf);
+    find_hanging_vertices();
+  }
+
+  int Triangulation::n_levels() const
+  {
+    int m = 0;
+    for (int l : cell_level) m = std::max(m, l);
+    return m + 1;
+  }
+
+  void Triangulation::execute_coarsening_and_refinement(const std::vector<unsigned char> &refine_flags,
+                                                         const std::vector<unsigned char> &coarsen_flags, TransferPlan *plan)
+  {
+    const int vpc = verts_per_cell(), nc = n_cells(), nv = n_vertices();
+    if ((int)refine_flags.size() != nc || (!coarsen_flags.empty() && (int)coarsen_flags.size() != nc))
+      throw std::runtime_error("execute_coarsening_and_refinement: one flag per active cell expected");
+    if (!chart_of_cell.empty()) throw std::runtime_error("execute_coarsening_and_refinement: meshes with curved charts are not supported");
+    if (cell_level.empty()) cell_level.assign((size_t)nc, 0);
+    if (cell_family.empty())
+      {
+        cell_family.assign((size_t)nc, -1);
+        cell_child_no.assign((size_t)nc, 0);
+      }
+    // ---- target level of every cell ----
+    std::vector<int> desired(cell_level);
+    for (int c = 0; c < nc; ++c)
+      if (refine_flags[c]) desired[c] = cell_level[c] + 1;
+      else if (!coarsen_flags.empty() && coarsen_flags[c] && cell_family[c] >= 0) desired[c] = cell_level[c] - 1;
+    // members of every family among the active cells
+    std::vector<std::vector<int>> members(families.size());
+    for (int c = 0; c < nc; ++c)
+      if (cell_family[c] >= 0) members[cell_family[c]].push_back(c);
+    auto fix_families = [&]() {
+      bool changed = false;
+      for (size_t f = 0; f < members.size(); ++f)
+        {
+          const std::vector<int> &m = members[f];
+          if (m.empty()) continue;
+          bool all = (int)m.size() == vpc;
+          for (int c : m) all = all && desired[c] == cell_level[c] - 1;
+          if (all) continue;
+          for (int c : m)
+            if (desired[c] < cell_level[c])
+              {
+                desired[c] = cell_level[c];
+                changed = true;
+              }
+        }
+      return changed;
+    };
+    fix_families();
+    // ---- 2:1 balance over shared vertices ----
+    std::vector<int> vmax((size_t)nv);
+    for (int sweep = 0; sweep < 64; ++sweep)
+      {
+        std::fill(vmax.begin(), vmax.end(), -1);
+        for (int c = 0; c < nc; ++c)
+          for (int v = 0; v < vpc; ++v) vmax[cells[(size_t)c * vpc + v]] = std::max(vmax[cells[(size_t)c * vpc + v]], desired[c]);
+        // (a fine cell next to a coarser one always shares one of the coarse cell's corners with it, so the corners carry every
+        // demand across a refinement interface; hanging vertices need no special treatment)
+        bool changed = false;
+        for (int c = 0; c < nc; ++c)
+          {
+            int need = -1;
+            for (int v = 0; v < vpc; ++v) need = std::max(need, vmax[cells[(size_t)c * vpc + v]] - 1);
+            need = std::min(need, cell_level[c] + 1);
+            if (desired[c] < need)
+              {
+                desired[c] = need;
+                changed = true;
+              }
+          }
+        changed = fix_families() || changed;
+        if (!changed) break;
+      }
+    // ---- new cells ----
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d) lo[d] = hi[d] = vertices[d];
+    for (int i = 0; i < nv; ++i)
+      for (int d = 0; d < dim; ++d)
+        {
+          lo[d] = std::min(lo[d], vertices[(size_t)i * dim + d]);
+          hi[d] = std::max(hi[d], vertices[(size_t)i * dim + d]);
+        }
+    auto key_of = [&](const double *x) {
+      uint64_t key = 0;
+      for (int d = dim - 1; d >= 0; --d)
+        {
+          const double ext = hi[d] - lo[d];
+          key = (key << 21) | (uint64_t)std::llround((ext > 0 ? (x[d] - lo[d]) / ext : 0.0) * double((1u << 21) - 2));
+        }
+      return key;
+    };
+    std::unordered_map<uint64_t, int> at;
+    at.reserve((size_t)nv * 2);
+    for (int i = 0; i < nv; ++i) at.emplace(key_of(&vertices[(size_t)i * dim]), i);
+    std::vector<double> verts(vertices);
+    // transfer weights of vertices created here: (old vertex, weight) lists, old vertices are the identity
+    std::vector<std::vector<std::pair<int, double>>> created;
+    auto lattice_vertex = [&](int c, const int *ijk) {
+      // point (i, j, k) / 2 of cell c under its Q1 map = mean of the corners whose bits agree where the index is 0 or 2
+      int ids[8], n = 0;
+      for (int v = 0; v < vpc; ++v)
+        {
+          bool ok = true;
+          for (int d = 0; d < dim; ++d)
+            {
+              const int bit = (v >> d) & 1;
+              if ((ijk[d] == 0 && bit) || (ijk[d] == 2 && !bit)) ok = false;
+            }
+          if (ok) ids[n++] = cells[(size_t)c * vpc + v];
+        }
+      if (n == 1) return ids[0];
+      double x[3] = {0, 0, 0};
+      for (int k = 0; k < n; ++k)
+        for (int d = 0; d < dim; ++d) x[d] += vertices[(size_t)ids[k] * dim + d] / n;
+      const uint64_t key = key_of(x);
+      auto it = at.find(key);
+      if (it != at.end()) return it->second;
+      const int id = (int)(verts.size() / dim);
+      for (int d = 0; d < dim; ++d) verts.push_back(x[d]);
+      at.emplace(key, id);
+      std::vector<std::pair<int, double>> w;
+      for (int k = 0; k < n; ++k) w.emplace_back(ids[k], 1.0 / n);
+      created.push_back(w);
+      return id;
+    };
+    std::vector<int> new_cells, new_mat, new_level, new_fam, new_cno;
+    std::vector<int> new_index_of_old((size_t)nc, -1), n_new_of_old((size_t)nc, 0);
+    std::vector<char> family_done(families.size(), 0);
+    for (int c = 0; c < nc; ++c)
+      {
+        if (desired[c] == cell_level[c] - 1)
+          {
+            const int f = cell_family[c];
+            if (family_done[f]) continue;
+            family_done[f] = 1;
+            // the parent: corner k is corner k of child k
+            std::vector<int> child_cell(vpc, -1);
+            for (int m : members[f]) child_cell[cell_child_no[m]] = m;
+            new_index_of_old[c] = (int)new_mat.size();
+            for (int k = 0; k < vpc; ++k) new_cells.push_back(cells[(size_t)child_cell[k] * vpc + k]);
+            new_mat.push_back(families[f].material);
+            new_level.push_back(families[f].parent_level);
+            new_fam.push_back(families[f].parent_family);
+            new_cno.push_back(families[f].parent_child_no);
+            for (int m : members[f]) new_index_of_old[m] = new_index_of_old[c]; // children -> the parent (boundary faces below)
+            continue;
+          }
+        new_index_of_old[c] = (int)new_mat.size();
+        if (desired[c] == cell_level[c])
+          {
+            for (int v = 0; v < vpc; ++v) new_cells.push_back(cells[(size_t)c * vpc + v]);
+            new_mat.push_back(material_id[c]);
+            new_level.push_back(cell_level[c]);
+            new_fam.push_back(cell_family[c]);
+            new_cno.push_back(cell_child_no[c]);
+            n_new_of_old[c] = 1;
+            continue;
+          }
+        Family f;
+        f.parent_family = cell_family[c];
+        f.parent_child_no = cell_child_no[c];
+        f.parent_level = cell_level[c];
+        f.material = material_id[c];
+        families.push_back(f);
+        for (int child = 0; child < vpc; ++child)
+          {
+            for (int v = 0; v < vpc; ++v)
+              {
+                int ijk[3] = {0, 0, 0};
+                for (int d = 0; d < dim; ++d) ijk[d] = ((child >> d) & 1) + ((v >> d) & 1);
+                new_cells.push_back(lattice_vertex(c, ijk));
+              }
+            new_mat.push_back(material_id[c]);
+            new_level.push_back(cell_level[c] + 1);
+            new_fam.push_back((int)families.size() - 1);
+            new_cno.push_back(child);
+          }
+        n_new_of_old[c] = vpc;
+      }
+    // ---- boundary faces ----
+    std::vector<int> new_bf;
+    {
+      std::vector<char> seen; // (new cell, face) already emitted (a coarsened family meets it once per child on that side)
+      seen.assign(new_mat.size() * 2 * (size_t)dim, 0);
+      for (int f = 0; f < n_boundary_faces(); ++f)
+        {
+          const int c = boundary_faces[3 * f], face = boundary_faces[3 * f + 1], id = boundary_faces[3 * f + 2];
+          const int axis = face / 2, side = face % 2;
+          if (desired[c] == cell_level[c] + 1)
+            {
+              for (int child = 0; child < vpc; ++child)
+                if (((child >> axis) & 1) == side) new_bf.insert(new_bf.end(), {new_index_of_old[c] + child, face, id});
+              continue;
+            }
+          const int nc2 = new_index_of_old[c];
+          if (desired[c] == cell_level[c] - 1 && ((cell_child_no[c] >> axis) & 1) != side) continue; // an inner face of the parent
+          char &s = seen[(size_t)nc2 * 2 * dim + face];
+          if (s) continue;
+          s = 1;
+          new_bf.insert(new_bf.end(), {nc2, face, id});
+        }
+    }
+    // ---- drop unused vertices ----
+    const int nv_all = (int)(verts.size() / dim);
+    std::vector<int> new_id((size_t)nv_all, -1);
+    for (int v : new_cells) new_id[v] = 0;
+    int nv_new = 0;
+    for (int i = 0; i < nv_all; ++i)
+      if (new_id[i] == 0) new_id[i] = nv_new++;
+    std::vector<double> new_vertices((size_t)nv_new * dim);
+    for (int i = 0; i < nv_all; ++i)
+      if (new_id[i] >= 0)
+        for (int d = 0; d < dim; ++d) new_vertices[(size_t)new_id[i] * dim + d] = verts[(size_t)i * dim + d];
+    for (int &v : new_cells) v = new_id[v];
+    if (plan)
+      {
+        plan->ptr.assign((size_t)nv_new + 1, 0);
+        plan->old_vertex.clear();
+        plan->weight.clear();
+        std::vector<int> old_of_new((size_t)nv_new, -1);
+        for (int i = 0; i < nv_all; ++i)
+          if (new_id[i] >= 0) old_of_new[new_id[i]] = i;
+        for (int k = 0; k < nv_new; ++k)
+          {
+            const int i = old_of_new[k];
+            if (i < nv)
+              {
+                plan->old_vertex.push_back(i);
+                plan->weight.push_back(1.0);
+              }
+            else
+              for (const auto &pw : created[(size_t)i - nv])
+                {
+                  plan->old_vertex.push_back(pw.first);
+                  plan->weight.push_back(pw.second);
+                }
+            plan->ptr[(size_t)k + 1] = (int64_t)plan->old_vertex.size();
+          }
+      }
+    vertices.swap(new_vertices);
+    cells.swap(new_cells);
+    material_id.swap(new_mat);
+    cell_level.swap(new_level);
+    cell_family.swap(new_fam);
+    cell_child_no.swap(new_cno);
     boundary_faces.swap(new_bf);
     find_hanging_vertices();
   }

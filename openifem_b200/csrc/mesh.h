@@ -58,6 +58,34 @@ namespace ifem
     std::vector<Hanging> hanging;
     std::vector<int> cell_level; // [n_cells] refinement level of every active cell (empty: all 0)
 
+    // Refinement forest, kept so that cells can be coarsened again (FSI::refine_mesh, source/mpi_fsi.cpp:1024-1117): the 2^dim
+    // children of a refined cell form a family; the parent is recovered from them (its corner c is corner c of child c, its
+    // boundary faces are those of the children on that side) together with the family it belonged to itself.
+    struct Family
+    {
+      int parent_family = -1, parent_child_no = 0; // what the parent was a child of (-1: a cell of the coarse mesh)
+      int parent_level = 0, material = 1;
+    };
+    std::vector<Family> families;
+    std::vector<int> cell_family;   // [n_cells] family of an active cell, -1 for coarse-mesh cells (empty: all -1)
+    std::vector<int> cell_child_no; // [n_cells] which child of its parent (lexicographic)
+
+    // values of a Q1 field on the new vertices in terms of the old ones (parallel::distributed::SolutionTransfer for FE_Q(1):
+    // a vertex that existed keeps its value, a vertex created inside a refined cell interpolates the cell's corners)
+    struct TransferPlan
+    {
+      std::vector<int64_t> ptr;    // [n_new_vertices + 1]
+      std::vector<int> old_vertex; // old vertex ids
+      std::vector<double> weight;
+    };
+    // cell->set_refine_flag() / set_coarsen_flag() + prepare_coarsening_and_refinement() + execute_coarsening_and_refinement():
+    // one level up or down per call. A family is coarsened when all its children are active and flagged; flags are then adjusted
+    // until neighbouring cells (sharing a vertex - p4est's full 2:1 balance) differ by at most one level: refinement wins over
+    // a neighbour's coarsening and forces coarser neighbours to refine. Straight-sided meshes only.
+    void execute_coarsening_and_refinement(const std::vector<unsigned char> &refine_flags, const std::vector<unsigned char> &coarsen_flags,
+                                           TransferPlan *plan = nullptr);
+    int n_levels() const;
+
     void refine_global(int times);
     // cell->set_refine_flag() on the flagged cells + execute_coarsening_and_refinement() (tests/fsi_leaflet_mpi/fsi_leaflet_mpi.cpp:
     // 66-76): flagged cells are replaced by their 2^dim children, the others stay; straight-sided meshes only (no charts).

@@ -75,3 +75,62 @@ def test_mesh_import_through_the_abi_round_trips_and_finds_hanging_vertices():
 
     with pytest.raises(RuntimeError, match="inverted"):
         ifem.Triangulation(3).set_mesh(v, bad, f)
+
+
+def _cell_volumes(v, c):
+    dim = v.shape[1]
+    e = [v[c[:, 1 << d]] - v[c[:, 0]] for d in range(dim)]
+    return np.abs(np.linalg.det(np.stack(e, axis=1)))
+
+
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_coarsening_and_refinement_keeps_a_balanced_mesh_and_transfers_linear_fields(dim):
+    """execute_coarsening_and_refinement (FSI::refine_mesh's mesh operation): random refine / coarsen flags over several rounds -
+    the mesh stays a partition of the box, neighbours differ by one level at most (find_hanging_vertices would throw), the
+    transfer plan reproduces a linear field, and coarsening everything leads back to the coarse mesh"""
+    import openifem_b200 as ifem
+
+    rng = np.random.default_rng(4)
+    t = ifem.Triangulation(dim)
+    reps = (5, 4) if dim == 2 else (3, 2, 3)
+    hi = (2.5, 2.0) if dim == 2 else (1.5, 1.0, 1.5)
+    ifem.GridGenerator.subdivided_hyper_rectangle(t, reps, (0,) * dim, hi, True)
+    vol = float(np.prod(hi))
+    n0 = t.n_active_cells()
+    lin = lambda x: 0.3 + x @ np.array([0.8, -0.4, 0.55][:dim])
+    v, c, b = t.get_mesh()
+    area0 = {}
+    for k in range(6):
+        nc = t.n_active_cells()
+        refine = rng.uniform(size=nc) < (0.25 if k < 4 else 0.05)
+        coarsen = (rng.uniform(size=nc) < 0.5) & ~refine
+        field = lin(v)
+        ptr, old, w = t.execute_coarsening_and_refinement(refine, coarsen)
+        v, c, b = t.get_mesh()
+        assert abs(_cell_volumes(v, c).sum() - vol) < 1e-12 * vol
+        new_field = np.array([np.dot(w[ptr[i]:ptr[i + 1]], field[old[ptr[i]:ptr[i + 1]]]) for i in range(v.shape[0])])
+        assert np.abs(new_field - lin(v)).max() < 1e-13
+        lv = t.levels()
+        assert lv.min() >= 0 and lv.max() <= k + 1
+        # boundary faces still cover the boundary: total boundary measure is that of the box
+        meas = 0.0
+        for (cell, face, _id) in b:
+            axis, side = face // 2, face % 2
+            cv = v[c[cell]]
+            ext = cv.max(axis=0) - cv.min(axis=0)
+            meas += np.prod(np.delete(ext, axis))
+        expect = 2 * sum(np.prod(np.delete(np.array(hi), a)) for a in range(dim))
+        assert abs(meas - expect) < 1e-12 * expect
+        hv, hk, hm = t.hanging()
+        assert (lv.max() == lv.min()) == (hv.size == 0)
+    assert t.levels().max() >= 2
+    for _ in range(8):  # coarsen everything: back to the coarse mesh, cell for cell
+        nc = t.n_active_cells()
+        t.execute_coarsening_and_refinement(np.zeros(nc, bool), np.ones(nc, bool))
+    v2, c2, b2 = t.get_mesh()
+    assert t.n_active_cells() == n0 and t.levels().max() == 0 and t.hanging()[0].size == 0
+    assert abs(_cell_volumes(v2, c2).sum() - vol) < 1e-12 * vol and v2.shape[0] == int(np.prod([r + 1 for r in reps]))

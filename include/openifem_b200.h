@@ -347,6 +347,10 @@ int ifem_fsi_run_one_step(ifem_fsi *f, int first_step);
  * fsi_acceleration the fluid solver is about to see (tests compare them and the assembled system with the oracle) */
 int ifem_fsi_prepare_fluid_step(ifem_fsi *f, int first_step);
 int ifem_fsi_run(ifem_fsi *f);
+/* FSI::refine_mesh(min_grid_level, max_grid_level) (source/mpi_fsi.cpp:1024-1117): flags from the distance of every fluid cell to the
+ * boundary of the deformed solid, coarsening and refinement of the fluid triangulation, solution transfer, new fluid system.
+ * ifem_fsi_run calls it like the reference when `Refinement interval` < `End time` (:1164-1168, :1215-1218) */
+int ifem_fsi_refine_mesh(ifem_fsi *f, unsigned int min_grid_level, unsigned int max_grid_level);
 /* n_steps passes of the coupled loop (ifem_fsi_run_one_step) between two CUDA events on the library's stream: the span covers
  * the device work and the host orchestration between the kernels (bench.py) */
 int ifem_fsi_bench_steps(ifem_fsi *f, int n_steps, int first_step, double *ms_total);

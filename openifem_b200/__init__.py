@@ -802,6 +802,9 @@ class _FSI:
         check(lib().ifem_fsi_timer_ms(self._h, section.encode(), C.byref(ms)))
         return ms.value
 
+    def refine_mesh(self, min_grid_level, max_grid_level):
+        check(lib().ifem_fsi_refine_mesh(self._h, C.c_uint(min_grid_level), C.c_uint(max_grid_level)))
+
     def bench_steps(self, n_steps, first_step=False):
         """n_steps coupled passes between CUDA events on the library's stream; total milliseconds"""
         ms = C.c_double()

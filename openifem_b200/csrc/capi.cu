@@ -1126,6 +1126,10 @@ int ifem_ilu0_apply(int n, const int64_t *rowptr, const int *col, const double *
     if (n_levels_upper) *n_levels_upper = ilu.n_levels_upper;
   });
 }
+int ifem_fsi_refine_mesh(ifem_fsi *f, unsigned int min_grid_level, unsigned int max_grid_level)
+{
+  return guard([&] { f->f->refine_mesh(min_grid_level, max_grid_level); });
+}
 int ifem_fsi_bench_steps(ifem_fsi *f, int n_steps, int first_step, double *ms_total)
 {
   return guard([&] {

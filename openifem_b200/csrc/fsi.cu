@@ -821,6 +821,31 @@ namespace ifem
         n_bseg = (int)seg.size() / 2;
         d_bseg.upload(seg, s);
       }
+    // vertices of the solid's boundary faces that are not fully fixed (mpi_fsi.cpp:690-703)
+    {
+      const Triangulation &st = solid.triangulation;
+      const unsigned fixed = (1u << dim) - 1;
+      std::vector<int> bv;
+      for (int f = 0; f < st.n_boundary_faces(); ++f)
+        {
+          auto bc = parameters.solid_dirichlet_bcs.find((unsigned)st.boundary_faces[3 * f + 2]);
+          if (bc != parameters.solid_dirichlet_bcs.end() && bc->second == fixed) continue;
+          const int cell = st.boundary_faces[3 * f], face = st.boundary_faces[3 * f + 1];
+          for (int a : face_local_nodes(dim, 1, face)) bv.push_back(ss.nt.cell_nodes[(size_t)cell * ss.npc + a]);
+        }
+      std::sort(bv.begin(), bv.end());
+      bv.erase(std::unique(bv.begin(), bv.end()), bv.end());
+      n_solid_bvert = (int)bv.size();
+      if (n_solid_bvert) d_solid_bvert.upload(bv, s);
+    }
+    build_fluid_side();
+    IFEM_CUDA(cudaStreamSynchronize(s));
+  }
+
+  void FsiCoupling::build_fluid_side()
+  {
+    const FluidSpace &fs = fluid.fs;
+    cudaStream_t s = ctx.stream;
     // fluid velocity node -> (cell, local index), cells ascending
     {
       const int nn = fs.un.n_nodes, nu = fs.nu;
@@ -866,25 +891,82 @@ namespace ifem
     }
     d_inner_con.alloc(fs.n_dofs);
     d_inner_inhom.alloc(fs.n_dofs);
-    // vertices of the solid's boundary faces that are not fully fixed (mpi_fsi.cpp:690-703)
+    build_fluid_bins();
+  }
+
+  void FsiCoupling::refine_mesh(unsigned int min_grid_level, unsigned int max_grid_level)
+  {
+    ScopedTimer t(ctx, timer_ms["Refine mesh"]);
+    Triangulation &ft = fluid.triangulation;
+    const Triangulation &st = solid.triangulation;
+    const SolidSpace &ss = solid.ss;
+    // move_solid_mesh(true): deformed vertex positions (:1029)
+    refresh_deformed();
+    const std::vector<double> x = d_x.to_host(ctx.stream);
+    // one point per solid boundary cell: the centre of its first boundary face (:1030-1050)
+    std::vector<double> pts;
     {
-      const Triangulation &st = solid.triangulation;
-      const unsigned fixed = (1u << dim) - 1;
-      std::vector<int> bv;
+      std::vector<int> first_face((size_t)st.n_cells(), -1);
       for (int f = 0; f < st.n_boundary_faces(); ++f)
         {
-          auto bc = parameters.solid_dirichlet_bcs.find((unsigned)st.boundary_faces[3 * f + 2]);
-          if (bc != parameters.solid_dirichlet_bcs.end() && bc->second == fixed) continue;
-          const int cell = st.boundary_faces[3 * f], face = st.boundary_faces[3 * f + 1];
-          for (int a : face_local_nodes(dim, 1, face)) bv.push_back(ss.nt.cell_nodes[(size_t)cell * ss.npc + a]);
+          int &ff = first_face[st.boundary_faces[3 * f]];
+          const int face = st.boundary_faces[3 * f + 1];
+          if (ff < 0 || face < ff) ff = face;
         }
-      std::sort(bv.begin(), bv.end());
-      bv.erase(std::unique(bv.begin(), bv.end()), bv.end());
-      n_solid_bvert = (int)bv.size();
-      if (n_solid_bvert) d_solid_bvert.upload(bv, s);
+      for (int c = 0; c < st.n_cells(); ++c)
+        {
+          if (first_face[c] < 0) continue;
+          const std::vector<int> fn = face_local_nodes(dim, 1, first_face[c]);
+          double p[3] = {0, 0, 0};
+          for (int a : fn)
+            for (int d = 0; d < dim; ++d) p[d] += x[(size_t)ss.nt.cell_nodes[(size_t)c * ss.npc + a] * dim + d] / fn.size();
+          pts.insert(pts.end(), p, p + dim);
+        }
     }
-    build_fluid_bins();
-    IFEM_CUDA(cudaStreamSynchronize(s));
+    const int n_pts = (int)(pts.size() / dim), nc = ft.n_cells(), vpc = ft.verts_per_cell();
+    std::vector<unsigned char> refine((size_t)nc, 0), coarsen((size_t)nc, 0);
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nc; ++c)
+      {
+        double ctr[3] = {0, 0, 0}, diam2 = 0.0;
+        for (int v = 0; v < vpc; ++v)
+          for (int d = 0; d < dim; ++d) ctr[d] += ft.vertices[(size_t)ft.cells[(size_t)c * vpc + v] * dim + d] / vpc;
+        for (int v = 0; v < vpc; ++v)
+          for (int w = v + 1; w < vpc; ++w)
+            {
+              double d2 = 0.0;
+              for (int d = 0; d < dim; ++d)
+                {
+                  const double e = ft.vertices[(size_t)ft.cells[(size_t)c * vpc + v] * dim + d] - ft.vertices[(size_t)ft.cells[(size_t)c * vpc + w] * dim + d];
+                  d2 += e * e;
+                }
+              diam2 = std::max(diam2, d2);
+            }
+        double best = std::numeric_limits<double>::max();
+        for (int k = 0; k < n_pts; ++k)
+          {
+            double d2 = 0.0;
+            for (int d = 0; d < dim; ++d) d2 += (ctr[d] - pts[(size_t)k * dim + d]) * (ctr[d] - pts[(size_t)k * dim + d]);
+            best = std::min(best, d2);
+          }
+        if (std::sqrt(best) < std::sqrt(diam2)) refine[c] = 1;
+        else coarsen[c] = 1;
+      }
+    // level limits (:1064-1080)
+    const std::vector<int> &level = ft.cell_level;
+    auto lvl = [&](int c) { return level.empty() ? 0 : level[c]; };
+    if ((unsigned)ft.n_levels() > max_grid_level)
+      for (int c = 0; c < nc; ++c)
+        if ((unsigned)lvl(c) >= max_grid_level) refine[c] = 0;
+    for (int c = 0; c < nc; ++c)
+      if ((unsigned)lvl(c) == min_grid_level) coarsen[c] = 0;
+    const std::vector<double> old_vertices = ft.vertices;
+    Triangulation::TransferPlan plan;
+    ft.execute_coarsening_and_refinement(refine, coarsen, &plan);
+    fluid.after_mesh_change(plan, old_vertices);
+    build_fluid_side();
+    deformed_valid = false;
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
 
   void FsiCoupling::build_fluid_bins()
@@ -1107,17 +1189,19 @@ namespace ifem
           throw std::runtime_error("Solid and fluid restart files have different time steps. Check and remove inconsistent restart files!");
         while (time.get_timestep() < solid.time.get_timestep()) time.increment();
       }
-    // FSI::refine_mesh (mpi_fsi.cpp:1024-1117; called twice before the first step and at every refinement interval, :1164-1168,
-    // :1215-1218) needs coarsening and solution transfer, which the mesh class does not have: fail loudly instead of running the
-    // case on a mesh the reference would not use
-    if (parameters.refinement_interval < parameters.end_time)
-      throw std::runtime_error("MPI::FSI::run: `Refinement interval` < `End time` asks for FSI::refine_mesh (adaptive refinement with solution "
-                               "transfer), which is not implemented; refine the fluid mesh before constructing the solver");
+    const unsigned int g0 = parameters.global_refinements.empty() ? 0u : (unsigned)parameters.global_refinements[0];
+    const bool adaptive = parameters.refinement_interval < parameters.end_time;
+    if (adaptive) // :1164-1168
+      {
+        refine_mesh(g0, g0 + 3);
+        refine_mesh(g0, g0 + 3);
+      }
     bool first_step = !restarted;
     while (time.end() - time.current() > 1e-12)
       {
         run_one_step(first_step);
         first_step = false;
+        if (adaptive && time.time_to_refine()) refine_mesh(g0, g0 + 3); // :1215-1218
       }
   }
 

@@ -34,6 +34,10 @@ namespace ifem
     void find_solid_bc();
     // one coupled time step / the time loop of FSI::run (source/mpi_fsi.cpp:1172-1226), without refinement / checkpoints
     void run_one_step(bool first_step, bool stop_before_fluid_step = false);
+    // FSI::refine_mesh(min_grid_level, max_grid_level) (source/mpi_fsi.cpp:1024-1117): fluid cells whose centre is closer to the
+    // boundary of the (deformed) solid than their diameter are refined, the others coarsened, between the two levels; the fluid
+    // solution is transferred and the fluid solver set up again
+    void refine_mesh(unsigned int min_grid_level, unsigned int max_grid_level);
     void run();
     Time time;
     // FSI::set_penetration_criterion (source/mpi_fsi.cpp:1229-1237) / apply_contact_model (:869-970): while a boundary
@@ -80,6 +84,7 @@ namespace ifem
     DevBuf<double> d_sp_tables;            // dN_u at the unit support points [nu][nu][dim] | dN_geo [nu][nv][dim]
     // uniform-grid bins of the (static) fluid cells, for locating solid vertices in the fluid mesh
     void build_fluid_bins();
+    void build_fluid_side(); // everything the coupling derives from the fluid mesh / dofs (constructor, refine_mesh)
     int fbin[3] = {1, 1, 1};
     double fluid_box[6] = {0, 0, 0, 0, 0, 0};
     DevBuf<double> d_fluid_box;

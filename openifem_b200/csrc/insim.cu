@@ -1,5 +1,7 @@
 #include "insim.h"
 
+#include <unordered_map>
+
 #include "comm.h"
 
 #include <chrono>
@@ -79,6 +81,85 @@ namespace ifem
     fs.d_nonzero_val.upload(fs.nonzero_val, ctx.stream);
     fs.schur_valid = false;
     fs.flags_merged = true;
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+
+  namespace
+  {
+    // node of a Q1 table at a position (the tables are renumbered spatially: vertices are matched by their coordinates)
+    struct CoordLookup
+    {
+      int dim;
+      double lo[3], ext[3];
+      std::unordered_map<uint64_t, int> at;
+      uint64_t key(const double *x) const
+      {
+        uint64_t k = 0;
+        for (int d = dim - 1; d >= 0; --d) k = (k << 21) | (uint64_t)std::llround((x[d] - lo[d]) / ext[d] * double((1u << 21) - 2));
+        return k;
+      }
+      CoordLookup(int dim_, const std::vector<double> &box_pts, const std::vector<double> &coords) : dim(dim_)
+      {
+        for (int d = 0; d < dim; ++d)
+          {
+            double a = box_pts[d], b = box_pts[d];
+            for (size_t i = 0; i < box_pts.size() / dim; ++i)
+              {
+                a = std::min(a, box_pts[i * dim + d]);
+                b = std::max(b, box_pts[i * dim + d]);
+              }
+            lo[d] = a;
+            ext[d] = b > a ? b - a : 1.0;
+          }
+        for (size_t i = 0; i < coords.size() / dim; ++i) at.emplace(key(&coords[i * dim]), (int)i);
+      }
+      int find(const double *x) const
+      {
+        auto it = at.find(key(x));
+        if (it == at.end()) throw std::runtime_error("refine_mesh: a vertex has no node at its position");
+        return it->second;
+      }
+    };
+  } // namespace
+
+  void InsIM::after_mesh_change(const Triangulation::TransferPlan &plan, const std::vector<double> &old_vertices)
+  {
+    if (fs.n_ranks > 1) throw std::runtime_error("refine_mesh: solution transfer on several ranks is not implemented");
+    if (fs.pu != 1 || fs.pp != 1) throw std::runtime_error("refine_mesh: solution transfer is implemented for FE_Q(1) velocity and pressure");
+    const int dim = fs.dim;
+    // old solution per old vertex
+    const int64_t n_old_u = fs.n_u;
+    const std::vector<double> old = present_solution.to_host(ctx.stream);
+    const int nv_old = (int)(old_vertices.size() / dim);
+    std::vector<double> vert_val((size_t)nv_old * (dim + 1));
+    {
+      const CoordLookup un_old(dim, old_vertices, fs.un.coords), pn_old(dim, old_vertices, fs.pn.coords);
+      for (int v = 0; v < nv_old; ++v)
+        {
+          const int nu_ = un_old.find(&old_vertices[(size_t)v * dim]), np_ = pn_old.find(&old_vertices[(size_t)v * dim]);
+          for (int c = 0; c < dim; ++c) vert_val[(size_t)v * (dim + 1) + c] = old[(size_t)dim * nu_ + c];
+          vert_val[(size_t)v * (dim + 1) + dim] = old[(size_t)n_old_u + np_];
+        }
+    }
+    // new spaces
+    fs.base_valid = false;
+    setup_dofs();
+    make_constraints();
+    initialize_system();
+    const int nv_new = triangulation.n_vertices();
+    if ((int64_t)plan.ptr.size() != (int64_t)nv_new + 1) throw std::runtime_error("refine_mesh: the transfer plan does not belong to this mesh");
+    std::vector<double> fresh((size_t)fs.n_dofs, 0.0);
+    const CoordLookup un_new(dim, triangulation.vertices, fs.un.coords), pn_new(dim, triangulation.vertices, fs.pn.coords);
+    for (int v = 0; v < nv_new; ++v)
+      {
+        double val[4] = {0, 0, 0, 0};
+        for (int64_t k = plan.ptr[v]; k < plan.ptr[v + 1]; ++k)
+          for (int c = 0; c <= dim; ++c) val[c] += plan.weight[k] * vert_val[(size_t)plan.old_vertex[k] * (dim + 1) + c];
+        const int nu_ = un_new.find(&triangulation.vertices[(size_t)v * dim]), np_ = pn_new.find(&triangulation.vertices[(size_t)v * dim]);
+        for (int c = 0; c < dim; ++c) fresh[(size_t)dim * nu_ + c] = val[c];
+        fresh[(size_t)fs.n_u + np_] = val[dim];
+      }
+    present_solution.upload(fresh, ctx.stream);
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
 

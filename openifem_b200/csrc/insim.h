@@ -109,6 +109,10 @@ namespace ifem
     // push the host constraint flags / values (fs.con, fs.nonzero_val) to the device after a merge
     void upload_constraints();
     virtual void initialize_system();
+    // second half of refine_mesh (source/mpi_fluid_solver.cpp:466-487, source/mpi_fsi.cpp:1090-1110) after the triangulation was
+    // coarsened / refined: new dofs, constraints and system, present_solution interpolated onto the new mesh through the
+    // vertex transfer plan (FE_Q(1) velocity and pressure, one rank); everything else starts as initialize_system() leaves it
+    virtual void after_mesh_change(const Triangulation::TransferPlan &plan, const std::vector<double> &old_vertices);
     virtual void assemble(bool use_nonzero_constraints);
     virtual std::pair<unsigned int, double> solve(bool use_nonzero_constraints);
     // FluidSolver::update_stress (source/mpi_fluid_solver.cpp:716-811): nodal viscous stress 2 mu sym grad v from

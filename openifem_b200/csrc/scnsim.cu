@@ -494,6 +494,8 @@ namespace ifem
   {
     fs.setup(ctx, triangulation, 1, 1, true);
     dofs_ready = true;
+    ilu_vv = Ilu0(); // factors belong to the old pattern (refine_mesh calls setup_dofs again)
+    ilu_b2 = Ilu0();
   }
 
   void SCnsIM::initialize_system()

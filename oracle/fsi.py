@@ -379,6 +379,50 @@ class FSI:
                     s.fsi_stress_rows[d1, dim * node + dim - 1] += extra
         return still
 
+    def refine_mesh(self, tria, min_grid_level, max_grid_level):
+        """FSI::refine_mesh (mpi_fsi.cpp:1024-1117). `tria` is the host-side triangulation object that owns the fluid mesh (the
+        product's mesh class: flagged coarsening / refinement with 2:1 balancing is host infrastructure, like the mesh generators);
+        the flags (:1030-1080) and the solution transfer (:1082-1110, parallel::distributed::SolutionTransfer = the old FE field
+        evaluated at the new support points) are restated here. The fluid solver is rebuilt on the new mesh as setup_dofs /
+        make_constraints / initialize_system do, with present_solution interpolated."""
+        from . import grid, scns
+
+        f, s = self.fluid, self.solid
+        dim = f.dim
+        x = deformed(s.mesh.vertices, s.cur_u, dim)
+        first_face = {}
+        for (cell, face, _fid) in s.mesh.boundary_faces:
+            first_face[int(cell)] = min(first_face.get(int(cell), 99), int(face))
+        pts = np.array([x[s.mesh.cells[c, fem.face_local_nodes(dim, 1, face)]].mean(axis=0) for c, face in sorted(first_face.items())])
+        X = f.mesh.vertices[f.mesh.cells]  # [nc][2^d][dim]
+        centre = X.mean(axis=1)
+        diam = np.sqrt(((X[:, :, None, :] - X[:, None, :, :]) ** 2).sum(-1)).max(axis=(1, 2))
+        dist = np.sqrt(((centre[:, None, :] - pts[None, :, :]) ** 2).sum(-1)).min(axis=1)
+        refine = dist < diam
+        coarsen = ~refine
+        level = tria.levels()
+        if level.max() + 1 > max_grid_level:
+            refine &= level < max_grid_level
+        coarsen &= level != min_grid_level
+        old_mesh, old = f.mesh, f.present.copy()
+        old_d = f.dofs
+        tria.execute_coarsening_and_refinement(refine, coarsen)
+        v, c, b = tria.get_mesh()
+        new = type(f)((grid.QuadMesh if dim == 2 else grid.HexMesh)(v, c, b), f.prm, hard_coded=f.hard_coded)
+        # solution transfer: the old Q1 field at the new support points
+        feu, fep = f.feu, f.fep
+        for coords, nodes_old, n_comp, off_old, off_new in ((new.dofs.ucoords, old_d.unodes, dim, 0, 0), (new.dofs.pcoords, old_d.pnodes, 1, f.n_u, new.n_u)):
+            fe = feu if n_comp == dim else fep
+            for n, p in enumerate(coords):
+                cell, xi = locate_in_fluid(old_mesh, p)
+                N = fe.eval(xi[None, :])[0][0]
+                for comp in range(n_comp):
+                    new.present[off_new + n_comp * n + comp] = N @ old[off_old + n_comp * nodes_old[cell] + comp]
+        new.time, new.timestep, new.history, new.bc_time = f.time, f.timestep, f.history, f.bc_time
+        self.fluid = new
+        self.base_con, self.base_val = new.con.copy(), new.nonzero_val.copy()
+        return new
+
     def run(self):
         """the time loop of FSI::run (mpi_fsi.cpp:1172-1226) without refinement / checkpoints"""
         p = self.fluid.prm

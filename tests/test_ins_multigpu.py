@@ -271,7 +271,8 @@ def _run_scns(size, dim, reps, steps, tmp_path, mode="plain"):
     hist = [r for r in res if r[0] == 0][0][6]
     if mode.startswith("fsi"):
         for r in res[1:]:  # the solid is replicated: every rank holds the same displacement
-            assert np.array_equal(r[7], res[0][7])
+            # (not bitwise on hardware: the solid kernels add with atomics, the CG solves stop at 1e-8 |b|)
+            assert np.abs(r[7] - res[0][7]).max() <= 1e-6 * np.abs(res[0][7]).max()
         return sol, stress, hist, res[0][7]
     return sol, stress, hist
 

@@ -670,7 +670,7 @@ namespace ifem
     // ---------------------------------------------------------------------------
     struct CgState
     {
-      double rr, alpha, beta, tol2;
+      double rr, alpha, beta, tol2, gamma;
       int its, max_it, done, converged;
     };
     enum CgStage { kCInit, kCDot, kCXR, kCGear };
@@ -784,6 +784,115 @@ namespace ifem
       if (finish_reduce<2>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) cg_gear_advance(st, acc);
     }
 
+    // ---- two-level preconditioned single-reduction CG ----
+    // u = M^-1 r, w = A u; gamma = r . u, delta = u . w, rho = r . r in ONE reduction; beta = gamma / gamma_old,
+    // alpha = gamma / (delta - beta gamma / alpha_old); p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s
+    __device__ __forceinline__ void pcg_advance(CgState *st, const double *red)
+    {
+      if (st->done) return;
+      const double gamma = red[0], delta = red[1], rho = red[2];
+      if (!(rho > st->tol2) || !isfinite(rho))
+        {
+          st->rr = rho;
+          st->done = 1;
+          st->converged = rho <= st->tol2 ? 1 : 0;
+          return;
+        }
+      if (st->its >= st->max_it)
+        {
+          st->rr = rho;
+          st->done = 1;
+          return;
+        }
+      const double beta = st->its == 0 ? 0.0 : gamma / st->gamma;
+      const double denom = st->its == 0 ? delta : delta - beta * gamma / st->alpha;
+      if (!(denom > 0.0) || !(gamma > 0.0) || !isfinite(denom))
+        {
+          st->rr = rho;
+          st->done = 1; // breakdown: the caller falls back
+          return;
+        }
+      st->beta = beta;
+      st->alpha = gamma / denom;
+      st->gamma = gamma;
+      st->rr = rho;
+      st->its += 1;
+    }
+    __global__ void pcg_advance_kernel(CgState *st, const double *red) { pcg_advance(st, red); }
+
+    // c[a] = sum of r over the rows of aggregate a, in a fixed order (one CTA per aggregate)
+    __global__ void __launch_bounds__(kT)
+    pcg_restrict_kernel(const CgState *__restrict__ st, const int *__restrict__ agg_ptr, const int *__restrict__ agg_rows, const float *__restrict__ r,
+                        double *__restrict__ c)
+    {
+      if (st->done) return;
+      const int a = blockIdx.x;
+      double acc[1] = {0.0};
+      for (int k = agg_ptr[a] + threadIdx.x; k < agg_ptr[a + 1]; k += blockDim.x) acc[0] += (double)r[agg_rows[k]];
+      cta_sum<1>(acc);
+      if (threadIdx.x == 0) c[a] = acc[0];
+    }
+
+    // y = E^+ c: one warp per row
+    __global__ void __launch_bounds__(kT)
+    pcg_coarse_kernel(const CgState *__restrict__ st, int n_c, const double *__restrict__ Einv, const double *__restrict__ c, double *__restrict__ y)
+    {
+      if (st->done) return;
+      const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+      if (row >= n_c) return;
+      double s = 0.0;
+      for (int j = lane; j < n_c; j += 32) s += Einv[(size_t)row * n_c + j] * c[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) y[row] = s;
+    }
+
+    // u = diag^-1 r + Z y (into the gather source of the product)
+    __global__ void __launch_bounds__(kT)
+    pcg_build_u_kernel(int n_pad, const CgState *__restrict__ st, const float *__restrict__ r, const float *__restrict__ dinv,
+                       const int *__restrict__ agg, const double *__restrict__ y, float *__restrict__ u)
+    {
+      if (st->done) return;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const int a = agg[i];
+          u[i] = a >= 0 ? fmaf(dinv[i], r[i], (float)y[a]) : 0.0f;
+        }
+    }
+
+    __global__ void __launch_bounds__(kT)
+    pcg_dot_kernel(int n_pad, const float *__restrict__ r, const float *__restrict__ u, const float *__restrict__ w, CgState *st,
+                   double *__restrict__ partials, unsigned int *__restrict__ counter, double *__restrict__ red, PeerDev pd, int adv)
+    {
+      if (st->done) return;
+      double acc[3] = {0.0, 0.0, 0.0};
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const double ri = (double)r[i], ui = (double)u[i];
+          acc[0] += ri * ui;
+          acc[1] += ui * (double)w[i];
+          acc[2] += ri * ri;
+        }
+      if (finish_reduce<3>(acc, partials, counter, red, pd) && adv && threadIdx.x == 0) pcg_advance(st, acc);
+    }
+
+    // p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s
+    __global__ void __launch_bounds__(kT)
+    pcg_update_kernel(int n_pad, const CgState *__restrict__ st, float *__restrict__ r, const float *__restrict__ u, const float *__restrict__ w,
+                      float *__restrict__ p, float *__restrict__ s, float *__restrict__ x)
+    {
+      if (st->done) return;
+      const float alpha = (float)st->alpha, beta = (float)st->beta;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        {
+          const float pi = fmaf(beta, p[i], u[i]), si = fmaf(beta, s[i], w[i]);
+          p[i] = pi;
+          s[i] = si;
+          x[i] = fmaf(alpha, pi, x[i]);
+          r[i] = fmaf(-alpha, si, r[i]);
+        }
+    }
+
     // p = r + beta p; s = w + beta s; x += alpha p; r -= alpha s
     __global__ void __launch_bounds__(kT)
     cg_gear_update_kernel(int n_pad, const CgState *__restrict__ st, float *__restrict__ r, const float *__restrict__ w, float *__restrict__ p,
@@ -804,7 +913,7 @@ namespace ifem
     __global__ void cg_begin_kernel(CgState *st, double tol2, int max_it)
     {
       st->rr = 0.0;
-      st->alpha = st->beta = 0.0;
+      st->alpha = st->beta = st->gamma = 0.0;
       st->tol2 = tol2;
       st->its = 0;
       st->max_it = max_it;
@@ -1420,8 +1529,11 @@ namespace ifem
     p = S.gather_source(ctx, 0);
     rg = S.gather_source(ctx, 1);
     if (const char *e = std::getenv("IFEM_CG_SM_GEAR")) single_reduction = std::atoi(e) != 0;
+    if (const char *e = std::getenv("IFEM_CG_SM_COARSE")) coarse_space = std::atoi(e) != 0;
+    dim = nodes.dim;
+    n_coarse = 0;
     grid = std::max(1, std::min((S.n_pad + kT - 1) / kT, ctx.sm_count * 4));
-    partials.alloc((size_t)grid * 2);
+    partials.alloc((size_t)grid * 3);
     red.alloc(kPeerMaxVals);
     red.zero(ctx.stream);
     counter.alloc(1);
@@ -1460,6 +1572,49 @@ namespace ifem
     const double tol_rel = tol_abs / src_norm;
     cg_begin_kernel<<<1, 1, 0, ctx.stream>>>(st, tol_rel * tol_rel, max_it);
     launched();
+    if (coarse_space && n_coarse > 0)
+      {
+        // r in `r`, u = M^-1 r in the gather source `rg` (what the product reads), w = A u in `ap`
+        cg_gear_init_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, src, 1.0 / src_norm, r.p, pg.p, sg.p, x.p);
+        launched();
+        const bool many = ctx.comm && ctx.comm->size > 1;
+        int enqueued = 0;
+        while (true)
+          {
+            const int chunk = std::max(1, std::min(check_every, max_it + 1 - enqueued));
+            for (int k = 0; k < chunk; ++k)
+              {
+                pcg_restrict_kernel<<<n_coarse, kT, 0, ctx.stream>>>(st, agg_ptr.p, agg_rows.p, r.p, cvec.p);
+                launched();
+                if (many) comm_allreduce_sum(*ctx.comm, cvec.p, n_coarse, ctx.stream);
+                pcg_coarse_kernel<<<(n_coarse * 32 + kT - 1) / kT, kT, 0, ctx.stream>>>(st, n_coarse, Einv.p, cvec.p, yvec.p);
+                pcg_build_u_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, r.p, dinv.p, agg.p, yvec.p, rg);
+                launched(2);
+                S.halo(ctx, rg, &st->done);
+                S.apply(ctx, rg, ap.p, &st->done);
+                pcg_dot_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, r.p, rg, ap.p, st, partials.p, counter.p, red.p, m.pd, m.adv);
+                launched();
+                if (m.nccl)
+                  {
+                    comm_allreduce_sum(*ctx.comm, red.p, 3, ctx.stream);
+                    pcg_advance_kernel<<<1, 1, 0, ctx.stream>>>(st, red.p);
+                    launched();
+                  }
+                pcg_update_kernel<<<grid, kT, 0, ctx.stream>>>(n_pad, st, r.p, rg, ap.p, pg.p, sg.p, x.p);
+                launched();
+              }
+            enqueued += chunk;
+            IFEM_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CgState), cudaMemcpyDeviceToHost, ctx.stream));
+            IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+            if (h->done || enqueued > max_it) break;
+          }
+        out.iterations = h->its;
+        out.residual = std::sqrt(std::max(0.0, h->rr)) * src_norm;
+        out.converged = h->done && h->converged;
+        final_kernel<1><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x.p, src_norm, dst);
+        launched();
+        return out;
+      }
     if (single_reduction)
       {
         // w lives in `ap`, r in the gather source `rg` (it is what the product reads)
@@ -1530,5 +1685,132 @@ namespace ifem
     final_kernel<1><<<grid, kT, 0, ctx.stream>>>(n_pad, S.perm_row.p, x.p, src_norm, dst);
     launched();
     return out;
+  }
+  void InnerCG32::build_coarse(Context &ctx, const Bcsr &A, const NodeTable &nodes)
+  {
+    n_coarse = 0;
+    if (!coarse_space) return;
+    const int G = dim == 3 ? 9 : 27, n_c = dim == 3 ? G * G * G : G * G;
+    const int n = S.n_rows, n_cols = S.n_cols, n_pad = S.n_pad;
+    // aggregate of every local node (owned and ghost) from its position in the global box
+    std::vector<int> agg_node((size_t)n_cols);
+    for (int i = 0; i < n_cols; ++i)
+      {
+        int a = 0, stride = 1;
+        for (int d = 0; d < dim; ++d)
+          {
+            const double ext = box[2 * d + 1] - box[2 * d];
+            int k = ext > 0 ? (int)std::floor((nodes.coords[(size_t)i * dim + d] - box[2 * d]) / ext * G) : 0;
+            k = std::min(std::max(k, 0), G - 1);
+            a += k * stride;
+            stride *= G;
+          }
+        agg_node[i] = a;
+      }
+    // E = Z^T A Z over the owned rows, summed over the ranks
+    std::vector<int64_t> rp;
+    std::vector<int> ci;
+    std::vector<double> v;
+    A.to_host_csr(ctx.stream, rp, ci, v);
+    std::vector<double> E((size_t)n_c * n_c, 0.0), diag((size_t)n, 1.0), count((size_t)n_c, 0.0);
+    for (int i = 0; i < n; ++i)
+      {
+        double *Er = &E[(size_t)agg_node[i] * n_c];
+        count[agg_node[i]] += 1.0;
+        for (int64_t k = rp[i]; k < rp[i + 1]; ++k)
+          {
+            Er[agg_node[ci[k]]] += v[k];
+            if (ci[k] == i) diag[i] = v[k];
+          }
+      }
+    const bool many = ctx.comm && ctx.comm->size > 1;
+    if (many)
+      {
+        DevBuf<double> dE(E.size() + count.size());
+        dE.upload(E.data(), E.size(), ctx.stream);
+        IFEM_CUDA(cudaMemcpyAsync(dE.p + E.size(), count.data(), count.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+        comm_allreduce_sum(*ctx.comm, dE.p, (int)(E.size() + count.size()), ctx.stream);
+        std::vector<double> back = dE.to_host(ctx.stream);
+        std::copy(back.begin(), back.begin() + E.size(), E.begin());
+        std::copy(back.begin() + E.size(), back.end(), count.begin());
+      }
+    // empty aggregates decouple; the constant null space of a singular S_m is shifted away
+    double mean_diag = 0.0;
+    int n_used = 0;
+    for (int a = 0; a < n_c; ++a)
+      if (count[a] > 0)
+        {
+          mean_diag += E[(size_t)a * n_c + a];
+          ++n_used;
+        }
+    if (!n_used || !(mean_diag > 0.0)) return;
+    mean_diag /= n_used;
+    for (int a = 0; a < n_c; ++a)
+      for (int b = 0; b < n_c; ++b)
+        {
+          double &e = E[(size_t)a * n_c + b];
+          if (count[a] > 0 && count[b] > 0) e += mean_diag / n_used;
+          else e = a == b ? 1.0 : 0.0;
+        }
+    // inverse by Gauss-Jordan with partial pivoting (n_c <= 729, once per matrix)
+    std::vector<double> inv((size_t)n_c * n_c, 0.0);
+    for (int a = 0; a < n_c; ++a) inv[(size_t)a * n_c + a] = 1.0;
+    for (int c = 0; c < n_c; ++c)
+      {
+        int piv = c;
+        for (int r2 = c + 1; r2 < n_c; ++r2)
+          if (std::fabs(E[(size_t)r2 * n_c + c]) > std::fabs(E[(size_t)piv * n_c + c])) piv = r2;
+        if (!(std::fabs(E[(size_t)piv * n_c + c]) > 1e-300)) return; // singular beyond the shift: no coarse space
+        if (piv != c)
+          for (int k = 0; k < n_c; ++k)
+            {
+              std::swap(E[(size_t)c * n_c + k], E[(size_t)piv * n_c + k]);
+              std::swap(inv[(size_t)c * n_c + k], inv[(size_t)piv * n_c + k]);
+            }
+        const double d = 1.0 / E[(size_t)c * n_c + c];
+        for (int k = 0; k < n_c; ++k)
+          {
+            E[(size_t)c * n_c + k] *= d;
+            inv[(size_t)c * n_c + k] *= d;
+          }
+#pragma omp parallel for schedule(static)
+        for (int r2 = 0; r2 < n_c; ++r2)
+          {
+            if (r2 == c) continue;
+            const double f = E[(size_t)r2 * n_c + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < n_c; ++k)
+              {
+                E[(size_t)r2 * n_c + k] -= f * E[(size_t)c * n_c + k];
+                inv[(size_t)r2 * n_c + k] -= f * inv[(size_t)c * n_c + k];
+              }
+          }
+      }
+    // SELL-ordered tables
+    const std::vector<int> perm = S.perm_row.to_host(ctx.stream);
+    std::vector<int> agg_h((size_t)n_pad, -1), ptr((size_t)n_c + 1, 0), rows;
+    std::vector<float> dinv_h((size_t)n_pad, 0.0f);
+    for (int i = 0; i < n_pad; ++i)
+      if (perm[i] >= 0)
+        {
+          agg_h[i] = agg_node[perm[i]];
+          dinv_h[i] = (float)(1.0 / diag[perm[i]]);
+          ptr[agg_h[i] + 1]++;
+        }
+    for (int a = 0; a < n_c; ++a) ptr[a + 1] += ptr[a];
+    rows.resize(ptr[n_c]);
+    std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < n_pad; ++i)
+      if (agg_h[i] >= 0) rows[cur[agg_h[i]]++] = i;
+    agg.upload(agg_h, ctx.stream);
+    agg_ptr.upload(ptr, ctx.stream);
+    if (rows.empty()) rows.push_back(0);
+    agg_rows.upload(rows, ctx.stream);
+    dinv.upload(dinv_h, ctx.stream);
+    Einv.upload(inv, ctx.stream);
+    cvec.alloc((size_t)n_c);
+    yvec.alloc((size_t)n_c);
+    IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
+    n_coarse = n_c;
   }
 } // namespace ifem

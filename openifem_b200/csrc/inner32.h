@@ -152,8 +152,24 @@ namespace ifem
     // single-reduction recurrence (Chronopoulos-Gear): one fused all-reduce of two values and four launches per iteration instead
     // of two all-reduces and six launches (inner32.cu cg_gear_*); IFEM_CG_SM_GEAR=0 selects the classical recurrence
     bool single_reduction = true;
+    // Two-level preconditioner for "CG for Sm" (the reference runs it unpreconditioned, mpi_insim.cpp:88-109: 4 200 iterations per
+    // time step at config 3): M^-1 = diag(A)^-1 + Z E^+ Z^T with Z = piecewise constants over G^dim boxes of the domain (<= 729
+    // aggregates) and E = Z^T A Z formed on the host whenever the matrix changes, inverted there once (rank-one shifted: S_m is
+    // singular in closed cavities). Per iteration: a segmented sum per aggregate (fixed order: deterministic), one all-reduce of
+    // the coarse vector over the ranks, a dense mat-vec with E^+ and a fused build of u = M^-1 r. Inside the preconditioner of
+    // FGMRES only the accuracy of the result matters (tolerance 1e-3 |src| as in the reference). IFEM_CG_SM_COARSE=0 switches it off.
+    bool coarse_space = true;
+    int n_coarse = 0;
+    // global bounding box of the nodes (every rank the same): set before refresh() so that the aggregates agree across ranks
+    double box[6] = {0, 1, 0, 1, 0, 1};
+    int dim = 3;
+    void build_coarse(Context &ctx, const Bcsr &A, const NodeTable &nodes);
 
   private:
+    DevBuf<int> agg;              // [n_pad] aggregate of a SELL row (-1: padding row)
+    DevBuf<int> agg_ptr, agg_rows; // rows of every aggregate (segmented restriction in a fixed order)
+    DevBuf<double> Einv, cvec, yvec;
+    DevBuf<float> dinv;           // [n_pad] 1 / diag(A)
     DevBuf<float> r, ap, x; // [n_pad]
     DevBuf<float> pg, sg;   // [n_pad] search direction and its product (single-reduction variant)
     float *p = nullptr;     // [x_len] gather source (S.gather_source)

@@ -291,6 +291,19 @@ namespace ifem
     if (!sm_copy_valid)
       {
         inner_sm.refresh(ctx, fs.S_m);
+        // aggregates of the coarse space from the bounding box of the whole mesh (every rank holds the triangulation)
+        for (int d = 0; d < fs.dim; ++d)
+          {
+            double lo = triangulation.vertices[d], hi = lo;
+            for (int i = 0; i < triangulation.n_vertices(); ++i)
+              {
+                lo = std::min(lo, triangulation.vertices[(size_t)i * fs.dim + d]);
+                hi = std::max(hi, triangulation.vertices[(size_t)i * fs.dim + d]);
+              }
+            inner_sm.box[2 * d] = lo;
+            inner_sm.box[2 * d + 1] = hi;
+          }
+        inner_sm.build_coarse(ctx, fs.S_m, fs.pn);
         sm_copy_valid = true;
       }
     // fp32 CG occasionally stagnates on the (singular, in closed cavities) S_m where fp64 CG converges - observed once in

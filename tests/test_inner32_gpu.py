@@ -52,7 +52,7 @@ def test_fp32_cg_for_mass_schur(dim, reps):
     for mode, tol in [(1, 5e-5), (2, 1e-2)]:
         x, it, res = g.solve_mass_schur(b, mode=mode, rel_tol=1e-5)
         assert np.linalg.norm(S @ x - b) / nb < tol, (mode, it, res)
-        assert 0.5 * it0 <= it <= 2 * it0 + 10, (mode, it, it0)
+        assert it <= 2 * it0 + 10, (mode, it, it0)  # the two-level preconditioner of the fp32 path needs FEWER iterations than plain CG
         assert res <= 1.01e-5 * nb
 
 

@@ -89,3 +89,39 @@ def test_ilu_factors_cut_the_inner_iterations_of_a_viscous_supg_case():
     (outer_j, inner_j), (outer_i, inner_i) = counts[0], counts[1]
     print(f"Jacobi factors: {outer_j} FGMRES / {inner_j} inner T_pp iterations; ILU(0): {outer_i} / {inner_i}")
     assert outer_i <= outer_j and inner_i * 3 <= inner_j
+
+
+def test_iteration_counts_against_the_references_preconditioner():
+    """the device's BlockIncompSchurPreconditioner with ILU(0) factors against the oracle's restatement of the reference's
+    (oracle/supg_precond.py: ILU(0) for P_vv and B2pp, left-preconditioned GMRES(200) from the line-search guess) on the same Newton
+    systems of a viscous case: FGMRES and inner T_pp iteration counts within a factor 2 of each other (the device restarts the inner
+    solve after 50 vectors, preconditions it from the right and starts from zero)"""
+    import openifem_b200 as ifem
+    from oracle import fem, prm, scns, supg_precond
+    from test_scns_gpu import scns_prm
+
+    text = scns_prm(2, dt=5e-2, mu=0.5, rho=1.0, newton_tol=1e-8)
+    reps, hi = (40, 12), (4.0, 1.2)
+    o = scns.SCnsIM(fem.BoxMesh(reps, (0, 0), hi), prm.Params(text, is_text=True))
+    tria = ifem.Triangulation(2)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, reps, (0, 0), hi, True)
+    g = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=text))
+    g.setup()
+    g.set_control(supg_ilu=1)  # default tolerance: 1e-6 |rhs| as in the reference
+    g.run_one_step(True)
+    dev = [(r["gmres_its"], r["a_inv_its"]) for r in g.history()]
+    # the oracle walks the same Newton iteration with the reference's preconditioner
+    o.timestep, o.time = 1, o.dt
+    o.evaluation_point = o.present.copy()
+    ref = []
+    for it in range(len(dev)):
+        o.assemble(it == 0)
+        x, outer, inner = supg_precond.solve(o, it == 0)
+        o.evaluation_point = o.evaluation_point + x
+        ref.append((outer, inner))
+    print("device (FGMRES, inner):", dev, " reference algorithm:", ref)
+    for (do, di), (ro, ri) in zip(dev, ref):
+        assert do <= 2 * ro + 2 and ro <= 2 * do + 2, (dev, ref)
+        assert di <= 2 * ri + 10 and ri <= 2 * di + 10, (dev, ref)
+    sol = g.get_current_solution()
+    assert np.linalg.norm(sol - o.evaluation_point) / np.linalg.norm(sol) < 1e-4  # both solved to 1e-6 |rhs| per Newton step

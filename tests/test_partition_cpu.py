@@ -134,3 +134,38 @@ def test_halo_exchange_world2_gloo(dim, reps):
         p.join(timeout=60)
     for rank, ok, msg in res:
         assert ok, f"rank {rank}: {msg}"
+
+
+@pytest.mark.parametrize("dim,reps,axis,size", [(3, (3, 3, 12), 2, 2), (3, (3, 3, 12), 2, 4), (2, (12, 4), 0, 3), (2, (4, 12), 1, 2)])
+def test_slabs_of_a_band_refined_mesh_keep_hanging_nodes_with_their_masters(dim, reps, axis, size):
+    """locally refined meshes (csrc/partition.cpp plane_slabs): every rank's owned nodes tile the mesh, and a hanging node has
+    the owner of all its masters - the condition under which the condensation of the hanging rows is local to a rank
+    (csrc/hanging.cu); the slab axis is found automatically (last axis with enough admissible planes)"""
+    import openifem_b200 as ifem
+
+    t = _tria(dim, reps)
+    v, c, _ = t.get_mesh()
+    x = v[c].mean(axis=1)[:, axis]
+    t.execute_refinement(((x > 0.34) & (x < 0.67)).astype(np.uint8))
+    v, c, _ = t.get_mesh()
+    hv, hk, hm = t.hanging()
+    assert hv.size > 0
+    parts = [ifem.Partition(t, 1, 1, r, size) for r in range(size)]
+    owner = np.full(v.shape[0], -1)
+    for r, p in enumerate(parts):
+        n_owned = p.counts(0)["n_owned"]
+        l2g = p.local_to_global(0)
+        assert n_owned > 0
+        assert np.all(owner[l2g[:n_owned]] == -1)
+        owner[l2g[:n_owned]] = r
+    assert np.all(owner >= 0)
+    # the FE_Q(1) node of a vertex: nodes are numbered in lexicographic (z, y, x) order of their quantised position (csrc/mesh.cpp
+    # spatial_renumber)
+    lo, hi = v.min(axis=0), v.max(axis=0)
+    q = np.rint((v - lo) / np.where(hi > lo, hi - lo, 1.0) * float((1 << 21) - 1)).astype(np.int64)
+    order = np.lexsort(tuple(q[:, d] for d in range(dim)))
+    vert_node = np.empty(v.shape[0], dtype=int)
+    vert_node[order] = np.arange(v.shape[0])
+    for h, k, m in zip(hv, hk, hm):
+        owners = {owner[vert_node[h]]} | {owner[vert_node[j]] for j in m[:k]}
+        assert len(owners) == 1, (h, m[:k], owners)

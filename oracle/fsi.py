@@ -124,6 +124,10 @@ class SolidGeometry:
         self.cells = mesh.cells
         self.x = deformed(mesh.vertices, displacement, mesh.dim)
         self.box = solid_box(self.x)
+        # bounding boxes of the cells: the same reject point_in_cell applies first, for all cells at once (speed only - the cells
+        # that pass are visited in index order exactly as before)
+        X = self.x[self.cells]
+        self.cell_lo, self.cell_hi = X.min(axis=1) - 1e-12, X.max(axis=1) + 1e-12
         self.segments = []
         if self.dim == 2:
             # face f = 2*axis+side of a quad: its two vertices in lexicographic local numbering
@@ -140,17 +144,20 @@ class SolidGeometry:
             return False
         if self.dim == 2:
             return point_in_solid_2d(p, self.box, self.segments)
-        for c in range(self.cells.shape[0]):
+        for c in self._candidates(p):
             if point_in_cell(self.x[self.cells[c]], p)[0]:
                 return True
         return False
 
+    def _candidates(self, p):
+        return np.nonzero(np.all((p >= self.cell_lo) & (p <= self.cell_hi), axis=1))[0]
+
     def locate(self, p):
         """lowest-index solid cell containing p (within TOL) and the unit coordinates, or (None, None)"""
-        for c in range(self.cells.shape[0]):
+        for c in self._candidates(p):
             ok, xi = point_in_cell(self.x[self.cells[c]], p)
             if ok:
-                return c, np.clip(xi, 0.0, 1.0)  # GeometryInfo::project_to_unit_cell
+                return int(c), np.clip(xi, 0.0, 1.0)  # GeometryInfo::project_to_unit_cell
         return None, None
 
     def interpolate(self, field, p):
@@ -274,10 +281,14 @@ def find_fluid_bc(fluid, solid: SolidGeometry, indicator, solid_velocity, solid_
 # ----------------------------------------------------------------------------------------------------------
 def locate_in_fluid(fluid_mesh: fem.BoxMesh, p):
     """lowest-index fluid cell containing p (GridInterpolator on the fluid DoFHandler) and unit coordinates"""
-    for c in range(fluid_mesh.n_cells):
+    boxes = getattr(fluid_mesh, "_cell_boxes", None)
+    if boxes is None:  # cached on the mesh object (speed only: the same reject point_in_cell applies first)
+        X = fluid_mesh.vertices[fluid_mesh.cells]
+        boxes = fluid_mesh._cell_boxes = (X.min(axis=1) - 1e-12, X.max(axis=1) + 1e-12)
+    for c in np.nonzero(np.all((p >= boxes[0]) & (p <= boxes[1]), axis=1))[0]:
         ok, xi = point_in_cell(fluid_mesh.vertices[fluid_mesh.cells[c]], p)
         if ok:
-            return c, np.clip(xi, 0.0, 1.0)
+            return int(c), np.clip(xi, 0.0, 1.0)
     return None, None
 
 

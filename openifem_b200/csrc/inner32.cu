@@ -1690,8 +1690,18 @@ namespace ifem
   {
     n_coarse = 0;
     if (!coarse_space) return;
-    const int G = dim == 3 ? 9 : 27, n_c = dim == 3 ? G * G * G : G * G;
     const int n = S.n_rows, n_cols = S.n_cols, n_pad = S.n_pad;
+    // boxes per direction: at most 729 aggregates (9^3 / 27^2), at least ~8 rows per aggregate on small problems; every rank must
+    // come to the same G
+    int64_t n_global = n;
+    if (ctx.comm && ctx.comm->size > 1)
+      {
+        n_global = 0;
+        for (int64_t k : comm_allgather_i64(ctx, std::vector<int64_t>{(int64_t)n})) n_global += k;
+      }
+    const int g_max = dim == 3 ? 9 : 27;
+    const int G = std::max(2, std::min(g_max, (int)std::floor(std::pow((double)n_global / 8.0, 1.0 / dim))));
+    const int n_c = dim == 3 ? G * G * G : G * G;
     // aggregate of every local node (owned and ghost) from its position in the global box
     std::vector<int> agg_node((size_t)n_cols);
     for (int i = 0; i < n_cols; ++i)

@@ -53,6 +53,7 @@ namespace ifem
 
   void SUPGInsIM::assemble(bool use_nonzero_constraints)
   {
+    if (fs.pu != 1 || fs.pp != 1) throw std::runtime_error("SUPGInsIM: equal-order Q1/Q1 elements only (what the reference's cases use)");
     SectionTimer t(ctx, timer_ms["Assemble system"]);
     if (fs.n_ranks > 1)
       {

@@ -485,14 +485,15 @@ namespace ifem
   // ===========================================================================
   SCnsIM::SCnsIM(Context &ctx_, Triangulation &tria, const Parameters::AllParameters &params) : InsIM(ctx_, tria, params, false)
   {
-    if (parameters.fluid_velocity_degree != 1 || parameters.fluid_pressure_degree != 1)
-      throw std::runtime_error("SCnsIM: only equal-order Q1/Q1 elements are implemented on the device");
+    const unsigned pu = parameters.fluid_velocity_degree, pp = parameters.fluid_pressure_degree;
+    if (pu < 1 || pu > 2 || !(pp == 1 || pp == pu))
+      throw std::runtime_error("SCnsIM: velocity degree 1 or 2 with pressure degree 1 or equal to it");
     control.fgmres_rel = 1e-6; // SUPGFluidSolver::solve: SolverControl(m, 1e-6 * |rhs|) (mpi_supg_solver.cpp:311-312)
   }
 
   void SCnsIM::setup_dofs()
   {
-    fs.setup(ctx, triangulation, 1, 1, true);
+    fs.setup(ctx, triangulation, (int)parameters.fluid_velocity_degree, (int)parameters.fluid_pressure_degree, true);
     dofs_ready = true;
     ilu_vv = Ilu0(); // factors belong to the old pattern (refine_mesh calls setup_dofs again)
     ilu_b2 = Ilu0();
@@ -558,6 +559,26 @@ namespace ifem
     fs.A_pu.zero(s);
     fs.A_pp.zero(s);
     fs.rhs.zero(s);
+    if (fs.pu != 1 || fs.pp != 1)
+      {
+        ScnsGenericInput in{};
+        in.eval_pt = evaluation_point.p;
+        in.present = present_solution.p;
+        in.fsi_acc = fsi_acceleration.p;
+        in.stress = stress.p;
+        in.fsi_stress = fsi_stress.p;
+        in.sigma_pml = d_sigma_pml.n ? d_sigma_pml.p : nullptr;
+        in.body_force = d_body_force.n ? d_body_force.p : nullptr;
+        in.mu = parameters.viscosity;
+        in.rho_f = parameters.fluid_rho;
+        in.rho_s = parameters.solid_rho;
+        in.dt = time.get_delta_t();
+        for (int d = 0; d < 3; ++d) in.grav[d] = d < (int)parameters.gravity.size() ? parameters.gravity[d] : 0.0;
+        scns_assemble_generic(ctx, fs, in, use_nonzero_constraints);
+        neumann_faces(ctx, fs);
+        fs.hanging.condense(ctx, fs, use_nonzero_constraints ? fs.d_nonzero_val.p : nullptr);
+        return;
+      }
     ScnsArgs a{};
     a.cell_un = fs.d_cell_un.p;
     a.cell_pn = fs.d_cell_pn.p;

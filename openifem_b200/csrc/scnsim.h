@@ -2,7 +2,7 @@
 // of Fluid::MPI::SUPGFluidSolver (include/mpi_supg_solver.h, source/mpi_supg_solver.cpp): slightly
 // compressible Navier-Stokes, SUPG / PSPG / LSIC stabilisation, PML attenuation, artificial-fluid terms for
 // the immersed solid. Equal-order Q1/Q1 elements (what every reference SCnsIM test and BASELINE configs 4, 5
-// use). Shares the FluidSpace / Newton / FGMRES machinery of InsIM; differs in the cell integrand, in
+// use) have their own kernel; other pairs (Q2/Q1, Q2/Q2) go through the degree-generic kernel of scnsim_generic.cu. Shares the FluidSpace / Newton / FGMRES machinery of InsIM; differs in the cell integrand, in
 // update_stress() after every step and in the block preconditioner (BlockIncompSchurPreconditioner).
 #pragma once
 #include "ilu0.h"
@@ -10,6 +10,14 @@
 
 namespace ifem
 {
+  // SCnsIM::assemble for element pairs other than Q1/Q1 (scnsim_generic.cu): fills A_uu / A_up / A_pu / A_pp and rhs of the space
+  struct ScnsGenericInput
+  {
+    const double *eval_pt, *present, *fsi_acc, *stress, *fsi_stress, *sigma_pml, *body_force;
+    double mu, rho_f, rho_s, dt, grav[3];
+  };
+  void scns_assemble_generic(Context &ctx, FluidSpace &fs, const ScnsGenericInput &in, bool use_nonzero_constraints);
+
   class SCnsIM : public InsIM
   {
   public:

@@ -98,3 +98,65 @@ def test_time_steps_on_refined_mesh_match_oracle(dim):
     assert len(ho) == len(hg)
     for a, b in zip(ho, hg):
         assert abs(a[2] - b["abs_res"]) <= 1e-6 * max(a[2], 1e-12) + 1e-13
+
+
+def test_hanging_node_properties_at_scale():
+    """size-independent properties on a config-5-shaped mesh far beyond what the oracle handles in seconds (fsi-wall-3D box at three
+    times the reference's resolution: 183 600 cells, 0.8 M dofs, 3 960 hanging nodes): a uniform state leaves a zero residual, the
+    rows and columns of hanging dofs are diagonal after the condensation, and a time step returns a field that satisfies every
+    hanging-node line"""
+    import openifem_b200 as ifem
+
+    scale = 3
+    tria = ifem.Triangulation(3)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, (10 * scale, 10 * scale, 40 * scale), (0, 0, 0), (1, 1, 4), True)
+    v, c, _ = tria.get_mesh()
+    cz = v[c].mean(axis=1)[:, 2]
+    tria.execute_refinement(((cz >= 2) & (cz <= 2.4)).astype(np.uint8))
+    v, c, _ = tria.get_mesh()
+    hv, hk, hm = tria.hanging()
+    assert tria.n_active_cells() == 6800 * scale ** 3 and hv.size > 3000
+    full = 7
+    text = scns_prm(3, dirichlet={i: (full, [0.0] * 3) for i in range(6)}, mu=0.7, rho=1.1, dt=1e-3)
+    g = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=text))
+    g.setup()
+    n_nodes = v.shape[0]
+    assert g.n_dofs == 4 * n_nodes
+    x = np.zeros(g.n_dofs)
+    x[: 3 * n_nodes] = np.tile([0.3, -0.2, 0.45], n_nodes)
+    x[3 * n_nodes:] = 2.5
+    g.set_vector(g.EVALUATION_POINT, x)
+    g.set_vector(g.PRESENT, x)
+    g.assemble(False)
+    assert np.abs(g.get_vector(g.SYSTEM_RHS)).max() < 1e-11
+    # node of a vertex: lexicographic (z, y, x) order of the quantised positions (csrc/mesh.cpp spatial_renumber)
+    lo, hi = v.min(axis=0), v.max(axis=0)
+    q = np.rint((v - lo) / (hi - lo) * float((1 << 21) - 1)).astype(np.int64)
+    order = np.lexsort((q[:, 0], q[:, 1], q[:, 2]))
+    node = np.empty(n_nodes, dtype=np.int64)
+    node[order] = np.arange(n_nodes)
+    A = g.get_matrix(0).tocsr()
+    hd = np.concatenate([3 * node[hv] + k for k in range(3)] + [3 * n_nodes + node[hv]])
+    D = sp.diags(A.diagonal()).tocsr()
+    assert abs(A[hd] - D[hd]).max() == 0.0 and abs(A.tocsc()[:, hd] - D.tocsc()[:, hd]).max() == 0.0 and (A.diagonal()[hd] > 0).all()
+    # a time step from a non-trivial state: the update is distributed through the lines
+    x0 = np.zeros(g.n_dofs)
+    interior = np.all((v > lo + 1e-9) & (v < hi - 1e-9), axis=1)
+    bump = np.where(interior, np.sin(np.pi * v[:, 0]) * np.sin(np.pi * v[:, 1]) * np.sin(np.pi * v[:, 2] / 4), 0.0)
+    vel = np.zeros((n_nodes, 3))
+    for k in (2, 4):  # the initial state has to satisfy the lines itself: the Newton updates are distributed, the state is not
+        sel = hk == k
+        bump[hv[sel]] = bump[hm[sel, :k]].mean(axis=1)
+    vel[node, 0] = bump
+    x0[: 3 * n_nodes] = vel.ravel()
+    g.set_vector(g.PRESENT, x0)
+    g.run_one_step(False)
+    sol = g.get_current_solution()
+    u = sol[: 3 * n_nodes].reshape(-1, 3)
+    p = sol[3 * n_nodes:]
+    for k in (2, 4):
+        sel = hk == k
+        m = node[hm[sel, :k]]
+        assert np.abs(u[node[hv[sel]]] - u[m].mean(axis=1)).max() < 1e-12 * max(np.abs(u).max(), 1e-300) + 1e-15
+        assert np.abs(p[node[hv[sel]]] - p[m].mean(axis=1)).max() < 1e-12 * max(np.abs(p).max(), 1e-300) + 1e-15
+    assert np.abs(u).max() > 0.1

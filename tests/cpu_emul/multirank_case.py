@@ -55,10 +55,14 @@ def main():
         v, c, _ = tria.get_mesh()
         z = v[c].mean(axis=1)[:, dim - 1]
         tria.execute_refinement(((z > 0.34) & (z < 0.67)).astype(np.uint8))
+    q2 = "q2" in sys.argv[7 + dim:]
     if solver == "SCnsIM":
         from test_scns_gpu import scns_prm
 
         text = scns_prm(dim, dt=1e-3)
+        if q2:  # Taylor-Hood pair through the degree-generic kernel (csrc/scnsim_generic.cu)
+            text = text.replace("set Velocity degree = 1", "set Velocity degree = 2")
+            q1 = False
     elif solver == "SUPGInsIM":
         full = 3 if dim == 2 else 7
         text = cavity_prm(dim, newton_tol=1e-8, dirichlet={2: (full, [0.0] * dim), 3: (full, [0.5] + [0.0] * (dim - 1))}, neumann={0: 1.0})
@@ -75,7 +79,7 @@ def main():
         flow.set_control(a_inv_rel=1e-3, a_inv_max_it=500, fgmres_rel=1e-9, a_inv_fp32=3, cg_sm_fp32=1)
     elif solver == "InsIM":
         flow.set_control(a_inv_rel=1e-10, a_inv_max_it=5000, fgmres_rel=1e-9)
-    elif q1:
+    elif solver in ("SCnsIM", "SUPGInsIM"):
         flow.set_control(fgmres_rel=1e-10, supg_ilu=0)
     n_un_glob = int(np.prod([(1 if q1 else 2) * k + 1 for k in reps]))
     n_pn_glob = int(np.prod([k + 1 for k in reps]))

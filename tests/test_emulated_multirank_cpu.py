@@ -59,7 +59,7 @@ SLOW = pytest.mark.slow
     pytest.param("InsIM", 2, (6, 8), 2, marks=SLOW), pytest.param("InsIM:inner32", 2, (6, 8), 2, marks=SLOW), ("SCnsIM", 2, (8, 10), 2), pytest.param("SUPGInsIM", 2, (8, 10), 2, marks=SLOW),
     ("InsIMEX", 2, (6, 8), 2), pytest.param("SCnsIM", 3, (4, 4, 6), 2, marks=SLOW),
     # locally refined band (hanging nodes): the slabs are cut along mesh planes that carry no hanging node or master
-    ("SCnsIM:refined", 2, (4, 9), 2), pytest.param("SCnsIM:refined", 3, (3, 3, 9), 2, marks=SLOW), pytest.param("SCnsIM:refined", 3, (2, 2, 12), 4, marks=SLOW),
+    ("SCnsIM:refined", 2, (4, 9), 2), ("SCnsIM:q2", 2, (5, 6), 2), pytest.param("SCnsIM:refined", 3, (3, 3, 9), 2, marks=SLOW), pytest.param("SCnsIM:refined", 3, (2, 2, 12), 4, marks=SLOW),
     # four z-slabs: the middle ranks have two neighbours (both halo directions inside one group)
     pytest.param("InsIM", 3, (3, 3, 8), 4, marks=SLOW), pytest.param("SCnsIM", 3, (4, 4, 8), 4, marks=SLOW)])
 def test_two_ranks_match_one_rank_on_the_emulated_device(emulated_library, solver, dim, reps, size, tmp_path):
@@ -69,7 +69,8 @@ def test_two_ranks_match_one_rank_on_the_emulated_device(emulated_library, solve
     assert rel(y2, y1) < 1e-13
     assert rel(rhs2, rhs1) < 1e-13
     assert h1.shape == h2.shape and np.array_equal(h1[:, :2], h2[:, :2])  # same (time step, Newton iteration) pattern
-    assert np.all(np.abs(h2[:, 2] - h1[:, 2]) <= 1e-6 * np.maximum(h1[:, 2], 1e-9))
+    # (residuals near the floor of the linear tolerance - 1e-10 of a right-hand side of order one - only agree to that floor)
+    assert np.all(np.abs(h2[:, 2] - h1[:, 2]) <= 1e-6 * np.maximum(h1[:, 2], 1e-8))
     assert rel(sol2[:nu], sol1[:nu]) < 1e-6
     p2, p1 = sol2[nu:], sol1[nu:]
     if solver.split(":")[0] in ("InsIM", "InsIMEX"):  # closed cavity: pressure up to a constant

@@ -54,3 +54,39 @@ def test_q1_interpolation_reproduces_linear_fields():
         val = s.interpolate(field, p)
         assert val is not None
         assert np.allclose(val, A @ p + np.array([0.3, -0.2, 0.1]), atol=1e-11)
+
+
+def test_refine_mesh_flags_and_transfer_of_the_oracle():
+    """oracle/fsi.py FSI.refine_mesh (mpi_fsi.cpp:1024-1117) on its own: cells within one diameter of the solid boundary reach
+    level 2 after the two calls FSI::run makes, cells far away stay coarse, the levels are capped, and the transfer (old FE field
+    evaluated at the new support points) reproduces a bilinear field exactly"""
+    import openifem_b200 as ifem  # host-side mesh class only (no device work)
+    from oracle import grid, prm, scns, solid
+    from test_fsi_gpu import _fsi_text
+
+    P = prm.Params(_fsi_text(2), is_text=True)
+    tria = ifem.Triangulation(2)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, (12, 12), (0.0, 0.0), (1.0, 1.0), True)
+    v, c, b = tria.get_mesh()
+    o_fluid = scns.SCnsIM(grid.QuadMesh(v, c, b), P)
+    o_solid = solid.HyperElasticity(fem.BoxMesh((4, 6), (0.3125, 0.0), (0.5625, 0.6875)), P)
+    loop = fsi.FSI(o_fluid, o_solid, True)
+    f = lambda X: 0.3 + 0.8 * X[:, 0] - 0.4 * X[:, 1] + 0.25 * X[:, 0] * X[:, 1]  # bilinear: in the Q1 space of every mesh
+    d = o_fluid.dofs
+    o_fluid.present[0: o_fluid.n_u: 2] = f(d.ucoords)
+    o_fluid.present[o_fluid.n_u:] = -f(d.pcoords)
+    for _ in range(2):
+        new = loop.refine_mesh(tria, 0, 3)
+    lv = tria.levels()
+    assert lv.max() == 2 and lv.min() == 0 and new.mesh.n_cells == tria.n_active_cells() > 144
+    X = new.mesh.vertices[new.mesh.cells].mean(axis=1)
+    far = np.hypot(X[:, 0] - 0.9, X[:, 1] - 0.9) < 0.08
+    assert far.any() and (lv[far] == 0).all()
+    near = (np.abs(X[:, 0] - 0.3125) < 0.02) & (X[:, 1] < 0.6)
+    assert near.any() and (lv[near] == 2).all()
+    nd = new.dofs
+    assert np.abs(new.present[0: new.n_u: 2] - f(nd.ucoords)).max() < 1e-13 and np.abs(new.present[new.n_u:] + f(nd.pcoords)).max() < 1e-13
+    assert len(nd.hanging_u) > 0
+    for _ in range(3):  # never beyond Global refinements + 3
+        new = loop.refine_mesh(tria, 0, 3)
+    assert tria.levels().max() == 3

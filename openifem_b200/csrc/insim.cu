@@ -124,24 +124,32 @@ namespace ifem
 
   void InsIM::after_mesh_change(const Triangulation::TransferPlan &plan, const std::vector<double> &old_vertices)
   {
-    if (fs.n_ranks > 1) throw std::runtime_error("refine_mesh: solution transfer on several ranks is not implemented");
     if (fs.pu != 1 || fs.pp != 1) throw std::runtime_error("refine_mesh: solution transfer is implemented for FE_Q(1) velocity and pressure");
     const int dim = fs.dim;
-    // old solution per old vertex
+    // old solution per old vertex: every rank contributes the nodes it owns (the triangulation is replicated, the solution is not)
     const int64_t n_old_u = fs.n_u;
     const std::vector<double> old = present_solution.to_host(ctx.stream);
     const int nv_old = (int)(old_vertices.size() / dim);
-    std::vector<double> vert_val((size_t)nv_old * (dim + 1));
+    std::vector<double> vert_val((size_t)nv_old * (dim + 1), 0.0);
     {
-      const CoordLookup un_old(dim, old_vertices, fs.un.coords), pn_old(dim, old_vertices, fs.pn.coords);
-      for (int v = 0; v < nv_old; ++v)
+      const CoordLookup vertex_at(dim, old_vertices, old_vertices);
+      for (int l = 0; l < fs.n_owned_unodes; ++l)
         {
-          const int nu_ = un_old.find(&old_vertices[(size_t)v * dim]), np_ = pn_old.find(&old_vertices[(size_t)v * dim]);
-          for (int c = 0; c < dim; ++c) vert_val[(size_t)v * (dim + 1) + c] = old[(size_t)dim * nu_ + c];
-          vert_val[(size_t)v * (dim + 1) + dim] = old[(size_t)n_old_u + np_];
+          const int v = vertex_at.find(&fs.un.coords[(size_t)l * dim]);
+          for (int c = 0; c < dim; ++c) vert_val[(size_t)v * (dim + 1) + c] = old[(size_t)dim * l + c];
+        }
+      for (int l = 0; l < fs.n_owned_pnodes; ++l)
+        vert_val[(size_t)vertex_at.find(&fs.pn.coords[(size_t)l * dim]) * (dim + 1) + dim] = old[(size_t)n_old_u + l];
+      if (fs.n_ranks > 1)
+        {
+          DevBuf<double> d(vert_val.size());
+          d.upload(vert_val, ctx.stream);
+          for (size_t off = 0; off < vert_val.size(); off += (size_t)1 << 28)
+            comm_allreduce_sum(*ctx.comm, d.p + off, (int)std::min<size_t>(vert_val.size() - off, (size_t)1 << 28), ctx.stream);
+          vert_val = d.to_host(ctx.stream);
         }
     }
-    // new spaces
+    // new spaces (on several ranks: a new partition of the new mesh)
     fs.base_valid = false;
     setup_dofs();
     make_constraints();
@@ -149,16 +157,16 @@ namespace ifem
     const int nv_new = triangulation.n_vertices();
     if ((int64_t)plan.ptr.size() != (int64_t)nv_new + 1) throw std::runtime_error("refine_mesh: the transfer plan does not belong to this mesh");
     std::vector<double> fresh((size_t)fs.n_dofs, 0.0);
-    const CoordLookup un_new(dim, triangulation.vertices, fs.un.coords), pn_new(dim, triangulation.vertices, fs.pn.coords);
-    for (int v = 0; v < nv_new; ++v)
-      {
-        double val[4] = {0, 0, 0, 0};
-        for (int64_t k = plan.ptr[v]; k < plan.ptr[v + 1]; ++k)
-          for (int c = 0; c <= dim; ++c) val[c] += plan.weight[k] * vert_val[(size_t)plan.old_vertex[k] * (dim + 1) + c];
-        const int nu_ = un_new.find(&triangulation.vertices[(size_t)v * dim]), np_ = pn_new.find(&triangulation.vertices[(size_t)v * dim]);
-        for (int c = 0; c < dim; ++c) fresh[(size_t)dim * nu_ + c] = val[c];
-        fresh[(size_t)fs.n_u + np_] = val[dim];
-      }
+    const CoordLookup vertex_at(dim, triangulation.vertices, triangulation.vertices);
+    auto value = [&](const double *x, int c) {
+      const int v = vertex_at.find(x);
+      double val = 0.0;
+      for (int64_t k = plan.ptr[v]; k < plan.ptr[v + 1]; ++k) val += plan.weight[k] * vert_val[(size_t)plan.old_vertex[k] * (dim + 1) + c];
+      return val;
+    };
+    for (int l = 0; l < fs.un.n_nodes; ++l) // owned and ghost nodes alike
+      for (int c = 0; c < dim; ++c) fresh[(size_t)dim * l + c] = value(&fs.un.coords[(size_t)l * dim], c);
+    for (int l = 0; l < fs.pn.n_nodes; ++l) fresh[(size_t)fs.n_u + l] = value(&fs.pn.coords[(size_t)l * dim], dim);
     present_solution.upload(fresh, ctx.stream);
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
   }

@@ -194,9 +194,18 @@ def fsi_case(rank, size, out, dim, reps):
     solid.setup()
     fluid.set_control(fgmres_rel=1e-10, supg_ilu=0)
     coupling = ifem.MPI.FSI(fluid, solid, params, sys.argv[-1] == "dirichlet")
-    for k in range(2):
-        coupling.run_one_step(k == 0)
-    n_un_glob = int(np.prod([k + 1 for k in reps]))
+    if "refine" in sys.argv[7 + dim:]:
+        # FSI::refine_mesh around the solid before and between the steps: new partition, transferred solution (every rank holds the
+        # whole triangulation and refines it identically; the slabs avoid the planes that carry hanging nodes)
+        coupling.refine_mesh(0, 2)
+        fluid.set_control(fgmres_rel=1e-10, supg_ilu=0)
+        coupling.run_one_step(True)
+        coupling.refine_mesh(0, 2)
+        coupling.run_one_step(False)
+    else:
+        for k in range(2):
+            coupling.run_one_step(k == 0)
+    n_un_glob = ftria.n_vertices()
     loc, glo = fluid.owned_global_dofs(n_un_glob)
     sol = fluid.get_current_solution()
     acc = fluid.get_vector(fluid.FSI_ACCELERATION)

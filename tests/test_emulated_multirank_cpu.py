@@ -96,6 +96,18 @@ def test_two_rank_fsi_loop_matches_one_rank_on_the_emulated_device(emulated_libr
     assert h1.shape == h2.shape and np.array_equal(h1[:, :2], h2[:, :2])
 
 
+@SLOW  # fifteen minutes on the emulator
+def test_two_rank_fsi_loop_with_refine_mesh_matches_one_rank_on_the_emulated_device(emulated_library, tmp_path):
+    """FSI::refine_mesh on two ranks: identical replicated mesh operations, solution gathered through the vertices and handed to the
+    new partition (InsIM::after_mesh_change); two coupled steps with a refinement before each equal the one-rank run"""
+    y1, rhs1, sol1, h1, nu, us1 = _run(1, "FSI:refine", 2, (12, 12), tmp_path)
+    y2, rhs2, sol2, h2, _, us2 = _run(2, "FSI:refine", 2, (12, 12), tmp_path)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert sol1.size == sol2.size > 3 * 169 and h1.shape == h2.shape
+    assert rel(sol2[:nu], sol1[:nu]) < 1e-6 and rel(sol2[nu:], sol1[nu:]) < 1e-6 and rel(us2, us1) < 1e-6
+    assert rel(y2, y1) < 1e-6  # fsi_acceleration
+
+
 def test_two_rank_output_pieces_tile_the_mesh(emulated_library, tmp_path):
     """FluidSolver::output_results on two ranks: every rank writes the cells of its own slab (cell->is_locally_owned()), rank 0
     the .pvtu naming both pieces; together the pieces hold every cell exactly once and the right values at every vertex"""

@@ -235,6 +235,8 @@ namespace ifem
 
     con.assign(n_dofs, 0);
     nonzero_val.assign(n_dofs, 0.0);
+    base_valid = false; // cached constraint lines belong to the previous space
+    flags_merged = false;
     d_con.upload(con, s);
     d_nonzero_val.upload(nonzero_val, s);
     IFEM_CUDA(cudaStreamSynchronize(s));

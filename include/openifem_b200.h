@@ -249,6 +249,31 @@ int ifem_scnsim_update_stress(ifem_insim *s);
 int ifem_scnsim_get_field(ifem_insim *s, int which, double *host);
 int ifem_scnsim_set_field(ifem_insim *s, int which, const double *host);
 
+/* ---- Fluid::MPI::SpalartAllmaras<dim> (include/mpi_spalart_allmaras.h, source/mpi_spalart_allmaras.cpp) on
+ *      Fluid::MPI::TurbulenceModel (include/mpi_turbulence_model.h): the turbulence model of an SCnsIM solver. The model lives
+ *      inside the fluid solver's handle, like the reference's FluidSolver::turbulence_model. ---- */
+/* FluidSolver::attach_turbulence_model(model_name) (source/mpi_fluid_solver.cpp:53-63); "Spalart-Allmaras" is the one model the
+ * reference's factory knows (source/mpi_turbulence_model.cpp:11-26). Before or after ifem_insim_setup; from then on ifem_insim_run
+ * advances the model before every fluid step (source/mpi_supg_solver.cpp:456-468) and SCnsIM::assemble adds the eddy viscosity
+ * (source/mpi_scnsim.cpp:198-216). Equal-order Q1/Q1 solvers. */
+int ifem_insim_attach_turbulence_model(ifem_insim *s, const char *model_name);
+/* vectors over the scalar support points (pressure-node numbering of this rank): 0 present_solution (nu~), 1 evaluation_point,
+ * 2 eddy_viscosity (get_eddy_viscosity(), include/mpi_turbulence_model.h:40), 3 system_rhs, 4 newton_update,
+ * 5 fixed wall distance (setup_cell_property, :415-552). set: 0, 1, 2 */
+int ifem_turbulence_get_vector(ifem_insim *s, int which, double *host);
+int ifem_turbulence_set_vector(ifem_insim *s, int which, const double *host);
+/* SpalartAllmaras::assemble(use_nonzero_constraints) (:620-832); the system matrix is ifem_insim_get_matrix(s, 3, ...) with the
+ * pattern of M_p */
+int ifem_turbulence_assemble(ifem_insim *s, int use_nonzero_constraints);
+/* run_one_step(apply_nonzero_constraints) (:296-349): Newton loop + update_eddy_viscosity (:864-889) */
+int ifem_turbulence_run_one_step(ifem_insim *s, int apply_nonzero_constraints);
+/* update_boundary_condition(first_step) (:133-224): lines of the cells inside the immersed solid (CellProperty::indicator == 1) */
+int ifem_turbulence_update_boundary_condition(ifem_insim *s, int first_step);
+/* get_shear_velocity(vel, init_guess) (:227-293) */
+int ifem_turbulence_get_shear_velocity(ifem_insim *s, double vel, double init_guess, double *out);
+/* Newton records of the model (the " ITR = .. ABS_RES = .." lines of :333-338): abs_res / gmres_its of the last max_records */
+int ifem_turbulence_history(ifem_insim *s, int max_records, double *abs_res, int *gmres_its, int *n_records);
+
 /* ---- Solid::MPI::HyperElasticity<dim> (include/mpi_hyper_elasticity.h:96-176, source/mpi_hyper_elasticity.cpp;
  *      base class include/mpi_solid_solver.h:75-79, source/mpi_solid_solver.cpp) ---- */
 typedef struct ifem_hyper ifem_hyper;

@@ -384,11 +384,11 @@ class _InsIM:
         check(lib().ifem_insim_set_indicator(self._h, iptr(ind)))
 
     def get_matrix(self, which=0):
-        """0 system_matrix, 1 M_p, 2 mass_schur -> scipy.sparse.csr_matrix"""
+        """0 system_matrix, 1 M_p, 2 mass_schur, 3 system matrix of the attached turbulence model -> scipy.sparse.csr_matrix"""
         import scipy.sparse as sp
 
         n_u, n_p, nnz, nnz_mp, nnz_s = self.sizes()
-        n, z = {0: (n_u + n_p, nnz), 1: (n_p, nnz_mp), 2: (n_p, nnz_s)}[which]
+        n, z = {0: (n_u + n_p, nnz), 1: (n_p, nnz_mp), 2: (n_p, nnz_s), 3: (n_p, nnz_mp)}[which]
         rp, ci, v = np.empty(n + 1, dtype=np.int64), np.empty(z, dtype=np.int32), np.empty(z)
         check(lib().ifem_insim_get_matrix(self._h, C.c_int(which), lptr(rp), iptr(ci), dptr(v)))
         return sp.csr_matrix((v, ci, rp), shape=(n, n))
@@ -558,6 +558,61 @@ class _SCnsIM(_InsIM):
     def set_field(self, which, host):
         host = np.ascontiguousarray(host, dtype=np.float64).reshape(self._field_shape(which))
         check(lib().ifem_scnsim_set_field(self._h, C.c_int(which), dptr(host)))
+
+    def attach_turbulence_model(self, model_name: str):
+        """FluidSolver::attach_turbulence_model; returns the model (a view of this solver's handle)"""
+        check(lib().ifem_insim_attach_turbulence_model(self._h, model_name.encode()))
+        self.turbulence_model = _TurbulenceModel(self)
+        return self.turbulence_model
+
+
+class _TurbulenceModel:
+    """Fluid::MPI::SpalartAllmaras<dim> attached to an SCnsIM solver (lives inside the solver's handle)"""
+
+    PRESENT, EVALUATION_POINT, EDDY_VISCOSITY, SYSTEM_RHS, NEWTON_UPDATE, WALL_DISTANCE = range(6)
+
+    def __init__(self, fluid):
+        self.fluid = fluid
+
+    @property
+    def n_dofs(self):
+        return self.fluid.partition(1)[1]
+
+    def get_vector(self, which):
+        out = np.empty(self.n_dofs)
+        check(lib().ifem_turbulence_get_vector(self.fluid._h, C.c_int(which), dptr(out)))
+        return out
+
+    def set_vector(self, which, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        assert host.size == self.n_dofs
+        check(lib().ifem_turbulence_set_vector(self.fluid._h, C.c_int(which), dptr(host)))
+
+    def get_eddy_viscosity(self):
+        return self.get_vector(self.EDDY_VISCOSITY)
+
+    def assemble(self, use_nonzero_constraints):
+        check(lib().ifem_turbulence_assemble(self.fluid._h, C.c_int(1 if use_nonzero_constraints else 0)))
+
+    def get_matrix(self):
+        return self.fluid.get_matrix(3)
+
+    def run_one_step(self, apply_nonzero_constraints):
+        check(lib().ifem_turbulence_run_one_step(self.fluid._h, C.c_int(1 if apply_nonzero_constraints else 0)))
+
+    def update_boundary_condition(self, first_step):
+        check(lib().ifem_turbulence_update_boundary_condition(self.fluid._h, C.c_int(1 if first_step else 0)))
+
+    def get_shear_velocity(self, vel, init_guess):
+        out = C.c_double()
+        check(lib().ifem_turbulence_get_shear_velocity(self.fluid._h, C.c_double(vel), C.c_double(init_guess), C.byref(out)))
+        return out.value
+
+    def history(self, max_records=1024):
+        res, its, n = np.empty(max_records), np.empty(max_records, dtype=np.int32), C.c_int()
+        check(lib().ifem_turbulence_history(self.fluid._h, C.c_int(max_records), dptr(res), iptr(its), C.byref(n)))
+        k = min(n.value, max_records)
+        return list(zip(res[:k].tolist(), its[:k].tolist()))
 
 
 class _HyperElasticity:

@@ -621,6 +621,16 @@ int ifem_insim_get_matrix(ifem_insim *s, int which, int64_t *rowptr, int *col, d
         std::copy(v.begin(), v.end(), val);
         return;
       }
+    if (which == 3) // system matrix of the attached turbulence model (pattern of M_p)
+      {
+        SCnsIM *f = dynamic_cast<SCnsIM *>(s->s.get());
+        if (!f || !f->turbulence_model) throw std::runtime_error("no turbulence model attached");
+        f->turbulence_model->system_matrix.to_host_csr(st, rp, ci, v);
+        std::copy(rp.begin(), rp.end(), rowptr);
+        std::copy(ci.begin(), ci.end(), col);
+        std::copy(v.begin(), v.end(), val);
+        return;
+      }
     if (which != 0) throw std::runtime_error("unknown matrix id");
     HostCsr uu, up, pu, ppm;
     fs.A_uu.to_host_csr(st, uu.rp, uu.ci, uu.v);
@@ -1313,6 +1323,91 @@ int ifem_scnsim_update_stress(ifem_insim *s)
   return guard([&] {
     s->s->update_stress();
     IFEM_CUDA(cudaStreamSynchronize(s->s->ctx.stream));
+  });
+}
+namespace
+{
+  SpalartAllmaras &as_turbulence(ifem_insim *s)
+  {
+    SCnsIM &f = as_scns(s);
+    if (!f.turbulence_model) throw std::runtime_error("no turbulence model attached");
+    return *f.turbulence_model;
+  }
+  DevBuf<double> &turbulence_vector(SpalartAllmaras &t, int which)
+  {
+    switch (which)
+      {
+      case 0: return t.present_solution;
+      case 1: return t.evaluation_point;
+      case 2: return t.eddy_viscosity;
+      case 3: return t.system_rhs;
+      case 4: return t.newton_update;
+      case 5: return t.fixed_wall_distance;
+      default: throw std::runtime_error("unknown turbulence vector id");
+      }
+  }
+} // namespace
+int ifem_insim_attach_turbulence_model(ifem_insim *s, const char *model_name)
+{
+  return guard([&] { as_scns(s).attach_turbulence_model(model_name ? model_name : ""); });
+}
+int ifem_turbulence_get_vector(ifem_insim *s, int which, double *host)
+{
+  return guard([&] {
+    SpalartAllmaras &t = as_turbulence(s);
+    DevBuf<double> &v = turbulence_vector(t, which);
+    v.download(host, v.n, t.ctx.stream);
+  });
+}
+int ifem_turbulence_set_vector(ifem_insim *s, int which, const double *host)
+{
+  return guard([&] {
+    if (which < 0 || which > 2) throw std::runtime_error("turbulence vector is read-only");
+    SpalartAllmaras &t = as_turbulence(s);
+    DevBuf<double> &v = turbulence_vector(t, which);
+    v.upload(host, v.n, t.ctx.stream);
+    IFEM_CUDA(cudaStreamSynchronize(t.ctx.stream));
+  });
+}
+int ifem_turbulence_assemble(ifem_insim *s, int use_nonzero_constraints)
+{
+  return guard([&] {
+    SpalartAllmaras &t = as_turbulence(s);
+    t.assemble(use_nonzero_constraints != 0);
+    IFEM_CUDA(cudaStreamSynchronize(t.ctx.stream));
+  });
+}
+int ifem_turbulence_run_one_step(ifem_insim *s, int apply_nonzero_constraints)
+{
+  return guard([&] {
+    SpalartAllmaras &t = as_turbulence(s);
+    t.run_one_step(apply_nonzero_constraints != 0);
+    IFEM_CUDA(cudaStreamSynchronize(t.ctx.stream));
+  });
+}
+int ifem_turbulence_update_boundary_condition(ifem_insim *s, int first_step)
+{
+  return guard([&] {
+    SpalartAllmaras &t = as_turbulence(s);
+    t.update_boundary_condition(first_step != 0);
+    IFEM_CUDA(cudaStreamSynchronize(t.ctx.stream));
+  });
+}
+int ifem_turbulence_get_shear_velocity(ifem_insim *s, double vel, double init_guess, double *out)
+{
+  return guard([&] { *out = as_turbulence(s).get_shear_velocity(vel, init_guess); });
+}
+int ifem_turbulence_history(ifem_insim *s, int max_records, double *abs_res, int *gmres_its, int *n_records)
+{
+  return guard([&] {
+    const SpalartAllmaras &t = as_turbulence(s);
+    const int n = (int)t.history.size(), k = std::min(n, max_records);
+    for (int i = 0; i < k; ++i)
+      {
+        abs_res[i] = t.history[n - k + i].abs_res;
+        gmres_its[i] = t.history[n - k + i].gmres_its;
+      }
+    *n_records = n;
   });
 }
 int ifem_scnsim_get_field(ifem_insim *s, int which, double *host)

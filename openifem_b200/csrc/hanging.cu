@@ -466,6 +466,31 @@ namespace ifem
                            (uu.n_mrows > 0) + (up.n_mrows > 0) + (pu.n_mrows > 0) + (pp.n_mrows > 0);
   }
 
+  void HangingConstraints::condense_scalar(Context &ctx, const FluidSpace &fs, Bcsr &A, double *rhs, const unsigned char *con,
+                                           const double *inhom) const
+  {
+    if (!active || !p.n) return;
+    if (!with_pp) throw std::runtime_error("HangingConstraints::condense_scalar needs the fold plan of A_pp");
+    cudaStream_t s = ctx.stream;
+    const Space P{1, 0, p.d_node.p, p.d_n_masters.p, p.d_master.p};
+    const Mat M = view(A);
+    hanging_diag_kernel<<<blocks(p.n), 128, 0, s>>>(p.n, fs.n_owned_pnodes, M, P, p.d_diag.p);
+    if (pp.n_rows) fold_columns_kernel<<<blocks(pp.n_rows), 128, 0, s>>>(pp.n_rows, pp.d_row.p, pp.d_ptr.p, pp.d_item.p, M, P, P, con, inhom, rhs);
+    if (pp.n_mrows) fold_rows_kernel<<<blocks(pp.n_mrows), 128, 0, s>>>(pp.n_mrows, pp.d_mrow.p, pp.d_mptr.p, pp.d_mslave.p, M, P, con, rhs, 1);
+    hanging_rows_kernel<<<blocks(p.n), 128, 0, s>>>(p.n, fs.n_owned_pnodes, M, M, P, p.d_diag.p, con, inhom, rhs);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches += 2 + (pp.n_rows > 0) + (pp.n_mrows > 0);
+  }
+
+  void HangingConstraints::distribute_scalar(Context &ctx, double *x) const
+  {
+    if (!active || !p.n) return;
+    const Space P{1, 0, p.d_node.p, p.d_n_masters.p, p.d_master.p};
+    hanging_distribute_kernel<<<blocks(p.n), 128, 0, ctx.stream>>>(p.n, P, x);
+    IFEM_KERNEL_CHECK();
+    ctx.kernel_launches++;
+  }
+
   void HangingConstraints::distribute(Context &ctx, const FluidSpace &fs, double *x) const
   {
     if (!active) return;

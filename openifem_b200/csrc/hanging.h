@@ -68,5 +68,10 @@ namespace ifem
     void condense(Context &ctx, FluidSpace &fs, const double *inhom) const;
     // x_h = sum_k w_k x_master(k) for every hanging dof of the block vector x (after the Dirichlet entries were set)
     void distribute(Context &ctx, const FluidSpace &fs, double *x) const;
+    // the same condensation / distribution for ONE scalar system on the pressure node space (pattern and fold plan of A_pp):
+    // the transport equation of a turbulence model (source/mpi_spalart_allmaras.cpp:817-826, :855-858). con / inhom are the
+    // model's own lines, indexed by pressure node.
+    void condense_scalar(Context &ctx, const FluidSpace &fs, Bcsr &A, double *rhs, const unsigned char *con, const double *inhom) const;
+    void distribute_scalar(Context &ctx, double *x) const;
   };
 } // namespace ifem

@@ -60,6 +60,7 @@ namespace ifem
     if (fs.base_valid && (hard_coded.empty() || base_bc_time == bc_time))
       {
         fs.restore_base_constraints(ctx);
+        if (after_make_constraints) after_make_constraints();
         return;
       }
     base_bc_time = bc_time;
@@ -73,6 +74,7 @@ namespace ifem
       };
     fs.make_constraints(ctx, triangulation, parameters.fluid_dirichlet_bcs, hc);
     fs.set_neumann_faces(ctx, triangulation, parameters.fluid_neumann_bcs);
+    if (after_make_constraints) after_make_constraints();
   }
 
   void InsIM::upload_constraints()
@@ -124,6 +126,8 @@ namespace ifem
 
   void InsIM::after_mesh_change(const Triangulation::TransferPlan &plan, const std::vector<double> &old_vertices)
   {
+    if (after_make_constraints) // pre_refine_mesh / post_refine_mesh of the turbulence model (mpi_spalart_allmaras.cpp:594-617)
+      throw std::runtime_error("refine_mesh with an attached turbulence model is not built");
     if (fs.pu != 1 || fs.pp != 1) throw std::runtime_error("refine_mesh: solution transfer is implemented for FE_Q(1) velocity and pressure");
     const int dim = fs.dim;
     // old solution per old vertex: every rank contributes the nodes it owns (the triangulation is replicated, the solution is not)

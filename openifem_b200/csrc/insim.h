@@ -148,6 +148,8 @@ namespace ifem
     // per-section device time, keyed by the reference's TimerOutput section names
     std::map<std::string, double> timer_ms;
     bool dofs_ready = false;
+    // called at the end of make_constraints(): an attached turbulence model re-makes its own lines (mpi_fluid_solver.cpp:276-279)
+    std::function<void()> after_make_constraints;
 
   protected:
     void io_before_step(); // output of step 0

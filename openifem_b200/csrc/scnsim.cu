@@ -28,6 +28,7 @@ namespace ifem
       const double *cell_x, *tables; // N[nq][nu] | dN[nq][nu][dim] | Np[nq][np] | dNgeo[nq][nv][dim] | qw[nq]
       const unsigned char *slots, *con;
       const double *eval_pt, *present, *fsi_acc, *stress, *fsi_stress, *sigma_pml, *body_force, *inhom;
+      const double *eddy; // nodal eddy viscosity of an attached turbulence model (pressure-node numbering) or null
       int64_t n_u;
       int n_unodes, n_owned_u, n_owned_p, n_h, h_node[8];
       double mu, rho_f, rho_s, dt, grav[3];
@@ -81,7 +82,7 @@ namespace ifem
           for (int j = 0; j < DIM; ++j) J[i * DIM + j] = fma(X[v * DIM + i], tdG[(q * NV + v) * DIM + j], J[i * DIM + j]);
       invert<DIM>(J, Ji, det);
       Q.JxW = det * tqw[q];
-      double up[DIM], pp = 0.0;
+      double up[DIM], pp = 0.0, eddy = 0.0;
 #pragma unroll
       for (int c = 0; c < DIM; ++c) Q.u[c] = up[c] = Q.acc[c] = Q.gradp[c] = Q.sdiv[c] = 0.0;
 #pragma unroll
@@ -103,6 +104,7 @@ namespace ifem
           const double pe = A.eval_pt[A.n_u + pn];
           Q.p = fma(N, pe, Q.p);
           pp = fma(N, A.present[A.n_u + pn], pp);
+          if (A.eddy) eddy = fma(N, A.eddy[pn], eddy);
 #pragma unroll
           for (int c = 0; c < DIM; ++c)
             {
@@ -137,7 +139,7 @@ namespace ifem
       Q.dp = Q.p - pp;
       Q.sigma = A.sigma_pml ? A.sigma_pml[(int64_t)cell * NQ + q] : 0.0;
       Q.rho = A.rho_f * (1 + pp / kAtm) * (1 - ind) + ind * A.rho_s; // :210-213
-      Q.visc = ind == 1 ? 1.0 : A.mu;                                  // :214-216 (no turbulence model)
+      Q.visc = (ind == 1 ? 1.0 : A.mu) + (eddy > 0.0 ? eddy : 0.0);    // :198-203, :214-216
       // UGN stabilisation parameters (:247-274) from the previous-step velocity
       double h = 0.0;
       for (int k = 0; k < A.n_h; ++k) h += fabs(dotd<DIM>(up, Q.g[A.h_node[k]]));
@@ -542,6 +544,19 @@ namespace ifem
         present_solution.upload(ic, s);
       }
     IFEM_CUDA(cudaStreamSynchronize(s));
+    if (turbulence_model) turbulence_model->initialize_system(); // mpi_supg_solver.cpp:290-293
+  }
+
+  void SCnsIM::attach_turbulence_model(const std::string &model_name)
+  {
+    if (model_name != "Spalart-Allmaras") throw std::runtime_error("attach_turbulence_model: model <" + model_name + "> is not implemented");
+    turbulence_model = std::make_unique<SpalartAllmaras>(ctx, *this);
+    after_make_constraints = [this] { turbulence_model->make_constraints(); };
+    if (dofs_ready) // attached after setup: what make_constraints() / initialize_system() would have done (mpi_supg_solver.cpp:290-293)
+      {
+        turbulence_model->make_constraints();
+        turbulence_model->initialize_system();
+      }
   }
 
   void SCnsIM::assemble(bool use_nonzero_constraints)
@@ -595,6 +610,7 @@ namespace ifem
     a.sigma_pml = d_sigma_pml.n ? d_sigma_pml.p : nullptr;
     a.body_force = d_body_force.n ? d_body_force.p : nullptr;
     a.inhom = use_nonzero_constraints ? fs.d_nonzero_val.p : nullptr;
+    a.eddy = turbulence_model ? turbulence_model->eddy_viscosity.p : nullptr;
     a.n_u = fs.n_u;
     a.n_unodes = fs.un.n_nodes;
     a.n_owned_u = fs.n_owned_unodes;
@@ -824,9 +840,14 @@ namespace ifem
       }
     else if (advance_clock)
       make_constraints();
-    if (!success_load) run_one_step(true);
+    if (!success_load)
+      {
+        if (turbulence_model) turbulence_model->run_one_step(true); // :456-459
+        run_one_step(true);
+      }
     while (time.end() - time.current() > 1e-12)
       {
+        if (turbulence_model) turbulence_model->run_one_step(false); // :464-467
         if (time_dependent)
           {
             bc_time += time.get_delta_t();

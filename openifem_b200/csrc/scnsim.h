@@ -7,6 +7,7 @@
 #pragma once
 #include "ilu0.h"
 #include "insim.h"
+#include "spalart_allmaras.h"
 
 namespace ifem
 {
@@ -38,6 +39,10 @@ namespace ifem
     void run() override;
     DevBuf<double> fsi_stress; // [dim(dim+1)/2][n_unodes]
     int tpp_its = 0;
+    // FluidSolver::attach_turbulence_model (source/mpi_fluid_solver.cpp:53-63; TurbulenceModelFactory::create accepts
+    // "Spalart-Allmaras" only, source/mpi_turbulence_model.cpp:11-26). Before or after setup.
+    void attach_turbulence_model(const std::string &model_name);
+    std::unique_ptr<SpalartAllmaras> turbulence_model;
 
   protected:
     void precondition_supg(const double *src, double *dst);

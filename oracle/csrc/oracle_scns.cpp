@@ -42,6 +42,8 @@ namespace
     double *A, *rhs;
   };
 
+  const double *g_eddy_viscosity = nullptr; // nodal eddy viscosity of an attached turbulence model (oracle_scns_set_eddy_viscosity)
+
   template <int dim>
   inline T1<dim> vecmat(const T1<dim> &a, const T2<dim> &B) // a * B  (contract a with first index of B)
   {
@@ -177,7 +179,11 @@ namespace
 
               // :210-216
               const double rho = a.rho_f * (1 + present_pressure_values / atm) * (1 - ind) + ind * a.rho_s;
-              const double viscosity = (ind == 1 ? 1 : a.viscosity);
+              // turbulence_model->get_eddy_viscosity() on scalar FE_Q(pu), clipped at zero (:198-203, :214-216)
+              double eddy_viscosity = 0.0;
+              if (g_eddy_viscosity)
+                for (int b = 0; b < nu; ++b) eddy_viscosity += g_eddy_viscosity[un[b]] * a.Nu[q * nu + b];
+              const double viscosity = (ind == 1 ? 1 : a.viscosity) + (eddy_viscosity > 0.0 ? eddy_viscosity : 0.0);
 
               // UGN stabilisation parameters (:247-274)
               double tau_SUPG, tau_PSPG, tau_LSIC;
@@ -328,6 +334,8 @@ namespace
     }
   }
 } // namespace
+
+extern "C" void oracle_scns_set_eddy_viscosity(const double *nodal) { g_eddy_viscosity = nodal; }
 
 extern "C" int oracle_scns_assemble(
   int dim, int nu, int np, int n_cells, const double *vertices, const int *cells, const int *cell_dofs, const int *cell_unodes,

@@ -33,6 +33,7 @@ def _lst(s, f):
 class Params:
     def __init__(self, path_or_text: str, is_text: bool = False):
         d = parse_prm(path_or_text, is_text)
+        self.raw = d
         g = lambda sec, key, default: d.get((sec, key), default)
         S = "Simulation"
         self.simulation_type = g(S, "Simulation type", "FSI")

@@ -76,6 +76,7 @@ class SCnsIM:
         self.fsi_stress = np.zeros((dim * (dim + 1) // 2, d.n_unodes))
         self.time, self.timestep, self.dt = 0.0, 0, params.time_step
         self.history = []
+        self.turbulence_model = None
         self.vertices = np.ascontiguousarray(mesh.vertices)
         self.cells = np.ascontiguousarray(mesh.cells)
         self.cell_dofs = np.ascontiguousarray(d.cell_dofs)
@@ -101,6 +102,16 @@ class SCnsIM:
         Mref = np.einsum("qi,qj,q->ij", self.Nu, self.Nu, self.qw)
         self.qpt_to_dof = np.linalg.solve(Mref, (self.Nu * self.qw[:, None]).T)
 
+    def attach_turbulence_model(self, model_name: str):
+        """FluidSolver::attach_turbulence_model (mpi_fluid_solver.cpp:53-63); the model's make_constraints / initialize_system
+        (:276-279, mpi_supg_solver.cpp:290-293) run here because this class sets itself up in the constructor"""
+        if model_name != "Spalart-Allmaras":
+            raise NotImplementedError(model_name)  # TurbulenceModelFactory::create: ExcNotImplemented
+        from .spalart_allmaras import SpalartAllmaras
+
+        self.turbulence_model = SpalartAllmaras(self)
+        return self.turbulence_model
+
     def _closed_constraints(self, use_nonzero_constraints: bool):
         """(flags, inhomogeneities or None) of nonzero_constraints / zero_constraints after close(); hanging-node lines
         (locally refined meshes) are handed to the C cell loops through oracle_set_constraint_lines"""
@@ -125,6 +136,8 @@ class SCnsIM:
         grav = np.asarray(p.gravity, dtype=np.float64)
         stress = np.ascontiguousarray(self.stress)
         fsis = np.ascontiguousarray(self.fsi_stress)
+        eddy = np.ascontiguousarray(self.turbulence_model.eddy_viscosity) if self.turbulence_model is not None else None
+        lib().oracle_scns_set_eddy_viscosity(_p(eddy))
         rc = lib().oracle_scns_assemble(
             C.c_int(self.dim), C.c_int(self.feu.n), C.c_int(self.fep.n), C.c_int(self.mesh.n_cells), _p(self.vertices),
             _p(self.cells, C.c_int), _p(self.cell_dofs, C.c_int), _p(self.cell_unodes, C.c_int), C.c_int(self.nq), _p(self.qw),
@@ -136,6 +149,7 @@ class SCnsIM:
             _p(self.bfaces, C.c_int), C.c_int(nids.size), _p(nids, C.c_int), _p(nvals), _p(con, C.c_ubyte), _p(inhom),
             _p(self.rowptr, C.c_int64), _p(self.col, C.c_int), _p(A), _p(rhs))
         self._release_constraints()
+        lib().oracle_scns_set_eddy_viscosity(None)
         assert rc == 0
         self.system_matrix = sp.csr_matrix((A, self.col, self.rowptr), shape=(self.n, self.n))
         self.system_rhs = rhs
@@ -193,6 +207,8 @@ class SCnsIM:
     def make_constraints(self):
         self.con, self.nonzero_val = fem.make_dirichlet_constraints(self.dofs, self.prm.fluid_dirichlet_bcs, self.hard_coded,
                                                                     self.bc_time)
+        if self.turbulence_model is not None:  # mpi_fluid_solver.cpp:276-279
+            self.turbulence_model.make_constraints()
 
     def run(self, max_steps=None):
         """SUPGFluidSolver::run (mpi_supg_solver.cpp:427-486): with hard-coded boundary values the functions' clock is
@@ -201,9 +217,13 @@ class SCnsIM:
         if self.hard_coded:
             self.bc_time += self.dt
             self.make_constraints()
+        if self.turbulence_model is not None:  # :456-461
+            self.turbulence_model.run_one_step(True)
         self.run_one_step(True)
         k = 1
         while self.prm.end_time - self.time > 1e-12 and (max_steps is None or k < max_steps):
+            if self.turbulence_model is not None:  # :464-469
+                self.turbulence_model.run_one_step(False)
             if self.hard_coded:
                 self.bc_time += self.dt
                 self.make_constraints()

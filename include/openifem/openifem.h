@@ -381,6 +381,18 @@ namespace Fluid
       void set_body_force(const Field &f) { openifem_detail::check(ifem_scnsim_set_body_force(this->h, &thunk, keep(f))); }
       void set_sigma_pml_field(const Field &f) { openifem_detail::check(ifem_scnsim_set_sigma_pml_field(this->h, &thunk, keep(f))); }
       void set_initial_condition(const Field &f) { openifem_detail::check(ifem_scnsim_set_initial_condition(this->h, &thunk, keep(f))); }
+      // FluidSolver::attach_turbulence_model (include/mpi_fluid_solver.h:113): "Spalart-Allmaras"
+      void attach_turbulence_model(const std::string &model_name)
+      {
+        openifem_detail::check(ifem_insim_attach_turbulence_model(this->h, model_name.c_str()));
+      }
+      // turbulence_model->get_eddy_viscosity() (include/mpi_turbulence_model.h:40) over the scalar support points of this rank
+      std::vector<double> get_eddy_viscosity(std::size_t n_scalar_dofs)
+      {
+        std::vector<double> v(n_scalar_dofs);
+        openifem_detail::check(ifem_turbulence_get_vector(this->h, 2, v.data()));
+        return v;
+      }
 
     private:
       static double thunk(const double *p, unsigned int c, void *user)

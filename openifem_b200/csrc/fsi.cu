@@ -1118,10 +1118,14 @@ namespace ifem
     update_indicator();
     fluid.make_constraints();
     if (!first_step) fluid.fs.d_nonzero_val.zero(ctx.stream); // nonzero_constraints.copy_from(zero_constraints) (:1193-1198): homogeneous increments from now on
+    SCnsIM *supg = dynamic_cast<SCnsIM *>(&fluid);
+    SpalartAllmaras *turbulence_model = supg ? supg->turbulence_model.get() : nullptr;
+    if (turbulence_model) turbulence_model->update_boundary_condition(first_step); // :1199-1203
     find_fluid_bc();
     if (stop_before_fluid_step) return; // tests: the state the fluid solver is about to see
     {
       ScopedTimer t(ctx, timer_ms["Run fluid solver"]);
+      if (turbulence_model) turbulence_model->run_one_step(true); // :1207-1210
       fluid.run_one_step(true);
     }
     time.increment();

@@ -465,4 +465,9 @@ class FSI:
             new = (icon != 0) & (f.con == 0) & ~f.dofs.is_hanging  # merge(..., left_object_wins): existing lines stay
             f.con[new] = 1
             f.nonzero_val[new] = iinh[new]
+        tm = getattr(f, "turbulence_model", None)
+        if tm is not None:  # mpi_fsi.cpp:1199-1210 (update_boundary_condition comes before find_fluid_bc there; they are independent)
+            tm.make_constraints()
+            tm.update_boundary_condition(first_step)
+            tm.run_one_step(True)
         f.run_one_step(True)

@@ -56,10 +56,15 @@ def main():
         z = v[c].mean(axis=1)[:, dim - 1]
         tria.execute_refinement(((z > 0.34) & (z < 0.67)).astype(np.uint8))
     q2 = "q2" in sys.argv[7 + dim:]
+    with_sa = "sa" in sys.argv[7 + dim:]  # Spalart-Allmaras model attached (walls on boundary ids 2 / 3, inflow on 0)
     if solver == "SCnsIM":
         from test_scns_gpu import scns_prm
 
         text = scns_prm(dim, dt=1e-3)
+        if with_sa:
+            text = scns_prm(dim, dt=1e-2, mu=1e-3, rho=1.0) + (
+                "subsection Spalart Allmaras model\n  set Number of S-A model BCs = 3\n  set S-A model boundary id = 0, 2, 3\n"
+                "  set S-A model boundary types = 1, 0, 0\n  set Initial condition coefficient = 3.0\nend\n")
         if q2:  # Taylor-Hood pair through the degree-generic kernel (csrc/scnsim_generic.cu)
             text = text.replace("set Velocity degree = 1", "set Velocity degree = 2")
             q1 = False
@@ -73,6 +78,7 @@ def main():
     if solver == "SCnsIM":
         flow.set_body_force(lambda p, c: 5.0 if c == 0 else 0.0)
     flow.setup()
+    model = flow.attach_turbulence_model("Spalart-Allmaras") if with_sa else None
     if solver == "InsIM" and "inner32" in sys.argv[7 + dim:]:
         # device-resident fp32 inner solvers (BiCGStab on the fp16 SELL copy of A_uu, CG on the SELL copy of S_m): on emulated ranks
         # their reductions and halos go through the communicator between the kernels (no peer memory there)
@@ -100,17 +106,31 @@ def main():
     flow.assemble(True)
     y = flow.vmult(localise(xg))
     rhs = flow.get_vector(flow.SYSTEM_RHS)
+    extra = {}
+    if model is not None:  # assembly of the transport system at a global state (the fluid's present_solution is 0.5 ev)
+        nu0 = 1e-3 * (1.5 + np.sin(0.37 * np.arange(n_pn_glob)))
+        model.set_vector(model.PRESENT, nu0[gp])
+        model.set_vector(model.EVALUATION_POINT, 1.1 * nu0[gp])
+        model.assemble(True)
+        n_own_p = flow.partition(1)[0]
+        extra = dict(glo_p=gp[:n_own_p], sa_rhs=model.get_vector(model.SYSTEM_RHS)[:n_own_p])
+        model.set_vector(model.PRESENT, np.full(gp.size, 3e-3))
+        model.update_boundary_condition(True)  # restores the boundary lines (no cell is inside a solid here)
     zero = np.zeros(flow.n_dofs)
     flow.set_vector(flow.EVALUATION_POINT, zero)
     flow.set_vector(flow.PRESENT, zero)
     for k in range(2):
+        if model is not None:
+            model.run_one_step(k == 0)
         if solver == "InsIMEX":
             flow.run_one_step(k == 0, k < 2)
         else:
             flow.run_one_step(k == 0)
     sol = flow.get_current_solution()
     hist = np.array([(h["timestep"], h["iteration"], h["abs_res"], h["gmres_its"]) for h in flow.history()], dtype=np.float64)
-    np.savez(out, glo=glo, y=y[loc], rhs=rhs[loc], sol=sol[loc], hist=hist, n_u=dim * n_un_glob)
+    if model is not None:
+        extra["nu"] = model.get_vector(model.PRESENT)[:extra["glo_p"].size]
+    np.savez(out, glo=glo, y=y[loc], rhs=rhs[loc], sol=sol[loc], hist=hist, n_u=dim * n_un_glob, **extra)
     if size > 1:
         ifem.comm_finalize()
 

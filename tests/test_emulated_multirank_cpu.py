@@ -38,6 +38,12 @@ def _run(size, solver, dim, reps, tmp_path):
         y[r["glo"]], rhs[r["glo"]], sol[r["glo"]] = r["y"], r["rhs"], r["sol"]
         seen[r["glo"]] += 1
     assert np.all(seen == 1)  # the owned dofs of the ranks tile the global vector exactly once
+    if "nu" in res[0]:  # turbulence model attached: its right-hand side and nu~ over the owned scalar nodes
+        n_p = sum(r["glo_p"].size for r in res)
+        sa_rhs, nu = np.zeros(n_p), np.zeros(n_p)
+        for r in res:
+            sa_rhs[r["glo_p"]], nu[r["glo_p"]] = r["sa_rhs"], r["nu"]
+        return y, rhs, sol, res[0]["hist"], int(res[0]["n_u"]), (sa_rhs, nu)
     if "solid" in res[0]:
         for r in res[1:]:  # the solid is replicated: every rank must hold the same displacement
             assert np.array_equal(r["solid"], res[0]["solid"])
@@ -76,6 +82,20 @@ def test_two_ranks_match_one_rank_on_the_emulated_device(emulated_library, solve
     if solver.split(":")[0] in ("InsIM", "InsIMEX"):  # closed cavity: pressure up to a constant
         p2, p1 = p2 - p2.mean(), p1 - p1.mean()
     assert rel(p2, p1) < 1e-6
+
+
+@pytest.mark.parametrize("dim,reps", [(2, (6, 10)), pytest.param(3, (3, 3, 8), marks=SLOW)])
+def test_two_ranks_with_the_turbulence_model_on_the_emulated_device(emulated_library, dim, reps, tmp_path):
+    """Spalart-Allmaras model attached to SCnsIM on two ranks: owner-computes assembly of the transport system (ghost values of
+    nu~ and of the fluid velocity through the halos), FGMRES with all-reduced dot products, eddy viscosity read by the fluid's
+    cell kernel on every rank"""
+    y1, rhs1, sol1, h1, nu, (sa_rhs1, nu1) = _run(1, "SCnsIM:sa", dim, reps, tmp_path)
+    y2, rhs2, sol2, h2, _, (sa_rhs2, nu2) = _run(2, "SCnsIM:sa", dim, reps, tmp_path)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(sa_rhs2, sa_rhs1) < 1e-13 and rel(rhs2, rhs1) < 1e-13
+    assert nu1.max() > 1e-3 and rel(nu2, nu1) < 1e-6
+    assert rel(sol2[:nu], sol1[:nu]) < 1e-6 and rel(sol2[nu:], sol1[nu:]) < 1e-6
+    assert h1.shape == h2.shape and np.array_equal(h1[:, :2], h2[:, :2])
 
 
 # (both variants run on two B200s with NCCL in tests/test_ins_multigpu.py::test_coupled_fsi_two_ranks_match_one_rank)

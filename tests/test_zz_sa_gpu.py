@@ -177,3 +177,42 @@ def test_unknown_model_is_rejected():
     o, g, to, tg = _make(2)
     with pytest.raises(ifem.IfemError):
         g.attach_turbulence_model("k-epsilon")
+
+
+def test_coupled_fsi_steps_with_the_model():
+    """MPI::FSI::run with a turbulence model attached to the fluid solver (source/mpi_fsi.cpp:1199-1210): per pass the model's lines
+    are re-made, the cells inside the solid get nu~ -> 0, the model steps, then the fluid steps with the eddy viscosity"""
+    import openifem_b200 as ifem
+    from oracle import fem, fsi, prm, scns, solid
+    from test_fsi_gpu import _fsi_text
+
+    dim, f_reps, s_reps, s_lo, s_hi = 2, (12, 12), (4, 6), (0.3125, 0.0), (0.5625, 0.6875)
+    text = _fsi_text(dim) + SA
+    lo, hi = (0.0,) * dim, (1.0,) * dim
+    P = prm.Params(text, is_text=True)
+    o_fluid = scns.SCnsIM(fem.BoxMesh(f_reps, lo, hi), P)
+    to = o_fluid.attach_turbulence_model("Spalart-Allmaras")
+    o_solid = solid.HyperElasticity(fem.BoxMesh(s_reps, s_lo, s_hi), P)
+    ftria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(ftria, f_reps, lo, hi, True)
+    params = ifem.Parameters.AllParameters(text=text)
+    fluid = ifem.Fluid.MPI.SCnsIM(ftria, params)
+    tg = fluid.attach_turbulence_model("Spalart-Allmaras")
+    fluid.setup()
+    fluid.set_control(fgmres_rel=1e-10)
+    stria = ifem.Triangulation(dim)
+    ifem.GridGenerator.subdivided_hyper_rectangle(stria, s_reps, s_lo, s_hi, True)
+    sol = ifem.Solid.MPI.HyperElasticity(stria, params)
+    sol.setup()
+    coupling = ifem.MPI.FSI(fluid, sol, params, False)
+    loop = fsi.FSI(o_fluid, o_solid, False)
+    for k in range(2):
+        loop.run_one_step(k == 0)
+        coupling.run_one_step(k == 0)
+    inside = np.unique(to.nodes[o_fluid.indicator == 1])
+    x = tg.get_vector(tg.PRESENT)
+    assert inside.size and np.abs(x[inside]).max() < 1e-18 and x.max() > 0
+    assert _rel(x, to.present) < 1e-6
+    fsol = fluid.get_current_solution()
+    assert _rel(fsol[: o_fluid.n_u], o_fluid.velocity()) < 1e-6 and _rel(fsol[o_fluid.n_u:], o_fluid.pressure()) < 1e-6
+    assert _rel(sol.get_current_solution(), o_solid.cur_u) < 1e-6

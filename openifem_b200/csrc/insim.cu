@@ -126,24 +126,29 @@ namespace ifem
 
   void InsIM::after_mesh_change(const Triangulation::TransferPlan &plan, const std::vector<double> &old_vertices)
   {
-    if (after_make_constraints) // pre_refine_mesh / post_refine_mesh of the turbulence model (mpi_spalart_allmaras.cpp:594-617)
-      throw std::runtime_error("refine_mesh with an attached turbulence model is not built");
     if (fs.pu != 1 || fs.pp != 1) throw std::runtime_error("refine_mesh: solution transfer is implemented for FE_Q(1) velocity and pressure");
     const int dim = fs.dim;
     // old solution per old vertex: every rank contributes the nodes it owns (the triangulation is replicated, the solution is not)
     const int64_t n_old_u = fs.n_u;
     const std::vector<double> old = present_solution.to_host(ctx.stream);
     const int nv_old = (int)(old_vertices.size() / dim);
-    std::vector<double> vert_val((size_t)nv_old * (dim + 1), 0.0);
+    std::vector<std::vector<double>> old_extra;
+    for (DevBuf<double> *f : transferred_scalar_fields()) old_extra.push_back(f->to_host(ctx.stream));
+    const int stride = dim + 1 + (int)old_extra.size(); // per vertex: velocity, pressure, the extra scalar fields
+    std::vector<double> vert_val((size_t)nv_old * stride, 0.0);
     {
       const CoordLookup vertex_at(dim, old_vertices, old_vertices);
       for (int l = 0; l < fs.n_owned_unodes; ++l)
         {
           const int v = vertex_at.find(&fs.un.coords[(size_t)l * dim]);
-          for (int c = 0; c < dim; ++c) vert_val[(size_t)v * (dim + 1) + c] = old[(size_t)dim * l + c];
+          for (int c = 0; c < dim; ++c) vert_val[(size_t)v * stride + c] = old[(size_t)dim * l + c];
         }
       for (int l = 0; l < fs.n_owned_pnodes; ++l)
-        vert_val[(size_t)vertex_at.find(&fs.pn.coords[(size_t)l * dim]) * (dim + 1) + dim] = old[(size_t)n_old_u + l];
+        {
+          const size_t v = (size_t)vertex_at.find(&fs.pn.coords[(size_t)l * dim]);
+          vert_val[v * stride + dim] = old[(size_t)n_old_u + l];
+          for (size_t e = 0; e < old_extra.size(); ++e) vert_val[v * stride + dim + 1 + e] = old_extra[e][l];
+        }
       if (fs.n_ranks > 1)
         {
           DevBuf<double> d(vert_val.size());
@@ -155,6 +160,7 @@ namespace ifem
     }
     // new spaces (on several ranks: a new partition of the new mesh)
     fs.base_valid = false;
+    if (on_mesh_change) on_mesh_change();
     setup_dofs();
     make_constraints();
     initialize_system();
@@ -165,13 +171,20 @@ namespace ifem
     auto value = [&](const double *x, int c) {
       const int v = vertex_at.find(x);
       double val = 0.0;
-      for (int64_t k = plan.ptr[v]; k < plan.ptr[v + 1]; ++k) val += plan.weight[k] * vert_val[(size_t)plan.old_vertex[k] * (dim + 1) + c];
+      for (int64_t k = plan.ptr[v]; k < plan.ptr[v + 1]; ++k) val += plan.weight[k] * vert_val[(size_t)plan.old_vertex[k] * stride + c];
       return val;
     };
     for (int l = 0; l < fs.un.n_nodes; ++l) // owned and ghost nodes alike
       for (int c = 0; c < dim; ++c) fresh[(size_t)dim * l + c] = value(&fs.un.coords[(size_t)l * dim], c);
     for (int l = 0; l < fs.pn.n_nodes; ++l) fresh[(size_t)fs.n_u + l] = value(&fs.pn.coords[(size_t)l * dim], dim);
     present_solution.upload(fresh, ctx.stream);
+    const std::vector<DevBuf<double> *> extra = transferred_scalar_fields();
+    for (size_t e = 0; e < extra.size() && e < old_extra.size(); ++e)
+      {
+        std::vector<double> field((size_t)fs.pn.n_nodes);
+        for (int l = 0; l < fs.pn.n_nodes; ++l) field[l] = value(&fs.pn.coords[(size_t)l * dim], dim + 1 + (int)e);
+        extra[e]->upload(field, ctx.stream);
+      }
     IFEM_CUDA(cudaStreamSynchronize(ctx.stream));
   }
 

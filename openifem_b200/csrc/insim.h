@@ -150,6 +150,11 @@ namespace ifem
     bool dofs_ready = false;
     // called at the end of make_constraints(): an attached turbulence model re-makes its own lines (mpi_fluid_solver.cpp:276-279)
     std::function<void()> after_make_constraints;
+    // refine_mesh: further scalar nodal fields (pressure-node numbering) carried to the new mesh with present_solution - nu~ of an
+    // attached turbulence model (pre_refine_mesh / post_refine_mesh, source/mpi_spalart_allmaras.cpp:594-617); on_mesh_change
+    // runs before the new spaces are set up
+    virtual std::vector<DevBuf<double> *> transferred_scalar_fields() { return {}; }
+    std::function<void()> on_mesh_change;
 
   protected:
     void io_before_step(); // output of step 0

@@ -552,6 +552,7 @@ namespace ifem
     if (model_name != "Spalart-Allmaras") throw std::runtime_error("attach_turbulence_model: model <" + model_name + "> is not implemented");
     turbulence_model = std::make_unique<SpalartAllmaras>(ctx, *this);
     after_make_constraints = [this] { turbulence_model->make_constraints(); };
+    on_mesh_change = [this] { turbulence_model->mesh_changed(); };
     if (dofs_ready) // attached after setup: what make_constraints() / initialize_system() would have done (mpi_supg_solver.cpp:290-293)
       {
         turbulence_model->make_constraints();

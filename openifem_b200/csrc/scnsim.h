@@ -43,6 +43,11 @@ namespace ifem
     // "Spalart-Allmaras" only, source/mpi_turbulence_model.cpp:11-26). Before or after setup.
     void attach_turbulence_model(const std::string &model_name);
     std::unique_ptr<SpalartAllmaras> turbulence_model;
+    std::vector<DevBuf<double> *> transferred_scalar_fields() override
+    {
+      if (turbulence_model && turbulence_model->ready) return {&turbulence_model->present_solution};
+      return {};
+    }
 
   protected:
     void precondition_supg(const double *src, double *dst);

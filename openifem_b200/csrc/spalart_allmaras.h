@@ -50,6 +50,14 @@ namespace ifem
     void run_one_step(bool apply_nonzero_constraints);                   // :296-349
     void update_eddy_viscosity();                                        // :864-889
     double get_shear_velocity(double vel, double init_guess) const;      // :227-293
+    // refine_mesh: the cached lines and the ILU analysis belong to the old mesh. nu~ itself travels with the fluid's solution
+    // (InsIM::after_mesh_change = pre_refine_mesh / post_refine_mesh, :594-617); the eddy viscosity restarts from zero until the
+    // next model step, as TurbulenceModel::initialize_system leaves it (source/mpi_turbulence_model.cpp:123-125)
+    void mesh_changed()
+    {
+      constraints_made = false;
+      ilu = Ilu0();
+    }
 
     Context &ctx;
     SCnsIM &fluid;

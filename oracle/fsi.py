@@ -430,6 +430,14 @@ class FSI:
                 for comp in range(n_comp):
                     new.present[off_new + n_comp * n + comp] = N @ old[off_old + n_comp * nodes_old[cell] + comp]
         new.time, new.timestep, new.history, new.bc_time = f.time, f.timestep, f.history, f.bc_time
+        if getattr(f, "turbulence_model", None) is not None:
+            # pre_refine_mesh / post_refine_mesh of the turbulence model (mpi_fsi.cpp:1093-1096, 1113-1116): nu~ travels like the
+            # fluid's solution; the model is re-initialised on the new mesh first (mpi_supg_solver.cpp:290-293)
+            tm_old, tm = f.turbulence_model, new.attach_turbulence_model("Spalart-Allmaras")
+            for n, p in enumerate(new.dofs.ucoords):
+                cell, xi = locate_in_fluid(old_mesh, p)
+                tm.present[n] = feu.eval(xi[None, :])[0][0] @ tm_old.present[old_d.unodes[cell]]
+            tm.history = tm_old.history
         self.fluid = new
         self.base_con, self.base_val = new.con.copy(), new.nonzero_val.copy()
         return new

@@ -216,3 +216,52 @@ def test_coupled_fsi_steps_with_the_model():
     fsol = fluid.get_current_solution()
     assert _rel(fsol[: o_fluid.n_u], o_fluid.velocity()) < 1e-6 and _rel(fsol[o_fluid.n_u:], o_fluid.pressure()) < 1e-6
     assert _rel(sol.get_current_solution(), o_solid.cur_u) < 1e-6
+
+
+def test_refine_mesh_carries_the_model():
+    """FSI::refine_mesh with a turbulence model (source/mpi_fsi.cpp:1093-1096, 1113-1116): nu~ is transferred like the fluid's
+    solution, the model's lines / wall distances / system are rebuilt on the new mesh; coupled steps before and after agree"""
+    import openifem_b200 as ifem
+    from oracle import fem, fsi, prm, scns, solid
+    from test_fsi_gpu import _fsi_text
+
+    reps, s_reps, s_lo, s_hi = (12, 12), (4, 6), (0.3125, 0.0), (0.5625, 0.6875)
+    text = _fsi_text(2) + SA
+    P = prm.Params(text, is_text=True)
+    o_fluid = scns.SCnsIM(fem.BoxMesh(reps, (0.0, 0.0), (1.0, 1.0)), P)
+    o_fluid.attach_turbulence_model("Spalart-Allmaras")
+    o_solid = solid.HyperElasticity(fem.BoxMesh(s_reps, s_lo, s_hi), P)
+    params = ifem.Parameters.AllParameters(text=text)
+    ftria, stria, otria = ifem.Triangulation(2), ifem.Triangulation(2), ifem.Triangulation(2)
+    for t in (ftria, otria):
+        ifem.GridGenerator.subdivided_hyper_rectangle(t, reps, (0.0, 0.0), (1.0, 1.0), True)
+    ifem.GridGenerator.subdivided_hyper_rectangle(stria, s_reps, s_lo, s_hi, True)
+    fluid = ifem.Fluid.MPI.SCnsIM(ftria, params)
+    fluid.setup()
+    tg = fluid.attach_turbulence_model("Spalart-Allmaras")
+    fluid.set_control(fgmres_rel=1e-10)
+    sol = ifem.Solid.MPI.HyperElasticity(stria, params)
+    sol.setup()
+    coupling = ifem.MPI.FSI(fluid, sol, params, False)
+    loop = fsi.FSI(o_fluid, o_solid, False)
+
+    def refine_both():
+        loop.refine_mesh(otria, 0, 2)
+        coupling.refine_mesh(0, 2)
+        assert all(np.array_equal(x, y) for x, y in zip(otria.get_mesh(), ftria.get_mesh()))
+        to = loop.fluid.turbulence_model
+        assert tg.n_dofs == to.n and _rel(tg.get_vector(tg.PRESENT), to.present) < 1e-13
+        assert np.abs(tg.get_vector(tg.WALL_DISTANCE) - to.fixed_wall_distance).max() < 1e-14
+        fluid.set_control(fgmres_rel=1e-10)
+
+    refine_both()
+    assert ftria.hanging()[0].size > 0
+    for k in range(3):
+        loop.run_one_step(k == 0)
+        coupling.run_one_step(k == 0)
+        if k == 1:
+            refine_both()  # nu~ is no longer uniform here: wall and solid lines have acted for two steps
+    of, to = loop.fluid, loop.fluid.turbulence_model
+    fsol = fluid.get_current_solution()
+    assert to.present.max() > 0 and _rel(tg.get_vector(tg.PRESENT), to.present) < 1e-6
+    assert _rel(fsol[: of.n_u], of.velocity()) < 1e-6 and _rel(fsol[of.n_u:], of.pressure()) < 1e-6

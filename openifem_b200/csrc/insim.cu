@@ -436,6 +436,17 @@ namespace ifem
     copy(ctx, n, evaluation_point.p, present_solution.p);
     update_stress(); // mpi_insim.cpp:475
     io_after_step();
+    // mpi_insim.cpp:485-489: a "Fluid" run refines with the Kelly estimator at the refinement interval (FluidSolver::refine_mesh,
+    // mpi_fluid_solver.cpp:417-488). Not built: it leaves hanging nodes on the FE_Q(2) velocity space, which the condensation of
+    // hanging.h does not cover (every reference .prm keeps the interval beyond the end time; the reference's own preconditioner
+    // carries a FIXME about this path, :90-98). Said once instead of silently computing on the unrefined mesh.
+    if (parameters.simulation_type == "Fluid" && time.time_to_refine() && time.end() - time.current() > 1e-12 && !refine_warned)
+      {
+        refine_warned = true;
+        if (fs.rank == 0)
+          std::fprintf(stderr, "openifem_b200: InsIM reached its refinement interval; FluidSolver::refine_mesh (Kelly estimator, FE_Q(2) "
+                               "hanging nodes) is not built - the run continues on the current mesh\n");
+      }
   }
 
   void InsIM::update_stress()

@@ -148,6 +148,7 @@ namespace ifem
     // per-section device time, keyed by the reference's TimerOutput section names
     std::map<std::string, double> timer_ms;
     bool dofs_ready = false;
+    bool refine_warned = false;
     // called at the end of make_constraints(): an attached turbulence model re-makes its own lines (mpi_fluid_solver.cpp:276-279)
     std::function<void()> after_make_constraints;
     // refine_mesh: further scalar nodal fields (pressure-node numbering) carried to the new mesh with present_solution - nu~ of an

@@ -330,6 +330,10 @@ def run_fsi_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# inner T_pp solve on fp32 copies of the blocks: off until measured on hardware
+TPP_FP32_DEFAULT = {4: 0, 5: 0}
+
+
 def fsi_workload(args):
     if args.config == 4:
         return ("fsi_leaflet_mpi (config 4): MPI::FSI<2>(SCnsIM Q1/Q1 on the 80 x 20 channel with the band 0.8 <= x <= 1.3 refined once, "
@@ -368,6 +372,9 @@ def run_fsi(args):
     if args.config == 4:
         fluid.add_hard_coded_boundary_condition(0, leaflet_inflow)
     fluid.setup()
+    tpp_fp32 = args.tpp_fp32 if args.tpp_fp32 >= 0 else TPP_FP32_DEFAULT[args.config]
+    if tpp_fp32:
+        fluid.set_control(a_inv_fp32=1)  # SUPG solvers: the inner T_pp solve streams fp32 copies of A_vp / A_pv / A_pp
     solid = ifem.Solid.MPI.SharedHyperElasticity(stria, params)
     solid.setup()
     coupling = ifem.MPI.FSI(fluid, solid, params, args.config == 4)
@@ -453,6 +460,7 @@ def run_fsi(args):
                    "parallelism": f"{world} slab(s) of the fluid along mesh planes, one rank per GPU; the solid is replicated; NCCL: ghost halos, "
                                   "dot products and the sum of the solid-side interpolation",
                    "setup_s": round(t_setup, 1),
+                   "tpp_fp32": int(tpp_fp32),
                    "section_ms_per_step": {**sec, **{"fluid: " + k: v for k, v in fsec.items()}},
                    "newton_its_per_step": len(hist) / max(1, args.steps),
                    "fgmres_its": [h["gmres_its"] for h in hist], "inner_tpp_its": [h["a_inv_its"] for h in hist]},
@@ -693,6 +701,8 @@ def main():
     ap.add_argument("--solid-scale", type=int, default=1, help="config 5: factor on the {20,20,8} solid subdivisions")
     ap.add_argument("--refine", type=int, default=2, help="config 2: Global refinements of the cylinder mesh")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tpp-fp32", type=int, default=-1, choices=[-1, 0, 1],
+                    help="configs 4 / 5: inner T_pp solve of the SUPG block preconditioner on fp32 copies of the blocks (-1: the config's default)")
     ap.add_argument("--ref-cells", default="24,32,48",
                     help="--impl reference: cells per direction of the timed samples (the fit is extrapolated to --cells)")
     ap.add_argument("--sm-mode", type=int, default=1, choices=[0, 1, 2],

@@ -405,6 +405,32 @@ namespace ifem
         ctx.kernel_launches++;
         return;
       }
+    if (key == 31 || key == 13 || key == 11)
+      {
+        // the off-diagonal and pressure blocks of an equal-order system (short rows): the 16-lane row kernel that is the fp64 default
+        // for these shapes (profiles/r02_spmv_short_sweep.txt), reading the padded fp32 copy
+        const int64_t nblk = ((int64_t)n_rows * 16 + 255) / 256;
+        if (key == 31)
+          bcsr_spmv_row_kernel<3, 1, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
+        else if (key == 13)
+          bcsr_spmv_row_kernel<1, 3, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
+        else
+          bcsr_spmv_row_kernel<1, 1, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+        return;
+      }
+    if (key == 21 || key == 12)
+      {
+        const int64_t nblk = ((int64_t)n_rows * 16 + 255) / 256;
+        if (key == 21)
+          bcsr_spmv_row_kernel<2, 1, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
+        else
+          bcsr_spmv_row_kernel<1, 2, 16, float, 1, 4><<<(unsigned)nblk, 256, 0, ctx.stream>>>(n_rows, A.rowptr32.p, A.col32.p, A.val32.p, x, y, 0);
+        IFEM_KERNEL_CHECK();
+        ctx.kernel_launches++;
+        return;
+      }
     auto launch = [&](auto r_tag, auto tpr_tag, auto m_tag) {
       constexpr int RR = decltype(r_tag)::value, T = decltype(tpr_tag)::value, M = decltype(m_tag)::value;
       const int rpw = std::max(1, ctx.spmv_rpw);

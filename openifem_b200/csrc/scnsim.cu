@@ -364,6 +364,252 @@ namespace ifem
         }
     }
 
+
+    // 3-D default: variant 1 - 18.3 ms against 42.7 ms per assembly of 435 200 cells on a B200, results equal to 1e-16
+    // (profiles/r02_scns_asm_variants.json); the 2-D kernel (1 ms per assembly at config 4) keeps the original until it is measured
+    constexpr int kScnsAssembleVariant = 1;
+
+    template <int V>
+    struct Divisor
+    {
+      double d, inv;
+    };
+    template <int V>
+    __device__ __forceinline__ double operator*(double x, const Divisor<V> &r)
+    {
+      return V ? x * r.inv : x / r.d;
+    }
+
+    template <int DIM, int V, int MINB>
+    __global__ void __launch_bounds__(64, MINB) scns_assemble_v1_kernel(const ScnsArgs A)
+    {
+      constexpr int NU = 1 << DIM, NQ = NU, PAIRS = NU * NU, CPB = 64 / PAIRS, D1 = DIM + 1, DPC = NU * D1;
+      __shared__ QPoint<DIM> sq[CPB][NQ];
+      __shared__ double lrhs[CPB][DPC], ldiag[CPB][DPC];
+      const int cl = threadIdx.x / PAIRS, pr = threadIdx.x % PAIRS;
+      const int li = blockIdx.x * CPB + cl;
+      const bool active = li < A.n_list;
+      const int cell = active ? A.cell_list[li] : 0;
+      const int ind = (active && A.indicator) ? A.indicator[cell] : 0;
+      if (active && pr < NQ) fill_qpoint<DIM>(A, cell, pr, ind, sq[cl][pr]);
+      if (active && pr < DPC)
+        {
+          lrhs[cl][pr] = 0.0;
+          ldiag[cl][pr] = 0.0;
+        }
+      __syncthreads();
+      if (!active) return;
+      const int a = pr / NU, b = pr % NU;
+      const double cp = kCpToCv, atm = kAtm, om = 1.0 - ind;
+      const Divisor<V> idt{A.dt, 1.0 / A.dt}, iatm{kAtm, 1.0 / kAtm}, iks{kKappaS, 1.0 / kKappaS};
+      double K[D1][D1], r[D1];
+#pragma unroll
+      for (int i = 0; i < D1; ++i)
+        {
+          r[i] = 0.0;
+#pragma unroll
+          for (int j = 0; j < D1; ++j) K[i][j] = 0.0;
+        }
+      for (int q = 0; q < NQ; ++q)
+        {
+          const QPoint<DIM> &Q = sq[cl][q];
+          const double w = Q.JxW, Na = Q.N[a], Nb = Q.N[b], rho = Q.rho, ts = Q.tau_supg, tp = Q.tau_pspg, tl = Q.tau_lsic;
+          const double *ga = Q.g[a], *gb = Q.g[b];
+          const double gagb = dotd<DIM>(ga, gb), ugb = dotd<DIM>(Q.u, gb);
+          // ga . X for the vectors that meet "phi_u[j] * grad_phi_u[i]" (only when the components agree)
+          const double ga_ugu = dotd<DIM>(ga, Q.u_gradu), ga_dv = dotd<DIM>(ga, Q.dv), ga_gp = dotd<DIM>(ga, Q.gradp),
+                       ga_sd = dotd<DIM>(ga, Q.sdiv), ga_bf = dotd<DIM>(ga, Q.g_bf), ga_u = dotd<DIM>(ga, Q.u), ga_acc = dotd<DIM>(ga, Q.acc);
+          const double same = ts * rho * Nb * ga_ugu + ts * rho * Nb * ga_dv * idt + ts * Nb * ga_gp - ts * Nb * ga_sd - ts * Nb * ga_bf * rho +
+                              ts * rho * Nb * ga_u * Q.sigma - (ind == 1 ? ts * Nb * ga_acc * rho : 0.0);
+#pragma unroll
+          for (int c = 0; c < DIM; ++c)
+            {
+              const double uc = Q.u[c];
+              // ---- velocity test (a,c) x velocity trial (b,d) ----
+#pragma unroll
+              for (int d = 0; d < DIM; ++d)
+                {
+                  double m = rho * Q.G[c * DIM + d] * Nb * Na;                      // (grad u phi_j) . phi_i
+                  m += ts * rho * uc * Nb * dotd<DIM>(ga, &Q.G[d * DIM]);            // SUPG: (u grad phi_i).(phi_j grad u)
+                  m += ts * rho * uc * Q.u[d] * gagb;                                // SUPG: (u grad phi_i).(u grad phi_j)
+                  m += ts * rho * uc * ga[d] * Nb * idt;                              // SUPG acceleration
+                  m += ts * rho * uc * ga[d] * Nb * Q.sigma;                         // SUPG PML
+                  m += tl * rho * cp * ga[c] * gb[d] * (1.0 + Q.p * om * iatm);       // LSIC velocity divergence (2 terms)
+                  m += tl * rho * ga[c] * Nb * Q.gradp[d] * iatm * om;                // LSIC pressure gradient (phi_j . grad p)
+                  if (c == d)
+                    m += Q.visc * gagb + rho * ugb * Na + rho * Na * Nb * idt + rho * Q.sigma * Nb * Na + same;
+                  K[c][d] = fma(m, w, K[c][d]);
+                }
+              // ---- velocity test (a,c) x pressure trial b ----
+              {
+                double m = -ga[c] * Nb + ts * uc * gagb;
+                m += tl * rho * ga[c] * Nb * idt * om * iatm + tl * rho * iks * ga[c] * Nb * idt * ind;
+                m += tl * rho * cp * ga[c] * Nb * om * Q.divu * iatm + tl * rho * ga[c] * ugb * iatm * om;
+                K[c][DIM] = fma(m, w, K[c][DIM]);
+              }
+              // ---- pressure test a x velocity trial (b,c) ----
+              {
+                double m = tp * rho * Nb * dotd<DIM>(ga, &Q.G[c * DIM]) + tp * rho * Q.u[c] * gagb + tp * rho * ga[c] * Nb * idt +
+                           tp * rho * ga[c] * Nb * Q.sigma;
+                m += (cp * (atm + Q.p * om) * gb[c] * Na + Nb * Q.gradp[c] * Na * om) * iatm;
+                K[DIM][c] = fma(m, w, K[DIM][c]);
+              }
+              if (b == 0)
+                {
+                  // rhs of velocity row (a,c) (:429-512)
+                  double v = -Q.visc * dotd<DIM>(&Q.G[c * DIM], ga) - rho * Q.gradu_u[c] * Na + Q.p * ga[c] - rho * Q.dv[c] * Na * idt +
+                             Q.g_bf[c] * Na * rho;
+                  v += -rho * Q.sigma * uc * Na;
+                  v += -ts * uc * dotd<DIM>(ga, Q.res);
+                  v += -(tl * rho * ga[c]) * ((Q.dp * idt * om + cp * atm * Q.divu + cp * Q.p * Q.divu * om + dotd<DIM>(Q.u, Q.gradp) * om) * iatm +
+                                              (1 * iks * Q.dp * idt) * ind);
+                  if (ind == 1) v += dotd<DIM>(ga, &Q.fsis[c * DIM]) + rho * (Q.acc[c] * Na + ts * uc * ga_acc);
+                  r[c] = fma(v, w, r[c]);
+                }
+            }
+          // ---- pressure test a x pressure trial b ----
+          {
+            double m = Q.sigma * Nb * Na * iatm + tp * gagb;
+            m += (Nb * Q.divu * Na * om + ugb * Na * om + Na * Nb * idt * om) * iatm + 1 * iks * Na * Nb * ind * idt;
+            K[DIM][DIM] = fma(m, w, K[DIM][DIM]);
+          }
+          if (b == 0)
+            {
+              double v = -Q.sigma * Q.p * Na * iatm;
+              v += -(cp * (atm + Q.p * om) * Q.divu * Na + dotd<DIM>(Q.u, Q.gradp) * Na * om + Q.dp * Na * idt * om) * iatm - 1 * iks * Q.dp * Na * ind * idt;
+              v += -tp * dotd<DIM>(ga, Q.res);
+              if (ind == 1) v += rho * tp * ga_acc;
+              r[DIM] = fma(v, w, r[DIM]);
+            }
+        }
+      // ---- scatter through the constraints (distribute_local_to_global, :548-560) ----
+      constexpr int SPC = 4 * PAIRS; // uu | up | pu | pp slot tables, NU x NU each
+      const unsigned char *slots = A.slots + (int64_t)cell * SPC;
+      const int nAu = A.cell_un[(int64_t)cell * NU + a], nBu = A.cell_un[(int64_t)cell * NU + b];
+      const int nAp = A.cell_pn[(int64_t)cell * NU + a], nBp = A.cell_pn[(int64_t)cell * NU + b];
+      int rcon[D1], ccon[D1];
+      double cinh[D1];
+#pragma unroll
+      for (int c = 0; c < DIM; ++c)
+        {
+          rcon[c] = A.con[(int64_t)DIM * nAu + c];
+          ccon[c] = A.con[(int64_t)DIM * nBu + c];
+          cinh[c] = (ccon[c] && A.inhom) ? A.inhom[(int64_t)DIM * nBu + c] : 0.0;
+        }
+      rcon[DIM] = A.con[A.n_u + nAp];
+      ccon[DIM] = A.con[A.n_u + nBp];
+      cinh[DIM] = (ccon[DIM] && A.inhom) ? A.inhom[A.n_u + nBp] : 0.0;
+      const bool own_u = nAu < A.n_owned_u, own_p = nAp < A.n_owned_p;
+      // row pointers of the four blocks
+      const int64_t uu0 = own_u ? A.uu_rp[nAu] : 0, up0 = own_u ? A.up_rp[nAu] : 0, pu0 = own_p ? A.pu_rp[nAp] : 0, pp0 = own_p ? A.pp_rp[nAp] : 0;
+      const int uun = own_u ? (int)(A.uu_rp[nAu + 1] - uu0) : 0, upn = own_u ? (int)(A.up_rp[nAu + 1] - up0) : 0;
+      const int pun = own_p ? (int)(A.pu_rp[nAp + 1] - pu0) : 0;
+      const int s_uu = slots[pr], s_up = slots[PAIRS + pr], s_pu = slots[2 * PAIRS + pr], s_pp = slots[3 * PAIRS + pr];
+      // where entry (i, j) of this thread's block goes (nullptr: not stored)
+      auto target = [&](int i, int j) -> double * {
+        if (i < DIM && j < DIM) return A.uu + uu0 * DIM * DIM + (int64_t)(i * DIM + j) * uun + s_uu;
+        if (i < DIM) return A.up + up0 * DIM + (int64_t)i * upn + s_up;
+        if (j < DIM) return A.pu + pu0 * DIM + (int64_t)j * pun + s_pu;
+        return A.pp + pp0 + s_pp;
+      };
+      if (V == 0)
+        {
+#pragma unroll
+          for (int i = 0; i < D1; ++i)
+            {
+              const bool own = i < DIM ? own_u : own_p;
+              if (!own) continue;
+              double corr = 0.0;
+#pragma unroll
+              for (int j = 0; j < D1; ++j)
+                {
+                  const double v = K[i][j];
+                  if (rcon[i])
+                    {
+                      if (a == b && i == j)
+                        {
+                          const double dv = fabs(v);
+                          *target(i, j) += dv;
+                          ldiag[cl][a * D1 + i] = dv;
+                        }
+                      continue;
+                    }
+                  if (ccon[j])
+                    {
+                      corr = fma(v, cinh[j], corr);
+                      continue;
+                    }
+                  *target(i, j) += v;
+                }
+              if (!rcon[i])
+                {
+                  double add = -corr;
+                  if (b == 0) add += r[i];
+                  if (add != 0.0) atomicAdd(&lrhs[cl][a * D1 + i], add);
+                }
+            }
+        }
+      else
+        {
+          // pass 1: decide per entry (stored value in K, bit in `store`), right-hand side corrections
+          unsigned store = 0;
+#pragma unroll
+          for (int i = 0; i < D1; ++i)
+            {
+              const bool own = i < DIM ? own_u : own_p;
+              if (!own) continue;
+              double corr = 0.0;
+#pragma unroll
+              for (int j = 0; j < D1; ++j)
+                {
+                  if (rcon[i])
+                    {
+                      if (a == b && i == j)
+                        {
+                          K[i][j] = fabs(K[i][j]);
+                          ldiag[cl][a * D1 + i] = K[i][j];
+                          store |= 1u << (i * D1 + j);
+                        }
+                    }
+                  else if (ccon[j])
+                    corr = fma(K[i][j], cinh[j], corr);
+                  else
+                    store |= 1u << (i * D1 + j);
+                }
+              if (!rcon[i])
+                {
+                  double add = -corr;
+                  if (b == 0) add += r[i];
+                  if (add != 0.0) atomicAdd(&lrhs[cl][a * D1 + i], add);
+                }
+            }
+          // pass 2: all loads, then all stores
+          double cur[D1][D1];
+#pragma unroll
+          for (int i = 0; i < D1; ++i)
+#pragma unroll
+            for (int j = 0; j < D1; ++j) cur[i][j] = (store >> (i * D1 + j)) & 1u ? *target(i, j) : 0.0;
+#pragma unroll
+          for (int i = 0; i < D1; ++i)
+#pragma unroll
+            for (int j = 0; j < D1; ++j)
+              if ((store >> (i * D1 + j)) & 1u) *target(i, j) = cur[i][j] + K[i][j];
+        }
+      __syncthreads();
+      if (pr < DPC)
+        {
+          const int aa = pr / D1, i = pr % D1;
+          const int nu_ = A.cell_un[(int64_t)cell * NU + aa], np_ = A.cell_pn[(int64_t)cell * NU + aa];
+          const bool own = i < DIM ? nu_ < A.n_owned_u : np_ < A.n_owned_p;
+          const int64_t g = i < DIM ? (int64_t)DIM * nu_ + i : A.n_u + np_;
+          if (own)
+            {
+              if (!A.con[g]) A.rhs[g] += lrhs[cl][pr];
+              else if (A.inhom) A.rhs[g] += ldiag[cl][pr] * A.inhom[g];
+            }
+        }
+    }
+
     // rowsum(|A_vv|)^-1 per velocity dof (mpi_supg_solver.cpp:68-118)
     template <int DIM>
     __global__ void abs_rowsum_inv_kernel(int n_brows, const int64_t *__restrict__ rp, const double *__restrict__ val, double *__restrict__ out)
@@ -636,13 +882,26 @@ namespace ifem
     a.pp = fs.A_pp.val.p;
     a.rhs = fs.rhs.p;
     const int n_colours = (int)fs.colour_offsets.size() - 1;
+    // kernel variant (see scns_assemble_kernel): IFEM_SCNS_ASM = 0 / 1 overrides the default
+    const char *env = std::getenv("IFEM_SCNS_ASM");
+    const int variant = env ? std::atoi(env) : (dim == 3 ? kScnsAssembleVariant : 0);
     for (int k = 0; k < n_colours; ++k)
       {
         a.n_list = fs.colour_offsets[k + 1] - fs.colour_offsets[k];
         a.cell_list = fs.d_colour_order.p + fs.colour_offsets[k];
         if (!a.n_list) continue;
-        if (dim == 2)
+        if (dim == 2 && variant)
+          scns_assemble_v1_kernel<2, 1, 7><<<(a.n_list + 3) / 4, 64, 0, s>>>(a);
+        else if (dim == 2)
           scns_assemble_kernel<2><<<(a.n_list + 3) / 4, 64, 0, s>>>(a);
+        else if (variant == 2) // variant 1 held to 128 registers: 8 CTAs per SM instead of 6
+          scns_assemble_v1_kernel<3, 1, 8><<<a.n_list, 64, 0, s>>>(a);
+        else if (variant == 3) // variant 1 with the register allocation left to the compiler (5 CTAs per SM)
+          scns_assemble_v1_kernel<3, 1, 1><<<a.n_list, 64, 0, s>>>(a);
+        else if (variant == 4) // the reference arithmetic (divisions) with the batched scatter only
+          scns_assemble_v1_kernel<3, 0, 1><<<a.n_list, 64, 0, s>>>(a);
+        else if (variant)
+          scns_assemble_v1_kernel<3, 1, 6><<<a.n_list, 64, 0, s>>>(a);
         else
           scns_assemble_kernel<3><<<a.n_list, 64, 0, s>>>(a);
         IFEM_KERNEL_CHECK();
@@ -681,13 +940,17 @@ namespace ifem
     // dst_p = T_pp^-1 ptmp,  T_pp = A_pp - A_pv P_vv^-1 A_vp  (matrix-free, :20-32)
     {
       ScopedTimer t(ctx, timer_ms["Solving Tpp"]);
+      // control.a_inv_fp32 != 0: the three products of the INNER solve stream fp32 copies of the blocks (x, y and the sums stay
+      // fp64). T_pp^-1 is applied to 1e-3 inside a preconditioner of a flexible GMRES - the perturbation of the operator (6e-8
+      // relative per entry) is far below that; the outer operator, residuals and bases stay fp64
+      const bool f32 = control.a_inv_fp32 != 0 && fs.A_up.val32.p != nullptr;
       LinOp Tpp = [&](const double *x, double *y) {
         fs.halo_p.update(ctx, const_cast<double *>(x));
-        spmv(ctx, fs.A_up, x, d_ut2.p);
+        if (f32) spmv_fp32(ctx, fs.A_up, x, d_ut2.p); else spmv(ctx, fs.A_up, x, d_ut2.p);
         Pvv(d_ut2.p, d_ut1.p);
         fs.halo_u.update(ctx, d_ut1.p);
-        spmv(ctx, fs.A_pu, d_ut1.p, d_pt2.p);
-        spmv(ctx, fs.A_pp, x, y);
+        if (f32) spmv_fp32(ctx, fs.A_pu, d_ut1.p, d_pt2.p); else spmv(ctx, fs.A_pu, d_ut1.p, d_pt2.p);
+        if (f32) spmv_fp32(ctx, fs.A_pp, x, y); else spmv(ctx, fs.A_pp, x, y);
         axpy(ctx, vp, -1.0, d_pt2.p, y);
       };
       LinOp B2 = [&](const double *x, double *y) {
@@ -758,6 +1021,12 @@ namespace ifem
         IFEM_KERNEL_CHECK();
         ctx.kernel_launches++;
         ilu_b2.factor(ctx);
+      }
+    if (control.a_inv_fp32 != 0) // fp32 copies of the blocks the inner T_pp solve streams (precondition_supg)
+      {
+        make_fp32_copy(ctx, fs.A_up);
+        make_fp32_copy(ctx, fs.A_pu);
+        make_fp32_copy(ctx, fs.A_pp);
       }
     const VecSpace &va = fs.vs_all;
     const double nrm = nrm2(ctx, va, fs.rhs.p);

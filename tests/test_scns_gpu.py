@@ -159,6 +159,28 @@ def test_scns_time_steps_match_oracle(dim, reps, hi):
     assert [(h["timestep"], h["iteration"]) for h in g.history()] == [(h[0], h[1]) for h in o.history]
 
 
+@pytest.mark.parametrize("dim,reps,hi", [(2, (6, 5), (1.0, 0.8)), (3, (3, 4, 3), (1.0, 1.2, 0.9))])
+@pytest.mark.parametrize("ilu", [0, 1])
+def test_inner_tpp_solve_on_fp32_blocks(dim, reps, hi, ilu):
+    """control.a_inv_fp32 = 1 on a SUPG solver: the products of the INNER T_pp solve (1e-3, inside the preconditioner of a flexible
+    GMRES) stream fp32 copies of A_vp / A_pv / A_pp; operator, residuals and Krylov bases of the outer solve stay fp64, so the
+    converged fields agree with the oracle to the same 1e-6 and the outer iteration counts do not move"""
+    text = scns_prm(dim, dt=1e-3)
+    o, g = _make(text, reps, (0,) * dim, hi, body_force=lambda p, c: 5.0 if c == 0 else 0.0)
+    _, g64 = _make(text, reps, (0,) * dim, hi, body_force=lambda p, c: 5.0 if c == 0 else 0.0)
+    g.set_control(fgmres_rel=1e-10, a_inv_fp32=1, supg_ilu=ilu)
+    g64.set_control(fgmres_rel=1e-10, supg_ilu=ilu)
+    for k in range(3):
+        o.run_one_step(k == 0)
+        g.run_one_step(k == 0)
+        g64.run_one_step(k == 0)
+    sol = g.get_current_solution()
+    assert _rel(sol[: o.n_u], o.velocity()) < 1e-6 and _rel(sol[o.n_u:], o.pressure()) < 1e-6
+    h32, h64 = g.history(), g64.history()
+    assert [(h["timestep"], h["iteration"]) for h in h32] == [(h[0], h[1]) for h in o.history]
+    assert all(abs(a["gmres_its"] - b["gmres_its"]) <= 1 for a, b in zip(h32, h64))
+
+
 def test_initial_condition_reference_golden(golden_dir):
     """tests/fluid_initial_condition_mpi/fluid_initial_condition_mpi.cpp:31-60"""
     import openifem_b200 as ifem

@@ -181,6 +181,29 @@ def test_inner_tpp_solve_on_fp32_blocks(dim, reps, hi, ilu):
     assert all(abs(a["gmres_its"] - b["gmres_its"]) <= 1 for a, b in zip(h32, h64))
 
 
+@pytest.mark.parametrize("dim,reps,hi", [(2, (6, 5), (1.0, 0.8)), (3, (3, 4, 3), (1.0, 1.2, 0.9))])
+def test_cell_kernel_variants_agree(dim, reps, hi, monkeypatch):
+    """IFEM_SCNS_ASM: 0 = the cell kernel with the reference's divisions by dt / atm / kappa_s, 1 = reciprocals + batched scatter
+    (the 3-D default, profiles/r02_scns_assemble_ncu_summary.md), 2-4 = its register / arithmetic variants: one system to round-off"""
+    import scipy.sparse as sp
+
+    o, g = _make(scns_prm(dim, gravity=[0.3, -9.8, 0.5][:dim], neumann={1: 2.0}), reps, (0,) * dim, hi, body_force=BF, sigma=SIG)
+    rng = np.random.default_rng(2)
+    g.set_vector(g.EVALUATION_POINT, rng.uniform(-1, 1, o.n))
+    g.set_vector(g.PRESENT, rng.uniform(-1, 1, o.n))
+    g.set_vector(g.FSI_ACCELERATION, rng.uniform(-1, 1, o.n))
+    g.set_indicator((rng.uniform(size=o.mesh.n_cells) < 0.4).astype(np.int32))
+    out = {}
+    for v in (0, 1, 2, 3, 4):
+        monkeypatch.setenv("IFEM_SCNS_ASM", str(v))
+        g.assemble(True)
+        out[v] = (g.get_matrix(0), g.get_vector(g.SYSTEM_RHS))
+    A0, b0 = out[0]
+    for v in (1, 2, 3, 4):
+        A, b = out[v]
+        assert sp.linalg.norm(A - A0) <= 1e-14 * sp.linalg.norm(A0) and _rel(b, b0) < 1e-14, v
+
+
 def test_initial_condition_reference_golden(golden_dir):
     """tests/fluid_initial_condition_mpi/fluid_initial_condition_mpi.cpp:31-60"""
     import openifem_b200 as ifem

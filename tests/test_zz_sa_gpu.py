@@ -265,3 +265,30 @@ def test_refine_mesh_carries_the_model():
     fsol = fluid.get_current_solution()
     assert to.present.max() > 0 and _rel(tg.get_vector(tg.PRESENT), to.present) < 1e-6
     assert _rel(fsol[: of.n_u], of.velocity()) < 1e-6 and _rel(fsol[of.n_u:], of.pressure()) < 1e-6
+
+
+def test_no_wall_boundary_and_no_model():
+    """edge cases: without a wall boundary the wall distance is DBL_MAX (:521) - a uniform nu~ at rest is then a steady state of the
+    transport equation; the ifem_turbulence_* entry points fail loudly on a solver that has no model attached"""
+    import openifem_b200 as ifem
+    from oracle import fem, prm, scns
+
+    text = scns_prm(2, mu=1e-3, rho=1.0, dt=1e-2) + SA.replace("= 3\n", "= 0\n", 1).replace("= 0, 2, 3", "= 0").replace("= 1, 0, 0", "= 0")
+    o = scns.SCnsIM(fem.BoxMesh((5, 4), (0.0, 0.0), (1.0, 1.0)), prm.Params(text, is_text=True))
+    to = o.attach_turbulence_model("Spalart-Allmaras")
+    assert not to.sa["bcs"] and to.con.sum() == 0
+    tria = ifem.Triangulation(2)
+    ifem.GridGenerator.subdivided_hyper_rectangle(tria, (5, 4), (0.0, 0.0), (1.0, 1.0), True)
+    g = ifem.Fluid.MPI.SCnsIM(tria, ifem.Parameters.AllParameters(text=text))
+    g.setup()
+    with pytest.raises(ifem.IfemError):
+        ifem._TurbulenceModel(g).get_vector(0)
+    tg = g.attach_turbulence_model("Spalart-Allmaras")
+    assert (tg.get_vector(tg.WALL_DISTANCE) == np.finfo(np.float64).max).all()
+    tg.set_vector(tg.EVALUATION_POINT, tg.get_vector(tg.PRESENT))  # run_one_step starts from evaluation_point = present_solution (:307)
+    tg.assemble(False)
+    assert np.abs(tg.get_vector(tg.SYSTEM_RHS)).max() < 1e-18
+    tg.run_one_step(True)
+    assert np.allclose(tg.get_vector(tg.PRESENT), 3.0 * to.nu_laminar, rtol=1e-14, atol=0)
+    A_ref, _ = to.assemble(False)
+    assert sp.linalg.norm(tg.get_matrix() - A_ref) < 1e-12 * sp.linalg.norm(A_ref)
